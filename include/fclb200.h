@@ -1,0 +1,166 @@
+/* fclb200.h -- C ABI of libfclb200.so, the B200 batched narrowphase engine.
+ *
+ * This is the drop-in boundary.  mind-fcl has no FFI/plugin
+ * seam of its own: its public seam is the C++ template API
+ *     fcl::collide(o1, tf1, o2, tf2, request, result)
+ *         reference include/fcl/narrowphase/collision.h:55-64,
+ *         impl      include/fcl/narrowphase/collision_interface-inl.h:13-44
+ * plus the internal function-pointer table
+ *     detail::CollisionFunctionMatrix<S>::collision_matrix[NODE][NODE]
+ *         reference include/fcl/narrowphase/detail/collision_func_matrix.h:67-78.
+ * Each entry point below replaces a LOOP of those calls over a batch of
+ * independent (geometry pair, pose pair) queries.  The host-side C++ mirror of
+ * the fcl API (include/fcl_b200/fcl.h) and the binding a mind-fcl maintainer
+ * would add sit directly on top of this header.
+ *
+ * Conventions
+ *   - plain C, POD structs, SoA outputs, caller-allocated buffers, int error
+ *     codes (0 = ok), no exceptions, no callbacks.
+ *   - scalar_type: FCLB_F32 or FCLB_F64 -- the scalar S the reference would be
+ *     instantiated with.  All arithmetic is done in S on the device.
+ *   - pose: 12 S = rotation 3x3 row-major, then translation xyz
+ *     (the meaningful part of Eigen::Transform<S,3,Isometry>, common/types.h:91).
+ *   - "_host" entry points take HOST pointers and do H2D + kernels + D2H on the
+ *     engine's streams (pinned buffers from fclb_host_alloc make the copies
+ *     asynchronous);  "_dev" entry points take DEVICE pointers (cudaMalloc'd or
+ *     fclb_dev_alloc'd) and only launch kernels + synchronise.
+ *   - handles are opaque, immutable after creation, usable from any thread.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns FCLB_ERR_NO_DEVICE.
+ */
+#ifndef FCLB200_H_
+#define FCLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCLB_F32 0
+#define FCLB_F64 1
+
+/* error codes */
+#define FCLB_OK 0
+#define FCLB_ERR_NO_DEVICE 1
+#define FCLB_ERR_CUDA 2
+#define FCLB_ERR_BAD_ARG 3
+#define FCLB_ERR_UNSUPPORTED 4
+#define FCLB_ERR_CAPACITY 5
+
+/* shape type codes; the first six equal cvx_collide::GJKShapeType
+ * (reference include/fcl/cvx_collide/gjk_shape.h:12-30). */
+#define FCLB_BOX 0       /* p = side x,y,z            (geometry/shape/box.h)       */
+#define FCLB_SPHERE 1    /* p = radius                (geometry/shape/sphere.h)    */
+#define FCLB_ELLIPSOID 2 /* p = radii x,y,z           (geometry/shape/ellipsoid.h) */
+#define FCLB_CAPSULE 3   /* p = radius, lz            (geometry/shape/capsule.h)   */
+#define FCLB_CONE 4      /* p = radius, lz            (geometry/shape/cone.h)      */
+#define FCLB_CYLINDER 5  /* p = radius, lz            (geometry/shape/cylinder.h)  */
+#define FCLB_CONVEX 6    /* geom = convex handle slot (geometry/shape/convex.h)    */
+
+typedef struct {
+  uint32_t type;  /* FCLB_* */
+  uint32_t geom;  /* FCLB_CONVEX: index returned by fclb_convex_upload */
+  double p[3];    /* parameters, converted to S on upload */
+} fclb_shape;
+
+typedef struct {
+  uint32_t shape1, shape2; /* indices into the shape table */
+} fclb_pair;
+
+/* CollisionRequest<S> by value (reference narrowphase/collision_request.h:51-94)
+ * plus the GJKSolver knobs fcl::collide fixes (gjk_solver-inl.h:1121-1130). */
+#define FCLB_PEN_DISABLED 0
+#define FCLB_PEN_DEFAULT_GJK_EPA 1
+#define FCLB_PEN_DIRECTED 2
+#define FCLB_PEN_INCREMENTAL_MIN 3
+typedef struct {
+  uint32_t max_contacts;     /* num_max_contacts_; 0 => every query returns 0 (collision-inl.h:79-84) */
+  uint32_t penetration_mode; /* FCLB_PEN_* */
+  double dir[3];             /* escape direction for the MPR penetration modes */
+  double binary_tol;         /* GJK/MPR tolerance; <=0 => 1e-6 (collision_request.h:66) */
+  double distance_tol;       /* EPA tolerance;     <=0 => 1e-6 (collision_request.h:67) */
+  uint32_t gjk_max_iter;     /* 0 => 128 */
+  uint32_t epa_max_faces;    /* 0 => 256 */
+  uint32_t epa_max_iter;     /* 0 => 255 */
+  uint32_t flags;            /* reserved, 0 */
+} fclb_request;
+
+typedef uint64_t fclb_handle;
+
+/* ---- engine ------------------------------------------------------------ */
+int fclb_init(int device);             /* bind the calling process to one GPU (one process per GPU) */
+int fclb_device_count(void);           /* 0 when no CUDA device is visible */
+const char* fclb_last_error(void);     /* thread-local message for the last non-zero return */
+const char* fclb_version(void);
+
+/* pinned host / device buffers for the batch arrays */
+int fclb_host_alloc(void** p, size_t bytes);
+int fclb_host_free(void* p);
+int fclb_dev_alloc(void** p, size_t bytes);
+int fclb_dev_free(void* p);
+int fclb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
+int fclb_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
+int fclb_synchronize(void);
+
+/* ---- geometry upload (host pointers; device copies are immutable) -------- */
+/* Convex<S>: vertices (n_verts x 3 doubles) + faces in the reference encoding
+ * (count, v0, v1, ... per face; geometry/shape/convex.h:84-108).  The engine
+ * derives the neighbour CSR, the 6 axis seeds and the interior point exactly as
+ * Convex<S>'s constructor does (convex-inl.h:52-75,153-200,379-407).
+ * *slot is the value to put in fclb_shape.geom. */
+int fclb_convex_upload(const double* verts, int n_verts, const int* faces, int faces_len, int num_faces,
+                       uint32_t* slot);
+/* shape table (replaces the per-call ShapeBase<S> objects) */
+int fclb_shapes_upload(const fclb_shape* shapes, uint32_t n_shapes, fclb_handle* table);
+int fclb_release(fclb_handle h);
+
+/* ---- batched queries ------------------------------------------------------ */
+/* fcl::distance semantics == detail::GJKSolver<S>::shapeDistance
+ * (gjk_solver-inl.h:801-808; closed forms :902-988; generic GJK :762-798):
+ *   ok[q]=1, dist>0, p1/p2 = world-frame witness points   when separated
+ *   ok[q]=0, dist=-1                                       otherwise.
+ * gjk_tol<=0 => constants<S>::gjk_default_tolerance() (eps^(7/8));
+ * gjk_max_iter==0 => 128.  Any of out_* may be NULL. */
+int fclb_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                             size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
+                             void* out_p1, void* out_p2, uint8_t* out_ok);
+int fclb_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                            size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
+                            void* out_p1, void* out_p2, uint8_t* out_ok);
+
+/* fcl::collide semantics for shape-shape pairs
+ * (collision_func_matrix-inl.h:340 ShapeShapeCollide -> shape_pair_intersect-inl.h:49).
+ * out_contacts: max_keep records per query of 9 S = {b1, b2, normal[3], pos[3], depth}
+ * (Contact<S>, narrowphase/contact.h:46-87; b1=b2=-1 for shape pairs);
+ * out_counts[q] = result.numContacts().  out_contacts may be NULL. */
+int fclb_collide_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                            size_t n, int scalar_type, const fclb_request* req, uint32_t max_keep,
+                            void* out_contacts, uint32_t* out_counts);
+int fclb_collide_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                           size_t n, int scalar_type, const fclb_request* req, uint32_t max_keep,
+                           void* out_contacts, uint32_t* out_counts);
+
+/* The cvx_collide path driven directly, as the reference's tests do
+ * (test/cvx_collide/test_epa2_with_gjk2.cpp:76-162): GJK(max_iter, tol) and, on
+ * Intersect, EPA(max_faces, max_iter, tol) on the GJK simplex.
+ * out_gjk: GJK_Status (gjk.h:13-29); out_epa: EPA_Status (epa.h:14-22) or -1;
+ * out_geom: 7 S per query {depth, p0[3], p1[3]} in shape-1's frame. */
+int fclb_gjk_epa_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                            size_t n, int scalar_type, const fclb_request* req, int32_t* out_gjk, int32_t* out_epa,
+                            void* out_geom);
+int fclb_gjk_epa_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                           size_t n, int scalar_type, const fclb_request* req, int32_t* out_gjk, int32_t* out_epa,
+                           void* out_geom);
+
+/* kernel launches issued by this process so far (bench.py's gpu_launches) */
+uint64_t fclb_launch_count(void);
+/* device time (ms, CUDA events on the engine's stream) of the kernels of the
+ * most recent *_dev / *_host call, and of its dominant kernel */
+double fclb_last_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCLB200_H_ */

@@ -1,0 +1,584 @@
+// fclb_engine.cu -- engine state, geometry upload, query bucketing and the C ABI
+// declared in include/fclb200.h.
+//
+// One process binds one GPU (fclb_init).  A batch call
+//   1. (host entry points) stages the batch arrays H2D in chunks on a copy
+//      stream while earlier chunks compute and drain D2H;
+//   2. buckets the queries by (type1,type2) on the device (histogram + scatter),
+//      so every kernel launch sees one pair kind;
+//   3. launches the per-kind kernels (fclb_distance_*.cu, fclb_collide_*.cu).
+// There is no CPU fallback: with no CUDA device every compute entry point
+// returns FCLB_ERR_NO_DEVICE.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "fclb_internal.h"
+#include "fclb_shapes.cuh"
+
+namespace fclb {
+
+thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define FCLB_CUDA(expr)                                                                        \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(FCLB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+struct ConvexHost {
+  // per scalar type device arrays
+  void* d_verts[2] = {nullptr, nullptr};
+  int* d_nbr = nullptr;
+  int n_verts = 0;
+  int walk = 0;
+  int seed[2][6];
+  double interior[2][3];
+};
+
+struct ShapeTable {
+  void* d_shapes[2] = {nullptr, nullptr};  // ShapeD<float>[], ShapeD<double>[]
+  std::vector<fclb_shape> host;
+  uint32_t n = 0;
+  uint64_t convex_epoch = 0;
+};
+
+struct Engine {
+  std::recursive_mutex mu;
+  bool ready = false;
+  int device = -1;
+  int sms = 148;
+  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<ConvexHost> convex;
+  void* d_convex_tab[2] = {nullptr, nullptr};  // ConvexD<S>[]
+  uint64_t convex_epoch = 0;
+  std::map<fclb_handle, ShapeTable*> tables;
+  fclb_handle next_handle = 1;
+  // scratch for bucketing
+  uint32_t* d_perm = nullptr;
+  uint8_t* d_kind = nullptr;
+  size_t scratch_cap = 0;
+  uint32_t* d_hist = nullptr;  // kNumKinds counters + kNumKinds cursors
+  uint32_t* h_hist = nullptr;  // pinned
+  // staging for host entry points
+  void* d_stage = nullptr;
+  size_t stage_cap = 0;
+  std::atomic<uint64_t> launches{0};
+  double last_ms = 0.0;
+};
+static Engine& eng() {
+  static Engine e;
+  return e;
+}
+
+static int ensureInit() {
+  Engine& e = eng();
+  if (e.ready) return FCLB_OK;
+  return fclb_init(-1);
+}
+
+// ---------------------------------------------------------------------------
+// bucketing kernels
+template <typename S>
+__global__ void classifyKernel(const ShapeD<S>* __restrict__ shapes, const fclb_pair* __restrict__ pairs, size_t n,
+                               uint8_t* __restrict__ kind, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kNumKinds];
+  for (int i = threadIdx.x; i < kNumKinds; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (size_t q = blockIdx.x * size_t(blockDim.x) + threadIdx.x; q < n; q += size_t(gridDim.x) * blockDim.x) {
+    const fclb_pair p = pairs[q];
+    const int k = (shapes[p.shape1].type & 7) * kNumTypes + (shapes[p.shape2].type & 7);
+    kind[q] = uint8_t(k);
+    atomicAdd(&sh[k], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNumKinds; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// hist[0..K) counts -> hist[K..2K) exclusive offsets (also used as cursors)
+__global__ void scanKernel(uint32_t* hist) {
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int i = 0; i < kNumKinds; i++) {
+      hist[kNumKinds + i] = acc;
+      acc += hist[i];
+    }
+  }
+}
+
+// Stable within a block-chunk: each block owns a contiguous chunk of queries,
+// reserves space per kind with one atomic per (block, kind), and ranks its
+// queries locally in order.
+__global__ void scatterKernel(const uint8_t* __restrict__ kind, size_t n, size_t chunk, uint32_t* __restrict__ cursors,
+                              uint32_t* __restrict__ perm) {
+  __shared__ uint32_t cnt[kNumKinds];
+  __shared__ uint32_t base[kNumKinds];
+  const size_t b = size_t(blockIdx.x) * chunk;
+  const size_t e = (b + chunk < n) ? (b + chunk) : n;
+  for (int i = threadIdx.x; i < kNumKinds; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  for (size_t q = b + threadIdx.x; q < e; q += blockDim.x) atomicAdd(&cnt[kind[q]], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNumKinds; i += blockDim.x) {
+    base[i] = cnt[i] ? atomicAdd(&cursors[i], cnt[i]) : 0;
+    cnt[i] = 0;
+  }
+  __syncthreads();
+  // placement: tiles of blockDim queries, one shared-memory atomic per
+  // (warp, kind) via match_any aggregation
+  const unsigned lane = threadIdx.x & 31;
+  for (size_t t = b; t < e; t += blockDim.x) {
+    const size_t q = t + threadIdx.x;
+    const int k = (q < e) ? int(kind[q]) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    const unsigned rank_in_warp = __popc(peers & ((1u << lane) - 1));
+    uint32_t start = 0;
+    if (rank_in_warp == 0 && k >= 0) start = atomicAdd(&cnt[k], uint32_t(__popc(peers)));
+    start = __shfl_sync(peers, start, __ffs(peers) - 1);
+    if (k >= 0) perm[base[k] + start + rank_in_warp] = uint32_t(q);
+  }
+}
+
+// ---------------------------------------------------------------------------
+static int uploadConvexTables(Engine& e) {
+  for (int st = 0; st < 2; st++) {
+    if (e.d_convex_tab[st]) {
+      cudaFree(e.d_convex_tab[st]);
+      e.d_convex_tab[st] = nullptr;
+    }
+  }
+  if (e.convex.empty()) return FCLB_OK;
+  {
+    std::vector<ConvexD<float>> tf(e.convex.size());
+    std::vector<ConvexD<double>> td(e.convex.size());
+    for (size_t i = 0; i < e.convex.size(); i++) {
+      const ConvexHost& c = e.convex[i];
+      tf[i].verts = static_cast<const float*>(c.d_verts[0]);
+      td[i].verts = static_cast<const double*>(c.d_verts[1]);
+      tf[i].nbr = td[i].nbr = c.d_nbr;
+      tf[i].n_verts = td[i].n_verts = c.n_verts;
+      tf[i].walk = td[i].walk = c.walk;
+      for (int k = 0; k < 6; k++) {
+        tf[i].seed[k] = c.seed[0][k];
+        td[i].seed[k] = c.seed[1][k];
+      }
+      for (int k = 0; k < 3; k++) {
+        tf[i].interior[k] = float(c.interior[0][k]);
+        td[i].interior[k] = c.interior[1][k];
+      }
+    }
+    FCLB_CUDA(cudaMalloc(&e.d_convex_tab[0], tf.size() * sizeof(ConvexD<float>)));
+    FCLB_CUDA(cudaMalloc(&e.d_convex_tab[1], td.size() * sizeof(ConvexD<double>)));
+    FCLB_CUDA(cudaMemcpy(e.d_convex_tab[0], tf.data(), tf.size() * sizeof(ConvexD<float>), cudaMemcpyHostToDevice));
+    FCLB_CUDA(cudaMemcpy(e.d_convex_tab[1], td.data(), td.size() * sizeof(ConvexD<double>), cudaMemcpyHostToDevice));
+  }
+  return FCLB_OK;
+}
+
+template <typename S>
+static void convexDerive(const std::vector<double>& verts_d, int n, int (&seed)[6], double (&interior)[3],
+                         std::vector<S>& verts_s) {
+  verts_s.resize(size_t(3) * n);
+  for (size_t i = 0; i < verts_s.size(); i++) verts_s[i] = S(verts_d[i]);
+  // interior point: running sum in S, times (S)(1.0/n)   (convex-inl.h:64-71)
+  S sum[3] = {S(0), S(0), S(0)};
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < 3; k++) sum[k] += verts_s[3 * i + k];
+  const S inv = S(1.0 / double(n));
+  for (int k = 0; k < 3; k++) interior[k] = double(sum[k] * inv);
+  // six axis seeds by the naive scan (convex-inl.h:153-200): dot with a unit
+  // axis picks one coordinate; first strict maximum wins.
+  for (int k = 0; k < 6; k++) {
+    const int axis = k / 2;
+    const S sgn = (k & 1) ? S(-1) : S(1);
+    int best = 0;
+    S best_v = sgn * verts_s[axis];
+    for (int i = 1; i < n; i++) {
+      const S v = sgn * verts_s[3 * i + axis];
+      if (v > best_v) {
+        best = i;
+        best_v = v;
+      }
+    }
+    seed[k] = best;
+  }
+}
+
+template <typename S>
+static int buildShapeTable(Engine& e, ShapeTable* t, int st) {
+  std::vector<ShapeD<S>> h(t->n);
+  for (uint32_t i = 0; i < t->n; i++) {
+    const fclb_shape& s = t->host[i];
+    if (s.type > FCLB_CONVEX) return fail(FCLB_ERR_BAD_ARG, "fclb_shapes_upload: unknown shape type");
+    if (s.type == FCLB_CONVEX && s.geom >= e.convex.size())
+      return fail(FCLB_ERR_BAD_ARG, "fclb_shapes_upload: convex slot out of range");
+    h[i].type = int(s.type);
+    h[i].geom = int(s.geom);
+    for (int k = 0; k < 3; k++) h[i].p[k] = S(s.p[k]);
+  }
+  FCLB_CUDA(cudaMalloc(&t->d_shapes[st], std::max<size_t>(1, h.size()) * sizeof(ShapeD<S>)));
+  FCLB_CUDA(cudaMemcpy(t->d_shapes[st], h.data(), h.size() * sizeof(ShapeD<S>), cudaMemcpyHostToDevice));
+  return FCLB_OK;
+}
+
+static int ensureScratch(Engine& e, size_t n) {
+  if (n <= e.scratch_cap) return FCLB_OK;
+  if (e.d_perm) cudaFree(e.d_perm);
+  if (e.d_kind) cudaFree(e.d_kind);
+  e.d_perm = nullptr;
+  e.d_kind = nullptr;
+  e.scratch_cap = 0;
+  FCLB_CUDA(cudaMalloc(&e.d_perm, n * sizeof(uint32_t)));
+  FCLB_CUDA(cudaMalloc(&e.d_kind, n));
+  e.scratch_cap = n;
+  return FCLB_OK;
+}
+
+// Bucket a device-resident batch.  On return counts/offsets hold the per-kind
+// histogram; *uniform_kind >= 0 when every query has the same kind (then no
+// permutation is needed and perm stays unused).
+template <typename S>
+static int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs, size_t n, uint32_t* counts,
+                       uint32_t* offsets, int* uniform_kind) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  int rc = ensureScratch(e, n);
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemsetAsync(e.d_hist, 0, 2 * kNumKinds * sizeof(uint32_t), e.compute));
+  const int block = 256;
+  const int grid = int(std::min<size_t>((n + block - 1) / block, size_t(e.sms) * 8));
+  classifyKernel<S><<<grid, block, 0, e.compute>>>(static_cast<const ShapeD<S>*>(t->d_shapes[st]), d_pairs, n, e.d_kind,
+                                                   e.d_hist);
+  scanKernel<<<1, 32, 0, e.compute>>>(e.d_hist);
+  e.launches += 2;
+  FCLB_CUDA(cudaMemcpyAsync(e.h_hist, e.d_hist, 2 * kNumKinds * sizeof(uint32_t), cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  *uniform_kind = -1;
+  for (int k = 0; k < kNumKinds; k++) {
+    counts[k] = e.h_hist[k];
+    offsets[k] = e.h_hist[kNumKinds + k];
+    if (counts[k] == n) *uniform_kind = k;
+  }
+  if (*uniform_kind < 0) {
+    const size_t chunk = 4096;
+    const int sgrid = int((n + chunk - 1) / chunk);
+    scatterKernel<<<sgrid, 256, 0, e.compute>>>(e.d_kind, n, chunk, e.d_hist + kNumKinds, e.d_perm);
+    e.launches += 1;
+    FCLB_CUDA(cudaGetLastError());
+  }
+  return FCLB_OK;
+}
+
+static SolverParams distanceParams(int scalar_type, double gjk_tol, uint32_t gjk_max_iter) {
+  SolverParams sp{};
+  // constants<S>::eps_78(): pow(eps, 7/8) evaluated in double, rounded to S
+  const double eps = scalar_type == FCLB_F32 ? double(1.1920928955078125e-07f) : 2.220446049250313e-16;
+  const double e78 = std::pow(eps, 7. / 8.);
+  sp.eps78 = scalar_type == FCLB_F32 ? double(float(e78)) : e78;
+  sp.gjk_tol = gjk_tol > 0 ? gjk_tol : sp.eps78;
+  sp.gjk_max_iter = gjk_max_iter ? int(gjk_max_iter) : 128;
+  sp.epa_tol = sp.eps78;
+  sp.epa_max_faces = 256;
+  sp.epa_max_iter = 255;
+  return sp;
+}
+
+template <typename S>
+static int distanceDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const void* poses1, const void* poses2, size_t n,
+                       const SolverParams& sp, const DistanceOut& out) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  uint32_t counts[kNumKinds], offsets[kNumKinds];
+  int uniform = -1;
+  int rc = bucketBatch<S>(e, t, pairs, n, counts, offsets, &uniform);
+  if (rc) return rc;
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  int launches = 0;
+  for (int k = 0; k < kNumKinds; k++) {
+    if (!counts[k]) continue;
+    BatchView b{};
+    b.shapes = t->d_shapes[st];
+    b.convex = e.d_convex_tab[st];
+    b.pairs = pairs;
+    b.poses1 = poses1;
+    b.poses2 = poses2;
+    b.perm = (uniform >= 0) ? nullptr : e.d_perm;
+    b.begin = (uniform >= 0) ? 0 : offsets[k];
+    b.count = counts[k];
+    b.type1 = k / kNumTypes;
+    b.type2 = k % kNumTypes;
+    FCLB_CUDA(launchDistance<S>(b, sp, out, e.compute, &launches));
+  }
+  e.launches += uint64_t(launches);
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.last_ms = ms;
+  return FCLB_OK;
+}
+
+static ShapeTable* findTable(Engine& e, fclb_handle h) {
+  auto it = e.tables.find(h);
+  return it == e.tables.end() ? nullptr : it->second;
+}
+
+static int ensureStage(Engine& e, size_t bytes) {
+  if (bytes <= e.stage_cap) return FCLB_OK;
+  if (e.d_stage) cudaFree(e.d_stage);
+  e.d_stage = nullptr;
+  e.stage_cap = 0;
+  FCLB_CUDA(cudaMalloc(&e.d_stage, bytes));
+  e.stage_cap = bytes;
+  return FCLB_OK;
+}
+
+static size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace fclb
+
+using namespace fclb;
+
+extern "C" {
+
+const char* fclb_last_error(void) { return g_err.c_str(); }
+const char* fclb_version(void) { return "fclb200 0.1 (sm_100a)"; }
+
+int fclb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int fclb_init(int device) {
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (e.ready && (device < 0 || device == e.device)) return FCLB_OK;
+  if (e.ready) return fail(FCLB_ERR_BAD_ARG, "fclb_init: engine already bound to another device (one process per GPU)");
+  const int n = fclb_device_count();
+  if (n <= 0) return fail(FCLB_ERR_NO_DEVICE, "no CUDA device visible: libfclb200 has no CPU fallback");
+  if (device < 0) device = 0;
+  if (device >= n) return fail(FCLB_ERR_BAD_ARG, "fclb_init: device index out of range");
+  FCLB_CUDA(cudaSetDevice(device));
+  e.device = device;
+  FCLB_CUDA(cudaDeviceGetAttribute(&e.sms, cudaDevAttrMultiProcessorCount, device));
+  FCLB_CUDA(cudaStreamCreateWithFlags(&e.compute, cudaStreamNonBlocking));
+  FCLB_CUDA(cudaStreamCreateWithFlags(&e.copy_in, cudaStreamNonBlocking));
+  FCLB_CUDA(cudaStreamCreateWithFlags(&e.copy_out, cudaStreamNonBlocking));
+  FCLB_CUDA(cudaEventCreate(&e.ev0));
+  FCLB_CUDA(cudaEventCreate(&e.ev1));
+  FCLB_CUDA(cudaMalloc(&e.d_hist, 2 * kNumKinds * sizeof(uint32_t)));
+  FCLB_CUDA(cudaMallocHost(&e.h_hist, 2 * kNumKinds * sizeof(uint32_t)));
+  e.ready = true;
+  return FCLB_OK;
+}
+
+int fclb_host_alloc(void** p, size_t bytes) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  FCLB_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+  return FCLB_OK;
+}
+int fclb_host_free(void* p) {
+  FCLB_CUDA(cudaFreeHost(p));
+  return FCLB_OK;
+}
+int fclb_dev_alloc(void** p, size_t bytes) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  FCLB_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+  return FCLB_OK;
+}
+int fclb_dev_free(void* p) {
+  FCLB_CUDA(cudaFree(p));
+  return FCLB_OK;
+}
+int fclb_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return FCLB_OK;
+}
+int fclb_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return FCLB_OK;
+}
+int fclb_synchronize(void) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  FCLB_CUDA(cudaDeviceSynchronize());
+  return FCLB_OK;
+}
+
+int fclb_convex_upload(const double* verts, int n_verts, const int* faces, int faces_len, int num_faces,
+                       uint32_t* slot) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (!verts || !faces || n_verts <= 0 || num_faces <= 0 || !slot)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_convex_upload: null or empty input");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  ConvexHost c;
+  c.n_verts = n_verts;
+  // neighbour CSR (convex-inl.h:379-407): std::set => ascending, de-duplicated
+  std::vector<std::set<int>> nb(n_verts);
+  std::map<std::pair<int, int>, int> edge_faces;
+  int fi = 0;
+  for (int f = 0; f < num_faces; f++) {
+    if (fi >= faces_len) return fail(FCLB_ERR_BAD_ARG, "fclb_convex_upload: faces array too short");
+    const int cnt = faces[fi];
+    if (cnt < 1 || fi + cnt > faces_len - 1) return fail(FCLB_ERR_BAD_ARG, "fclb_convex_upload: faces array too short");
+    int prev = faces[fi + cnt];
+    for (int i = fi + 1; i <= fi + cnt; i++) {
+      const int v = faces[i];
+      if (v < 0 || v >= n_verts || prev < 0 || prev >= n_verts)
+        return fail(FCLB_ERR_BAD_ARG, "fclb_convex_upload: vertex index out of range");
+      nb[v].insert(prev);
+      nb[prev].insert(v);
+      edge_faces[std::make_pair(std::min(v, prev), std::max(v, prev))] += 1;
+      prev = v;
+    }
+    fi += cnt + 1;
+  }
+  std::vector<int> csr(n_verts);
+  bool all_connected = true;
+  for (int v = 0; v < n_verts; v++) {
+    csr[v] = int(csr.size());
+    csr.push_back(int(nb[v].size()));
+    csr.insert(csr.end(), nb[v].begin(), nb[v].end());
+    if (nb[v].empty()) all_connected = false;
+  }
+  // ValidateTopology (convex-inl.h:293-368): walk only on a watertight,
+  // fully connected mesh with more than 32 vertices (convex.h:259).
+  bool watertight = true;
+  for (const auto& kv : edge_faces)
+    if (kv.second != 2) watertight = false;
+  c.walk = (n_verts > 32 && watertight && all_connected) ? 1 : 0;
+  std::vector<double> vd(verts, verts + size_t(3) * n_verts);
+  std::vector<float> vf;
+  std::vector<double> vdd;
+  convexDerive<float>(vd, n_verts, c.seed[0], c.interior[0], vf);
+  convexDerive<double>(vd, n_verts, c.seed[1], c.interior[1], vdd);
+  FCLB_CUDA(cudaMalloc(&c.d_verts[0], vf.size() * sizeof(float)));
+  FCLB_CUDA(cudaMalloc(&c.d_verts[1], vdd.size() * sizeof(double)));
+  FCLB_CUDA(cudaMalloc(&c.d_nbr, csr.size() * sizeof(int)));
+  FCLB_CUDA(cudaMemcpy(c.d_verts[0], vf.data(), vf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  FCLB_CUDA(cudaMemcpy(c.d_verts[1], vdd.data(), vdd.size() * sizeof(double), cudaMemcpyHostToDevice));
+  FCLB_CUDA(cudaMemcpy(c.d_nbr, csr.data(), csr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  e.convex.push_back(c);
+  e.convex_epoch++;
+  *slot = uint32_t(e.convex.size() - 1);
+  return uploadConvexTables(e);
+}
+
+int fclb_shapes_upload(const fclb_shape* shapes, uint32_t n_shapes, fclb_handle* table) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (!shapes || !table || n_shapes == 0) return fail(FCLB_ERR_BAD_ARG, "fclb_shapes_upload: null or empty input");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  ShapeTable* t = new ShapeTable();
+  t->host.assign(shapes, shapes + n_shapes);
+  t->n = n_shapes;
+  rc = buildShapeTable<float>(e, t, 0);
+  if (!rc) rc = buildShapeTable<double>(e, t, 1);
+  if (rc) {
+    delete t;
+    return rc;
+  }
+  const fclb_handle h = e.next_handle++;
+  e.tables[h] = t;
+  *table = h;
+  return FCLB_OK;
+}
+
+int fclb_release(fclb_handle h) {
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = e.tables.find(h);
+  if (it == e.tables.end()) return fail(FCLB_ERR_BAD_ARG, "fclb_release: unknown handle");
+  for (int st = 0; st < 2; st++)
+    if (it->second->d_shapes[st]) cudaFree(it->second->d_shapes[st]);
+  delete it->second;
+  e.tables.erase(it);
+  return FCLB_OK;
+}
+
+int fclb_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                            size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
+                            void* out_p1, void* out_p2, uint8_t* out_ok) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  ShapeTable* t = findTable(e, shapes);
+  if (!t) return fail(FCLB_ERR_BAD_ARG, "fclb_distance_batch: unknown shape table handle");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (n > 0xffffffffull) return fail(FCLB_ERR_CAPACITY, "batch larger than 2^32-1 queries: split it");
+  if (!pairs || !poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "fclb_distance_batch: null input array");
+  const SolverParams sp = distanceParams(scalar_type, gjk_tol, gjk_max_iter);
+  DistanceOut out{out_dist, out_p1, out_p2, out_ok};
+  if (scalar_type == FCLB_F32) return distanceDev<float>(e, t, pairs, poses1, poses2, n, sp, out);
+  return distanceDev<double>(e, t, pairs, poses1, poses2, n, sp, out);
+}
+
+int fclb_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                             size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
+                             void* out_p1, void* out_p2, uint8_t* out_ok) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!pairs || !poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "fclb_distance_batch: null input array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> batch_lk(e.mu);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  // device layout of the staging arena
+  const size_t o_pairs = 0;
+  const size_t o_p1 = alignUp(o_pairs + n * sizeof(fclb_pair), 256);
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_dist = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_w1 = alignUp(o_dist + n * ss, 256);
+  const size_t o_w2 = alignUp(o_w1 + n * 3 * ss, 256);
+  const size_t o_ok = alignUp(o_w2 + n * 3 * ss, 256);
+  const size_t total = alignUp(o_ok + n, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_pairs, pairs, n * sizeof(fclb_pair), cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  rc = fclb_distance_batch_dev(shapes, reinterpret_cast<const fclb_pair*>(base + o_pairs), base + o_p1, base + o_p2, n,
+                               scalar_type, gjk_tol, gjk_max_iter, out_dist ? base + o_dist : nullptr,
+                               out_p1 ? base + o_w1 : nullptr, out_p2 ? base + o_w2 : nullptr,
+                               out_ok ? reinterpret_cast<uint8_t*>(base + o_ok) : nullptr);
+  if (rc) return rc;
+  if (out_dist) FCLB_CUDA(cudaMemcpyAsync(out_dist, base + o_dist, n * ss, cudaMemcpyDeviceToHost, e.compute));
+  if (out_p1) FCLB_CUDA(cudaMemcpyAsync(out_p1, base + o_w1, n * 3 * ss, cudaMemcpyDeviceToHost, e.compute));
+  if (out_p2) FCLB_CUDA(cudaMemcpyAsync(out_p2, base + o_w2, n * 3 * ss, cudaMemcpyDeviceToHost, e.compute));
+  if (out_ok) FCLB_CUDA(cudaMemcpyAsync(out_ok, base + o_ok, n, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+uint64_t fclb_launch_count(void) { return eng().launches.load(); }
+double fclb_last_kernel_ms(void) { return eng().last_ms; }
+
+}  // extern "C"

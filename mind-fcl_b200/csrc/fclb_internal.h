@@ -1,0 +1,50 @@
+// fclb_internal.h -- glue between the C ABI (fclb_engine.cu) and the kernel
+// translation units.  Not part of the public interface.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/fclb200.h"
+
+namespace fclb {
+
+constexpr int kNumTypes = 8;                      // ShapeType codes 0..7
+constexpr int kNumKinds = kNumTypes * kNumTypes;  // (type1,type2) buckets
+constexpr int kBlock = 128;                       // threads per CTA for per-query kernels
+
+// One bucket of a batch: queries perm[begin .. begin+count) all have the same
+// (type1,type2).  perm == nullptr means the identity permutation.
+struct BatchView {
+  const void* shapes;   // ShapeD<S>[]
+  const void* convex;   // ConvexD<S>[]
+  const fclb_pair* pairs;
+  const void* poses1;
+  const void* poses2;
+  const uint32_t* perm;
+  size_t begin, count;
+  int type1, type2;
+};
+
+struct DistanceOut {
+  void* dist;
+  void* p1;
+  void* p2;
+  uint8_t* ok;
+};
+
+struct SolverParams {
+  double gjk_tol;
+  int gjk_max_iter;
+  double epa_tol;
+  int epa_max_faces;
+  int epa_max_iter;
+  double eps78;  // constants<S>::eps_78()
+};
+
+// implemented in fclb_distance_f32.cu / fclb_distance_f64.cu
+template <typename S>
+cudaError_t launchDistance(const BatchView& b, const SolverParams& sp, const DistanceOut& out, cudaStream_t st,
+                           int* n_launches);
+
+}  // namespace fclb

@@ -1,0 +1,227 @@
+"""ctypes binding of libfclb200.so (include/fclb200.h) used by tests/ and bench.py.
+
+This is host plumbing only: it loads the in-tree shared library, declares the
+C ABI, and moves numpy / torch buffers across it.  There is no Python compute
+path and no CPU fallback: if the library is missing or no GPU is visible the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfclb200.so")
+
+F32, F64 = 0, 1
+BOX, SPHERE, ELLIPSOID, CAPSULE, CONE, CYLINDER, CONVEX = range(7)
+PEN_DISABLED, PEN_DEFAULT_GJK_EPA, PEN_DIRECTED, PEN_INCREMENTAL_MIN = range(4)
+
+# every symbol include/fclb200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "fclb_init", "fclb_device_count", "fclb_last_error", "fclb_version",
+    "fclb_host_alloc", "fclb_host_free", "fclb_dev_alloc", "fclb_dev_free",
+    "fclb_memcpy_h2d", "fclb_memcpy_d2h", "fclb_synchronize",
+    "fclb_convex_upload", "fclb_shapes_upload", "fclb_release",
+    "fclb_distance_batch_host", "fclb_distance_batch_dev",
+    "fclb_collide_batch_host", "fclb_collide_batch_dev",
+    "fclb_gjk_epa_batch_host", "fclb_gjk_epa_batch_dev",
+    "fclb_launch_count", "fclb_last_kernel_ms",
+]
+
+
+class Shape(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("geom", C.c_uint32), ("p", C.c_double * 3)]
+
+
+class Request(C.Structure):
+    _fields_ = [
+        ("max_contacts", C.c_uint32), ("penetration_mode", C.c_uint32), ("dir", C.c_double * 3),
+        ("binary_tol", C.c_double), ("distance_tol", C.c_double),
+        ("gjk_max_iter", C.c_uint32), ("epa_max_faces", C.c_uint32), ("epa_max_iter", C.c_uint32),
+        ("flags", C.c_uint32),
+    ]
+
+
+def make_request(max_contacts=1, penetration_mode=PEN_DISABLED, direction=(0.0, 0.0, 0.0), binary_tol=0.0,
+                 distance_tol=0.0, gjk_max_iter=0, epa_max_faces=0, epa_max_iter=0) -> Request:
+    r = Request()
+    r.max_contacts = max_contacts
+    r.penetration_mode = penetration_mode
+    r.dir[:] = direction
+    r.binary_tol = binary_tol
+    r.distance_tol = distance_tol
+    r.gjk_max_iter = gjk_max_iter
+    r.epa_max_faces = epa_max_faces
+    r.epa_max_iter = epa_max_iter
+    r.flags = 0
+    return r
+
+
+def shape_array(shapes) -> C.Array:
+    """shapes: iterable of (type, geom, (p0,p1,p2))."""
+    arr = (Shape * len(shapes))()
+    for i, (t, g, p) in enumerate(shapes):
+        arr[i].type = t
+        arr[i].geom = g
+        p = list(p) + [0.0] * (3 - len(p))
+        arr[i].p[:] = p
+    return arr
+
+
+class FclbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FclbError(f"{LIB_PATH} is missing: run `make -C mind-fcl_b200/csrc` (or __graft_entry__.build())")
+    lib = C.CDLL(LIB_PATH)
+    lib.fclb_last_error.restype = C.c_char_p
+    lib.fclb_version.restype = C.c_char_p
+    lib.fclb_launch_count.restype = C.c_uint64
+    lib.fclb_last_kernel_ms.restype = C.c_double
+    vp, sz, u32 = C.c_void_p, C.c_size_t, C.c_uint32
+    lib.fclb_init.argtypes = [C.c_int]
+    lib.fclb_host_alloc.argtypes = [C.POINTER(vp), sz]
+    lib.fclb_host_free.argtypes = [vp]
+    lib.fclb_dev_alloc.argtypes = [C.POINTER(vp), sz]
+    lib.fclb_dev_free.argtypes = [vp]
+    lib.fclb_memcpy_h2d.argtypes = [vp, vp, sz]
+    lib.fclb_memcpy_d2h.argtypes = [vp, vp, sz]
+    lib.fclb_convex_upload.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(u32)]
+    lib.fclb_shapes_upload.argtypes = [vp, u32, C.POINTER(C.c_uint64)]
+    lib.fclb_release.argtypes = [C.c_uint64]
+    dist_args = [C.c_uint64, vp, vp, vp, sz, C.c_int, C.c_double, u32, vp, vp, vp, vp]
+    lib.fclb_distance_batch_host.argtypes = dist_args
+    lib.fclb_distance_batch_dev.argtypes = dist_args
+    col_args = [C.c_uint64, vp, vp, vp, sz, C.c_int, vp, u32, vp, vp]
+    ge_args = [C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp, vp]
+    for name, args in (("fclb_collide_batch_host", col_args), ("fclb_collide_batch_dev", col_args),
+                       ("fclb_gjk_epa_batch_host", ge_args), ("fclb_gjk_epa_batch_dev", ge_args)):
+        if hasattr(lib, name):
+            getattr(lib, name).argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise FclbError(f"fclb error {rc}: {load().fclb_last_error().decode()}")
+
+
+def _ptr(a):
+    """numpy array / torch tensor / int / None -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    return C.cast(a, C.c_void_p)
+
+
+def np_dtype(scalar_type):
+    return np.float32 if scalar_type == F32 else np.float64
+
+
+def init(device: int = 0) -> None:
+    check(load().fclb_init(device))
+
+
+def convex_upload(verts: np.ndarray, faces: np.ndarray, num_faces: int) -> int:
+    verts = np.ascontiguousarray(verts, dtype=np.float64)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    slot = C.c_uint32()
+    check(load().fclb_convex_upload(_ptr(verts), verts.shape[0], _ptr(faces), faces.size, num_faces, C.byref(slot)))
+    return slot.value
+
+
+def shapes_upload(shapes) -> int:
+    arr = shape_array(shapes)
+    h = C.c_uint64()
+    check(load().fclb_shapes_upload(C.cast(arr, C.c_void_p), len(shapes), C.byref(h)))
+    return h.value
+
+
+def release(h: int) -> None:
+    check(load().fclb_release(h))
+
+
+@dataclass
+class DistanceResult:
+    dist: np.ndarray
+    p1: np.ndarray
+    p2: np.ndarray
+    ok: np.ndarray
+
+
+def distance_batch_host(table, pairs, poses1, poses2, scalar_type, gjk_tol=0.0, gjk_max_iter=0, out=None):
+    """Host-buffer call (numpy or pinned torch tensors)."""
+    n = len(pairs)
+    dt = np_dtype(scalar_type)
+    if out is None:
+        out = DistanceResult(np.empty(n, dt), np.empty((n, 3), dt), np.empty((n, 3), dt), np.empty(n, np.uint8))
+    check(load().fclb_distance_batch_host(table, _ptr(pairs), _ptr(poses1), _ptr(poses2), n, scalar_type, gjk_tol,
+                                          gjk_max_iter, _ptr(out.dist), _ptr(out.p1), _ptr(out.p2), _ptr(out.ok)))
+    return out
+
+
+def distance_batch_dev(table, pairs, poses1, poses2, n, scalar_type, dist, p1, p2, ok, gjk_tol=0.0, gjk_max_iter=0):
+    """Device-buffer call: every array argument is a CUDA tensor or raw device pointer."""
+    check(load().fclb_distance_batch_dev(table, _ptr(pairs), _ptr(poses1), _ptr(poses2), n, scalar_type, gjk_tol,
+                                         gjk_max_iter, _ptr(dist), _ptr(p1), _ptr(p2), _ptr(ok)))
+
+
+def collide_batch_host(table, pairs, poses1, poses2, scalar_type, request: Request, max_keep=1, want_contacts=True):
+    n = len(pairs)
+    dt = np_dtype(scalar_type)
+    contacts = np.zeros((n, max_keep, 9), dt) if want_contacts else None
+    counts = np.zeros(n, np.uint32)
+    check(load().fclb_collide_batch_host(table, _ptr(pairs), _ptr(poses1), _ptr(poses2), n, scalar_type,
+                                         C.cast(C.pointer(request), C.c_void_p), max_keep, _ptr(contacts),
+                                         _ptr(counts)))
+    return counts, contacts
+
+
+def collide_batch_dev(table, pairs, poses1, poses2, n, scalar_type, request: Request, max_keep, contacts, counts):
+    check(load().fclb_collide_batch_dev(table, _ptr(pairs), _ptr(poses1), _ptr(poses2), n, scalar_type,
+                                        C.cast(C.pointer(request), C.c_void_p), max_keep, _ptr(contacts),
+                                        _ptr(counts)))
+
+
+def gjk_epa_batch_host(table, pairs, poses1, poses2, scalar_type, request: Request):
+    n = len(pairs)
+    dt = np_dtype(scalar_type)
+    gjk = np.zeros(n, np.int32)
+    epa = np.zeros(n, np.int32)
+    geom = np.zeros((n, 7), dt)
+    check(load().fclb_gjk_epa_batch_host(table, _ptr(pairs), _ptr(poses1), _ptr(poses2), n, scalar_type,
+                                         C.cast(C.pointer(request), C.c_void_p), _ptr(gjk), _ptr(epa), _ptr(geom)))
+    return gjk, epa, geom
+
+
+def gjk_epa_batch_dev(table, pairs, poses1, poses2, n, scalar_type, request: Request, gjk, epa, geom):
+    check(load().fclb_gjk_epa_batch_dev(table, _ptr(pairs), _ptr(poses1), _ptr(poses2), n, scalar_type,
+                                        C.cast(C.pointer(request), C.c_void_p), _ptr(gjk), _ptr(epa), _ptr(geom)))
+
+
+def launch_count() -> int:
+    return int(load().fclb_launch_count())
+
+
+def last_kernel_ms() -> float:
+    return float(load().fclb_last_kernel_ms())

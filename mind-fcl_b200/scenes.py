@@ -1,0 +1,149 @@
+"""Seeded synthetic workloads for the configs of BASELINE.json / SURVEY.md 8(d).
+
+Poses follow the reference's test helper semantics (test/test_fcl_utility.h:346-411:
+uniform translation in a box + three uniform Euler angles through eulerToMatrix),
+but with an explicit numpy PCG64 seed instead of an unseeded rand(), computed in
+float64 and then rounded ONCE to the scalar type S.  The rounded arrays are the
+shared input of the CUDA path, the oracle port and the reference oracle.
+Layout: pose = 12 S, rotation row-major then translation.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BOX, SPHERE, ELLIPSOID, CAPSULE, CONE, CYLINDER, CONVEX = range(7)
+PAIR_DTYPE = np.dtype([("shape1", np.uint32), ("shape2", np.uint32)])
+
+
+def euler_to_matrix(a, b, c):
+    """Vectorised eulerToMatrix (test/test_fcl_utility.h:346-357)."""
+    c1, c2, c3 = np.cos(a), np.cos(b), np.cos(c)
+    s1, s2, s3 = np.sin(a), np.sin(b), np.sin(c)
+    R = np.empty(a.shape + (3, 3), np.float64)
+    R[..., 0, 0] = c1 * c2
+    R[..., 0, 1] = -c2 * s1
+    R[..., 0, 2] = s2
+    R[..., 1, 0] = c3 * s1 + c1 * s2 * s3
+    R[..., 1, 1] = c1 * c3 - s1 * s2 * s3
+    R[..., 1, 2] = -c2 * s3
+    R[..., 2, 0] = s1 * s3 - c1 * c3 * s2
+    R[..., 2, 1] = c3 * s1 * s2 + c1 * s3
+    R[..., 2, 2] = c2 * c3
+    return R
+
+
+def random_poses(rng: np.random.Generator, n: int, extent: float, dtype) -> np.ndarray:
+    """n poses, translation uniform in [-extent, extent]^3, Euler angles in [0, 2pi)."""
+    t = rng.uniform(-extent, extent, size=(n, 3))
+    ang = rng.uniform(0.0, 2.0 * np.pi, size=(n, 3))
+    R = euler_to_matrix(ang[:, 0], ang[:, 1], ang[:, 2])
+    out = np.empty((n, 12), np.float64)
+    out[:, :9] = R.reshape(n, 9)
+    out[:, 9:] = t
+    return np.ascontiguousarray(out.astype(dtype))
+
+
+def make_pairs(s1, s2) -> np.ndarray:
+    p = np.empty(len(s1), PAIR_DTYPE)
+    p["shape1"] = s1
+    p["shape2"] = s2
+    return p
+
+
+def config_c2(n: int, dtype, seed: int = 2001):
+    """C2: sphere / capsule / cylinder (round-robin) vs box, distance queries.
+
+    Sphere(0.05), Capsule(0.05, 0.2), Cylinder(0.05, 0.2) vs Box(0.2,0.2,0.2), poses
+    uniform in [-0.5,0.5]^3."""
+    shapes = [(SPHERE, 0, (0.05,)), (CAPSULE, 0, (0.05, 0.2)), (CYLINDER, 0, (0.05, 0.2)), (BOX, 0, (0.2, 0.2, 0.2))]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    poses1 = random_poses(rng, n, 0.5, dtype)
+    poses2 = random_poses(rng, n, 0.5, dtype)
+    s1 = (np.arange(n) % 3).astype(np.uint32)
+    s2 = np.full(n, 3, np.uint32)
+    return shapes, make_pairs(s1, s2), poses1, poses2
+
+
+def config_c1_boxes(n: int, dtype, seed: int = 1001):
+    """C1: Box(2,1,0.5) vs Box(1,1,1), both poses uniform in [-2,2]^3
+    (matches test/cvx_collide/test_epa2_with_gjk2.cpp:76-80)."""
+    shapes = [(BOX, 0, (2.0, 1.0, 0.5)), (BOX, 0, (1.0, 1.0, 1.0))]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    poses1 = random_poses(rng, n, 2.0, dtype)
+    poses2 = random_poses(rng, n, 2.0, dtype)
+    return shapes, make_pairs(np.zeros(n, np.uint32), np.ones(n, np.uint32)), poses1, poses2
+
+
+def ellipsoid_mesh(rx, ry, rz, n_lat=8, n_lon=8):
+    """Closed triangle mesh of an ellipsoid: 2 poles + (n_lat-1) rings of n_lon
+    vertices => 58 vertices / 112 triangles for 8x8, the size of the reference's
+    test convex (test/create_primitive_mesh-inl.h:148-182).  Returns
+    (verts[n,3], faces in the reference encoding, num_faces)."""
+    verts = [(0.0, 0.0, rz)]
+    for i in range(1, n_lat):
+        th = np.pi * i / n_lat
+        for j in range(n_lon):
+            ph = 2 * np.pi * j / n_lon
+            verts.append((rx * np.sin(th) * np.cos(ph), ry * np.sin(th) * np.sin(ph), rz * np.cos(th)))
+    verts.append((0.0, 0.0, -rz))
+    faces = []
+
+    def ring(i, j):
+        return 1 + (i - 1) * n_lon + (j % n_lon)
+
+    for j in range(n_lon):
+        faces.append((0, ring(1, j), ring(1, j + 1)))
+    for i in range(1, n_lat - 1):
+        for j in range(n_lon):
+            a, b, c, d = ring(i, j), ring(i + 1, j), ring(i + 1, j + 1), ring(i, j + 1)
+            faces.append((a, b, c))
+            faces.append((a, c, d))
+    south = len(verts) - 1
+    for j in range(n_lon):
+        faces.append((south, ring(n_lat - 1, j + 1), ring(n_lat - 1, j)))
+    enc = []
+    for f in faces:
+        enc.extend((3,) + f)
+    return np.asarray(verts, np.float64), np.asarray(enc, np.int32), len(faces)
+
+
+def random_hull16(seed: int = 7, scale=(0.25, 0.2, 0.3)):
+    """A 16-vertex convex polytope: two twisted octagonal rings (all 16 points are
+    hull vertices by construction), triangulated.  Exercises the <=32-vertex
+    linear-scan support path (convex-inl.h:133-150)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    m = 8
+    verts = []
+    for ring_i, (z, r) in enumerate(((0.6, 0.8), (-0.6, 1.0))):
+        for j in range(m):
+            ph = 2 * np.pi * (j + 0.5 * ring_i) / m
+            rr = r * (1.0 + 0.02 * rng.uniform(-1, 1))
+            verts.append((scale[0] * rr * np.cos(ph), scale[1] * rr * np.sin(ph), scale[2] * z))
+    verts = np.asarray(verts, np.float64)
+    faces = []
+    # top and bottom caps as fans
+    for j in range(1, m - 1):
+        faces.append((0, j, j + 1))
+        faces.append((m, m + j + 1, m + j))
+    # side band
+    for j in range(m):
+        a, b = j, (j + 1) % m
+        c, d = m + j, m + (j + 1) % m
+        faces.append((a, c, b))
+        faces.append((b, c, d))
+    enc = []
+    for f in faces:
+        enc.extend((3,) + f)
+    return verts, np.asarray(enc, np.int32), len(faces)
+
+
+def config_c1_convex(n: int, dtype, seed: int = 1003):
+    """C1b(ii): 58-vertex ellipsoid hull (0.2,0.3,0.4) vs a 16-vertex hull, poses in
+    [-0.3,0.3]^3.  Returns the convex meshes separately: the caller uploads them and
+    builds the shape table [(CONVEX, slot0), (CONVEX, slot1)]."""
+    m0 = ellipsoid_mesh(0.2, 0.3, 0.4)
+    m1 = random_hull16()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    poses1 = random_poses(rng, n, 0.3, dtype)
+    poses2 = random_poses(rng, n, 0.3, dtype)
+    return (m0, m1), make_pairs(np.zeros(n, np.uint32), np.ones(n, np.uint32)), poses1, poses2

@@ -1,0 +1,164 @@
+"""ctypes access to the two CPU oracles.  TEST INFRASTRUCTURE ONLY.
+
+  * RefOracle  -> oracle/_ref/libfclref.so : the unmodified reference headers,
+                  compiled against oracle/eigen_shim (kind "reference").
+  * PortOracle -> oracle/liboracle.so      : our CPU restatement (kind "port").
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import this module;
+nothing under mind-fcl_b200/ or include/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_PATH = os.path.join(_HERE, "_ref", "libfclref.so")
+PORT_PATH = os.path.join(_HERE, "liboracle.so")
+
+
+class Shape(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("geom", C.c_uint32), ("p", C.c_double * 3)]
+
+
+class Request(C.Structure):
+    _fields_ = [
+        ("max_contacts", C.c_uint32), ("penetration_mode", C.c_uint32), ("dir", C.c_double * 3),
+        ("binary_tol", C.c_double), ("distance_tol", C.c_double),
+        ("gjk_max_iter", C.c_uint32), ("epa_max_faces", C.c_uint32), ("epa_max_iter", C.c_uint32),
+        ("flags", C.c_uint32),
+    ]
+
+
+def _shape_array(shapes):
+    arr = (Shape * len(shapes))()
+    for i, (t, g, p) in enumerate(shapes):
+        arr[i].type = t
+        arr[i].geom = g
+        p = list(p) + [0.0] * (3 - len(p))
+        arr[i].p[:] = p
+    return arr
+
+
+def _request(**kw):
+    r = Request()
+    r.max_contacts = kw.get("max_contacts", 1)
+    r.penetration_mode = kw.get("penetration_mode", 0)
+    r.dir[:] = kw.get("direction", (0.0, 0.0, 0.0))
+    r.binary_tol = kw.get("binary_tol", 0.0)
+    r.distance_tol = kw.get("distance_tol", 0.0)
+    r.gjk_max_iter = kw.get("gjk_max_iter", 0)
+    r.epa_max_faces = kw.get("epa_max_faces", 0)
+    r.epa_max_iter = kw.get("epa_max_iter", 0)
+    r.flags = 0
+    return r
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+def _st(dtype):
+    return 0 if np.dtype(dtype) == np.float32 else 1
+
+
+class _Oracle:
+    prefix = ""
+    path = ""
+    kind = ""
+
+    def __init__(self):
+        if not os.path.exists(self.path):
+            raise FileNotFoundError(f"{self.path} missing: run `make -C oracle`")
+        self.lib = C.CDLL(self.path)
+        self._convex_slots = 0
+
+    def available(self):
+        return True
+
+    def fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def hardware_threads(self):
+        return int(self.fn("hardware_threads")())
+
+    def register_convex(self, verts, faces, num_faces):
+        verts = np.ascontiguousarray(verts, np.float64)
+        faces = np.ascontiguousarray(faces, np.int32)
+        f = self.fn("register_convex")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        return int(f(_p(verts), verts.shape[0], _p(faces), faces.size, num_faces))
+
+    def distance_batch(self, shapes, pairs, poses1, poses2, gjk_tol=0.0, gjk_max_iter=0, threads=1):
+        n = len(pairs)
+        dt = poses1.dtype
+        dist = np.zeros(n, dt)
+        p1 = np.zeros((n, 3), dt)
+        p2 = np.zeros((n, 3), dt)
+        ok = np.zeros(n, np.uint8)
+        arr = _shape_array(shapes)
+        f = self.fn("distance_batch")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double,
+                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        rc = f(_st(dt), C.cast(arr, C.c_void_p), len(shapes), _p(pairs), _p(poses1), _p(poses2), n, gjk_tol,
+               gjk_max_iter, _p(dist), _p(p1), _p(p2), _p(ok), threads)
+        assert rc == 0
+        return dist, p1, p2, ok
+
+    def collide_batch(self, shapes, pairs, poses1, poses2, max_keep=1, threads=1, want_contacts=True, **req):
+        n = len(pairs)
+        dt = poses1.dtype
+        contacts = np.zeros((n, max_keep, 9), dt) if want_contacts else None
+        counts = np.zeros(n, np.uint32)
+        arr = _shape_array(shapes)
+        r = _request(**req)
+        f = self.fn("collide_batch")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        rc = f(_st(dt), C.cast(arr, C.c_void_p), len(shapes), _p(pairs), _p(poses1), _p(poses2), n,
+               C.cast(C.pointer(r), C.c_void_p), max_keep, _p(contacts), _p(counts), threads)
+        assert rc == 0
+        return counts, contacts
+
+    def gjk_epa_batch(self, shapes, pairs, poses1, poses2, mode=0, threads=1, **req):
+        n = len(pairs)
+        dt = poses1.dtype
+        status = np.zeros(n, np.int32)
+        epa = np.zeros(n, np.int32)
+        mpr = np.zeros(n, np.int32)
+        geom = np.zeros((n, 7), dt)
+        iters = np.zeros((n, 2), np.uint32)
+        arr = _shape_array(shapes)
+        r = _request(**req)
+        f = self.fn("gjk_epa_batch")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        rc = f(_st(dt), C.cast(arr, C.c_void_p), len(shapes), _p(pairs), _p(poses1), _p(poses2), n,
+               C.cast(C.pointer(r), C.c_void_p), mode, _p(status), _p(epa), _p(mpr), _p(geom), _p(iters), threads)
+        assert rc == 0
+        return status, epa, mpr, geom, iters
+
+
+class RefOracle(_Oracle):
+    prefix = "fclref_"
+    path = REF_PATH
+    kind = "reference"
+
+
+class PortOracle(_Oracle):
+    prefix = "fclport_"
+    path = PORT_PATH
+    kind = "port"
+
+
+def have_ref():
+    return os.path.exists(REF_PATH)
+
+
+def have_port():
+    return os.path.exists(PORT_PATH)
