@@ -156,9 +156,17 @@ int fclb_gjk_epa_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const voi
 
 /* kernel launches issued by this process so far (bench.py's gpu_launches) */
 uint64_t fclb_launch_count(void);
-/* device time (ms, CUDA events on the engine's stream) of the kernels of the
- * most recent *_dev / *_host call, and of its dominant kernel */
+/* device time (ms, CUDA events on the engine's stream) of the most recent batch
+ * call: query kernels only / whole device side including the bucketing pass */
 double fclb_last_kernel_ms(void);
+double fclb_last_call_ms(void);
+/* per-launch records of the most recent batch call: kinds[i] = type1*8+type2 of
+ * the bucket, counts[i] = queries in it, ms[i] = CUDA-event duration.
+ * Returns the number of records (may exceed cap). */
+int fclb_last_launches(int* kinds, uint64_t* counts, double* ms, int cap);
+/* the engine's compute stream (cudaStream_t) so callers can order their own
+ * work / events against it */
+void* fclb_stream(void);
 
 #ifdef __cplusplus
 }

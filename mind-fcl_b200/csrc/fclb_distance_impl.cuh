@@ -84,6 +84,21 @@ __global__ void __launch_bounds__(kBlock) distanceClosedKernel(BatchView b, S ep
 // ok: 0 = not separated (dist = -1); 1 = separated, witness points valid;
 //     3 = separated but the reference's witness extraction reported invalid
 //         (it then returns uninitialised points; we return zeros mapped by tf1).
+//
+// One query per thread, written as a STATE MACHINE around a single support
+// site.  The reference runs three loops back to back -- boolean GJK
+// (gjk.hpp:90-137), the distance refinement (gjk_distance.hpp:48-105) and the
+// witness extraction (:376-470, up to six more supports).  A straight
+// translation leaves each lane of a warp in a different loop at a different
+// iteration: the first version of this kernel ran at 6.8 of 32 lanes active and
+// was instruction-fetch bound (ncu: stall_no_inst 75 %, 7k SASS lines).  Every
+// one of those loops is "evaluate support0(d) and support1(-d), then update
+// some state", so here all lanes meet at ONE support evaluation per trip and
+// only the (short) state update diverges; a lane that finishes a query
+// immediately fetches its next one (persistent, strided), so early finishers do
+// not idle.  Arithmetic and decision order per query are unchanged.
+enum GjkPhase : int { PH_FETCH = 0, PH_BOOL_FIRST = 1, PH_BOOL = 2, PH_DIST = 3, PH_EXTRACT = 4 };
+
 template <typename S, int T0, int T1>
 __global__ void __launch_bounds__(kBlock) distanceGjkKernel(BatchView b, S tol, int max_iter, DistanceOut out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -94,31 +109,197 @@ __global__ void __launch_bounds__(kBlock) distanceGjkKernel(BatchView b, S tol, 
   const ConvexD<S>* __restrict__ cvx = static_cast<const ConvexD<S>*>(b.convex);
   const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
   const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < b.count; i += size_t(gridDim.x) * blockDim.x) {
-    const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
-    const fclb_pair pr = b.pairs[q];
-    MinkDiff<S, T0, T1> md;
-    md.s0 = bindShape(shapes, cvx, pr.shape1);
-    md.s1 = bindShape(shapes, cvx, pr.shape2);
-    const Pose<S> tf1 = loadPose(poses1, q);
-    {
-      const Pose<S> tf2 = loadPose(poses2, q);
-      md.setPoses(tf1, tf2);
+  const S tol_sq = tol * tol;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+
+  int phase = PH_FETCH;
+  size_t q = 0;
+  MinkDiff<S, T0, T1> md;
+  Simp simplex;
+  simplex.ord = 0;
+  simplex.rank = -1;
+  V3<S> d = mk<S>(S(-1), S(0), S(0));
+  V3<S> cur = zero3<S>();
+  S book = S(0);
+  int it = 0;
+  ExtractPlan<S> plan;
+  plan.n = 0;
+  int ex_k = 0;
+  V3<S> p0 = zero3<S>(), p1 = zero3<S>();
+
+  while (true) {
+    if (phase == PH_FETCH) {
+      if (i >= b.count) break;
+      q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
+      i += stride;
+      const fclb_pair pr = b.pairs[q];
+      md.s0 = bindShape(shapes, cvx, pr.shape1);
+      md.s1 = bindShape(shapes, cvx, pr.shape2);
+      md.setPoses(loadPose(poses1, q), loadPose(poses2, q));
+      // guess = (1,0,0); Evaluate is called with -guess (gjk_solver-inl.h:768,783)
+      d = normalized(mk<S>(S(-1), S(0), S(0)));
+      simplex.ord = 0;
+      simplex.rank = -1;
+      phase = PH_BOOL_FIRST;
     }
-    Simp simplex;
-    GjkDistOut<S> dout;
-    dout.valid = false;
-    dout.p0 = zero3<S>();
-    dout.p1 = zero3<S>();
-    // guess = (1,0,0); Evaluate is called with -guess (gjk_solver-inl.h:768,783)
-    const int status = gjkEvaluate(md, st, simplex, mk<S>(S(-1), S(0), S(0)), tol, max_iter, &dout, nullptr);
-    if (status == GJK_SEPARATED) {
-      const V3<S> w1 = apply(tf1, dout.p0);
-      const V3<S> w2 = apply(tf1, dout.p1);
-      const S d = norm(dout.p0 - dout.p1);
-      writeDistance(out, q, d, w1, w2, dout.valid ? uint8_t(1) : uint8_t(3));
+
+    // ---- the single support site ----
+    const V3<S> s0 = md.support0(d);
+    const V3<S> s1 = md.support1(-d);
+
+    bool done = false;        // query finished this trip
+    bool separated = false;   // result flag when done
+    bool valid = false;       // witness validity when done && separated
+    bool begin_extract = false;
+
+    if (phase == PH_EXTRACT) {
+      if (!plan.weighted) {
+        p0 = s0;
+        p1 = s1;
+      } else {
+        const S w = (ex_k == 0) ? plan.w0 : ((ex_k == 1) ? plan.w1 : plan.w2);
+        if (ex_k == 0) {
+          p0 = s0 * w;
+          p1 = s1 * w;
+        } else {
+          p0 = p0 + s0 * w;
+          p1 = p1 + s1 * w;
+        }
+      }
+      ex_k += 1;
+      if (ex_k >= plan.n) {
+        done = true;
+        separated = true;
+        valid = plan.valid;
+      } else {
+        d = st.dir((plan.slots >> (8 * ex_k)) & 0xff);
+      }
     } else {
-      writeDistance(out, q, S(-1), zero3<S>(), zero3<S>(), uint8_t(0));
+      const V3<S> v = s0 - s1;
+      bool to_dist = false;
+      if (phase == PH_BOOL_FIRST) {  // gjk.hpp:73-88
+        addVertex(st, simplex, v, d);
+        if (sqnorm(v) <= tol_sq) {
+          done = true;  // Intersect
+        } else if (dot(v, d) < 0) {
+          to_dist = true;
+        } else {
+          d = d * S(-1);
+          it = 0;
+          phase = PH_BOOL;
+          if (it >= max_iter) done = true;  // IterationLimit
+        }
+      } else if (phase == PH_BOOL) {  // gjk.hpp:92-141
+        it += 1;
+        if (dot(v, d) < 0) {
+          to_dist = true;
+        } else {
+          bool dup = false;
+          for (int j = 0; j < simplex.rank; j++)
+            if (sqnorm(st.vtx(slotOf(simplex, j)) - v) < tol_sq) dup = true;
+          if (dup || sqnorm(v) <= tol_sq) {
+            done = true;  // ConvergeNoProgress / Intersect: not separated either way
+          } else {
+            addVertex(st, simplex, v, d);
+            const int ps = simplexProjection(st, simplex, d, tol);
+            if (ps != PROJ_CONTINUE || it >= max_iter) done = true;
+          }
+        }
+      } else {  // PH_DIST: gjk_distance.hpp:48-101, v is the new vertex along d
+        it += 1;
+        const S delta = dot(d, v - cur);
+        bool stop = delta < tol;
+        if (!stop) {
+          for (int j = 0; j < simplex.rank; j++)
+            if (sqnorm(st.vtx(slotOf(simplex, j)) - v) < tol_sq) stop = true;
+        }
+        if (stop) {
+          begin_extract = true;
+        } else {
+          addVertex(st, simplex, v, d);
+          const int us = minDistUpdate(st, simplex, cur, tol);
+          if (us == 0) {
+            begin_extract = true;
+          } else if (us == 1) {
+            const S nd = norm(cur);
+            const S improvement = book - nd;
+            if (improvement < tol || nd < tol) {
+              begin_extract = true;
+            } else {
+              book = nd;
+              d = (-cur) / book;
+              if (it >= max_iter) {  // loop falls through: "return false" (:104-105)
+                done = true;
+                separated = true;
+                valid = false;
+                p0 = zero3<S>();
+                p1 = zero3<S>();
+              }
+            }
+          } else {
+            done = true;
+            separated = true;
+            valid = false;
+            p0 = zero3<S>();
+            p1 = zero3<S>();
+          }
+        }
+      }
+      if (to_dist) {
+        // process_separated_vertex (gjk.hpp:22-52) + the distance loop's prologue
+        // (gjk_distance.hpp:14-46): the simplex restarts from the certifying vertex.
+        simplex.rank = -1;
+        simplex.ord = 0;
+        addVertex(st, simplex, v, d);
+        cur = v;
+        book = norm(cur);
+        if (book <= tol) {
+          begin_extract = true;
+        } else {
+          d = (-cur) / book;
+          it = 0;
+          phase = PH_DIST;
+          if (it >= max_iter) {
+            done = true;
+            separated = true;
+            valid = false;
+            p0 = zero3<S>();
+            p1 = zero3<S>();
+          }
+        }
+      }
+      if (begin_extract) {
+        plan = planExtraction(st, simplex);
+        if (plan.n == 0) {
+          done = true;
+          separated = true;
+          valid = false;
+          p0 = zero3<S>();
+          p1 = zero3<S>();
+        } else {
+          ex_k = 0;
+          d = st.dir(plan.slots & 0xff);
+          phase = PH_EXTRACT;
+        }
+      }
+    }
+
+    if (done) {
+      S dist = S(-1);
+      V3<S> w1 = zero3<S>(), w2 = zero3<S>();
+      uint8_t ok = 0;
+      if (separated) {
+        // answers are in shape-1's frame; report them in the world frame
+        // (gjk_solver-inl.h:785-792)
+        const Pose<S> tf1 = loadPose(poses1, q);
+        dist = norm(p0 - p1);
+        w1 = apply(tf1, p0);
+        w2 = apply(tf1, p1);
+        ok = valid ? uint8_t(1) : uint8_t(3);
+      }
+      writeDistance(out, q, dist, w1, w2, ok);
+      phase = PH_FETCH;
     }
   }
 }

@@ -76,7 +76,16 @@ struct Engine {
   void* d_stage = nullptr;
   size_t stage_cap = 0;
   std::atomic<uint64_t> launches{0};
-  double last_ms = 0.0;
+  double last_ms = 0.0;       // kernels of the last call (bucketing excluded)
+  double last_call_ms = 0.0;  // whole device side of the last call (bucketing included)
+  // per-launch CUDA-event timing of the last call
+  static constexpr int kMaxRec = 2 * kNumKinds;
+  cudaEvent_t rec_ev[kMaxRec + 1] = {};
+  int rec_kind[kMaxRec] = {};
+  uint64_t rec_count[kMaxRec] = {};
+  float rec_ms[kMaxRec] = {};
+  int n_rec = 0;
+  cudaEvent_t ev_call0 = nullptr;
 };
 static Engine& eng() {
   static Engine e;
@@ -301,10 +310,13 @@ static int distanceDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const v
   const int st = sizeof(S) == 4 ? 0 : 1;
   uint32_t counts[kNumKinds], offsets[kNumKinds];
   int uniform = -1;
+  FCLB_CUDA(cudaEventRecord(e.ev_call0, e.compute));
   int rc = bucketBatch<S>(e, t, pairs, n, counts, offsets, &uniform);
   if (rc) return rc;
   FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
   int launches = 0;
+  e.n_rec = 0;
+  FCLB_CUDA(cudaEventRecord(e.rec_ev[0], e.compute));
   for (int k = 0; k < kNumKinds; k++) {
     if (!counts[k]) continue;
     BatchView b{};
@@ -319,6 +331,10 @@ static int distanceDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const v
     b.type1 = k / kNumTypes;
     b.type2 = k % kNumTypes;
     FCLB_CUDA(launchDistance<S>(b, sp, out, e.compute, &launches));
+    e.rec_kind[e.n_rec] = k;
+    e.rec_count[e.n_rec] = counts[k];
+    e.n_rec++;
+    FCLB_CUDA(cudaEventRecord(e.rec_ev[e.n_rec], e.compute));
   }
   e.launches += uint64_t(launches);
   FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
@@ -326,6 +342,9 @@ static int distanceDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const v
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e.ev0, e.ev1);
   e.last_ms = ms;
+  cudaEventElapsedTime(&ms, e.ev_call0, e.ev1);
+  e.last_call_ms = ms;
+  for (int i = 0; i < e.n_rec; i++) cudaEventElapsedTime(&e.rec_ms[i], e.rec_ev[i], e.rec_ev[i + 1]);
   return FCLB_OK;
 }
 
@@ -381,6 +400,8 @@ int fclb_init(int device) {
   FCLB_CUDA(cudaStreamCreateWithFlags(&e.copy_out, cudaStreamNonBlocking));
   FCLB_CUDA(cudaEventCreate(&e.ev0));
   FCLB_CUDA(cudaEventCreate(&e.ev1));
+  FCLB_CUDA(cudaEventCreate(&e.ev_call0));
+  for (int i = 0; i <= Engine::kMaxRec; i++) FCLB_CUDA(cudaEventCreate(&e.rec_ev[i]));
   FCLB_CUDA(cudaMalloc(&e.d_hist, 2 * kNumKinds * sizeof(uint32_t)));
   FCLB_CUDA(cudaMallocHost(&e.h_hist, 2 * kNumKinds * sizeof(uint32_t)));
   e.ready = true;
@@ -578,7 +599,24 @@ int fclb_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const v
   return FCLB_OK;
 }
 
+// (collide / gjk_epa entry points: fclb_collide_api.cu)
+
 uint64_t fclb_launch_count(void) { return eng().launches.load(); }
 double fclb_last_kernel_ms(void) { return eng().last_ms; }
+double fclb_last_call_ms(void) { return eng().last_call_ms; }
+int fclb_last_launches(int* kinds, uint64_t* counts, double* ms, int cap) {
+  Engine& e = eng();
+  const int n = e.n_rec < cap ? e.n_rec : cap;
+  for (int i = 0; i < n; i++) {
+    if (kinds) kinds[i] = e.rec_kind[i];
+    if (counts) counts[i] = e.rec_count[i];
+    if (ms) ms[i] = double(e.rec_ms[i]);
+  }
+  return e.n_rec;
+}
+void* fclb_stream(void) {
+  if (ensureInit()) return nullptr;
+  return static_cast<void*>(eng().compute);
+}
 
 }  // extern "C"

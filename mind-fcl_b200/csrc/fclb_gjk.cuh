@@ -59,9 +59,11 @@ FCLB_DI int slotOf(const Simp& s, int k) { return (s.ord >> (8 * k)) & 0xff; }
 FCLB_DI uint32_t ord1(int a) { return uint32_t(a); }
 FCLB_DI uint32_t ord2(int a, int b) { return uint32_t(a) | (uint32_t(b) << 8); }
 FCLB_DI uint32_t ord3(int a, int b, int c) { return uint32_t(a) | (uint32_t(b) << 8) | (uint32_t(c) << 16); }
-FCLB_DI int freeSlot(const Simp& s) {
-  uint32_t used = 0;
-  for (int k = 0; k < s.rank; k++) used |= 1u << slotOf(s, k);
+FCLB_DI int freeSlot(const Simp& s) {  // branch-free: lowest slot not named by the first `rank` bytes
+  uint32_t used = (s.rank > 0) ? (1u << (s.ord & 3u)) : 0u;
+  used |= (s.rank > 1) ? (1u << ((s.ord >> 8) & 3u)) : 0u;
+  used |= (s.rank > 2) ? (1u << ((s.ord >> 16) & 3u)) : 0u;
+  used |= (s.rank > 3) ? (1u << ((s.ord >> 24) & 3u)) : 0u;
   return __ffs(~used) - 1;
 }
 template <typename S>
@@ -135,34 +137,38 @@ FCLB_DI int simplexProjection3(const SlotStore<S>& st, Simp& s, V3<S>& direction
   return PROJ_CONTINUE;
 }
 
-// gjk.hpp:289-362
+// gjk.hpp:289-362 (tetrahedron case) falling into :204-286 (triangle case).
+// One function so the triangle code exists once in the SASS.
 template <typename S>
-FCLB_DI int simplexProjection4(const SlotStore<S>& st, Simp& s, V3<S>& direction, S tol) {
-  const int sD = slotOf(s, 0), sC = slotOf(s, 1), sB = slotOf(s, 2), sA = slotOf(s, 3);
-  const V3<S> a = st.vtx(sA), b = st.vtx(sB), c = st.vtx(sC), d = st.vtx(sD);
-  const V3<S> ab = b - a, ac = c - a, ad = d - a;
-  V3<S> abc_n = cross(ab, ac);
-  V3<S> acd_n = cross(ac, ad);
-  V3<S> abd_n = cross(ab, ad);
-  const S abc_dot_ad = dot(abc_n, ad);
-  const S acd_dot_ab = dot(acd_n, ab);
-  const S abd_dot_ac = dot(abd_n, ac);
-  if (fabs_(abc_dot_ad) <= S(0)) return PROJ_ZERO_VOLUME;
-  if (abc_dot_ad > 0) abc_n = abc_n * S(-1);
-  if (acd_dot_ab > 0) acd_n = acd_n * S(-1);
-  if (abd_dot_ac > 0) abd_n = abd_n * S(-1);
-  const bool d_side = dot(a, abc_n) > 0;
-  const bool c_side = dot(a, abd_n) > 0;
-  const bool b_side = dot(a, acd_n) > 0;
-  if (d_side && c_side && b_side) return PROJ_INTERSECT;
-  if (!b_side) {
-    s.ord = ord3(sD, sC, sA);  // remove b
-  } else if (!c_side) {
-    s.ord = ord3(sD, sB, sA);  // remove c
-  } else {
-    s.ord = ord3(sC, sB, sA);  // remove d
+FCLB_DI int simplexProjection(const SlotStore<S>& st, Simp& s, V3<S>& direction, S tol) {
+  if (s.rank == 2) return simplexProjection2(st, s, direction);
+  if (s.rank == 4) {
+    const int sD = slotOf(s, 0), sC = slotOf(s, 1), sB = slotOf(s, 2), sA = slotOf(s, 3);
+    const V3<S> a = st.vtx(sA), b = st.vtx(sB), c = st.vtx(sC), d = st.vtx(sD);
+    const V3<S> ab = b - a, ac = c - a, ad = d - a;
+    V3<S> abc_n = cross(ab, ac);
+    V3<S> acd_n = cross(ac, ad);
+    V3<S> abd_n = cross(ab, ad);
+    const S abc_dot_ad = dot(abc_n, ad);
+    const S acd_dot_ab = dot(acd_n, ab);
+    const S abd_dot_ac = dot(abd_n, ac);
+    if (fabs_(abc_dot_ad) <= S(0)) return PROJ_ZERO_VOLUME;
+    if (abc_dot_ad > 0) abc_n = abc_n * S(-1);
+    if (acd_dot_ab > 0) acd_n = acd_n * S(-1);
+    if (abd_dot_ac > 0) abd_n = abd_n * S(-1);
+    const bool d_side = dot(a, abc_n) > 0;
+    const bool c_side = dot(a, abd_n) > 0;
+    const bool b_side = dot(a, acd_n) > 0;
+    if (d_side && c_side && b_side) return PROJ_INTERSECT;
+    if (!b_side) {
+      s.ord = ord3(sD, sC, sA);  // remove b
+    } else if (!c_side) {
+      s.ord = ord3(sD, sB, sA);  // remove c
+    } else {
+      s.ord = ord3(sC, sB, sA);  // remove d
+    }
+    s.rank = 3;
   }
-  s.rank = 3;
   return simplexProjection3(st, s, direction, tol);
 }
 
@@ -189,46 +195,62 @@ FCLB_DI V3<S> minDist2(const SlotStore<S>& st, Simp& s, S tol) {
   return w2 * s2 + (S(1.0) - w2) * s1;
 }
 
-// gjk_distance.hpp:156-289
+// gjk_distance.hpp:156-289 (triangle) and :128-153 (segment) as ONE routine.
+// The reference evaluates up to three edge sub-simplices of a triangle through
+// separate code paths; here the candidate edges are collected into a mask and
+// evaluated by one loop body (same order, same strict "<" selection).  A
+// rank-2 input is the degenerate case "one candidate edge, no triangle".
+// Keeping a single copy of each piece keeps the kernel inside the 32 KB L1.5
+// instruction cache.
 template <typename S>
-FCLB_DI V3<S> minDist3(const SlotStore<S>& st, Simp& s, S tol) {
-  const int k0 = slotOf(s, 0), k1 = slotOf(s, 1), k2 = slotOf(s, 2);
-  const V3<S> s1 = st.vtx(k2), s2 = st.vtx(k1), s3 = st.vtx(k0);
-  const V3<S> s1_to_s2 = s2 - s1;
-  const V3<S> s1_to_s3 = s3 - s1;
-  const bool s1_sep_s2 = dot(s1, s1_to_s2) >= 0;
-  const bool s1_sep_s3 = dot(s1, s1_to_s3) >= 0;
-  if (s1_sep_s2 && s1_sep_s3) {
-    s.ord = ord1(k2);
-    s.rank = 1;
-    return s1;
+FCLB_DI V3<S> subSimplexClosest(const SlotStore<S>& st, Simp& s, S tol) {
+  int k0, k1, k2, mask;
+  V3<S> s1 = zero3<S>(), n = zero3<S>();
+  S area_sq = S(0);
+  if (s.rank == 2) {
+    k1 = slotOf(s, 0);
+    k2 = slotOf(s, 1);
+    k0 = k1;
+    mask = 1;
+  } else {
+    k0 = slotOf(s, 0);
+    k1 = slotOf(s, 1);
+    k2 = slotOf(s, 2);
+    s1 = st.vtx(k2);
+    const V3<S> s2 = st.vtx(k1), s3 = st.vtx(k0);
+    const V3<S> s1_to_s2 = s2 - s1;
+    const V3<S> s1_to_s3 = s3 - s1;
+    const bool s1_sep_s2 = dot(s1, s1_to_s2) >= 0;
+    const bool s1_sep_s3 = dot(s1, s1_to_s3) >= 0;
+    if (s1_sep_s2 && s1_sep_s3) {
+      s.ord = ord1(k2);
+      s.rank = 1;
+      return s1;
+    }
+    n = cross(s1_to_s2, s1_to_s3);
+    area_sq = sqnorm(n);
+    const bool zero_area = area_sq <= S(0);
+    const bool s12_sep = dot(s1, cross(n, s1_to_s2)) > 0;
+    const bool s13_sep = dot(s1, cross(n, s1_to_s3)) < 0;
+    const bool s23_sep = dot(s2, cross(n, s3 - s2)) > 0;
+    // candidate edges, bit 0: [k1,k2]  bit 1: [k0,k2]  bit 2: [k0,k1]
+    if (!s1_sep_s2 && s12_sep) {
+      mask = 1;  // decided: segment s1s2 (:186-193)
+    } else if (!s1_sep_s3 && s13_sep) {
+      mask = 2;  // decided: segment s1s3 (:200-206)
+    } else {
+      mask = ((zero_area || s12_sep) ? 1 : 0) | ((zero_area || s13_sep) ? 2 : 0) | ((zero_area || s23_sep) ? 4 : 0);
+    }
   }
-  const V3<S> n = cross(s1_to_s2, s1_to_s3);
-  const S area_sq = sqnorm(n);
-  const bool zero_area = area_sq <= S(0);
-
-  const V3<S> s12_n = cross(n, s1_to_s2);
-  const bool s12_sep = dot(s1, s12_n) > 0;
-  if (!s1_sep_s2 && s12_sep) {
-    s.ord = ord2(k1, k2);
-    s.rank = 2;
-    return minDist2(st, s, tol);
-  }
-  const V3<S> s13_n = cross(n, s1_to_s3);
-  const bool s13_sep = dot(s1, s13_n) < 0;
-  if (!s1_sep_s3 && s13_sep) {
-    s.ord = ord2(k0, k2);
-    s.rank = 2;
-    return minDist2(st, s, tol);
-  }
-
   S best_sq = S(-1);
   V3<S> best_pt = zero3<S>();
   Simp best_s = s;
-  if (zero_area || s12_sep) {
+#pragma unroll 1
+  for (int e = 0; e < 3; e++) {
+    if (!(mask & (1 << e))) continue;
     Simp c;
-    c.ord = ord2(k1, k2);
     c.rank = 2;
+    c.ord = (e == 0) ? ord2(k1, k2) : ((e == 1) ? ord2(k0, k2) : ord2(k0, k1));
     const V3<S> p = minDist2(st, c, tol);
     const S d2 = sqnorm(p);
     if (best_sq < 0 || d2 < best_sq) {
@@ -237,54 +259,41 @@ FCLB_DI V3<S> minDist3(const SlotStore<S>& st, Simp& s, S tol) {
       best_pt = p;
     }
   }
-  if (zero_area || s13_sep) {
-    Simp c;
-    c.ord = ord2(k0, k2);
-    c.rank = 2;
-    const V3<S> p = minDist2(st, c, tol);
-    const S d2 = sqnorm(p);
-    if (best_sq < 0 || d2 < best_sq) {
-      best_sq = d2;
-      best_s = c;
-      best_pt = p;
-    }
-  }
-  const V3<S> s23_n = cross(n, s3 - s2);
-  const bool s23_sep = dot(s2, s23_n) > 0;
-  if (zero_area || s23_sep) {
-    Simp c;
-    c.ord = ord2(k0, k1);
-    c.rank = 2;
-    const V3<S> p = minDist2(st, c, tol);
-    const S d2 = sqnorm(p);
-    if (best_sq < 0 || d2 < best_sq) {
-      best_sq = d2;
-      best_s = c;
-      best_pt = p;
-    }
-  }
-  if (best_sq < 0) {
+  if (best_sq < 0) {  // only reachable from the triangle case: interior projection
     const S d = dot(s1, n);
     return n * (d / area_sq);
   }
   s = best_s;
   return best_pt;
 }
-
-// gjk_distance.hpp:292-371.  Returns false for NoImprovement (unreachable in
-// practice: the three candidates always update) and keeps the interface.
 template <typename S>
-FCLB_DI bool minDist4(const SlotStore<S>& st, Simp& s, V3<S>& out, S tol) {
+FCLB_DI V3<S> minDist3(const SlotStore<S>& st, Simp& s, S tol) {
+  return subSimplexClosest(st, s, tol);
+}
+
+// gjk_distance.hpp:109-126 with :292-371 (tetrahedron = best of the three faces
+// through the newest vertex).  status: 0 NoImprovement, 1 OK, 2 Failed
+template <typename S>
+FCLB_DI int minDistUpdate(const SlotStore<S>& st, Simp& s, V3<S>& out, S tol) {
+  if (s.rank == 1) {
+    out = st.vtx(slotOf(s, 0));
+    return 1;
+  }
+  if (s.rank < 1 || s.rank > 4) return 2;
+  const bool tetra = (s.rank == 4);
   const int k0 = slotOf(s, 0), k1 = slotOf(s, 1), k2 = slotOf(s, 2), k3 = slotOf(s, 3);
+  const int n_cand = tetra ? 3 : 1;
   S best_sq = S(-1);
   V3<S> best_pt = zero3<S>();
   Simp best_s = s;
 #pragma unroll 1
-  for (int f = 0; f < 3; f++) {
-    Simp c;
-    c.rank = 3;
-    c.ord = (f == 0) ? ord3(k1, k2, k3) : ((f == 1) ? ord3(k0, k2, k3) : ord3(k0, k1, k3));
-    const V3<S> p = minDist3(st, c, tol);
+  for (int f = 0; f < n_cand; f++) {
+    Simp c = s;
+    if (tetra) {
+      c.rank = 3;
+      c.ord = (f == 0) ? ord3(k1, k2, k3) : ((f == 1) ? ord3(k0, k2, k3) : ord3(k0, k1, k3));
+    }
+    const V3<S> p = subSimplexClosest(st, c, tol);
     const S d2 = sqnorm(p);
     if (best_sq < 0 || d2 < best_sq) {
       best_sq = d2;
@@ -292,28 +301,10 @@ FCLB_DI bool minDist4(const SlotStore<S>& st, Simp& s, V3<S>& out, S tol) {
       best_s = c;
     }
   }
-  if (best_sq < 0) return false;
+  if (best_sq < 0) return 0;
   s = best_s;
   out = best_pt;
-  return true;
-}
-
-// gjk_distance.hpp:109-126 ; status: 0 NoImprovement, 1 OK, 2 Failed
-template <typename S>
-FCLB_DI int minDistUpdate(const SlotStore<S>& st, Simp& s, V3<S>& out, S tol) {
-  if (s.rank == 1) {
-    out = st.vtx(slotOf(s, 0));
-    return 1;
-  } else if (s.rank == 2) {
-    out = minDist2(st, s, tol);
-    return 1;
-  } else if (s.rank == 3) {
-    out = minDist3(st, s, tol);
-    return 1;
-  } else if (s.rank == 4) {
-    return minDist4(st, s, out, tol) ? 1 : 0;
-  }
-  return 2;
+  return 1;
 }
 
 // gjk_distance.hpp:376-470 (extractSeparationPointNoSubSimplex)
@@ -371,6 +362,89 @@ FCLB_DI bool extractSeparationPoint(const MD& shape, const SlotStore<S>& st, con
   p0 = (shape.support0(d1) * w1 + shape.support0(d2) * w2) + shape.support0(d3) * w3;
   p1 = (shape.support1(-d1) * w1 + shape.support1(-d2) * w2) + shape.support1(-d3) * w3;
   return true;
+}
+
+// Witness extraction split in two for the state-machine kernel: the PLAN (which
+// stored directions to support along, with which weights; gjk_distance.hpp
+// :376-470) is pure simplex arithmetic, the supports themselves are evaluated by
+// the kernel's single shared support site.
+//   n == 0         : nothing to evaluate, result invalid (:381-384,:438,:451-455)
+//   weighted==false: one support pair along slot[0], p = support directly
+//   weighted==true : p = sum_k support(slot[k]) * w[k], accumulated left to right
+template <typename S>
+struct ExtractPlan {
+  int n;
+  bool weighted;
+  bool valid;
+  uint32_t slots;  // byte k = slot of the k-th direction
+  S w0, w1, w2;
+};
+template <typename S>
+FCLB_DI ExtractPlan<S> planExtraction(const SlotStore<S>& st, const Simp& s) {
+  constexpr S bary_tol = S(1e-3);  // gjk.h:131
+  ExtractPlan<S> p;
+  p.n = 0;
+  p.weighted = false;
+  p.valid = false;
+  p.slots = 0;
+  p.w0 = p.w1 = p.w2 = S(0);
+  if (s.rank == 4 || s.rank <= 0) return p;
+  if (s.rank == 1) {
+    p.n = 1;
+    p.valid = true;
+    p.slots = ord1(slotOf(s, 0));
+    return p;
+  }
+  if (s.rank == 2) {
+    const int ka = slotOf(s, 0), kb = slotOf(s, 1);
+    const V3<S> s1 = st.vtx(ka), s2 = st.vtx(kb);
+    const V3<S> s1_to_s2 = s2 - s1;
+    const S sq_len = sqnorm(s1_to_s2);
+    p.n = 1;
+    if (sq_len <= S(0)) {
+      p.valid = true;
+      p.slots = ord1(ka);
+      return p;
+    }
+    const S t = -dot(s1, s1_to_s2);
+    const S w2 = t / sq_len;
+    if (w2 > 1 + bary_tol) {
+      p.slots = ord1(kb);  // written but reported invalid
+      return p;
+    } else if (w2 < -bary_tol) {
+      p.slots = ord1(ka);
+      return p;
+    }
+    p.n = 2;
+    p.weighted = true;
+    p.valid = true;
+    p.slots = ord2(ka, kb);
+    p.w0 = S(1.0) - w2;
+    p.w1 = w2;
+    return p;
+  }
+  const int ka = slotOf(s, 0), kb = slotOf(s, 1), kc = slotOf(s, 2);
+  const V3<S> s1 = st.vtx(ka), s2 = st.vtx(kb), s3 = st.vtx(kc);
+  const V3<S> s1_to_s2 = s2 - s1;
+  const V3<S> s1_to_s3 = s3 - s1;
+  const V3<S> n = cross(s1_to_s2, s1_to_s3);
+  const S area_sq = sqnorm(n);
+  if (area_sq <= S(0)) return p;
+  const S d = dot(s1, n);
+  const V3<S> o_proj = n * (d / area_sq);
+  const S area = fsqrt(area_sq);
+  const S w2 = norm(cross(s1_to_s3, s1 - o_proj)) / area;
+  const S w3 = norm(cross(s1_to_s2, s1 - o_proj)) / area;
+  const S w1 = S(1.0) - w2 - w3;
+  if (w1 < -bary_tol || w2 < -bary_tol || w3 < -bary_tol) return p;
+  p.n = 3;
+  p.weighted = true;
+  p.valid = true;
+  p.slots = ord3(ka, kb, kc);
+  p.w0 = w1;
+  p.w1 = w2;
+  p.w2 = w3;
+  return p;
 }
 
 // gjk_distance.hpp:11-106.  The simplex holds the one separating vertex.
@@ -468,13 +542,7 @@ FCLB_DI int gjkEvaluate(const MD& shape, SlotStore<S>& st, Simp& s, V3<S> guess,
         return GJK_INTERSECT;
       }
       addVertex(st, s, v, direction);
-      int ps;
-      if (s.rank == 2)
-        ps = simplexProjection2(st, s, direction);
-      else if (s.rank == 3)
-        ps = simplexProjection3(st, s, direction, tol);
-      else
-        ps = simplexProjection4(st, s, direction, tol);
+      const int ps = simplexProjection(st, s, direction, tol);
       if (ps == PROJ_FAILED) return GJK_FAILED;
       if (ps == PROJ_INTERSECT) return GJK_INTERSECT;
       if (ps == PROJ_ZERO_VOLUME) {

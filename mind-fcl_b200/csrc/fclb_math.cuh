@@ -57,9 +57,16 @@ template <typename S>
 FCLB_DI V3<S> operator*(S s, const V3<S>& a) {
   return mk<S>(s * a.x, s * a.y, s * a.z);
 }
+// IEEE division expands to ~10 SASS instructions per quotient plus a slow-path
+// call; the GJK kernels divide vectors at a dozen sites, so the three quotients
+// live in ONE out-of-line copy (instruction-cache footprint).
+template <typename S>
+__device__ __noinline__ V3<S> div3(V3<S> a, S s) {
+  return mk<S>(a.x / s, a.y / s, a.z / s);
+}
 template <typename S>
 FCLB_DI V3<S> operator/(const V3<S>& a, S s) {
-  return mk<S>(a.x / s, a.y / s, a.z / s);
+  return div3<S>(a, s);
 }
 template <typename S>
 FCLB_DI S dot(const V3<S>& a, const V3<S>& b) {
@@ -69,8 +76,8 @@ template <typename S>
 FCLB_DI S sqnorm(const V3<S>& a) {
   return (a.x * a.x + a.y * a.y) + a.z * a.z;
 }
-FCLB_DI float fsqrt(float v) { return sqrtf(v); }
-FCLB_DI double fsqrt(double v) { return sqrt(v); }
+__device__ __noinline__ inline float fsqrt(float v) { return sqrtf(v); }
+__device__ __noinline__ inline double fsqrt(double v) { return sqrt(v); }
 FCLB_DI float fabs_(float v) { return fabsf(v); }
 FCLB_DI double fabs_(double v) { return fabs(v); }
 template <typename S>

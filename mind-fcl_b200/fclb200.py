@@ -29,7 +29,7 @@ EXPORTS = [
     "fclb_distance_batch_host", "fclb_distance_batch_dev",
     "fclb_collide_batch_host", "fclb_collide_batch_dev",
     "fclb_gjk_epa_batch_host", "fclb_gjk_epa_batch_dev",
-    "fclb_launch_count", "fclb_last_kernel_ms",
+    "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
 
@@ -90,6 +90,9 @@ def load() -> C.CDLL:
     lib.fclb_version.restype = C.c_char_p
     lib.fclb_launch_count.restype = C.c_uint64
     lib.fclb_last_kernel_ms.restype = C.c_double
+    lib.fclb_last_call_ms.restype = C.c_double
+    lib.fclb_stream.restype = C.c_void_p
+    lib.fclb_last_launches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     vp, sz, u32 = C.c_void_p, C.c_size_t, C.c_uint32
     lib.fclb_init.argtypes = [C.c_int]
     lib.fclb_host_alloc.argtypes = [C.POINTER(vp), sz]
@@ -225,3 +228,21 @@ def launch_count() -> int:
 
 def last_kernel_ms() -> float:
     return float(load().fclb_last_kernel_ms())
+
+
+def last_call_ms() -> float:
+    return float(load().fclb_last_call_ms())
+
+
+def last_launches():
+    """[(type1, type2, n_queries, ms)] of the most recent batch call."""
+    cap = 128
+    kinds = (C.c_int * cap)()
+    counts = (C.c_uint64 * cap)()
+    ms = (C.c_double * cap)()
+    n = load().fclb_last_launches(kinds, counts, ms, cap)
+    return [(kinds[i] // 8, kinds[i] % 8, int(counts[i]), float(ms[i])) for i in range(min(n, cap))]
+
+
+def stream_ptr() -> int:
+    return int(load().fclb_stream())
