@@ -1,22 +1,213 @@
-// fclb_collide_api.cu -- C ABI entry points for batched fcl::collide and the
-// direct GJK+EPA path.  (Kernels: fclb_collide_impl.cuh.)
-#include "fclb_internal.h"
+// fclb_collide_api.cu -- C ABI entry points for batched fcl::collide
+// (shape-shape) and the direct GJK+EPA path.  Kernels: fclb_collide_impl.cuh.
+#include "fclb_collide_impl.cuh"
+#include "fclb_engine.h"
+
+namespace fclb {
+
+struct CollideWorkspace {
+  uint32_t* count = nullptr;
+  uint32_t* query = nullptr;
+  void* simplex = nullptr;
+  int32_t* rank = nullptr;
+  size_t cap = 0;      // queries
+  size_t scalar = 0;   // bytes per scalar the simplex buffer was sized for
+};
+static CollideWorkspace g_ws;
+
+static int ensureWorkspace(size_t n, size_t ss) {
+  if (n <= g_ws.cap && ss <= g_ws.scalar) return FCLB_OK;
+  if (g_ws.count) cudaFree(g_ws.count);
+  if (g_ws.query) cudaFree(g_ws.query);
+  if (g_ws.simplex) cudaFree(g_ws.simplex);
+  if (g_ws.rank) cudaFree(g_ws.rank);
+  g_ws = CollideWorkspace();
+  const size_t cap = n > g_ws.cap ? n : g_ws.cap;
+  FCLB_CUDA(cudaMalloc(&g_ws.count, sizeof(uint32_t)));
+  FCLB_CUDA(cudaMalloc(&g_ws.query, cap * sizeof(uint32_t)));
+  FCLB_CUDA(cudaMalloc(&g_ws.simplex, cap * 24 * 8));
+  FCLB_CUDA(cudaMalloc(&g_ws.rank, cap * sizeof(int32_t)));
+  g_ws.cap = cap;
+  g_ws.scalar = 8;
+  return FCLB_OK;
+}
+
+template <typename S>
+static int collideDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const void* poses1, const void* poses2, size_t n,
+                      const CollideLaunchArgs& base) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  uint32_t counts[kNumKinds], offsets[kNumKinds];
+  int uniform = -1;
+  FCLB_CUDA(cudaEventRecord(e.ev_call0, e.compute));
+  int rc = bucketBatch<S>(e, t, pairs, n, counts, offsets, &uniform);
+  if (rc) return rc;
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  int launches = 0;
+  e.n_rec = 0;
+  FCLB_CUDA(cudaEventRecord(e.rec_ev[0], e.compute));
+  for (int k = 0; k < kNumKinds; k++) {
+    if (!counts[k]) continue;
+    BatchView b{};
+    b.shapes = t->d_shapes[st];
+    b.convex = e.d_convex_tab[st];
+    b.pairs = pairs;
+    b.poses1 = poses1;
+    b.poses2 = poses2;
+    b.perm = (uniform >= 0) ? nullptr : e.d_perm;
+    b.begin = (uniform >= 0) ? 0 : offsets[k];
+    b.count = counts[k];
+    b.type1 = k / kNumTypes;
+    b.type2 = k % kNumTypes;
+    CollideLaunchArgs a = base;
+    if (a.mode & 2) FCLB_CUDA(cudaMemsetAsync(g_ws.count, 0, sizeof(uint32_t), e.compute));
+    FCLB_CUDA(launchCollide<S>(b, a, e.compute, &launches));
+    e.rec_kind[e.n_rec] = k;
+    e.rec_count[e.n_rec] = counts[k];
+    e.n_rec++;
+    FCLB_CUDA(cudaEventRecord(e.rec_ev[e.n_rec], e.compute));
+  }
+  e.launches += uint64_t(launches);
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.last_ms = ms;
+  cudaEventElapsedTime(&ms, e.ev_call0, e.ev1);
+  e.last_call_ms = ms;
+  for (int i = 0; i < e.n_rec; i++) cudaEventElapsedTime(&e.rec_ms[i], e.rec_ev[i], e.rec_ev[i + 1]);
+  return FCLB_OK;
+}
+
+static int runCollide(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2, size_t n,
+                      int scalar_type, const fclb_request* req, int api_mode, CollideOut out) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  ShapeTable* t = findTable(e, shapes);
+  if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (!req) return fail(FCLB_ERR_BAD_ARG, "null request");
+  if (n == 0) return FCLB_OK;
+  if (n > 0xffffffffull) return fail(FCLB_ERR_CAPACITY, "batch larger than 2^32-1 queries: split it");
+  if (!pairs || !poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null input array");
+  if (req->penetration_mode == FCLB_PEN_DIRECTED || req->penetration_mode == FCLB_PEN_INCREMENTAL_MIN)
+    return fail(FCLB_ERR_UNSUPPORTED,
+                "MPR directed / incremental-minimum penetration modes are not on the device yet (SURVEY.md 8f rank 1)");
+  if (req->epa_max_faces > 1024) return fail(FCLB_ERR_CAPACITY, "epa_max_faces > 1024 does not fit shared memory");
+  CollideLaunchArgs a{};
+  a.sp = solverParams(scalar_type, req->binary_tol, req->gjk_max_iter, req->distance_tol, req->epa_max_faces,
+                      req->epa_max_iter, true);
+  a.out = out;
+  a.out.max_contacts = req->max_contacts;
+  a.out.penetration = (req->penetration_mode == FCLB_PEN_DEFAULT_GJK_EPA) ? 1 : 0;
+  if (api_mode == 1) {
+    a.mode = 4 | 2;  // direct GJK then EPA
+  } else {
+    a.mode = a.out.penetration ? 2 : 1;  // contacts: GJK+EPA; none: MPR with GJK fallback
+  }
+  if (a.mode & 2) {
+    rc = ensureWorkspace(n, scalar_type == FCLB_F32 ? 4 : 8);
+    if (rc) return rc;
+  }
+  a.work.count = g_ws.count;
+  a.work.query = g_ws.query;
+  a.work.simplex = g_ws.simplex;
+  a.work.rank = g_ws.rank;
+  a.work.capacity = uint32_t(g_ws.cap);
+  if (scalar_type == FCLB_F32) return collideDev<float>(e, t, pairs, poses1, poses2, n, a);
+  return collideDev<double>(e, t, pairs, poses1, poses2, n, a);
+}
+
+// host-buffer wrapper: stage inputs, run, copy the requested outputs back
+static int runCollideHost(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2, size_t n,
+                          int scalar_type, const fclb_request* req, int api_mode, uint32_t max_keep, void* h_contacts,
+                          uint32_t* h_counts, int32_t* h_gjk, int32_t* h_epa, void* h_geom) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!pairs || !poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null input array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t o_pairs = 0;
+  const size_t o_p1 = alignUp(o_pairs + n * sizeof(fclb_pair), 256);
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_cont = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t cont_bytes = h_contacts ? n * size_t(max_keep) * 9 * ss : 0;
+  const size_t o_cnt = alignUp(o_cont + cont_bytes, 256);
+  const size_t o_gjk = alignUp(o_cnt + n * 4, 256);
+  const size_t o_epa = alignUp(o_gjk + n * 4, 256);
+  const size_t o_geom = alignUp(o_epa + n * 4, 256);
+  const size_t total = alignUp(o_geom + n * 7 * ss, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_pairs, pairs, n * sizeof(fclb_pair), cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  CollideOut out{};
+  out.contacts = h_contacts ? base + o_cont : nullptr;
+  out.counts = reinterpret_cast<uint32_t*>(base + o_cnt);
+  out.max_keep = h_contacts ? max_keep : 0;
+  out.gjk_status = reinterpret_cast<int32_t*>(base + o_gjk);
+  out.epa_status = reinterpret_cast<int32_t*>(base + o_epa);
+  out.geom = base + o_geom;
+  rc = runCollide(shapes, reinterpret_cast<const fclb_pair*>(base + o_pairs), base + o_p1, base + o_p2, n, scalar_type,
+                  req, api_mode, out);
+  if (rc) return rc;
+  if (h_contacts) FCLB_CUDA(cudaMemcpyAsync(h_contacts, base + o_cont, cont_bytes, cudaMemcpyDeviceToHost, e.compute));
+  if (h_counts) FCLB_CUDA(cudaMemcpyAsync(h_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  if (h_gjk) FCLB_CUDA(cudaMemcpyAsync(h_gjk, base + o_gjk, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  if (h_epa) FCLB_CUDA(cudaMemcpyAsync(h_epa, base + o_epa, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  if (h_geom) FCLB_CUDA(cudaMemcpyAsync(h_geom, base + o_geom, n * 7 * ss, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+}  // namespace fclb
+
+using namespace fclb;
 
 extern "C" {
-int fclb_collide_batch_dev(fclb_handle, const fclb_pair*, const void*, const void*, size_t, int, const fclb_request*,
-                           uint32_t, void*, uint32_t*) {
-  return FCLB_ERR_UNSUPPORTED;
+
+int fclb_collide_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                           size_t n, int scalar_type, const fclb_request* req, uint32_t max_keep, void* out_contacts,
+                           uint32_t* out_counts) {
+  if (!out_counts) return fail(FCLB_ERR_BAD_ARG, "fclb_collide_batch: out_counts is required");
+  CollideOut out{};
+  out.contacts = out_contacts;
+  out.counts = out_counts;
+  out.max_keep = out_contacts ? max_keep : 0;
+  return runCollide(shapes, pairs, poses1, poses2, n, scalar_type, req, 0, out);
 }
-int fclb_collide_batch_host(fclb_handle, const fclb_pair*, const void*, const void*, size_t, int, const fclb_request*,
-                            uint32_t, void*, uint32_t*) {
-  return FCLB_ERR_UNSUPPORTED;
+
+int fclb_collide_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                            size_t n, int scalar_type, const fclb_request* req, uint32_t max_keep, void* out_contacts,
+                            uint32_t* out_counts) {
+  if (!out_counts) return fail(FCLB_ERR_BAD_ARG, "fclb_collide_batch: out_counts is required");
+  return runCollideHost(shapes, pairs, poses1, poses2, n, scalar_type, req, 0, max_keep, out_contacts, out_counts,
+                        nullptr, nullptr, nullptr);
 }
-int fclb_gjk_epa_batch_dev(fclb_handle, const fclb_pair*, const void*, const void*, size_t, int, const fclb_request*,
-                           int32_t*, int32_t*, void*) {
-  return FCLB_ERR_UNSUPPORTED;
+
+int fclb_gjk_epa_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                           size_t n, int scalar_type, const fclb_request* req, int32_t* out_gjk, int32_t* out_epa,
+                           void* out_geom) {
+  if (!out_gjk) return fail(FCLB_ERR_BAD_ARG, "fclb_gjk_epa_batch: out_gjk is required");
+  CollideOut out{};
+  out.gjk_status = out_gjk;
+  out.epa_status = out_epa;
+  out.geom = out_geom;
+  return runCollide(shapes, pairs, poses1, poses2, n, scalar_type, req, 1, out);
 }
-int fclb_gjk_epa_batch_host(fclb_handle, const fclb_pair*, const void*, const void*, size_t, int, const fclb_request*,
-                            int32_t*, int32_t*, void*) {
-  return FCLB_ERR_UNSUPPORTED;
+
+int fclb_gjk_epa_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                            size_t n, int scalar_type, const fclb_request* req, int32_t* out_gjk, int32_t* out_epa,
+                            void* out_geom) {
+  if (!out_gjk) return fail(FCLB_ERR_BAD_ARG, "fclb_gjk_epa_batch: out_gjk is required");
+  return runCollideHost(shapes, pairs, poses1, poses2, n, scalar_type, req, 1, 0, nullptr, nullptr, out_gjk, out_epa,
+                        out_geom);
 }
-}
+
+}  // extern "C"

@@ -1,0 +1,386 @@
+// fclb_collide_impl.cuh -- batched fcl::collide for shape-shape pairs and the
+// direct GJK+EPA path.
+//
+// Reference path: fcl::collide -> ShapeShapeCollide (collision_func_matrix-inl.h:340)
+// -> ShapePairIntersectSolver::ShapeIntersect (shape_pair_intersect-inl.h:49-116)
+// -> GJKSolver::shapeIntersect: closed form for the registered pairs
+// (gjk_solver-inl.h:152-243), else MPR (no contact wanted) / GJK (+EPA)
+// (gjk_solver-inl.h:71-140).
+//
+// Three kernel families, one launch per (type1,type2) bucket:
+//   collideClosedKernel  thread per query   closed-form pairs (HBM bound)
+//   convexBoolKernel     thread per query   MPR and/or GJK boolean; colliding
+//                                           queries that need a contact append
+//                                           their GJK simplex to a work list
+//   epaKernel            WARP per query     EPA on the work list (fclb_epa.cuh)
+#pragma once
+#include "fclb_boxbox.cuh"
+#include "fclb_epa.cuh"
+#include "fclb_internal.h"
+#include "fclb_mpr.cuh"
+
+namespace fclb {
+
+struct CollideOut {
+  void* contacts;    // max_keep x 9 S per query, or nullptr
+  uint32_t* counts;  // numContacts per query (collide API) -- may be nullptr in gjk_epa mode
+  uint32_t max_keep;
+  uint32_t max_contacts;
+  int penetration;  // 0 disabled, 1 default GJK/EPA
+  // gjk_epa API outputs
+  int32_t* gjk_status;
+  int32_t* epa_status;
+  void* geom;  // 7 S per query {depth, p0, p1}
+};
+
+// EPA work list: colliding queries + their GJK simplices
+struct EpaWork {
+  uint32_t* count;   // device counter
+  uint32_t* query;   // [capacity] query index
+  void* simplex;     // [capacity] x 24 S (slot s: vertex 3, direction 3)
+  int32_t* rank;     // [capacity]
+  uint32_t capacity;
+};
+
+template <typename S>
+FCLB_DI void writeContact(const CollideOut& o, size_t q, uint32_t k, const ContactPt<S>& c) {
+  if (!o.contacts || k >= o.max_keep) return;
+  S* p = static_cast<S*>(o.contacts) + (q * o.max_keep + k) * 9;
+  p[0] = S(-1);
+  p[1] = S(-1);
+  p[2] = c.normal.x; p[3] = c.normal.y; p[4] = c.normal.z;
+  p[5] = c.pos.x; p[6] = c.pos.y; p[7] = c.pos.z;
+  p[8] = c.depth;
+}
+template <typename S>
+FCLB_DI void clearContacts(const CollideOut& o, size_t q, uint32_t from) {
+  if (!o.contacts) return;
+  for (uint32_t k = from; k < o.max_keep; k++) {
+    S* p = static_cast<S*>(o.contacts) + (q * o.max_keep + k) * 9;
+#pragma unroll
+    for (int j = 0; j < 9; j++) p[j] = S(0);
+  }
+}
+
+// std::partial_sort(first, first+k, last, comp) exactly as libstdc++ implements it
+// (__heap_select + __sort_heap), on an index array, comp(a,b) = depth[a] > depth[b]
+// (shape_pair_intersect-inl.h:96-106 keeps the k deepest contacts; which of two
+// equally deep contacts survives is decided by this algorithm).
+template <typename S>
+struct SmallPartialSort {
+  int idx[8];
+  const S* depth;
+  FCLB_DI bool comp(int a, int b) const { return depth[b] < depth[a]; }
+  FCLB_DI void pushHeap(int hole, int top, int value) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && comp(idx[parent], value)) {
+      idx[hole] = idx[parent];
+      hole = parent;
+      parent = (hole - 1) / 2;
+    }
+    idx[hole] = value;
+  }
+  FCLB_DI void adjustHeap(int hole, int len, int value) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+      child = 2 * (child + 1);
+      if (comp(idx[child], idx[child - 1])) child--;
+      idx[hole] = idx[child];
+      hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+      child = 2 * (child + 1);
+      idx[hole] = idx[child - 1];
+      hole = child - 1;
+    }
+    pushHeap(hole, top, value);
+  }
+  FCLB_DI void run(int n, int k) {
+    // __make_heap(first, middle)
+    if (k >= 2) {
+      int parent = (k - 2) / 2;
+      while (true) {
+        const int value = idx[parent];
+        adjustHeap(parent, k, value);
+        if (parent == 0) break;
+        parent--;
+      }
+    }
+    for (int i = k; i < n; i++) {
+      if (comp(idx[i], idx[0])) {  // __pop_heap(first, middle, i)
+        const int value = idx[i];
+        idx[i] = idx[0];
+        adjustHeap(0, k, value);
+      }
+    }
+    // __sort_heap(first, middle)
+    int last = k;
+    while (last > 1) {
+      --last;
+      const int value = idx[last];
+      idx[last] = idx[0];
+      adjustHeap(0, last, value);
+    }
+  }
+};
+
+// Emit the result of one shape pair the way ShapeIntersect does (:49-116).
+template <typename S>
+FCLB_DI void emitContacts(const CollideOut& o, size_t q, bool hit, const ContactPt<S>* cps, int n) {
+  if (!hit || o.max_contacts == 0) {
+    if (o.counts) o.counts[q] = 0;
+    clearContacts<S>(o, q, 0);
+    return;
+  }
+  if (!o.penetration) {
+    if (o.counts) o.counts[q] = 1;
+    clearContacts<S>(o, q, 0);
+    if (o.contacts && o.max_keep > 0) {
+      S* p = static_cast<S*>(o.contacts) + (q * o.max_keep) * 9;
+      p[0] = S(-1);
+      p[1] = S(-1);
+    }
+    return;
+  }
+  const uint32_t free_space = o.max_contacts;
+  uint32_t adding = uint32_t(n);
+  if (free_space < uint32_t(n)) {
+    S depth[8];
+    SmallPartialSort<S> ps;
+    for (int i = 0; i < n; i++) {
+      depth[i] = cps[i].depth;
+      ps.idx[i] = i;
+    }
+    ps.depth = depth;
+    ps.run(n, int(free_space));
+    adding = free_space;
+    for (uint32_t k = 0; k < adding; k++) writeContact(o, q, k, cps[ps.idx[k]]);
+  } else {
+    for (uint32_t k = 0; k < adding; k++) writeContact(o, q, k, cps[k]);
+  }
+  if (o.counts) o.counts[q] = adding;
+  clearContacts<S>(o, q, adding);
+}
+
+enum ClosedCollide : int {
+  CC_NONE = 0,
+  CC_SPHERE_SPHERE,
+  CC_SPHERE_CAPSULE,
+  CC_CAPSULE_SPHERE,
+  CC_SPHERE_BOX,
+  CC_BOX_SPHERE,
+  CC_SPHERE_CYLINDER,
+  CC_CYLINDER_SPHERE,
+  CC_BOX_BOX
+};
+inline int closedCollideOf(int t1, int t2) {
+  if (t1 == ST_SPHERE && t2 == ST_SPHERE) return CC_SPHERE_SPHERE;
+  if (t1 == ST_SPHERE && t2 == ST_CAPSULE) return CC_SPHERE_CAPSULE;
+  if (t1 == ST_CAPSULE && t2 == ST_SPHERE) return CC_CAPSULE_SPHERE;
+  if (t1 == ST_SPHERE && t2 == ST_BOX) return CC_SPHERE_BOX;
+  if (t1 == ST_BOX && t2 == ST_SPHERE) return CC_BOX_SPHERE;
+  if (t1 == ST_SPHERE && t2 == ST_CYLINDER) return CC_SPHERE_CYLINDER;
+  if (t1 == ST_CYLINDER && t2 == ST_SPHERE) return CC_CYLINDER_SPHERE;
+  if (t1 == ST_BOX && t2 == ST_BOX) return CC_BOX_BOX;
+  return CC_NONE;
+}
+
+template <typename S, int CC>
+__global__ void __launch_bounds__(kBlock) collideClosedKernel(BatchView b, CollideOut out) {
+  const ShapeD<S>* __restrict__ shapes = static_cast<const ShapeD<S>*>(b.shapes);
+  const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
+  const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
+  const bool want = out.penetration != 0;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < b.count; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
+    const fclb_pair pr = b.pairs[q];
+    const ShapeD<S> a = shapes[pr.shape1];
+    const ShapeD<S> c = shapes[pr.shape2];
+    const Pose<S> tf1 = loadPose(poses1, q);
+    const Pose<S> tf2 = loadPose(poses2, q);
+    ContactPt<S> cp[4];
+    int n = 1;
+    bool hit = false;
+    bool flip = false;
+    if (CC == CC_SPHERE_SPHERE) {
+      hit = sphereSphereIntersect(a.p[0], tf1, c.p[0], tf2, want, cp[0]);
+    } else if (CC == CC_SPHERE_CAPSULE) {
+      hit = sphereCapsuleIntersect(a.p[0], tf1, c.p[0], c.p[1], tf2, want, cp[0]);
+    } else if (CC == CC_CAPSULE_SPHERE) {
+      hit = sphereCapsuleIntersect(c.p[0], tf2, a.p[0], a.p[1], tf1, want, cp[0]);
+      flip = true;
+    } else if (CC == CC_SPHERE_BOX) {
+      hit = sphereBoxIntersect(a.p[0], tf1, mk<S>(c.p[0], c.p[1], c.p[2]), tf2, want, cp[0]);
+    } else if (CC == CC_BOX_SPHERE) {
+      hit = sphereBoxIntersect(c.p[0], tf2, mk<S>(a.p[0], a.p[1], a.p[2]), tf1, want, cp[0]);
+      flip = true;
+    } else if (CC == CC_SPHERE_CYLINDER) {
+      hit = sphereCylinderIntersect(a.p[0], tf1, c.p[0], c.p[1], tf2, want, cp[0]);
+    } else if (CC == CC_CYLINDER_SPHERE) {
+      hit = sphereCylinderIntersect(c.p[0], tf2, a.p[0], a.p[1], tf1, want, cp[0]);
+      flip = true;
+    } else if (CC == CC_BOX_BOX) {
+      const int code = boxBox2(mk<S>(a.p[0], a.p[1], a.p[2]), tf1, mk<S>(c.p[0], c.p[1], c.p[2]), tf2, cp, &n);
+      hit = code != 0;
+    }
+    if (flip && want && hit) cp[0].normal = -cp[0].normal;  // flipNormal (gjk_solver-inl.h:186-197)
+    emitContacts<S>(out, q, hit, cp, n);
+  }
+}
+
+// ---- generic convex pairs: boolean stage -------------------------------------
+// mode bit 0: run MPR first (collide API without penetration, gjk_solver-inl.h:88-98)
+// mode bit 1: colliding queries go to the EPA work list
+// mode bit 2: gjk_epa API (write GJK status instead of counts)
+template <typename S, int T0, int T1>
+__global__ void __launch_bounds__(kBlock) convexBoolKernel(BatchView b, S tol, int max_iter, int mode, CollideOut out,
+                                                           EpaWork work) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SlotStore<S> st;
+  st.base = reinterpret_cast<S*>(smem_raw) + threadIdx.x;
+  st.stride = blockDim.x;
+  const ShapeD<S>* __restrict__ shapes = static_cast<const ShapeD<S>*>(b.shapes);
+  const ConvexD<S>* __restrict__ cvx = static_cast<const ConvexD<S>*>(b.convex);
+  const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
+  const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < b.count; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
+    const fclb_pair pr = b.pairs[q];
+    MinkDiff<S, T0, T1> md;
+    md.s0 = bindShape(shapes, cvx, pr.shape1);
+    md.s1 = bindShape(shapes, cvx, pr.shape2);
+    md.setPoses(loadPose(poses1, q), loadPose(poses2, q));
+    int decided = -1;  // -1 undecided, 0 no collision, 1 collision
+    if (mode & 1) {
+      const int ms = mprIntersect(md, max_iter, tol, nullptr);
+      if (ms == MPR_INTERSECT) decided = 1;
+      if (ms == MPR_SEPARATED) decided = 0;
+    }
+    int gs = -1;
+    Simp simplex;
+    simplex.ord = 0;
+    simplex.rank = -1;
+    if (decided < 0) {
+      gs = gjkEvaluate<S>(md, st, simplex, mk<S>(S(-1), S(0), S(0)), tol, max_iter, nullptr, nullptr);
+      decided = (gs == GJK_INTERSECT) ? 1 : 0;
+    }
+    if (mode & 4) {
+      out.gjk_status[q] = gs;
+      if (out.epa_status) out.epa_status[q] = -1;
+      if (out.geom) {
+        S* g = static_cast<S*>(out.geom) + 7 * q;
+#pragma unroll
+        for (int j = 0; j < 7; j++) g[j] = S(0);
+      }
+    }
+    if (decided == 1 && (mode & 2)) {
+      const uint32_t w = atomicAdd(work.count, 1u);
+      if (w < work.capacity) {
+        work.query[w] = uint32_t(q);
+        work.rank[w] = simplex.rank;
+        S* sp = static_cast<S*>(work.simplex) + size_t(w) * 24;
+        for (int k = 0; k < 4; k++) {
+          const int slot = (k < simplex.rank) ? slotOf(simplex, k) : 0;
+          const V3<S> v = st.vtx(slot), d = st.dir(slot);
+          sp[6 * k + 0] = v.x; sp[6 * k + 1] = v.y; sp[6 * k + 2] = v.z;
+          sp[6 * k + 3] = d.x; sp[6 * k + 4] = d.y; sp[6 * k + 5] = d.z;
+        }
+      }
+    } else if (!(mode & 4)) {
+      // collide API, final answer without a contact computation
+      ContactPt<S> dummy;
+      dummy.normal = zero3<S>();
+      dummy.pos = zero3<S>();
+      dummy.depth = S(0);
+      emitContacts<S>(out, q, decided == 1 && !out.penetration, &dummy, 0);
+    }
+  }
+}
+
+// ---- EPA stage: one warp per work item ---------------------------------------
+constexpr int kEpaWarps = 4;
+
+template <typename S, int T0, int T1>
+__global__ void __launch_bounds__(kEpaWarps * 32) epaKernel(BatchView b, S tol, int max_faces, int max_iter, int mode,
+                                                            CollideOut out, EpaWork work, size_t poly_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* my = smem_raw + size_t(warp) * (poly_bytes + 24 * sizeof(S) + 16);
+  SlotStore<S> st;
+  st.base = reinterpret_cast<S*>(my);
+  st.stride = 1;
+  unsigned char* poly_mem = my + ((24 * sizeof(S) + 15) / 16 * 16);
+  const ShapeD<S>* __restrict__ shapes = static_cast<const ShapeD<S>*>(b.shapes);
+  const ConvexD<S>* __restrict__ cvx = static_cast<const ConvexD<S>*>(b.convex);
+  const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
+  const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
+  const uint32_t n_work = min(*work.count, work.capacity);
+  const uint32_t n_warps = gridDim.x * kEpaWarps;
+  for (uint32_t w = blockIdx.x * kEpaWarps + warp; w < n_work; w += n_warps) {
+    const size_t q = work.query[w];
+    const fclb_pair pr = b.pairs[q];
+    MinkDiff<S, T0, T1> md;
+    md.s0 = bindShape(shapes, cvx, pr.shape1);
+    md.s1 = bindShape(shapes, cvx, pr.shape2);
+    const Pose<S> tf1 = loadPose(poses1, q);
+    md.setPoses(tf1, loadPose(poses2, q));
+    // GJK simplex -> slots 0..rank-1
+    const S* sp = static_cast<const S*>(work.simplex) + size_t(w) * 24;
+    if (lane < 24) st.base[lane] = sp[lane];
+    __syncwarp();
+    Simp sx;
+    sx.rank = work.rank[w];
+    sx.ord = 0x03020100u;
+    EpaWarp<S, MinkDiff<S, T0, T1>> epa(md, poly_mem, max_faces, lane, nullptr);
+    S depth = S(0);
+    V3<S> p0 = zero3<S>(), p1 = zero3<S>();
+    const int es = epa.evaluate(st, sx, max_iter, tol, depth, p0, p1);
+    __syncwarp();
+    if (lane == 0) {
+      if (mode & 4) {
+        if (out.epa_status) out.epa_status[q] = es;
+        if (out.geom) {
+          S* g = static_cast<S*>(out.geom) + 7 * q;
+          g[0] = depth;
+          g[1] = p0.x; g[2] = p0.y; g[3] = p0.z;
+          g[4] = p1.x; g[5] = p1.y; g[6] = p1.z;
+        }
+      } else {
+        // gjk_solver-inl.h:117-133: contact in the world frame
+        bool hit = false;
+        ContactPt<S> c;
+        c.normal = zero3<S>();
+        c.pos = zero3<S>();
+        c.depth = S(0);
+        if (es != EPA_FAILED) {
+          V3<S> n1 = p0 - p1;
+          if (sqnorm(n1) <= S(0))
+            n1 = mk<S>(S(0), S(0), S(1));
+          else
+            n1 = normalized(n1);
+          const V3<S> pt1 = S(0.5) * (p0 + p1);
+          c.pos = apply(tf1, pt1);
+          c.normal = mulMV(tf1.R, n1);
+          c.depth = depth;
+          hit = true;
+        }
+        emitContacts<S>(out, q, hit, &c, 1);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+struct CollideLaunchArgs {
+  SolverParams sp;
+  int mode;
+  CollideOut out;
+  EpaWork work;
+};
+
+// implemented in fclb_collide_f32.cu / fclb_collide_f64.cu
+template <typename S>
+cudaError_t launchCollide(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st, int* n_launches);
+
+}  // namespace fclb

@@ -20,79 +20,23 @@
 #include <utility>
 #include <vector>
 
-#include "fclb_internal.h"
+#include "fclb_engine.h"
 #include "fclb_shapes.cuh"
 
 namespace fclb {
 
 thread_local std::string g_err;
-static int fail(int code, const std::string& msg) {
+int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
-#define FCLB_CUDA(expr)                                                                        \
-  do {                                                                                         \
-    cudaError_t e_ = (expr);                                                                   \
-    if (e_ != cudaSuccess)                                                                     \
-      return fail(FCLB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
-  } while (0)
 
-struct ConvexHost {
-  // per scalar type device arrays
-  void* d_verts[2] = {nullptr, nullptr};
-  int* d_nbr = nullptr;
-  int n_verts = 0;
-  int walk = 0;
-  int seed[2][6];
-  double interior[2][3];
-};
-
-struct ShapeTable {
-  void* d_shapes[2] = {nullptr, nullptr};  // ShapeD<float>[], ShapeD<double>[]
-  std::vector<fclb_shape> host;
-  uint32_t n = 0;
-  uint64_t convex_epoch = 0;
-};
-
-struct Engine {
-  std::recursive_mutex mu;
-  bool ready = false;
-  int device = -1;
-  int sms = 148;
-  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::vector<ConvexHost> convex;
-  void* d_convex_tab[2] = {nullptr, nullptr};  // ConvexD<S>[]
-  uint64_t convex_epoch = 0;
-  std::map<fclb_handle, ShapeTable*> tables;
-  fclb_handle next_handle = 1;
-  // scratch for bucketing
-  uint32_t* d_perm = nullptr;
-  uint8_t* d_kind = nullptr;
-  size_t scratch_cap = 0;
-  uint32_t* d_hist = nullptr;  // kNumKinds counters + kNumKinds cursors
-  uint32_t* h_hist = nullptr;  // pinned
-  // staging for host entry points
-  void* d_stage = nullptr;
-  size_t stage_cap = 0;
-  std::atomic<uint64_t> launches{0};
-  double last_ms = 0.0;       // kernels of the last call (bucketing excluded)
-  double last_call_ms = 0.0;  // whole device side of the last call (bucketing included)
-  // per-launch CUDA-event timing of the last call
-  static constexpr int kMaxRec = 2 * kNumKinds;
-  cudaEvent_t rec_ev[kMaxRec + 1] = {};
-  int rec_kind[kMaxRec] = {};
-  uint64_t rec_count[kMaxRec] = {};
-  float rec_ms[kMaxRec] = {};
-  int n_rec = 0;
-  cudaEvent_t ev_call0 = nullptr;
-};
-static Engine& eng() {
+Engine& eng() {
   static Engine e;
   return e;
 }
 
-static int ensureInit() {
+int ensureInit() {
   Engine& e = eng();
   if (e.ready) return FCLB_OK;
   return fclb_init(-1);
@@ -260,7 +204,7 @@ static int ensureScratch(Engine& e, size_t n) {
 // histogram; *uniform_kind >= 0 when every query has the same kind (then no
 // permutation is needed and perm stays unused).
 template <typename S>
-static int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs, size_t n, uint32_t* counts,
+int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs, size_t n, uint32_t* counts,
                        uint32_t* offsets, int* uniform_kind) {
   const int st = sizeof(S) == 4 ? 0 : 1;
   int rc = ensureScratch(e, n);
@@ -290,19 +234,29 @@ static int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs,
   return FCLB_OK;
 }
 
-static SolverParams distanceParams(int scalar_type, double gjk_tol, uint32_t gjk_max_iter) {
+SolverParams solverParams(int scalar_type, double gjk_tol, uint32_t gjk_max_iter, double epa_tol, uint32_t epa_max_faces,
+                          uint32_t epa_max_iter, bool collide_defaults) {
   SolverParams sp{};
   // constants<S>::eps_78(): pow(eps, 7/8) evaluated in double, rounded to S
   const double eps = scalar_type == FCLB_F32 ? double(1.1920928955078125e-07f) : 2.220446049250313e-16;
   const double e78 = std::pow(eps, 7. / 8.);
   sp.eps78 = scalar_type == FCLB_F32 ? double(float(e78)) : e78;
-  sp.gjk_tol = gjk_tol > 0 ? gjk_tol : sp.eps78;
+  // GJKSolver defaults are eps^(7/8) (gjk_solver-inl.h:1121-1130); fcl::collide
+  // overrides both tolerances with the request's 1e-6 (collision_interface-inl.h:19-20)
+  const double dflt = collide_defaults ? 1e-6 : sp.eps78;
+  sp.gjk_tol = gjk_tol > 0 ? gjk_tol : dflt;
+  sp.epa_tol = epa_tol > 0 ? epa_tol : dflt;
   sp.gjk_max_iter = gjk_max_iter ? int(gjk_max_iter) : 128;
-  sp.epa_tol = sp.eps78;
-  sp.epa_max_faces = 256;
-  sp.epa_max_iter = 255;
+  sp.epa_max_faces = epa_max_faces ? int(epa_max_faces) : 256;
+  sp.epa_max_iter = epa_max_iter ? int(epa_max_iter) : 255;
   return sp;
 }
+static SolverParams distanceParams(int scalar_type, double gjk_tol, uint32_t gjk_max_iter) {
+  return solverParams(scalar_type, gjk_tol, gjk_max_iter, 0.0, 0, 0, false);
+}
+
+template int bucketBatch<float>(Engine&, const ShapeTable*, const fclb_pair*, size_t, uint32_t*, uint32_t*, int*);
+template int bucketBatch<double>(Engine&, const ShapeTable*, const fclb_pair*, size_t, uint32_t*, uint32_t*, int*);
 
 template <typename S>
 static int distanceDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const void* poses1, const void* poses2, size_t n,
@@ -348,12 +302,12 @@ static int distanceDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const v
   return FCLB_OK;
 }
 
-static ShapeTable* findTable(Engine& e, fclb_handle h) {
+ShapeTable* findTable(Engine& e, fclb_handle h) {
   auto it = e.tables.find(h);
   return it == e.tables.end() ? nullptr : it->second;
 }
 
-static int ensureStage(Engine& e, size_t bytes) {
+int ensureStage(Engine& e, size_t bytes) {
   if (bytes <= e.stage_cap) return FCLB_OK;
   if (e.d_stage) cudaFree(e.d_stage);
   e.d_stage = nullptr;
@@ -363,7 +317,6 @@ static int ensureStage(Engine& e, size_t bytes) {
   return FCLB_OK;
 }
 
-static size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace fclb
 

@@ -1,0 +1,85 @@
+// fclb_engine.h -- engine state shared by the C-ABI translation units
+// (fclb_engine.cu, fclb_collide_api.cu, fclb_bvh_api.cu).  Internal.
+#pragma once
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fclb_internal.h"
+
+namespace fclb {
+
+int fail(int code, const std::string& msg);
+#define FCLB_CUDA(expr)                                                                        \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return ::fclb::fail(FCLB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));  \
+  } while (0)
+
+struct ConvexHost {
+  // per scalar type device arrays
+  void* d_verts[2] = {nullptr, nullptr};
+  int* d_nbr = nullptr;
+  int n_verts = 0;
+  int walk = 0;
+  int seed[2][6];
+  double interior[2][3];
+};
+
+struct ShapeTable {
+  void* d_shapes[2] = {nullptr, nullptr};  // ShapeD<float>[], ShapeD<double>[]
+  std::vector<fclb_shape> host;
+  uint32_t n = 0;
+  uint64_t convex_epoch = 0;
+};
+
+struct Engine {
+  std::recursive_mutex mu;
+  bool ready = false;
+  int device = -1;
+  int sms = 148;
+  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<ConvexHost> convex;
+  void* d_convex_tab[2] = {nullptr, nullptr};  // ConvexD<S>[]
+  uint64_t convex_epoch = 0;
+  std::map<fclb_handle, ShapeTable*> tables;
+  fclb_handle next_handle = 1;
+  // scratch for bucketing
+  uint32_t* d_perm = nullptr;
+  uint8_t* d_kind = nullptr;
+  size_t scratch_cap = 0;
+  uint32_t* d_hist = nullptr;  // kNumKinds counters + kNumKinds cursors
+  uint32_t* h_hist = nullptr;  // pinned
+  // staging for host entry points
+  void* d_stage = nullptr;
+  size_t stage_cap = 0;
+  std::atomic<uint64_t> launches{0};
+  double last_ms = 0.0;       // kernels of the last call (bucketing excluded)
+  double last_call_ms = 0.0;  // whole device side of the last call (bucketing included)
+  // per-launch CUDA-event timing of the last call
+  static constexpr int kMaxRec = 2 * kNumKinds;
+  cudaEvent_t rec_ev[kMaxRec + 1] = {};
+  int rec_kind[kMaxRec] = {};
+  uint64_t rec_count[kMaxRec] = {};
+  float rec_ms[kMaxRec] = {};
+  int n_rec = 0;
+  cudaEvent_t ev_call0 = nullptr;
+};
+Engine& eng();
+
+int ensureInit();
+ShapeTable* findTable(Engine& e, fclb_handle h);
+int ensureStage(Engine& e, size_t bytes);
+inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+SolverParams solverParams(int scalar_type, double gjk_tol, uint32_t gjk_max_iter, double epa_tol, uint32_t epa_max_faces,
+                          uint32_t epa_max_iter, bool collide_defaults);
+// Bucket a device-resident batch by (type1,type2); see fclb_engine.cu.
+template <typename S>
+int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs, size_t n, uint32_t* counts,
+                uint32_t* offsets, int* uniform_kind);
+
+}  // namespace fclb

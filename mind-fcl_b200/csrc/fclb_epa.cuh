@@ -1,0 +1,1032 @@
+// fclb_epa.cuh -- Expanding Polytope Algorithm, ONE WARP PER QUERY, polytope in
+// shared memory.
+//
+// Behavioural contract (results, not structure):
+//   include/fcl/cvx_collide/epa.hpp                 Evaluate :240, main loop :137-237,
+//                                                   findNextSupportDirection :11-113,
+//                                                   checkTerminateCondition :269-298,
+//                                                   assignPenetrationPair* :341-497
+//   include/fcl/cvx_collide/epa_simplex2polytope.hpp simplexToPolytope{,2,3,4} :46-380
+//   include/fcl/cvx_collide/epa_polytope.hpp        AddNew* :185-290, ComputeMinDistanceToOrigin :295-345,
+//                                                   ComputeFaceNormalPointingOutward :348-410
+//   include/fcl/cvx_collide/epa_polytope_expand.hpp ExpandPolytope :33-91, computeVisiblePatch :121-180,
+//                                                   removeAccordingToVisibility :244-281
+//   include/fcl/cvx_collide/epa_polytope_utils.h    pointTo{Segment,Triangle}SquaredDistance, pointTo{Line,Plane}Distance
+//
+// The reference keeps three pointer-linked, push-front lists in heap-allocated
+// pools (3 std::vector resizes per query) and walks them serially.  What its
+// RESULTS depend on is only
+//   (1) the selection order of ComputeMinDistanceToOrigin: strict "<" while
+//       scanning vertices, then edges, then faces, each newest-first;
+//   (2) the order in which ExpandPolytope creates new edges/faces (it walks the
+//       edge list newest-first), because that fixes (1) for later iterations.
+// Pool slot identity, free-list order and the flood-fill visiting order are
+// unobservable.  So here every element carries an insertion SEQUENCE NUMBER,
+// the pools are flat index arrays (u16 links) in shared memory, and
+//   * the O(V+E+F) nearest-feature scan is a warp-parallel arg-min with the key
+//     (distance, class, newest-first) -- exactly the sequential tie-break;
+//   * face visibility is evaluated for all faces at once and the visible patch
+//     is grown by warp-parallel label propagation (same set as the DFS);
+//   * the new cone of faces is built from the border edges ranked by sequence
+//     number, with their distance records computed one element per lane.
+// Control flow between those sections is warp-uniform (all lanes execute the
+// same scalar code on broadcast shared-memory reads).
+#pragma once
+#include "fclb_gjk.cuh"
+
+namespace fclb {
+
+enum EpaStatus : int { EPA_FAILED = 0, EPA_OK = 1, EPA_TOUCHING = 2, EPA_ITER_LIMIT = 3, EPA_MALLOC_FAILED = 4 };  // epa.h:14
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint16_t kNil = 0xffff;
+
+template <typename S>
+struct MinDist {  // MinDistanceToSimplex, epa_polytope_utils.h:15-20
+  bool in_simplex;
+  S dist_sq;
+  V3<S> witness;
+};
+
+// epa_polytope_utils.h:22-52
+template <typename S>
+FCLB_DI MinDist<S> pointToSegment(const V3<S>& p, const V3<S>& x0, const V3<S>& x1) {
+  MinDist<S> r;
+  const V3<S> d = x1 - x0;
+  const V3<S> a = x0 - p;
+  const S len_sq = sqnorm(d);
+  const S t = S(-1.0) * dot(a, d) / len_sq;
+  if (t <= S(0)) {
+    r.witness = x0;
+    r.in_simplex = false;
+    r.dist_sq = sqnorm(x0 - p);
+  } else if (t >= S(1.0)) {
+    r.witness = x1;
+    r.in_simplex = false;
+    r.dist_sq = sqnorm(x1 - p);
+  } else {
+    const V3<S> w = x0 + t * d;
+    r.witness = w;
+    r.in_simplex = true;
+    r.dist_sq = sqnorm(w);
+  }
+  return r;
+}
+// epa_polytope_utils.h:64-76
+template <typename S>
+FCLB_DI S pointToLineDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b) {
+  const V3<S> ab = b - a;
+  const S len = norm(ab);
+  if (len <= S(0)) return norm(p - a);
+  return norm(cross(p - a, ab)) / len;
+}
+// epa_polytope_utils.h:78-93
+template <typename S>
+FCLB_DI S pointToPlaneDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b, const V3<S>& c) {
+  const V3<S> n = cross(a - b, b - c);
+  const S len = norm(n);
+  if (len <= S(0)) return pointToLineDistance(p, a, b);
+  const V3<S> p_to_a = a - p;
+  const V3<S> un = n / len;
+  return fabs_(dot(un, p_to_a));
+}
+// epa_polytope_utils.h:95-165
+template <typename S>
+FCLB_DI MinDist<S> pointToTriangle(const V3<S>& p, const V3<S>& a, const V3<S>& b, const V3<S>& c) {
+  MinDist<S> r;
+  const V3<S> dl0 = a - b, dl1 = b - c, dl2 = c - a;
+  const V3<S> n = cross(dl0, dl1);
+  const S n_sq = sqnorm(n);
+  const S area = fsqrt(n_sq);
+  bool in_tri = false;
+  if (!(fabs_(area) <= S(1e-16))) {
+    const S d = dot(a - p, n);
+    const V3<S> p_to_proj = n * (d / n_sq);
+    const V3<S> proj = p + p_to_proj;
+    const S w0 = norm(cross(dl1, b - proj)) / area;
+    const S w1 = norm(cross(dl2, c - proj)) / area;
+    const S w2 = S(1.0) - w0 - w1;
+    in_tri = true;
+    if (w0 < S(0) || w0 > S(1)) {
+      in_tri = false;
+    } else if (w1 < S(0) || w1 > S(1)) {
+      in_tri = false;
+    } else if (w2 < S(0) || w2 > S(1)) {
+      in_tri = false;
+    }
+    const S w2_check = norm(cross(dl0, a - proj)) / area;
+    if (fabs_(w2_check - w2) > S(1e-3)) in_tri = false;
+    if (in_tri) {
+      r.in_simplex = true;
+      r.dist_sq = sqnorm(p_to_proj);
+      r.witness = a * w0 + b * w1 + c * w2;
+      return r;
+    }
+  }
+  // process_distance_in_sub_simplex: best of the three edges, first minimum wins
+  MinDist<S> best = pointToSegment(p, a, b);
+  {
+    const MinDist<S> e1 = pointToSegment(p, b, c);
+    if (e1.dist_sq < best.dist_sq) best = e1;
+    const MinDist<S> e2 = pointToSegment(p, c, a);
+    if (e2.dist_sq < best.dist_sq) best = e2;
+  }
+  r.in_simplex = false;
+  r.dist_sq = best.dist_sq;
+  r.witness = best.witness;
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// Shared-memory polytope of one warp.  Capacities as the reference:
+// faces = max_faces, edges = vertices = floor(1.51 * max_faces) (epa_polytope.hpp:88-96).
+template <typename S>
+struct PolyStore {
+  int vcap, ecap, fcap;
+  // vertices
+  S *vx, *vy, *vz, *dx, *dy, *dz, *vd;
+  uint16_t *v_seq, *v_newedge;
+  uint8_t *v_alive, *v_rm;
+  // edges
+  uint16_t *e_v0, *e_v1, *e_f0, *e_f1, *e_seq;
+  S* e_d;
+  uint8_t *e_alive, *e_in, *e_vis;  // vis: 0 unknown, 1 border, 2 internal
+  // faces
+  uint16_t *f_e0, *f_e1, *f_e2, *f_a, *f_b, *f_c, *f_seq;
+  S* f_d;
+  uint8_t *f_alive, *f_in, *f_vis;  // vis: 0 unknown, 1 visible(in patch), 2 hidden, 3 "outside" but not reached
+
+  static __host__ __device__ size_t bytes(int max_faces) {
+    const size_t f = size_t(max_faces), v = size_t(1.51 * double(max_faces)), e = v;
+    size_t b = 0;
+    b += 7 * v * sizeof(S) + e * sizeof(S) + f * sizeof(S);
+    b += (2 * v + 5 * e + 7 * f) * sizeof(uint16_t);
+    b += 2 * v + 3 * e + 3 * f;
+    return (b + 15) / 16 * 16;
+  }
+  FCLB_DI void bind(unsigned char* base, int max_faces) {
+    fcap = max_faces;
+    vcap = int(1.51 * double(max_faces));
+    ecap = vcap;
+    S* ps = reinterpret_cast<S*>(base);
+    vx = ps; ps += vcap;
+    vy = ps; ps += vcap;
+    vz = ps; ps += vcap;
+    dx = ps; ps += vcap;
+    dy = ps; ps += vcap;
+    dz = ps; ps += vcap;
+    vd = ps; ps += vcap;
+    e_d = ps; ps += ecap;
+    f_d = ps; ps += fcap;
+    uint16_t* p16 = reinterpret_cast<uint16_t*>(ps);
+    v_seq = p16; p16 += vcap;
+    v_newedge = p16; p16 += vcap;
+    e_v0 = p16; p16 += ecap;
+    e_v1 = p16; p16 += ecap;
+    e_f0 = p16; p16 += ecap;
+    e_f1 = p16; p16 += ecap;
+    e_seq = p16; p16 += ecap;
+    f_e0 = p16; p16 += fcap;
+    f_e1 = p16; p16 += fcap;
+    f_e2 = p16; p16 += fcap;
+    f_a = p16; p16 += fcap;
+    f_b = p16; p16 += fcap;
+    f_c = p16; p16 += fcap;
+    f_seq = p16; p16 += fcap;
+    uint8_t* p8 = reinterpret_cast<uint8_t*>(p16);
+    v_alive = p8; p8 += vcap;
+    v_rm = p8; p8 += vcap;
+    e_alive = p8; p8 += ecap;
+    e_in = p8; p8 += ecap;
+    e_vis = p8; p8 += ecap;
+    f_alive = p8; p8 += fcap;
+    f_in = p8; p8 += fcap;
+    f_vis = p8; p8 += fcap;
+  }
+  FCLB_DI V3<S> vloc(int i) const { return mk<S>(vx[i], vy[i], vz[i]); }
+  FCLB_DI V3<S> vdir(int i) const { return mk<S>(dx[i], dy[i], dz[i]); }
+};
+
+struct Feature {  // nearest feature: cls 0 vertex, 1 edge, 2 face; idx = slot; -1 none
+  int cls;
+  int idx;
+};
+
+template <typename S, typename MD>
+struct EpaWarp {
+  PolyStore<S> P;
+  const MD& shape;
+  const int lane;
+  int v_hw, e_hw, f_hw;     // high-water marks (slots ever used)
+  int v_n, e_n, f_n;        // alive counts
+  int v_sq, e_sq, f_sq;     // next sequence numbers
+  uint32_t* n_support;
+
+  FCLB_DI EpaWarp(const MD& sh, unsigned char* smem, int max_faces, int lane_, uint32_t* ns)
+      : shape(sh), lane(lane_), n_support(ns) {
+    P.bind(smem, max_faces);
+  }
+
+  FCLB_DI V3<S> support(const V3<S>& d) const {
+    if (n_support) *n_support += 2;
+    return shape.support(d);
+  }
+
+  // Polytope::Reset (epa_polytope.hpp:78-103)
+  FCLB_DI void reset() {
+    for (int i = lane; i < P.vcap; i += 32) P.v_alive[i] = 0;
+    for (int i = lane; i < P.ecap; i += 32) P.e_alive[i] = 0;
+    for (int i = lane; i < P.fcap; i += 32) P.f_alive[i] = 0;
+    v_hw = e_hw = f_hw = 0;
+    v_n = e_n = f_n = 0;
+    v_sq = e_sq = f_sq = 0;
+    __syncwarp();
+  }
+
+  // first dead slot of a pool (uniform result); -1 if the pool is full
+  FCLB_DI int allocSlot(const uint8_t* alive, int cap, int& hw) const {
+    if (hw < cap) return hw++;
+    for (int base = 0; base < cap; base += 32) {
+      const int i = base + lane;
+      const unsigned m = __ballot_sync(kFull, i < cap && !alive[i]);
+      if (m) return base + __ffs(m) - 1;
+    }
+    return -1;
+  }
+
+  // AddNewVertex (epa_polytope.hpp:185-209)
+  FCLB_DI int addVertex(const V3<S>& v, const V3<S>& d) {
+    const int s = allocSlot(P.v_alive, P.vcap, v_hw);
+    if (s < 0) return -1;
+    if (lane == 0) {
+      P.vx[s] = v.x; P.vy[s] = v.y; P.vz[s] = v.z;
+      P.dx[s] = d.x; P.dy[s] = d.y; P.dz[s] = d.z;
+      P.vd[s] = sqnorm(v);
+      P.v_seq[s] = uint16_t(v_sq);
+      P.v_alive[s] = 1;
+    }
+    v_sq++;
+    v_n++;
+    __syncwarp();
+    return s;
+  }
+  // topology part of AddNewEdge (:212-240); the distance record is filled by fillEdge
+  FCLB_DI int addEdgeTopo(int v1, int v2) {
+    if (v1 < 0 || v2 < 0) return -1;
+    const int s = allocSlot(P.e_alive, P.ecap, e_hw);
+    if (s < 0) return -1;
+    if (lane == 0) {
+      P.e_v0[s] = uint16_t(v1);
+      P.e_v1[s] = uint16_t(v2);
+      P.e_f0[s] = kNil;
+      P.e_f1[s] = kNil;
+      P.e_seq[s] = uint16_t(e_sq);
+      P.e_alive[s] = 1;
+      P.e_vis[s] = 0;
+    }
+    e_sq++;
+    e_n++;
+    __syncwarp();
+    return s;
+  }
+  FCLB_DI void fillEdge(int s) {  // any single lane
+    const MinDist<S> md = pointToSegment(zero3<S>(), P.vloc(P.e_v0[s]), P.vloc(P.e_v1[s]));
+    P.e_d[s] = md.dist_sq;
+    P.e_in[s] = md.in_simplex ? 1 : 0;
+  }
+  // topology part of AddNewFace (:243-290). Returns slot, or -1 (malloc / "wrong edge").
+  FCLB_DI int addFaceTopo(int e1, int e2, int e3) {
+    if (e1 < 0 || e2 < 0 || e3 < 0) return -1;
+    const int s = allocSlot(P.f_alive, P.fcap, f_hw);
+    if (s < 0) return -1;
+    bool ok = true;
+    if (lane == 0) {
+      const int a = P.e_v0[e1], b = P.e_v1[e1];
+      const int c = (P.e_v0[e2] != a && P.e_v0[e2] != b) ? P.e_v0[e2] : P.e_v1[e2];
+      P.f_e0[s] = uint16_t(e1);
+      P.f_e1[s] = uint16_t(e2);
+      P.f_e2[s] = uint16_t(e3);
+      P.f_a[s] = uint16_t(a);
+      P.f_b[s] = uint16_t(b);
+      P.f_c[s] = uint16_t(c);
+      P.f_seq[s] = uint16_t(f_sq);
+      P.f_alive[s] = 1;
+      P.f_vis[s] = 0;
+      const int es[3] = {e1, e2, e3};
+      for (int i = 0; i < 3 && ok; i++) {
+        if (P.e_f0[es[i]] == kNil) {
+          P.e_f0[es[i]] = uint16_t(s);
+        } else if (P.e_f1[es[i]] != kNil) {
+          ok = false;  // wrong connection at degeneration (:279-283)
+        } else {
+          P.e_f1[es[i]] = uint16_t(s);
+        }
+      }
+    }
+    ok = __shfl_sync(kFull, ok ? 1 : 0, 0) != 0;
+    f_sq++;
+    f_n++;
+    __syncwarp();
+    return ok ? s : -1;
+  }
+  FCLB_DI void fillFace(int s) {  // any single lane
+    const MinDist<S> md = pointToTriangle(zero3<S>(), P.vloc(P.f_a[s]), P.vloc(P.f_b[s]), P.vloc(P.f_c[s]));
+    P.f_d[s] = md.dist_sq;
+    P.f_in[s] = md.in_simplex ? 1 : 0;
+  }
+
+  // formNewTetrahedronPolytope (epa_simplex2polytope.hpp:177-215)
+  FCLB_DI bool formTetrahedron(const V3<S> v[4], const V3<S> d[4]) {
+    reset();
+    int vi[4];
+    for (int k = 0; k < 4; k++) vi[k] = addVertex(v[k], d[k]);
+    int e[6];
+    e[0] = addEdgeTopo(vi[0], vi[1]);
+    e[1] = addEdgeTopo(vi[1], vi[2]);
+    e[2] = addEdgeTopo(vi[2], vi[0]);
+    e[3] = addEdgeTopo(vi[3], vi[0]);
+    e[4] = addEdgeTopo(vi[3], vi[1]);
+    e[5] = addEdgeTopo(vi[3], vi[2]);
+    int f[4];
+    f[0] = addFaceTopo(e[0], e[1], e[2]);
+    f[1] = addFaceTopo(e[3], e[4], e[0]);
+    f[2] = addFaceTopo(e[4], e[5], e[1]);
+    f[3] = addFaceTopo(e[5], e[3], e[2]);
+    if (lane < 6 && e[lane] >= 0) fillEdge(e[lane]);
+    if (lane >= 8 && lane < 12 && f[lane - 8] >= 0) fillFace(f[lane - 8]);
+    __syncwarp();
+    for (int k = 0; k < 4; k++)
+      if (f[k] < 0) return false;
+    return true;
+  }
+
+  // extractTouchingPoint (epa_simplex2polytope.hpp:11-43)
+  FCLB_DI void touchingPoint(const V3<S>& dir, V3<S>& p0, V3<S>& p1) {
+    if (n_support) *n_support += 2;
+    const V3<S> mid = (shape.support0(dir) + shape.support1(-dir)) / S(2);
+    p0 = mid;
+    p1 = mid;
+  }
+
+  // simplexToPolytope3 (epa_simplex2polytope.hpp:135-175); 0 OK, 1 Touching, 2 Failed
+  FCLB_DI int simplexToPolytope3(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, const V3<S>& c,
+                                 const V3<S>& dc, S thr, V3<S>& p0, V3<S>& p1) {
+    const V3<S> ab = b - a, ac = c - a;
+    V3<S> n = cross(ab, ac);
+    if (sqnorm(n) <= S(0)) return 2;
+    n = normalized(n);
+    const V3<S> dir0 = n;
+    const V3<S> d0 = support(dir0);
+    const S d0_to_plane = pointToPlaneDistance(d0, a, b, c);
+    const V3<S> dir1 = -n;
+    const V3<S> d1 = support(dir1);
+    const S d1_to_plane = pointToPlaneDistance(d1, a, b, c);
+    if (d0_to_plane <= thr) {
+      touchingPoint(dir0, p0, p1);
+      return 1;
+    } else if (d1_to_plane <= thr) {
+      touchingPoint(dir1, p0, p1);
+      return 1;
+    }
+    V3<S> v[4] = {a, b, c, d0};
+    V3<S> d[4] = {da, db, dc, dir0};
+    if (!(d0_to_plane > d1_to_plane)) {
+      v[3] = d1;
+      d[3] = dir1;
+    }
+    return formTetrahedron(v, d) ? 0 : 2;
+  }
+
+  // simplexToPolytope2 (epa_simplex2polytope.hpp:218-380)
+  FCLB_DI int simplexToPolytope2(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, S thr, V3<S>& p0,
+                                 V3<S>& p1) {
+    const S thr_sq = thr * thr;
+    const V3<S> a_to_b = b - a;
+    if (sqnorm(a_to_b) < thr_sq) return 2;
+    const V3<S> u = normalized(a_to_b);
+    V3<S> d_init = mk<S>(u.y, -u.x, S(0));
+    bool valid = sqnorm(d_init) > thr_sq;
+    if (!valid) {
+      d_init = mk<S>(u.z, S(0), -u.x);
+      valid = sqnorm(d_init) > thr_sq;
+    }
+    if (!valid) {
+      d_init = mk<S>(S(0), u.z, -u.y);
+      valid = sqnorm(d_init) > thr_sq;
+    }
+    if (!valid) return 2;
+    d_init = normalized(d_init);
+    V3<S> d_cur = d_init, d_not = zero3<S>(), v_not = zero3<S>();
+    bool found = false;
+    for (int i = 0; i < 72; i++) {
+      const V3<S> v_cur = support(d_cur);
+      const S dist = pointToLineDistance(v_cur, a, b);
+      if (dist > thr) {
+        v_not = v_cur;
+        d_not = d_cur;
+        found = true;
+        break;
+      }
+      const S pi_value = S(3.145926);  // sic (epa_simplex2polytope.hpp:270)
+      const S delta_len = S(2.0) * pi_value / S(72);
+      const V3<S> delta = cross(u, v_cur);
+      d_cur = normalized(d_cur + delta_len * delta);
+    }
+    if (!found) {
+      touchingPoint(d_init, p0, p1);
+      return 1;
+    }
+    const V3<S> v0 = v_not, dir0 = d_not;
+    const V3<S> dir1 = -dir0;
+    const V3<S> v1 = support(dir1);
+    if (pointToLineDistance(v1, a, b) < thr) {
+      touchingPoint(dir1, p0, p1);
+      return 1;
+    }
+    const V3<S> nrm = cross(v0 - a, v1 - a);
+    if (sqnorm(nrm) < thr_sq) return 2;
+    const V3<S> dir2 = normalized(nrm);
+    const V3<S> v2 = support(dir2);
+    if (pointToLineDistance(v2, a, b) < thr) {
+      touchingPoint(dir2, p0, p1);
+      return 1;
+    }
+    const V3<S> dir3 = -dir2;
+    const V3<S> v3 = support(dir3);
+    if (pointToLineDistance(v3, a, b) < thr) {
+      touchingPoint(dir3, p0, p1);
+      return 1;
+    }
+    reset();
+    int v[6];
+    v[0] = addVertex(a, da);
+    v[1] = addVertex(v0, dir0);
+    v[2] = addVertex(b, db);
+    v[3] = addVertex(v1, dir1);
+    v[4] = addVertex(v2, dir2);
+    v[5] = addVertex(v3, dir3);
+    int e[12];
+    e[0] = addEdgeTopo(v[0], v[1]);
+    e[1] = addEdgeTopo(v[1], v[2]);
+    e[2] = addEdgeTopo(v[2], v[3]);
+    e[3] = addEdgeTopo(v[3], v[0]);
+    e[4] = addEdgeTopo(v[4], v[0]);
+    e[5] = addEdgeTopo(v[4], v[1]);
+    e[6] = addEdgeTopo(v[4], v[2]);
+    e[7] = addEdgeTopo(v[4], v[3]);
+    e[8] = addEdgeTopo(v[5], v[0]);
+    e[9] = addEdgeTopo(v[5], v[1]);
+    e[10] = addEdgeTopo(v[5], v[2]);
+    e[11] = addEdgeTopo(v[5], v[3]);
+    int f[8];
+    f[0] = addFaceTopo(e[4], e[5], e[0]);
+    f[1] = addFaceTopo(e[5], e[6], e[1]);
+    f[2] = addFaceTopo(e[6], e[7], e[2]);
+    f[3] = addFaceTopo(e[7], e[4], e[3]);
+    f[4] = addFaceTopo(e[8], e[9], e[0]);
+    f[5] = addFaceTopo(e[9], e[10], e[1]);
+    f[6] = addFaceTopo(e[10], e[11], e[2]);
+    f[7] = addFaceTopo(e[11], e[8], e[3]);
+    if (lane < 12 && e[lane] >= 0) fillEdge(e[lane]);
+    if (lane >= 16 && lane < 24 && f[lane - 16] >= 0) fillFace(f[lane - 16]);
+    __syncwarp();
+    for (int k = 0; k < 8; k++)
+      if (f[k] < 0) return 2;
+    return 0;
+  }
+
+  // simplexToPolytope (epa_simplex2polytope.hpp:46-133)
+  FCLB_DI int simplexToPolytope(const SlotStore<S>& st, const Simp& sx, S thr, V3<S>& p0, V3<S>& p1) {
+    const S thr_sq = thr * thr;
+    V3<S> v[4], d[4];
+    for (int i = 0; i < 4; i++) {
+      v[i] = zero3<S>();
+      d[i] = zero3<S>();
+    }
+    for (int i = 0; i < sx.rank; i++) {
+      v[i] = st.vtx(slotOf(sx, i));
+      d[i] = st.dir(slotOf(sx, i));
+    }
+    for (int i = 0; i < sx.rank; i++) {
+      if (sqnorm(v[i]) <= thr_sq) {
+        touchingPoint(d[i], p0, p1);
+        return 1;
+      }
+    }
+    if (sx.rank == 4) {  // simplexToPolytope4 :96-133
+      const V3<S> o = zero3<S>();
+      if (pointToPlaneDistance(o, v[0], v[1], v[2]) < thr)
+        return simplexToPolytope3(v[0], d[0], v[1], d[1], v[2], d[2], thr, p0, p1);
+      if (pointToPlaneDistance(o, v[0], v[2], v[3]) < thr)
+        return simplexToPolytope3(v[0], d[0], v[2], d[2], v[3], d[3], thr, p0, p1);
+      if (pointToPlaneDistance(o, v[0], v[1], v[3]) < thr)
+        return simplexToPolytope3(v[0], d[0], v[1], d[1], v[3], d[3], thr, p0, p1);
+      if (pointToPlaneDistance(o, v[1], v[2], v[3]) < thr)
+        return simplexToPolytope3(v[1], d[1], v[2], d[2], v[3], d[3], thr, p0, p1);
+      return formTetrahedron(v, d) ? 0 : 2;
+    } else if (sx.rank == 3) {
+      return simplexToPolytope3(v[0], d[0], v[1], d[1], v[2], d[2], thr, p0, p1);
+    } else if (sx.rank == 2) {
+      return simplexToPolytope2(v[0], d[0], v[1], d[1], thr, p0, p1);
+    }
+    if (n_support) *n_support += 2;
+    p0 = shape.support0(d[0]);
+    p1 = shape.support1(-d[0]);
+    return 1;
+  }
+
+  // ---- nearest feature ------------------------------------------------------
+  // ComputeMinDistanceToOrigin (epa_polytope.hpp:295-345): sequential scan with a
+  // strict "<" over vertices, edges, faces (each newest first).  Equivalent key:
+  // smaller distance, then smaller class, then larger sequence number.
+  static FCLB_DI bool better(S d, int cls, int seq, S bd, int bcls, int bseq) {
+    if (d < bd) return true;
+    if (d > bd) return false;
+    if (cls != bcls) return cls < bcls;
+    return seq > bseq;
+  }
+  FCLB_DI Feature nearest(bool exclude_vertex) const {
+    S bd = S(INFINITY);
+    int bcls = 3, bseq = -1, bidx = -1;
+    if (!exclude_vertex) {
+      for (int i = lane; i < v_hw; i += 32) {
+        if (!P.v_alive[i]) continue;
+        const S d = P.vd[i];
+        if (d < S(INFINITY) && better(d, 0, P.v_seq[i], bd, bcls, bseq)) {
+          bd = d; bcls = 0; bseq = P.v_seq[i]; bidx = i;
+        }
+      }
+    }
+    for (int i = lane; i < e_hw; i += 32) {
+      if (!P.e_alive[i]) continue;
+      if (!exclude_vertex && !P.e_in[i]) continue;
+      const S d = P.e_d[i];
+      if (d < S(INFINITY) && better(d, 1, P.e_seq[i], bd, bcls, bseq)) {
+        bd = d; bcls = 1; bseq = P.e_seq[i]; bidx = i;
+      }
+    }
+    for (int i = lane; i < f_hw; i += 32) {
+      if (!P.f_alive[i] || !P.f_in[i]) continue;
+      const S d = P.f_d[i];
+      if (d < S(INFINITY) && better(d, 2, P.f_seq[i], bd, bcls, bseq)) {
+        bd = d; bcls = 2; bseq = P.f_seq[i]; bidx = i;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const S od = __shfl_xor_sync(kFull, bd, off);
+      const int ocls = __shfl_xor_sync(kFull, bcls, off);
+      const int oseq = __shfl_xor_sync(kFull, bseq, off);
+      const int oidx = __shfl_xor_sync(kFull, bidx, off);
+      if (oidx >= 0 && (bidx < 0 || better(od, ocls, oseq, bd, bcls, bseq))) {
+        bd = od; bcls = ocls; bseq = oseq; bidx = oidx;
+      }
+    }
+    Feature f;
+    f.cls = bcls;
+    f.idx = bidx;
+    return f;
+  }
+
+  // ComputeFaceNormalPointingOutward (epa_polytope.hpp:348-410).  `par`: the
+  // caller is warp-uniform and the rare all-vertex pass may use all lanes.
+  FCLB_DI bool faceNormal(int f, V3<S>& normal, S* area, bool par) const {
+    const V3<S> a = P.vloc(P.f_a[f]), b = P.vloc(P.f_b[f]), c = P.vloc(P.f_c[f]);
+    const V3<S> e1 = a - b, e2 = b - c;
+    const V3<S> cr = cross(e1, e2);
+    const S nrm = norm(cr);
+    if (area) *area = S(0.5) * nrm;
+    if (nrm <= S(0)) return false;
+    const V3<S> dir = cr / nrm;
+    const S o_to_a_dot_n = dot(a, dir);
+    if (fabs_(o_to_a_dot_n) >= S(1e-4)) {
+      normal = (o_to_a_dot_n > 0) ? dir : -dir;
+      return true;
+    }
+    S max_pos = S(0), min_neg = S(0);
+    if (par) {
+      for (int i = lane; i < v_hw; i += 32) {
+        if (!P.v_alive[i]) continue;
+        const S dv = dot(P.vloc(i), dir);
+        if (dv > max_pos) max_pos = dv;
+        if (dv < min_neg) min_neg = dv;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const S om = __shfl_xor_sync(kFull, max_pos, off);
+        const S on = __shfl_xor_sync(kFull, min_neg, off);
+        if (om > max_pos) max_pos = om;
+        if (on < min_neg) min_neg = on;
+      }
+    } else {
+      for (int i = 0; i < v_hw; i++) {
+        if (!P.v_alive[i]) continue;
+        const S dv = dot(P.vloc(i), dir);
+        if (dv > max_pos) max_pos = dv;
+        if (dv < min_neg) min_neg = dv;
+      }
+    }
+    normal = (fabs_(max_pos) > fabs_(min_neg)) ? -dir : dir;
+    return true;
+  }
+  // IsPointOutsidePolytopeFace (epa_polytope_expand.hpp:13-31), threshold 0
+  FCLB_DI bool pointOutsideFace(int f, const V3<S>& pt, bool par) const {
+    V3<S> n;
+    S area = S(0);
+    if (!faceNormal(f, n, &area, par)) return area <= S(0);
+    const V3<S> on_face = P.vloc(P.f_a[f]);
+    return dot(n, pt - on_face) >= S(0);
+  }
+
+  // findNextSupportDirection (epa.hpp:11-113): 0 OK, 1 Failed, 2 Converge
+  FCLB_DI int faceCandidate(int f, bool try_witness, const V3<S>& witness, S dist_sq, S tol, V3<S>& next_d, V3<S>& next_v,
+                            int& start_face) {
+    const S outer_thr = S(1e-3) * S(1e-3);
+    V3<S> fn;
+    if (!faceNormal(f, fn, nullptr, true)) return 1;
+    const V3<S> on_face = P.vloc(P.f_a[f]);
+    if (try_witness && dist_sq > outer_thr) {
+      next_d = normalized(witness);
+      next_v = support(next_d);
+      const S delta = dot(fn, next_v - on_face);
+      if (delta >= S(0)) {
+        start_face = f;
+        return 0;
+      }
+    }
+    next_d = fn;
+    next_v = support(next_d);
+    const S delta = dot(fn, next_v - on_face);
+    if (delta > tol) {
+      start_face = f;
+      return 0;
+    }
+    return 2;
+  }
+
+  // ExpandPolytope (epa_polytope_expand.hpp:33-91): 0 OK, 1 Failed, 2 MallocFailed
+  FCLB_DI int expand(const V3<S>& nv, const V3<S>& nd, int start_face) {
+    // initVisibilityCacheVariables + visibility predicate of EVERY face
+    for (int i = lane; i < v_hw; i += 32) {
+      P.v_rm[i] = 1;
+      P.v_newedge[i] = kNil;
+    }
+    for (int i = lane; i < e_hw; i += 32) P.e_vis[i] = 0;
+    for (int i = lane; i < f_hw; i += 32) {
+      if (!P.f_alive[i]) continue;
+      P.f_vis[i] = pointOutsideFace(i, nv, false) ? 3 : 2;  // 3 = outside (not reached yet), 2 = hidden
+    }
+    __syncwarp();
+    if (lane == 0) P.f_vis[start_face] = 1;  // the start face is visible by construction (:133)
+    __syncwarp();
+    // grow the visible patch: a face joins when it is "outside" and shares an
+    // edge with a patch face (computeVisiblePatch, :121-180)
+    bool broken = false;
+    while (true) {
+      bool changed = false;
+      for (int i = lane; i < f_hw; i += 32) {
+        if (!P.f_alive[i] || P.f_vis[i] != 1) continue;
+        const int es[3] = {P.f_e0[i], P.f_e1[i], P.f_e2[i]};
+        for (int k = 0; k < 3; k++) {
+          const int e = es[k];
+          const int g = (P.e_f0[e] == i) ? P.e_f1[e] : P.e_f0[e];
+          if (g == kNil) {
+            broken = true;
+            continue;
+          }
+          if (P.f_vis[g] == 3) {
+            P.f_vis[g] = 1;
+            changed = true;
+          }
+        }
+      }
+      __syncwarp();
+      if (!__any_sync(kFull, changed)) break;
+    }
+    if (__any_sync(kFull, broken)) return 1;
+    // edge classification + vertex keep flags (updateVertexRemoveFlag, :183-205)
+    for (int i = lane; i < e_hw; i += 32) {
+      if (!P.e_alive[i]) continue;
+      const int f0 = P.e_f0[i], f1 = P.e_f1[i];
+      const bool in0 = (f0 != kNil) && P.f_vis[f0] == 1;
+      const bool in1 = (f1 != kNil) && P.f_vis[f1] == 1;
+      const uint8_t vis = (in0 && in1) ? 2 : ((in0 || in1) ? 1 : 0);
+      P.e_vis[i] = vis;
+      if (vis != 2) {
+        P.v_rm[P.e_v0[i]] = 0;
+        P.v_rm[P.e_v1[i]] = 0;
+      }
+    }
+    __syncwarp();
+    // removeAccordingToVisibility (:244-281)
+    int rm_f = 0, rm_e = 0, rm_v = 0;
+    for (int i = lane; i < e_hw; i += 32) {
+      if (!P.e_alive[i]) continue;
+      if (P.e_vis[i] == 2) {
+        P.e_alive[i] = 0;
+        rm_e++;
+      } else if (P.e_vis[i] == 1) {
+        // drop the reference to the removed face, keep the hidden one in f0
+        const int f0 = P.e_f0[i], f1 = P.e_f1[i];
+        const bool in0 = (f0 != kNil) && P.f_vis[f0] == 1;
+        P.e_f0[i] = in0 ? uint16_t(f1) : uint16_t(f0);
+        P.e_f1[i] = kNil;
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < f_hw; i += 32) {
+      if (P.f_alive[i] && P.f_vis[i] == 1) {
+        P.f_alive[i] = 0;
+        rm_f++;
+      }
+    }
+    for (int i = lane; i < v_hw; i += 32) {
+      if (P.v_alive[i] && P.v_rm[i]) {
+        P.v_alive[i] = 0;
+        rm_v++;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      rm_f += __shfl_xor_sync(kFull, rm_f, off);
+      rm_e += __shfl_xor_sync(kFull, rm_e, off);
+      rm_v += __shfl_xor_sync(kFull, rm_v, off);
+    }
+    f_n -= rm_f;
+    e_n -= rm_e;
+    v_n -= rm_v;
+    __syncwarp();
+
+    const int new_v = addVertex(nv, nd);
+    if (new_v < 0) return 2;
+
+    // border edges in list order (newest first): repeatedly take the alive border
+    // edge with the largest sequence number below the previous one
+    bool ok = true;
+    int prev_seq = 0x7fffffff;
+    int first_new_e = -1, first_new_f = -1;
+    int made_e[2];
+    while (true) {
+      int best_seq = -1, best_idx = -1;
+      for (int i = lane; i < e_hw; i += 32) {
+        if (P.e_alive[i] && P.e_vis[i] == 1) {
+          const int sq = P.e_seq[i];
+          if (sq < prev_seq && sq > best_seq) {
+            best_seq = sq;
+            best_idx = i;
+          }
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const int os = __shfl_xor_sync(kFull, best_seq, off);
+        const int oi = __shfl_xor_sync(kFull, best_idx, off);
+        if (os > best_seq) {
+          best_seq = os;
+          best_idx = oi;
+        }
+      }
+      if (best_idx < 0) break;
+      prev_seq = best_seq;
+      const int edge = best_idx;
+      // the two side edges (new_v, v_i), created on first use (:62-70)
+      for (int k = 0; k < 2; k++) {
+        const int vi = (k == 0) ? P.e_v0[edge] : P.e_v1[edge];
+        int ne = P.v_newedge[vi];
+        if (ne == kNil) {
+          ne = addEdgeTopo(new_v, vi);
+          if (ne >= 0) {
+            if (lane == 0) {
+              P.v_newedge[vi] = uint16_t(ne);
+              P.e_vis[ne] = 3;  // freshly made: distance record pending, not a border edge
+            }
+            if (first_new_e < 0) first_new_e = ne;
+            __syncwarp();
+          } else {
+            ne = -1;
+          }
+        }
+        made_e[k] = (ne == kNil) ? -1 : ne;
+      }
+      const int nf = addFaceTopo(edge, made_e[0], made_e[1]);
+      if (nf < 0) {
+        ok = false;  // keep walking like the reference does; the result is MallocFailed
+      } else {
+        if (lane == 0) P.f_vis[nf] = 4;  // distance record pending
+        if (first_new_f < 0) first_new_f = nf;
+        __syncwarp();
+      }
+    }
+    (void)first_new_e;
+    (void)first_new_f;
+    // distance records of the new cone, one element per lane
+    for (int i = lane; i < e_hw; i += 32) {
+      if (P.e_alive[i] && P.e_vis[i] == 3) {
+        fillEdge(i);
+        P.e_vis[i] = 0;
+      }
+    }
+    for (int i = lane; i < f_hw; i += 32) {
+      if (P.f_alive[i] && P.f_vis[i] == 4) {
+        fillFace(i);
+        P.f_vis[i] = 0;
+      }
+    }
+    __syncwarp();
+    return ok ? 0 : 2;
+  }
+
+  struct RawFeature {  // epa.h:70-74
+    int cls;
+    MinDist<S> md;
+    V3<S> a, b, c, da, db, dc;
+  };
+
+  // assignPenetrationPairFromSegment (epa.hpp:377-433)
+  FCLB_DI bool pairFromSegment(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
+    depth = fsqrt(f.md.dist_sq);
+    const V3<S> p = f.md.witness;
+    const V3<S> a_to_b = f.b - f.a;
+    int mx = 0;
+    S mxd = fabs_(a_to_b.x);
+    if (fabs_(a_to_b.y) > mxd) {
+      mx = 1;
+      mxd = fabs_(a_to_b.y);
+    }
+    if (fabs_(a_to_b.z) > mxd) {
+      mx = 2;
+      mxd = fabs_(a_to_b.z);
+    }
+    if (double(mxd) <= 1e-10) {
+      if (n_support) *n_support += 2;
+      p0 = shape.support0(f.da);
+      p1 = shape.support1(-f.da);
+      return true;
+    }
+    const S s = (comp(p, mx) - comp(f.a, mx)) / (comp(f.b, mx) - comp(f.a, mx));
+    if (s < 0 || s > S(1.0)) return false;
+    const S aw = S(1.0) - s, bw = s;
+    if (n_support) *n_support += 4;
+    p0 = aw * shape.support0(f.da) + bw * shape.support0(f.db);
+    p1 = aw * shape.support1(-f.da) + bw * shape.support1(-f.db);
+    return true;
+  }
+  // assignPenetrationPairFromFace (epa.hpp:436-497)
+  FCLB_DI bool pairFromFace(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
+    depth = fsqrt(f.md.dist_sq);
+    const V3<S> p = f.md.witness;
+    const V3<S> dl0 = f.a - f.b, dl1 = f.b - f.c, dl2 = f.c - f.a;
+    const V3<S> n = cross(dl0, dl1);
+    const S area = fsqrt(sqnorm(n));
+    const S w0 = norm(cross(dl1, f.b - p)) / area;
+    const S w1 = norm(cross(dl2, f.c - p)) / area;
+    const S w2_check = norm(cross(dl0, f.a - p)) / area;
+    const S w2 = S(1.0) - w0 - w1;
+    if (fabs_(w2_check - w2) > S(0.01)) return false;
+    if (n_support) *n_support += 6;
+    p0 = w0 * shape.support0(f.da) + w1 * shape.support0(f.db) + w2 * shape.support0(f.dc);
+    p1 = w0 * shape.support1(-f.da) + w1 * shape.support1(-f.db) + w2 * shape.support1(-f.dc);
+    return true;
+  }
+  // assignPenetrationPair (epa.hpp:341-375)
+  FCLB_DI void assignPair(const V3<S>& cand_d, const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
+    if (f.cls == 0) {
+      if (n_support) *n_support += 2;
+      p0 = shape.support0(f.da);
+      p1 = shape.support1(-f.da);
+      depth = norm(f.a);
+      return;
+    } else if (f.cls == 1) {
+      if (pairFromSegment(f, depth, p0, p1)) return;
+    } else if (f.cls == 2) {
+      if (pairFromFace(f, depth, p0, p1)) return;
+    }
+    if (n_support) *n_support += 2;
+    p0 = shape.support0(cand_d);
+    p1 = shape.support1(-cand_d);
+    depth = norm(p0 - p1);
+  }
+
+  // checkTerminateCondition (epa.hpp:269-298)
+  FCLB_DI bool converged(const RawFeature& f, const V3<S>& new_v, S tol) const {
+    S delta_sq;
+    if (f.cls == 1) {
+      delta_sq = pointToSegment(new_v, f.a, f.b).dist_sq;
+    } else {
+      const S d = pointToPlaneDistance(new_v, f.a, f.b, f.c);
+      delta_sq = d * d;
+    }
+    return delta_sq < tol * tol;
+  }
+
+  // evaluateFromInitializedPolytope (epa.hpp:137-237)
+  FCLB_DI int run(int max_iterations, S tol, S& depth, V3<S>& p0, V3<S>& p1) {
+    int iteration = 0;
+    while (true) {
+      Feature nf = nearest(false);
+      if (nf.idx < 0) return EPA_FAILED;
+      if (nf.cls == 0) {
+        const S vdist = P.vd[nf.idx];
+        const S ratio = S(1) - S(1e-3);
+        const Feature other = nearest(true);
+        if (other.idx < 0) return EPA_FAILED;
+        if (other.cls == 1) {
+          if (ratio * P.e_d[other.idx] < vdist) nf = other;
+        } else if (other.cls == 2) {
+          if (ratio * P.f_d[other.idx] < vdist) nf = other;
+        }
+      }
+      if (nf.cls != 1 && nf.cls != 2) return EPA_FAILED;
+
+      // transformToRawFeature (epa.hpp:301-338); the witness is recomputed from the
+      // stored vertex order (a pure function of it)
+      RawFeature raw;
+      raw.cls = nf.cls;
+      raw.c = zero3<S>();
+      raw.dc = zero3<S>();
+      if (nf.cls == 1) {
+        const int a = P.e_v0[nf.idx], b = P.e_v1[nf.idx];
+        raw.a = P.vloc(a);
+        raw.b = P.vloc(b);
+        raw.da = P.vdir(a);
+        raw.db = P.vdir(b);
+        raw.md = pointToSegment(zero3<S>(), raw.a, raw.b);
+      } else {
+        const int a = P.f_a[nf.idx], b = P.f_b[nf.idx], c = P.f_c[nf.idx];
+        raw.a = P.vloc(a);
+        raw.b = P.vloc(b);
+        raw.c = P.vloc(c);
+        raw.da = P.vdir(a);
+        raw.db = P.vdir(b);
+        raw.dc = P.vdir(c);
+        raw.md = pointToTriangle(zero3<S>(), raw.a, raw.b, raw.c);
+      }
+
+      V3<S> next_d = zero3<S>(), next_v = zero3<S>();
+      int start_face = -1;
+      int ds;
+      if (nf.cls == 2) {
+        ds = faceCandidate(nf.idx, true, raw.md.witness, raw.md.dist_sq, tol, next_d, next_v, start_face);
+      } else {
+        const S outer_thr = S(1e-3) * S(1e-3);
+        const int f0 = P.e_f0[nf.idx], f1 = P.e_f1[nf.idx];
+        bool decided = false;
+        ds = 1;
+        if (raw.md.dist_sq > outer_thr) {
+          next_d = normalized(raw.md.witness);
+          next_v = support(next_d);
+          if (f0 != kNil && pointOutsideFace(f0, next_v, true)) {
+            start_face = f0;
+            ds = 0;
+            decided = true;
+          } else if (f1 != kNil && pointOutsideFace(f1, next_v, true)) {
+            start_face = f1;
+            ds = 0;
+            decided = true;
+          }
+        }
+        if (!decided) {
+          if (f0 == kNil || f1 == kNil) return EPA_FAILED;
+          ds = faceCandidate(f0, false, raw.md.witness, raw.md.dist_sq, tol, next_d, next_v, start_face);
+          if (ds != 0) ds = faceCandidate(f1, false, raw.md.witness, raw.md.dist_sq, tol, next_d, next_v, start_face);
+        }
+      }
+      if (ds == 1) return EPA_FAILED;
+      if (ds == 2) {
+        assignPair(next_d, raw, depth, p0, p1);
+        return EPA_OK;
+      }
+      if (start_face < 0) return EPA_FAILED;
+      if (converged(raw, next_v, tol)) {
+        assignPair(next_d, raw, depth, p0, p1);
+        return EPA_OK;
+      }
+      const int es = expand(next_v, next_d, start_face);
+      if (es == 1) return EPA_FAILED;
+      if (es == 2) {
+        assignPair(next_d, raw, depth, p0, p1);
+        return EPA_MALLOC_FAILED;
+      }
+      iteration += 1;
+      if (iteration >= max_iterations) {
+        assignPair(next_d, raw, depth, p0, p1);
+        return EPA_ITER_LIMIT;
+      }
+    }
+  }
+
+  // EPA::Evaluate (epa.hpp:240-256) via evaluateFromUnInitializedPolytope (:116-135)
+  FCLB_DI int evaluate(const SlotStore<S>& st, const Simp& sx, int max_iterations, S tol, S& depth, V3<S>& p0,
+                       V3<S>& p1) {
+    reset();
+    const int s2p = simplexToPolytope(st, sx, tol, p0, p1);
+    if (s2p == 2) return EPA_FAILED;
+    if (s2p == 1) {
+      depth = S(0);
+      return EPA_TOUCHING;
+    }
+    return run(max_iterations, tol, depth, p0, p1);
+  }
+};
+
+}  // namespace fclb
