@@ -154,6 +154,33 @@ int fclb_gjk_epa_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const voi
                            size_t n, int scalar_type, const fclb_request* req, int32_t* out_gjk, int32_t* out_epa,
                            void* out_geom);
 
+/* ---- meshes: BVHModel<OBBRSS<S>> flattened by the caller ------------------------
+ * (reference geometry/bvh/BVH_model.h:63-196, BV_node_base.h:50-82).  Only the
+ * OBB half of OBBRSS is ever read by collide (math/bv/OBBRSS-inl.h:130-135).
+ *   obb         15 S per node: axis 3x3 row-major (axis(i,j)), To xyz, extent xyz
+ *   first_child BVNodeBase::first_child per node (>0: children at fc, fc+1;
+ *               <0: leaf holding primitive -(fc+1)); node 0 is the root
+ *   tri_verts   9 S per triangle, indexed by primitive id
+ * The tree is built on the host by the caller (mind-fcl's own builder in an
+ * integration); the device copy is immutable. */
+int fclb_bvh_upload(const void* obb, const int32_t* first_child, int n_nodes, const void* tri_verts, int n_tris,
+                    int scalar_type, fclb_handle* bvh);
+int fclb_bvh_release(fclb_handle bvh);
+/* fcl::collide(BVHModel<OBBRSS>, tf1, BVHModel<OBBRSS>, tf2, request, result) per query
+ * (-> OrientedNodeBVHSolver::MeshIntersect, traversal/collision/bvh_solver-inl.h:75).
+ * request.penetration_mode must be FCLB_PEN_DISABLED (boolean / counting collide):
+ *   out_counts[q]   = result.numContacts() = min(#intersecting triangle pairs, max_contacts)
+ *   out_first_pair  = (b1, b2) of ONE colliding triangle pair or (-1,-1); optional.
+ *                     Not necessarily the pair the reference's DFS reports first. */
+int fclb_bvh_collide_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+                                int scalar_type, const fclb_request* req, uint32_t* out_counts,
+                                int32_t* out_first_pair);
+int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+                               int scalar_type, const fclb_request* req, uint32_t* out_counts,
+                               int32_t* out_first_pair);
+/* BV-pair and leaf-pair tests executed by the most recent mesh batch call */
+int fclb_bvh_last_visit_counts(uint64_t* n_bv, uint64_t* n_leaf);
+
 /* kernel launches issued by this process so far (bench.py's gpu_launches) */
 uint64_t fclb_launch_count(void);
 /* device time (ms, CUDA events on the engine's stream) of the most recent batch

@@ -1,0 +1,529 @@
+// fclb_bvh.cu -- batched mesh-mesh collide over flattened BVHModel<OBBRSS>
+// trees: ONE WARP PER QUERY (relative pose).
+//
+// Reference path (results contract):
+//   fcl::collide(BVH, BVH) -> BVHCollide<OBBRSS> -> OrientedNodeBVHSolver::MeshIntersect
+//     narrowphase/detail/traversal/collision/bvh_solver-inl.h:75-160
+//   overlap(R, T, OBBRSS, OBBRSS) -> OBB only (math/bv/OBBRSS-inl.h:130-135)
+//     -> overlap(R0,T0,b1,b2) + obbDisjoint (math/bv/OBB-inl.h:305-436)
+//   leaf: SimplexIntersect -> trianglePairIntersect -> Intersect::intersect_Triangle
+//     (shape_pair_intersect-inl.h:201-270; traversal/collision/intersect-inl.h:594-612,724-845)
+//   relativeTransform (math/geometry-inl.h:409-435)
+//
+// The reference walks ONE (node,node) pair at a time from a std::stack (DFS).
+// The boolean result and the number of intersecting triangle pairs do not
+// depend on the visiting order, so here a warp owns the query and
+//   * keeps the pair stack in shared memory and pops up to 32 pairs per step,
+//     one per lane (adaptive: near capacity it degrades to 1-wide DFS);
+//   * every lane fetches its two 64-byte nodes with four 128-bit loads each
+//     (128-byte nodes / eight loads in double) and runs the 15-axis OBB test;
+//   * surviving pairs are expanded and pushed back with ballot + popc prefix
+//     sums; leaf pairs go to a separate shared-memory queue and the 17-axis
+//     triangle test runs on full batches of 32 (the "leaf stage");
+//   * a hit is reduced with a warp ballot: boolean queries stop at once,
+//     counting queries add popc(ballot) until max_contacts is reached.
+// Which contact is reported first for max_contacts == 1 is therefore NOT the
+// reference's DFS-first pair (SURVEY.md 7 "Traversal-order-dependent outputs");
+// out_first_pair holds *a* colliding triangle pair.
+#include <cstdio>
+#include <vector>
+
+#include "fclb_engine.h"
+#include "fclb_math.cuh"
+
+namespace fclb {
+
+struct BvhDev {
+  void* nodes = nullptr;  // 16 S per node: axis[9] row-major, To[3], extent[3], first_child bits
+  void* tris = nullptr;   // 12 S per triangle (3 x {x,y,z,pad})
+  int n_nodes = 0, n_tris = 0;
+  int scalar_type = 0;
+};
+
+static std::map<fclb_handle, BvhDev*>& bvhTable() {
+  static std::map<fclb_handle, BvhDev*> t;
+  return t;
+}
+
+template <typename S>
+struct NodeD {
+  M3<S> axis;
+  V3<S> To, extent;
+  int first_child;
+};
+
+FCLB_DI NodeD<float> loadNode(const float* __restrict__ base, int i) {
+  const float4* p = reinterpret_cast<const float4*>(base) + 4 * size_t(i);
+  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+  NodeD<float> n;
+  n.axis.m[0] = a.x; n.axis.m[1] = a.y; n.axis.m[2] = a.z; n.axis.m[3] = a.w;
+  n.axis.m[4] = b.x; n.axis.m[5] = b.y; n.axis.m[6] = b.z; n.axis.m[7] = b.w;
+  n.axis.m[8] = c.x;
+  n.To = mk<float>(c.y, c.z, c.w);
+  n.extent = mk<float>(d.x, d.y, d.z);
+  n.first_child = __float_as_int(d.w);
+  return n;
+}
+FCLB_DI NodeD<double> loadNode(const double* __restrict__ base, int i) {
+  const double2* p = reinterpret_cast<const double2*>(base) + 8 * size_t(i);
+  double2 v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) v[k] = __ldg(p + k);
+  NodeD<double> n;
+  n.axis.m[0] = v[0].x; n.axis.m[1] = v[0].y; n.axis.m[2] = v[1].x; n.axis.m[3] = v[1].y;
+  n.axis.m[4] = v[2].x; n.axis.m[5] = v[2].y; n.axis.m[6] = v[3].x; n.axis.m[7] = v[3].y;
+  n.axis.m[8] = v[4].x;
+  n.To = mk<double>(v[4].y, v[5].x, v[5].y);
+  n.extent = mk<double>(v[6].x, v[6].y, v[7].x);
+  n.first_child = int(__double_as_longlong(v[7].y));
+  return n;
+}
+FCLB_DI void loadTri(const float* __restrict__ base, int t, V3<float> p[3]) {
+  const float4* q = reinterpret_cast<const float4*>(base) + 3 * size_t(t);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float4 v = __ldg(q + k);
+    p[k] = mk<float>(v.x, v.y, v.z);
+  }
+}
+FCLB_DI void loadTri(const double* __restrict__ base, int t, V3<double> p[3]) {
+  const double2* q = reinterpret_cast<const double2*>(base) + 6 * size_t(t);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double2 a = __ldg(q + 2 * k), b = __ldg(q + 2 * k + 1);
+    p[k] = mk<double>(a.x, a.y, b.x);
+  }
+}
+
+// obbDisjoint (math/bv/OBB-inl.h:319-436): 15-axis SAT, reps added to |B|
+template <typename S>
+FCLB_DI bool obbDisjoint(const M3<S>& B, const V3<S>& T, const V3<S>& a, const V3<S>& b) {
+  S t, s;
+  const S reps = S(1e-6);
+  M3<S> Bf;
+#pragma unroll
+  for (int i = 0; i < 9; i++) Bf.m[i] = fabs_(B.m[i]) + reps;
+  t = (T.x < 0) ? -T.x : T.x;
+  if (t > (a.x + dot(row(Bf, 0), b))) return true;
+  s = dot(col(B, 0), T);
+  t = (s < 0) ? -s : s;
+  if (t > (b.x + dot(col(Bf, 0), a))) return true;
+  t = (T.y < 0) ? -T.y : T.y;
+  if (t > (a.y + dot(row(Bf, 1), b))) return true;
+  t = (T.z < 0) ? -T.z : T.z;
+  if (t > (a.z + dot(row(Bf, 2), b))) return true;
+  s = dot(col(B, 1), T);
+  t = (s < 0) ? -s : s;
+  if (t > (b.y + dot(col(Bf, 1), a))) return true;
+  s = dot(col(B, 2), T);
+  t = (s < 0) ? -s : s;
+  if (t > (b.z + dot(col(Bf, 2), a))) return true;
+#define FCLB_OBB_EDGE(SEXPR, RAD) \
+  s = (SEXPR);                    \
+  t = (s < 0) ? -s : s;           \
+  if (t > (RAD)) return true;
+  FCLB_OBB_EDGE(T.z * B(1, 0) - T.y * B(2, 0), a.y * Bf(2, 0) + a.z * Bf(1, 0) + b.y * Bf(0, 2) + b.z * Bf(0, 1))
+  FCLB_OBB_EDGE(T.z * B(1, 1) - T.y * B(2, 1), a.y * Bf(2, 1) + a.z * Bf(1, 1) + b.x * Bf(0, 2) + b.z * Bf(0, 0))
+  FCLB_OBB_EDGE(T.z * B(1, 2) - T.y * B(2, 2), a.y * Bf(2, 2) + a.z * Bf(1, 2) + b.x * Bf(0, 1) + b.y * Bf(0, 0))
+  FCLB_OBB_EDGE(T.x * B(2, 0) - T.z * B(0, 0), a.x * Bf(2, 0) + a.z * Bf(0, 0) + b.y * Bf(1, 2) + b.z * Bf(1, 1))
+  FCLB_OBB_EDGE(T.x * B(2, 1) - T.z * B(0, 1), a.x * Bf(2, 1) + a.z * Bf(0, 1) + b.x * Bf(1, 2) + b.z * Bf(1, 0))
+  FCLB_OBB_EDGE(T.x * B(2, 2) - T.z * B(0, 2), a.x * Bf(2, 2) + a.z * Bf(0, 2) + b.x * Bf(1, 1) + b.y * Bf(1, 0))
+  FCLB_OBB_EDGE(T.y * B(0, 0) - T.x * B(1, 0), a.x * Bf(1, 0) + a.y * Bf(0, 0) + b.y * Bf(2, 2) + b.z * Bf(2, 1))
+  FCLB_OBB_EDGE(T.y * B(0, 1) - T.x * B(1, 1), a.x * Bf(1, 1) + a.y * Bf(0, 1) + b.x * Bf(2, 2) + b.z * Bf(2, 0))
+  FCLB_OBB_EDGE(T.y * B(0, 2) - T.x * B(1, 2), a.x * Bf(1, 2) + a.y * Bf(0, 2) + b.x * Bf(2, 1) + b.y * Bf(2, 0))
+#undef FCLB_OBB_EDGE
+  return false;
+}
+
+// overlap(R0, T0, b1, b2) (math/bv/OBB-inl.h:305-316)
+template <typename S>
+FCLB_DI bool obbOverlap(const M3<S>& R0, const V3<S>& T0, const NodeD<S>& b1, const NodeD<S>& b2) {
+  const M3<S> R0b2 = mulMM(R0, b2.axis);
+  const M3<S> R = mulMtM(b1.axis, R0b2);
+  const V3<S> Ttemp = (mulMV(R0, b2.To) + T0) - b1.To;
+  const V3<S> T = mulMtV(b1.axis, Ttemp);
+  return !obbDisjoint(R, T, b1.extent, b2.extent);
+}
+
+// project6 (intersect-inl.h:1082-1105); std::min(a,b) = (b<a)?b:a, std::max(a,b) = (a<b)?b:a
+template <typename S>
+FCLB_DI bool project6(const V3<S>& ax, const V3<S>& p1, const V3<S>& p2, const V3<S>& p3, const V3<S>& q1,
+                      const V3<S>& q2, const V3<S>& q3) {
+  const S P1 = dot(ax, p1), P2 = dot(ax, p2), P3 = dot(ax, p3);
+  const S Q1 = dot(ax, q1), Q2 = dot(ax, q2), Q3 = dot(ax, q3);
+  const S mn1 = fmin_(P1, fmin_(P2, P3));
+  const S mx2 = fmax_(Q1, fmax_(Q2, Q3));
+  if (mn1 > mx2) return false;
+  const S mx1 = fmax_(P1, fmax_(P2, P3));
+  const S mn2 = fmin_(Q1, fmin_(Q2, Q3));
+  if (mn2 > mx1) return false;
+  return true;
+}
+
+// Intersect::intersect_Triangle, boolean (intersect-inl.h:594-612 -> :724-794)
+template <typename S>
+FCLB_DI bool triTriIntersect(const V3<S> P[3], const V3<S> Q[3], const M3<S>& R, const V3<S>& T) {
+  const V3<S> Q1 = mulMV(R, Q[0]) + T, Q2 = mulMV(R, Q[1]) + T, Q3 = mulMV(R, Q[2]) + T;
+  const V3<S> p1 = P[0] - P[0], p2 = P[1] - P[0], p3 = P[2] - P[0];
+  const V3<S> q1 = Q1 - P[0], q2 = Q2 - P[0], q3 = Q3 - P[0];
+  const V3<S> e1 = p2 - p1, e2 = p3 - p2;
+  const V3<S> n1 = cross(e1, e2);
+  if (!project6(n1, p1, p2, p3, q1, q2, q3)) return false;
+  const V3<S> f1 = q2 - q1, f2 = q3 - q2;
+  const V3<S> m1 = cross(f1, f2);
+  if (!project6(m1, p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e1, f1), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e1, f2), p1, p2, p3, q1, q2, q3)) return false;
+  const V3<S> f3 = q1 - q3;
+  if (!project6(cross(e1, f3), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e2, f1), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e2, f2), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e2, f3), p1, p2, p3, q1, q2, q3)) return false;
+  const V3<S> e3 = p1 - p3;
+  if (!project6(cross(e3, f1), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e3, f2), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e3, f3), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e1, n1), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e2, n1), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(e3, n1), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(f1, m1), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(f2, m1), p1, p2, p3, q1, q2, q3)) return false;
+  if (!project6(cross(f3, m1), p1, p2, p3, q1, q2, q3)) return false;
+  return true;
+}
+
+constexpr int kBvhWarps = 8;        // warps per CTA
+constexpr int kStackCap = 1024;     // (node,node) pairs per warp
+constexpr int kLeafCap = 64;        // queued leaf pairs per warp
+
+struct BvhArgs {
+  const void* nodes1;
+  const void* nodes2;
+  const void* tris1;
+  const void* tris2;
+  const void* poses1;
+  const void* poses2;
+  size_t n;
+  uint32_t max_contacts;
+  uint32_t* counts;
+  int32_t* first_pair;
+  unsigned long long* work_counter;
+  unsigned long long* stats;  // [0] BV-pair tests, [1] leaf-pair tests (optional)
+};
+
+template <typename S>
+__global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
+  extern __shared__ __align__(16) int2 s_bvh[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int2* stack = s_bvh + size_t(warp) * (kStackCap + kLeafCap);
+  int2* leafq = stack + kStackCap;
+  const S* __restrict__ nodes1 = static_cast<const S*>(a.nodes1);
+  const S* __restrict__ nodes2 = static_cast<const S*>(a.nodes2);
+  const S* __restrict__ tris1 = static_cast<const S*>(a.tris1);
+  const S* __restrict__ tris2 = static_cast<const S*>(a.tris2);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned long long st_bv = 0, st_leaf = 0;
+
+  while (true) {
+    unsigned long long q64 = 0;
+    if (lane == 0) q64 = atomicAdd(a.work_counter, 1ull);
+    q64 = __shfl_sync(0xffffffffu, q64, 0);
+    if (q64 >= a.n) break;
+    const size_t q = size_t(q64);
+    // relativeTransform (geometry-inl.h:433-434)
+    M3<S> R;
+    V3<S> t;
+    {
+      const Pose<S> tf1 = loadPose(static_cast<const S*>(a.poses1), q);
+      const Pose<S> tf2 = loadPose(static_cast<const S*>(a.poses2), q);
+      R = mulMtM(tf1.R, tf2.R);
+      t = mulMtV(tf1.R, tf2.t - tf1.t);
+    }
+    uint32_t count = 0;
+    int first_a = -1, first_b = -1;
+    int sp = 1, nleaf = 0;
+    if (lane == 0) stack[0] = make_int2(0, 0);
+    __syncwarp();
+    bool done = (a.max_contacts == 0);
+
+    while (!done && (sp > 0 || nleaf > 0)) {
+      if (sp > 0 && nleaf < 32) {
+        // ---- BV stage: pop up to 32 pairs ----
+        int take = sp < 32 ? sp : 32;
+        if (sp + take > kStackCap - 256) take = 1;  // near capacity: plain DFS (grows by <= 1 per step)
+        int2 pr = make_int2(-1, -1);
+        if (lane < take) pr = stack[sp - 1 - lane];
+        sp -= take;
+        __syncwarp();
+        bool expand = false, leaf = false;
+        int2 c0 = make_int2(0, 0), c1 = make_int2(0, 0);
+        if (lane < take) {
+          const NodeD<S> n1 = loadNode(nodes1, pr.x);
+          const NodeD<S> n2 = loadNode(nodes2, pr.y);
+          st_bv++;
+          if (obbOverlap(R, t, n1, n2)) {
+            const bool l1 = n1.first_child < 0, l2 = n2.first_child < 0;
+            if (l1 && l2) {
+              leaf = true;
+              c0 = make_int2(-(n1.first_child + 1), -(n2.first_child + 1));
+            } else {
+              expand = true;
+              // descend the first tree if the second is a leaf, or if both are
+              // inner and bv_1.size() > bv_2.size() (bvh_solver-inl.h:148-160)
+              const bool on1 = l2 || (!l1 && sqnorm(n1.extent) > sqnorm(n2.extent));
+              if (on1) {
+                c0 = make_int2(n1.first_child, pr.y);
+                c1 = make_int2(n1.first_child + 1, pr.y);
+              } else {
+                c0 = make_int2(pr.x, n2.first_child);
+                c1 = make_int2(pr.x, n2.first_child + 1);
+              }
+            }
+          }
+        }
+        const unsigned em = __ballot_sync(0xffffffffu, expand);
+        const unsigned lm = __ballot_sync(0xffffffffu, leaf);
+        if (expand) {
+          const int pos = sp + 2 * __popc(em & lt_mask);
+          stack[pos] = c0;
+          stack[pos + 1] = c1;
+        }
+        if (leaf) leafq[nleaf + __popc(lm & lt_mask)] = c0;
+        sp += 2 * __popc(em);
+        nleaf += __popc(lm);
+        __syncwarp();
+      }
+      if (nleaf >= 32 || (sp == 0 && nleaf > 0)) {
+        // ---- leaf stage: one triangle pair per lane ----
+        const int batch = nleaf < 32 ? nleaf : 32;
+        bool hit = false;
+        int2 lp = make_int2(-1, -1);
+        if (lane < batch) {
+          lp = leafq[nleaf - 1 - lane];
+          V3<S> P[3], Q[3];
+          loadTri(tris1, lp.x, P);
+          loadTri(tris2, lp.y, Q);
+          st_leaf++;
+          hit = triTriIntersect(P, Q, R, t);
+        }
+        nleaf -= batch;
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm) {
+          if (first_a < 0) {
+            const int src = __ffs(hm) - 1;
+            first_a = __shfl_sync(0xffffffffu, lp.x, src);
+            first_b = __shfl_sync(0xffffffffu, lp.y, src);
+          }
+          count += uint32_t(__popc(hm));
+          if (count >= a.max_contacts) {
+            count = a.max_contacts;
+            done = true;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      a.counts[q] = count;
+      if (a.first_pair) {
+        a.first_pair[2 * q] = first_a;
+        a.first_pair[2 * q + 1] = first_b;
+      }
+    }
+    __syncwarp();
+  }
+  if (a.stats) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      st_bv += __shfl_xor_sync(0xffffffffu, st_bv, off);
+      st_leaf += __shfl_xor_sync(0xffffffffu, st_leaf, off);
+    }
+    if (lane == 0) {
+      atomicAdd(&a.stats[0], st_bv);
+      atomicAdd(&a.stats[1], st_leaf);
+    }
+  }
+}
+
+static unsigned long long* g_bvh_counters = nullptr;  // [0] work counter, [1..2] stats
+static unsigned long long g_last_stats[2] = {0, 0};
+
+template <typename S>
+static int bvhCollideDev(Engine& e, const BvhDev* m1, const BvhDev* m2, const void* poses1, const void* poses2, size_t n,
+                         uint32_t max_contacts, uint32_t* counts, int32_t* first_pair) {
+  if (!g_bvh_counters) FCLB_CUDA(cudaMalloc(&g_bvh_counters, 4 * sizeof(unsigned long long)));
+  FCLB_CUDA(cudaMemsetAsync(g_bvh_counters, 0, 4 * sizeof(unsigned long long), e.compute));
+  BvhArgs a{};
+  a.nodes1 = m1->nodes;
+  a.nodes2 = m2->nodes;
+  a.tris1 = m1->tris;
+  a.tris2 = m2->tris;
+  a.poses1 = poses1;
+  a.poses2 = poses2;
+  a.n = n;
+  a.max_contacts = max_contacts;
+  a.counts = counts;
+  a.first_pair = first_pair;
+  a.work_counter = g_bvh_counters;
+  a.stats = g_bvh_counters + 1;
+  const size_t need = (n + kBvhWarps - 1) / kBvhWarps;
+  const size_t cap = size_t(e.sms) * 3;
+  const int grid = int(need < cap ? need : cap);
+  FCLB_CUDA(cudaEventRecord(e.ev_call0, e.compute));
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  const size_t smem = size_t(kBvhWarps) * (kStackCap + kLeafCap) * sizeof(int2);
+  FCLB_CUDA(cudaFuncSetAttribute(bvhCollideKernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  bvhCollideKernel<S><<<grid, kBvhWarps * 32, smem, e.compute>>>(a);
+  FCLB_CUDA(cudaGetLastError());
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  e.launches += 1;
+  FCLB_CUDA(cudaMemcpyAsync(g_last_stats, g_bvh_counters + 1, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                            e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.last_ms = ms;
+  e.last_call_ms = ms;
+  e.n_rec = 1;
+  e.rec_kind[0] = -1;
+  e.rec_count[0] = n;
+  e.rec_ms[0] = ms;
+  return FCLB_OK;
+}
+
+template <typename S>
+static int uploadBvh(BvhDev* d, const void* obb, const int32_t* first_child, int n_nodes, const void* tri, int n_tris) {
+  const S* o = static_cast<const S*>(obb);
+  const S* tv = static_cast<const S*>(tri);
+  std::vector<S> nodes(size_t(16) * n_nodes), tris(size_t(12) * n_tris, S(0));
+  for (int i = 0; i < n_nodes; i++) {
+    for (int k = 0; k < 15; k++) nodes[size_t(16) * i + k] = o[size_t(15) * i + k];
+    S bits;
+    if (sizeof(S) == 4) {
+      const int32_t v = first_child[i];
+      memcpy(&bits, &v, 4);
+    } else {
+      const long long v = first_child[i];
+      memcpy(&bits, &v, 8);
+    }
+    nodes[size_t(16) * i + 15] = bits;
+  }
+  for (int t = 0; t < n_tris; t++)
+    for (int v = 0; v < 3; v++)
+      for (int k = 0; k < 3; k++) tris[size_t(12) * t + 4 * v + k] = tv[size_t(9) * t + 3 * v + k];
+  FCLB_CUDA(cudaMalloc(&d->nodes, nodes.size() * sizeof(S)));
+  FCLB_CUDA(cudaMalloc(&d->tris, tris.size() * sizeof(S)));
+  FCLB_CUDA(cudaMemcpy(d->nodes, nodes.data(), nodes.size() * sizeof(S), cudaMemcpyHostToDevice));
+  FCLB_CUDA(cudaMemcpy(d->tris, tris.data(), tris.size() * sizeof(S), cudaMemcpyHostToDevice));
+  return FCLB_OK;
+}
+
+}  // namespace fclb
+
+using namespace fclb;
+
+extern "C" {
+
+int fclb_bvh_upload(const void* obb, const int32_t* first_child, int n_nodes, const void* tri_verts, int n_tris,
+                    int scalar_type, fclb_handle* h) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (!obb || !first_child || !tri_verts || !h || n_nodes <= 0 || n_tris <= 0)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_upload: null or empty input");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  for (int i = 0; i < n_nodes; i++) {
+    const int fc = first_child[i];
+    if (fc >= 0 ? (fc + 1 >= n_nodes || fc == 0) : (-(fc + 1) >= n_tris))
+      return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_upload: child / primitive index out of range");
+  }
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  BvhDev* d = new BvhDev();
+  d->n_nodes = n_nodes;
+  d->n_tris = n_tris;
+  d->scalar_type = scalar_type;
+  rc = scalar_type == FCLB_F32 ? uploadBvh<float>(d, obb, first_child, n_nodes, tri_verts, n_tris)
+                               : uploadBvh<double>(d, obb, first_child, n_nodes, tri_verts, n_tris);
+  if (rc) {
+    delete d;
+    return rc;
+  }
+  const fclb_handle hd = e.next_handle++;
+  bvhTable()[hd] = d;
+  *h = hd;
+  return FCLB_OK;
+}
+
+int fclb_bvh_release(fclb_handle h) {
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = bvhTable().find(h);
+  if (it == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_release: unknown handle");
+  cudaFree(it->second->nodes);
+  cudaFree(it->second->tris);
+  delete it->second;
+  bvhTable().erase(it);
+  return FCLB_OK;
+}
+
+int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+                               int scalar_type, const fclb_request* req, uint32_t* out_counts,
+                               int32_t* out_first_pair) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto i1 = bvhTable().find(bvh1), i2 = bvhTable().find(bvh2);
+  if (i1 == bvhTable().end() || i2 == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown BVH handle");
+  if (i1->second->scalar_type != scalar_type || i2->second->scalar_type != scalar_type)
+    return fail(FCLB_ERR_BAD_ARG, "BVH was uploaded for a different scalar type");
+  if (!req || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null request / out_counts");
+  if (req->penetration_mode != FCLB_PEN_DISABLED)
+    return fail(FCLB_ERR_UNSUPPORTED, "mesh-mesh contact generation (penetration modes) is not on the device yet");
+  if (n == 0) return FCLB_OK;
+  if (!poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null pose array");
+  if (scalar_type == FCLB_F32)
+    return bvhCollideDev<float>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts,
+                                out_first_pair);
+  return bvhCollideDev<double>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts,
+                               out_first_pair);
+}
+
+int fclb_bvh_collide_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+                                int scalar_type, const fclb_request* req, uint32_t* out_counts,
+                                int32_t* out_first_pair) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!poses1 || !poses2 || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t o_p1 = 0;
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_fp = alignUp(o_cnt + n * 4, 256);
+  const size_t total = alignUp(o_fp + n * 8, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  rc = fclb_bvh_collide_batch_dev(bvh1, bvh2, base + o_p1, base + o_p2, n, scalar_type, req,
+                                  reinterpret_cast<uint32_t*>(base + o_cnt),
+                                  out_first_pair ? reinterpret_cast<int32_t*>(base + o_fp) : nullptr);
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  if (out_first_pair) FCLB_CUDA(cudaMemcpyAsync(out_first_pair, base + o_fp, n * 8, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+int fclb_bvh_last_visit_counts(uint64_t* n_bv, uint64_t* n_leaf) {
+  if (n_bv) *n_bv = g_last_stats[0];
+  if (n_leaf) *n_leaf = g_last_stats[1];
+  return FCLB_OK;
+}
+
+}  // extern "C"

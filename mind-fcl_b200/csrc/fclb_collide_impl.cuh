@@ -379,6 +379,9 @@ struct CollideLaunchArgs {
   EpaWork work;
 };
 
+// implemented in fclb_epa_f32.cu / fclb_epa_f64.cu (EPA stage of one bucket)
+template <typename S>
+cudaError_t launchEpa(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st);
 // implemented in fclb_collide_f32.cu / fclb_collide_f64.cu
 template <typename S>
 cudaError_t launchCollide(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st, int* n_launches);

@@ -21,21 +21,7 @@ cudaError_t launchConvex(const BatchView& b, const CollideLaunchArgs& a, cudaStr
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (a.mode & 2) {
-    const size_t poly = PolyStore<S>::bytes(a.sp.epa_max_faces);
-    const size_t per_warp = poly + 24 * sizeof(S) + 16;
-    const size_t esmem = per_warp * kEpaWarps;
-    auto kern = epaKernel<S, T0, T1>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(esmem));
-    if (e != cudaSuccess) return e;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int per_sm = int((227 * 1024) / esmem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    kern<<<sms * per_sm, kEpaWarps * 32, esmem, st>>>(b, S(a.sp.epa_tol), a.sp.epa_max_faces, a.sp.epa_max_iter, a.mode,
-                                                      a.out, a.work, poly);
-    e = cudaGetLastError();
+    e = launchEpa<S>(b, a, st);
     if (n_launches) *n_launches += 1;
   }
   return e;
@@ -71,8 +57,6 @@ cudaError_t launchCollide(const BatchView& b, const CollideLaunchArgs& a, cudaSt
   if (b.type1 == A && b.type2 == B) return launchConvex<S, A, B>(b, a, st, n_launches);
   FCLB_CVX_CASE(ST_BOX, ST_BOX)
   FCLB_CVX_CASE(ST_CONVEX, ST_CONVEX)
-  FCLB_CVX_CASE(ST_CAPSULE, ST_BOX)
-  FCLB_CVX_CASE(ST_CYLINDER, ST_BOX)
 #undef FCLB_CVX_CASE
   return launchConvex<S, ST_DYNAMIC, ST_DYNAMIC>(b, a, st, n_launches);
 }

@@ -29,6 +29,8 @@ EXPORTS = [
     "fclb_distance_batch_host", "fclb_distance_batch_dev",
     "fclb_collide_batch_host", "fclb_collide_batch_dev",
     "fclb_gjk_epa_batch_host", "fclb_gjk_epa_batch_dev",
+    "fclb_bvh_upload", "fclb_bvh_release", "fclb_bvh_collide_batch_host", "fclb_bvh_collide_batch_dev",
+    "fclb_bvh_last_visit_counts",
     "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -113,6 +115,13 @@ def load() -> C.CDLL:
                        ("fclb_gjk_epa_batch_host", ge_args), ("fclb_gjk_epa_batch_dev", ge_args)):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = args
+    if hasattr(lib, "fclb_bvh_upload"):
+        lib.fclb_bvh_upload.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        lib.fclb_bvh_release.argtypes = [C.c_uint64]
+        bvh_args = [C.c_uint64, C.c_uint64, vp, vp, sz, C.c_int, vp, vp, vp]
+        lib.fclb_bvh_collide_batch_host.argtypes = bvh_args
+        lib.fclb_bvh_collide_batch_dev.argtypes = bvh_args
+        lib.fclb_bvh_last_visit_counts.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 
@@ -246,3 +255,37 @@ def last_launches():
 
 def stream_ptr() -> int:
     return int(load().fclb_stream())
+
+
+def bvh_upload(obb: np.ndarray, first_child: np.ndarray, tri_verts: np.ndarray, scalar_type) -> int:
+    dt = np_dtype(scalar_type)
+    obb = np.ascontiguousarray(obb, dt)
+    fc = np.ascontiguousarray(first_child, np.int32)
+    tv = np.ascontiguousarray(tri_verts, dt)
+    h = C.c_uint64()
+    check(load().fclb_bvh_upload(_ptr(obb), _ptr(fc), len(fc), _ptr(tv), tv.size // 9, scalar_type, C.byref(h)))
+    return h.value
+
+
+def bvh_release(h: int) -> None:
+    check(load().fclb_bvh_release(h))
+
+
+def bvh_collide_batch_host(bvh1, bvh2, poses1, poses2, scalar_type, request: Request, want_pair=False):
+    n = len(poses1)
+    counts = np.zeros(n, np.uint32)
+    pair = np.zeros((n, 2), np.int32) if want_pair else None
+    check(load().fclb_bvh_collide_batch_host(bvh1, bvh2, _ptr(poses1), _ptr(poses2), n, scalar_type,
+                                             C.cast(C.pointer(request), C.c_void_p), _ptr(counts), _ptr(pair)))
+    return counts, pair
+
+
+def bvh_collide_batch_dev(bvh1, bvh2, poses1, poses2, n, scalar_type, request: Request, counts, pair=None):
+    check(load().fclb_bvh_collide_batch_dev(bvh1, bvh2, _ptr(poses1), _ptr(poses2), n, scalar_type,
+                                            C.cast(C.pointer(request), C.c_void_p), _ptr(counts), _ptr(pair)))
+
+
+def bvh_last_visit_counts():
+    a, b = C.c_uint64(), C.c_uint64()
+    check(load().fclb_bvh_last_visit_counts(C.byref(a), C.byref(b)))
+    return a.value, b.value

@@ -147,3 +147,80 @@ def config_c1_convex(n: int, dtype, seed: int = 1003):
     poses1 = random_poses(rng, n, 0.3, dtype)
     poses2 = random_poses(rng, n, 0.3, dtype)
     return (m0, m1), make_pairs(np.zeros(n, np.uint32), np.ones(n, np.uint32)), poses1, poses2
+
+
+# ---- procedural meshes (config C3) ---------------------------------------------
+def noisy_uv_sphere(n_lat=51, n_lon=100, radius=1.0, noise=0.08, seed=3001):
+    """Closed UV sphere with smooth radial noise: 2*n_lon*(n_lat-1) triangles
+    (10,000 for the defaults).  Returns (verts[n,3] float64, tris[m,3] int32)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    k = rng.uniform(1.0, 4.0, size=(6, 3))
+    ph = rng.uniform(0, 2 * np.pi, size=6)
+
+    def bump(p):
+        return sum(np.sin(p @ k[i] + ph[i]) for i in range(6)) / 6.0
+
+    verts = [(0.0, 0.0, 1.0)]
+    for i in range(1, n_lat):
+        th = np.pi * i / n_lat
+        for j in range(n_lon):
+            a = 2 * np.pi * j / n_lon
+            verts.append((np.sin(th) * np.cos(a), np.sin(th) * np.sin(a), np.cos(th)))
+    verts.append((0.0, 0.0, -1.0))
+    verts = np.asarray(verts, np.float64)
+    verts = verts * (radius * (1.0 + noise * bump(verts)))[:, None]
+
+    def ring(i, j):
+        return 1 + (i - 1) * n_lon + (j % n_lon)
+
+    tris = []
+    for j in range(n_lon):
+        tris.append((0, ring(1, j), ring(1, j + 1)))
+    for i in range(1, n_lat - 1):
+        for j in range(n_lon):
+            a, b, c, d = ring(i, j), ring(i + 1, j), ring(i + 1, j + 1), ring(i, j + 1)
+            tris.append((a, b, c))
+            tris.append((a, c, d))
+    south = len(verts) - 1
+    for j in range(n_lon):
+        tris.append((south, ring(n_lat - 1, j + 1), ring(n_lat - 1, j)))
+    return verts, np.asarray(tris, np.int32)
+
+
+def noisy_torus(n_major=100, n_minor=50, R=0.75, r=0.3, noise=0.06, seed=3002):
+    """Torus with smooth radial noise: 2*n_major*n_minor triangles (10,000 for the defaults)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    k = rng.uniform(1.0, 4.0, size=(6, 3))
+    ph = rng.uniform(0, 2 * np.pi, size=6)
+    verts = []
+    for i in range(n_major):
+        u = 2 * np.pi * i / n_major
+        for j in range(n_minor):
+            v = 2 * np.pi * j / n_minor
+            base = np.array([np.cos(u), np.sin(u), 0.0])
+            p = base * R + r * (np.cos(v) * base + np.array([0.0, 0.0, np.sin(v)]))
+            verts.append(p)
+    verts = np.asarray(verts, np.float64)
+    b = sum(np.sin(verts @ k[i] + ph[i]) for i in range(6)) / 6.0
+    verts = verts * (1.0 + noise * b)[:, None]
+
+    def idx(i, j):
+        return (i % n_major) * n_minor + (j % n_minor)
+
+    tris = []
+    for i in range(n_major):
+        for j in range(n_minor):
+            a, bb, c, d = idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)
+            tris.append((a, bb, c))
+            tris.append((a, c, d))
+    return verts, np.asarray(tris, np.int32)
+
+
+def config_c3_poses(n: int, dtype, seed: int = 3003, extent: float = 2.5):
+    """C3: mesh 2 at identity, mesh 1 translated uniformly in [-extent,extent]^3 with a
+    random rotation."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    poses1 = random_poses(rng, n, extent, dtype)
+    poses2 = np.zeros((n, 12), dtype)
+    poses2[:, 0] = poses2[:, 4] = poses2[:, 8] = 1
+    return poses1, np.ascontiguousarray(poses2)

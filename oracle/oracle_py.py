@@ -149,6 +149,53 @@ class RefOracle(_Oracle):
     path = REF_PATH
     kind = "reference"
 
+    # ---- meshes (reference BVHModel<OBBRSS<S>>) ----
+    def bvh_create(self, verts, tris):
+        verts = np.ascontiguousarray(verts, np.float64)
+        tris = np.ascontiguousarray(tris, np.int32)
+        f = self.fn("bvh_create")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        return int(f(_p(verts), len(verts), _p(tris), len(tris)))
+
+    def bvh_export(self, mesh_id, dtype):
+        st = _st(dtype)
+        fn_nodes = self.fn("bvh_num_nodes")
+        fn_nodes.argtypes = [C.c_int, C.c_int]
+        n_nodes = int(fn_nodes(mesh_id, st))
+        fn_tris = self.fn("bvh_num_tris")
+        fn_tris.argtypes = [C.c_int]
+        n_tris = int(fn_tris(mesh_id))
+        obb = np.zeros((n_nodes, 15), dtype)
+        child = np.zeros(n_nodes, np.int32)
+        tri = np.zeros((n_tris, 9), dtype)
+        f = self.fn("bvh_export")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        f(mesh_id, st, _p(obb), _p(child), _p(tri))
+        return obb, child, tri
+
+    def bvh_collide_batch(self, id1, id2, poses1, poses2, threads=1, want_pair=True, **req):
+        n = len(poses1)
+        counts = np.zeros(n, np.uint32)
+        pair = np.zeros((n, 2), np.int32) if want_pair else None
+        r = _request(**req)
+        f = self.fn("bvh_collide_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                      C.c_void_p, C.c_int]
+        f(_st(poses1.dtype), id1, id2, _p(poses1), _p(poses2), n, C.cast(C.pointer(r), C.c_void_p), _p(counts),
+          _p(pair), threads)
+        return counts, pair
+
+    def bvh_visit_counts(self, id1, id2, poses1, poses2, threads=1):
+        n = len(poses1)
+        n_bv = np.zeros(n, np.uint64)
+        n_leaf = np.zeros(n, np.uint64)
+        n_hit = np.zeros(n, np.uint32)
+        f = self.fn("bvh_visit_counts")
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                      C.c_void_p, C.c_int]
+        f(_st(poses1.dtype), id1, id2, _p(poses1), _p(poses2), n, _p(n_bv), _p(n_leaf), _p(n_hit), threads)
+        return n_bv, n_leaf, n_hit
+
 
 class PortOracle(_Oracle):
     prefix = "fclport_"

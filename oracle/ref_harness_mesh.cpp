@@ -1,1 +1,226 @@
-// mesh / heightmap / broadphase entry points of the reference oracle (filled in below)
+// oracle/ref_harness_mesh.cpp -- TEST INFRASTRUCTURE (the "reference" oracle,
+// mesh part).  Compiled with ref_harness.cpp into oracle/_ref/libfclref.so from
+// the UNMODIFIED reference headers + oracle/eigen_shim.
+//
+//   * BVHModel<OBBRSS<S>> construction by the reference's own builder
+//     (geometry/bvh/BVH_model-inl.h:402-570) and export of the flattened OBB
+//     nodes / triangles -- the same data a mind-fcl integration would hand to
+//     fclb_bvh_upload;
+//   * batched fcl::collide(BVH, BVH) (-> OrientedNodeBVHSolver::MeshIntersect,
+//     narrowphase/detail/traversal/collision/bvh_solver-inl.h:75);
+//   * visit counters (BV-pair tests, leaf-pair tests) from an instrumented
+//     replica of that loop which calls the reference's own overlap() and
+//     Intersect::intersect_Triangle -- the counts SURVEY.md 8(d) uses for the
+//     algorithmic bytes of config C3.
+#include <climits>
+#include <cstdint>
+#include <memory>
+#include <stack>
+#include <thread>
+#include <vector>
+
+#include "fcl/fcl.h"
+
+namespace {
+
+struct RequestRec {
+  uint32_t max_contacts;
+  uint32_t penetration_mode;
+  double dir[3];
+  double binary_tol, distance_tol;
+  uint32_t gjk_max_iter, epa_max_faces, epa_max_iter;
+  uint32_t flags;
+};
+
+template <typename S>
+using Model = fcl::BVHModel<fcl::OBBRSS<S>>;
+
+struct MeshRec {
+  std::shared_ptr<Model<float>> f;
+  std::shared_ptr<Model<double>> d;
+};
+std::vector<MeshRec>& meshes() {
+  static std::vector<MeshRec> m;
+  return m;
+}
+template <typename S>
+Model<S>* get(int id);
+template <>
+Model<float>* get<float>(int id) {
+  return meshes().at(id).f.get();
+}
+template <>
+Model<double>* get<double>(int id) {
+  return meshes().at(id).d.get();
+}
+
+template <typename S>
+std::shared_ptr<Model<S>> build(const double* verts, int n_verts, const int* tris, int n_tris) {
+  std::vector<fcl::Vector3<S>> pts;
+  std::vector<fcl::MeshSimplex> simp;
+  for (int i = 0; i < n_verts; i++) pts.emplace_back(S(verts[3 * i]), S(verts[3 * i + 1]), S(verts[3 * i + 2]));
+  for (int i = 0; i < n_tris; i++) simp.emplace_back(tris[3 * i], tris[3 * i + 1], tris[3 * i + 2]);
+  auto m = std::make_shared<Model<S>>();
+  m->beginModel();
+  m->addSubModel(pts, simp);
+  m->endModel();
+  return m;
+}
+
+template <typename S>
+fcl::Transform3<S> loadPose(const S* p) {
+  fcl::Transform3<S> tf;
+  tf.setIdentity();
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) tf.linear()(i, j) = p[3 * i + j];
+  for (int i = 0; i < 3; i++) tf.translation()[i] = p[9 + i];
+  return tf;
+}
+
+template <typename F>
+void parallelFor(size_t n, int n_threads, F&& f) {
+  if (n_threads <= 1 || n < 2) {
+    f(size_t(0), n);
+    return;
+  }
+  std::vector<std::thread> ts;
+  const size_t chunk = (n + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; t++) {
+    const size_t b = std::min(n, chunk * t), e = std::min(n, chunk * (t + 1));
+    if (b >= e) break;
+    ts.emplace_back([=, &f] { f(b, e); });
+  }
+  for (auto& t : ts) t.join();
+}
+
+template <typename S>
+void exportModel(int id, S* obb, int32_t* child, S* tri) {
+  const Model<S>* m = get<S>(id);
+  for (int i = 0; i < m->getNumBVs(); i++) {
+    const auto& node = m->getBV(i);
+    const fcl::OBB<S>& b = node.bv.obb;
+    S* o = obb + 15 * size_t(i);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) o[3 * r + c] = b.axis(r, c);
+    for (int k = 0; k < 3; k++) o[9 + k] = b.To[k];
+    for (int k = 0; k < 3; k++) o[12 + k] = b.extent[k];
+    child[i] = node.first_child;
+  }
+  for (int t = 0; t < m->num_simplex(); t++) {
+    const fcl::Simplex<S> s = m->getSimplex(t);
+    for (int v = 0; v < 3; v++)
+      for (int k = 0; k < 3; k++) tri[9 * size_t(t) + 3 * v + k] = s[v][k];
+  }
+}
+
+template <typename S>
+void collideBatch(int id1, int id2, const S* poses1, const S* poses2, size_t n, const RequestRec* rq,
+                  uint32_t* counts, int32_t* first_pair, int threads) {
+  const Model<S>* m1 = get<S>(id1);
+  const Model<S>* m2 = get<S>(id2);
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    fcl::CollisionRequest<S> req(rq->max_contacts);
+    if (rq->penetration_mode == 1)
+      req.useDefaultPenetration();
+    else
+      req.disablePenetration();
+    for (size_t q = b; q < e; q++) {
+      fcl::CollisionResult<S> res;
+      const size_t c = fcl::collide<S>(m1, loadPose<S>(poses1 + 12 * q), m2, loadPose<S>(poses2 + 12 * q), req, res);
+      counts[q] = uint32_t(c);
+      if (first_pair) {
+        first_pair[2 * q] = c ? int32_t(res.getContact(0).b1) : -1;
+        first_pair[2 * q + 1] = c ? int32_t(res.getContact(0).b2) : -1;
+      }
+    }
+  });
+}
+
+// Instrumented replica of MeshIntersect's loop (bvh_solver-inl.h:90-160) in
+// all-contacts, no-penetration mode: counts BV-pair tests and leaf-pair tests.
+template <typename S>
+void visitCounts(int id1, int id2, const S* poses1, const S* poses2, size_t n, uint64_t* n_bv, uint64_t* n_leaf,
+                 uint32_t* n_hit, int threads) {
+  using namespace fcl;
+  const Model<S>* m1 = get<S>(id1);
+  const Model<S>* m2 = get<S>(id2);
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    for (size_t q = b; q < e; q++) {
+      const auto tf1 = loadPose<S>(poses1 + 12 * q), tf2 = loadPose<S>(poses2 + 12 * q);
+      Matrix3<S> R;
+      Vector3<S> t;
+      relativeTransform(tf1.linear(), tf1.translation(), tf2.linear(), tf2.translation(), R, t);
+      std::stack<std::pair<int, int>> st;
+      st.emplace(0, 0);
+      uint64_t bv = 0, leaf = 0;
+      uint32_t hit = 0;
+      while (!st.empty()) {
+        const auto task = st.top();
+        st.pop();
+        const auto& a = m1->getBV(task.first);
+        const auto& c = m2->getBV(task.second);
+        bv++;
+        if (!overlap(R, t, a.bv, c.bv)) continue;
+        const bool l1 = a.isLeaf(), l2 = c.isLeaf();
+        if (l1 && l2) {
+          leaf++;
+          const Simplex<S> s1 = m1->getSimplex(a.primitiveId());
+          const Simplex<S> s2 = m2->getSimplex(c.primitiveId());
+          if (detail::Intersect<S>::intersect_Triangle(s1[0], s1[1], s1[2], s2[0], s2[1], s2[2], R, t)) hit++;
+        } else if (l2 || (!l1 && a.bv.size() > c.bv.size())) {
+          st.push(std::make_pair(a.leftChild(), task.second));
+          st.push(std::make_pair(a.rightChild(), task.second));
+        } else {
+          st.push(std::make_pair(task.first, c.leftChild()));
+          st.push(std::make_pair(task.first, c.rightChild()));
+        }
+      }
+      if (n_bv) n_bv[q] = bv;
+      if (n_leaf) n_leaf[q] = leaf;
+      if (n_hit) n_hit[q] = hit;
+    }
+  });
+}
+
+}  // namespace
+
+extern "C" {
+
+int fclref_bvh_create(const double* verts, int n_verts, const int* tris, int n_tris) {
+  MeshRec r;
+  r.f = build<float>(verts, n_verts, tris, n_tris);
+  r.d = build<double>(verts, n_verts, tris, n_tris);
+  meshes().push_back(r);
+  return int(meshes().size()) - 1;
+}
+int fclref_bvh_num_nodes(int id, int scalar_type) {
+  return scalar_type == 0 ? get<float>(id)->getNumBVs() : get<double>(id)->getNumBVs();
+}
+int fclref_bvh_num_tris(int id) { return get<double>(id)->num_simplex(); }
+int fclref_bvh_export(int id, int scalar_type, void* obb, int32_t* child, void* tri) {
+  if (scalar_type == 0)
+    exportModel<float>(id, (float*)obb, child, (float*)tri);
+  else
+    exportModel<double>(id, (double*)obb, child, (double*)tri);
+  return 0;
+}
+int fclref_bvh_collide_batch(int scalar_type, int id1, int id2, const void* poses1, const void* poses2, size_t n,
+                             const void* request, uint32_t* counts, int32_t* first_pair, int threads) {
+  if (scalar_type == 0)
+    collideBatch<float>(id1, id2, (const float*)poses1, (const float*)poses2, n, (const RequestRec*)request, counts,
+                        first_pair, threads);
+  else
+    collideBatch<double>(id1, id2, (const double*)poses1, (const double*)poses2, n, (const RequestRec*)request, counts,
+                         first_pair, threads);
+  return 0;
+}
+int fclref_bvh_visit_counts(int scalar_type, int id1, int id2, const void* poses1, const void* poses2, size_t n,
+                            uint64_t* n_bv, uint64_t* n_leaf, uint32_t* n_hit, int threads) {
+  if (scalar_type == 0)
+    visitCounts<float>(id1, id2, (const float*)poses1, (const float*)poses2, n, n_bv, n_leaf, n_hit, threads);
+  else
+    visitCounts<double>(id1, id2, (const double*)poses1, (const double*)poses2, n, n_bv, n_leaf, n_hit, threads);
+  return 0;
+}
+
+}  // extern "C"
