@@ -1,0 +1,451 @@
+// fcl_b200/fcl.h -- host-side C++ mirror of the mind-fcl public API for the
+// batched narrowphase path, implemented on top of the C ABI (include/fclb200.h).
+//
+// What is mirrored (same names, argument meaning and error behaviour):
+//   fcl::collide(o1, tf1, o2, tf2, request, result)      reference narrowphase/collision.h:55-64
+//   fcl::collide(CollisionObject*, CollisionObject*, ..)  reference narrowphase/collision.h:62-64
+//   CollisionRequest<S> / CollisionResult<S> / Contact<S>  collision_request.h:51-94, collision_result.h:56-95, contact.h:46-101
+//   CollisionObject<S>, Box / Sphere / Ellipsoid / Capsule / Cone / Cylinder / Convex, BVHModel<OBBRSS<S>>
+// What is added (absent from mind-fcl):
+//   fcl::distance + DistanceRequest / DistanceResult  == detail::GJKSolver<S>::shapeDistance semantics
+//   fcl::collideBatch / fcl::distanceBatch            one call for many (pair, pose) queries
+//
+// mind-fcl's math types come from Eigen, which this repository does not depend
+// on: Vector3 / Matrix3 / Transform3 below are minimal stand-ins with the same
+// member names for the operations this path needs (linear(), translation()).
+// An integration inside mind-fcl uses Eigen's types and calls the C ABI directly
+// (INTEGRATION.md).
+//
+// Error behaviour follows the reference: no exceptions on the query path;
+// unsupported pairs / max_contacts == 0 print a warning and return 0
+// (collision-inl.h:73-110).  A missing GPU is NOT silently tolerated: the first
+// call aborts with the engine's error message (there is no CPU fallback).
+#pragma once
+
+#include <array>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <memory>
+#include <vector>
+
+#include "../fclb200.h"
+
+namespace fcl {
+
+template <typename S>
+struct Vector3 {
+  S v[3]{0, 0, 0};
+  Vector3() = default;
+  Vector3(S x, S y, S z) : v{x, y, z} {}
+  S& operator[](int i) { return v[i]; }
+  S operator[](int i) const { return v[i]; }
+  static Vector3 Zero() { return Vector3(); }
+  static Vector3 UnitX() { return Vector3(1, 0, 0); }
+};
+template <typename S>
+struct Matrix3 {
+  S m[3][3]{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  S& operator()(int i, int j) { return m[i][j]; }
+  S operator()(int i, int j) const { return m[i][j]; }
+  static Matrix3 Identity() { return Matrix3(); }
+};
+template <typename S>
+struct Transform3 {
+  Matrix3<S> R;
+  Vector3<S> t;
+  static Transform3 Identity() { return Transform3(); }
+  Matrix3<S>& linear() { return R; }
+  const Matrix3<S>& linear() const { return R; }
+  Vector3<S>& translation() { return t; }
+  const Vector3<S>& translation() const { return t; }
+  void setIdentity() { *this = Transform3(); }
+  void toPose12(S* out) const {
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) out[3 * i + j] = R.m[i][j];
+    for (int i = 0; i < 3; i++) out[9 + i] = t.v[i];
+  }
+};
+
+namespace detail {
+inline void check(int rc, const char* what) {
+  if (rc != FCLB_OK) {
+    std::fprintf(stderr, "fcl_b200: %s failed (%d): %s\n", what, rc, fclb_last_error());
+    std::abort();
+  }
+}
+template <typename S>
+constexpr int scalarType() {
+  return sizeof(S) == 4 ? FCLB_F32 : FCLB_F64;
+}
+}  // namespace detail
+
+enum NODE_TYPE {  // subset of geometry/collision_geometry.h:50-54 this path supports
+  GEOM_BOX,
+  GEOM_SPHERE,
+  GEOM_ELLIPSOID,
+  GEOM_CAPSULE,
+  GEOM_CONE,
+  GEOM_CYLINDER,
+  GEOM_CONVEX,
+  BV_OBBRSS
+};
+
+template <typename S>
+class CollisionGeometry {
+ public:
+  virtual ~CollisionGeometry() = default;
+  virtual NODE_TYPE getNodeType() const = 0;
+  virtual bool isShape() const { return true; }
+  // shape record for the engine's shape table
+  virtual fclb_shape shapeRecord() const = 0;
+};
+
+template <typename S>
+class ShapeBase : public CollisionGeometry<S> {};
+
+#define FCLB_DEFINE_SHAPE(NAME, NODE, CODE, ...)                                   \
+  fclb_shape shapeRecord() const override {                                        \
+    fclb_shape s{};                                                                \
+    s.type = CODE;                                                                 \
+    const double p[3] = {__VA_ARGS__};                                             \
+    for (int i = 0; i < 3; i++) s.p[i] = p[i];                                     \
+    return s;                                                                      \
+  }                                                                                \
+  NODE_TYPE getNodeType() const override { return NODE; }
+
+template <typename S>
+class Box : public ShapeBase<S> {
+ public:
+  Box(S x, S y, S z) : side(x, y, z) {}
+  Vector3<S> side;
+  FCLB_DEFINE_SHAPE(Box, GEOM_BOX, FCLB_BOX, double(side[0]), double(side[1]), double(side[2]))
+};
+template <typename S>
+class Sphere : public ShapeBase<S> {
+ public:
+  explicit Sphere(S r) : radius(r) {}
+  S radius;
+  FCLB_DEFINE_SHAPE(Sphere, GEOM_SPHERE, FCLB_SPHERE, double(radius), 0, 0)
+};
+template <typename S>
+class Ellipsoid : public ShapeBase<S> {
+ public:
+  Ellipsoid(S a, S b, S c) : radii(a, b, c) {}
+  Vector3<S> radii;
+  FCLB_DEFINE_SHAPE(Ellipsoid, GEOM_ELLIPSOID, FCLB_ELLIPSOID, double(radii[0]), double(radii[1]), double(radii[2]))
+};
+template <typename S>
+class Capsule : public ShapeBase<S> {
+ public:
+  Capsule(S r, S l) : radius(r), lz(l) {}
+  S radius, lz;
+  FCLB_DEFINE_SHAPE(Capsule, GEOM_CAPSULE, FCLB_CAPSULE, double(radius), double(lz), 0)
+};
+template <typename S>
+class Cone : public ShapeBase<S> {
+ public:
+  Cone(S r, S l) : radius(r), lz(l) {}
+  S radius, lz;
+  FCLB_DEFINE_SHAPE(Cone, GEOM_CONE, FCLB_CONE, double(radius), double(lz), 0)
+};
+template <typename S>
+class Cylinder : public ShapeBase<S> {
+ public:
+  Cylinder(S r, S l) : radius(r), lz(l) {}
+  S radius, lz;
+  FCLB_DEFINE_SHAPE(Cylinder, GEOM_CYLINDER, FCLB_CYLINDER, double(radius), double(lz), 0)
+};
+#undef FCLB_DEFINE_SHAPE
+
+// Convex<S>(vertices, num_faces, faces) -- reference geometry/shape/convex.h:106-108;
+// faces use the reference encoding (count, v0, v1, ... per face).
+template <typename S>
+class Convex : public ShapeBase<S> {
+ public:
+  Convex(const std::shared_ptr<const std::vector<Vector3<S>>>& vertices, int num_faces,
+         const std::shared_ptr<const std::vector<int>>& faces)
+      : vertices_(vertices), num_faces_(num_faces), faces_(faces) {
+    std::vector<double> v;
+    for (const auto& p : *vertices_)
+      for (int k = 0; k < 3; k++) v.push_back(double(p[k]));
+    detail::check(fclb_convex_upload(v.data(), int(vertices_->size()), faces_->data(), int(faces_->size()), num_faces_,
+                                     &slot_),
+                  "fclb_convex_upload");
+  }
+  NODE_TYPE getNodeType() const override { return GEOM_CONVEX; }
+  fclb_shape shapeRecord() const override {
+    fclb_shape s{};
+    s.type = FCLB_CONVEX;
+    s.geom = slot_;
+    return s;
+  }
+  const std::vector<Vector3<S>>& getVertices() const { return *vertices_; }
+
+ private:
+  std::shared_ptr<const std::vector<Vector3<S>>> vertices_;
+  int num_faces_;
+  std::shared_ptr<const std::vector<int>> faces_;
+  uint32_t slot_ = 0;
+};
+
+// BVHModel<OBBRSS<S>>: the tree is built by the caller's builder (mind-fcl's
+// BVHModel::endModel in an integration) and handed over flattened.
+template <typename S>
+struct OBBRSS {};
+template <typename BV>
+class BVHModel;
+template <typename S>
+class BVHModel<OBBRSS<S>> : public CollisionGeometry<S> {
+ public:
+  // obb: 15 S per node (axis row-major, To, extent); first_child per node; tri_verts: 9 S per triangle
+  BVHModel(const std::vector<S>& obb, const std::vector<int32_t>& first_child, const std::vector<S>& tri_verts) {
+    detail::check(fclb_bvh_upload(obb.data(), first_child.data(), int(first_child.size()), tri_verts.data(),
+                                  int(tri_verts.size() / 9), detail::scalarType<S>(), &handle_),
+                  "fclb_bvh_upload");
+  }
+  ~BVHModel() override { fclb_bvh_release(handle_); }
+  NODE_TYPE getNodeType() const override { return BV_OBBRSS; }
+  bool isShape() const override { return false; }
+  fclb_shape shapeRecord() const override { return fclb_shape{}; }
+  fclb_handle handle() const { return handle_; }
+
+ private:
+  fclb_handle handle_ = 0;
+};
+
+// narrowphase/collision_request.h:51-94
+template <typename S>
+struct CollisionRequest {
+  explicit CollisionRequest(std::size_t n_max_contacts = 1) : num_max_contacts_(n_max_contacts) {}
+  void disablePenetration() { penetration_mode_ = FCLB_PEN_DISABLED; }
+  void useDefaultPenetration() { penetration_mode_ = FCLB_PEN_DEFAULT_GJK_EPA; }
+  bool isPenetrationEnabled() const { return penetration_mode_ != FCLB_PEN_DISABLED; }
+  std::size_t maxNumContacts() const { return num_max_contacts_; }
+  void setMaxContactCount(std::size_t n) { num_max_contacts_ = n; }
+  void setBinaryCollisionTolerance(S t) { binary_collision_tolerance_ = t; }
+  void setPenetrationDistanceTolerance(S t) { distance_tolerance_ = t; }
+  S binaryCollisionTolerance() const { return binary_collision_tolerance_; }
+  S distanceTolerance() const { return distance_tolerance_; }
+  fclb_request toAbi() const {
+    fclb_request r{};
+    r.max_contacts = num_max_contacts_ > 0xffffffffull ? 0xffffffffu : uint32_t(num_max_contacts_);
+    r.penetration_mode = penetration_mode_;
+    r.binary_tol = double(binary_collision_tolerance_);
+    r.distance_tol = double(distance_tolerance_);
+    return r;
+  }
+
+ private:
+  std::size_t num_max_contacts_;
+  uint32_t penetration_mode_ = FCLB_PEN_DISABLED;
+  S binary_collision_tolerance_{S(1e-6)};
+  S distance_tolerance_{S(1e-6)};
+};
+
+// narrowphase/contact.h:46-101
+template <typename S>
+struct Contact {
+  const CollisionGeometry<S>* o1 = nullptr;
+  const CollisionGeometry<S>* o2 = nullptr;
+  intptr_t b1 = -1, b2 = -1;
+  Vector3<S> normal, pos;
+  S penetration_depth = 0;
+  static constexpr int NONE = -1;
+};
+
+// narrowphase/collision_result.h:56-95
+template <typename S>
+struct CollisionResult {
+  void addContact(const Contact<S>& c) { contacts_.push_back(c); }
+  std::size_t numContacts() const { return contacts_.size(); }
+  bool isCollision() const { return !contacts_.empty(); }
+  void clear() { contacts_.clear(); }
+  const Contact<S>& getContact(std::size_t i) const { return contacts_[i]; }
+  const std::vector<Contact<S>>& getContacts() const { return contacts_; }
+
+ private:
+  std::vector<Contact<S>> contacts_;
+};
+
+// narrowphase/collision_object.h
+template <typename S>
+class CollisionObject {
+ public:
+  CollisionObject(const std::shared_ptr<const CollisionGeometry<S>>& g, const Transform3<S>& tf = Transform3<S>())
+      : geom_(g), tf_(tf) {}
+  const std::shared_ptr<const CollisionGeometry<S>>& collisionGeometry() const { return geom_; }
+  const Transform3<S>& getTransform() const { return tf_; }
+  void setTransform(const Transform3<S>& tf) { tf_ = tf; }
+
+ private:
+  std::shared_ptr<const CollisionGeometry<S>> geom_;
+  Transform3<S> tf_;
+};
+
+// ---- batched entry points --------------------------------------------------------
+// One query = (o1, tf1, o2, tf2).  Results: one CollisionResult per query.
+template <typename S>
+struct CollisionQuery {
+  const CollisionGeometry<S>* o1;
+  Transform3<S> tf1;
+  const CollisionGeometry<S>* o2;
+  Transform3<S> tf2;
+};
+
+template <typename S>
+void collideBatch(const std::vector<CollisionQuery<S>>& queries, const CollisionRequest<S>& request,
+                  std::vector<CollisionResult<S>>& results) {
+  const std::size_t n = queries.size();
+  results.assign(n, CollisionResult<S>());
+  if (request.maxNumContacts() == 0) {
+    std::cerr << "Warning: should stop early as num_max_contact is " << request.maxNumContacts() << " !" << std::endl;
+    return;
+  }
+  if (n == 0) return;
+  // split: shape-shape queries go through one shape table, mesh-mesh queries per mesh pair
+  std::vector<fclb_shape> shapes;
+  std::vector<fclb_pair> pairs;
+  std::vector<S> p1, p2;
+  std::vector<std::size_t> shape_q;
+  const fclb_request req = request.toAbi();
+  for (std::size_t q = 0; q < n; q++) {
+    const auto& Q = queries[q];
+    if (Q.o1->isShape() && Q.o2->isShape()) {
+      fclb_pair pr{uint32_t(shapes.size()), uint32_t(shapes.size() + 1)};
+      shapes.push_back(Q.o1->shapeRecord());
+      shapes.push_back(Q.o2->shapeRecord());
+      pairs.push_back(pr);
+      p1.resize(p1.size() + 12);
+      p2.resize(p2.size() + 12);
+      Q.tf1.toPose12(&p1[p1.size() - 12]);
+      Q.tf2.toPose12(&p2[p2.size() - 12]);
+      shape_q.push_back(q);
+    } else if (!Q.o1->isShape() && !Q.o2->isShape()) {
+      const auto* m1 = static_cast<const BVHModel<OBBRSS<S>>*>(Q.o1);
+      const auto* m2 = static_cast<const BVHModel<OBBRSS<S>>*>(Q.o2);
+      S a[12], b[12];
+      Q.tf1.toPose12(a);
+      Q.tf2.toPose12(b);
+      uint32_t count = 0;
+      int32_t pair_ids[2] = {-1, -1};
+      detail::check(fclb_bvh_collide_batch_host(m1->handle(), m2->handle(), a, b, 1, detail::scalarType<S>(), &req,
+                                                &count, pair_ids),
+                    "fclb_bvh_collide_batch_host");
+      for (uint32_t c = 0; c < count && c < 1; c++) {
+        Contact<S> ct;
+        ct.o1 = Q.o1;
+        ct.o2 = Q.o2;
+        ct.b1 = pair_ids[0];
+        ct.b2 = pair_ids[1];
+        results[q].addContact(ct);
+      }
+    } else {
+      std::cerr << "Warning: collision function between node type " << Q.o1->getNodeType() << " and node type "
+                << Q.o2->getNodeType() << " is not supported" << std::endl;
+    }
+  }
+  if (pairs.empty()) return;
+  fclb_handle table = 0;
+  detail::check(fclb_shapes_upload(shapes.data(), uint32_t(shapes.size()), &table), "fclb_shapes_upload");
+  const uint32_t keep = req.max_contacts < 4 ? req.max_contacts : 4;
+  std::vector<S> contacts(pairs.size() * keep * 9);
+  std::vector<uint32_t> counts(pairs.size());
+  detail::check(fclb_collide_batch_host(table, pairs.data(), p1.data(), p2.data(), pairs.size(),
+                                        detail::scalarType<S>(), &req, keep, contacts.data(), counts.data()),
+                "fclb_collide_batch_host");
+  fclb_release(table);
+  for (std::size_t i = 0; i < pairs.size(); i++) {
+    const std::size_t q = shape_q[i];
+    for (uint32_t c = 0; c < counts[i] && c < keep; c++) {
+      const S* r = &contacts[(i * keep + c) * 9];
+      Contact<S> ct;
+      ct.o1 = queries[q].o1;
+      ct.o2 = queries[q].o2;
+      ct.normal = Vector3<S>(r[2], r[3], r[4]);
+      ct.pos = Vector3<S>(r[5], r[6], r[7]);
+      ct.penetration_depth = r[8];
+      results[q].addContact(ct);
+    }
+  }
+}
+
+// fcl::collide, single pair (reference narrowphase/collision_interface-inl.h:13-32)
+template <typename S>
+std::size_t collide(const CollisionGeometry<S>* o1, const Transform3<S>& tf1, const CollisionGeometry<S>* o2,
+                    const Transform3<S>& tf2, const CollisionRequest<S>& request, CollisionResult<S>& result) {
+  std::vector<CollisionQuery<S>> q{{o1, tf1, o2, tf2}};
+  std::vector<CollisionResult<S>> r;
+  collideBatch(q, request, r);
+  for (const auto& c : r[0].getContacts()) result.addContact(c);
+  return result.numContacts();
+}
+template <typename S>
+std::size_t collide(const CollisionObject<S>* o1, const CollisionObject<S>* o2, const CollisionRequest<S>& request,
+                    CollisionResult<S>& result) {
+  return collide(o1->collisionGeometry().get(), o1->getTransform(), o2->collisionGeometry().get(), o2->getTransform(),
+                 request, result);
+}
+
+// ---- distance (added API; semantics of detail::GJKSolver<S>::shapeDistance) -----------
+template <typename S>
+struct DistanceRequest {
+  S gjk_tolerance = S(0);        // <= 0: constants<S>::gjk_default_tolerance()
+  uint32_t gjk_max_iterations = 0;  // 0: 128
+};
+template <typename S>
+struct DistanceResult {
+  bool separated = false;  // shapeDistance's return value
+  S min_distance = S(-1);  // -1 when not separated
+  std::array<Vector3<S>, 2> nearest_points;
+};
+
+template <typename S>
+void distanceBatch(const std::vector<CollisionQuery<S>>& queries, const DistanceRequest<S>& request,
+                   std::vector<DistanceResult<S>>& results) {
+  const std::size_t n = queries.size();
+  results.assign(n, DistanceResult<S>());
+  if (n == 0) return;
+  std::vector<fclb_shape> shapes;
+  std::vector<fclb_pair> pairs(n);
+  std::vector<S> p1(12 * n), p2(12 * n), dist(n), w1(3 * n), w2(3 * n);
+  std::vector<uint8_t> ok(n);
+  for (std::size_t q = 0; q < n; q++) {
+    pairs[q] = fclb_pair{uint32_t(shapes.size()), uint32_t(shapes.size() + 1)};
+    shapes.push_back(queries[q].o1->shapeRecord());
+    shapes.push_back(queries[q].o2->shapeRecord());
+    queries[q].tf1.toPose12(&p1[12 * q]);
+    queries[q].tf2.toPose12(&p2[12 * q]);
+  }
+  fclb_handle table = 0;
+  detail::check(fclb_shapes_upload(shapes.data(), uint32_t(shapes.size()), &table), "fclb_shapes_upload");
+  detail::check(fclb_distance_batch_host(table, pairs.data(), p1.data(), p2.data(), n, detail::scalarType<S>(),
+                                         double(request.gjk_tolerance), request.gjk_max_iterations, dist.data(),
+                                         w1.data(), w2.data(), ok.data()),
+                "fclb_distance_batch_host");
+  fclb_release(table);
+  for (std::size_t q = 0; q < n; q++) {
+    results[q].separated = ok[q] != 0;
+    results[q].min_distance = dist[q];
+    results[q].nearest_points[0] = Vector3<S>(w1[3 * q], w1[3 * q + 1], w1[3 * q + 2]);
+    results[q].nearest_points[1] = Vector3<S>(w2[3 * q], w2[3 * q + 1], w2[3 * q + 2]);
+  }
+}
+
+template <typename S>
+S distance(const CollisionGeometry<S>* o1, const Transform3<S>& tf1, const CollisionGeometry<S>* o2,
+           const Transform3<S>& tf2, const DistanceRequest<S>& request, DistanceResult<S>& result) {
+  std::vector<CollisionQuery<S>> q{{o1, tf1, o2, tf2}};
+  std::vector<DistanceResult<S>> r;
+  distanceBatch(q, request, r);
+  result = r[0];
+  return result.min_distance;
+}
+
+using CollisionRequestf = CollisionRequest<float>;
+using CollisionRequestd = CollisionRequest<double>;
+using CollisionResultf = CollisionResult<float>;
+using CollisionResultd = CollisionResult<double>;
+
+}  // namespace fcl
