@@ -10,6 +10,8 @@ struct CollideWorkspace {
   uint32_t* query = nullptr;
   void* simplex = nullptr;
   int32_t* rank = nullptr;
+  uint32_t* defer_count = nullptr;
+  uint32_t* defer_item = nullptr;
   size_t cap = 0;      // queries
   size_t scalar = 0;   // bytes per scalar the simplex buffer was sized for
 };
@@ -21,12 +23,16 @@ static int ensureWorkspace(size_t n, size_t ss) {
   if (g_ws.query) cudaFree(g_ws.query);
   if (g_ws.simplex) cudaFree(g_ws.simplex);
   if (g_ws.rank) cudaFree(g_ws.rank);
+  if (g_ws.defer_count) cudaFree(g_ws.defer_count);
+  if (g_ws.defer_item) cudaFree(g_ws.defer_item);
   g_ws = CollideWorkspace();
   const size_t cap = n > g_ws.cap ? n : g_ws.cap;
   FCLB_CUDA(cudaMalloc(&g_ws.count, sizeof(uint32_t)));
   FCLB_CUDA(cudaMalloc(&g_ws.query, cap * sizeof(uint32_t)));
   FCLB_CUDA(cudaMalloc(&g_ws.simplex, cap * 24 * 8));
   FCLB_CUDA(cudaMalloc(&g_ws.rank, cap * sizeof(int32_t)));
+  FCLB_CUDA(cudaMalloc(&g_ws.defer_count, sizeof(uint32_t)));
+  FCLB_CUDA(cudaMalloc(&g_ws.defer_item, cap * sizeof(uint32_t)));
   g_ws.cap = cap;
   g_ws.scalar = 8;
   return FCLB_OK;
@@ -115,6 +121,10 @@ static int runCollide(fclb_handle shapes, const fclb_pair* pairs, const void* po
   a.work.simplex = g_ws.simplex;
   a.work.rank = g_ws.rank;
   a.work.capacity = uint32_t(g_ws.cap);
+  a.defer.count = g_ws.defer_count;
+  a.defer.item = g_ws.defer_item;
+  a.defer.enabled = 0;
+  a.defer.consume = 0;
   if (scalar_type == FCLB_F32) return collideDev<float>(e, t, pairs, poses1, poses2, n, a);
   return collideDev<double>(e, t, pairs, poses1, poses2, n, a);
 }

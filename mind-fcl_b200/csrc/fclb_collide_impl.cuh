@@ -298,15 +298,34 @@ __global__ void __launch_bounds__(kBlock) convexBoolKernel(BatchView b, S tol, i
   }
 }
 
-// ---- EPA stage: one warp per work item ---------------------------------------
-constexpr int kEpaWarps = 4;
+// ---- EPA stage: one TILE of T lanes per work item -----------------------------
+// Tier 1: T = 8 (four queries per warp) with a small pool; a query whose polytope
+// outgrows the pool is appended to `defer` and re-run from scratch by tier 2
+// (T = 32, the reference's capacity), so the reported status is always the one the
+// reference's pool size produces.
+constexpr int kEpaThreads = 128;
+template <typename S>
+__host__ __device__ inline size_t epaTileBytes(size_t poly_bytes) {
+  return (poly_bytes + 24 * sizeof(S) + 16 + 127) / 128 * 128 + 32;
+}
 
-template <typename S, int T0, int T1>
-__global__ void __launch_bounds__(kEpaWarps * 32) epaKernel(BatchView b, S tol, int max_faces, int max_iter, int mode,
-                                                            CollideOut out, EpaWork work, size_t poly_bytes) {
+struct EpaDefer {
+  uint32_t* count;  // device counter of deferred items
+  uint32_t* item;   // work-list indices
+  int enabled;      // tier 1: defer on pool exhaustion; tier 2: 0
+  int consume;      // tier 2: iterate the deferred list instead of the full work list
+};
+
+template <typename S, int T0, int T1, int T>
+__global__ void __launch_bounds__(kEpaThreads) epaKernel(BatchView b, S tol, int pool_faces, int max_iter, int mode,
+                                                         CollideOut out, EpaWork work, EpaDefer defer,
+                                                         size_t poly_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* my = smem_raw + size_t(warp) * (poly_bytes + 24 * sizeof(S) + 16);
+  constexpr int kTiles = kEpaThreads / T;
+  const int warp_lane = threadIdx.x & 31, tile = threadIdx.x / T, lane = threadIdx.x % T;
+  // tiles of one warp sit 32 B apart modulo 128 B, so their (tile-uniform) accesses hit different banks
+  const size_t per_tile = epaTileBytes<S>(poly_bytes);
+  unsigned char* my = smem_raw + size_t(tile) * per_tile;
   SlotStore<S> st;
   st.base = reinterpret_cast<S*>(my);
   st.stride = 1;
@@ -315,9 +334,10 @@ __global__ void __launch_bounds__(kEpaWarps * 32) epaKernel(BatchView b, S tol, 
   const ConvexD<S>* __restrict__ cvx = static_cast<const ConvexD<S>*>(b.convex);
   const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
   const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
-  const uint32_t n_work = min(*work.count, work.capacity);
-  const uint32_t n_warps = gridDim.x * kEpaWarps;
-  for (uint32_t w = blockIdx.x * kEpaWarps + warp; w < n_work; w += n_warps) {
+  const uint32_t n_items = defer.consume ? *defer.count : min(*work.count, work.capacity);
+  const uint32_t n_tiles = gridDim.x * kTiles;
+  for (uint32_t it = blockIdx.x * kTiles + tile; it < n_items; it += n_tiles) {
+    const uint32_t w = defer.consume ? defer.item[it] : it;
     const size_t q = work.query[w];
     const fclb_pair pr = b.pairs[q];
     MinkDiff<S, T0, T1> md;
@@ -325,20 +345,22 @@ __global__ void __launch_bounds__(kEpaWarps * 32) epaKernel(BatchView b, S tol, 
     md.s1 = bindShape(shapes, cvx, pr.shape2);
     const Pose<S> tf1 = loadPose(poses1, q);
     md.setPoses(tf1, loadPose(poses2, q));
+    EpaWarp<S, MinkDiff<S, T0, T1>, T> epa(md, poly_mem, pool_faces, warp_lane, nullptr);
     // GJK simplex -> slots 0..rank-1
     const S* sp = static_cast<const S*>(work.simplex) + size_t(w) * 24;
-    if (lane < 24) st.base[lane] = sp[lane];
-    __syncwarp();
+    for (int k = lane; k < 24; k += T) st.base[k] = sp[k];
+    epa.sync();
     Simp sx;
     sx.rank = work.rank[w];
     sx.ord = 0x03020100u;
-    EpaWarp<S, MinkDiff<S, T0, T1>> epa(md, poly_mem, max_faces, lane, nullptr);
     S depth = S(0);
     V3<S> p0 = zero3<S>(), p1 = zero3<S>();
     const int es = epa.evaluate(st, sx, max_iter, tol, depth, p0, p1);
-    __syncwarp();
+    epa.sync();
     if (lane == 0) {
-      if (mode & 4) {
+      if (defer.enabled && es == EPA_MALLOC_FAILED) {
+        defer.item[atomicAdd(defer.count, 1u)] = w;
+      } else if (mode & 4) {
         if (out.epa_status) out.epa_status[q] = es;
         if (out.geom) {
           S* g = static_cast<S*>(out.geom) + 7 * q;
@@ -368,7 +390,7 @@ __global__ void __launch_bounds__(kEpaWarps * 32) epaKernel(BatchView b, S tol, 
         emitContacts<S>(out, q, hit, &c, 1);
       }
     }
-    __syncwarp();
+    epa.sync();
   }
 }
 
@@ -377,6 +399,7 @@ struct CollideLaunchArgs {
   int mode;
   CollideOut out;
   EpaWork work;
+  EpaDefer defer;
 };
 
 // implemented in fclb_epa_f32.cu / fclb_epa_f64.cu (EPA stage of one bucket)

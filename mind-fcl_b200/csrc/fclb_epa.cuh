@@ -34,6 +34,11 @@
 #pragma once
 #include "fclb_gjk.cuh"
 
+// Out-of-line on purpose: the EPA kernel calls these from dozens of sites; fully
+// inlined it was 74k SASS lines (1.2 MB) and instruction-fetch bound (ncu:
+// stall_no_inst 40 % of samples).  See DESIGN.md 4.4.
+#define FCLB_DN __device__ __noinline__
+
 namespace fclb {
 
 enum EpaStatus : int { EPA_FAILED = 0, EPA_OK = 1, EPA_TOUCHING = 2, EPA_ITER_LIMIT = 3, EPA_MALLOC_FAILED = 4 };  // epa.h:14
@@ -50,7 +55,7 @@ struct MinDist {  // MinDistanceToSimplex, epa_polytope_utils.h:15-20
 
 // epa_polytope_utils.h:22-52
 template <typename S>
-FCLB_DI MinDist<S> pointToSegment(const V3<S>& p, const V3<S>& x0, const V3<S>& x1) {
+FCLB_DN MinDist<S> pointToSegment(const V3<S>& p, const V3<S>& x0, const V3<S>& x1) {
   MinDist<S> r;
   const V3<S> d = x1 - x0;
   const V3<S> a = x0 - p;
@@ -74,7 +79,7 @@ FCLB_DI MinDist<S> pointToSegment(const V3<S>& p, const V3<S>& x0, const V3<S>& 
 }
 // epa_polytope_utils.h:64-76
 template <typename S>
-FCLB_DI S pointToLineDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b) {
+FCLB_DN S pointToLineDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b) {
   const V3<S> ab = b - a;
   const S len = norm(ab);
   if (len <= S(0)) return norm(p - a);
@@ -82,7 +87,7 @@ FCLB_DI S pointToLineDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b) {
 }
 // epa_polytope_utils.h:78-93
 template <typename S>
-FCLB_DI S pointToPlaneDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b, const V3<S>& c) {
+FCLB_DN S pointToPlaneDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b, const V3<S>& c) {
   const V3<S> n = cross(a - b, b - c);
   const S len = norm(n);
   if (len <= S(0)) return pointToLineDistance(p, a, b);
@@ -92,7 +97,7 @@ FCLB_DI S pointToPlaneDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b, c
 }
 // epa_polytope_utils.h:95-165
 template <typename S>
-FCLB_DI MinDist<S> pointToTriangle(const V3<S>& p, const V3<S>& a, const V3<S>& b, const V3<S>& c) {
+FCLB_DN MinDist<S> pointToTriangle(const V3<S>& p, const V3<S>& a, const V3<S>& b, const V3<S>& c) {
   MinDist<S> r;
   const V3<S> dl0 = a - b, dl1 = b - c, dl2 = c - a;
   const V3<S> n = cross(dl0, dl1);
@@ -212,50 +217,81 @@ struct Feature {  // nearest feature: cls 0 vertex, 1 edge, 2 face; idx = slot; 
   int idx;
 };
 
-template <typename S, typename MD>
+// T = lanes cooperating on one query (a "tile": 8, 16 or 32 consecutive lanes of a
+// warp).  Small polytopes (boxes, hulls: < 30 faces at the 99th percentile) leave
+// most of a 32-lane warp idle in the parallel sections and replicate the uniform
+// code 32x, so the first pass runs FOUR queries per warp (T = 8) with a small pool;
+// queries that outgrow it are re-run by a T = 32 pass with the reference's full
+// capacity (fclb_epa_launch.cuh).
+template <typename S, typename MD, int T>
 struct EpaWarp {
   PolyStore<S> P;
   const MD& shape;
-  const int lane;
+  const int lane;      // lane within the tile
+  const unsigned tmask;  // this tile's lanes within the warp
+  const int tshift;
   int v_hw, e_hw, f_hw;     // high-water marks (slots ever used)
   int v_n, e_n, f_n;        // alive counts
   int v_sq, e_sq, f_sq;     // next sequence numbers
   uint32_t* n_support;
 
-  FCLB_DI EpaWarp(const MD& sh, unsigned char* smem, int max_faces, int lane_, uint32_t* ns)
-      : shape(sh), lane(lane_), n_support(ns) {
+  FCLB_DI EpaWarp(const MD& sh, unsigned char* smem, int max_faces, int warp_lane, uint32_t* ns)
+      : shape(sh),
+        lane(warp_lane % T),
+        tmask(T == 32 ? 0xffffffffu : (((1u << T) - 1u) << ((warp_lane / T) * T))),
+        tshift((warp_lane / T) * T),
+        n_support(ns) {
     P.bind(smem, max_faces);
   }
+  // tile-scoped collectives
+  FCLB_DI void sync() const { __syncwarp(tmask); }
+  FCLB_DI unsigned ballot(bool p) const { return (__ballot_sync(tmask, p) >> tshift) & (T == 32 ? 0xffffffffu : ((1u << T) - 1u)); }
+  FCLB_DI bool any(bool p) const { return __any_sync(tmask, p) != 0; }
+  template <typename V>
+  FCLB_DI V shflXor(V v, int off) const {
+    return __shfl_xor_sync(tmask, v, off, T);
+  }
+  template <typename V>
+  FCLB_DI V shfl(V v, int src) const {
+    return __shfl_sync(tmask, v, src, T);
+  }
 
-  FCLB_DI V3<S> support(const V3<S>& d) const {
+  // the ONE place the shape support mappings are instantiated in this kernel
+  FCLB_DN void supportBoth(const V3<S>& d, V3<S>& s0, V3<S>& s1) const {
     if (n_support) *n_support += 2;
-    return shape.support(d);
+    s0 = shape.support0(d);
+    s1 = shape.support1(-d);
+  }
+  FCLB_DI V3<S> support(const V3<S>& d) const {
+    V3<S> s0, s1;
+    supportBoth(d, s0, s1);
+    return s0 - s1;
   }
 
   // Polytope::Reset (epa_polytope.hpp:78-103)
-  FCLB_DI void reset() {
-    for (int i = lane; i < P.vcap; i += 32) P.v_alive[i] = 0;
-    for (int i = lane; i < P.ecap; i += 32) P.e_alive[i] = 0;
-    for (int i = lane; i < P.fcap; i += 32) P.f_alive[i] = 0;
+  FCLB_DN void reset() {
+    for (int i = lane; i < P.vcap; i += T) P.v_alive[i] = 0;
+    for (int i = lane; i < P.ecap; i += T) P.e_alive[i] = 0;
+    for (int i = lane; i < P.fcap; i += T) P.f_alive[i] = 0;
     v_hw = e_hw = f_hw = 0;
     v_n = e_n = f_n = 0;
     v_sq = e_sq = f_sq = 0;
-    __syncwarp();
+    sync();
   }
 
   // first dead slot of a pool (uniform result); -1 if the pool is full
-  FCLB_DI int allocSlot(const uint8_t* alive, int cap, int& hw) const {
+  FCLB_DN int allocSlot(const uint8_t* alive, int cap, int& hw) const {
     if (hw < cap) return hw++;
-    for (int base = 0; base < cap; base += 32) {
+    for (int base = 0; base < cap; base += T) {
       const int i = base + lane;
-      const unsigned m = __ballot_sync(kFull, i < cap && !alive[i]);
+      const unsigned m = ballot(i < cap && !alive[i]);
       if (m) return base + __ffs(m) - 1;
     }
     return -1;
   }
 
   // AddNewVertex (epa_polytope.hpp:185-209)
-  FCLB_DI int addVertex(const V3<S>& v, const V3<S>& d) {
+  FCLB_DN int addVertex(const V3<S>& v, const V3<S>& d) {
     const int s = allocSlot(P.v_alive, P.vcap, v_hw);
     if (s < 0) return -1;
     if (lane == 0) {
@@ -267,11 +303,11 @@ struct EpaWarp {
     }
     v_sq++;
     v_n++;
-    __syncwarp();
+    sync();
     return s;
   }
   // topology part of AddNewEdge (:212-240); the distance record is filled by fillEdge
-  FCLB_DI int addEdgeTopo(int v1, int v2) {
+  FCLB_DN int addEdgeTopo(int v1, int v2) {
     if (v1 < 0 || v2 < 0) return -1;
     const int s = allocSlot(P.e_alive, P.ecap, e_hw);
     if (s < 0) return -1;
@@ -286,16 +322,16 @@ struct EpaWarp {
     }
     e_sq++;
     e_n++;
-    __syncwarp();
+    sync();
     return s;
   }
-  FCLB_DI void fillEdge(int s) {  // any single lane
+  FCLB_DN void fillEdge(int s) {  // any single lane
     const MinDist<S> md = pointToSegment(zero3<S>(), P.vloc(P.e_v0[s]), P.vloc(P.e_v1[s]));
     P.e_d[s] = md.dist_sq;
     P.e_in[s] = md.in_simplex ? 1 : 0;
   }
   // topology part of AddNewFace (:243-290). Returns slot, or -1 (malloc / "wrong edge").
-  FCLB_DI int addFaceTopo(int e1, int e2, int e3) {
+  FCLB_DN int addFaceTopo(int e1, int e2, int e3) {
     if (e1 < 0 || e2 < 0 || e3 < 0) return -1;
     const int s = allocSlot(P.f_alive, P.fcap, f_hw);
     if (s < 0) return -1;
@@ -323,20 +359,20 @@ struct EpaWarp {
         }
       }
     }
-    ok = __shfl_sync(kFull, ok ? 1 : 0, 0) != 0;
+    ok = shfl(ok ? 1 : 0, 0) != 0;
     f_sq++;
     f_n++;
-    __syncwarp();
+    sync();
     return ok ? s : -1;
   }
-  FCLB_DI void fillFace(int s) {  // any single lane
+  FCLB_DN void fillFace(int s) {  // any single lane
     const MinDist<S> md = pointToTriangle(zero3<S>(), P.vloc(P.f_a[s]), P.vloc(P.f_b[s]), P.vloc(P.f_c[s]));
     P.f_d[s] = md.dist_sq;
     P.f_in[s] = md.in_simplex ? 1 : 0;
   }
 
   // formNewTetrahedronPolytope (epa_simplex2polytope.hpp:177-215)
-  FCLB_DI bool formTetrahedron(const V3<S> v[4], const V3<S> d[4]) {
+  FCLB_DN bool formTetrahedron(const V3<S> v[4], const V3<S> d[4]) {
     reset();
     int vi[4];
     for (int k = 0; k < 4; k++) vi[k] = addVertex(v[k], d[k]);
@@ -352,24 +388,30 @@ struct EpaWarp {
     f[1] = addFaceTopo(e[3], e[4], e[0]);
     f[2] = addFaceTopo(e[4], e[5], e[1]);
     f[3] = addFaceTopo(e[5], e[3], e[2]);
-    if (lane < 6 && e[lane] >= 0) fillEdge(e[lane]);
-    if (lane >= 8 && lane < 12 && f[lane - 8] >= 0) fillFace(f[lane - 8]);
-    __syncwarp();
+    for (int k = lane; k < 10; k += T) {
+      if (k < 6) {
+        if (e[k] >= 0) fillEdge(e[k]);
+      } else if (f[k - 6] >= 0) {
+        fillFace(f[k - 6]);
+      }
+    }
+    sync();
     for (int k = 0; k < 4; k++)
       if (f[k] < 0) return false;
     return true;
   }
 
   // extractTouchingPoint (epa_simplex2polytope.hpp:11-43)
-  FCLB_DI void touchingPoint(const V3<S>& dir, V3<S>& p0, V3<S>& p1) {
-    if (n_support) *n_support += 2;
-    const V3<S> mid = (shape.support0(dir) + shape.support1(-dir)) / S(2);
+  FCLB_DN void touchingPoint(const V3<S>& dir, V3<S>& p0, V3<S>& p1) {
+    V3<S> a0, a1;
+    supportBoth(dir, a0, a1);
+    const V3<S> mid = (a0 + a1) / S(2);
     p0 = mid;
     p1 = mid;
   }
 
   // simplexToPolytope3 (epa_simplex2polytope.hpp:135-175); 0 OK, 1 Touching, 2 Failed
-  FCLB_DI int simplexToPolytope3(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, const V3<S>& c,
+  FCLB_DN int simplexToPolytope3(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, const V3<S>& c,
                                  const V3<S>& dc, S thr, V3<S>& p0, V3<S>& p1) {
     const V3<S> ab = b - a, ac = c - a;
     V3<S> n = cross(ab, ac);
@@ -398,7 +440,7 @@ struct EpaWarp {
   }
 
   // simplexToPolytope2 (epa_simplex2polytope.hpp:218-380)
-  FCLB_DI int simplexToPolytope2(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, S thr, V3<S>& p0,
+  FCLB_DN int simplexToPolytope2(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, S thr, V3<S>& p0,
                                  V3<S>& p1) {
     const S thr_sq = thr * thr;
     const V3<S> a_to_b = b - a;
@@ -487,16 +529,21 @@ struct EpaWarp {
     f[5] = addFaceTopo(e[9], e[10], e[1]);
     f[6] = addFaceTopo(e[10], e[11], e[2]);
     f[7] = addFaceTopo(e[11], e[8], e[3]);
-    if (lane < 12 && e[lane] >= 0) fillEdge(e[lane]);
-    if (lane >= 16 && lane < 24 && f[lane - 16] >= 0) fillFace(f[lane - 16]);
-    __syncwarp();
+    for (int k = lane; k < 20; k += T) {
+      if (k < 12) {
+        if (e[k] >= 0) fillEdge(e[k]);
+      } else if (f[k - 12] >= 0) {
+        fillFace(f[k - 12]);
+      }
+    }
+    sync();
     for (int k = 0; k < 8; k++)
       if (f[k] < 0) return 2;
     return 0;
   }
 
   // simplexToPolytope (epa_simplex2polytope.hpp:46-133)
-  FCLB_DI int simplexToPolytope(const SlotStore<S>& st, const Simp& sx, S thr, V3<S>& p0, V3<S>& p1) {
+  FCLB_DN int simplexToPolytope(const SlotStore<S>& st, const Simp& sx, S thr, V3<S>& p0, V3<S>& p1) {
     const S thr_sq = thr * thr;
     V3<S> v[4], d[4];
     for (int i = 0; i < 4; i++) {
@@ -529,9 +576,7 @@ struct EpaWarp {
     } else if (sx.rank == 2) {
       return simplexToPolytope2(v[0], d[0], v[1], d[1], thr, p0, p1);
     }
-    if (n_support) *n_support += 2;
-    p0 = shape.support0(d[0]);
-    p1 = shape.support1(-d[0]);
+    supportBoth(d[0], p0, p1);
     return 1;
   }
 
@@ -545,11 +590,11 @@ struct EpaWarp {
     if (cls != bcls) return cls < bcls;
     return seq > bseq;
   }
-  FCLB_DI Feature nearest(bool exclude_vertex) const {
+  FCLB_DN Feature nearest(bool exclude_vertex) const {
     S bd = S(INFINITY);
     int bcls = 3, bseq = -1, bidx = -1;
     if (!exclude_vertex) {
-      for (int i = lane; i < v_hw; i += 32) {
+      for (int i = lane; i < v_hw; i += T) {
         if (!P.v_alive[i]) continue;
         const S d = P.vd[i];
         if (d < S(INFINITY) && better(d, 0, P.v_seq[i], bd, bcls, bseq)) {
@@ -557,7 +602,7 @@ struct EpaWarp {
         }
       }
     }
-    for (int i = lane; i < e_hw; i += 32) {
+    for (int i = lane; i < e_hw; i += T) {
       if (!P.e_alive[i]) continue;
       if (!exclude_vertex && !P.e_in[i]) continue;
       const S d = P.e_d[i];
@@ -565,7 +610,7 @@ struct EpaWarp {
         bd = d; bcls = 1; bseq = P.e_seq[i]; bidx = i;
       }
     }
-    for (int i = lane; i < f_hw; i += 32) {
+    for (int i = lane; i < f_hw; i += T) {
       if (!P.f_alive[i] || !P.f_in[i]) continue;
       const S d = P.f_d[i];
       if (d < S(INFINITY) && better(d, 2, P.f_seq[i], bd, bcls, bseq)) {
@@ -573,11 +618,11 @@ struct EpaWarp {
       }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const S od = __shfl_xor_sync(kFull, bd, off);
-      const int ocls = __shfl_xor_sync(kFull, bcls, off);
-      const int oseq = __shfl_xor_sync(kFull, bseq, off);
-      const int oidx = __shfl_xor_sync(kFull, bidx, off);
+    for (int off = T / 2; off > 0; off >>= 1) {
+      const S od = shflXor(bd, off);
+      const int ocls = shflXor(bcls, off);
+      const int oseq = shflXor(bseq, off);
+      const int oidx = shflXor(bidx, off);
       if (oidx >= 0 && (bidx < 0 || better(od, ocls, oseq, bd, bcls, bseq))) {
         bd = od; bcls = ocls; bseq = oseq; bidx = oidx;
       }
@@ -590,7 +635,7 @@ struct EpaWarp {
 
   // ComputeFaceNormalPointingOutward (epa_polytope.hpp:348-410).  `par`: the
   // caller is warp-uniform and the rare all-vertex pass may use all lanes.
-  FCLB_DI bool faceNormal(int f, V3<S>& normal, S* area, bool par) const {
+  FCLB_DN bool faceNormal(int f, V3<S>& normal, S* area, bool par) const {
     const V3<S> a = P.vloc(P.f_a[f]), b = P.vloc(P.f_b[f]), c = P.vloc(P.f_c[f]);
     const V3<S> e1 = a - b, e2 = b - c;
     const V3<S> cr = cross(e1, e2);
@@ -605,16 +650,16 @@ struct EpaWarp {
     }
     S max_pos = S(0), min_neg = S(0);
     if (par) {
-      for (int i = lane; i < v_hw; i += 32) {
+      for (int i = lane; i < v_hw; i += T) {
         if (!P.v_alive[i]) continue;
         const S dv = dot(P.vloc(i), dir);
         if (dv > max_pos) max_pos = dv;
         if (dv < min_neg) min_neg = dv;
       }
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const S om = __shfl_xor_sync(kFull, max_pos, off);
-        const S on = __shfl_xor_sync(kFull, min_neg, off);
+      for (int off = T / 2; off > 0; off >>= 1) {
+        const S om = shflXor(max_pos, off);
+        const S on = shflXor(min_neg, off);
         if (om > max_pos) max_pos = om;
         if (on < min_neg) min_neg = on;
       }
@@ -630,7 +675,7 @@ struct EpaWarp {
     return true;
   }
   // IsPointOutsidePolytopeFace (epa_polytope_expand.hpp:13-31), threshold 0
-  FCLB_DI bool pointOutsideFace(int f, const V3<S>& pt, bool par) const {
+  FCLB_DN bool pointOutsideFace(int f, const V3<S>& pt, bool par) const {
     V3<S> n;
     S area = S(0);
     if (!faceNormal(f, n, &area, par)) return area <= S(0);
@@ -639,7 +684,7 @@ struct EpaWarp {
   }
 
   // findNextSupportDirection (epa.hpp:11-113): 0 OK, 1 Failed, 2 Converge
-  FCLB_DI int faceCandidate(int f, bool try_witness, const V3<S>& witness, S dist_sq, S tol, V3<S>& next_d, V3<S>& next_v,
+  FCLB_DN int faceCandidate(int f, bool try_witness, const V3<S>& witness, S dist_sq, S tol, V3<S>& next_d, V3<S>& next_v,
                             int& start_face) {
     const S outer_thr = S(1e-3) * S(1e-3);
     V3<S> fn;
@@ -665,26 +710,26 @@ struct EpaWarp {
   }
 
   // ExpandPolytope (epa_polytope_expand.hpp:33-91): 0 OK, 1 Failed, 2 MallocFailed
-  FCLB_DI int expand(const V3<S>& nv, const V3<S>& nd, int start_face) {
+  FCLB_DN int expand(const V3<S>& nv, const V3<S>& nd, int start_face) {
     // initVisibilityCacheVariables + visibility predicate of EVERY face
-    for (int i = lane; i < v_hw; i += 32) {
+    for (int i = lane; i < v_hw; i += T) {
       P.v_rm[i] = 1;
       P.v_newedge[i] = kNil;
     }
-    for (int i = lane; i < e_hw; i += 32) P.e_vis[i] = 0;
-    for (int i = lane; i < f_hw; i += 32) {
+    for (int i = lane; i < e_hw; i += T) P.e_vis[i] = 0;
+    for (int i = lane; i < f_hw; i += T) {
       if (!P.f_alive[i]) continue;
       P.f_vis[i] = pointOutsideFace(i, nv, false) ? 3 : 2;  // 3 = outside (not reached yet), 2 = hidden
     }
-    __syncwarp();
+    sync();
     if (lane == 0) P.f_vis[start_face] = 1;  // the start face is visible by construction (:133)
-    __syncwarp();
+    sync();
     // grow the visible patch: a face joins when it is "outside" and shares an
     // edge with a patch face (computeVisiblePatch, :121-180)
     bool broken = false;
     while (true) {
       bool changed = false;
-      for (int i = lane; i < f_hw; i += 32) {
+      for (int i = lane; i < f_hw; i += T) {
         if (!P.f_alive[i] || P.f_vis[i] != 1) continue;
         const int es[3] = {P.f_e0[i], P.f_e1[i], P.f_e2[i]};
         for (int k = 0; k < 3; k++) {
@@ -700,12 +745,12 @@ struct EpaWarp {
           }
         }
       }
-      __syncwarp();
-      if (!__any_sync(kFull, changed)) break;
+      sync();
+      if (!any(changed)) break;
     }
-    if (__any_sync(kFull, broken)) return 1;
+    if (any(broken)) return 1;
     // edge classification + vertex keep flags (updateVertexRemoveFlag, :183-205)
-    for (int i = lane; i < e_hw; i += 32) {
+    for (int i = lane; i < e_hw; i += T) {
       if (!P.e_alive[i]) continue;
       const int f0 = P.e_f0[i], f1 = P.e_f1[i];
       const bool in0 = (f0 != kNil) && P.f_vis[f0] == 1;
@@ -717,10 +762,10 @@ struct EpaWarp {
         P.v_rm[P.e_v1[i]] = 0;
       }
     }
-    __syncwarp();
+    sync();
     // removeAccordingToVisibility (:244-281)
     int rm_f = 0, rm_e = 0, rm_v = 0;
-    for (int i = lane; i < e_hw; i += 32) {
+    for (int i = lane; i < e_hw; i += T) {
       if (!P.e_alive[i]) continue;
       if (P.e_vis[i] == 2) {
         P.e_alive[i] = 0;
@@ -733,29 +778,29 @@ struct EpaWarp {
         P.e_f1[i] = kNil;
       }
     }
-    __syncwarp();
-    for (int i = lane; i < f_hw; i += 32) {
+    sync();
+    for (int i = lane; i < f_hw; i += T) {
       if (P.f_alive[i] && P.f_vis[i] == 1) {
         P.f_alive[i] = 0;
         rm_f++;
       }
     }
-    for (int i = lane; i < v_hw; i += 32) {
+    for (int i = lane; i < v_hw; i += T) {
       if (P.v_alive[i] && P.v_rm[i]) {
         P.v_alive[i] = 0;
         rm_v++;
       }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      rm_f += __shfl_xor_sync(kFull, rm_f, off);
-      rm_e += __shfl_xor_sync(kFull, rm_e, off);
-      rm_v += __shfl_xor_sync(kFull, rm_v, off);
+    for (int off = T / 2; off > 0; off >>= 1) {
+      rm_f += shflXor(rm_f, off);
+      rm_e += shflXor(rm_e, off);
+      rm_v += shflXor(rm_v, off);
     }
     f_n -= rm_f;
     e_n -= rm_e;
     v_n -= rm_v;
-    __syncwarp();
+    sync();
 
     const int new_v = addVertex(nv, nd);
     if (new_v < 0) return 2;
@@ -768,7 +813,7 @@ struct EpaWarp {
     int made_e[2];
     while (true) {
       int best_seq = -1, best_idx = -1;
-      for (int i = lane; i < e_hw; i += 32) {
+      for (int i = lane; i < e_hw; i += T) {
         if (P.e_alive[i] && P.e_vis[i] == 1) {
           const int sq = P.e_seq[i];
           if (sq < prev_seq && sq > best_seq) {
@@ -778,9 +823,9 @@ struct EpaWarp {
         }
       }
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const int os = __shfl_xor_sync(kFull, best_seq, off);
-        const int oi = __shfl_xor_sync(kFull, best_idx, off);
+      for (int off = T / 2; off > 0; off >>= 1) {
+        const int os = shflXor(best_seq, off);
+        const int oi = shflXor(best_idx, off);
         if (os > best_seq) {
           best_seq = os;
           best_idx = oi;
@@ -801,7 +846,7 @@ struct EpaWarp {
               P.e_vis[ne] = 3;  // freshly made: distance record pending, not a border edge
             }
             if (first_new_e < 0) first_new_e = ne;
-            __syncwarp();
+            sync();
           } else {
             ne = -1;
           }
@@ -814,25 +859,25 @@ struct EpaWarp {
       } else {
         if (lane == 0) P.f_vis[nf] = 4;  // distance record pending
         if (first_new_f < 0) first_new_f = nf;
-        __syncwarp();
+        sync();
       }
     }
     (void)first_new_e;
     (void)first_new_f;
     // distance records of the new cone, one element per lane
-    for (int i = lane; i < e_hw; i += 32) {
+    for (int i = lane; i < e_hw; i += T) {
       if (P.e_alive[i] && P.e_vis[i] == 3) {
         fillEdge(i);
         P.e_vis[i] = 0;
       }
     }
-    for (int i = lane; i < f_hw; i += 32) {
+    for (int i = lane; i < f_hw; i += T) {
       if (P.f_alive[i] && P.f_vis[i] == 4) {
         fillFace(i);
         P.f_vis[i] = 0;
       }
     }
-    __syncwarp();
+    sync();
     return ok ? 0 : 2;
   }
 
@@ -843,7 +888,7 @@ struct EpaWarp {
   };
 
   // assignPenetrationPairFromSegment (epa.hpp:377-433)
-  FCLB_DI bool pairFromSegment(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
+  FCLB_DN bool pairFromSegment(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
     depth = fsqrt(f.md.dist_sq);
     const V3<S> p = f.md.witness;
     const V3<S> a_to_b = f.b - f.a;
@@ -858,21 +903,21 @@ struct EpaWarp {
       mxd = fabs_(a_to_b.z);
     }
     if (double(mxd) <= 1e-10) {
-      if (n_support) *n_support += 2;
-      p0 = shape.support0(f.da);
-      p1 = shape.support1(-f.da);
+      supportBoth(f.da, p0, p1);
       return true;
     }
     const S s = (comp(p, mx) - comp(f.a, mx)) / (comp(f.b, mx) - comp(f.a, mx));
     if (s < 0 || s > S(1.0)) return false;
     const S aw = S(1.0) - s, bw = s;
-    if (n_support) *n_support += 4;
-    p0 = aw * shape.support0(f.da) + bw * shape.support0(f.db);
-    p1 = aw * shape.support1(-f.da) + bw * shape.support1(-f.db);
+    V3<S> a0, a1, b0, b1;
+    supportBoth(f.da, a0, a1);
+    supportBoth(f.db, b0, b1);
+    p0 = aw * a0 + bw * b0;
+    p1 = aw * a1 + bw * b1;
     return true;
   }
   // assignPenetrationPairFromFace (epa.hpp:436-497)
-  FCLB_DI bool pairFromFace(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
+  FCLB_DN bool pairFromFace(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
     depth = fsqrt(f.md.dist_sq);
     const V3<S> p = f.md.witness;
     const V3<S> dl0 = f.a - f.b, dl1 = f.b - f.c, dl2 = f.c - f.a;
@@ -883,17 +928,18 @@ struct EpaWarp {
     const S w2_check = norm(cross(dl0, f.a - p)) / area;
     const S w2 = S(1.0) - w0 - w1;
     if (fabs_(w2_check - w2) > S(0.01)) return false;
-    if (n_support) *n_support += 6;
-    p0 = w0 * shape.support0(f.da) + w1 * shape.support0(f.db) + w2 * shape.support0(f.dc);
-    p1 = w0 * shape.support1(-f.da) + w1 * shape.support1(-f.db) + w2 * shape.support1(-f.dc);
+    V3<S> a0, a1, b0, b1, c0, c1;
+    supportBoth(f.da, a0, a1);
+    supportBoth(f.db, b0, b1);
+    supportBoth(f.dc, c0, c1);
+    p0 = w0 * a0 + w1 * b0 + w2 * c0;
+    p1 = w0 * a1 + w1 * b1 + w2 * c1;
     return true;
   }
   // assignPenetrationPair (epa.hpp:341-375)
-  FCLB_DI void assignPair(const V3<S>& cand_d, const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
+  FCLB_DN void assignPair(const V3<S>& cand_d, const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
     if (f.cls == 0) {
-      if (n_support) *n_support += 2;
-      p0 = shape.support0(f.da);
-      p1 = shape.support1(-f.da);
+      supportBoth(f.da, p0, p1);
       depth = norm(f.a);
       return;
     } else if (f.cls == 1) {
@@ -901,14 +947,12 @@ struct EpaWarp {
     } else if (f.cls == 2) {
       if (pairFromFace(f, depth, p0, p1)) return;
     }
-    if (n_support) *n_support += 2;
-    p0 = shape.support0(cand_d);
-    p1 = shape.support1(-cand_d);
+    supportBoth(cand_d, p0, p1);
     depth = norm(p0 - p1);
   }
 
   // checkTerminateCondition (epa.hpp:269-298)
-  FCLB_DI bool converged(const RawFeature& f, const V3<S>& new_v, S tol) const {
+  FCLB_DN bool converged(const RawFeature& f, const V3<S>& new_v, S tol) const {
     S delta_sq;
     if (f.cls == 1) {
       delta_sq = pointToSegment(new_v, f.a, f.b).dist_sq;
@@ -920,7 +964,7 @@ struct EpaWarp {
   }
 
   // evaluateFromInitializedPolytope (epa.hpp:137-237)
-  FCLB_DI int run(int max_iterations, S tol, S& depth, V3<S>& p0, V3<S>& p1) {
+  FCLB_DN int run(int max_iterations, S tol, S& depth, V3<S>& p0, V3<S>& p1) {
     int iteration = 0;
     while (true) {
       Feature nf = nearest(false);

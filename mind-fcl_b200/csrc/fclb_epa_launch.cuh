@@ -5,23 +5,45 @@
 
 namespace fclb {
 
-template <typename S, int T0, int T1>
-cudaError_t launchEpaT(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st) {
-  const size_t poly = PolyStore<S>::bytes(a.sp.epa_max_faces);
-  const size_t per_warp = poly + 24 * sizeof(S) + 16;
-  const size_t esmem = per_warp * kEpaWarps;
-  auto kern = epaKernel<S, T0, T1>;
+constexpr int kTier1Faces = 48;  // tier-1 pool: 48 faces, 72 edges, 72 vertices per query
+
+template <typename S, int T0, int T1, int T>
+cudaError_t launchEpaTier(const BatchView& b, const CollideLaunchArgs& a, int pool_faces, const EpaDefer& defer,
+                          cudaStream_t st) {
+  const size_t poly = PolyStore<S>::bytes(pool_faces);
+  const size_t per_tile = epaTileBytes<S>(poly);
+  const size_t esmem = per_tile * (kEpaThreads / T);
+  auto kern = epaKernel<S, T0, T1, T>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(esmem));
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int per_sm = int((227 * 1024) / esmem);
+  int per_sm = int((227 * 1024) / (esmem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  kern<<<sms * per_sm, kEpaWarps * 32, esmem, st>>>(b, S(a.sp.epa_tol), a.sp.epa_max_faces, a.sp.epa_max_iter, a.mode,
-                                                    a.out, a.work, poly);
+  if (per_sm > 4) per_sm = 4;
+  kern<<<sms * per_sm, kEpaThreads, esmem, st>>>(b, S(a.sp.epa_tol), pool_faces, a.sp.epa_max_iter, a.mode, a.out,
+                                                 a.work, defer, poly);
   return cudaGetLastError();
+}
+
+template <typename S, int T0, int T1>
+cudaError_t launchEpaT(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st) {
+  EpaDefer d = a.defer;
+  cudaError_t e = cudaMemsetAsync(d.count, 0, sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
+  if (a.sp.epa_max_faces > kTier1Faces) {
+    d.enabled = 1;
+    d.consume = 0;
+    e = launchEpaTier<S, T0, T1, 8>(b, a, kTier1Faces, d, st);
+    if (e != cudaSuccess) return e;
+    d.enabled = 0;
+    d.consume = 1;
+    return launchEpaTier<S, T0, T1, 32>(b, a, a.sp.epa_max_faces, d, st);
+  }
+  d.enabled = 0;
+  d.consume = 0;
+  return launchEpaTier<S, T0, T1, 8>(b, a, a.sp.epa_max_faces, d, st);
 }
 
 template <typename S>
