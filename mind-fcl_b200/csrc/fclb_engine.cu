@@ -307,6 +307,17 @@ ShapeTable* findTable(Engine& e, fclb_handle h) {
   return it == e.tables.end() ? nullptr : it->second;
 }
 
+int ensureChunkEvents(Engine& e, int n) {
+  while (int(e.ev_in.size()) < n) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    FCLB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    FCLB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    e.ev_in.push_back(a);
+    e.ev_done.push_back(b);
+  }
+  return FCLB_OK;
+}
+
 int ensureStage(Engine& e, size_t bytes) {
   if (bytes <= e.stage_cap) return FCLB_OK;
   if (e.d_stage) cudaFree(e.d_stage);
@@ -536,19 +547,53 @@ int fclb_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const v
   rc = ensureStage(e, total);
   if (rc) return rc;
   char* base = static_cast<char*>(e.d_stage);
-  FCLB_CUDA(cudaMemcpyAsync(base + o_pairs, pairs, n * sizeof(fclb_pair), cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  rc = fclb_distance_batch_dev(shapes, reinterpret_cast<const fclb_pair*>(base + o_pairs), base + o_p1, base + o_p2, n,
-                               scalar_type, gjk_tol, gjk_max_iter, out_dist ? base + o_dist : nullptr,
-                               out_p1 ? base + o_w1 : nullptr, out_p2 ? base + o_w2 : nullptr,
-                               out_ok ? reinterpret_cast<uint8_t*>(base + o_ok) : nullptr);
+  // Chunked three-stage pipeline: all H2D copies are queued up front on the copy-in
+  // stream (one event per chunk); the compute stream waits per chunk, runs the
+  // bucketed kernels, and the copy-out stream drains each chunk's results while later
+  // chunks are still uploading / computing.  PCIe is full duplex, so with pinned
+  // host buffers the call is bounded by the larger of the two copy directions.
+  const size_t chunk = e.host_chunk;
+  const int n_chunks = int((n + chunk - 1) / chunk);
+  rc = ensureChunkEvents(e, n_chunks);
   if (rc) return rc;
-  if (out_dist) FCLB_CUDA(cudaMemcpyAsync(out_dist, base + o_dist, n * ss, cudaMemcpyDeviceToHost, e.compute));
-  if (out_p1) FCLB_CUDA(cudaMemcpyAsync(out_p1, base + o_w1, n * 3 * ss, cudaMemcpyDeviceToHost, e.compute));
-  if (out_p2) FCLB_CUDA(cudaMemcpyAsync(out_p2, base + o_w2, n * 3 * ss, cudaMemcpyDeviceToHost, e.compute));
-  if (out_ok) FCLB_CUDA(cudaMemcpyAsync(out_ok, base + o_ok, n, cudaMemcpyDeviceToHost, e.compute));
-  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  const char* h_pairs = reinterpret_cast<const char*>(pairs);
+  const char* h_p1 = static_cast<const char*>(poses1);
+  const char* h_p2 = static_cast<const char*>(poses2);
+  // the staging arena may still be read by copy-out work of a previous call
+  FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
+  for (int c = 0; c < n_chunks; c++) {
+    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    FCLB_CUDA(cudaMemcpyAsync(base + o_pairs + b0 * sizeof(fclb_pair), h_pairs + b0 * sizeof(fclb_pair),
+                              m * sizeof(fclb_pair), cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaMemcpyAsync(base + o_p1 + b0 * 12 * ss, h_p1 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice,
+                              e.copy_in));
+    FCLB_CUDA(cudaMemcpyAsync(base + o_p2 + b0 * 12 * ss, h_p2 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice,
+                              e.copy_in));
+    FCLB_CUDA(cudaEventRecord(e.ev_in[c], e.copy_in));
+  }
+  for (int c = 0; c < n_chunks; c++) {
+    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    FCLB_CUDA(cudaStreamWaitEvent(e.compute, e.ev_in[c], 0));
+    rc = fclb_distance_batch_dev(shapes, reinterpret_cast<const fclb_pair*>(base + o_pairs) + b0, base + o_p1 + b0 * 12 * ss,
+                                 base + o_p2 + b0 * 12 * ss, m, scalar_type, gjk_tol, gjk_max_iter,
+                                 out_dist ? base + o_dist + b0 * ss : nullptr, out_p1 ? base + o_w1 + b0 * 3 * ss : nullptr,
+                                 out_p2 ? base + o_w2 + b0 * 3 * ss : nullptr,
+                                 out_ok ? reinterpret_cast<uint8_t*>(base + o_ok) + b0 : nullptr);
+    if (rc) return rc;
+    FCLB_CUDA(cudaEventRecord(e.ev_done[c], e.compute));
+    FCLB_CUDA(cudaStreamWaitEvent(e.copy_out, e.ev_done[c], 0));
+    if (out_dist)
+      FCLB_CUDA(cudaMemcpyAsync(static_cast<char*>(out_dist) + b0 * ss, base + o_dist + b0 * ss, m * ss,
+                                cudaMemcpyDeviceToHost, e.copy_out));
+    if (out_p1)
+      FCLB_CUDA(cudaMemcpyAsync(static_cast<char*>(out_p1) + b0 * 3 * ss, base + o_w1 + b0 * 3 * ss, m * 3 * ss,
+                                cudaMemcpyDeviceToHost, e.copy_out));
+    if (out_p2)
+      FCLB_CUDA(cudaMemcpyAsync(static_cast<char*>(out_p2) + b0 * 3 * ss, base + o_w2 + b0 * 3 * ss, m * 3 * ss,
+                                cudaMemcpyDeviceToHost, e.copy_out));
+    if (out_ok) FCLB_CUDA(cudaMemcpyAsync(out_ok + b0, base + o_ok + b0, m, cudaMemcpyDeviceToHost, e.copy_out));
+  }
+  FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
   return FCLB_OK;
 }
 

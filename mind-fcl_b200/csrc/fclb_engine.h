@@ -57,6 +57,8 @@ struct Engine {
   // staging for host entry points
   void* d_stage = nullptr;
   size_t stage_cap = 0;
+  size_t host_chunk = size_t(1) << 20;  // queries per pipeline stage of the *_host entry points
+  std::vector<cudaEvent_t> ev_in, ev_done;
   std::atomic<uint64_t> launches{0};
   double last_ms = 0.0;       // kernels of the last call (bucketing excluded)
   double last_call_ms = 0.0;  // whole device side of the last call (bucketing included)
@@ -74,6 +76,7 @@ Engine& eng();
 int ensureInit();
 ShapeTable* findTable(Engine& e, fclb_handle h);
 int ensureStage(Engine& e, size_t bytes);
+int ensureChunkEvents(Engine& e, int n);
 inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 SolverParams solverParams(int scalar_type, double gjk_tol, uint32_t gjk_max_iter, double epa_tol, uint32_t epa_max_faces,
                           uint32_t epa_max_iter, bool collide_defaults);

@@ -55,7 +55,7 @@ struct MinDist {  // MinDistanceToSimplex, epa_polytope_utils.h:15-20
 
 // epa_polytope_utils.h:22-52
 template <typename S>
-FCLB_DN MinDist<S> pointToSegment(const V3<S>& p, const V3<S>& x0, const V3<S>& x1) {
+FCLB_DN MinDist<S> pointToSegment(V3<S> p, V3<S> x0, V3<S> x1) {
   MinDist<S> r;
   const V3<S> d = x1 - x0;
   const V3<S> a = x0 - p;
@@ -79,7 +79,7 @@ FCLB_DN MinDist<S> pointToSegment(const V3<S>& p, const V3<S>& x0, const V3<S>& 
 }
 // epa_polytope_utils.h:64-76
 template <typename S>
-FCLB_DN S pointToLineDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b) {
+FCLB_DN S pointToLineDistance(V3<S> p, V3<S> a, V3<S> b) {
   const V3<S> ab = b - a;
   const S len = norm(ab);
   if (len <= S(0)) return norm(p - a);
@@ -87,7 +87,7 @@ FCLB_DN S pointToLineDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b) {
 }
 // epa_polytope_utils.h:78-93
 template <typename S>
-FCLB_DN S pointToPlaneDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b, const V3<S>& c) {
+FCLB_DN S pointToPlaneDistance(V3<S> p, V3<S> a, V3<S> b, V3<S> c) {
   const V3<S> n = cross(a - b, b - c);
   const S len = norm(n);
   if (len <= S(0)) return pointToLineDistance(p, a, b);
@@ -97,7 +97,7 @@ FCLB_DN S pointToPlaneDistance(const V3<S>& p, const V3<S>& a, const V3<S>& b, c
 }
 // epa_polytope_utils.h:95-165
 template <typename S>
-FCLB_DN MinDist<S> pointToTriangle(const V3<S>& p, const V3<S>& a, const V3<S>& b, const V3<S>& c) {
+FCLB_DN MinDist<S> pointToTriangle(V3<S> p, V3<S> a, V3<S> b, V3<S> c) {
   MinDist<S> r;
   const V3<S> dl0 = a - b, dl1 = b - c, dl2 = c - a;
   const V3<S> n = cross(dl0, dl1);
@@ -140,6 +140,16 @@ FCLB_DN MinDist<S> pointToTriangle(const V3<S>& p, const V3<S>& a, const V3<S>& 
   r.dist_sq = best.dist_sq;
   r.witness = best.witness;
   return r;
+}
+
+// Out-of-line support evaluation: the Minkowski difference is read through a
+// pointer (it lives in local memory, L1-resident), everything else stays in registers.
+template <typename S, typename MD>
+FCLB_DN void epaSupportBoth(const MD* shape, V3<S> d, S* out) {
+  const V3<S> s0 = shape->support0(d);
+  const V3<S> s1 = shape->support1(-d);
+  out[0] = s0.x; out[1] = s0.y; out[2] = s0.z;
+  out[3] = s1.x; out[4] = s1.y; out[5] = s1.z;
 }
 
 // ---------------------------------------------------------------------------
@@ -257,10 +267,12 @@ struct EpaWarp {
   }
 
   // the ONE place the shape support mappings are instantiated in this kernel
-  FCLB_DN void supportBoth(const V3<S>& d, V3<S>& s0, V3<S>& s1) const {
+  FCLB_DI void supportBoth(const V3<S>& d, V3<S>& s0, V3<S>& s1) const {
     if (n_support) *n_support += 2;
-    s0 = shape.support0(d);
-    s1 = shape.support1(-d);
+    S out[6];
+    epaSupportBoth<S, MD>(&shape, d, out);
+    s0 = mk<S>(out[0], out[1], out[2]);
+    s1 = mk<S>(out[3], out[4], out[5]);
   }
   FCLB_DI V3<S> support(const V3<S>& d) const {
     V3<S> s0, s1;
@@ -269,7 +281,7 @@ struct EpaWarp {
   }
 
   // Polytope::Reset (epa_polytope.hpp:78-103)
-  FCLB_DN void reset() {
+  FCLB_DI void reset() {
     for (int i = lane; i < P.vcap; i += T) P.v_alive[i] = 0;
     for (int i = lane; i < P.ecap; i += T) P.e_alive[i] = 0;
     for (int i = lane; i < P.fcap; i += T) P.f_alive[i] = 0;
@@ -280,7 +292,7 @@ struct EpaWarp {
   }
 
   // first dead slot of a pool (uniform result); -1 if the pool is full
-  FCLB_DN int allocSlot(const uint8_t* alive, int cap, int& hw) const {
+  FCLB_DI int allocSlot(const uint8_t* alive, int cap, int& hw) const {
     if (hw < cap) return hw++;
     for (int base = 0; base < cap; base += T) {
       const int i = base + lane;
@@ -291,7 +303,7 @@ struct EpaWarp {
   }
 
   // AddNewVertex (epa_polytope.hpp:185-209)
-  FCLB_DN int addVertex(const V3<S>& v, const V3<S>& d) {
+  FCLB_DI int addVertex(const V3<S>& v, const V3<S>& d) {
     const int s = allocSlot(P.v_alive, P.vcap, v_hw);
     if (s < 0) return -1;
     if (lane == 0) {
@@ -307,7 +319,7 @@ struct EpaWarp {
     return s;
   }
   // topology part of AddNewEdge (:212-240); the distance record is filled by fillEdge
-  FCLB_DN int addEdgeTopo(int v1, int v2) {
+  FCLB_DI int addEdgeTopo(int v1, int v2) {
     if (v1 < 0 || v2 < 0) return -1;
     const int s = allocSlot(P.e_alive, P.ecap, e_hw);
     if (s < 0) return -1;
@@ -325,13 +337,13 @@ struct EpaWarp {
     sync();
     return s;
   }
-  FCLB_DN void fillEdge(int s) {  // any single lane
+  FCLB_DI void fillEdge(int s) {  // any single lane
     const MinDist<S> md = pointToSegment(zero3<S>(), P.vloc(P.e_v0[s]), P.vloc(P.e_v1[s]));
     P.e_d[s] = md.dist_sq;
     P.e_in[s] = md.in_simplex ? 1 : 0;
   }
   // topology part of AddNewFace (:243-290). Returns slot, or -1 (malloc / "wrong edge").
-  FCLB_DN int addFaceTopo(int e1, int e2, int e3) {
+  FCLB_DI int addFaceTopo(int e1, int e2, int e3) {
     if (e1 < 0 || e2 < 0 || e3 < 0) return -1;
     const int s = allocSlot(P.f_alive, P.fcap, f_hw);
     if (s < 0) return -1;
@@ -365,14 +377,14 @@ struct EpaWarp {
     sync();
     return ok ? s : -1;
   }
-  FCLB_DN void fillFace(int s) {  // any single lane
+  FCLB_DI void fillFace(int s) {  // any single lane
     const MinDist<S> md = pointToTriangle(zero3<S>(), P.vloc(P.f_a[s]), P.vloc(P.f_b[s]), P.vloc(P.f_c[s]));
     P.f_d[s] = md.dist_sq;
     P.f_in[s] = md.in_simplex ? 1 : 0;
   }
 
   // formNewTetrahedronPolytope (epa_simplex2polytope.hpp:177-215)
-  FCLB_DN bool formTetrahedron(const V3<S> v[4], const V3<S> d[4]) {
+  FCLB_DI bool formTetrahedron(const V3<S> v[4], const V3<S> d[4]) {
     reset();
     int vi[4];
     for (int k = 0; k < 4; k++) vi[k] = addVertex(v[k], d[k]);
@@ -402,7 +414,7 @@ struct EpaWarp {
   }
 
   // extractTouchingPoint (epa_simplex2polytope.hpp:11-43)
-  FCLB_DN void touchingPoint(const V3<S>& dir, V3<S>& p0, V3<S>& p1) {
+  FCLB_DI void touchingPoint(const V3<S>& dir, V3<S>& p0, V3<S>& p1) {
     V3<S> a0, a1;
     supportBoth(dir, a0, a1);
     const V3<S> mid = (a0 + a1) / S(2);
@@ -411,7 +423,7 @@ struct EpaWarp {
   }
 
   // simplexToPolytope3 (epa_simplex2polytope.hpp:135-175); 0 OK, 1 Touching, 2 Failed
-  FCLB_DN int simplexToPolytope3(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, const V3<S>& c,
+  FCLB_DI int simplexToPolytope3(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, const V3<S>& c,
                                  const V3<S>& dc, S thr, V3<S>& p0, V3<S>& p1) {
     const V3<S> ab = b - a, ac = c - a;
     V3<S> n = cross(ab, ac);
@@ -440,7 +452,7 @@ struct EpaWarp {
   }
 
   // simplexToPolytope2 (epa_simplex2polytope.hpp:218-380)
-  FCLB_DN int simplexToPolytope2(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, S thr, V3<S>& p0,
+  FCLB_DI int simplexToPolytope2(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, S thr, V3<S>& p0,
                                  V3<S>& p1) {
     const S thr_sq = thr * thr;
     const V3<S> a_to_b = b - a;
@@ -543,7 +555,7 @@ struct EpaWarp {
   }
 
   // simplexToPolytope (epa_simplex2polytope.hpp:46-133)
-  FCLB_DN int simplexToPolytope(const SlotStore<S>& st, const Simp& sx, S thr, V3<S>& p0, V3<S>& p1) {
+  FCLB_DI int simplexToPolytope(const SlotStore<S>& st, const Simp& sx, S thr, V3<S>& p0, V3<S>& p1) {
     const S thr_sq = thr * thr;
     V3<S> v[4], d[4];
     for (int i = 0; i < 4; i++) {
@@ -561,16 +573,20 @@ struct EpaWarp {
       }
     }
     if (sx.rank == 4) {  // simplexToPolytope4 :96-133
+      // the four faces are tried in the order abc, acd, abd, bcd; the first one
+      // whose plane passes (almost) through the origin reduces to the triangle case
       const V3<S> o = zero3<S>();
-      if (pointToPlaneDistance(o, v[0], v[1], v[2]) < thr)
-        return simplexToPolytope3(v[0], d[0], v[1], d[1], v[2], d[2], thr, p0, p1);
-      if (pointToPlaneDistance(o, v[0], v[2], v[3]) < thr)
-        return simplexToPolytope3(v[0], d[0], v[2], d[2], v[3], d[3], thr, p0, p1);
-      if (pointToPlaneDistance(o, v[0], v[1], v[3]) < thr)
-        return simplexToPolytope3(v[0], d[0], v[1], d[1], v[3], d[3], thr, p0, p1);
-      if (pointToPlaneDistance(o, v[1], v[2], v[3]) < thr)
-        return simplexToPolytope3(v[1], d[1], v[2], d[2], v[3], d[3], thr, p0, p1);
-      return formTetrahedron(v, d) ? 0 : 2;
+      int sel = -1;
+      const int tri[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 1, 3}, {1, 2, 3}};
+#pragma unroll 1
+      for (int k = 0; k < 4 && sel < 0; k++)
+        if (pointToPlaneDistance(o, v[tri[k][0]], v[tri[k][1]], v[tri[k][2]]) < thr) sel = k;
+      if (sel < 0) return formTetrahedron(v, d) ? 0 : 2;
+      const int i0 = tri[sel][0], i1 = tri[sel][1], i2 = tri[sel][2];
+      const V3<S> ta = v[i0], tb = v[i1], tc = v[i2], tda = d[i0], tdb = d[i1], tdc = d[i2];
+      v[0] = ta; v[1] = tb; v[2] = tc;
+      d[0] = tda; d[1] = tdb; d[2] = tdc;
+      return simplexToPolytope3(v[0], d[0], v[1], d[1], v[2], d[2], thr, p0, p1);
     } else if (sx.rank == 3) {
       return simplexToPolytope3(v[0], d[0], v[1], d[1], v[2], d[2], thr, p0, p1);
     } else if (sx.rank == 2) {
@@ -590,7 +606,7 @@ struct EpaWarp {
     if (cls != bcls) return cls < bcls;
     return seq > bseq;
   }
-  FCLB_DN Feature nearest(bool exclude_vertex) const {
+  FCLB_DI Feature nearest(bool exclude_vertex) const {
     S bd = S(INFINITY);
     int bcls = 3, bseq = -1, bidx = -1;
     if (!exclude_vertex) {
@@ -635,7 +651,7 @@ struct EpaWarp {
 
   // ComputeFaceNormalPointingOutward (epa_polytope.hpp:348-410).  `par`: the
   // caller is warp-uniform and the rare all-vertex pass may use all lanes.
-  FCLB_DN bool faceNormal(int f, V3<S>& normal, S* area, bool par) const {
+  FCLB_DI bool faceNormal(int f, V3<S>& normal, S* area, bool par) const {
     const V3<S> a = P.vloc(P.f_a[f]), b = P.vloc(P.f_b[f]), c = P.vloc(P.f_c[f]);
     const V3<S> e1 = a - b, e2 = b - c;
     const V3<S> cr = cross(e1, e2);
@@ -675,7 +691,7 @@ struct EpaWarp {
     return true;
   }
   // IsPointOutsidePolytopeFace (epa_polytope_expand.hpp:13-31), threshold 0
-  FCLB_DN bool pointOutsideFace(int f, const V3<S>& pt, bool par) const {
+  FCLB_DI bool pointOutsideFace(int f, const V3<S>& pt, bool par) const {
     V3<S> n;
     S area = S(0);
     if (!faceNormal(f, n, &area, par)) return area <= S(0);
@@ -684,7 +700,7 @@ struct EpaWarp {
   }
 
   // findNextSupportDirection (epa.hpp:11-113): 0 OK, 1 Failed, 2 Converge
-  FCLB_DN int faceCandidate(int f, bool try_witness, const V3<S>& witness, S dist_sq, S tol, V3<S>& next_d, V3<S>& next_v,
+  FCLB_DI int faceCandidate(int f, bool try_witness, const V3<S>& witness, S dist_sq, S tol, V3<S>& next_d, V3<S>& next_v,
                             int& start_face) {
     const S outer_thr = S(1e-3) * S(1e-3);
     V3<S> fn;
@@ -710,7 +726,7 @@ struct EpaWarp {
   }
 
   // ExpandPolytope (epa_polytope_expand.hpp:33-91): 0 OK, 1 Failed, 2 MallocFailed
-  FCLB_DN int expand(const V3<S>& nv, const V3<S>& nd, int start_face) {
+  FCLB_DI int expand(const V3<S>& nv, const V3<S>& nd, int start_face) {
     // initVisibilityCacheVariables + visibility predicate of EVERY face
     for (int i = lane; i < v_hw; i += T) {
       P.v_rm[i] = 1;
@@ -888,7 +904,7 @@ struct EpaWarp {
   };
 
   // assignPenetrationPairFromSegment (epa.hpp:377-433)
-  FCLB_DN bool pairFromSegment(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
+  FCLB_DI bool pairFromSegment(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
     depth = fsqrt(f.md.dist_sq);
     const V3<S> p = f.md.witness;
     const V3<S> a_to_b = f.b - f.a;
@@ -917,7 +933,7 @@ struct EpaWarp {
     return true;
   }
   // assignPenetrationPairFromFace (epa.hpp:436-497)
-  FCLB_DN bool pairFromFace(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
+  FCLB_DI bool pairFromFace(const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
     depth = fsqrt(f.md.dist_sq);
     const V3<S> p = f.md.witness;
     const V3<S> dl0 = f.a - f.b, dl1 = f.b - f.c, dl2 = f.c - f.a;
@@ -937,7 +953,7 @@ struct EpaWarp {
     return true;
   }
   // assignPenetrationPair (epa.hpp:341-375)
-  FCLB_DN void assignPair(const V3<S>& cand_d, const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
+  FCLB_DI void assignPair(const V3<S>& cand_d, const RawFeature& f, S& depth, V3<S>& p0, V3<S>& p1) {
     if (f.cls == 0) {
       supportBoth(f.da, p0, p1);
       depth = norm(f.a);
@@ -952,7 +968,7 @@ struct EpaWarp {
   }
 
   // checkTerminateCondition (epa.hpp:269-298)
-  FCLB_DN bool converged(const RawFeature& f, const V3<S>& new_v, S tol) const {
+  FCLB_DI bool converged(const RawFeature& f, const V3<S>& new_v, S tol) const {
     S delta_sq;
     if (f.cls == 1) {
       delta_sq = pointToSegment(new_v, f.a, f.b).dist_sq;
@@ -964,7 +980,7 @@ struct EpaWarp {
   }
 
   // evaluateFromInitializedPolytope (epa.hpp:137-237)
-  FCLB_DN int run(int max_iterations, S tol, S& depth, V3<S>& p0, V3<S>& p1) {
+  FCLB_DI int run(int max_iterations, S tol, S& depth, V3<S>& p0, V3<S>& p1) {
     int iteration = 0;
     while (true) {
       Feature nf = nearest(false);
