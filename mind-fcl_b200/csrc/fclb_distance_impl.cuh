@@ -97,10 +97,13 @@ __global__ void __launch_bounds__(kBlock) distanceClosedKernel(BatchView b, S ep
 // only the (short) state update diverges; a lane that finishes a query
 // immediately fetches its next one (persistent, strided), so early finishers do
 // not idle.  Arithmetic and decision order per query are unchanged.
+#ifndef FCLB_GJK_MIN_BLOCKS
+#define FCLB_GJK_MIN_BLOCKS 6
+#endif
 enum GjkPhase : int { PH_FETCH = 0, PH_BOOL_FIRST = 1, PH_BOOL = 2, PH_DIST = 3, PH_EXTRACT = 4 };
 
 template <typename S, int T0, int T1>
-__global__ void __launch_bounds__(kBlock) distanceGjkKernel(BatchView b, S tol, int max_iter, DistanceOut out) {
+__global__ void __launch_bounds__(kBlock, FCLB_GJK_MIN_BLOCKS) distanceGjkKernel(BatchView b, S tol, int max_iter, DistanceOut out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SlotStore<S> st;
   st.base = reinterpret_cast<S*>(smem_raw) + threadIdx.x;
