@@ -165,6 +165,20 @@ int fclb_gjk_epa_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const voi
  * integration); the device copy is immutable. */
 int fclb_bvh_upload(const void* obb, const int32_t* first_child, int n_nodes, const void* tri_verts, int n_tris,
                     int scalar_type, fclb_handle* bvh);
+/* Host-side mirror of BVHModel<OBBRSS<S>>::beginModel / addSubModel / endModel
+ * (geometry/bvh/BVH_model-inl.h:402-570; OBBRSS fitter detail/BV_fitter-inl.h:324-345;
+ * mean split detail/BV_splitter-inl.h:361-372): builds the tree on the host with the
+ * reference's arithmetic (node-for-node identical OBBs) and uploads it.
+ * verts: n_verts x 3 doubles (rounded once to S); tris: n_tris x 3 vertex indices. */
+int fclb_bvh_build(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type,
+                   fclb_handle* bvh);
+/* same builder, host only (no GPU needed): obb / first_child / tri_verts must hold
+ * 15*(2*n_tris-1) S / (2*n_tris-1) / 9*n_tris S entries; *n_nodes = nodes written. */
+int fclb_bvh_build_host(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type, void* obb,
+                        int32_t* first_child, void* tri_verts, int* n_nodes);
+int fclb_bvh_info(fclb_handle bvh, int* n_nodes, int* n_tris, int* scalar_type);
+/* copies the tree back in the fclb_bvh_upload layout (any pointer may be NULL) */
+int fclb_bvh_export(fclb_handle bvh, void* obb, int32_t* first_child, void* tri_verts);
 int fclb_bvh_release(fclb_handle bvh);
 /* fcl::collide(BVHModel<OBBRSS>, tf1, BVHModel<OBBRSS>, tf2, request, result) per query
  * (-> OrientedNodeBVHSolver::MeshIntersect, traversal/collision/bvh_solver-inl.h:75).

@@ -26,8 +26,10 @@
 // reference's DFS-first pair (SURVEY.md 7 "Traversal-order-dependent outputs");
 // out_first_pair holds *a* colliding triangle pair.
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
+#include "fclb_bvh_build.h"
 #include "fclb_engine.h"
 #include "fclb_math.cuh"
 
@@ -38,6 +40,9 @@ struct BvhDev {
   void* tris = nullptr;   // 12 S per triangle (3 x {x,y,z,pad})
   int n_nodes = 0, n_tris = 0;
   int scalar_type = 0;
+  // host copy in the upload layout (fclb_bvh_export)
+  std::vector<unsigned char> h_obb, h_tri;
+  std::vector<int32_t> h_child;
 };
 
 static std::map<fclb_handle, BvhDev*>& bvhTable() {
@@ -415,6 +420,9 @@ static int uploadBvh(BvhDev* d, const void* obb, const int32_t* first_child, int
   FCLB_CUDA(cudaMalloc(&d->tris, tris.size() * sizeof(S)));
   FCLB_CUDA(cudaMemcpy(d->nodes, nodes.data(), nodes.size() * sizeof(S), cudaMemcpyHostToDevice));
   FCLB_CUDA(cudaMemcpy(d->tris, tris.data(), tris.size() * sizeof(S), cudaMemcpyHostToDevice));
+  d->h_obb.assign(reinterpret_cast<const unsigned char*>(o), reinterpret_cast<const unsigned char*>(o + size_t(15) * n_nodes));
+  d->h_tri.assign(reinterpret_cast<const unsigned char*>(tv), reinterpret_cast<const unsigned char*>(tv + size_t(9) * n_tris));
+  d->h_child.assign(first_child, first_child + n_nodes);
   return FCLB_OK;
 }
 
@@ -451,6 +459,68 @@ int fclb_bvh_upload(const void* obb, const int32_t* first_child, int n_nodes, co
   const fclb_handle hd = e.next_handle++;
   bvhTable()[hd] = d;
   *h = hd;
+  return FCLB_OK;
+}
+
+int fclb_bvh_build(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type, fclb_handle* h) {
+  if (!verts || !tris || !h || n_verts <= 0 || n_tris <= 0) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build: null or empty input");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  for (size_t i = 0; i < size_t(3) * n_tris; i++)
+    if (tris[i] < 0 || tris[i] >= n_verts) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build: vertex index out of range");
+  if (scalar_type == FCLB_F32) {
+    hostbuild::TreeOut<float> t;
+    hostbuild::buildObbTree<float>(verts, n_verts, tris, n_tris, t);
+    return fclb_bvh_upload(t.obb.data(), t.first_child.data(), int(t.first_child.size()), t.tri.data(), n_tris, scalar_type, h);
+  }
+  hostbuild::TreeOut<double> t;
+  hostbuild::buildObbTree<double>(verts, n_verts, tris, n_tris, t);
+  return fclb_bvh_upload(t.obb.data(), t.first_child.data(), int(t.first_child.size()), t.tri.data(), n_tris, scalar_type, h);
+}
+
+int fclb_bvh_build_host(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type, void* obb,
+                        int32_t* first_child, void* tri_verts, int* n_nodes) {
+  if (!verts || !tris || n_verts <= 0 || n_tris <= 0) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build_host: null or empty input");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  for (size_t i = 0; i < size_t(3) * n_tris; i++)
+    if (tris[i] < 0 || tris[i] >= n_verts) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build_host: vertex index out of range");
+  auto emit = [&](auto& t) {
+    if (obb) memcpy(obb, t.obb.data(), t.obb.size() * sizeof(t.obb[0]));
+    if (first_child) memcpy(first_child, t.first_child.data(), t.first_child.size() * sizeof(int32_t));
+    if (tri_verts) memcpy(tri_verts, t.tri.data(), t.tri.size() * sizeof(t.tri[0]));
+    if (n_nodes) *n_nodes = int(t.first_child.size());
+  };
+  if (scalar_type == FCLB_F32) {
+    hostbuild::TreeOut<float> t;
+    hostbuild::buildObbTree<float>(verts, n_verts, tris, n_tris, t);
+    emit(t);
+  } else {
+    hostbuild::TreeOut<double> t;
+    hostbuild::buildObbTree<double>(verts, n_verts, tris, n_tris, t);
+    emit(t);
+  }
+  return FCLB_OK;
+}
+
+int fclb_bvh_info(fclb_handle h, int* n_nodes, int* n_tris, int* scalar_type) {
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = bvhTable().find(h);
+  if (it == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_info: unknown handle");
+  if (n_nodes) *n_nodes = it->second->n_nodes;
+  if (n_tris) *n_tris = it->second->n_tris;
+  if (scalar_type) *scalar_type = it->second->scalar_type;
+  return FCLB_OK;
+}
+
+int fclb_bvh_export(fclb_handle h, void* obb, int32_t* first_child, void* tri_verts) {
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = bvhTable().find(h);
+  if (it == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_export: unknown handle");
+  const BvhDev* d = it->second;
+  if (obb) memcpy(obb, d->h_obb.data(), d->h_obb.size());
+  if (first_child) memcpy(first_child, d->h_child.data(), d->h_child.size() * sizeof(int32_t));
+  if (tri_verts) memcpy(tri_verts, d->h_tri.data(), d->h_tri.size());
   return FCLB_OK;
 }
 

@@ -122,6 +122,11 @@ def load() -> C.CDLL:
         lib.fclb_bvh_collide_batch_host.argtypes = bvh_args
         lib.fclb_bvh_collide_batch_dev.argtypes = bvh_args
         lib.fclb_bvh_last_visit_counts.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    if hasattr(lib, "fclb_bvh_build"):
+        lib.fclb_bvh_build.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        lib.fclb_bvh_build_host.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_int)]
+        lib.fclb_bvh_info.argtypes = [C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.fclb_bvh_export.argtypes = [C.c_uint64, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -265,6 +270,41 @@ def bvh_upload(obb: np.ndarray, first_child: np.ndarray, tri_verts: np.ndarray, 
     h = C.c_uint64()
     check(load().fclb_bvh_upload(_ptr(obb), _ptr(fc), len(fc), _ptr(tv), tv.size // 9, scalar_type, C.byref(h)))
     return h.value
+
+
+def bvh_build(verts: np.ndarray, tris: np.ndarray, scalar_type) -> int:
+    """BVHModel<OBBRSS<S>> beginModel/addSubModel/endModel on the host + upload."""
+    v = np.ascontiguousarray(verts, np.float64)
+    t = np.ascontiguousarray(tris, np.int32)
+    h = C.c_uint64()
+    check(load().fclb_bvh_build(_ptr(v), len(v), _ptr(t), len(t), scalar_type, C.byref(h)))
+    return h.value
+
+
+def bvh_build_host(verts: np.ndarray, tris: np.ndarray, scalar_type):
+    """The host builder alone (no GPU): returns (obb [n,15], first_child [n], tri_verts [t,9])."""
+    v = np.ascontiguousarray(verts, np.float64)
+    t = np.ascontiguousarray(tris, np.int32)
+    dt = np_dtype(scalar_type)
+    cap = 2 * len(t) - 1
+    obb = np.zeros((cap, 15), dt)
+    fc = np.zeros(cap, np.int32)
+    tv = np.zeros((len(t), 9), dt)
+    n = C.c_int()
+    check(load().fclb_bvh_build_host(_ptr(v), len(v), _ptr(t), len(t), scalar_type, _ptr(obb), _ptr(fc), _ptr(tv),
+                                     C.byref(n)))
+    return obb[:n.value], fc[:n.value], tv
+
+
+def bvh_export(h: int):
+    n, t, st = C.c_int(), C.c_int(), C.c_int()
+    check(load().fclb_bvh_info(h, C.byref(n), C.byref(t), C.byref(st)))
+    dt = np_dtype(st.value)
+    obb = np.zeros((n.value, 15), dt)
+    fc = np.zeros(n.value, np.int32)
+    tv = np.zeros((t.value, 9), dt)
+    check(load().fclb_bvh_export(h, _ptr(obb), _ptr(fc), _ptr(tv)))
+    return obb, fc, tv
 
 
 def bvh_release(h: int) -> None:
