@@ -195,6 +195,23 @@ int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* p
 /* BV-pair and leaf-pair tests executed by the most recent mesh batch call */
 int fclb_bvh_last_visit_counts(uint64_t* n_bv, uint64_t* n_leaf);
 
+/* ---- mesh vs shape ----------------------------------------------------------------
+ * fcl::collide(BVHModel<OBBRSS>, tf_mesh, Shape, tf_shape, request, result) per query
+ * (collision_func_matrix-inl.h:390-408 -> OrientedNodeBVHSolver::MeshShapeIntersect,
+ * traversal/collision/bvh_solver-inl.h:8-72; leaf = GJKSolver::shapeTriangleIntersect,
+ * gjk_solver-inl.h:540-600).  shape_ids[q] indexes the shape table.
+ * request.penetration_mode must be FCLB_PEN_DISABLED (boolean / counting collide):
+ *   out_counts[q]    = result.numContacts() = min(#triangles hit, max_contacts)
+ *   out_first_tri[q] = b1 of ONE hit triangle or -1 (optional; not necessarily the DFS-first) */
+int fclb_bvh_shape_collide_batch_host(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids,
+                                      const void* poses_mesh, const void* poses_shape, size_t n, int scalar_type,
+                                      const fclb_request* req, uint32_t* out_counts, int32_t* out_first_tri);
+int fclb_bvh_shape_collide_batch_dev(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids,
+                                     const void* poses_mesh, const void* poses_shape, size_t n, int scalar_type,
+                                     const fclb_request* req, uint32_t* out_counts, int32_t* out_first_tri);
+/* node tests and leaf (shape-triangle / shape-pixel) tests of the most recent scene batch call */
+int fclb_scene_last_visit_counts(uint64_t* n_node, uint64_t* n_leaf);
+
 /* kernel launches issued by this process so far (bench.py's gpu_launches) */
 uint64_t fclb_launch_count(void);
 /* device time (ms, CUDA events on the engine's stream) of the most recent batch

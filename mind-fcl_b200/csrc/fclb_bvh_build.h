@@ -21,6 +21,12 @@
 #include <limits>
 #include <vector>
 
+#ifdef __CUDACC__
+#define FCLB_HD __host__ __device__
+#else
+#define FCLB_HD
+#endif
+
 namespace fclb {
 namespace hostbuild {
 
@@ -37,7 +43,7 @@ struct P3 {
 // The literal types (0.2, 100.0, 0.5, 1.0 are double; 1 is int) decide where a
 // float instantiation computes in double -- they are kept on purpose.
 template <typename S>
-bool jacobi3(const S m[3][3], S d[3], S vec[3][3]) {
+FCLB_HD bool jacobi3(const S m[3][3], S d[3], S vec[3][3]) {
   S R[3][3];
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) {
@@ -108,7 +114,7 @@ bool jacobi3(const S m[3][3], S d[3], S vec[3][3]) {
 // axisFromEigen (Matrix3 overload): columns 0/1 = eigenvectors of the largest /
 // middle eigenvalue, column 2 = their cross product.  axis is row-major 3x3.
 template <typename S>
-void axesFromEigen(const S vec[3][3], const S d[3], S axis[9]) {
+FCLB_HD void axesFromEigen(const S vec[3][3], const S d[3], S axis[9]) {
   int mn, md, mx;
   if (d[0] > d[1]) {
     mx = 0;

@@ -1,0 +1,406 @@
+// fclb_bvh_shape_impl.cuh -- batched mesh-shape collide: BVHModel<OBBRSS> vs one
+// convex shape per query, ONE WARP PER QUERY.
+//
+// Reference path (results contract):
+//   fcl::collide(BVH, tf1, Shape, tf2) -> BVHShapeCollider<OBBRSS, Shape>
+//     -> orientedBVHShapeCollide (collision_func_matrix-inl.h:390-408)
+//     -> OrientedNodeBVHSolver::MeshShapeIntersect (traversal/collision/bvh_solver-inl.h:8-72)
+//   shape BV: computeBV<OBBRSS, Shape> = fit(getBoundVertices(tf2)) (geometry/shape/utility-inl.h:62-69
+//     -> math/bv/utility-inl.h:133-146 fitn: covariance, eigen_old, axisFromEigen, extent/centre)
+//   node test: overlap(tf1.R, tf1.t, shape_bv, node_bv) -> OBB only (math/bv/OBB-inl.h:305-436)
+//   leaf: ShapeSimplexIntersect (shape_pair_intersect-inl.h:133-198) -> GJKSolver::shapeTriangleIntersect
+//     (gjk_solver-inl.h:540-600): Sphere -> sphereTriangleIntersect (sphere_triangle-inl.h:108-186),
+//     Box -> boxTriangleIntersect (box_triangle-inl.h:8-150), every other shape -> MPR on the
+//     Minkowski difference (shape, triangle) (gjk_solver-inl.h:452-477); MPR "Failed" counts as no hit.
+// The reference walks one node at a time from a std::stack; the number of
+// intersecting triangles does not depend on the visiting order, so the warp pops
+// up to 32 nodes per step (one per lane), compacts children / leaves with ballots
+// and runs the leaf routine on batches of 32 triangles.
+#pragma once
+#include "fclb_bound.h"
+#include "fclb_bvh.cuh"
+#include "fclb_bvh_build.h"
+#include "fclb_mpr.cuh"
+
+namespace fclb {
+
+// ---- fitn on the transformed bound vertices (math/bv/utility-inl.h:133-146) ----
+template <typename S, typename PointFn>
+FCLB_DI NodeD<S> fitObbPoints(int n, PointFn pt) {
+  S S1[3] = {0, 0, 0};
+  S c00 = 0, c11 = 0, c22 = 0, c01 = 0, c02 = 0, c12 = 0;
+  for (int i = 0; i < n; i++) {  // getCovariance, point-cloud branch (math/geometry-inl.h:757-768)
+    const V3<S> p = pt(i);
+    S1[0] += p.x;
+    S1[1] += p.y;
+    S1[2] += p.z;
+    c00 += (p.x * p.x);
+    c11 += (p.y * p.y);
+    c22 += (p.z * p.z);
+    c01 += (p.x * p.y);
+    c02 += (p.x * p.z);
+    c12 += (p.y * p.z);
+  }
+  const int n_points = n;
+  S M[3][3];
+  M[0][0] = c00 - S1[0] * S1[0] / n_points;
+  M[1][1] = c11 - S1[1] * S1[1] / n_points;
+  M[2][2] = c22 - S1[2] * S1[2] / n_points;
+  M[0][1] = c01 - S1[0] * S1[1] / n_points;
+  M[1][2] = c12 - S1[1] * S1[2] / n_points;
+  M[0][2] = c02 - S1[0] * S1[2] / n_points;
+  M[1][0] = M[0][1];
+  M[2][0] = M[0][2];
+  M[2][1] = M[1][2];
+  S d[3] = {0, 0, 0}, vec[3][3];
+  if (!hostbuild::jacobi3<S>(M, d, vec)) {
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) vec[i][j] = (i == j) ? S(1) : S(0);
+  }
+  NodeD<S> bv;
+  hostbuild::axesFromEigen<S>(vec, d, bv.axis.m);
+  // getExtentAndCenter_pointcloud (math/geometry-inl.h:116-144)
+  const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
+  V3<S> mn = mk<S>(big, big, big), mx = mk<S>(-big, -big, -big);
+  const V3<S> a0 = col(bv.axis, 0), a1 = col(bv.axis, 1), a2 = col(bv.axis, 2);
+  for (int i = 0; i < n; i++) {
+    const V3<S> p = pt(i);
+    const V3<S> proj = mk<S>(dot(a0, p), dot(a1, p), dot(a2, p));
+    if (proj.x > mx.x) mx.x = proj.x;
+    if (proj.x < mn.x) mn.x = proj.x;
+    if (proj.y > mx.y) mx.y = proj.y;
+    if (proj.y < mn.y) mn.y = proj.y;
+    if (proj.z > mx.z) mx.z = proj.z;
+    if (proj.z < mn.z) mn.z = proj.z;
+  }
+  const V3<S> o = mk<S>((mx.x + mn.x) / 2, (mx.y + mn.y) / 2, (mx.z + mn.z) / 2);
+  bv.To = mulMV(bv.axis, o);
+  bv.extent = mk<S>((mx.x - mn.x) * S(0.5), (mx.y - mn.y) * S(0.5), (mx.z - mn.z) * S(0.5));
+  bv.first_child = -1;
+  return bv;
+}
+
+// computeBV<OBBRSS<S>, Shape>(shape, tf, bv), OBB half
+template <typename S>
+FCLB_DI NodeD<S> shapeWorldObb(const ShapeInst<S>& sh, const BoundD<S>* __restrict__ bound, const Pose<S>& tf) {
+  if (sh.type == ST_CONVEX) {
+    const ConvexD<S>& c = *sh.cvx;
+    return fitObbPoints<S>(c.n_verts, [&](int i) { return apply(tf, loadVert(c.verts, i)); });
+  }
+  return fitObbPoints<S>(bound->n, [&](int i) { return apply(tf, loadVert(bound->v, i)); });
+}
+
+// ---- sphere_triangle-inl.h:50-186 (boolean part) ----
+template <typename S>
+FCLB_DI S segmentSqrDistance(const V3<S>& from, const V3<S>& to, const V3<S>& p, V3<S>& nearest) {
+  V3<S> diff = p - from;
+  const V3<S> v = to - from;
+  S t = dot(v, diff);
+  if (t > 0) {
+    const S dotVV = dot(v, v);
+    if (t < dotVV) {
+      t /= dotVV;
+      diff = diff - v * t;
+    } else {
+      t = 1;
+      diff = diff - v;
+    }
+  } else {
+    t = 0;
+  }
+  nearest = from + v * t;
+  return dot(diff, diff);
+}
+template <typename S>
+FCLB_DI bool projectInTriangle(const V3<S>& p1, const V3<S>& p2, const V3<S>& p3, const V3<S>& normal, const V3<S>& p) {
+  const V3<S> edge1 = p2 - p1, edge2 = p3 - p2, edge3 = p1 - p3;
+  const V3<S> p1_to_p = p - p1, p2_to_p = p - p2, p3_to_p = p - p3;
+  const S r1 = dot(cross(edge1, normal), p1_to_p);
+  const S r2 = dot(cross(edge2, normal), p2_to_p);
+  const S r3 = dot(cross(edge3, normal), p3_to_p);
+  return (r1 > 0 && r2 > 0 && r3 > 0) || (r1 <= 0 && r2 <= 0 && r3 <= 0);
+}
+template <typename S>
+FCLB_DI bool sphereTriangleIntersect(S radius, const V3<S>& center, const V3<S>& P1, const V3<S>& P2, const V3<S>& P3) {
+  V3<S> normal = normalized(cross(P2 - P1, P3 - P1));
+  const S radius_with_threshold = radius + numeric_eps<S>::value();
+  const V3<S> p1_to_center = center - P1;
+  S distance_from_plane = dot(p1_to_center, normal);
+  if (distance_from_plane < 0) {
+    distance_from_plane *= -1;
+    normal = normal * S(-1);
+  }
+  const bool is_inside_contact_plane = (distance_from_plane < radius_with_threshold);
+  bool has_contact = false;
+  V3<S> contact_point = zero3<S>();
+  if (is_inside_contact_plane) {
+    if (projectInTriangle(P1, P2, P3, normal, center)) {
+      has_contact = true;
+      contact_point = center - normal * distance_from_plane;
+    } else {
+      const S contact_capsule_radius_sqr = radius_with_threshold * radius_with_threshold;
+      V3<S> nearest_on_edge;
+      S distance_sqr = segmentSqrDistance(P1, P2, center, nearest_on_edge);
+      if (distance_sqr < contact_capsule_radius_sqr) {
+        has_contact = true;
+        contact_point = nearest_on_edge;
+      }
+      distance_sqr = segmentSqrDistance(P2, P3, center, nearest_on_edge);
+      if (distance_sqr < contact_capsule_radius_sqr) {
+        has_contact = true;
+        contact_point = nearest_on_edge;
+      }
+      distance_sqr = segmentSqrDistance(P3, P1, center, nearest_on_edge);
+      if (distance_sqr < contact_capsule_radius_sqr) {
+        has_contact = true;
+        contact_point = nearest_on_edge;
+      }
+    }
+  }
+  if (has_contact) {
+    const V3<S> contact_to_center = contact_point - center;
+    const S distance_sqr = sqnorm(contact_to_center);
+    if (distance_sqr < radius_with_threshold * radius_with_threshold) return true;
+  }
+  return false;
+}
+
+// ---- box_triangle-inl.h:8-150 ----
+template <typename S>
+FCLB_DI bool boxTriSeparatedByEdgeAxes(const V3<S>& h, const V3<S>& e0, const V3<S>& v0, const V3<S>& v1) {
+  const S ax = fabs_(e0.x), ay = fabs_(e0.y), az = fabs_(e0.z);
+#define FCLB_BT_AXIS(RAD, D0, D1)       \
+  {                                     \
+    const S r = (RAD);                  \
+    const S d0 = (D0), d1 = (D1);       \
+    if (d0 < d1) {                      \
+      if (d0 > r) return true;          \
+      if (d1 < -r) return true;         \
+    } else {                            \
+      if (d1 > r) return true;          \
+      if (d0 < -r) return true;         \
+    }                                   \
+  }
+  FCLB_BT_AXIS(h.y * az + h.z * ay, v0.y * e0.z - v0.z * e0.y, v1.y * e0.z - v1.z * e0.y)
+  FCLB_BT_AXIS(h.x * az + h.z * ax, v0.x * e0.z - v0.z * e0.x, v1.x * e0.z - v1.z * e0.x)
+  FCLB_BT_AXIS(h.x * ay + h.y * ax, v0.x * e0.y - v0.y * e0.x, v1.x * e0.y - v1.y * e0.x)
+#undef FCLB_BT_AXIS
+  return false;
+}
+template <typename S>
+FCLB_DI void findMinMax3(S a, S b, S c, S& mn, S& mx) {
+  mn = mx = a;
+  if (b < mn) mn = b;
+  if (b > mx) mx = b;
+  if (c < mn) mn = c;
+  if (c > mx) mx = c;
+}
+template <typename S>
+FCLB_DI bool boxTriangleOverlap(const V3<S>& h, const V3<S>& v0, const V3<S>& v1, const V3<S>& v2) {
+  S mn, mx;
+  findMinMax3(v0.x, v1.x, v2.x, mn, mx);
+  if (mx < -h.x || mn > h.x) return false;
+  findMinMax3(v0.y, v1.y, v2.y, mn, mx);
+  if (mx < -h.y || mn > h.y) return false;
+  findMinMax3(v0.z, v1.z, v2.z, mn, mx);
+  if (mx < -h.z || mn > h.z) return false;
+  const V3<S> e0 = v1 - v0;
+  if (boxTriSeparatedByEdgeAxes(h, e0, v0, v2)) return false;
+  const V3<S> e1 = v2 - v1;
+  if (boxTriSeparatedByEdgeAxes(h, e1, v1, v0)) return false;
+  const V3<S> e2 = v0 - v2;
+  if (boxTriSeparatedByEdgeAxes(h, e2, v0, v1)) return false;
+  const V3<S> nrm = cross(e0, e1);
+  V3<S> p_min, p_max;
+#define FCLB_BT_FACE(C)             \
+  if (nrm.C > S(0.0)) {             \
+    p_min.C = -h.C - v0.C;          \
+    p_max.C = h.C - v0.C;           \
+  } else {                          \
+    p_min.C = h.C - v0.C;           \
+    p_max.C = -h.C - v0.C;          \
+  }
+  FCLB_BT_FACE(x)
+  FCLB_BT_FACE(y)
+  FCLB_BT_FACE(z)
+#undef FCLB_BT_FACE
+  return dot(nrm, p_min) <= 0 && dot(nrm, p_max) >= 0;
+}
+
+// Per-query constants of the leaf routine.
+template <typename S>
+struct LeafCtx {
+  ShapeInst<S> shape;
+  Pose<S> tf_shape, tf_mesh;
+  M3<S> toshape1;    // tf_mesh.R^T * tf_shape.R        (gjk_solver-inl.h:466)
+  Pose<S> toshape0;  // tf_shape^-1 * tf_mesh           (gjk_solver-inl.h:467; box_triangle-inl.h:138)
+  S tol;
+  int max_iter;
+};
+
+// GJKSolver::shapeTriangleIntersect(s, tf1, P1, P2, P3, tf2, nullptr), boolean
+template <typename S, int T0>
+FCLB_DI bool shapeTriangleHit(const LeafCtx<S>& c, const V3<S> P[3]) {
+  const int type = (T0 == ST_DYNAMIC) ? c.shape.type : T0;
+  if (type == ST_SPHERE) {
+    return sphereTriangleIntersect(c.shape.p0, c.tf_shape.t, apply(c.tf_mesh, P[0]), apply(c.tf_mesh, P[1]),
+                                   apply(c.tf_mesh, P[2]));
+  } else if (type == ST_BOX) {
+    const V3<S> h = mk<S>(S(0.5) * c.shape.p0, S(0.5) * c.shape.p1, S(0.5) * c.shape.p2);
+    return boxTriangleOverlap(h, apply(c.toshape0, P[0]), apply(c.toshape0, P[1]), apply(c.toshape0, P[2]));
+  } else {
+    MinkDiff<S, T0, ST_TRIANGLE> md;
+    md.s0 = c.shape;
+    md.s1.type = ST_TRIANGLE;
+    md.s1.cvx = nullptr;
+    md.s1.tri[0] = P[0];
+    md.s1.tri[1] = P[1];
+    md.s1.tri[2] = P[2];
+    md.toshape1 = c.toshape1;
+    md.toshape0 = c.toshape0;
+    return mprIntersect<S>(md, c.max_iter, c.tol, nullptr) == MPR_INTERSECT;
+  }
+}
+
+constexpr int kBsWarps = kBvhShapeWarps;
+constexpr int kBsStackCap = 1024;
+constexpr int kBsLeafCap = 64;
+
+template <typename S, int T0>
+__global__ void __launch_bounds__(kBsWarps * 32) bvhShapeCollideKernel(BvhShapeArgs a) {
+  extern __shared__ __align__(16) int s_bs[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* stack = s_bs + size_t(warp) * (kBsStackCap + kBsLeafCap);
+  int* leafq = stack + kBsStackCap;
+  const S* __restrict__ nodes = static_cast<const S*>(a.nodes);
+  const S* __restrict__ tris = static_cast<const S*>(a.tris);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned long long st_bv = 0, st_leaf = 0;
+
+  while (true) {
+    unsigned long long q64 = 0;
+    if (lane == 0) q64 = atomicAdd(a.work_counter, 1ull);
+    q64 = __shfl_sync(0xffffffffu, q64, 0);
+    if (q64 >= a.n) break;
+    const size_t q = size_t(q64);
+    LeafCtx<S> ctx;
+    const uint32_t sid = a.shape_ids[q];
+    ctx.shape = bindShape(static_cast<const ShapeD<S>*>(a.shapes), static_cast<const ConvexD<S>*>(a.convex), sid);
+    ctx.tf_mesh = loadPose(static_cast<const S*>(a.poses_mesh), q);
+    ctx.tf_shape = loadPose(static_cast<const S*>(a.poses_shape), q);
+    ctx.toshape1 = mulMtM(ctx.tf_mesh.R, ctx.tf_shape.R);
+    ctx.toshape0 = compose(inverse(ctx.tf_shape), ctx.tf_mesh);
+    ctx.tol = S(a.tol);
+    ctx.max_iter = a.max_iter;
+    // every lane fits the same OBB (uniform control flow, no shuffles needed)
+    const NodeD<S> shape_bv = shapeWorldObb(ctx.shape, static_cast<const BoundD<S>*>(a.bound) + sid, ctx.tf_shape);
+
+    uint32_t count = 0;
+    int first = -1;
+    int sp = 1, nleaf = 0;
+    if (lane == 0) stack[0] = 0;
+    __syncwarp();
+    bool done = (a.max_contacts == 0);
+
+    while (!done && (sp > 0 || nleaf > 0)) {
+      if (sp > 0 && nleaf < 32) {
+        int take = sp < 32 ? sp : 32;
+        if (sp + take > kBsStackCap - 64) take = 1;
+        int id = -1;
+        if (lane < take) id = stack[sp - 1 - lane];
+        sp -= take;
+        __syncwarp();
+        bool expand = false, leaf = false;
+        int c0 = 0;
+        if (lane < take) {
+          const NodeD<S> nd = loadNode(nodes, id);
+          st_bv++;
+          if (obbOverlap(ctx.tf_mesh.R, ctx.tf_mesh.t, shape_bv, nd)) {
+            if (nd.first_child < 0) {
+              leaf = true;
+              c0 = -(nd.first_child + 1);
+            } else {
+              expand = true;
+              c0 = nd.first_child;
+            }
+          }
+        }
+        const unsigned em = __ballot_sync(0xffffffffu, expand);
+        const unsigned lm = __ballot_sync(0xffffffffu, leaf);
+        if (expand) {
+          const int pos = sp + 2 * __popc(em & lt_mask);
+          stack[pos] = c0;
+          stack[pos + 1] = c0 + 1;
+        }
+        if (leaf) leafq[nleaf + __popc(lm & lt_mask)] = c0;
+        sp += 2 * __popc(em);
+        nleaf += __popc(lm);
+        __syncwarp();
+      }
+      if (nleaf >= 32 || (sp == 0 && nleaf > 0)) {
+        const int batch = nleaf < 32 ? nleaf : 32;
+        bool hit = false;
+        int tri_id = -1;
+        if (lane < batch) {
+          tri_id = leafq[nleaf - 1 - lane];
+          V3<S> P[3];
+          loadTri(tris, tri_id, P);
+          st_leaf++;
+          hit = shapeTriangleHit<S, T0>(ctx, P);
+        }
+        nleaf -= batch;
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm) {
+          if (first < 0) first = __shfl_sync(0xffffffffu, tri_id, __ffs(hm) - 1);
+          count += uint32_t(__popc(hm));
+          if (count >= a.max_contacts) {
+            count = a.max_contacts;
+            done = true;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      a.counts[q] = count;
+      if (a.first_tri) a.first_tri[q] = first;
+    }
+    __syncwarp();
+  }
+  if (a.stats) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      st_bv += __shfl_xor_sync(0xffffffffu, st_bv, off);
+      st_leaf += __shfl_xor_sync(0xffffffffu, st_leaf, off);
+    }
+    if (lane == 0) {
+      atomicAdd(&a.stats[0], st_bv);
+      atomicAdd(&a.stats[1], st_leaf);
+    }
+  }
+}
+
+template <typename S>
+cudaError_t launchBvhShape(int type0, const BvhShapeArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = size_t(kBsWarps) * (kBsStackCap + kBsLeafCap) * sizeof(int);
+#define FCLB_BS_CASE(T)                                                                                          \
+  case T:                                                                                                        \
+    bvhShapeCollideKernel<S, T><<<grid, kBsWarps * 32, smem, st>>>(a);                                           \
+    break;
+  switch (type0) {
+    FCLB_BS_CASE(ST_BOX)
+    FCLB_BS_CASE(ST_SPHERE)
+    FCLB_BS_CASE(ST_ELLIPSOID)
+    FCLB_BS_CASE(ST_CAPSULE)
+    FCLB_BS_CASE(ST_CONE)
+    FCLB_BS_CASE(ST_CYLINDER)
+    FCLB_BS_CASE(ST_CONVEX)
+    default:
+      bvhShapeCollideKernel<S, ST_DYNAMIC><<<grid, kBsWarps * 32, smem, st>>>(a);
+      break;
+  }
+#undef FCLB_BS_CASE
+  return cudaGetLastError();
+}
+
+}  // namespace fclb

@@ -20,6 +20,7 @@
 #include <utility>
 #include <vector>
 
+#include "fclb_bound.h"
 #include "fclb_engine.h"
 #include "fclb_shapes.cuh"
 
@@ -184,6 +185,11 @@ static int buildShapeTable(Engine& e, ShapeTable* t, int st) {
   }
   FCLB_CUDA(cudaMalloc(&t->d_shapes[st], std::max<size_t>(1, h.size()) * sizeof(ShapeD<S>)));
   FCLB_CUDA(cudaMemcpy(t->d_shapes[st], h.data(), h.size() * sizeof(ShapeD<S>), cudaMemcpyHostToDevice));
+  // bounding polytopes of the primitives (getBoundVertices in the shape's own frame)
+  std::vector<BoundD<S>> bd(t->n);
+  for (uint32_t i = 0; i < t->n; i++) boundVertices<S>(t->host[i].type, h[i].p, bd[i]);
+  FCLB_CUDA(cudaMalloc(&t->d_bound[st], std::max<size_t>(1, bd.size()) * sizeof(BoundD<S>)));
+  FCLB_CUDA(cudaMemcpy(t->d_bound[st], bd.data(), bd.size() * sizeof(BoundD<S>), cudaMemcpyHostToDevice));
   return FCLB_OK;
 }
 
@@ -499,7 +505,10 @@ int fclb_release(fclb_handle h) {
   auto it = e.tables.find(h);
   if (it == e.tables.end()) return fail(FCLB_ERR_BAD_ARG, "fclb_release: unknown handle");
   for (int st = 0; st < 2; st++)
+  {
     if (it->second->d_shapes[st]) cudaFree(it->second->d_shapes[st]);
+    if (it->second->d_bound[st]) cudaFree(it->second->d_bound[st]);
+  }
   delete it->second;
   e.tables.erase(it);
   return FCLB_OK;

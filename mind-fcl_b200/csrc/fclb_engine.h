@@ -31,6 +31,7 @@ struct ConvexHost {
 
 struct ShapeTable {
   void* d_shapes[2] = {nullptr, nullptr};  // ShapeD<float>[], ShapeD<double>[]
+  void* d_bound[2] = {nullptr, nullptr};   // BoundD<float>[], BoundD<double>[] (fclb_bound.h)
   std::vector<fclb_shape> host;
   uint32_t n = 0;
   uint64_t convex_epoch = 0;

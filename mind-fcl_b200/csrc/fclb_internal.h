@@ -47,4 +47,28 @@ template <typename S>
 cudaError_t launchDistance(const BatchView& b, const SolverParams& sp, const DistanceOut& out, cudaStream_t st,
                            int* n_launches);
 
+constexpr int kBvhShapeWarps = 8;  // warps per CTA of the mesh-shape kernel
+// mesh-shape traversal (fclb_bvh_shape_impl.cuh, instantiated in fclb_bvh_shape_f32/f64.cu)
+struct BvhShapeArgs {
+  const void* nodes;
+  const void* tris;
+  const void* shapes;       // ShapeD<S>[]
+  const void* convex;       // ConvexD<S>[]
+  const void* bound;        // BoundD<S>[]
+  const uint32_t* shape_ids;  // per query index into the shape table
+  const void* poses_mesh;
+  const void* poses_shape;
+  size_t n;
+  uint32_t max_contacts;
+  double tol;
+  int max_iter;
+  uint32_t* counts;
+  int32_t* first_tri;
+  unsigned long long* work_counter;
+  unsigned long long* stats;  // [0] node tests, [1] leaf tests
+};
+
+template <typename S>
+cudaError_t launchBvhShape(int type0, const BvhShapeArgs& a, int grid, cudaStream_t st);
+
 }  // namespace fclb

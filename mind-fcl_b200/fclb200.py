@@ -30,7 +30,8 @@ EXPORTS = [
     "fclb_collide_batch_host", "fclb_collide_batch_dev",
     "fclb_gjk_epa_batch_host", "fclb_gjk_epa_batch_dev",
     "fclb_bvh_upload", "fclb_bvh_release", "fclb_bvh_collide_batch_host", "fclb_bvh_collide_batch_dev",
-    "fclb_bvh_last_visit_counts",
+    "fclb_bvh_last_visit_counts", "fclb_bvh_build", "fclb_bvh_build_host", "fclb_bvh_info", "fclb_bvh_export",
+    "fclb_bvh_shape_collide_batch_host", "fclb_bvh_shape_collide_batch_dev", "fclb_scene_last_visit_counts",
     "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -127,6 +128,11 @@ def load() -> C.CDLL:
         lib.fclb_bvh_build_host.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_int)]
         lib.fclb_bvh_info.argtypes = [C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.fclb_bvh_export.argtypes = [C.c_uint64, vp, vp, vp]
+    if hasattr(lib, "fclb_bvh_shape_collide_batch_host"):
+        bs_args = [C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp]
+        lib.fclb_bvh_shape_collide_batch_host.argtypes = bs_args
+        lib.fclb_bvh_shape_collide_batch_dev.argtypes = bs_args
+        lib.fclb_scene_last_visit_counts.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 
@@ -328,4 +334,30 @@ def bvh_collide_batch_dev(bvh1, bvh2, poses1, poses2, n, scalar_type, request: R
 def bvh_last_visit_counts():
     a, b = C.c_uint64(), C.c_uint64()
     check(load().fclb_bvh_last_visit_counts(C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def bvh_shape_collide_batch_host(bvh, table, shape_ids, poses_mesh, poses_shape, scalar_type, request: Request,
+                                 want_tri=False):
+    """fcl::collide(BVHModel<OBBRSS>, tf_mesh, Shape, tf_shape) per query; returns (counts, first_tri)."""
+    n = len(poses_mesh)
+    ids = np.ascontiguousarray(shape_ids, np.uint32)
+    counts = np.zeros(n, np.uint32)
+    tri = np.zeros(n, np.int32) if want_tri else None
+    check(load().fclb_bvh_shape_collide_batch_host(bvh, table, _ptr(ids), _ptr(poses_mesh), _ptr(poses_shape), n,
+                                                   scalar_type, C.cast(C.pointer(request), C.c_void_p), _ptr(counts),
+                                                   _ptr(tri)))
+    return counts, tri
+
+
+def bvh_shape_collide_batch_dev(bvh, table, shape_ids, poses_mesh, poses_shape, n, scalar_type, request: Request, counts,
+                                tri=None):
+    check(load().fclb_bvh_shape_collide_batch_dev(bvh, table, _ptr(shape_ids), _ptr(poses_mesh), _ptr(poses_shape), n,
+                                                  scalar_type, C.cast(C.pointer(request), C.c_void_p), _ptr(counts),
+                                                  _ptr(tri)))
+
+
+def scene_last_visit_counts():
+    a, b = C.c_uint64(), C.c_uint64()
+    check(load().fclb_scene_last_visit_counts(C.byref(a), C.byref(b)))
     return a.value, b.value

@@ -196,6 +196,22 @@ class RefOracle(_Oracle):
         f(_st(poses1.dtype), id1, id2, _p(poses1), _p(poses2), n, _p(n_bv), _p(n_leaf), _p(n_hit), threads)
         return n_bv, n_leaf, n_hit
 
+    # ---- mesh vs shape ----
+    def mesh_shape_collide_batch(self, mesh_id, shapes, shape_ids, poses_mesh, poses_shape, threads=1, want_tri=True,
+                                 **req):
+        n = len(poses_mesh)
+        ids = np.ascontiguousarray(shape_ids, np.uint32)
+        counts = np.zeros(n, np.uint32)
+        tri = np.zeros(n, np.int32) if want_tri else None
+        r = _request(**req)
+        arr = _shape_array(shapes)
+        f = self.fn("mesh_shape_collide_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(poses_mesh.dtype), mesh_id, C.cast(arr, C.c_void_p), len(shapes), _p(ids), _p(poses_mesh),
+          _p(poses_shape), n, C.cast(C.pointer(r), C.c_void_p), _p(counts), _p(tri), threads)
+        return counts, tri
+
 
 class PortOracle(_Oracle):
     prefix = "fclport_"

@@ -347,3 +347,9 @@ int fclref_gjk_epa_batch(int scalar_type, const void* shapes, int n_shapes, cons
 int fclref_hardware_threads(void) { return int(std::thread::hardware_concurrency()); }
 
 }  // extern "C"
+
+// shape factory for the other harness translation units (ref_harness_scene.cpp)
+namespace fclref {
+std::shared_ptr<fcl::ShapeBase<float>> makeShapeF(const void* rec) { return makeShape<float>(*static_cast<const ShapeRec*>(rec)); }
+std::shared_ptr<fcl::ShapeBase<double>> makeShapeD(const void* rec) { return makeShape<double>(*static_cast<const ShapeRec*>(rec)); }
+}  // namespace fclref

@@ -224,3 +224,9 @@ int fclref_bvh_visit_counts(int scalar_type, int id1, int id2, const void* poses
 }
 
 }  // extern "C"
+
+// mesh registry access for the other harness translation units (ref_harness_scene.cpp)
+namespace fclref {
+const fcl::BVHModel<fcl::OBBRSS<float>>* meshF(int id) { return get<float>(id); }
+const fcl::BVHModel<fcl::OBBRSS<double>>* meshD(int id) { return get<double>(id); }
+}  // namespace fclref
