@@ -209,6 +209,31 @@ int fclb_bvh_shape_collide_batch_host(fclb_handle bvh, fclb_handle shapes, const
 int fclb_bvh_shape_collide_batch_dev(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids,
                                      const void* poses_mesh, const void* poses_shape, size_t n, int scalar_type,
                                      const fclb_request* req, uint32_t* out_counts, int32_t* out_first_tri);
+/* ---- heightmap vs shape ----------------------------------------------------------
+ * LayeredHeightMap<S> (geometry/heightmap/layered_heightmap.h, flat_heightmap.h): the caller hands
+ * over the BOTTOM layer verbatim -- heights in millimetres, index = y * full_x + x
+ * (flat_heightmap-inl.h:121-124), full = 2 * half shape, half shapes powers of two -- plus the
+ * bottom resolution; the coarser layers (2x2 max, layered_heightmap-inl.h:77-101) are rebuilt here.
+ * upper_bound_mm: FlatHeightMap::height_upper_bound_in_mm (0 => the maximum height). */
+int fclb_heightmap_upload(const uint16_t* heights_mm, uint32_t full_x, uint32_t full_y, double resolution_x,
+                          double resolution_y, uint32_t upper_bound_mm, fclb_handle* hm);
+int fclb_heightmap_release(fclb_handle hm);
+/* Host-side mirror of FlatHeightMap<S>::updateHeightsByPointGenerationFunctor (flat_heightmap-inl.h:249-272):
+ * rasterises n_points (x, y, z doubles, rounded once to S) into heights_mm (2*half_x * 2*half_y, caller-zeroed
+ * or holding earlier heights).  Host only, no GPU needed. */
+int fclb_heightmap_build_host(const double* points, size_t n_points, double resolution_x, double resolution_y,
+                              uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, uint16_t* heights_mm);
+/* fcl::collide(HeightMapCollisionGeometry, tf_hm, Shape, tf_shape, request, result) per query
+ * (collision_func_matrix-inl.h:99-118 -> heightmap_solver_traverse-inl.h:23-118; leaf = pixel Box vs Shape,
+ * heightmap_solver_leaf-inl.h:10-31).  request.penetration_mode must be FCLB_PEN_DISABLED:
+ *   out_counts[q]      = result.numContacts() = min(#pixel boxes hit, max_contacts)
+ *   out_first_pixel[q] = b1 = encodePixel (x << 16 | y, heightmap_types.h:53-58) of ONE hit pixel or -1 */
+int fclb_heightmap_shape_collide_batch_host(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
+                                            const void* poses_hm, const void* poses_shape, size_t n, int scalar_type,
+                                            const fclb_request* req, uint32_t* out_counts, int32_t* out_first_pixel);
+int fclb_heightmap_shape_collide_batch_dev(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
+                                           const void* poses_hm, const void* poses_shape, size_t n, int scalar_type,
+                                           const fclb_request* req, uint32_t* out_counts, int32_t* out_first_pixel);
 /* node tests and leaf (shape-triangle / shape-pixel) tests of the most recent scene batch call */
 int fclb_scene_last_visit_counts(uint64_t* n_node, uint64_t* n_leaf);
 

@@ -71,4 +71,31 @@ struct BvhShapeArgs {
 template <typename S>
 cudaError_t launchBvhShape(int type0, const BvhShapeArgs& a, int grid, cudaStream_t st);
 
+// heightmap-shape scan (fclb_heightmap_impl.cuh, instantiated in fclb_heightmap_f32/f64.cu)
+constexpr int kHeightmapWarps = 8;
+struct HeightmapArgs {
+  const uint16_t* bottom;   // bottom layer, index = y * full_x + x (flat_heightmap-inl.h:121-124)
+  const uint16_t* coarse;   // layer `coarse_shift` levels above the bottom (max over 2^shift x 2^shift pixels)
+  int coarse_shift;
+  uint32_t coarse_full_x;
+  uint32_t full_x, full_y, half_x, half_y;
+  uint32_t upper_mm;        // height_upper_bound_in_mm
+  double res_x, res_y;      // bottom resolution (already rounded to S)
+  const void* shapes;
+  const void* convex;
+  const uint32_t* shape_ids;
+  const void* poses_hm;
+  const void* poses_shape;
+  size_t n;
+  uint32_t max_contacts;
+  double tol;
+  int max_iter;
+  uint32_t* counts;
+  int32_t* first_pixel;     // encodePixel = x << 16 | y (heightmap_types.h:53-58) or -1
+  unsigned long long* work_counter;
+  unsigned long long* stats;  // [0] pixels read, [1] pixel boxes tested
+};
+template <typename S>
+cudaError_t launchHeightmapShape(int type1, const HeightmapArgs& a, int grid, cudaStream_t st);
+
 }  // namespace fclb

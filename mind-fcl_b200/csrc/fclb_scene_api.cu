@@ -1,6 +1,8 @@
 // fclb_scene_api.cu -- C ABI entry points for shape-vs-scene queries:
 //   fclb_bvh_shape_collide_batch_{dev,host}   mesh (BVHModel<OBBRSS>) vs convex shape
 // Kernels: fclb_bvh_shape_impl.cuh (instantiated in fclb_bvh_shape_f32/f64.cu).
+#include <cmath>
+
 #include "fclb_bvh.cuh"
 #include "fclb_shapes.cuh"
 
@@ -60,6 +62,95 @@ static int bvhShapeDev(Engine& e, const BvhDev* m, const ShapeTable* t, const ui
   e.rec_count[0] = n;
   e.rec_ms[0] = ms;
   return FCLB_OK;
+}
+
+// ---- LayeredHeightMap<S> on the device ------------------------------------------
+struct HeightmapDev {
+  uint16_t* d_layers = nullptr;        // all layers, bottom first
+  std::vector<size_t> off;             // element offset of layer k (k = 0: bottom, k levels above it)
+  std::vector<uint32_t> fx, fy;        // full shape per layer
+  uint32_t half_x = 0, half_y = 0;     // bottom half shape
+  uint32_t upper_mm = 0;
+  double res_x = 0, res_y = 0;
+};
+static std::map<fclb_handle, HeightmapDev*>& hmTable() {
+  static std::map<fclb_handle, HeightmapDev*> t;
+  return t;
+}
+
+template <typename S>
+static int heightmapShapeDev(Engine& e, const HeightmapDev* hm, const ShapeTable* t, const uint32_t* shape_ids,
+                             const void* poses_hm, const void* poses_shape, size_t n, const fclb_request* req,
+                             uint32_t* counts, int32_t* first_pixel) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  if (!g_counters) FCLB_CUDA(cudaMalloc(&g_counters, 4 * sizeof(unsigned long long)));
+  FCLB_CUDA(cudaMemsetAsync(g_counters, 0, 4 * sizeof(unsigned long long), e.compute));
+  const SolverParams sp = solverParams(st, req->binary_tol, req->gjk_max_iter, req->distance_tol, req->epa_max_faces,
+                                       req->epa_max_iter, true);
+  HeightmapArgs a{};
+  const int shift = int(hm->off.size()) - 1 < 3 ? int(hm->off.size()) - 1 : 3;
+  a.bottom = hm->d_layers;
+  a.coarse = hm->d_layers + hm->off[shift];
+  a.coarse_shift = shift;
+  a.coarse_full_x = hm->fx[shift];
+  a.full_x = hm->fx[0];
+  a.full_y = hm->fy[0];
+  a.half_x = hm->half_x;
+  a.half_y = hm->half_y;
+  a.upper_mm = hm->upper_mm;
+  a.res_x = double(S(hm->res_x));
+  a.res_y = double(S(hm->res_y));
+  a.shapes = t->d_shapes[st];
+  a.convex = e.d_convex_tab[st];
+  a.shape_ids = shape_ids;
+  a.poses_hm = poses_hm;
+  a.poses_shape = poses_shape;
+  a.n = n;
+  a.max_contacts = req->max_contacts;
+  a.tol = sp.gjk_tol;
+  a.max_iter = sp.gjk_max_iter;
+  a.counts = counts;
+  a.first_pixel = first_pixel;
+  a.work_counter = g_counters;
+  a.stats = g_counters + 1;
+  const size_t need = (n + kHeightmapWarps - 1) / kHeightmapWarps;
+  const size_t cap = size_t(e.sms) * 4;
+  const int grid = int(need < cap ? need : cap);
+  FCLB_CUDA(cudaEventRecord(e.ev_call0, e.compute));
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  FCLB_CUDA(launchHeightmapShape<S>(tableUniformType(t), a, grid, e.compute));
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  e.launches += 1;
+  FCLB_CUDA(cudaMemcpyAsync(g_stats, g_counters + 1, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.last_ms = ms;
+  e.last_call_ms = ms;
+  e.n_rec = 1;
+  e.rec_kind[0] = -3;
+  e.rec_count[0] = n;
+  e.rec_ms[0] = ms;
+  return FCLB_OK;
+}
+
+// FlatHeightMap<S>::updateHeightsByPointGenerationFunctor (flat_heightmap-inl.h:249-272)
+template <typename S>
+static void heightsFromPoints(const double* pts, size_t n, S res_x, S res_y, uint32_t half_x, uint32_t half_y,
+                              uint16_t* heights) {
+  const uint32_t full_x = 2 * half_x, full_y = 2 * half_y;
+  for (size_t i = 0; i < n; i++) {
+    const S point_x = S(pts[3 * i]), point_y = S(pts[3 * i + 1]), point_z = S(pts[3 * i + 2]);
+    if (point_z < 0) continue;
+    const int x = floor(point_x / res_x) + uint16_t(half_x);
+    const int y = floor(point_y / res_y) + uint16_t(half_y);
+    const bool in_range = (x >= 0 && x < int(full_x) && y >= 0 && y < int(full_y));
+    if (in_range) {
+      const size_t index = size_t(uint16_t(y)) * full_x + uint16_t(x);
+      const int z = static_cast<uint16_t>(point_z * 1000);
+      if (heights[index] < z) heights[index] = static_cast<uint16_t>(z);
+    }
+  }
 }
 
 }  // namespace fclb
@@ -126,6 +217,154 @@ int fclb_bvh_shape_collide_batch_host(fclb_handle bvh, fclb_handle shapes, const
   if (rc) return rc;
   FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
   if (out_first_tri) FCLB_CUDA(cudaMemcpyAsync(out_first_tri, base + o_ft, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+int fclb_heightmap_build_host(const double* points, size_t n_points, double resolution_x, double resolution_y,
+                              uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, uint16_t* heights_mm) {
+  if (!points || !heights_mm || half_shape_x == 0 || half_shape_y == 0 || half_shape_x > 32767 || half_shape_y > 32767)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_build_host: bad argument");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (scalar_type == FCLB_F32)
+    heightsFromPoints<float>(points, n_points, float(resolution_x), float(resolution_y), half_shape_x, half_shape_y,
+                             heights_mm);
+  else
+    heightsFromPoints<double>(points, n_points, resolution_x, resolution_y, half_shape_x, half_shape_y, heights_mm);
+  return FCLB_OK;
+}
+
+int fclb_heightmap_upload(const uint16_t* heights_mm, uint32_t full_x, uint32_t full_y, double resolution_x,
+                          double resolution_y, uint32_t upper_bound_mm, fclb_handle* hm) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (!heights_mm || !hm || full_x < 2 || full_y < 2 || (full_x & 1) || (full_y & 1) || full_x > 65534 || full_y > 65534)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_upload: bad shape");
+  const uint32_t hx = full_x / 2, hy = full_y / 2;
+  if ((hx & (hx - 1)) || (hy & (hy - 1)))
+    return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_upload: half shapes must be powers of two (layered_heightmap-inl.h:15-16)");
+  if (!(resolution_x > 0) || !(resolution_y > 0)) return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_upload: bad resolution");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  HeightmapDev* d = new HeightmapDev();
+  d->half_x = hx;
+  d->half_y = hy;
+  d->res_x = resolution_x;
+  d->res_y = resolution_y;
+  // layers: bottom, then 2x2 max pooling while both half shapes exceed 1 (layered_heightmap-inl.h:17-48,77-101)
+  std::vector<std::vector<uint16_t>> layers;
+  layers.emplace_back(heights_mm, heights_mm + size_t(full_x) * full_y);
+  d->fx.push_back(full_x);
+  d->fy.push_back(full_y);
+  uint32_t nx = hx, ny = hy;
+  while (nx > 1 && ny > 1) {
+    const std::vector<uint16_t>& down = layers.back();
+    const uint32_t dfx = d->fx.back(), dfy = d->fy.back();
+    const uint32_t ufx = dfx / 2, ufy = dfy / 2;
+    std::vector<uint16_t> up(size_t(ufx) * ufy, 0);
+    for (uint32_t y = 0; y < dfy; y++)
+      for (uint32_t x = 0; x < dfx; x++) {
+        const uint16_t h = down[size_t(y) * dfx + x];
+        uint16_t& u = up[size_t(y / 2) * ufx + x / 2];
+        if (h > u) u = h;
+      }
+    layers.push_back(std::move(up));
+    d->fx.push_back(ufx);
+    d->fy.push_back(ufy);
+    nx /= 2;
+    ny /= 2;
+  }
+  uint32_t mx = 0;
+  for (uint16_t h : layers[0]) mx = h > mx ? h : mx;
+  d->upper_mm = upper_bound_mm > mx ? upper_bound_mm : mx;
+  size_t total = 0;
+  for (auto& l : layers) {
+    d->off.push_back(total);
+    total += l.size();
+  }
+  if (cudaMalloc(&d->d_layers, total * sizeof(uint16_t)) != cudaSuccess) {
+    delete d;
+    return fail(FCLB_ERR_CUDA, "fclb_heightmap_upload: cudaMalloc failed");
+  }
+  for (size_t k = 0; k < layers.size(); k++)
+    cudaMemcpy(d->d_layers + d->off[k], layers[k].data(), layers[k].size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+  const fclb_handle h = e.next_handle++;
+  hmTable()[h] = d;
+  *hm = h;
+  return FCLB_OK;
+}
+
+int fclb_heightmap_release(fclb_handle h) {
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = hmTable().find(h);
+  if (it == hmTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_release: unknown handle");
+  cudaFree(it->second->d_layers);
+  delete it->second;
+  hmTable().erase(it);
+  return FCLB_OK;
+}
+
+int fclb_heightmap_shape_collide_batch_dev(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
+                                           const void* poses_hm, const void* poses_shape, size_t n, int scalar_type,
+                                           const fclb_request* req, uint32_t* out_counts, int32_t* out_first_pixel) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = hmTable().find(hm);
+  if (it == hmTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown heightmap handle");
+  ShapeTable* t = findTable(e, shapes);
+  if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (!req || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null request / out_counts");
+  if (req->penetration_mode != FCLB_PEN_DISABLED)
+    return fail(FCLB_ERR_UNSUPPORTED, "heightmap-shape contact generation (penetration modes) is not on the device yet");
+  if (n == 0) return FCLB_OK;
+  if (!shape_ids || !poses_hm || !poses_shape) return fail(FCLB_ERR_BAD_ARG, "null input array");
+  if (scalar_type == FCLB_F32)
+    return heightmapShapeDev<float>(e, it->second, t, shape_ids, poses_hm, poses_shape, n, req, out_counts,
+                                    out_first_pixel);
+  return heightmapShapeDev<double>(e, it->second, t, shape_ids, poses_hm, poses_shape, n, req, out_counts,
+                                   out_first_pixel);
+}
+
+int fclb_heightmap_shape_collide_batch_host(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
+                                            const void* poses_hm, const void* poses_shape, size_t n, int scalar_type,
+                                            const fclb_request* req, uint32_t* out_counts, int32_t* out_first_pixel) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!shape_ids || !poses_hm || !poses_shape || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  {
+    ShapeTable* t = findTable(e, shapes);
+    if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
+    for (size_t q = 0; q < n; q++)
+      if (shape_ids[q] >= t->n) return fail(FCLB_ERR_BAD_ARG, "shape id out of range");
+  }
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t o_ids = 0;
+  const size_t o_p1 = alignUp(o_ids + n * 4, 256);
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_fp = alignUp(o_cnt + n * 4, 256);
+  const size_t total = alignUp(o_fp + n * 4, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_ids, shape_ids, n * 4, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses_hm, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses_shape, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  rc = fclb_heightmap_shape_collide_batch_dev(hm, shapes, reinterpret_cast<const uint32_t*>(base + o_ids), base + o_p1,
+                                              base + o_p2, n, scalar_type, req, reinterpret_cast<uint32_t*>(base + o_cnt),
+                                              out_first_pixel ? reinterpret_cast<int32_t*>(base + o_fp) : nullptr);
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  if (out_first_pixel)
+    FCLB_CUDA(cudaMemcpyAsync(out_first_pixel, base + o_fp, n * 4, cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }

@@ -32,6 +32,8 @@ EXPORTS = [
     "fclb_bvh_upload", "fclb_bvh_release", "fclb_bvh_collide_batch_host", "fclb_bvh_collide_batch_dev",
     "fclb_bvh_last_visit_counts", "fclb_bvh_build", "fclb_bvh_build_host", "fclb_bvh_info", "fclb_bvh_export",
     "fclb_bvh_shape_collide_batch_host", "fclb_bvh_shape_collide_batch_dev", "fclb_scene_last_visit_counts",
+    "fclb_heightmap_upload", "fclb_heightmap_release", "fclb_heightmap_build_host",
+    "fclb_heightmap_shape_collide_batch_host", "fclb_heightmap_shape_collide_batch_dev",
     "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -133,6 +135,13 @@ def load() -> C.CDLL:
         lib.fclb_bvh_shape_collide_batch_host.argtypes = bs_args
         lib.fclb_bvh_shape_collide_batch_dev.argtypes = bs_args
         lib.fclb_scene_last_visit_counts.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    if hasattr(lib, "fclb_heightmap_upload"):
+        lib.fclb_heightmap_upload.argtypes = [vp, u32, u32, C.c_double, C.c_double, u32, C.POINTER(C.c_uint64)]
+        lib.fclb_heightmap_release.argtypes = [C.c_uint64]
+        lib.fclb_heightmap_build_host.argtypes = [vp, sz, C.c_double, C.c_double, u32, u32, C.c_int, vp]
+        hs_args = [C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp]
+        lib.fclb_heightmap_shape_collide_batch_host.argtypes = hs_args
+        lib.fclb_heightmap_shape_collide_batch_dev.argtypes = hs_args
     _lib = lib
     return lib
 
@@ -361,3 +370,44 @@ def scene_last_visit_counts():
     a, b = C.c_uint64(), C.c_uint64()
     check(load().fclb_scene_last_visit_counts(C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def heightmap_build_host(points, resolution, half_shape, scalar_type, heights=None):
+    """FlatHeightMap<S>::updateHeightsByPointGenerationFunctor on the host: bottom-layer heights in mm."""
+    pts = np.ascontiguousarray(points, np.float64)
+    if heights is None:
+        heights = np.zeros((2 * half_shape, 2 * half_shape), np.uint16)
+    check(load().fclb_heightmap_build_host(_ptr(pts), len(pts), resolution, resolution, half_shape, half_shape,
+                                           scalar_type, _ptr(heights)))
+    return heights
+
+
+def heightmap_upload(heights, resolution, upper_bound_mm=0) -> int:
+    h = np.ascontiguousarray(heights, np.uint16)
+    out = C.c_uint64()
+    check(load().fclb_heightmap_upload(_ptr(h), h.shape[1], h.shape[0], resolution, resolution, upper_bound_mm,
+                                       C.byref(out)))
+    return out.value
+
+
+def heightmap_release(h: int) -> None:
+    check(load().fclb_heightmap_release(h))
+
+
+def heightmap_shape_collide_batch_host(hm, table, shape_ids, poses_hm, poses_shape, scalar_type, request: Request,
+                                       want_pixel=False):
+    n = len(poses_hm)
+    ids = np.ascontiguousarray(shape_ids, np.uint32)
+    counts = np.zeros(n, np.uint32)
+    pix = np.zeros(n, np.int32) if want_pixel else None
+    check(load().fclb_heightmap_shape_collide_batch_host(hm, table, _ptr(ids), _ptr(poses_hm), _ptr(poses_shape), n,
+                                                         scalar_type, C.cast(C.pointer(request), C.c_void_p),
+                                                         _ptr(counts), _ptr(pix)))
+    return counts, pix
+
+
+def heightmap_shape_collide_batch_dev(hm, table, shape_ids, poses_hm, poses_shape, n, scalar_type, request: Request,
+                                      counts, pix=None):
+    check(load().fclb_heightmap_shape_collide_batch_dev(hm, table, _ptr(shape_ids), _ptr(poses_hm), _ptr(poses_shape), n,
+                                                        scalar_type, C.cast(C.pointer(request), C.c_void_p),
+                                                        _ptr(counts), _ptr(pix)))

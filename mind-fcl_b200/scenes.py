@@ -224,3 +224,41 @@ def config_c3_poses(n: int, dtype, seed: int = 3003, extent: float = 2.5):
     poses2 = np.zeros((n, 12), dtype)
     poses2[:, 0] = poses2[:, 4] = poses2[:, 8] = 1
     return poses1, np.ascontiguousarray(poses2)
+
+
+# ---- heightmaps (config C4) ------------------------------------------------------
+def terrain_points(n_points: int, half_range: float, z_max: float = 0.3, seed: int = 4200):
+    """Random 3-D points over a smooth terrain (pattern of the reference's
+    test/geometry/heightmap/test_heightmap_bvh_collision.cpp:15-24: uniform x/y, bounded z);
+    a few points fall outside the map or below z = 0 on purpose (both are ignored by
+    FlatHeightMap::updateHeightsByPointGenerationFunctor)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    xy = rng.uniform(-1.05 * half_range, 1.05 * half_range, size=(n_points, 2))
+    k = rng.uniform(1.0, 3.0, size=(4, 2)) / half_range
+    ph = rng.uniform(0, 2 * np.pi, size=4)
+    base = sum(np.sin(xy @ k[i] + ph[i]) for i in range(4)) / 4.0
+    z = z_max * (0.45 + 0.45 * base) + rng.uniform(-0.03, 0.03, size=n_points) * z_max
+    return np.ascontiguousarray(np.concatenate([xy, z[:, None]], axis=1))
+
+
+def compose_poses(a: np.ndarray, b: np.ndarray, dtype) -> np.ndarray:
+    """Row-wise a * b for [n,12] pose arrays (float64 arithmetic, rounded once to dtype)."""
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    Ra, ta = a[:, :9].reshape(-1, 3, 3), a[:, 9:]
+    Rb, tb = b[:, :9].reshape(-1, 3, 3), b[:, 9:]
+    out = np.empty((len(a), 12), np.float64)
+    out[:, :9] = (Ra @ Rb).reshape(-1, 9)
+    out[:, 9:] = np.einsum("nij,nj->ni", Ra, tb) + ta
+    return np.ascontiguousarray(out.astype(dtype))
+
+
+def heightmap_query_poses(n: int, dtype, half_range: float, z_lo: float, z_hi: float, seed: int = 4300):
+    """Heightmap poses (random rigid) and shape poses expressed relative to the map:
+    shape translation uniform over the map footprint x [z_lo, z_hi], random rotation."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tf_hm = random_poses(rng, n, 1.0, np.float64)
+    local = random_poses(rng, n, 1.0, np.float64)
+    local[:, 9:11] = rng.uniform(-1.1 * half_range, 1.1 * half_range, size=(n, 2))
+    local[:, 11] = rng.uniform(z_lo, z_hi, size=n)
+    return np.ascontiguousarray(tf_hm.astype(dtype)), compose_poses(tf_hm, local, dtype)

@@ -212,6 +212,35 @@ class RefOracle(_Oracle):
           _p(poses_shape), n, C.cast(C.pointer(r), C.c_void_p), _p(counts), _p(tri), threads)
         return counts, tri
 
+    # ---- heightmaps ----
+    def heightmap_create(self, points, resolution, half_shape):
+        pts = np.ascontiguousarray(points, np.float64)
+        f = self.fn("heightmap_create")
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_int]
+        return int(f(_p(pts), len(pts), resolution, half_shape))
+
+    def heightmap_export(self, hm_id, dtype, half_shape):
+        h = np.zeros((2 * half_shape, 2 * half_shape), np.uint16)
+        f = self.fn("heightmap_export")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        upper = int(f(hm_id, _st(dtype), _p(h)))
+        return h, upper
+
+    def heightmap_shape_collide_batch(self, hm_id, shapes, shape_ids, poses_hm, poses_shape, threads=1, want_pixel=True,
+                                      **req):
+        n = len(poses_hm)
+        ids = np.ascontiguousarray(shape_ids, np.uint32)
+        counts = np.zeros(n, np.uint32)
+        pix = np.zeros(n, np.int32) if want_pixel else None
+        r = _request(**req)
+        arr = _shape_array(shapes)
+        f = self.fn("heightmap_shape_collide_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(poses_hm.dtype), hm_id, C.cast(arr, C.c_void_p), len(shapes), _p(ids), _p(poses_hm), _p(poses_shape), n,
+          C.cast(C.pointer(r), C.c_void_p), _p(counts), _p(pix), threads)
+        return counts, pix
+
 
 class PortOracle(_Oracle):
     prefix = "fclport_"

@@ -103,9 +103,92 @@ void meshShapeBatch(int mesh_id, const ShapeRec* shapes, uint32_t n_shapes, cons
   });
 }
 
+// ---- heightmaps -----------------------------------------------------------------
+struct HmRec {
+  std::shared_ptr<fcl::HeightMapCollisionGeometry<float>> f;
+  std::shared_ptr<fcl::HeightMapCollisionGeometry<double>> d;
+};
+std::vector<HmRec>& heightmaps() {
+  static std::vector<HmRec> t;
+  return t;
+}
+template <typename S>
+const fcl::HeightMapCollisionGeometry<S>* getHm(int id);
+template <>
+const fcl::HeightMapCollisionGeometry<float>* getHm<float>(int id) {
+  return heightmaps().at(id).f.get();
+}
+template <>
+const fcl::HeightMapCollisionGeometry<double>* getHm<double>(int id) {
+  return heightmaps().at(id).d.get();
+}
+
+template <typename S>
+std::shared_ptr<fcl::HeightMapCollisionGeometry<S>> buildHm(const double* pts, size_t n, double res, int half_shape) {
+  auto map = std::make_shared<fcl::heightmap::LayeredHeightMap<S>>(S(res), uint16_t(half_shape));
+  map->updateHeightsByPointGenerationFunctor(
+      [&](int i, S& x, S& y, S& z) {
+        x = S(pts[3 * size_t(i)]);
+        y = S(pts[3 * size_t(i) + 1]);
+        z = S(pts[3 * size_t(i) + 2]);
+      },
+      int(n));
+  return std::make_shared<fcl::HeightMapCollisionGeometry<S>>(map);
+}
+
+template <typename S>
+void hmShapeBatch(int hm_id, const ShapeRec* shapes, uint32_t n_shapes, const uint32_t* shape_ids, const S* poses_hm,
+                  const S* poses_shape, size_t n, const RequestRec* rq, uint32_t* counts, int32_t* first_pixel,
+                  int threads) {
+  const auto* hm = getHm<S>(hm_id);
+  std::vector<std::shared_ptr<fcl::ShapeBase<S>>> objs;
+  for (uint32_t i = 0; i < n_shapes; i++) objs.push_back(Sel<S>::shape(shapes + i));
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    const fcl::CollisionRequest<S> req = makeRequest<S>(rq);
+    for (size_t q = b; q < e; q++) {
+      fcl::CollisionResult<S> res;
+      const size_t c = fcl::collide<S>(hm, loadPose<S>(poses_hm + 12 * q), objs[shape_ids[q]].get(),
+                                       loadPose<S>(poses_shape + 12 * q), req, res);
+      counts[q] = uint32_t(c);
+      if (first_pixel) first_pixel[q] = c ? int32_t(res.getContact(0).b1) : -1;
+    }
+  });
+}
+
 }  // namespace
 
 extern "C" {
+
+int fclref_heightmap_create(const double* points, size_t n_points, double resolution, int half_shape) {
+  HmRec r;
+  r.f = buildHm<float>(points, n_points, resolution, half_shape);
+  r.d = buildHm<double>(points, n_points, resolution, half_shape);
+  heightmaps().push_back(r);
+  return int(heightmaps().size()) - 1;
+}
+/* bottom layer heights (mm), index = y * full_x + x; returns height_upper_bound_mm */
+int fclref_heightmap_export(int id, int scalar_type, uint16_t* heights) {
+  auto dump = [&](const auto* g) {
+    const auto& bottom = g->raw_heightmap()->bottom();
+    for (uint16_t y = 0; y < bottom.full_shape_y(); y++)
+      for (uint16_t x = 0; x < bottom.full_shape_x(); x++)
+        heights[size_t(y) * bottom.full_shape_x() + x] = bottom.pixelHeight(fcl::heightmap::Pixel(x, y));
+    return int(g->raw_heightmap()->height_upper_bound_mm());
+  };
+  return scalar_type == 0 ? dump(getHm<float>(id)) : dump(getHm<double>(id));
+}
+int fclref_heightmap_shape_collide_batch(int scalar_type, int hm_id, const void* shapes, uint32_t n_shapes,
+                                         const uint32_t* shape_ids, const void* poses_hm, const void* poses_shape,
+                                         size_t n, const void* request, uint32_t* counts, int32_t* first_pixel,
+                                         int threads) {
+  if (scalar_type == 0)
+    hmShapeBatch<float>(hm_id, (const ShapeRec*)shapes, n_shapes, shape_ids, (const float*)poses_hm,
+                        (const float*)poses_shape, n, (const RequestRec*)request, counts, first_pixel, threads);
+  else
+    hmShapeBatch<double>(hm_id, (const ShapeRec*)shapes, n_shapes, shape_ids, (const double*)poses_hm,
+                         (const double*)poses_shape, n, (const RequestRec*)request, counts, first_pixel, threads);
+  return 0;
+}
 
 int fclref_mesh_shape_collide_batch(int scalar_type, int mesh_id, const void* shapes, uint32_t n_shapes,
                                     const uint32_t* shape_ids, const void* poses_mesh, const void* poses_shape, size_t n,
