@@ -237,6 +237,45 @@ int fclb_heightmap_shape_collide_batch_dev(fclb_handle hm, fclb_handle shapes, c
 /* node tests and leaf (shape-triangle / shape-pixel) tests of the most recent scene batch call */
 int fclb_scene_last_visit_counts(uint64_t* n_node, uint64_t* n_leaf);
 
+/* ---- broadphase: device-side AABB tree ---------------------------------------------
+ * detail::BinaryAABB_Tree<S, Alloc> (broadphase/binary_AABB_tree.h:44-58, -inl.h:70-573) over
+ * BroadphaseObjectInfo{AABB, user_id} (broadphase/broadphase_common.h:13-22).
+ * aabbs: 6 S per object = min xyz, max xyz.  The reported pair SET equals the reference's
+ * ({(a,b): AABB_a overlaps AABB_b}, math/bv/AABB-inl.h:82-88); the order of the list, and for
+ * self pairs which id comes first, follow the device tree (Morton-order linear BVH), not the
+ * reference's median-split tree.  out_pairs: 2 ids per pair; *n_pairs = pairs found; if that
+ * exceeds cap the call returns FCLB_ERR_CAPACITY after writing the first cap pairs' worth of
+ * nothing useful -- call again with a larger buffer (out_pairs == NULL just counts). */
+int fclb_broadphase_build_host(const void* aabbs, const uint64_t* user_ids, size_t n, int scalar_type,
+                               fclb_handle* tree);                         /* Rebuild / BuildTreeExternal */
+int fclb_broadphase_build_dev(const void* aabbs, const uint64_t* user_ids, size_t n, int scalar_type,
+                              fclb_handle* tree);                          /* same, DEVICE input arrays  */
+int fclb_broadphase_release(fclb_handle tree);
+int fclb_broadphase_self_pairs_host(fclb_handle tree, uint64_t* out_pairs, size_t cap, size_t* n_pairs);  /* SelfCollision */
+int fclb_broadphase_self_pairs_dev(fclb_handle tree, uint64_t* out_pairs, size_t cap, size_t* n_pairs);   /* DEVICE out buffer */
+/* TreeCollision: pairs (id in tree_a, id in tree_b) */
+int fclb_broadphase_tree_pairs_host(fclb_handle tree_a, fclb_handle tree_b, uint64_t* out_pairs, size_t cap,
+                                    size_t* n_pairs);
+/* SingleObjectCollision for n query boxes: pairs (leaf id, object id) */
+int fclb_broadphase_query_pairs_host(fclb_handle tree, const void* aabbs, const uint64_t* object_ids, size_t n,
+                                     uint64_t* out_pairs, size_t cap, size_t* n_pairs);
+/* UpdateObjectAABB (binary_AABB_tree-inl.h:332-355) for n objects of a tree built with
+ * fclb_broadphase_build_host.  As in the reference the leaf box GROWS to old U new (node.bv += new_AABB);
+ * ancestors are refitted.  An unknown id fails the call (the reference returns false). */
+int fclb_broadphase_update_host(fclb_handle tree, const uint64_t* user_ids, const void* new_aabbs, size_t n);
+uint64_t fclb_broadphase_last_visits(void); /* node / leaf boxes tested by the most recent pair search */
+/* CollisionObject<S>::computeAABB (narrowphase/collision_object-inl.h:141-154) for n objects:
+ * out_aabbs = 6 S per object.  Tight translate when the rotation is the identity, else the
+ * bounding-sphere box centre +- aabb_radius. */
+int fclb_compute_aabb_batch_host(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n,
+                                 int scalar_type, void* out_aabbs);
+int fclb_compute_aabb_batch_dev(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n,
+                                int scalar_type, void* out_aabbs);
+/* candidate (object id, object id) pairs -> the per-query arrays fclb_collide_batch_dev consumes
+ * (pairs of shape-table indices, pose of the first and of the second object).  DEVICE pointers. */
+int fclb_gather_pairs_dev(const uint64_t* id_pairs, size_t n_pairs, const uint32_t* shape_ids, const void* poses,
+                          int scalar_type, fclb_pair* out_pairs, void* out_poses1, void* out_poses2);
+
 /* kernel launches issued by this process so far (bench.py's gpu_launches) */
 uint64_t fclb_launch_count(void);
 /* device time (ms, CUDA events on the engine's stream) of the most recent batch

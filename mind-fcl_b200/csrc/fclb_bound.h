@@ -9,6 +9,7 @@
 // Convex uses its own vertices (convex-inl.h:97-107) and is not tabulated here.
 #pragma once
 #include <cmath>
+#include <limits>
 #include <vector>
 
 #include "../../include/fclb200.h"
@@ -105,6 +106,69 @@ inline void boundVertices(uint32_t type, const S p[3], BoundD<S>& out) {
       break;
   }
   out.n = n;
+}
+
+// CollisionGeometry::aabb_local / aabb_center / aabb_radius as each shape's
+// computeLocalAABB() leaves them (box-inl.h:72-80, sphere-inl.h:54-61, ellipsoid-inl.h:64-71,
+// capsule-inl.h:56-64, cone-inl.h:55-63, cylinder-inl.h:56-64, convex-inl.h:77-87);
+// read by CollisionObject::computeAABB (narrowphase/collision_object-inl.h:141-154).
+template <typename S>
+struct LocalAabbD {
+  S mn[3], mx[3], center[3], radius;
+};
+
+template <typename S>
+inline void localAabb(uint32_t type, const S p[3], const double* convex_verts, int n_verts, LocalAabbD<S>& o) {
+  S d[3] = {0, 0, 0};
+  bool symmetric = true;
+  switch (type) {
+    case FCLB_BOX:
+      for (int k = 0; k < 3; k++) d[k] = S(0.5) * p[k];
+      break;
+    case FCLB_SPHERE:
+      d[0] = d[1] = d[2] = p[0];
+      break;
+    case FCLB_ELLIPSOID:
+      for (int k = 0; k < 3; k++) d[k] = p[k];
+      break;
+    case FCLB_CAPSULE:
+      d[0] = d[1] = p[0];
+      d[2] = S(0.5 * p[1] + p[0]);
+      break;
+    case FCLB_CONE:
+    case FCLB_CYLINDER:
+      d[0] = d[1] = p[0];
+      d[2] = S(0.5 * p[1]);
+      break;
+    default:
+      symmetric = false;
+      break;
+  }
+  if (symmetric) {
+    for (int k = 0; k < 3; k++) {
+      o.mx[k] = d[k];
+      o.mn[k] = -d[k];
+    }
+  } else {
+    const S big = std::numeric_limits<S>::max();
+    for (int k = 0; k < 3; k++) {
+      o.mn[k] = big;
+      o.mx[k] = -big;
+    }
+    for (int i = 0; i < n_verts; i++)
+      for (int k = 0; k < 3; k++) {
+        const S v = S(convex_verts[3 * size_t(i) + k]);
+        if (v < o.mn[k]) o.mn[k] = v;
+        if (v > o.mx[k]) o.mx[k] = v;
+      }
+  }
+  for (int k = 0; k < 3; k++) o.center[k] = (o.mn[k] + o.mx[k]) * S(0.5);
+  if (type == FCLB_SPHERE) {
+    o.radius = p[0];
+  } else {
+    const S e0 = o.mn[0] - o.center[0], e1 = o.mn[1] - o.center[1], e2 = o.mn[2] - o.center[2];
+    o.radius = std::sqrt((e0 * e0 + e1 * e1) + e2 * e2);
+  }
 }
 
 }  // namespace fclb

@@ -190,6 +190,14 @@ static int buildShapeTable(Engine& e, ShapeTable* t, int st) {
   for (uint32_t i = 0; i < t->n; i++) boundVertices<S>(t->host[i].type, h[i].p, bd[i]);
   FCLB_CUDA(cudaMalloc(&t->d_bound[st], std::max<size_t>(1, bd.size()) * sizeof(BoundD<S>)));
   FCLB_CUDA(cudaMemcpy(t->d_bound[st], bd.data(), bd.size() * sizeof(BoundD<S>), cudaMemcpyHostToDevice));
+  std::vector<LocalAabbD<S>> la(t->n);
+  for (uint32_t i = 0; i < t->n; i++) {
+    const bool cvx = t->host[i].type == FCLB_CONVEX;
+    const ConvexHost* c = cvx ? &e.convex[t->host[i].geom] : nullptr;
+    localAabb<S>(t->host[i].type, h[i].p, cvx ? c->h_verts.data() : nullptr, cvx ? c->n_verts : 0, la[i]);
+  }
+  FCLB_CUDA(cudaMalloc(&t->d_local[st], std::max<size_t>(1, la.size()) * sizeof(LocalAabbD<S>)));
+  FCLB_CUDA(cudaMemcpy(t->d_local[st], la.data(), la.size() * sizeof(LocalAabbD<S>), cudaMemcpyHostToDevice));
   return FCLB_OK;
 }
 
@@ -462,6 +470,7 @@ int fclb_convex_upload(const double* verts, int n_verts, const int* faces, int f
     if (kv.second != 2) watertight = false;
   c.walk = (n_verts > 32 && watertight && all_connected) ? 1 : 0;
   std::vector<double> vd(verts, verts + size_t(3) * n_verts);
+  c.h_verts = vd;
   std::vector<float> vf;
   std::vector<double> vdd;
   convexDerive<float>(vd, n_verts, c.seed[0], c.interior[0], vf);
@@ -508,6 +517,7 @@ int fclb_release(fclb_handle h) {
   {
     if (it->second->d_shapes[st]) cudaFree(it->second->d_shapes[st]);
     if (it->second->d_bound[st]) cudaFree(it->second->d_bound[st]);
+    if (it->second->d_local[st]) cudaFree(it->second->d_local[st]);
   }
   delete it->second;
   e.tables.erase(it);

@@ -24,6 +24,7 @@ struct ConvexHost {
   void* d_verts[2] = {nullptr, nullptr};
   int* d_nbr = nullptr;
   int n_verts = 0;
+  std::vector<double> h_verts;  // 3 per vertex, as uploaded
   int walk = 0;
   int seed[2][6];
   double interior[2][3];
@@ -32,6 +33,7 @@ struct ConvexHost {
 struct ShapeTable {
   void* d_shapes[2] = {nullptr, nullptr};  // ShapeD<float>[], ShapeD<double>[]
   void* d_bound[2] = {nullptr, nullptr};   // BoundD<float>[], BoundD<double>[] (fclb_bound.h)
+  void* d_local[2] = {nullptr, nullptr};   // LocalAabbD<float>[], LocalAabbD<double>[] (fclb_bound.h)
   std::vector<fclb_shape> host;
   uint32_t n = 0;
   uint64_t convex_epoch = 0;

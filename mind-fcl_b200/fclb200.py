@@ -34,6 +34,10 @@ EXPORTS = [
     "fclb_bvh_shape_collide_batch_host", "fclb_bvh_shape_collide_batch_dev", "fclb_scene_last_visit_counts",
     "fclb_heightmap_upload", "fclb_heightmap_release", "fclb_heightmap_build_host",
     "fclb_heightmap_shape_collide_batch_host", "fclb_heightmap_shape_collide_batch_dev",
+    "fclb_broadphase_build_host", "fclb_broadphase_build_dev", "fclb_broadphase_release",
+    "fclb_broadphase_self_pairs_host", "fclb_broadphase_self_pairs_dev", "fclb_broadphase_tree_pairs_host",
+    "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
+    "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -142,6 +146,20 @@ def load() -> C.CDLL:
         hs_args = [C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp]
         lib.fclb_heightmap_shape_collide_batch_host.argtypes = hs_args
         lib.fclb_heightmap_shape_collide_batch_dev.argtypes = hs_args
+    if hasattr(lib, "fclb_broadphase_build_host"):
+        szp = C.POINTER(C.c_size_t)
+        lib.fclb_broadphase_build_host.argtypes = [vp, vp, sz, C.c_int, C.POINTER(C.c_uint64)]
+        lib.fclb_broadphase_build_dev.argtypes = [vp, vp, sz, C.c_int, C.POINTER(C.c_uint64)]
+        lib.fclb_broadphase_release.argtypes = [C.c_uint64]
+        lib.fclb_broadphase_self_pairs_host.argtypes = [C.c_uint64, vp, sz, szp]
+        lib.fclb_broadphase_self_pairs_dev.argtypes = [C.c_uint64, vp, sz, szp]
+        lib.fclb_broadphase_tree_pairs_host.argtypes = [C.c_uint64, C.c_uint64, vp, sz, szp]
+        lib.fclb_broadphase_query_pairs_host.argtypes = [C.c_uint64, vp, vp, sz, vp, sz, szp]
+        lib.fclb_broadphase_update_host.argtypes = [C.c_uint64, vp, vp, sz]
+        lib.fclb_broadphase_last_visits.restype = C.c_uint64
+        lib.fclb_compute_aabb_batch_host.argtypes = [C.c_uint64, vp, vp, sz, C.c_int, vp]
+        lib.fclb_compute_aabb_batch_dev.argtypes = [C.c_uint64, vp, vp, sz, C.c_int, vp]
+        lib.fclb_gather_pairs_dev.argtypes = [vp, sz, vp, vp, C.c_int, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -411,3 +429,58 @@ def heightmap_shape_collide_batch_dev(hm, table, shape_ids, poses_hm, poses_shap
     check(load().fclb_heightmap_shape_collide_batch_dev(hm, table, _ptr(shape_ids), _ptr(poses_hm), _ptr(poses_shape), n,
                                                         scalar_type, C.cast(C.pointer(request), C.c_void_p),
                                                         _ptr(counts), _ptr(pix)))
+
+
+# ---- broadphase ---------------------------------------------------------------------
+def compute_aabb_batch_host(table, shape_ids, poses, scalar_type):
+    """CollisionObject<S>::computeAABB per object: [n, 6] = min xyz, max xyz."""
+    ids = np.ascontiguousarray(shape_ids, np.uint32)
+    out = np.zeros((len(ids), 6), np_dtype(scalar_type))
+    check(load().fclb_compute_aabb_batch_host(table, _ptr(ids), _ptr(poses), len(ids), scalar_type, _ptr(out)))
+    return out
+
+
+def broadphase_build_host(aabbs, user_ids, scalar_type) -> int:
+    b = np.ascontiguousarray(aabbs, np_dtype(scalar_type))
+    ids = np.ascontiguousarray(user_ids, np.uint64)
+    h = C.c_uint64()
+    check(load().fclb_broadphase_build_host(_ptr(b), _ptr(ids), len(ids), scalar_type, C.byref(h)))
+    return h.value
+
+
+def broadphase_release(h: int) -> None:
+    check(load().fclb_broadphase_release(h))
+
+
+def _pairs_call(fn, *args):
+    """count, allocate, fetch: returns [m, 2] uint64"""
+    n = C.c_size_t()
+    check(fn(*args, None, 0, C.byref(n)))
+    out = np.zeros((n.value, 2), np.uint64)
+    if n.value:
+        check(fn(*args, _ptr(out), n.value, C.byref(n)))
+    return out
+
+
+def broadphase_self_pairs_host(tree):
+    return _pairs_call(load().fclb_broadphase_self_pairs_host, tree)
+
+
+def broadphase_tree_pairs_host(tree_a, tree_b):
+    return _pairs_call(load().fclb_broadphase_tree_pairs_host, tree_a, tree_b)
+
+
+def broadphase_query_pairs_host(tree, aabbs, object_ids, scalar_type):
+    b = np.ascontiguousarray(aabbs, np_dtype(scalar_type))
+    ids = np.ascontiguousarray(object_ids, np.uint64)
+    return _pairs_call(load().fclb_broadphase_query_pairs_host, tree, _ptr(b), _ptr(ids), len(ids))
+
+
+def broadphase_update_host(tree, user_ids, new_aabbs, scalar_type) -> None:
+    b = np.ascontiguousarray(new_aabbs, np_dtype(scalar_type))
+    ids = np.ascontiguousarray(user_ids, np.uint64)
+    check(load().fclb_broadphase_update_host(tree, _ptr(ids), _ptr(b), len(ids)))
+
+
+def broadphase_last_visits() -> int:
+    return int(load().fclb_broadphase_last_visits())

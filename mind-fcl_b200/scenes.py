@@ -262,3 +262,25 @@ def heightmap_query_poses(n: int, dtype, half_range: float, z_lo: float, z_hi: f
     local[:, 9:11] = rng.uniform(-1.1 * half_range, 1.1 * half_range, size=(n, 2))
     local[:, 11] = rng.uniform(z_lo, z_hi, size=n)
     return np.ascontiguousarray(tf_hm.astype(dtype)), compose_poses(tf_hm, local, dtype)
+
+
+# ---- broadphase scenes (config C5) -------------------------------------------------
+def config_c5_scene(n_objects: int, dtype, seed: int = 5000, neighbours: float = 8.0):
+    """C5: 40 % Box(5,10,20), 30 % Sphere(30) x0.1, 30 % Cylinder(10,40) x0.1 -- the mix of the
+    reference's broadphase tests (test/broadphase/test_binary_AABB_tree_collision.cpp:13-42) scaled by
+    0.1 -- at random poses in a cube sized for about `neighbours` overlapping-AABB neighbours per
+    object; 3 % of the objects keep an identity rotation (tight-AABB branch of computeAABB).
+    Returns (shapes, shape_ids[n], poses[n,12])."""
+    shapes = [(BOX, 0, (0.5, 1.0, 2.0)), (SPHERE, 0, (3.0,)), (CYLINDER, 0, (1.0, 4.0))]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    shape_ids = rng.choice(3, size=n_objects, p=(0.4, 0.3, 0.3)).astype(np.uint32)
+    # world AABBs are bounding-sphere boxes of half width r: box 1.146, sphere 3, cylinder 2.236
+    # (mean overlap volume of two boxes of half widths a, b is (2(a+b))^3)
+    r = np.array([np.sqrt(0.25 ** 2 + 0.5 ** 2 + 1.0), 3.0, np.sqrt(1.0 + 1.0 + 4.0)])
+    p = np.array([0.4, 0.3, 0.3])
+    mean_vol = sum(p[i] * p[j] * (2 * (r[i] + r[j])) ** 3 for i in range(3) for j in range(3))
+    side = (n_objects * mean_vol / neighbours) ** (1.0 / 3.0)
+    poses = random_poses(rng, n_objects, side / 2.0, np.float64)
+    ident = rng.uniform(size=n_objects) < 0.03
+    poses[ident, :9] = np.eye(3).reshape(9)
+    return shapes, shape_ids, np.ascontiguousarray(poses.astype(dtype))

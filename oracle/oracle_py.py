@@ -241,6 +241,61 @@ class RefOracle(_Oracle):
           C.cast(C.pointer(r), C.c_void_p), _p(counts), _p(pix), threads)
         return counts, pix
 
+    # ---- broadphase ----
+    def compute_aabb_batch(self, shapes, shape_ids, poses):
+        ids = np.ascontiguousarray(shape_ids, np.uint32)
+        out = np.zeros((len(ids), 6), poses.dtype)
+        arr = _shape_array(shapes)
+        f = self.fn("compute_aabb_batch")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        f(_st(poses.dtype), C.cast(arr, C.c_void_p), len(shapes), _p(ids), _p(poses), len(ids), _p(out))
+        return out
+
+    def broadphase_create(self, aabbs, user_ids):
+        ids = np.ascontiguousarray(user_ids, np.uint64)
+        f = self.fn("broadphase_create")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        return int(f(_st(aabbs.dtype), _p(aabbs), _p(ids), len(ids))), _st(aabbs.dtype)
+
+    def _pairs(self, name, argtypes, *args):
+        f = self.fn(name)
+        f.argtypes = argtypes + [C.c_void_p, C.c_size_t]
+        f.restype = C.c_size_t
+        n = int(f(*args, None, 0))
+        out = np.zeros((n, 2), np.uint64)
+        if n:
+            f(*args, _p(out), n)
+        return out
+
+    def broadphase_self_pairs(self, tree):
+        tid, st = tree
+        return self._pairs("broadphase_self_pairs", [C.c_int, C.c_int], st, tid)
+
+    def broadphase_tree_pairs(self, tree_a, tree_b):
+        return self._pairs("broadphase_tree_pairs", [C.c_int, C.c_int, C.c_int], tree_a[1], tree_a[0], tree_b[0])
+
+    def broadphase_query_pairs(self, tree, aabbs, object_ids):
+        ids = np.ascontiguousarray(object_ids, np.uint64)
+        return self._pairs("broadphase_query_pairs", [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t], tree[1],
+                           tree[0], _p(aabbs), _p(ids), len(ids))
+
+    def broadphase_update(self, tree, user_ids, aabbs):
+        ids = np.ascontiguousarray(user_ids, np.uint64)
+        f = self.fn("broadphase_update")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        return int(f(tree[1], tree[0], _p(ids), _p(aabbs), len(ids)))
+
+    def scene_self_collide(self, shapes, shape_ids, poses):
+        """computeAABB + Rebuild + SelfCollision with boolean fcl::collide per candidate: (hits, candidates)."""
+        ids = np.ascontiguousarray(shape_ids, np.uint32)
+        arr = _shape_array(shapes)
+        cand = C.c_size_t()
+        f = self.fn("scene_self_collide")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        f.restype = C.c_size_t
+        hits = int(f(_st(poses.dtype), C.cast(arr, C.c_void_p), len(shapes), _p(ids), _p(poses), len(ids), C.byref(cand)))
+        return hits, int(cand.value)
+
 
 class PortOracle(_Oracle):
     prefix = "fclport_"

@@ -155,9 +155,179 @@ void hmShapeBatch(int hm_id, const ShapeRec* shapes, uint32_t n_shapes, const ui
   });
 }
 
+// ---- broadphase -----------------------------------------------------------------------
+template <typename S>
+struct TreeRec {
+  fcl::BroadphaseAABB_Tree<S> tree;
+};
+struct BpRec {
+  std::shared_ptr<TreeRec<float>> f;
+  std::shared_ptr<TreeRec<double>> d;
+};
+std::vector<BpRec>& trees() {
+  static std::vector<BpRec> t;
+  return t;
+}
+template <typename S>
+fcl::BroadphaseAABB_Tree<S>& getTree(int id);
+template <>
+fcl::BroadphaseAABB_Tree<float>& getTree<float>(int id) {
+  return trees().at(id).f->tree;
+}
+template <>
+fcl::BroadphaseAABB_Tree<double>& getTree<double>(int id) {
+  return trees().at(id).d->tree;
+}
+
+template <typename S>
+std::vector<fcl::BroadphaseObjectInfo<S>> loadObjects(const S* boxes, const uint64_t* ids, size_t n) {
+  std::vector<fcl::BroadphaseObjectInfo<S>> objs(n);
+  for (size_t i = 0; i < n; i++) {
+    objs[i].bv.min_ = fcl::Vector3<S>(boxes[6 * i], boxes[6 * i + 1], boxes[6 * i + 2]);
+    objs[i].bv.max_ = fcl::Vector3<S>(boxes[6 * i + 3], boxes[6 * i + 4], boxes[6 * i + 5]);
+    objs[i].user_id = ids[i];
+  }
+  return objs;
+}
+
+struct PairSink {
+  uint64_t* out;
+  size_t cap;
+  size_t n;
+};
+bool sinkPair(std::uint64_t a, std::uint64_t b, void* data) {
+  PairSink* s = static_cast<PairSink*>(data);
+  if (s->out && s->n < s->cap) {
+    s->out[2 * s->n] = a;
+    s->out[2 * s->n + 1] = b;
+  }
+  s->n++;
+  return false;
+}
+
+template <typename S>
+void computeAabbs(const ShapeRec* shapes, uint32_t n_shapes, const uint32_t* shape_ids, const S* poses, size_t n, S* out) {
+  std::vector<std::shared_ptr<fcl::ShapeBase<S>>> objs;
+  for (uint32_t i = 0; i < n_shapes; i++) {
+    objs.push_back(Sel<S>::shape(shapes + i));
+    objs.back()->computeLocalAABB();
+  }
+  for (size_t q = 0; q < n; q++) {
+    fcl::CollisionObject<S> obj(objs[shape_ids[q]], loadPose<S>(poses + 12 * q));
+    obj.computeAABB();
+    const fcl::AABB<S>& b = obj.getAABB();
+    for (int k = 0; k < 3; k++) {
+      out[6 * q + k] = b.min_[k];
+      out[6 * q + 3 + k] = b.max_[k];
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int fclref_compute_aabb_batch(int scalar_type, const void* shapes, uint32_t n_shapes, const uint32_t* shape_ids,
+                              const void* poses, size_t n, void* out) {
+  if (scalar_type == 0)
+    computeAabbs<float>((const ShapeRec*)shapes, n_shapes, shape_ids, (const float*)poses, n, (float*)out);
+  else
+    computeAabbs<double>((const ShapeRec*)shapes, n_shapes, shape_ids, (const double*)poses, n, (double*)out);
+  return 0;
+}
+/* BinaryAABB_Tree::Rebuild over n (AABB, user_id) objects, both scalar types share the id */
+int fclref_broadphase_create(int scalar_type, const void* boxes, const uint64_t* ids, size_t n) {
+  BpRec r;
+  if (scalar_type == 0) {
+    r.f = std::make_shared<TreeRec<float>>();
+    auto objs = loadObjects<float>((const float*)boxes, ids, n);
+    r.f->tree.Rebuild(objs.data(), uint32_t(n));
+  } else {
+    r.d = std::make_shared<TreeRec<double>>();
+    auto objs = loadObjects<double>((const double*)boxes, ids, n);
+    r.d->tree.Rebuild(objs.data(), uint32_t(n));
+  }
+  trees().push_back(r);
+  return int(trees().size()) - 1;
+}
+size_t fclref_broadphase_self_pairs(int scalar_type, int tree, uint64_t* out, size_t cap) {
+  PairSink s{out, cap, 0};
+  if (scalar_type == 0)
+    getTree<float>(tree).SelfCollision(sinkPair, &s);
+  else
+    getTree<double>(tree).SelfCollision(sinkPair, &s);
+  return s.n;
+}
+size_t fclref_broadphase_tree_pairs(int scalar_type, int tree_a, int tree_b, uint64_t* out, size_t cap) {
+  PairSink s{out, cap, 0};
+  if (scalar_type == 0)
+    getTree<float>(tree_a).TreeCollision(getTree<float>(tree_b), sinkPair, &s);
+  else
+    getTree<double>(tree_a).TreeCollision(getTree<double>(tree_b), sinkPair, &s);
+  return s.n;
+}
+size_t fclref_broadphase_query_pairs(int scalar_type, int tree, const void* boxes, const uint64_t* ids, size_t n,
+                                     uint64_t* out, size_t cap) {
+  PairSink s{out, cap, 0};
+  if (scalar_type == 0) {
+    auto objs = loadObjects<float>((const float*)boxes, ids, n);
+    for (auto& o : objs) getTree<float>(tree).SingleObjectCollision(o, sinkPair, &s);
+  } else {
+    auto objs = loadObjects<double>((const double*)boxes, ids, n);
+    for (auto& o : objs) getTree<double>(tree).SingleObjectCollision(o, sinkPair, &s);
+  }
+  return s.n;
+}
+int fclref_broadphase_update(int scalar_type, int tree, const uint64_t* ids, const void* boxes, size_t n) {
+  int ok = 1;
+  if (scalar_type == 0) {
+    auto objs = loadObjects<float>((const float*)boxes, ids, n);
+    for (auto& o : objs) ok &= int(getTree<float>(tree).UpdateObjectAABB(o.user_id, o.bv));
+  } else {
+    auto objs = loadObjects<double>((const double*)boxes, ids, n);
+    for (auto& o : objs) ok &= int(getTree<double>(tree).UpdateObjectAABB(o.user_id, o.bv));
+  }
+  return ok;
+}
+/* the whole C5 scene step on the CPU: computeAABB, Rebuild, SelfCollision with fcl::collide (boolean) on
+ * every candidate; returns the number of colliding pairs, *n_candidates = candidate pairs */
+size_t fclref_scene_self_collide(int scalar_type, const void* shapes, uint32_t n_shapes, const uint32_t* shape_ids,
+                                 const void* poses, size_t n, size_t* n_candidates) {
+  auto run = [&](auto tag) -> size_t {
+    using S = decltype(tag);
+    const S* P = (const S*)poses;
+    std::vector<std::shared_ptr<fcl::ShapeBase<S>>> geoms;
+    for (uint32_t i = 0; i < n_shapes; i++) {
+      geoms.push_back(Sel<S>::shape((const ShapeRec*)shapes + i));
+      geoms.back()->computeLocalAABB();
+    }
+    std::vector<fcl::CollisionObject<S>> objs;
+    objs.reserve(n);
+    std::vector<fcl::BroadphaseObjectInfo<S>> infos(n);
+    for (size_t q = 0; q < n; q++) {
+      objs.emplace_back(geoms[shape_ids[q]], loadPose<S>(P + 12 * q));
+      objs.back().computeAABB();
+      infos[q].bv = objs.back().getAABB();
+      infos[q].user_id = q;
+    }
+    fcl::BroadphaseAABB_Tree<S> tree;
+    tree.Rebuild(infos.data(), uint32_t(n));
+    size_t cand = 0, hits = 0;
+    fcl::CollisionRequest<S> req(1);
+    req.disablePenetration();
+    tree.SelfCollision(
+        [&](std::uint64_t a, std::uint64_t b, void*) -> bool {
+          cand++;
+          fcl::CollisionResult<S> res;
+          if (fcl::collide<S>(&objs[a], &objs[b], req, res) > 0) hits++;
+          return false;
+        },
+        nullptr);
+    if (n_candidates) *n_candidates = cand;
+    return hits;
+  };
+  return scalar_type == 0 ? run(float(0)) : run(double(0));
+}
 
 int fclref_heightmap_create(const double* points, size_t n_points, double resolution, int half_shape) {
   HmRec r;
