@@ -42,6 +42,9 @@ WORKLOADS = {
     "c1b": "C1b box-box through cvx_collide GJK(128,1e-6)+EPA(256,255,1e-6)",
     "c1b_convex": "C1b convex-convex (58-vertex vs 16-vertex hulls) GJK+EPA",
     "c3": "C3 mesh-mesh BVHModel<OBBRSS> boolean collide, two 10k-triangle meshes, random relative poses",
+    "c4": "C4 7 convex links vs 200k-triangle scene mesh + 1024^2 heightmap, boolean collide per (link, configuration)",
+    "c5": "C5 broadphase + narrowphase: 100k mixed objects per scene (computeAABB, tree build, SelfCollision, "
+          "boolean collide per candidate pair), 8 scenes per GPU per step",
 }
 WORKLOAD = WORKLOADS["c2"]
 
@@ -316,9 +319,211 @@ class MeshWorkload:
                                                 want_pair=False, max_contacts=1)
 
 
+class ArmSceneWorkload:
+    """C4: n configurations x 7 convex links, each link tested against the scene mesh (mesh-shape
+    traversal) and against the heightmap (heightmap-shape scan): 14 n narrowphase queries per step."""
+
+    kind = "scene_collide"
+
+    def __init__(self, name, n, dtype_name, seed):
+        self.name = name
+        self.n_configs = n
+        self.n = 14 * n  # narrowphase queries per step
+        self.dtype_name = dtype_name
+        self.np_dtype = np.float32 if dtype_name == "f32" else np.float64
+        self.sb = 4 if dtype_name == "f32" else 8
+        self.links = scenes.c4_links()
+        self.mesh = scenes.c4_scene_mesh()
+        self.hm_points = scenes.c4_heightmap_points()
+        self.shape_ids, self.poses, self.ident = scenes.config_c4_poses(n, self.np_dtype, seed=4100 + seed)
+        self.visits = {}
+
+    def h2d_bytes(self):
+        return 7 * self.n_configs * (4 + 24 * self.sb) * 2  # ids + two poses, for the mesh call and the heightmap call
+
+    def d2h_bytes(self):
+        return self.n * 4
+
+    def algorithmic_bytes_per_query(self):
+        """SURVEY.md 8(d) row C4, averaged over the two query kinds of a step:
+        mesh: 24 S + 4 + N_node*64(128) + N_leaf*36(72); heightmap: 24 S + 4 + 2*N_pixels."""
+        node_b, tri_b = 16 * self.sb, 9 * self.sb
+        nb, nl = self.visits.get("mesh", (0, 0))
+        px, _ = self.visits.get("hm", (0, 0))
+        per_step = self.n * (24 * self.sb + 8) + nb * node_b + nl * tri_b + 2 * px
+        return per_step / max(self.n, 1)
+
+    def setup(self, fclb, torch, dev):
+        self.fclb = fclb
+        self.st = fclb.F32 if self.dtype_name == "f32" else fclb.F64
+        slots = [fclb.convex_upload(*m) for m in self.links]
+        self.shapes = [(scenes.CONVEX, s, ()) for s in slots]
+        self.table = fclb.shapes_upload(self.shapes)
+        self.bvh = fclb.bvh_build(self.mesh[0], self.mesh[1], self.st)
+        self.heights = fclb.heightmap_build_host(self.hm_points, 0.004, 512, self.st)
+        self.hm = fclb.heightmap_upload(self.heights, 0.004)
+        self.req = fclb.make_request(max_contacts=1)
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        m = len(self.shape_ids)
+        self.h_ids = pin(self.shape_ids.view(np.int32))
+        self.h_pose, self.h_ident = pin(self.poses), pin(self.ident)
+        self.d_ids, self.d_pose, self.d_ident = self.h_ids.to(dev), self.h_pose.to(dev), self.h_ident.to(dev)
+        self.d_out = [torch.empty(m, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.h_out = [torch.empty(m, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.m = m
+
+    def step_dev(self):
+        f = self.fclb
+        f.bvh_shape_collide_batch_dev(self.bvh, self.table, self.d_ids, self.d_ident, self.d_pose, self.m, self.st,
+                                      self.req, self.d_out[0])
+        self.visits["mesh"] = f.scene_last_visit_counts()
+        self.launch_ms = {"mesh-shape": f.last_kernel_ms()}
+        f.heightmap_shape_collide_batch_dev(self.hm, self.table, self.d_ids, self.d_ident, self.d_pose, self.m, self.st,
+                                            self.req, self.d_out[1])
+        self.visits["hm"] = f.scene_last_visit_counts()
+        self.launch_ms["heightmap-shape"] = f.last_kernel_ms()
+
+    def step_host(self):
+        import ctypes as C
+        f = self.fclb
+        lib, P = f.load(), f._ptr
+        rq = C.cast(C.pointer(self.req), C.c_void_p)
+        f.check(lib.fclb_bvh_shape_collide_batch_host(self.bvh, self.table, P(self.h_ids), P(self.h_ident), P(self.h_pose),
+                                                      self.m, self.st, rq, P(self.h_out[0]), None))
+        f.check(lib.fclb_heightmap_shape_collide_batch_host(self.hm, self.table, P(self.h_ids), P(self.h_ident),
+                                                            P(self.h_pose), self.m, self.st, rq, P(self.h_out[1]), None))
+
+    def kernel_records(self):
+        node_b, tri_b = 16 * self.sb, 9 * self.sb
+        nb, nl = self.visits.get("mesh", (0, 0))
+        px, _ = self.visits.get("hm", (0, 0))
+        io = 4 + 24 * self.sb + 4
+        ms = getattr(self, "launch_ms", {})
+        return [
+            {"kernel": "mesh-shape[convex]", "queries": self.m, "avg_ms": ms.get("mesh-shape", 0.0),
+             "bytes_per_query": io + (nb * node_b + nl * tri_b) / self.m},
+            {"kernel": "heightmap-shape[convex]", "queries": self.m, "avg_ms": ms.get("heightmap-shape", 0.0),
+             "bytes_per_query": io + 2 * px / self.m},
+        ]
+
+    def roof_note(self):
+        return ("two kernels per step (mesh-shape traversal, heightmap-shape scan); 'achieved' counts the node / triangle / "
+                "pixel bytes both fetched against the HBM peak; the 25.6 MB tree and the 2 MB grid are L2-resident, the "
+                "kernels are bound by FP32 issue of the OBB SAT and the per-leaf MPR (DESIGN.md 4.6-4.7)")
+
+    def extra(self):
+        nb, nl = self.visits.get("mesh", (0, 0))
+        px, bx = self.visits.get("hm", (0, 0))
+        return {"configurations_per_step": self.n_configs,
+                "mesh_colliding_fraction": float((self.d_out[0] != 0).float().mean().item()),
+                "heightmap_colliding_fraction": float((self.d_out[1] != 0).float().mean().item()),
+                "mesh_node_tests_per_query": nb / self.m, "mesh_leaf_tests_per_query": nl / self.m,
+                "heightmap_pixels_per_query": px / self.m, "heightmap_boxes_per_query": bx / self.m,
+                "kernel_ms": getattr(self, "launch_ms", {})}
+
+    def cpu_sample(self):
+        return 14 * min(self.n_configs, 3000)
+
+    def cpu_run(self, oracle, threads):
+        k = self.cpu_sample() // 2
+        slots = [oracle.register_convex(*m) for m in self.links]
+        shapes = [(scenes.CONVEX, s, ()) for s in slots]
+        mid = oracle.bvh_create(*self.mesh)
+        hid = oracle.heightmap_create(self.hm_points, 0.004, 512)
+
+        def run():
+            oracle.mesh_shape_collide_batch(mid, shapes, self.shape_ids[:k], self.ident[:k], self.poses[:k], threads=threads,
+                                            want_tri=False, max_contacts=1)
+            oracle.heightmap_shape_collide_batch(hid, shapes, self.shape_ids[:k], self.ident[:k], self.poses[:k],
+                                                 threads=threads, want_pixel=False, max_contacts=1)
+        return run
+
+
+class BroadphaseWorkload:
+    """C5: per scene computeAABB + tree build + SelfCollision + boolean collide on every candidate.
+    A step processes `scenes_per_step` scenes; the metric counts candidate pairs (narrowphase queries)."""
+
+    kind = "scene_self_collide"
+    SCENES = 8
+    cpu_threads = 1  # BinaryAABB_Tree::SelfCollision + its callback is one sequential loop in the reference
+
+    def __init__(self, name, n, dtype_name, seed):
+        self.name = name
+        self.n_objects = n
+        self.dtype_name = dtype_name
+        self.np_dtype = np.float32 if dtype_name == "f32" else np.float64
+        self.sb = 4 if dtype_name == "f32" else 8
+        self.scenes = [scenes.config_c5_scene(n, self.np_dtype, seed=5000 + 8 * seed + k) for k in range(self.SCENES)]
+        self.n = 0  # candidate pairs per step, known after the first step
+        self.cand = [0] * self.SCENES
+        self.hits = [0] * self.SCENES
+
+    def h2d_bytes(self):
+        return self.SCENES * self.n_objects * (4 + 12 * self.sb)
+
+    def d2h_bytes(self):
+        return self.SCENES * 16
+
+    def algorithmic_bytes_per_query(self):
+        """per candidate pair: 16 B of ids out of the broadphase + 2 gathered poses (24 S) + 8 B pair record
+        written and read again by the narrowphase + 4 B count (N_pairs * 8 B ids + C1/C2 rows)"""
+        return 16 + 2 * (24 * self.sb + 8) + 4
+
+    def setup(self, fclb, torch, dev):
+        self.fclb = fclb
+        self.torch = torch
+        self.st = fclb.F32 if self.dtype_name == "f32" else fclb.F64
+        self.table = fclb.shapes_upload(self.scenes[0][0])
+        self.req = fclb.make_request(max_contacts=1)
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        self.h_ids = [pin(sc[1].view(np.int32)) for sc in self.scenes]
+        self.h_pose = [pin(sc[2]) for sc in self.scenes]
+        self.d_ids = [t.to(dev) for t in self.h_ids]
+        self.d_pose = [t.to(dev) for t in self.h_pose]
+
+    def _run(self, host):
+        f = self.fclb
+        ids, pose = (self.h_ids, self.h_pose) if host else (self.d_ids, self.d_pose)
+        for k in range(self.SCENES):
+            self.cand[k], self.hits[k] = f.scene_self_collide(self.table, ids[k], pose[k], self.n_objects, self.st, self.req,
+                                                              host=host)
+        self.n = sum(self.cand)
+
+    def step_dev(self):
+        self._run(False)
+
+    def step_host(self):
+        self._run(True)
+
+    def roof_note(self):
+        return ("a step is 8 scenes x (computeAABB, Morton sort, hierarchy, refit, pair search, gather, bucketed boolean "
+                "collide); 'achieved' is candidate pairs x the bytes the narrowphase stage moves per pair over the whole "
+                "step time, against the HBM peak; per-stage times are in profiles/")
+
+    def extra(self):
+        return {"objects_per_scene": self.n_objects, "scenes_per_step": self.SCENES,
+                "candidate_pairs_per_scene": float(np.mean(self.cand)), "colliding_pairs_per_scene": float(np.mean(self.hits)),
+                "objects_per_sec_broadphase_plus_narrowphase": None}
+
+    def cpu_sample(self):
+        return self.cand[0] if self.cand[0] else self.n_objects * 4
+
+    def cpu_run(self, oracle, threads):
+        shapes, ids, poses = self.scenes[0]
+
+        def run():
+            hits, cand = oracle.scene_self_collide(shapes, ids, poses)
+            self.cand[0] = self.cand[0] or cand
+        return run
+
+
 def make_workload(name, n, dtype_name, seed):
     if name == "c3":
         return MeshWorkload(name, n, dtype_name, seed)
+    if name == "c4":
+        return ArmSceneWorkload(name, n, dtype_name, seed)
+    if name == "c5":
+        return BroadphaseWorkload(name, n, dtype_name, seed)
     return Workload(name, n, dtype_name, seed)
 
 
@@ -328,7 +533,7 @@ def run_reference(args, rank, world):
         return
     wl = make_workload(args.workload, args.queries, args.dtype, seed=0)
     oracle = load_oracle()
-    threads = os.cpu_count() or 1
+    threads = getattr(wl, "cpu_threads", os.cpu_count() or 1)
     fn = wl.cpu_run(oracle, threads)
     m = wl.cpu_sample() if hasattr(wl, "cpu_sample") else wl.n
     for _ in range(args.warmup):
@@ -364,7 +569,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.queries <= 0:
-        args.queries = 10_000_000 if args.workload == "c2" else 1_000_000
+        args.queries = {"c2": 10_000_000, "c4": 100_000, "c5": 100_000}.get(args.workload, 1_000_000)
 
     rank = env_int("RANK", 0)
     world = env_int("WORLD_SIZE", 1)
@@ -432,8 +637,14 @@ def main():
     e2e_steps = max(3, args.steps // 2)
     ms_e2e, _, _, _ = timed(wl.step_host, e2e_steps, 3)
 
-    value = world * n * args.steps / (ms_dev * 1e-3)
-    e2e_value = world * n * e2e_steps / (ms_e2e * 1e-3)
+    n = wl.n  # (C5 learns its candidate-pair count from the run itself)
+    total_n = n * world
+    if world > 1:
+        tn = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+        total_n = float(tn.item())
+    value = total_n * args.steps / (ms_dev * 1e-3)
+    e2e_value = total_n * e2e_steps / (ms_e2e * 1e-3)
 
     # dominant kernel of the step and its roofline
     names = {0: "box", 1: "sphere", 2: "ellipsoid", 3: "capsule", 4: "cone", 5: "cylinder", 6: "convex", 7: "triangle"}
@@ -441,12 +652,15 @@ def main():
     for (t1_, t2_, cnt), v in per_launch.items():
         label = f"{wl.kind}[{names.get(t1_, '?')}-{names.get(t2_, '?')}]" if t1_ >= 0 else wl.kind
         kern.append({"kernel": label, "queries": cnt, "avg_ms": float(np.mean(v))})
+    if hasattr(wl, "kernel_records"):
+        kern = wl.kernel_records()
     kern.sort(key=lambda k: -k["avg_ms"])
     peak, peak_src = measured_peaks()
     bpq = wl.algorithmic_bytes_per_query()
     roof = None
     if kern:
         top = kern[0]
+        bpq = top.get("bytes_per_query", bpq)
         achieved = top["queries"] * bpq / (top["avg_ms"] * 1e-3) / 1e9
         traffic = None
         prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -461,7 +675,7 @@ def main():
                 "iterative GJK/EPA buckets are FP32/FP64-issue and latency bound, not HBM bound (DESIGN.md 4.3); "
                 "closed-form buckets are the HBM-bound kernels; per-bucket figures under 'kernels'"}
         for k in kern:
-            k["hbm_gbs"] = k["queries"] * bpq / (k["avg_ms"] * 1e-3) / 1e9
+            k["hbm_gbs"] = k["queries"] * k.get("bytes_per_query", bpq) / (k["avg_ms"] * 1e-3) / 1e9
             k["hbm_frac"] = k["hbm_gbs"] / peak
 
     line = {
@@ -486,7 +700,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             oracle = load_oracle()
-            threads = os.cpu_count() or 1
+            threads = getattr(wl, "cpu_threads", os.cpu_count() or 1)
             fn = wl.cpu_run(oracle, threads)
             m = wl.cpu_sample() if hasattr(wl, "cpu_sample") else n
             best = None

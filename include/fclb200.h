@@ -276,6 +276,19 @@ int fclb_compute_aabb_batch_dev(fclb_handle shapes, const uint32_t* shape_ids, c
 int fclb_gather_pairs_dev(const uint64_t* id_pairs, size_t n_pairs, const uint32_t* shape_ids, const void* poses,
                           int scalar_type, fclb_pair* out_pairs, void* out_poses1, void* out_poses2);
 
+/* One scene end to end on the device -- the loop a planner runs per perception cycle:
+ * computeAABB for every object (object i has user id i), tree build, SelfCollision, and boolean
+ * fcl::collide (request as in fclb_collide_batch) on every candidate pair.
+ *   *n_candidates = candidate pairs of the broadphase, *n_colliding = pairs with numContacts > 0;
+ *   out_id_pairs / out_counts (optional, out_cap entries): the candidates and their numContacts.
+ * _dev: shape_ids / poses are DEVICE arrays; _host: HOST arrays (H2D inside the call). */
+int fclb_scene_self_collide_host(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n,
+                                 int scalar_type, const fclb_request* req, size_t* n_candidates, size_t* n_colliding,
+                                 uint64_t* out_id_pairs, uint32_t* out_counts, size_t out_cap);
+int fclb_scene_self_collide_dev(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n,
+                                int scalar_type, const fclb_request* req, size_t* n_candidates, size_t* n_colliding,
+                                uint64_t* out_id_pairs, uint32_t* out_counts, size_t out_cap);
+
 /* kernel launches issued by this process so far (bench.py's gpu_launches) */
 uint64_t fclb_launch_count(void);
 /* device time (ms, CUDA events on the engine's stream) of the most recent batch

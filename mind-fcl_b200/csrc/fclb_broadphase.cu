@@ -37,6 +37,7 @@ struct Box6 {
 
 struct BpTree {
   int n = 0;
+  int cap = 0;                    // objects the device arrays were allocated for
   int scalar_type = 0;
   void* leaf_box = nullptr;       // Box6<S>[n] in Morton order
   uint64_t* leaf_id = nullptr;    // user ids in Morton order
@@ -374,30 +375,60 @@ static int refit(Engine& e, BpTree* t) {
   return FCLB_OK;
 }
 
-// boxes / ids: DEVICE pointers
+// grow-only device scratch of the tree builder (bounds, sort keys, cub temp storage)
+struct BpScratch {
+  double* bounds = nullptr;
+  unsigned long long *keys = nullptr, *keys2 = nullptr;
+  void* tmp = nullptr;
+  size_t cap_n = 0, cap_tmp = 0;
+};
+static BpScratch g_bp_scratch;
+
+// boxes / ids: DEVICE pointers.  A tree whose arrays already hold `cap` >= n objects is rebuilt in place.
 template <typename S>
 static int buildTreeDev(Engine& e, const void* d_boxes, const uint64_t* d_ids, int n, BpTree* t, bool want_host_map) {
+  const Box6<S>* box = static_cast<const Box6<S>*>(d_boxes);
+  if (t->cap < n || t->scalar_type != (sizeof(S) == 4 ? FCLB_F32 : FCLB_F64)) {
+    cudaFree(t->leaf_box); cudaFree(t->leaf_id); cudaFree(t->node_box); cudaFree(t->node_child);
+    cudaFree(t->node_range); cudaFree(t->parent); cudaFree(t->flags);
+    t->leaf_box = t->node_box = nullptr;
+    t->leaf_id = nullptr; t->node_child = t->node_range = nullptr; t->parent = t->flags = nullptr;
+    t->cap = 0;
+    FCLB_CUDA(cudaMalloc(&t->leaf_box, size_t(n) * sizeof(Box6<S>)));
+    FCLB_CUDA(cudaMalloc(&t->leaf_id, size_t(n) * sizeof(uint64_t)));
+    const int ni = n > 1 ? n - 1 : 1;
+    FCLB_CUDA(cudaMalloc(&t->node_box, size_t(ni) * sizeof(Box6<S>)));
+    FCLB_CUDA(cudaMalloc(&t->node_child, size_t(ni) * sizeof(int2)));
+    FCLB_CUDA(cudaMalloc(&t->node_range, size_t(ni) * sizeof(int2)));
+    FCLB_CUDA(cudaMalloc(&t->parent, size_t(2 * n) * sizeof(int)));
+    FCLB_CUDA(cudaMalloc(&t->flags, size_t(ni) * sizeof(int)));
+    t->cap = n;
+  }
   t->n = n;
   t->scalar_type = sizeof(S) == 4 ? FCLB_F32 : FCLB_F64;
-  const Box6<S>* box = static_cast<const Box6<S>*>(d_boxes);
-  FCLB_CUDA(cudaMalloc(&t->leaf_box, size_t(n) * sizeof(Box6<S>)));
-  FCLB_CUDA(cudaMalloc(&t->leaf_id, size_t(n) * sizeof(uint64_t)));
-  const int ni = n > 1 ? n - 1 : 1;
-  FCLB_CUDA(cudaMalloc(&t->node_box, size_t(ni) * sizeof(Box6<S>)));
-  FCLB_CUDA(cudaMalloc(&t->node_child, size_t(ni) * sizeof(int2)));
-  FCLB_CUDA(cudaMalloc(&t->node_range, size_t(ni) * sizeof(int2)));
-  FCLB_CUDA(cudaMalloc(&t->parent, size_t(2 * n) * sizeof(int)));
-  FCLB_CUDA(cudaMalloc(&t->flags, size_t(ni) * sizeof(int)));
-  // scratch: bounds (6 doubles) + keys in/out + cub temp
-  double* d_bounds = nullptr;
-  unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
-  void* d_tmp = nullptr;
+  BpScratch& sc = g_bp_scratch;
   size_t tmp_bytes = 0;
-  cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys2, n, 0, 62, e.compute);
-  FCLB_CUDA(cudaMalloc(&d_bounds, 6 * sizeof(double)));
-  FCLB_CUDA(cudaMalloc(&d_keys, size_t(n) * 8));
-  FCLB_CUDA(cudaMalloc(&d_keys2, size_t(n) * 8));
-  FCLB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 8));
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, sc.keys, sc.keys2, n, 0, 62, e.compute);
+  if (!sc.bounds) FCLB_CUDA(cudaMalloc(&sc.bounds, 6 * sizeof(double)));
+  if (sc.cap_n < size_t(n)) {
+    cudaFree(sc.keys);
+    cudaFree(sc.keys2);
+    sc.keys = sc.keys2 = nullptr;
+    sc.cap_n = 0;
+    FCLB_CUDA(cudaMalloc(&sc.keys, size_t(n) * 8));
+    FCLB_CUDA(cudaMalloc(&sc.keys2, size_t(n) * 8));
+    sc.cap_n = size_t(n);
+  }
+  if (sc.cap_tmp < tmp_bytes || !sc.tmp) {
+    cudaFree(sc.tmp);
+    sc.tmp = nullptr;
+    sc.cap_tmp = 0;
+    FCLB_CUDA(cudaMalloc(&sc.tmp, tmp_bytes ? tmp_bytes : 8));
+    sc.cap_tmp = tmp_bytes ? tmp_bytes : 8;
+  }
+  double* d_bounds = sc.bounds;
+  unsigned long long *d_keys = sc.keys, *d_keys2 = sc.keys2;
+  void* d_tmp = sc.tmp;
   const double init[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300};
   FCLB_CUDA(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, e.compute));
   const int grid = (n + 127) / 128;
@@ -419,14 +450,8 @@ static int buildTreeDev(Engine& e, const void* d_boxes, const uint64_t* d_ids, i
     FCLB_CUDA(cudaStreamSynchronize(e.compute));
     t->pos_of.reserve(size_t(n) * 2);
     for (int i = 0; i < n; i++) t->pos_of[ids[i]] = i;
-  } else {
-    FCLB_CUDA(cudaStreamSynchronize(e.compute));
   }
-  cudaFree(d_bounds);
-  cudaFree(d_keys);
-  cudaFree(d_keys2);
-  cudaFree(d_tmp);
-  return FCLB_OK;
+  return FCLB_OK;  // stream-ordered: later work on e.compute sees the finished tree
 }
 
 template <typename S>
@@ -462,6 +487,99 @@ static int queryDev(Engine& e, const BpTree* t, const void* q_box, const uint64_
   return FCLB_OK;
 }
 
+__global__ void iotaKernel(uint64_t* ids, size_t n) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < n) ids[i] = i;
+}
+__global__ void countNonZeroKernel(const uint32_t* __restrict__ v, size_t n, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) c += v[i] != 0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// workspace of fclb_scene_self_collide_*: grow-only, reused across scenes
+struct SceneWs {
+  BpTree tree;
+  void* boxes = nullptr;
+  uint64_t* ids = nullptr;
+  size_t cap_obj = 0, obj_scalar = 0;
+  uint64_t* id_pairs = nullptr;
+  fclb_pair* pairs = nullptr;
+  void *poses1 = nullptr, *poses2 = nullptr;
+  uint32_t* counts = nullptr;
+  size_t cap_pairs = 0, pair_scalar = 0;
+  unsigned long long* hits = nullptr;
+};
+static SceneWs g_scene;
+
+template <typename S>
+static int sceneSelfCollide(Engine& e, fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n,
+                            const fclb_request* req, size_t* n_candidates, size_t* n_colliding, uint64_t* out_id_pairs,
+                            uint32_t* out_counts, size_t out_cap) {
+  SceneWs& w = g_scene;
+  const int st = sizeof(S) == 4 ? FCLB_F32 : FCLB_F64;
+  if (w.cap_obj < n || w.obj_scalar < sizeof(S)) {
+    cudaFree(w.boxes);
+    cudaFree(w.ids);
+    w.boxes = nullptr;
+    w.ids = nullptr;
+    w.cap_obj = 0;
+    FCLB_CUDA(cudaMalloc(&w.boxes, n * 6 * 8));
+    FCLB_CUDA(cudaMalloc(&w.ids, n * 8));
+    w.cap_obj = n;
+    w.obj_scalar = 8;
+  }
+  if (!w.hits) FCLB_CUDA(cudaMalloc(&w.hits, sizeof(unsigned long long)));
+  int rc = fclb_compute_aabb_batch_dev(shapes, shape_ids, poses, n, st, w.boxes);
+  if (rc) return rc;
+  iotaKernel<<<int((n + 255) / 256), 256, 0, e.compute>>>(w.ids, n);
+  e.launches += 1;
+  rc = buildTreeDev<S>(e, w.boxes, w.ids, int(n), &w.tree, false);
+  if (rc) return rc;
+  size_t found = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    const size_t want = attempt == 0 ? (w.cap_pairs ? w.cap_pairs : 8 * n) : found;
+    if (w.cap_pairs < want || w.pair_scalar < sizeof(S)) {
+      cudaFree(w.id_pairs); cudaFree(w.pairs); cudaFree(w.poses1); cudaFree(w.poses2); cudaFree(w.counts);
+      w.id_pairs = nullptr; w.pairs = nullptr; w.poses1 = w.poses2 = nullptr; w.counts = nullptr;
+      w.cap_pairs = 0;
+      const size_t cap = want + want / 8 + 1024;
+      FCLB_CUDA(cudaMalloc(&w.id_pairs, cap * 16));
+      FCLB_CUDA(cudaMalloc(&w.pairs, cap * sizeof(fclb_pair)));
+      FCLB_CUDA(cudaMalloc(&w.poses1, cap * 12 * 8));
+      FCLB_CUDA(cudaMalloc(&w.poses2, cap * 12 * 8));
+      FCLB_CUDA(cudaMalloc(&w.counts, cap * 4));
+      w.cap_pairs = cap;
+      w.pair_scalar = 8;
+    }
+    rc = queryDev<S>(e, &w.tree, w.tree.leaf_box, w.tree.leaf_id, w.tree.n, 1, 0, w.id_pairs, w.cap_pairs, &found);
+    if (rc == FCLB_OK) break;
+    if (rc != FCLB_ERR_CAPACITY || attempt == 1) return rc;
+  }
+  if (n_candidates) *n_candidates = found;
+  unsigned long long hits = 0;
+  if (found) {
+    rc = fclb_gather_pairs_dev(w.id_pairs, found, shape_ids, poses, st, w.pairs, w.poses1, w.poses2);
+    if (rc) return rc;
+    rc = fclb_collide_batch_dev(shapes, w.pairs, w.poses1, w.poses2, found, st, req, 0, nullptr, w.counts);
+    if (rc) return rc;
+    FCLB_CUDA(cudaMemsetAsync(w.hits, 0, sizeof(unsigned long long), e.compute));
+    countNonZeroKernel<<<296, 256, 0, e.compute>>>(w.counts, found, w.hits);
+    e.launches += 1;
+    FCLB_CUDA(cudaMemcpyAsync(&hits, w.hits, sizeof(hits), cudaMemcpyDeviceToHost, e.compute));
+    if (out_id_pairs && out_counts) {
+      const size_t m = found < out_cap ? found : out_cap;
+      FCLB_CUDA(cudaMemcpyAsync(out_id_pairs, w.id_pairs, m * 16, cudaMemcpyDefault, e.compute));
+      FCLB_CUDA(cudaMemcpyAsync(out_counts, w.counts, m * 4, cudaMemcpyDefault, e.compute));
+    }
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  }
+  if (n_colliding) *n_colliding = size_t(hits);
+  return FCLB_OK;
+}
+
 static BpTree* findTree(fclb_handle h) {
   auto it = bpTable().find(h);
   return it == bpTable().end() ? nullptr : it->second;
@@ -483,6 +601,7 @@ int fclb_broadphase_build_dev(const void* aabbs, const uint64_t* user_ids, size_
   BpTree* t = new BpTree();
   rc = scalar_type == FCLB_F32 ? buildTreeDev<float>(e, aabbs, user_ids, int(n), t, false)
                                : buildTreeDev<double>(e, aabbs, user_ids, int(n), t, false);
+  if (!rc && cudaStreamSynchronize(e.compute) != cudaSuccess) rc = fail(FCLB_ERR_CUDA, "broadphase build failed");
   if (rc) {
     freeTree(t);
     return rc;
@@ -686,6 +805,59 @@ int fclb_broadphase_update_host(fclb_handle tree, const uint64_t* user_ids, cons
 }
 
 uint64_t fclb_broadphase_last_visits(void) { return g_bp_last_visits; }
+
+/* One scene end to end on the device: computeAABB for every object, tree build, SelfCollision, and boolean
+ * fcl::collide on every candidate pair.  shape_ids / poses: DEVICE arrays (object i = user id i).
+ * out_id_pairs / out_counts (optional, host or device, out_cap pairs): the candidate (id, id) pairs and
+ * numContacts of each. */
+int fclb_scene_self_collide_dev(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n, int scalar_type,
+                                const fclb_request* req, size_t* n_candidates, size_t* n_colliding, uint64_t* out_id_pairs,
+                                uint32_t* out_counts, size_t out_cap) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (!req) return fail(FCLB_ERR_BAD_ARG, "null request");
+  if (n_candidates) *n_candidates = 0;
+  if (n_colliding) *n_colliding = 0;
+  if (n == 0) return FCLB_OK;
+  if (!shape_ids || !poses || n > 0x7fffffffull) return fail(FCLB_ERR_BAD_ARG, "fclb_scene_self_collide: bad argument");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (scalar_type == FCLB_F32)
+    return sceneSelfCollide<float>(e, shapes, shape_ids, poses, n, req, n_candidates, n_colliding, out_id_pairs, out_counts,
+                                   out_cap);
+  return sceneSelfCollide<double>(e, shapes, shape_ids, poses, n, req, n_candidates, n_colliding, out_id_pairs, out_counts,
+                                  out_cap);
+}
+
+int fclb_scene_self_collide_host(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n, int scalar_type,
+                                 const fclb_request* req, size_t* n_candidates, size_t* n_colliding, uint64_t* out_id_pairs,
+                                 uint32_t* out_counts, size_t out_cap) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return fclb_scene_self_collide_dev(shapes, shape_ids, poses, 0, scalar_type, req, n_candidates, n_colliding,
+                                                 out_id_pairs, out_counts, out_cap);
+  if (!shape_ids || !poses) return fail(FCLB_ERR_BAD_ARG, "null array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  static void* d_in = nullptr;
+  static size_t d_in_cap = 0;
+  const size_t o_p = alignUp(n * 4, 256), total = o_p + n * 12 * ss;
+  if (d_in_cap < total) {
+    cudaFree(d_in);
+    d_in = nullptr;
+    d_in_cap = 0;
+    FCLB_CUDA(cudaMalloc(&d_in, total));
+    d_in_cap = total;
+  }
+  char* base = static_cast<char*>(d_in);
+  FCLB_CUDA(cudaMemcpyAsync(base, shape_ids, n * 4, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p, poses, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  return fclb_scene_self_collide_dev(shapes, reinterpret_cast<const uint32_t*>(base), base + o_p, n, scalar_type, req,
+                                     n_candidates, n_colliding, out_id_pairs, out_counts, out_cap);
+}
 
 /* CollisionObject<S>::computeAABB for n objects: out = 6 S per object (min xyz, max xyz). DEVICE pointers. */
 int fclb_compute_aabb_batch_dev(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n, int scalar_type,

@@ -38,6 +38,7 @@ EXPORTS = [
     "fclb_broadphase_self_pairs_host", "fclb_broadphase_self_pairs_dev", "fclb_broadphase_tree_pairs_host",
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
+    "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
     "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -160,6 +161,9 @@ def load() -> C.CDLL:
         lib.fclb_compute_aabb_batch_host.argtypes = [C.c_uint64, vp, vp, sz, C.c_int, vp]
         lib.fclb_compute_aabb_batch_dev.argtypes = [C.c_uint64, vp, vp, sz, C.c_int, vp]
         lib.fclb_gather_pairs_dev.argtypes = [vp, sz, vp, vp, C.c_int, vp, vp, vp]
+        sc_args = [C.c_uint64, vp, vp, sz, C.c_int, vp, szp, szp, vp, vp, sz]
+        lib.fclb_scene_self_collide_host.argtypes = sc_args
+        lib.fclb_scene_self_collide_dev.argtypes = sc_args
     _lib = lib
     return lib
 
@@ -484,3 +488,19 @@ def broadphase_update_host(tree, user_ids, new_aabbs, scalar_type) -> None:
 
 def broadphase_last_visits() -> int:
     return int(load().fclb_broadphase_last_visits())
+
+
+def scene_self_collide(table, shape_ids, poses, n, scalar_type, request: Request, host=True, want_pairs=False):
+    """computeAABB + tree build + SelfCollision + boolean collide per candidate for one scene.
+    Returns (n_candidates, n_colliding[, id_pairs, counts])."""
+    fn = load().fclb_scene_self_collide_host if host else load().fclb_scene_self_collide_dev
+    cand, hits = C.c_size_t(), C.c_size_t()
+    rq = C.cast(C.pointer(request), C.c_void_p)
+    check(fn(table, _ptr(shape_ids), _ptr(poses), n, scalar_type, rq, C.byref(cand), C.byref(hits), None, None, 0))
+    if not want_pairs:
+        return cand.value, hits.value
+    pairs = np.zeros((cand.value, 2), np.uint64)
+    counts = np.zeros(cand.value, np.uint32)
+    check(fn(table, _ptr(shape_ids), _ptr(poses), n, scalar_type, rq, C.byref(cand), C.byref(hits), _ptr(pairs),
+             _ptr(counts), len(counts)))
+    return cand.value, hits.value, pairs, counts

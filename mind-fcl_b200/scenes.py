@@ -284,3 +284,99 @@ def config_c5_scene(n_objects: int, dtype, seed: int = 5000, neighbours: float =
     ident = rng.uniform(size=n_objects) < 0.03
     poses[ident, :9] = np.eye(3).reshape(9)
     return shapes, shape_ids, np.ascontiguousarray(poses.astype(dtype))
+
+
+# ---- robot-arm scene (config C4) ---------------------------------------------------
+def ellipsoid_point_hull(n_verts: int, semi_axes, seed: int):
+    """Convex hull of n_verts random points ON an ellipsoid (all of them are hull vertices).
+    Returns (verts[n,3], faces in the reference encoding, num_faces) for fclb_convex_upload."""
+    from scipy.spatial import ConvexHull
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    d = rng.normal(size=(n_verts, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    verts = d * np.asarray(semi_axes)[None, :]
+    hull = ConvexHull(verts)
+    assert len(hull.vertices) == n_verts
+    enc = []
+    for simplex, eq in zip(hull.simplices, hull.equations):
+        a, b, c = (int(v) for v in simplex)
+        nrm = np.cross(verts[b] - verts[a], verts[c] - verts[a])
+        if np.dot(nrm, eq[:3]) < 0:  # orient outward
+            b, c = c, b
+        enc.extend((3, a, b, c))
+    return np.ascontiguousarray(verts), np.asarray(enc, np.int32), len(hull.simplices)
+
+
+def c4_links(seed: int = 4001):
+    """7 convex link hulls, 32-128 vertices, semi-axes 0.05-0.25."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n_verts = [32, 48, 64, 80, 96, 112, 128]
+    return [ellipsoid_point_hull(n_verts[i], rng.uniform(0.05, 0.25, size=3), seed + 1 + i) for i in range(7)]
+
+
+def terrain_height(x, y):
+    return 0.35 + 0.2 * np.sin(1.7 * x + 0.3) * np.cos(1.3 * y - 0.5) + 0.1 * np.sin(3.1 * x * y * 0.25 + 1.0)
+
+
+def c4_scene_mesh(grid: int = 300, n_boxes: int = 1666, seed: int = 4050):
+    """Procedural scene in [-2,2]^2 x [0,1.5]: a grid terrain (2*grid^2 triangles) plus n_boxes small
+    boxes (12 triangles each) standing on it: 180,000 + 19,992 = 199,992 triangles for the defaults."""
+    xs = np.linspace(-2.0, 2.0, grid + 1)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    Z = terrain_height(X, Y)
+    verts = [np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)]
+    idx = np.arange((grid + 1) * (grid + 1)).reshape(grid + 1, grid + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel(), idx[:-1, 1:].ravel()
+    tris = [np.stack([a, b, c], axis=1), np.stack([a, c, d], axis=1)]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = (grid + 1) * (grid + 1)
+    corner = np.array([[i, j, k] for i in (-1, 1) for j in (-1, 1) for k in (-1, 1)], np.float64)
+    box_tris = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6],
+                         [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], np.int64)
+    for _ in range(n_boxes):
+        cx, cy = rng.uniform(-1.9, 1.9, size=2)
+        h = rng.uniform(0.02, 0.08, size=3)
+        cz = terrain_height(cx, cy) + h[2] * rng.uniform(0.5, 4.0)
+        verts.append(corner * h[None, :] + np.array([cx, cy, cz])[None, :])
+        tris.append(box_tris + base)
+        base += 8
+    return np.ascontiguousarray(np.concatenate(verts)), np.ascontiguousarray(np.concatenate(tris).astype(np.int32))
+
+
+def c4_heightmap_points(n_points: int = 1_000_000, seed: int = 4060):
+    """Random points on the same terrain for LayeredHeightMap(0.004, 512) (1024^2 bottom layer)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    xy = rng.uniform(-2.048, 2.048, size=(n_points, 2))
+    z = terrain_height(xy[:, 0], xy[:, 1]) + rng.uniform(-0.01, 0.01, size=n_points)
+    return np.ascontiguousarray(np.concatenate([xy, z[:, None]], axis=1))
+
+
+def config_c4_poses(n_configs: int, dtype, seed: int = 4100):
+    """Per configuration 7 link poses: a random-walk chain (link i+1 sits 0.15-0.3 m from link i)
+    starting above a random point of the workspace, heights 0.05-0.6 m above the terrain.
+    Returns (shape_ids[7n], link poses[7n,12], identity poses[7n,12]) -- query 7c+i is link i of
+    configuration c; the scene mesh and the heightmap sit at the identity."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = n_configs
+    pos = np.empty((n, 7, 3))
+    p = np.empty((n, 3))
+    p[:, :2] = rng.uniform(-1.6, 1.6, size=(n, 2))
+    p[:, 2] = terrain_height(p[:, 0], p[:, 1]) + rng.uniform(0.05, 0.6, size=n)
+    for i in range(7):
+        pos[:, i] = p
+        step = rng.normal(size=(n, 3))
+        step[:, 2] *= 0.4
+        step /= np.linalg.norm(step, axis=1)[:, None]
+        p = p + step * rng.uniform(0.15, 0.3, size=(n, 1))
+        p[:, :2] = np.clip(p[:, :2], -1.9, 1.9)
+        p[:, 2] = np.maximum(p[:, 2], terrain_height(p[:, 0], p[:, 1]) - 0.05)
+    ang = rng.uniform(0.0, 2.0 * np.pi, size=(n * 7, 3))
+    R = euler_to_matrix(ang[:, 0], ang[:, 1], ang[:, 2])
+    poses = np.empty((n * 7, 12), np.float64)
+    poses[:, :9] = R.reshape(-1, 9)
+    poses[:, 9:] = pos.reshape(-1, 3)
+    ident = np.zeros((n * 7, 12), dtype)
+    ident[:, 0] = ident[:, 4] = ident[:, 8] = 1
+    shape_ids = np.tile(np.arange(7, dtype=np.uint32), n)
+    return shape_ids, np.ascontiguousarray(poses.astype(dtype)), np.ascontiguousarray(ident)
