@@ -67,6 +67,10 @@ static int collideDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const vo
     CollideLaunchArgs a = base;
     if (a.mode & 2) FCLB_CUDA(cudaMemsetAsync(g_ws.count, 0, sizeof(uint32_t), e.compute));
     FCLB_CUDA(launchCollide<S>(b, a, e.compute, &launches));
+    if (a.pen_mode) {
+      FCLB_CUDA(launchMprPenetration<S>(b, a, e.compute));
+      launches += 1;
+    }
     e.rec_kind[e.n_rec] = k;
     e.rec_count[e.n_rec] = counts[k];
     e.n_rec++;
@@ -97,9 +101,9 @@ static int runCollide(fclb_handle shapes, const fclb_pair* pairs, const void* po
   if (n == 0) return FCLB_OK;
   if (n > 0xffffffffull) return fail(FCLB_ERR_CAPACITY, "batch larger than 2^32-1 queries: split it");
   if (!pairs || !poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null input array");
-  if (req->penetration_mode == FCLB_PEN_DIRECTED || req->penetration_mode == FCLB_PEN_INCREMENTAL_MIN)
-    return fail(FCLB_ERR_UNSUPPORTED,
-                "MPR directed / incremental-minimum penetration modes are not on the device yet (SURVEY.md 8f rank 1)");
+  const bool mpr_pen = req->penetration_mode == FCLB_PEN_DIRECTED || req->penetration_mode == FCLB_PEN_INCREMENTAL_MIN;
+  if (mpr_pen && api_mode == 1) return fail(FCLB_ERR_BAD_ARG, "the MPR penetration modes belong to fclb_collide_batch");
+  if (req->penetration_mode > FCLB_PEN_INCREMENTAL_MIN) return fail(FCLB_ERR_BAD_ARG, "unknown penetration mode");
   if (req->epa_max_faces > 1024) return fail(FCLB_ERR_CAPACITY, "epa_max_faces > 1024 does not fit shared memory");
   CollideLaunchArgs a{};
   a.sp = solverParams(scalar_type, req->binary_tol, req->gjk_max_iter, req->distance_tol, req->epa_max_faces,
@@ -125,6 +129,10 @@ static int runCollide(fclb_handle shapes, const fclb_pair* pairs, const void* po
   a.defer.item = g_ws.defer_item;
   a.defer.enabled = 0;
   a.defer.consume = 0;
+  if (mpr_pen) {  // boolean collide first (collision_penetration-inl.h:246-250), then one MPR contact per hit
+    a.pen_mode = int(req->penetration_mode);
+    for (int k = 0; k < 3; k++) a.pen_dir[k] = req->dir[k];
+  }
   if (scalar_type == FCLB_F32) return collideDev<float>(e, t, pairs, poses1, poses2, n, a);
   return collideDev<double>(e, t, pairs, poses1, poses2, n, a);
 }

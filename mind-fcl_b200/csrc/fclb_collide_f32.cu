@@ -2,4 +2,5 @@
 #include "fclb_collide_launch.cuh"
 namespace fclb {
 template cudaError_t launchCollide<float>(const BatchView&, const CollideLaunchArgs&, cudaStream_t, int*);
+template cudaError_t launchMprPenetration<float>(const BatchView&, const CollideLaunchArgs&, cudaStream_t);
 }

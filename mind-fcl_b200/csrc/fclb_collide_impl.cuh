@@ -18,6 +18,7 @@
 #include "fclb_epa.cuh"
 #include "fclb_internal.h"
 #include "fclb_mpr.cuh"
+#include "fclb_mpr_pen.cuh"
 
 namespace fclb {
 
@@ -394,13 +395,46 @@ __global__ void __launch_bounds__(kEpaThreads) epaKernel(BatchView b, S tol, int
   }
 }
 
+// ---- MPR penetration stage (request modes DirectedPenetration / IncrementalMinimumPenetration) --------
+// collisionPenetrationMPR (collision_penetration-inl.h:189-252): the boolean collide has already written
+// counts[q]; every colliding shape pair gets one contact from computePenetrationMPR with
+// MPR(128, request.distanceTolerance()).
+template <typename S, int T0, int T1>
+__global__ void __launch_bounds__(kBlock) mprPenetrationKernel(BatchView b, S tol, int incremental, S dx, S dy, S dz,
+                                                               CollideOut out) {
+  const ShapeD<S>* __restrict__ shapes = static_cast<const ShapeD<S>*>(b.shapes);
+  const ConvexD<S>* __restrict__ cvx = static_cast<const ConvexD<S>*>(b.convex);
+  const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
+  const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
+  const V3<S> dir_world = mk<S>(dx, dy, dz);
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < b.count; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
+    if (out.counts[q] == 0) continue;
+    const fclb_pair pr = b.pairs[q];
+    MinkDiff<S, T0, T1> md;
+    md.s0 = bindShape(shapes, cvx, pr.shape1);
+    md.s1 = bindShape(shapes, cvx, pr.shape2);
+    const Pose<S> tf1 = loadPose(poses1, q);
+    md.setPoses(tf1, loadPose(poses2, q));
+    ContactPt<S> cp;
+    computePenetrationMpr<S>(md, tf1, dir_world, incremental != 0, 128, tol, cp.pos, cp.normal, cp.depth);
+    writeContact<S>(out, q, 0, cp);
+  }
+}
+
 struct CollideLaunchArgs {
   SolverParams sp;
   int mode;
   CollideOut out;
   EpaWork work;
   EpaDefer defer;
+  int pen_mode = 0;  // FCLB_PEN_DIRECTED / FCLB_PEN_INCREMENTAL_MIN: run the MPR penetration stage after the boolean
+  double pen_dir[3] = {0, 0, 0};
 };
+
+// implemented in fclb_collide_f32.cu / fclb_collide_f64.cu (MPR penetration stage of one bucket)
+template <typename S>
+cudaError_t launchMprPenetration(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st);
 
 // implemented in fclb_epa_f32.cu / fclb_epa_f64.cu (EPA stage of one bucket)
 template <typename S>

@@ -28,6 +28,25 @@ cudaError_t launchConvex(const BatchView& b, const CollideLaunchArgs& a, cudaStr
 }
 
 template <typename S>
+cudaError_t launchMprPenetration(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st) {
+  if (b.count == 0) return cudaSuccess;
+  const int grid = gridFor(b.count, kBlock, 8);
+  const int inc = a.pen_mode == FCLB_PEN_INCREMENTAL_MIN ? 1 : 0;
+  const S tol = S(a.sp.epa_tol);  // request.distanceTolerance()
+  const S dx = S(a.pen_dir[0]), dy = S(a.pen_dir[1]), dz = S(a.pen_dir[2]);
+#define FCLB_PEN_CASE(A, B)                                                                    \
+  if (b.type1 == A && b.type2 == B) {                                                          \
+    mprPenetrationKernel<S, A, B><<<grid, kBlock, 0, st>>>(b, tol, inc, dx, dy, dz, a.out);    \
+    return cudaGetLastError();                                                                 \
+  }
+  FCLB_PEN_CASE(ST_BOX, ST_BOX)
+  FCLB_PEN_CASE(ST_CONVEX, ST_CONVEX)
+#undef FCLB_PEN_CASE
+  mprPenetrationKernel<S, ST_DYNAMIC, ST_DYNAMIC><<<grid, kBlock, 0, st>>>(b, tol, inc, dx, dy, dz, a.out);
+  return cudaGetLastError();
+}
+
+template <typename S>
 cudaError_t launchCollide(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st, int* n_launches) {
   if (b.count == 0) return cudaSuccess;
   if (n_launches) *n_launches += 1;
