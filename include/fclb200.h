@@ -234,6 +234,27 @@ int fclb_heightmap_shape_collide_batch_host(fclb_handle hm, fclb_handle shapes, 
 int fclb_heightmap_shape_collide_batch_dev(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
                                            const void* poses_hm, const void* poses_shape, size_t n, int scalar_type,
                                            const fclb_request* req, uint32_t* out_counts, int32_t* out_first_pixel);
+/* ---- octree vs shape ---------------------------------------------------------------
+ * octree2::Octree<S> (geometry/octree2/octree.h, octree_node.h:21-48) handed over as its flat arrays:
+ *   inner_children   8 x u32 per inner node, 0xffffffff = absent child (OctreeInnerNode::children); node 0 = root
+ *   inner_full       inner_nodes_fully_occupied()[i] as bytes
+ *   leaf_bits        OctreeLeafNode::child_occupied of every leaf-layer node (2x2x2 bitmask)
+ *   pruned_or_null   OctreePruneInfo::prune_internal_nodes as bytes, or NULL
+ *   root_aabb        root_bv(): min xyz, max xyz;  num_layers = n_layers()
+ * fcl::collide(Octree2CollisionGeometry, tf_octree, Shape, tf_shape, request, result) per query
+ * (collision_func_matrix-inl.h:253-273 -> octree2_solver_traverse-inl.h:12-136); penetration must be disabled:
+ *   out_counts[q]     = result.numContacts() = min(#voxel boxes hit, max_contacts)
+ *   out_first_node[q] = b1 = encodeOctree2Node (octree2_solver_leaf-inl.h:10-20) of ONE hit box or -1 */
+int fclb_octree_upload(const uint32_t* inner_children, const uint8_t* inner_full, uint32_t n_inner,
+                       const uint8_t* leaf_bits, uint32_t n_leaf, const uint8_t* pruned_or_null,
+                       const double* root_aabb, int num_layers, fclb_handle* octree);
+int fclb_octree_release(fclb_handle octree);
+int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
+                                         const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
+                                         const fclb_request* req, uint32_t* out_counts, int64_t* out_first_node);
+int fclb_octree_shape_collide_batch_dev(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
+                                        const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
+                                        const fclb_request* req, uint32_t* out_counts, int64_t* out_first_node);
 /* node tests and leaf (shape-triangle / shape-pixel) tests of the most recent scene batch call */
 int fclb_scene_last_visit_counts(uint64_t* n_node, uint64_t* n_leaf);
 

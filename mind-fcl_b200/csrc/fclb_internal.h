@@ -98,4 +98,31 @@ struct HeightmapArgs {
 template <typename S>
 cudaError_t launchHeightmapShape(int type1, const HeightmapArgs& a, int grid, cudaStream_t st);
 
+// octree-shape traversal (fclb_octree_impl.cuh, instantiated in fclb_octree_f32/f64.cu)
+constexpr int kOctreeWarps = 4;
+struct OctreeArgs {
+  const uint32_t* inner_children;  // 8 per inner node, 0xffffffff = no child (octree_node.h:35-39)
+  const uint8_t* inner_full;       // inner_nodes_fully_occupied
+  const uint8_t* leaf_bits;        // OctreeLeafNode::child_occupied, 1 byte per leaf-layer node
+  const uint8_t* pruned;           // prune_internal_nodes or nullptr
+  uint32_t n_inner, n_leaf;
+  int num_layers;                  // Octree::n_layers()
+  double root_box[6];              // root_bv: min xyz, max xyz
+  const void* shapes;
+  const void* convex;
+  const uint32_t* shape_ids;
+  const void* poses_octree;
+  const void* poses_shape;
+  size_t n;
+  uint32_t max_contacts;
+  double tol;
+  int max_iter;
+  uint32_t* counts;
+  long long* first_node;           // encodeOctree2Node of one hit box or -1
+  unsigned long long* work_counter;
+  unsigned long long* stats;       // [0] node boxes tested, [1] voxel boxes tested
+};
+template <typename S>
+cudaError_t launchOctreeShape(int type1, const OctreeArgs& a, int grid, cudaStream_t st);
+
 }  // namespace fclb

@@ -134,6 +134,71 @@ static int heightmapShapeDev(Engine& e, const HeightmapDev* hm, const ShapeTable
   return FCLB_OK;
 }
 
+// ---- Octree2 on the device ------------------------------------------------------------
+struct OctreeDev {
+  uint32_t* children = nullptr;
+  uint8_t *inner_full = nullptr, *leaf_bits = nullptr, *pruned = nullptr;
+  uint32_t n_inner = 0, n_leaf = 0;
+  int num_layers = 0;
+  double root_box[6] = {0, 0, 0, 0, 0, 0};
+};
+static std::map<fclb_handle, OctreeDev*>& octTable() {
+  static std::map<fclb_handle, OctreeDev*> t;
+  return t;
+}
+
+template <typename S>
+static int octreeShapeDev(Engine& e, const OctreeDev* o, const ShapeTable* t, const uint32_t* shape_ids,
+                          const void* poses_octree, const void* poses_shape, size_t n, const fclb_request* req,
+                          uint32_t* counts, long long* first_node) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  if (!g_counters) FCLB_CUDA(cudaMalloc(&g_counters, 4 * sizeof(unsigned long long)));
+  FCLB_CUDA(cudaMemsetAsync(g_counters, 0, 4 * sizeof(unsigned long long), e.compute));
+  const SolverParams sp = solverParams(st, req->binary_tol, req->gjk_max_iter, req->distance_tol, req->epa_max_faces,
+                                       req->epa_max_iter, true);
+  OctreeArgs a{};
+  a.inner_children = o->children;
+  a.inner_full = o->inner_full;
+  a.leaf_bits = o->leaf_bits;
+  a.pruned = o->pruned;
+  a.n_inner = o->n_inner;
+  a.n_leaf = o->n_leaf;
+  a.num_layers = o->num_layers;
+  for (int k = 0; k < 6; k++) a.root_box[k] = o->root_box[k];
+  a.shapes = t->d_shapes[st];
+  a.convex = e.d_convex_tab[st];
+  a.shape_ids = shape_ids;
+  a.poses_octree = poses_octree;
+  a.poses_shape = poses_shape;
+  a.n = n;
+  a.max_contacts = req->max_contacts;
+  a.tol = sp.gjk_tol;
+  a.max_iter = sp.gjk_max_iter;
+  a.counts = counts;
+  a.first_node = first_node;
+  a.work_counter = g_counters;
+  a.stats = g_counters + 1;
+  const size_t need = (n + kOctreeWarps - 1) / kOctreeWarps;
+  const size_t cap = size_t(e.sms) * 4;
+  const int grid = int(need < cap ? need : cap);
+  FCLB_CUDA(cudaEventRecord(e.ev_call0, e.compute));
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  FCLB_CUDA(launchOctreeShape<S>(tableUniformType(t), a, grid, e.compute));
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  e.launches += 1;
+  FCLB_CUDA(cudaMemcpyAsync(g_stats, g_counters + 1, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.last_ms = ms;
+  e.last_call_ms = ms;
+  e.n_rec = 1;
+  e.rec_kind[0] = -4;
+  e.rec_count[0] = n;
+  e.rec_ms[0] = ms;
+  return FCLB_OK;
+}
+
 // FlatHeightMap<S>::updateHeightsByPointGenerationFunctor (flat_heightmap-inl.h:249-272)
 template <typename S>
 static void heightsFromPoints(const double* pts, size_t n, S res_x, S res_y, uint32_t half_x, uint32_t half_y,
@@ -365,6 +430,124 @@ int fclb_heightmap_shape_collide_batch_host(fclb_handle hm, fclb_handle shapes, 
   FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
   if (out_first_pixel)
     FCLB_CUDA(cudaMemcpyAsync(out_first_pixel, base + o_fp, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+int fclb_octree_upload(const uint32_t* inner_children, const uint8_t* inner_full, uint32_t n_inner, const uint8_t* leaf_bits,
+                       uint32_t n_leaf, const uint8_t* pruned_or_null, const double* root_aabb, int num_layers,
+                       fclb_handle* octree) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (!octree || !root_aabb || num_layers < 2 || (n_inner && (!inner_children || !inner_full)) || (n_leaf && !leaf_bits))
+    return fail(FCLB_ERR_BAD_ARG, "fclb_octree_upload: bad argument");
+  for (size_t i = 0; i < size_t(8) * n_inner; i++)
+    if (inner_children[i] != 0xffffffffu && inner_children[i] >= (n_inner > n_leaf ? n_inner : n_leaf))
+      return fail(FCLB_ERR_BAD_ARG, "fclb_octree_upload: child index out of range");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  OctreeDev* d = new OctreeDev();
+  d->n_inner = n_inner;
+  d->n_leaf = n_leaf;
+  d->num_layers = num_layers;
+  for (int k = 0; k < 6; k++) d->root_box[k] = root_aabb[k];
+  auto up = [](auto** dst, const void* src, size_t bytes) -> bool {
+    if (cudaMalloc(reinterpret_cast<void**>(dst), bytes ? bytes : 1) != cudaSuccess) return false;
+    return !bytes || cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  bool ok = up(&d->children, inner_children, size_t(32) * n_inner) && up(&d->inner_full, inner_full, n_inner) &&
+            up(&d->leaf_bits, leaf_bits, n_leaf);
+  if (ok && pruned_or_null) ok = up(&d->pruned, pruned_or_null, n_inner);
+  if (!ok) {
+    delete d;
+    return fail(FCLB_ERR_CUDA, "fclb_octree_upload: device allocation / copy failed");
+  }
+  const fclb_handle h = e.next_handle++;
+  octTable()[h] = d;
+  *octree = h;
+  return FCLB_OK;
+}
+
+int fclb_octree_release(fclb_handle h) {
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = octTable().find(h);
+  if (it == octTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_octree_release: unknown handle");
+  cudaFree(it->second->children);
+  cudaFree(it->second->inner_full);
+  cudaFree(it->second->leaf_bits);
+  cudaFree(it->second->pruned);
+  delete it->second;
+  octTable().erase(it);
+  return FCLB_OK;
+}
+
+int fclb_octree_shape_collide_batch_dev(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
+                                        const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
+                                        const fclb_request* req, uint32_t* out_counts, int64_t* out_first_node) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = octTable().find(octree);
+  if (it == octTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown octree handle");
+  ShapeTable* t = findTable(e, shapes);
+  if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (!req || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null request / out_counts");
+  if (req->penetration_mode != FCLB_PEN_DISABLED)
+    return fail(FCLB_ERR_UNSUPPORTED, "octree-shape contact generation (penetration modes) is not on the device yet");
+  if (n == 0) return FCLB_OK;
+  if (!shape_ids || !poses_octree || !poses_shape) return fail(FCLB_ERR_BAD_ARG, "null input array");
+  for (uint32_t i = 0; i < t->n; i++)
+    if (t->host[i].type == FCLB_CONVEX) {
+      const int nv = e.convex[t->host[i].geom].n_verts;
+      if (nv <= 3 || nv == 6)
+        return fail(FCLB_ERR_UNSUPPORTED, "octree-shape: Convex with 1, 2, 3 or 6 vertices uses the special OBB fitters "
+                                          "(math/bv/utility-inl.h:63-131), which are not on the device");
+    }
+  if (scalar_type == FCLB_F32)
+    return octreeShapeDev<float>(e, it->second, t, shape_ids, poses_octree, poses_shape, n, req, out_counts,
+                                 reinterpret_cast<long long*>(out_first_node));
+  return octreeShapeDev<double>(e, it->second, t, shape_ids, poses_octree, poses_shape, n, req, out_counts,
+                                reinterpret_cast<long long*>(out_first_node));
+}
+
+int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
+                                         const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
+                                         const fclb_request* req, uint32_t* out_counts, int64_t* out_first_node) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!shape_ids || !poses_octree || !poses_shape || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  {
+    ShapeTable* t = findTable(e, shapes);
+    if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
+    for (size_t q = 0; q < n; q++)
+      if (shape_ids[q] >= t->n) return fail(FCLB_ERR_BAD_ARG, "shape id out of range");
+  }
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t o_ids = 0;
+  const size_t o_p1 = alignUp(o_ids + n * 4, 256);
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_fn = alignUp(o_cnt + n * 4, 256);
+  const size_t total = alignUp(o_fn + n * 8, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_ids, shape_ids, n * 4, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses_octree, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses_shape, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  rc = fclb_octree_shape_collide_batch_dev(octree, shapes, reinterpret_cast<const uint32_t*>(base + o_ids), base + o_p1,
+                                           base + o_p2, n, scalar_type, req, reinterpret_cast<uint32_t*>(base + o_cnt),
+                                           out_first_node ? reinterpret_cast<int64_t*>(base + o_fn) : nullptr);
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  if (out_first_node) FCLB_CUDA(cudaMemcpyAsync(out_first_node, base + o_fn, n * 8, cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }
