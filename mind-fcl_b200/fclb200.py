@@ -34,6 +34,8 @@ EXPORTS = [
     "fclb_bvh_shape_collide_batch_host", "fclb_bvh_shape_collide_batch_dev", "fclb_scene_last_visit_counts",
     "fclb_heightmap_upload", "fclb_heightmap_release", "fclb_heightmap_build_host",
     "fclb_heightmap_shape_collide_batch_host", "fclb_heightmap_shape_collide_batch_dev",
+    "fclb_octree_upload", "fclb_octree_release", "fclb_octree_shape_collide_batch_host",
+    "fclb_octree_shape_collide_batch_dev",
     "fclb_broadphase_build_host", "fclb_broadphase_build_dev", "fclb_broadphase_release",
     "fclb_broadphase_self_pairs_host", "fclb_broadphase_self_pairs_dev", "fclb_broadphase_tree_pairs_host",
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
@@ -164,6 +166,12 @@ def load() -> C.CDLL:
         sc_args = [C.c_uint64, vp, vp, sz, C.c_int, vp, szp, szp, vp, vp, sz]
         lib.fclb_scene_self_collide_host.argtypes = sc_args
         lib.fclb_scene_self_collide_dev.argtypes = sc_args
+    if hasattr(lib, "fclb_octree_upload"):
+        lib.fclb_octree_upload.argtypes = [vp, vp, u32, vp, u32, vp, vp, C.c_int, C.POINTER(C.c_uint64)]
+        lib.fclb_octree_release.argtypes = [C.c_uint64]
+        os_args = [C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp]
+        lib.fclb_octree_shape_collide_batch_host.argtypes = os_args
+        lib.fclb_octree_shape_collide_batch_dev.argtypes = os_args
     _lib = lib
     return lib
 
@@ -504,3 +512,32 @@ def scene_self_collide(table, shape_ids, poses, n, scalar_type, request: Request
     check(fn(table, _ptr(shape_ids), _ptr(poses), n, scalar_type, rq, C.byref(cand), C.byref(hits), _ptr(pairs),
              _ptr(counts), len(counts)))
     return cand.value, hits.value, pairs, counts
+
+
+# ---- octrees ---------------------------------------------------------------------------
+def octree_upload(inner_children, inner_full, leaf_bits, root_aabb, n_layers, pruned=None) -> int:
+    ch = np.ascontiguousarray(inner_children, np.uint32)
+    full = np.ascontiguousarray(inner_full, np.uint8)
+    leaf = np.ascontiguousarray(leaf_bits, np.uint8)
+    root = np.ascontiguousarray(root_aabb, np.float64)
+    pr = None if pruned is None else np.ascontiguousarray(pruned, np.uint8)
+    h = C.c_uint64()
+    check(load().fclb_octree_upload(_ptr(ch), _ptr(full), len(full), _ptr(leaf), len(leaf), _ptr(pr), _ptr(root), n_layers,
+                                    C.byref(h)))
+    return h.value
+
+
+def octree_release(h: int) -> None:
+    check(load().fclb_octree_release(h))
+
+
+def octree_shape_collide_batch_host(octree, table, shape_ids, poses_octree, poses_shape, scalar_type, request: Request,
+                                    want_node=False):
+    n = len(poses_octree)
+    ids = np.ascontiguousarray(shape_ids, np.uint32)
+    counts = np.zeros(n, np.uint32)
+    node = np.zeros(n, np.int64) if want_node else None
+    check(load().fclb_octree_shape_collide_batch_host(octree, table, _ptr(ids), _ptr(poses_octree), _ptr(poses_shape), n,
+                                                      scalar_type, C.cast(C.pointer(request), C.c_void_p), _ptr(counts),
+                                                      _ptr(node)))
+    return counts, node

@@ -241,6 +241,42 @@ class RefOracle(_Oracle):
           C.cast(C.pointer(r), C.c_void_p), _p(counts), _p(pix), threads)
         return counts, pix
 
+    # ---- octrees ----
+    def octree_create(self, points, resolution, half_shape):
+        pts = np.ascontiguousarray(points, np.float64)
+        f = self.fn("octree_create")
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_int]
+        return int(f(_p(pts), len(pts), resolution, half_shape))
+
+    def octree_export(self, oct_id, dtype):
+        """(inner_children [n,8] u32, inner_full [n] u8, leaf_bits [m] u8, root_aabb [6] f64, n_layers)"""
+        sizes = np.zeros(3, np.uint32)
+        f = self.fn("octree_sizes")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        f(oct_id, _st(dtype), _p(sizes))
+        ch = np.zeros((int(sizes[0]), 8), np.uint32)
+        full = np.zeros(int(sizes[0]), np.uint8)
+        leaf = np.zeros(int(sizes[1]), np.uint8)
+        root = np.zeros(6, np.float64)
+        g = self.fn("octree_export")
+        g.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        g(oct_id, _st(dtype), _p(ch), _p(full), _p(leaf), _p(root))
+        return ch, full, leaf, root, int(sizes[2])
+
+    def octree_shape_collide_batch(self, oct_id, shapes, shape_ids, poses_oct, poses_shape, threads=1, **req):
+        n = len(poses_oct)
+        ids = np.ascontiguousarray(shape_ids, np.uint32)
+        counts = np.zeros(n, np.uint32)
+        node = np.zeros(n, np.int64)
+        r = _request(**req)
+        arr = _shape_array(shapes)
+        f = self.fn("octree_shape_collide_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(poses_oct.dtype), oct_id, C.cast(arr, C.c_void_p), len(shapes), _p(ids), _p(poses_oct), _p(poses_shape), n,
+          C.cast(C.pointer(r), C.c_void_p), _p(counts), _p(node), threads)
+        return counts, node
+
     # ---- broadphase ----
     def compute_aabb_batch(self, shapes, shape_ids, poses):
         ids = np.ascontiguousarray(shape_ids, np.uint32)

@@ -155,6 +155,55 @@ void hmShapeBatch(int hm_id, const ShapeRec* shapes, uint32_t n_shapes, const ui
   });
 }
 
+// ---- octrees ---------------------------------------------------------------------------
+struct OctRec {
+  std::shared_ptr<fcl::Octree2CollisionGeometry<float>> f;
+  std::shared_ptr<fcl::Octree2CollisionGeometry<double>> d;
+};
+std::vector<OctRec>& octrees() {
+  static std::vector<OctRec> t;
+  return t;
+}
+template <typename S>
+const fcl::Octree2CollisionGeometry<S>* getOct(int id);
+template <>
+const fcl::Octree2CollisionGeometry<float>* getOct<float>(int id) {
+  return octrees().at(id).f.get();
+}
+template <>
+const fcl::Octree2CollisionGeometry<double>* getOct<double>(int id) {
+  return octrees().at(id).d.get();
+}
+template <typename S>
+std::shared_ptr<fcl::Octree2CollisionGeometry<S>> buildOct(const double* pts, size_t n, double res, int half_shape) {
+  auto tree = std::make_shared<fcl::octree2::Octree<S>>(S(res), uint16_t(half_shape));
+  tree->rebuildTree(
+      [&](int i, S& x, S& y, S& z) {
+        x = S(pts[3 * size_t(i)]);
+        y = S(pts[3 * size_t(i) + 1]);
+        z = S(pts[3 * size_t(i) + 2]);
+      },
+      int(n));
+  return std::make_shared<fcl::Octree2CollisionGeometry<S>>(tree);
+}
+template <typename S>
+void octShapeBatch(int oct_id, const ShapeRec* shapes, uint32_t n_shapes, const uint32_t* shape_ids, const S* poses_oct,
+                   const S* poses_shape, size_t n, const RequestRec* rq, uint32_t* counts, int64_t* first_node, int threads) {
+  const auto* oct = getOct<S>(oct_id);
+  std::vector<std::shared_ptr<fcl::ShapeBase<S>>> objs;
+  for (uint32_t i = 0; i < n_shapes; i++) objs.push_back(Sel<S>::shape(shapes + i));
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    const fcl::CollisionRequest<S> req = makeRequest<S>(rq);
+    for (size_t q = b; q < e; q++) {
+      fcl::CollisionResult<S> res;
+      const size_t c = fcl::collide<S>(oct, loadPose<S>(poses_oct + 12 * q), objs[shape_ids[q]].get(),
+                                       loadPose<S>(poses_shape + 12 * q), req, res);
+      counts[q] = uint32_t(c);
+      if (first_node) first_node[q] = c ? int64_t(res.getContact(0).b1) : -1;
+    }
+  });
+}
+
 // ---- broadphase -----------------------------------------------------------------------
 template <typename S>
 struct TreeRec {
@@ -327,6 +376,60 @@ size_t fclref_scene_self_collide(int scalar_type, const void* shapes, uint32_t n
     return hits;
   };
   return scalar_type == 0 ? run(float(0)) : run(double(0));
+}
+
+int fclref_octree_create(const double* points, size_t n_points, double resolution, int half_shape) {
+  OctRec r;
+  r.f = buildOct<float>(points, n_points, resolution, half_shape);
+  r.d = buildOct<double>(points, n_points, resolution, half_shape);
+  octrees().push_back(r);
+  return int(octrees().size()) - 1;
+}
+/* sizes[0..2] = n_inner, n_leaf, n_layers */
+int fclref_octree_sizes(int id, int scalar_type, uint32_t* sizes) {
+  auto get = [&](const auto* g) {
+    sizes[0] = uint32_t(g->inner_nodes().size());
+    sizes[1] = uint32_t(g->leaf_nodes().size());
+    sizes[2] = uint32_t(g->raw_octree()->n_layers());
+    return 0;
+  };
+  return scalar_type == 0 ? get(getOct<float>(id)) : get(getOct<double>(id));
+}
+int fclref_octree_export(int id, int scalar_type, uint32_t* inner_children, uint8_t* inner_full, uint8_t* leaf_bits,
+                         double* root_aabb) {
+  auto dump = [&](const auto* g) {
+    const auto& inner = g->inner_nodes();
+    const auto& full = g->inner_nodes_fully_occupied();
+    const auto& leaf = g->leaf_nodes();
+    for (size_t i = 0; i < inner.size(); i++) {
+      for (int c = 0; c < 8; c++) inner_children[8 * i + c] = inner[i].children[c];
+      inner_full[i] = full[i] ? 1 : 0;
+    }
+    for (size_t i = 0; i < leaf.size(); i++) {
+      uint8_t bits = 0;
+      for (uint8_t c = 0; c < 8; c++)
+        if (leaf[i].child_occupied.test_i(c)) bits |= uint8_t(1u << c);
+      leaf_bits[i] = bits;
+    }
+    const auto& bv = g->octree_root_bv();
+    for (int k = 0; k < 3; k++) {
+      root_aabb[k] = double(bv.min_[k]);
+      root_aabb[3 + k] = double(bv.max_[k]);
+    }
+    return 0;
+  };
+  return scalar_type == 0 ? dump(getOct<float>(id)) : dump(getOct<double>(id));
+}
+int fclref_octree_shape_collide_batch(int scalar_type, int oct_id, const void* shapes, uint32_t n_shapes,
+                                      const uint32_t* shape_ids, const void* poses_oct, const void* poses_shape, size_t n,
+                                      const void* request, uint32_t* counts, int64_t* first_node, int threads) {
+  if (scalar_type == 0)
+    octShapeBatch<float>(oct_id, (const ShapeRec*)shapes, n_shapes, shape_ids, (const float*)poses_oct,
+                         (const float*)poses_shape, n, (const RequestRec*)request, counts, first_node, threads);
+  else
+    octShapeBatch<double>(oct_id, (const ShapeRec*)shapes, n_shapes, shape_ids, (const double*)poses_oct,
+                          (const double*)poses_shape, n, (const RequestRec*)request, counts, first_node, threads);
+  return 0;
 }
 
 int fclref_heightmap_create(const double* points, size_t n_points, double resolution, int half_shape) {
