@@ -22,6 +22,7 @@
 // call aborts with the engine's error message (there is no CPU fallback).
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstdio>
@@ -89,7 +90,9 @@ enum NODE_TYPE {  // subset of geometry/collision_geometry.h:50-54 this path sup
   GEOM_CONE,
   GEOM_CYLINDER,
   GEOM_CONVEX,
-  BV_OBBRSS
+  BV_OBBRSS,
+  GEOM_HEIGHTMAP,
+  GEOM_OCTREE2
 };
 
 template <typename S>
@@ -205,8 +208,119 @@ class BVHModel<OBBRSS<S>> : public CollisionGeometry<S> {
                                   int(tri_verts.size() / 9), detail::scalarType<S>(), &handle_),
                   "fclb_bvh_upload");
   }
-  ~BVHModel() override { fclb_bvh_release(handle_); }
+  // the reference's own build protocol (geometry/bvh/BVH_model.h:104-124): beginModel, addSubModel, endModel;
+  // endModel runs the host mirror of BVHModel::buildTree (fclb_bvh_build) and uploads the tree
+  BVHModel() = default;
+  int beginModel() {
+    verts_.clear();
+    tris_.clear();
+    return 0;
+  }
+  int addSubModel(const std::vector<Vector3<S>>& points, const std::vector<std::array<int, 3>>& triangles) {
+    const int32_t base = int32_t(verts_.size() / 3);
+    for (const auto& p : points)
+      for (int k = 0; k < 3; k++) verts_.push_back(double(p[k]));
+    for (const auto& t : triangles)
+      for (int k = 0; k < 3; k++) tris_.push_back(base + t[k]);
+    return 0;
+  }
+  int endModel() {
+    if (handle_) fclb_bvh_release(handle_);
+    handle_ = 0;
+    detail::check(fclb_bvh_build(verts_.data(), int(verts_.size() / 3), tris_.data(), int(tris_.size() / 3),
+                                 detail::scalarType<S>(), &handle_),
+                  "fclb_bvh_build");
+    return 0;
+  }
+  int getNumBVs() const {
+    int n = 0;
+    if (handle_) fclb_bvh_info(handle_, &n, nullptr, nullptr);
+    return n;
+  }
+  ~BVHModel() override {
+    if (handle_) fclb_bvh_release(handle_);
+  }
   NODE_TYPE getNodeType() const override { return BV_OBBRSS; }
+  bool isShape() const override { return false; }
+  fclb_shape shapeRecord() const override { return fclb_shape{}; }
+  fclb_handle handle() const { return handle_; }
+
+ private:
+  fclb_handle handle_ = 0;
+  std::vector<double> verts_;
+  std::vector<int32_t> tris_;
+};
+
+// heightmap::LayeredHeightMap<S> (geometry/heightmap/layered_heightmap.h): the bottom layer lives on the host
+// until it is wrapped in a HeightMapCollisionGeometry, which uploads it (coarser layers are rebuilt on upload).
+namespace heightmap {
+template <typename S>
+class LayeredHeightMap {
+ public:
+  LayeredHeightMap(S bottom_resolution, uint16_t bottom_half_map_shape)
+      : resolution_(bottom_resolution), half_(bottom_half_map_shape),
+        heights_(std::size_t(2 * bottom_half_map_shape) * 2 * bottom_half_map_shape, 0) {}
+  // updateHeightsByPointGenerationFunctor (layered_heightmap-inl.h:134-140): generator(i, x, y, z)
+  template <typename PointGenerator>
+  void updateHeightsByPointGenerationFunctor(const PointGenerator& gen, int n_points) {
+    std::vector<double> pts(std::size_t(3) * n_points);
+    for (int i = 0; i < n_points; i++) {
+      S x, y, z;
+      gen(i, x, y, z);
+      pts[3 * std::size_t(i)] = double(x);
+      pts[3 * std::size_t(i) + 1] = double(y);
+      pts[3 * std::size_t(i) + 2] = double(z);
+    }
+    detail::check(fclb_heightmap_build_host(pts.data(), std::size_t(n_points), double(resolution_), double(resolution_),
+                                            half_, half_, detail::scalarType<S>(), heights_.data()),
+                  "fclb_heightmap_build_host");
+  }
+  void resetHeights() { std::fill(heights_.begin(), heights_.end(), uint16_t(0)); }
+  S resolution() const { return resolution_; }
+  uint16_t half_shape() const { return half_; }
+  const std::vector<uint16_t>& bottom_heights_mm() const { return heights_; }
+
+ private:
+  S resolution_;
+  uint16_t half_;
+  std::vector<uint16_t> heights_;
+};
+}  // namespace heightmap
+
+// geometry/heightmap/heightmap_collision_geometry.h
+template <typename S>
+class HeightMapCollisionGeometry : public CollisionGeometry<S> {
+ public:
+  explicit HeightMapCollisionGeometry(std::shared_ptr<const heightmap::LayeredHeightMap<S>> map) : map_(std::move(map)) {
+    detail::check(fclb_heightmap_upload(map_->bottom_heights_mm().data(), 2u * map_->half_shape(), 2u * map_->half_shape(),
+                                        double(map_->resolution()), double(map_->resolution()), 0, &handle_),
+                  "fclb_heightmap_upload");
+  }
+  ~HeightMapCollisionGeometry() override { fclb_heightmap_release(handle_); }
+  NODE_TYPE getNodeType() const override { return GEOM_HEIGHTMAP; }
+  bool isShape() const override { return false; }
+  fclb_shape shapeRecord() const override { return fclb_shape{}; }
+  fclb_handle handle() const { return handle_; }
+  const std::shared_ptr<const heightmap::LayeredHeightMap<S>>& raw_heightmap() const { return map_; }
+
+ private:
+  std::shared_ptr<const heightmap::LayeredHeightMap<S>> map_;
+  fclb_handle handle_ = 0;
+};
+
+// geometry/octree2/octree_collision_geometry.h: the octree is built by the caller (mind-fcl's octree2::Octree in
+// an integration) and handed over as its flat node arrays (see fclb_octree_upload).
+template <typename S>
+class Octree2CollisionGeometry : public CollisionGeometry<S> {
+ public:
+  Octree2CollisionGeometry(const std::vector<uint32_t>& inner_children, const std::vector<uint8_t>& inner_full,
+                           const std::vector<uint8_t>& leaf_bits, const std::array<double, 6>& root_aabb, int n_layers) {
+    detail::check(fclb_octree_upload(inner_children.data(), inner_full.data(), uint32_t(inner_full.size()), leaf_bits.data(),
+                                     uint32_t(leaf_bits.size()), nullptr, root_aabb.data(), n_layers, &handle_),
+                  "fclb_octree_upload");
+  }
+  ~Octree2CollisionGeometry() override { fclb_octree_release(handle_); }
+  NODE_TYPE getNodeType() const override { return GEOM_OCTREE2; }
   bool isShape() const override { return false; }
   fclb_shape shapeRecord() const override { return fclb_shape{}; }
   fclb_handle handle() const { return handle_; }
@@ -221,6 +335,15 @@ struct CollisionRequest {
   explicit CollisionRequest(std::size_t n_max_contacts = 1) : num_max_contacts_(n_max_contacts) {}
   void disablePenetration() { penetration_mode_ = FCLB_PEN_DISABLED; }
   void useDefaultPenetration() { penetration_mode_ = FCLB_PEN_DEFAULT_GJK_EPA; }
+  // collision_request.h:76-80 -> detail/collision_penetration_mode.h:16-76
+  void useDirectedPenetration(const Vector3<S>& shape2_escape_direction) {
+    penetration_mode_ = FCLB_PEN_DIRECTED;
+    direction_ = shape2_escape_direction;
+  }
+  void useIncrementalMinimumDistancePenetration(const Vector3<S>& shape2_escape_direction_init) {
+    penetration_mode_ = FCLB_PEN_INCREMENTAL_MIN;
+    direction_ = shape2_escape_direction_init;
+  }
   bool isPenetrationEnabled() const { return penetration_mode_ != FCLB_PEN_DISABLED; }
   std::size_t maxNumContacts() const { return num_max_contacts_; }
   void setMaxContactCount(std::size_t n) { num_max_contacts_ = n; }
@@ -232,6 +355,7 @@ struct CollisionRequest {
     fclb_request r{};
     r.max_contacts = num_max_contacts_ > 0xffffffffull ? 0xffffffffu : uint32_t(num_max_contacts_);
     r.penetration_mode = penetration_mode_;
+    for (int k = 0; k < 3; k++) r.dir[k] = double(direction_[k]);
     r.binary_tol = double(binary_collision_tolerance_);
     r.distance_tol = double(distance_tolerance_);
     return r;
@@ -240,6 +364,7 @@ struct CollisionRequest {
  private:
   std::size_t num_max_contacts_;
   uint32_t penetration_mode_ = FCLB_PEN_DISABLED;
+  Vector3<S> direction_;
   S binary_collision_tolerance_{S(1e-6)};
   S distance_tolerance_{S(1e-6)};
 };
@@ -278,10 +403,89 @@ class CollisionObject {
   const std::shared_ptr<const CollisionGeometry<S>>& collisionGeometry() const { return geom_; }
   const Transform3<S>& getTransform() const { return tf_; }
   void setTransform(const Transform3<S>& tf) { tf_ = tf; }
+  // computeAABB (collision_object-inl.h:141-154), shapes only: min xyz, max xyz
+  std::array<S, 6> computeAABB() const {
+    const fclb_shape rec = geom_->shapeRecord();
+    fclb_handle one = 0;
+    detail::check(fclb_shapes_upload(&rec, 1, &one), "fclb_shapes_upload");
+    S pose[12];
+    tf_.toPose12(pose);
+    const uint32_t sid = 0;
+    std::array<S, 6> box{};
+    detail::check(fclb_compute_aabb_batch_host(one, &sid, pose, 1, detail::scalarType<S>(), box.data()),
+                  "fclb_compute_aabb_batch_host");
+    fclb_release(one);
+    return box;
+  }
 
  private:
   std::shared_ptr<const CollisionGeometry<S>> geom_;
   Transform3<S> tf_;
+};
+
+// broadphase/broadphase_common.h:13-22 and broadphase_AABB_tree.h: the tree lives on the device; the collision
+// functor runs on the host over the returned pair list (callbacks cannot cross the C ABI).
+template <typename S>
+struct BroadphaseObjectInfo {
+  std::array<S, 6> bv{};  // min xyz, max xyz
+  std::uint64_t user_id{0};
+};
+template <typename S>
+class BroadphaseAABB_Tree {
+ public:
+  using CollisionFn = bool (*)(std::uint64_t, std::uint64_t, void*);
+  ~BroadphaseAABB_Tree() {
+    if (handle_) fclb_broadphase_release(handle_);
+  }
+  void Rebuild(BroadphaseObjectInfo<S>* objects, std::uint32_t n_objects) {
+    if (handle_) fclb_broadphase_release(handle_);
+    handle_ = 0;
+    if (n_objects == 0) return;
+    std::vector<S> boxes(6 * std::size_t(n_objects));
+    std::vector<std::uint64_t> ids(n_objects);
+    for (std::uint32_t i = 0; i < n_objects; i++) {
+      for (int k = 0; k < 6; k++) boxes[6 * std::size_t(i) + k] = objects[i].bv[k];
+      ids[i] = objects[i].user_id;
+    }
+    detail::check(fclb_broadphase_build_host(boxes.data(), ids.data(), n_objects, detail::scalarType<S>(), &handle_),
+                  "fclb_broadphase_build_host");
+  }
+  bool UpdateObjectAABB(std::uint64_t user_id, const std::array<S, 6>& new_aabb) {
+    return handle_ && fclb_broadphase_update_host(handle_, &user_id, new_aabb.data(), 1) == FCLB_OK;
+  }
+  template <typename Fn>
+  void SelfCollision(const Fn& fn, void* data) const {
+    if (!handle_) return;
+    report(fn, data, [&](std::uint64_t* out, std::size_t cap, std::size_t* n) {
+      return fclb_broadphase_self_pairs_host(handle_, out, cap, n);
+    });
+  }
+  template <typename Fn>
+  void TreeCollision(const BroadphaseAABB_Tree& tree2, const Fn& fn, void* data) const {
+    if (!handle_ || !tree2.handle_) return;
+    report(fn, data, [&](std::uint64_t* out, std::size_t cap, std::size_t* n) {
+      return fclb_broadphase_tree_pairs_host(handle_, tree2.handle_, out, cap, n);
+    });
+  }
+  template <typename Fn>
+  void SingleObjectCollision(const BroadphaseObjectInfo<S>& object, const Fn& fn, void* data) const {
+    if (!handle_) return;
+    report(fn, data, [&](std::uint64_t* out, std::size_t cap, std::size_t* n) {
+      return fclb_broadphase_query_pairs_host(handle_, object.bv.data(), &object.user_id, 1, out, cap, n);
+    });
+  }
+
+ private:
+  template <typename Fn, typename Query>
+  static void report(const Fn& fn, void* data, const Query& query) {
+    std::size_t n = 0;
+    detail::check(query(nullptr, 0, &n), "broadphase pair count");
+    std::vector<std::uint64_t> pairs(2 * n);
+    if (n) detail::check(query(pairs.data(), n, &n), "broadphase pairs");
+    for (std::size_t i = 0; i < n; i++)
+      if (fn(pairs[2 * i], pairs[2 * i + 1], data)) return;
+  }
+  fclb_handle handle_ = 0;
 };
 
 // ---- batched entry points --------------------------------------------------------
@@ -340,6 +544,46 @@ void collideBatch(const std::vector<CollisionQuery<S>>& queries, const Collision
         ct.b1 = pair_ids[0];
         ct.b2 = pair_ids[1];
         results[q].addContact(ct);
+      }
+    } else if (!Q.o1->isShape() && Q.o2->isShape()) {
+      // scene geometry vs shape: BVHShapeCollider / HeightMapShapeCollide / OcTree2ShapeCollide
+      // (collision_func_matrix-inl.h:754-762, 815-823, 774-782)
+      const fclb_shape rec = Q.o2->shapeRecord();
+      fclb_handle one = 0;
+      detail::check(fclb_shapes_upload(&rec, 1, &one), "fclb_shapes_upload");
+      S a[12], b[12];
+      Q.tf1.toPose12(a);
+      Q.tf2.toPose12(b);
+      const uint32_t sid = 0;
+      uint32_t count = 0;
+      int64_t b1 = -1;
+      const int st = detail::scalarType<S>();
+      if (Q.o1->getNodeType() == BV_OBBRSS) {
+        int32_t tri = -1;
+        detail::check(fclb_bvh_shape_collide_batch_host(static_cast<const BVHModel<OBBRSS<S>>*>(Q.o1)->handle(), one, &sid, a,
+                                                        b, 1, st, &req, &count, &tri),
+                      "fclb_bvh_shape_collide_batch_host");
+        b1 = tri;
+      } else if (Q.o1->getNodeType() == GEOM_HEIGHTMAP) {
+        int32_t pix = -1;
+        detail::check(fclb_heightmap_shape_collide_batch_host(static_cast<const HeightMapCollisionGeometry<S>*>(Q.o1)->handle(),
+                                                              one, &sid, a, b, 1, st, &req, &count, &pix),
+                      "fclb_heightmap_shape_collide_batch_host");
+        b1 = pix;
+      } else {
+        detail::check(fclb_octree_shape_collide_batch_host(static_cast<const Octree2CollisionGeometry<S>*>(Q.o1)->handle(), one,
+                                                           &sid, a, b, 1, st, &req, &count, &b1),
+                      "fclb_octree_shape_collide_batch_host");
+      }
+      fclb_release(one);
+      // the device reports the count and ONE contact id; further contacts repeat that id
+      for (uint32_t c = 0; c < count; c++) {
+        Contact<S> ct;
+        ct.o1 = Q.o1;
+        ct.o2 = Q.o2;
+        ct.b1 = intptr_t(b1);
+        results[q].addContact(ct);
+        if (c >= 63) break;
       }
     } else {
       std::cerr << "Warning: collision function between node type " << Q.o1->getNodeType() << " and node type "

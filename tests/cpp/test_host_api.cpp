@@ -87,9 +87,102 @@ void run() {
   }
 }
 
+// scene geometry through the mirrored classes: a two-triangle floor mesh (beginModel / addSubModel / endModel),
+// a heightmap rasterised from points, the MPR penetration request modes and the broadphase tree
+template <typename S>
+void runScene() {
+  using namespace fcl;
+  Transform3<S> I = Transform3<S>::Identity();
+  auto at = [](S x, S y, S z) {
+    Transform3<S> t;
+    t.translation() = Vector3<S>(x, y, z);
+    return t;
+  };
+  {
+    BVHModel<OBBRSS<S>> floor;
+    floor.beginModel();
+    floor.addSubModel({Vector3<S>(-1, -1, 0), Vector3<S>(1, -1, 0), Vector3<S>(1, 1, 0), Vector3<S>(-1, 1, 0)},
+                      {{0, 1, 2}, {0, 2, 3}});
+    floor.endModel();
+    EXPECT_TRUE(floor.getNumBVs() == 3);
+    Sphere<S> ball(S(0.25));
+    CollisionRequest<S> req(10);
+    CollisionResult<S> hit, miss;
+    EXPECT_TRUE(collide<S>(&floor, I, &ball, at(S(0.5), S(-0.5), S(0.2)), req, hit) == 1);   // touches one triangle
+    EXPECT_TRUE(collide<S>(&floor, I, &ball, at(S(0.5), S(-0.5), S(0.3)), req, miss) == 0);  // just above the floor
+    CollisionResult<S> both;
+    EXPECT_TRUE(collide<S>(&floor, I, &ball, at(0, 0, S(0.1)), req, both) == 2);  // on the shared diagonal
+  }
+  {
+    auto map = std::make_shared<heightmap::LayeredHeightMap<S>>(S(0.1), uint16_t(8));  // 16 x 16 pixels, +-0.8 m
+    map->updateHeightsByPointGenerationFunctor(
+        [](int i, S& x, S& y, S& z) {
+          x = S(0.05) + S(0.1) * S(i % 4);
+          y = S(0.05);
+          z = S(0.5);
+        },
+        4);  // four 0.5 m columns in a row
+    HeightMapCollisionGeometry<S> hm(map);
+    Box<S> box(S(0.06), S(0.06), S(0.06));
+    CollisionRequest<S> req(100);
+    CollisionResult<S> on, over, off;
+    EXPECT_TRUE(collide<S>(&hm, I, &box, at(S(0.05), S(0.05), S(0.3)), req, on) == 1);
+    EXPECT_TRUE(on.numContacts() == 1 && on.getContact(0).b1 == ((8 << 16) | 8));  // encodePixel(x=8, y=8)
+    EXPECT_TRUE(collide<S>(&hm, I, &box, at(S(0.05), S(0.05), S(0.6)), req, over) == 0);
+    EXPECT_TRUE(collide<S>(&hm, I, &box, at(S(-0.3), S(0.05), S(0.3)), req, off) == 0);
+  }
+  {
+    // directed penetration: two unit spheres 1.5 apart along x, escape direction +x => depth 0.5
+    Sphere<S> a(1), b(1);
+    CollisionRequest<S> req(1);
+    req.useDirectedPenetration(Vector3<S>(1, 0, 0));
+    CollisionResult<S> res;
+    EXPECT_TRUE(collide<S>(&a, I, &b, at(S(1.5), 0, 0), req, res) == 1);
+    if (res.numContacts() == 1) EXPECT_TRUE(std::fabs(res.getContact(0).penetration_depth - S(0.5)) < S(1e-3));
+    CollisionRequest<S> inc(1);
+    inc.useIncrementalMinimumDistancePenetration(Vector3<S>(0, S(0.6), S(0.8)));
+    CollisionResult<S> res2;
+    EXPECT_TRUE(collide<S>(&a, I, &b, at(S(1.5), 0, 0), inc, res2) == 1);
+    if (res2.numContacts() == 1) {
+      EXPECT_TRUE(res2.getContact(0).penetration_depth > 0 && res2.getContact(0).penetration_depth < S(1.3));
+    }
+  }
+  {
+    std::vector<BroadphaseObjectInfo<S>> objs(3);
+    objs[0].bv = {0, 0, 0, 1, 1, 1};
+    objs[0].user_id = 10;
+    objs[1].bv = {S(0.5), S(0.5), S(0.5), 2, 2, 2};
+    objs[1].user_id = 11;
+    objs[2].bv = {5, 5, 5, 6, 6, 6};
+    objs[2].user_id = 12;
+    BroadphaseAABB_Tree<S> tree;
+    tree.Rebuild(objs.data(), 3);
+    int n_pairs = 0;
+    std::uint64_t sum = 0;
+    tree.SelfCollision(
+        [&](std::uint64_t i, std::uint64_t j, void*) {
+          n_pairs++;
+          sum += i + j;
+          return false;
+        },
+        nullptr);
+    EXPECT_TRUE(n_pairs == 1 && sum == 21);
+    EXPECT_TRUE(tree.UpdateObjectAABB(12, {S(1.5), S(1.5), S(1.5), 6, 6, 6}));
+    n_pairs = 0;
+    tree.SelfCollision([&](std::uint64_t, std::uint64_t, void*) { return ++n_pairs, false; }, nullptr);
+    EXPECT_TRUE(n_pairs == 2);  // (10,11) and (11,12)
+    Box<S> unit(1, 1, 1);
+    CollisionObject<S> obj(std::make_shared<Box<S>>(1, 1, 1), at(3, 0, 0));
+    const auto box = obj.computeAABB();
+    EXPECT_TRUE(std::fabs(box[0] - S(2.5)) < S(1e-6) && std::fabs(box[3] - S(3.5)) < S(1e-6));
+  }
+}
+
 int main() {
   run<float>();
   run<double>();
+  runScene<float>();
+  runScene<double>();
   std::printf(failures ? "HOST API: %d FAILURES\n" : "HOST API: ALL OK\n", failures);
   return failures ? 1 : 0;
 }
