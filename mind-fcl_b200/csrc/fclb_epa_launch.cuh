@@ -1,11 +1,29 @@
 // fclb_epa_launch.cuh -- launch of the warp-per-query EPA stage (own translation
 // units: the EPA kernels dominate compile time).
 #pragma once
+#include <cstdlib>
+
 #include "fclb_collide_impl.cuh"
 
 namespace fclb {
 
-constexpr int kTier1Faces = 48;  // tier-1 pool: 48 faces, 72 edges, 72 vertices per query
+// tier-1 pool: faces per query (edges = vertices = 1.51 x faces); FCLB_EPA_TIER1_FACES overrides it for tuning
+inline int tier1Faces() {
+  static int v = [] {
+    const char* e = getenv("FCLB_EPA_TIER1_FACES");
+    const int x = e ? atoi(e) : 0;
+    return x >= 8 ? x : 40;
+  }();
+  return v;
+}
+inline int epaBlocksPerSmCap() {
+  static int v = [] {
+    const char* e = getenv("FCLB_EPA_BLOCKS_PER_SM");
+    const int x = e ? atoi(e) : 0;
+    return x >= 1 ? x : 4;
+  }();
+  return v;
+}
 
 template <typename S, int T0, int T1, int T>
 cudaError_t launchEpaTier(const BatchView& b, const CollideLaunchArgs& a, int pool_faces, const EpaDefer& defer,
@@ -21,7 +39,7 @@ cudaError_t launchEpaTier(const BatchView& b, const CollideLaunchArgs& a, int po
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = int((227 * 1024) / (esmem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > epaBlocksPerSmCap()) per_sm = epaBlocksPerSmCap();
   kern<<<sms * per_sm, kEpaThreads, esmem, st>>>(b, S(a.sp.epa_tol), pool_faces, a.sp.epa_max_iter, a.mode, a.out,
                                                  a.work, defer, poly);
   return cudaGetLastError();
@@ -32,10 +50,10 @@ cudaError_t launchEpaT(const BatchView& b, const CollideLaunchArgs& a, cudaStrea
   EpaDefer d = a.defer;
   cudaError_t e = cudaMemsetAsync(d.count, 0, sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;
-  if (a.sp.epa_max_faces > kTier1Faces) {
+  if (a.sp.epa_max_faces > tier1Faces()) {
     d.enabled = 1;
     d.consume = 0;
-    e = launchEpaTier<S, T0, T1, 8>(b, a, kTier1Faces, d, st);
+    e = launchEpaTier<S, T0, T1, 8>(b, a, tier1Faces(), d, st);
     if (e != cudaSuccess) return e;
     d.enabled = 0;
     d.consume = 1;

@@ -16,8 +16,17 @@ FCLB_DI S absNorm(const V3<S>& v) {  // mpr.hpp:17-20
   return fabs_(v.x) + fabs_(v.y) + fabs_(v.z);
 }
 // mpr.hpp:11-15: normalises the direction IN PLACE, then supports along it
+// One out-of-line copy per Minkowski-difference type: the seven call sites of MPR (ten with the penetration
+// queries) would otherwise each inline both support mappings (a convex hill climb is ~400 SASS instructions)
+// and push the traversal kernels past the instruction cache (profiles/r01_mesh_shape.summary.txt: 4.5 issue
+// slots stalled on instruction fetch per issued instruction before this change).
+#ifndef FCLB_MPR_SUPPORT_INLINE
+#define FCLB_MPR_SUPPORT_ATTR __device__ __noinline__
+#else
+#define FCLB_MPR_SUPPORT_ATTR FCLB_DI
+#endif
 template <typename S, typename MD>
-FCLB_DI V3<S> mprSupport(const MD& shape, V3<S>& dir, uint32_t* n_support) {
+FCLB_MPR_SUPPORT_ATTR V3<S> mprSupport(const MD& shape, V3<S>& dir, uint32_t* n_support) {
   dir = normalized(dir);
   if (n_support) *n_support += 2;
   return shape.support(dir);
