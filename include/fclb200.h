@@ -255,6 +255,27 @@ int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes,
 int fclb_octree_shape_collide_batch_dev(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
                                         const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
                                         const fclb_request* req, uint32_t* out_counts, int64_t* out_first_node);
+/* ---- MPR penetration for scene contacts ---------------------------------------------------
+ * fcl::collide(scene geometry, tf1, Shape, tf2, request, result) with request.useDirectedPenetration(dir) or
+ * useIncrementalMinimumDistancePenetration(dir) (collision_interface-inl.h:22-30 -> collisionPenetrationMPR,
+ * narrowphase/collision_penetration-inl.h:189-252): the boolean traversal, then computePenetrationMPR
+ * between the contact's leaf geometry (the mesh triangle / the pixel or voxel Box, :34-95) and the shape.
+ *   out_counts[q]              = result.numContacts() (<= request.max_contacts)
+ *   out_b1[q*max_keep + k]     = Contact::b1 of the k-th stored contact (triangle id, encodePixel,
+ *                                encodeOctree2Node) or -1; k < min(count, max_keep)
+ *   out_contacts[(q*max_keep + k)*7 ..] = normal[3], pos[3], penetration_depth (depth -1: MPR reported failure)
+ * Which contacts are the first max_keep follows the device traversal order, not the reference's DFS order. */
+#define FCLB_SCENE_BVH 0
+#define FCLB_SCENE_HEIGHTMAP 1
+#define FCLB_SCENE_OCTREE 2
+int fclb_scene_shape_contacts_batch_host(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                         const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
+                                         const fclb_request* req, uint32_t max_keep, uint32_t* out_counts,
+                                         int64_t* out_b1, void* out_contacts);
+int fclb_scene_shape_contacts_batch_dev(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                        const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
+                                        const fclb_request* req, uint32_t max_keep, uint32_t* out_counts,
+                                        int64_t* out_b1, void* out_contacts);
 /* node tests and leaf (shape-triangle / shape-pixel) tests of the most recent scene batch call */
 int fclb_scene_last_visit_counts(uint64_t* n_node, uint64_t* n_leaf);
 

@@ -352,6 +352,10 @@ __global__ void __launch_bounds__(kBsWarps * 32) bvhShapeCollideKernel(BvhShapeA
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
         if (hm) {
           if (first < 0) first = __shfl_sync(0xffffffffu, tri_id, __ffs(hm) - 1);
+          if (a.out_b1 && hit) {
+            const uint32_t slot = count + uint32_t(__popc(hm & lt_mask));
+            if (slot < a.max_keep && slot < a.max_contacts) a.out_b1[q * a.max_keep + slot] = tri_id;
+          }
           count += uint32_t(__popc(hm));
           if (count >= a.max_contacts) {
             count = a.max_contacts;

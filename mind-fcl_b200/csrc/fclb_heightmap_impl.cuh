@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kHmWarps * 32) heightmapShapeKernel(HeightmapA
         const int batch = nq < 32 ? nq : 32;
         bool hit = false;
         uint32_t pc = 0;
+        V3<S> hb_min = zero3<S>(), hb_max = zero3<S>();
         if (lane < batch) {
           pc = queue[nq - 1 - lane];
           const int x = int(pc >> 16), y = int(pc & 0xffffu);
@@ -199,11 +200,22 @@ __global__ void __launch_bounds__(kHmWarps * 32) heightmapShapeKernel(HeightmapA
           tf_box.t = mulMV(tf_hm.R, center) + tf_hm.t;
           st_leaf++;
           hit = boxShapeHit<S, T1>(side, tf_box, sh, tf_shape, S(a.tol), a.max_iter, st);
+          hb_min = bmin;
+          hb_max = bmax;
         }
         nq -= batch;
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
         if (hm) {
           if (first < 0) first = int(__shfl_sync(0xffffffffu, pc, __ffs(hm) - 1));
+          if (a.out_b1 && hit) {
+            const uint32_t slot = count + uint32_t(__popc(hm & lt_mask));
+            if (slot < a.max_keep && slot < a.max_contacts) {
+              a.out_b1[q * a.max_keep + slot] = (long long)pc;
+              S* ob = static_cast<S*>(a.out_box) + (q * a.max_keep + slot) * 6;
+              ob[0] = hb_min.x; ob[1] = hb_min.y; ob[2] = hb_min.z;
+              ob[3] = hb_max.x; ob[4] = hb_max.y; ob[5] = hb_max.z;
+            }
+          }
           count += uint32_t(__popc(hm));
           if (count >= a.max_contacts) {
             count = a.max_contacts;

@@ -64,6 +64,10 @@ struct BvhShapeArgs {
   int max_iter;
   uint32_t* counts;
   int32_t* first_tri;
+  // optional contact sink (pass 1 of the MPR penetration modes): ids / boxes of the first max_keep hit leaves
+  uint32_t max_keep;
+  long long* out_b1;   // [n * max_keep]
+  void* out_box;       // [n * max_keep * 6 S] leaf box in the scene frame (heightmap / octree), or nullptr
   unsigned long long* work_counter;
   unsigned long long* stats;  // [0] node tests, [1] leaf tests
 };
@@ -92,6 +96,10 @@ struct HeightmapArgs {
   int max_iter;
   uint32_t* counts;
   int32_t* first_pixel;     // encodePixel = x << 16 | y (heightmap_types.h:53-58) or -1
+  // optional contact sink (pass 1 of the MPR penetration modes): ids / boxes of the first max_keep hit leaves
+  uint32_t max_keep;
+  long long* out_b1;   // [n * max_keep]
+  void* out_box;       // [n * max_keep * 6 S] leaf box in the scene frame (heightmap / octree), or nullptr
   unsigned long long* work_counter;
   unsigned long long* stats;  // [0] pixels read, [1] pixel boxes tested
 };
@@ -119,10 +127,36 @@ struct OctreeArgs {
   int max_iter;
   uint32_t* counts;
   long long* first_node;           // encodeOctree2Node of one hit box or -1
+  // optional contact sink (pass 1 of the MPR penetration modes): ids / boxes of the first max_keep hit leaves
+  uint32_t max_keep;
+  long long* out_b1;   // [n * max_keep]
+  void* out_box;       // [n * max_keep * 6 S] leaf box in the scene frame (heightmap / octree), or nullptr
   unsigned long long* work_counter;
   unsigned long long* stats;       // [0] node boxes tested, [1] voxel boxes tested
 };
 template <typename S>
 cudaError_t launchOctreeShape(int type1, const OctreeArgs& a, int grid, cudaStream_t st);
+
+// pass 2 of the MPR penetration modes for scene contacts (fclb_scene_pen_impl.cuh)
+struct ScenePenArgs {
+  int leaf_is_triangle;      // 1: b1 = triangle id of `tris`; 0: box from out_box
+  const void* tris;          // 12 S per triangle (device BVH layout)
+  const void* shapes;
+  const void* convex;
+  const uint32_t* shape_ids;
+  const void* poses_scene;
+  const void* poses_shape;
+  size_t n;
+  uint32_t max_keep;
+  const uint32_t* counts;
+  const long long* b1;
+  const void* box;
+  int incremental;
+  double dir[3];
+  double tol;
+  void* out_contacts;        // [n * max_keep * 7 S] = normal, pos, depth
+};
+template <typename S>
+cudaError_t launchScenePenetration(const ScenePenArgs& a, cudaStream_t st);
 
 }  // namespace fclb

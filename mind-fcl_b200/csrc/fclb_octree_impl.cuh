@@ -185,8 +185,9 @@ __global__ void __launch_bounds__(kOctWarps * 32) octreeShapeKernel(OctreeArgs a
         const int batch = nq < 32 ? nq : 32;
         bool hit = false;
         long long code = -1;
+        OctCand<S> c;
         if (lane < batch) {
-          const OctCand<S> c = queue[nq - 1 - lane];
+          c = queue[nq - 1 - lane];
           code = c.code;
           const V3<S> bmin = mk<S>(c.mn[0], c.mn[1], c.mn[2]), bmax = mk<S>(c.mx[0], c.mx[1], c.mx[2]);
           const V3<S> side = bmax - bmin;
@@ -201,6 +202,18 @@ __global__ void __launch_bounds__(kOctWarps * 32) octreeShapeKernel(OctreeArgs a
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
         if (hm) {
           if (first < 0) first = __shfl_sync(0xffffffffu, code, __ffs(hm) - 1);
+          if (a.out_b1 && hit) {
+            const uint32_t slot = count + uint32_t(__popc(hm & ((1u << lane) - 1u)));
+            if (slot < a.max_keep && slot < a.max_contacts) {
+              a.out_b1[q * a.max_keep + slot] = code;
+              S* ob = static_cast<S*>(a.out_box) + (q * a.max_keep + slot) * 6;
+#pragma unroll
+              for (int k = 0; k < 3; k++) {
+                ob[k] = c.mn[k];
+                ob[3 + k] = c.mx[k];
+              }
+            }
+          }
           count += uint32_t(__popc(hm));
           if (count >= a.max_contacts) {
             count = a.max_contacts;
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(kOctWarps * 32) octreeShapeKernel(OctreeArgs a
             OctCand<S> cd;
             cd.mn[0] = mn.x; cd.mn[1] = mn.y; cd.mn[2] = mn.z;
             cd.mx[0] = mx.x; cd.mx[1] = mx.y; cd.mx[2] = mx.z;
-            cd.code = base;
+            cd.code = base + (8ll << 32);  // inner_child_idx defaults to kInvalidChildIndex = 8 (octree2_solver.h:47-49)
             queue[nq + cand_off] = cd;
           } else {
             int k = 0;

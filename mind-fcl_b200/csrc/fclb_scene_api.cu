@@ -11,6 +11,12 @@ namespace fclb {
 static unsigned long long* g_counters = nullptr;  // [0] work counter, [1..2] stats
 static unsigned long long g_stats[2] = {0, 0};
 
+struct ContactSink {  // pass 1 of the MPR penetration modes
+  uint32_t max_keep = 0;
+  long long* b1 = nullptr;
+  void* box = nullptr;
+};
+
 static int tableUniformType(const ShapeTable* t) {
   int type = int(t->host[0].type);
   for (uint32_t i = 1; i < t->n; i++)
@@ -20,7 +26,8 @@ static int tableUniformType(const ShapeTable* t) {
 
 template <typename S>
 static int bvhShapeDev(Engine& e, const BvhDev* m, const ShapeTable* t, const uint32_t* shape_ids, const void* poses_mesh,
-                       const void* poses_shape, size_t n, const fclb_request* req, uint32_t* counts, int32_t* first_tri) {
+                       const void* poses_shape, size_t n, const fclb_request* req, uint32_t* counts, int32_t* first_tri,
+                       const ContactSink& sink = ContactSink()) {
   const int st = sizeof(S) == 4 ? 0 : 1;
   if (!g_counters) FCLB_CUDA(cudaMalloc(&g_counters, 4 * sizeof(unsigned long long)));
   FCLB_CUDA(cudaMemsetAsync(g_counters, 0, 4 * sizeof(unsigned long long), e.compute));
@@ -41,6 +48,9 @@ static int bvhShapeDev(Engine& e, const BvhDev* m, const ShapeTable* t, const ui
   a.max_iter = sp.gjk_max_iter;
   a.counts = counts;
   a.first_tri = first_tri;
+  a.max_keep = sink.max_keep;
+  a.out_b1 = sink.b1;
+  a.out_box = sink.box;
   a.work_counter = g_counters;
   a.stats = g_counters + 1;
   const size_t need = (n + kBvhShapeWarps - 1) / kBvhShapeWarps;
@@ -81,7 +91,7 @@ static std::map<fclb_handle, HeightmapDev*>& hmTable() {
 template <typename S>
 static int heightmapShapeDev(Engine& e, const HeightmapDev* hm, const ShapeTable* t, const uint32_t* shape_ids,
                              const void* poses_hm, const void* poses_shape, size_t n, const fclb_request* req,
-                             uint32_t* counts, int32_t* first_pixel) {
+                             uint32_t* counts, int32_t* first_pixel, const ContactSink& sink = ContactSink()) {
   const int st = sizeof(S) == 4 ? 0 : 1;
   if (!g_counters) FCLB_CUDA(cudaMalloc(&g_counters, 4 * sizeof(unsigned long long)));
   FCLB_CUDA(cudaMemsetAsync(g_counters, 0, 4 * sizeof(unsigned long long), e.compute));
@@ -111,6 +121,9 @@ static int heightmapShapeDev(Engine& e, const HeightmapDev* hm, const ShapeTable
   a.max_iter = sp.gjk_max_iter;
   a.counts = counts;
   a.first_pixel = first_pixel;
+  a.max_keep = sink.max_keep;
+  a.out_b1 = sink.b1;
+  a.out_box = sink.box;
   a.work_counter = g_counters;
   a.stats = g_counters + 1;
   const size_t need = (n + kHeightmapWarps - 1) / kHeightmapWarps;
@@ -150,7 +163,7 @@ static std::map<fclb_handle, OctreeDev*>& octTable() {
 template <typename S>
 static int octreeShapeDev(Engine& e, const OctreeDev* o, const ShapeTable* t, const uint32_t* shape_ids,
                           const void* poses_octree, const void* poses_shape, size_t n, const fclb_request* req,
-                          uint32_t* counts, long long* first_node) {
+                          uint32_t* counts, long long* first_node, const ContactSink& sink = ContactSink()) {
   const int st = sizeof(S) == 4 ? 0 : 1;
   if (!g_counters) FCLB_CUDA(cudaMalloc(&g_counters, 4 * sizeof(unsigned long long)));
   FCLB_CUDA(cudaMemsetAsync(g_counters, 0, 4 * sizeof(unsigned long long), e.compute));
@@ -176,6 +189,9 @@ static int octreeShapeDev(Engine& e, const OctreeDev* o, const ShapeTable* t, co
   a.max_iter = sp.gjk_max_iter;
   a.counts = counts;
   a.first_node = first_node;
+  a.max_keep = sink.max_keep;
+  a.out_b1 = sink.b1;
+  a.out_box = sink.box;
   a.work_counter = g_counters;
   a.stats = g_counters + 1;
   const size_t need = (n + kOctreeWarps - 1) / kOctreeWarps;
@@ -196,6 +212,74 @@ static int octreeShapeDev(Engine& e, const OctreeDev* o, const ShapeTable* t, co
   e.rec_kind[0] = -4;
   e.rec_count[0] = n;
   e.rec_ms[0] = ms;
+  return FCLB_OK;
+}
+
+// fcl::collide with a DirectedPenetration / IncrementalMinimumPenetration request against a scene geometry:
+// boolean traversal with a contact sink (pass 1), then one MPR penetration per stored contact (pass 2).
+template <typename S>
+static int sceneContactsDev(Engine& e, int kind, fclb_handle scene, const ShapeTable* t, const uint32_t* shape_ids,
+                            const void* poses_scene, const void* poses_shape, size_t n, const fclb_request* req,
+                            uint32_t max_keep, uint32_t* counts, long long* b1, void* contacts) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  static void* d_box = nullptr;
+  static size_t d_box_cap = 0;
+  const size_t box_bytes = n * size_t(max_keep) * 6 * sizeof(S);
+  if (kind != FCLB_SCENE_BVH && d_box_cap < box_bytes) {
+    cudaFree(d_box);
+    d_box = nullptr;
+    d_box_cap = 0;
+    FCLB_CUDA(cudaMalloc(&d_box, box_bytes));
+    d_box_cap = box_bytes;
+  }
+  ContactSink sink;
+  sink.max_keep = max_keep;
+  sink.b1 = b1;
+  sink.box = kind == FCLB_SCENE_BVH ? nullptr : d_box;
+  fclb_request boolean_req = *req;
+  boolean_req.penetration_mode = FCLB_PEN_DISABLED;
+  const void* tris = nullptr;
+  int rc = FCLB_OK;
+  if (kind == FCLB_SCENE_BVH) {
+    auto it = bvhTable().find(scene);
+    if (it == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown BVH handle");
+    if (it->second->scalar_type != st) return fail(FCLB_ERR_BAD_ARG, "BVH was uploaded for a different scalar type");
+    tris = it->second->tris;
+    rc = bvhShapeDev<S>(e, it->second, t, shape_ids, poses_scene, poses_shape, n, &boolean_req, counts, nullptr, sink);
+  } else if (kind == FCLB_SCENE_HEIGHTMAP) {
+    auto it = hmTable().find(scene);
+    if (it == hmTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown heightmap handle");
+    rc = heightmapShapeDev<S>(e, it->second, t, shape_ids, poses_scene, poses_shape, n, &boolean_req, counts, nullptr, sink);
+  } else if (kind == FCLB_SCENE_OCTREE) {
+    auto it = octTable().find(scene);
+    if (it == octTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown octree handle");
+    rc = octreeShapeDev<S>(e, it->second, t, shape_ids, poses_scene, poses_shape, n, &boolean_req, counts, nullptr, sink);
+  } else {
+    return fail(FCLB_ERR_BAD_ARG, "unknown scene kind");
+  }
+  if (rc) return rc;
+  const SolverParams sp = solverParams(st, req->binary_tol, req->gjk_max_iter, req->distance_tol, req->epa_max_faces,
+                                       req->epa_max_iter, true);
+  ScenePenArgs p{};
+  p.leaf_is_triangle = kind == FCLB_SCENE_BVH ? 1 : 0;
+  p.tris = tris;
+  p.shapes = t->d_shapes[st];
+  p.convex = e.d_convex_tab[st];
+  p.shape_ids = shape_ids;
+  p.poses_scene = poses_scene;
+  p.poses_shape = poses_shape;
+  p.n = n;
+  p.max_keep = max_keep;
+  p.counts = counts;
+  p.b1 = b1;
+  p.box = sink.box;
+  p.incremental = req->penetration_mode == FCLB_PEN_INCREMENTAL_MIN ? 1 : 0;
+  for (int k = 0; k < 3; k++) p.dir[k] = req->dir[k];
+  p.tol = sp.epa_tol;  // MPR(128, request.distanceTolerance())
+  p.out_contacts = contacts;
+  FCLB_CUDA(launchScenePenetration<S>(p, e.compute));
+  e.launches += 1;
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }
 
@@ -548,6 +632,75 @@ int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes,
   if (rc) return rc;
   FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
   if (out_first_node) FCLB_CUDA(cudaMemcpyAsync(out_first_node, base + o_fn, n * 8, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+int fclb_scene_shape_contacts_batch_dev(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                        const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
+                                        const fclb_request* req, uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1,
+                                        void* out_contacts) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  ShapeTable* t = findTable(e, shapes);
+  if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (!req || !out_counts || !out_b1 || !out_contacts || max_keep == 0) return fail(FCLB_ERR_BAD_ARG, "null output / max_keep == 0");
+  if (req->penetration_mode != FCLB_PEN_DIRECTED && req->penetration_mode != FCLB_PEN_INCREMENTAL_MIN)
+    return fail(FCLB_ERR_UNSUPPORTED, "fclb_scene_shape_contacts_batch serves the MPR penetration modes "
+                                      "(FCLB_PEN_DIRECTED, FCLB_PEN_INCREMENTAL_MIN)");
+  if (n == 0) return FCLB_OK;
+  if (!shape_ids || !poses_scene || !poses_shape) return fail(FCLB_ERR_BAD_ARG, "null input array");
+  if (scalar_type == FCLB_F32)
+    return sceneContactsDev<float>(e, scene_kind, scene, t, shape_ids, poses_scene, poses_shape, n, req, max_keep, out_counts,
+                                   reinterpret_cast<long long*>(out_b1), out_contacts);
+  return sceneContactsDev<double>(e, scene_kind, scene, t, shape_ids, poses_scene, poses_shape, n, req, max_keep, out_counts,
+                                  reinterpret_cast<long long*>(out_b1), out_contacts);
+}
+
+int fclb_scene_shape_contacts_batch_host(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                         const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
+                                         const fclb_request* req, uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1,
+                                         void* out_contacts) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!shape_ids || !poses_scene || !poses_shape || !out_counts || !out_b1 || !out_contacts || max_keep == 0)
+    return fail(FCLB_ERR_BAD_ARG, "null array / max_keep == 0");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  {
+    ShapeTable* t = findTable(e, shapes);
+    if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
+    for (size_t q = 0; q < n; q++)
+      if (shape_ids[q] >= t->n) return fail(FCLB_ERR_BAD_ARG, "shape id out of range");
+  }
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t o_ids = 0;
+  const size_t o_p1 = alignUp(o_ids + n * 4, 256);
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_b1 = alignUp(o_cnt + n * 4, 256);
+  const size_t o_ct = alignUp(o_b1 + n * size_t(max_keep) * 8, 256);
+  const size_t total = alignUp(o_ct + n * size_t(max_keep) * 7 * ss, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_ids, shape_ids, n * 4, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses_scene, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses_shape, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemsetAsync(base + o_b1, 0xff, n * size_t(max_keep) * 8, e.compute));
+  rc = fclb_scene_shape_contacts_batch_dev(scene_kind, scene, shapes, reinterpret_cast<const uint32_t*>(base + o_ids),
+                                           base + o_p1, base + o_p2, n, scalar_type, req, max_keep,
+                                           reinterpret_cast<uint32_t*>(base + o_cnt), reinterpret_cast<int64_t*>(base + o_b1),
+                                           base + o_ct);
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(out_b1, base + o_b1, n * size_t(max_keep) * 8, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(out_contacts, base + o_ct, n * size_t(max_keep) * 7 * ss, cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }

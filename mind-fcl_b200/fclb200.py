@@ -36,6 +36,7 @@ EXPORTS = [
     "fclb_heightmap_shape_collide_batch_host", "fclb_heightmap_shape_collide_batch_dev",
     "fclb_octree_upload", "fclb_octree_release", "fclb_octree_shape_collide_batch_host",
     "fclb_octree_shape_collide_batch_dev",
+    "fclb_scene_shape_contacts_batch_host", "fclb_scene_shape_contacts_batch_dev",
     "fclb_broadphase_build_host", "fclb_broadphase_build_dev", "fclb_broadphase_release",
     "fclb_broadphase_self_pairs_host", "fclb_broadphase_self_pairs_dev", "fclb_broadphase_tree_pairs_host",
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
@@ -172,6 +173,10 @@ def load() -> C.CDLL:
         os_args = [C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp]
         lib.fclb_octree_shape_collide_batch_host.argtypes = os_args
         lib.fclb_octree_shape_collide_batch_dev.argtypes = os_args
+    if hasattr(lib, "fclb_scene_shape_contacts_batch_host"):
+        sc2 = [C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, u32, vp, vp, vp]
+        lib.fclb_scene_shape_contacts_batch_host.argtypes = sc2
+        lib.fclb_scene_shape_contacts_batch_dev.argtypes = sc2
     _lib = lib
     return lib
 
@@ -541,3 +546,20 @@ def octree_shape_collide_batch_host(octree, table, shape_ids, poses_octree, pose
                                                       scalar_type, C.cast(C.pointer(request), C.c_void_p), _ptr(counts),
                                                       _ptr(node)))
     return counts, node
+
+
+SCENE_BVH, SCENE_HEIGHTMAP, SCENE_OCTREE = 0, 1, 2
+
+
+def scene_shape_contacts_batch_host(kind, scene, table, shape_ids, poses_scene, poses_shape, scalar_type, request: Request,
+                                    max_keep):
+    """fcl::collide(scene, tf1, Shape, tf2) with an MPR penetration request: (counts, b1 [n,k], contacts [n,k,7])."""
+    n = len(poses_scene)
+    ids = np.ascontiguousarray(shape_ids, np.uint32)
+    counts = np.zeros(n, np.uint32)
+    b1 = np.zeros((n, max_keep), np.int64)
+    contacts = np.zeros((n, max_keep, 7), np_dtype(scalar_type))
+    check(load().fclb_scene_shape_contacts_batch_host(kind, scene, table, _ptr(ids), _ptr(poses_scene), _ptr(poses_shape), n,
+                                                      scalar_type, C.cast(C.pointer(request), C.c_void_p), max_keep,
+                                                      _ptr(counts), _ptr(b1), _ptr(contacts)))
+    return counts, b1, contacts

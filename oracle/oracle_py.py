@@ -277,6 +277,23 @@ class RefOracle(_Oracle):
           C.cast(C.pointer(r), C.c_void_p), _p(counts), _p(node), threads)
         return counts, node
 
+    # ---- every contact of a scene-vs-shape query (any request mode) ----
+    def scene_shape_contacts_batch(self, kind, scene_id, shapes, shape_ids, poses_scene, poses_shape, max_keep, threads=1,
+                                   **req):
+        n = len(poses_scene)
+        ids = np.ascontiguousarray(shape_ids, np.uint32)
+        counts = np.zeros(n, np.uint32)
+        b1 = np.zeros((n, max_keep), np.int64)
+        contacts = np.zeros((n, max_keep, 7), poses_scene.dtype)
+        r = _request(**req)
+        arr = _shape_array(shapes)
+        f = self.fn("scene_shape_contacts_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                      C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(poses_scene.dtype), kind, scene_id, C.cast(arr, C.c_void_p), len(shapes), _p(ids), _p(poses_scene),
+          _p(poses_shape), n, C.cast(C.pointer(r), C.c_void_p), max_keep, _p(counts), _p(b1), _p(contacts), threads)
+        return counts, b1, contacts
+
     # ---- broadphase ----
     def compute_aabb_batch(self, shapes, shape_ids, poses):
         ids = np.ascontiguousarray(shape_ids, np.uint32)

@@ -77,10 +77,23 @@ void parallelFor(size_t n, int n_threads, F&& f) {
 template <typename S>
 fcl::CollisionRequest<S> makeRequest(const RequestRec* rq) {
   fcl::CollisionRequest<S> req(rq->max_contacts);
-  if (rq->penetration_mode == 1)
-    req.useDefaultPenetration();
-  else
-    req.disablePenetration();
+  const fcl::Vector3<S> dir(S(rq->dir[0]), S(rq->dir[1]), S(rq->dir[2]));
+  switch (rq->penetration_mode) {
+    case 1:
+      req.useDefaultPenetration();
+      break;
+    case 2:
+      req.useDirectedPenetration(dir);
+      break;
+    case 3:
+      req.useIncrementalMinimumDistancePenetration(dir);
+      break;
+    default:
+      req.disablePenetration();
+      break;
+  }
+  if (rq->binary_tol > 0) req.setBinaryCollisionTolerance(S(rq->binary_tol));
+  if (rq->distance_tol > 0) req.setPenetrationDistanceTolerance(S(rq->distance_tol));
   return req;
 }
 
@@ -200,6 +213,40 @@ void octShapeBatch(int oct_id, const ShapeRec* shapes, uint32_t n_shapes, const 
                                        loadPose<S>(poses_shape + 12 * q), req, res);
       counts[q] = uint32_t(c);
       if (first_node) first_node[q] = c ? int64_t(res.getContact(0).b1) : -1;
+    }
+  });
+}
+
+// every contact of a scene-vs-shape query (any request mode): b1 + {normal, pos, depth}
+template <typename S>
+void sceneContactsBatch(const fcl::CollisionGeometry<S>* scene, const ShapeRec* shapes, uint32_t n_shapes,
+                        const uint32_t* shape_ids, const S* poses_scene, const S* poses_shape, size_t n,
+                        const RequestRec* rq, uint32_t max_keep, uint32_t* counts, int64_t* b1, S* contacts, int threads) {
+  std::vector<std::shared_ptr<fcl::ShapeBase<S>>> objs;
+  for (uint32_t i = 0; i < n_shapes; i++) objs.push_back(Sel<S>::shape(shapes + i));
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    const fcl::CollisionRequest<S> req = makeRequest<S>(rq);
+    for (size_t q = b; q < e; q++) {
+      fcl::CollisionResult<S> res;
+      const size_t c = fcl::collide<S>(scene, loadPose<S>(poses_scene + 12 * q), objs[shape_ids[q]].get(),
+                                       loadPose<S>(poses_shape + 12 * q), req, res);
+      counts[q] = uint32_t(c);
+      for (uint32_t k = 0; k < max_keep; k++) {
+        int64_t* id = b1 + q * max_keep + k;
+        S* o = contacts + (q * max_keep + k) * 7;
+        if (k < c) {
+          const auto& ct = res.getContact(k);
+          *id = int64_t(ct.b1);
+          for (int j = 0; j < 3; j++) {
+            o[j] = ct.normal[j];
+            o[3 + j] = ct.pos[j];
+          }
+          o[6] = ct.penetration_depth;
+        } else {
+          *id = -1;
+          for (int j = 0; j < 7; j++) o[j] = S(0);
+        }
+      }
     }
   });
 }
@@ -376,6 +423,29 @@ size_t fclref_scene_self_collide(int scalar_type, const void* shapes, uint32_t n
     return hits;
   };
   return scalar_type == 0 ? run(float(0)) : run(double(0));
+}
+
+/* kind: 0 mesh (BVHModel<OBBRSS>), 1 heightmap, 2 octree */
+int fclref_scene_shape_contacts_batch(int scalar_type, int kind, int scene_id, const void* shapes, uint32_t n_shapes,
+                                      const uint32_t* shape_ids, const void* poses_scene, const void* poses_shape, size_t n,
+                                      const void* request, uint32_t max_keep, uint32_t* counts, int64_t* b1, void* contacts,
+                                      int threads) {
+  if (scalar_type == 0) {
+    const fcl::CollisionGeometry<float>* g = kind == 0   ? (const fcl::CollisionGeometry<float>*)Sel<float>::mesh(scene_id)
+                                             : kind == 1 ? (const fcl::CollisionGeometry<float>*)getHm<float>(scene_id)
+                                                         : (const fcl::CollisionGeometry<float>*)getOct<float>(scene_id);
+    sceneContactsBatch<float>(g, (const ShapeRec*)shapes, n_shapes, shape_ids, (const float*)poses_scene,
+                              (const float*)poses_shape, n, (const RequestRec*)request, max_keep, counts, b1, (float*)contacts,
+                              threads);
+  } else {
+    const fcl::CollisionGeometry<double>* g = kind == 0   ? (const fcl::CollisionGeometry<double>*)Sel<double>::mesh(scene_id)
+                                              : kind == 1 ? (const fcl::CollisionGeometry<double>*)getHm<double>(scene_id)
+                                                          : (const fcl::CollisionGeometry<double>*)getOct<double>(scene_id);
+    sceneContactsBatch<double>(g, (const ShapeRec*)shapes, n_shapes, shape_ids, (const double*)poses_scene,
+                               (const double*)poses_shape, n, (const RequestRec*)request, max_keep, counts, b1,
+                               (double*)contacts, threads);
+  }
+  return 0;
 }
 
 int fclref_octree_create(const double* points, size_t n_points, double resolution, int half_shape) {
