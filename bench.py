@@ -666,7 +666,9 @@ def main():
         prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(prof):
             with open(prof) as f:
-                traffic = json.load(f).get(top["kernel"] + ":" + args.dtype)
+                rec = json.load(f).get(top["kernel"] + ":" + args.dtype)
+            if rec:  # one ncu capture, scaled linearly to this launch's query count
+                traffic = rec["bytes"] * top["queries"] / rec["queries"]
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": top["kernel"], "peak_source": peak_src,
                 "algorithmic_bytes_per_query": bpq, "queries_per_launch": top["queries"],
@@ -697,6 +699,12 @@ def main():
 
     if hasattr(wl, "extra"):
         line["config"].update(wl.extra())
+    if rank == 0:
+        try:  # measured CUDA-core FMA peaks: the denominators for the compute-bound GJK / MPR / EPA kernels
+            line["fp_peak_measured"] = {"fp32_tflops": fclb.measure_fp_peak(fclb.F32), "fp64_tflops": fclb.measure_fp_peak(fclb.F64),
+                                        "how": "FMA chain, 16 accumulators per thread, 8 CTAs x 256 threads per SM, best of 5"}
+        except Exception as ex:
+            line["fp_peak_measured"] = {"error": str(ex)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             oracle = load_oracle()

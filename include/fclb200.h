@@ -331,6 +331,10 @@ int fclb_scene_self_collide_dev(fclb_handle shapes, const uint32_t* shape_ids, c
                                 int scalar_type, const fclb_request* req, size_t* n_candidates, size_t* n_colliding,
                                 uint64_t* out_id_pairs, uint32_t* out_counts, size_t out_cap);
 
+/* measured FP32 / FP64 FMA throughput of the bound device (FMA-chain microbenchmark, TFLOP/s):
+ * the denominator for the compute-bound GJK / MPR / EPA kernels */
+int fclb_measure_fp_peak(int scalar_type, double* tflops);
+
 /* kernel launches issued by this process so far (bench.py's gpu_launches) */
 uint64_t fclb_launch_count(void);
 /* device time (ms, CUDA events on the engine's stream) of the most recent batch

@@ -347,6 +347,23 @@ int ensureStage(Engine& e, size_t bytes) {
 
 using namespace fclb;
 
+// FMA-chain microbenchmark: the FP32 / FP64 CUDA-core peak the compute-bound kernels are compared with
+// (SURVEY.md 8d asks for measured, not nominal, FP peaks).  16 independent accumulators per thread.
+template <typename S>
+__global__ void __launch_bounds__(256) fmaPeakKernel(S* out, int iters, S a, S b) {
+  S acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) acc[k] = S(threadIdx.x + k);
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = fma(acc[k], a, b);  // explicit: this file is compiled with --fmad=false
+  }
+  S sum = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) sum += acc[k];
+  if (sum == S(-12345)) out[0] = sum;  // keep the chain alive
+}
+
 extern "C" {
 
 const char* fclb_last_error(void) { return g_err.c_str(); }
@@ -422,6 +439,36 @@ int fclb_synchronize(void) {
   int rc = ensureInit();
   if (rc) return rc;
   FCLB_CUDA(cudaDeviceSynchronize());
+  return FCLB_OK;
+}
+
+int fclb_measure_fp_peak(int scalar_type, double* tflops) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (!tflops || (scalar_type != FCLB_F32 && scalar_type != FCLB_F64)) return fail(FCLB_ERR_BAD_ARG, "fclb_measure_fp_peak: bad argument");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  void* d_out = nullptr;
+  FCLB_CUDA(cudaMalloc(&d_out, 64));
+  const int grid = e.sms * 8, block = 256;
+  const int iters = scalar_type == FCLB_F32 ? 4096 : 1024;
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 6; rep++) {
+    FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+    if (scalar_type == FCLB_F32)
+      fmaPeakKernel<float><<<grid, block, 0, e.compute>>>(static_cast<float*>(d_out), iters, 1.000001f, 0.5f);
+    else
+      fmaPeakKernel<double><<<grid, block, 0, e.compute>>>(static_cast<double*>(d_out), iters, 1.000001, 0.5);
+    FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+    e.launches += 1;
+  }
+  cudaFree(d_out);
+  const double flops = 2.0 * 16.0 * double(iters) * double(grid) * double(block);
+  *tflops = flops / (double(best_ms) * 1e-3) / 1e12;
   return FCLB_OK;
 }
 

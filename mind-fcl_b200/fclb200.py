@@ -42,7 +42,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
-    "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
+    "fclb_measure_fp_peak", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
 
@@ -563,3 +563,10 @@ def scene_shape_contacts_batch_host(kind, scene, table, shape_ids, poses_scene, 
                                                       scalar_type, C.cast(C.pointer(request), C.c_void_p), max_keep,
                                                       _ptr(counts), _ptr(b1), _ptr(contacts)))
     return counts, b1, contacts
+
+
+def measure_fp_peak(scalar_type) -> float:
+    """FMA-chain microbenchmark on the bound device, TFLOP/s."""
+    v = C.c_double()
+    check(load().fclb_measure_fp_peak(scalar_type, C.byref(v)))
+    return v.value
