@@ -192,6 +192,22 @@ int fclb_bvh_collide_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* 
 int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
                                int scalar_type, const fclb_request* req, uint32_t* out_counts,
                                int32_t* out_first_pair);
+/* fcl::collide(BVH, BVH) with request.useDefaultPenetration(): contact generation of
+ * Intersect::intersect_Triangle (traversal/collision/intersect-inl.h:795-888) through trianglePairIntersect
+ * (shape_pair_intersect-inl.h:201-252): up to two contact points per intersecting triangle pair, sharing one
+ * normal and depth.
+ *   out_counts[q] = result.numContacts() = min(sum of contact points, max_contacts)
+ *   out_ids[(q*max_keep + k)*2 ..]      = b1, b2 of the k-th stored contact (or -1, -1)
+ *   out_contacts[(q*max_keep + k)*7 ..] = normal[3], pos[3], penetration_depth, as the reference reports them
+ *     (it maps the mesh-1-frame contact with tf2 -- SimplexIntersect passes tf2 as the contact frame,
+ *     shape_pair_intersect-inl.h:266 -- which is reproduced)
+ * Which contacts are the first max_keep follows the device traversal order. */
+int fclb_bvh_collide_contacts_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2,
+                                         size_t n, int scalar_type, const fclb_request* req, uint32_t max_keep,
+                                         uint32_t* out_counts, int32_t* out_ids, void* out_contacts);
+int fclb_bvh_collide_contacts_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2,
+                                        size_t n, int scalar_type, const fclb_request* req, uint32_t max_keep,
+                                        uint32_t* out_counts, int32_t* out_ids, void* out_contacts);
 /* BV-pair and leaf-pair tests executed by the most recent mesh batch call */
 int fclb_bvh_last_visit_counts(uint64_t* n_bv, uint64_t* n_leaf);
 

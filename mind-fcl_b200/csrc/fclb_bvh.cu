@@ -86,6 +86,64 @@ FCLB_DI bool triTriIntersect(const V3<S> P[3], const V3<S> Q[3], const M3<S>& R,
   return true;
 }
 
+// Contact part of Intersect::intersect_Triangle (intersect-inl.h:795-845) for an intersecting pair:
+// buildTrianglePlane (:1036-1050), computeDeepestPoints (:849-888).  P, Qw in mesh 1's frame.
+// Returns the number of contact points (0..2); points / depth / normal in mesh 1's frame.
+template <typename S>
+FCLB_DI void deepestPoints(const V3<S> pts[3], const V3<S>& n, S t, S& depth, V3<S> deepest[3], unsigned& num) {
+  const S eps = S(1e-5);  // Intersect<S>::getEpsilon()
+  S max_depth = -(sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308));
+  unsigned nd = 0, num_neg = 0, num_pos = 0, num_zero = 0;
+  for (int i = 0; i < 3; i++) {
+    const S dist = -(dot(n, pts[i]) - t);
+    if (dist > eps)
+      num_pos++;
+    else if (dist < -eps)
+      num_neg++;
+    else
+      num_zero++;
+    if (dist > max_depth) {
+      max_depth = dist;
+      nd = 1;
+      deepest[0] = pts[i];
+    } else if (double(dist) + 1e-6 >= double(max_depth)) {  // "dist + 1e-6": a double literal
+      nd++;
+      deepest[nd - 1] = pts[i];
+    }
+  }
+  if (max_depth < -eps) nd = 0;
+  if (num_zero == 0 && ((num_neg == 0) || (num_pos == 0))) nd = 0;
+  depth = max_depth;
+  num = nd;
+}
+template <typename S>
+FCLB_DI unsigned triTriContacts(const V3<S> P[3], const V3<S> Q[3], const M3<S>& R, const V3<S>& T, V3<S> pts[2], S& depth,
+                                V3<S>& normal) {
+  const V3<S> Qw[3] = {mulMV(R, Q[0]) + T, mulMV(R, Q[1]) + T, mulMV(R, Q[2]) + T};
+  V3<S> n1 = normalized(cross(P[1] - P[0], P[2] - P[0]));
+  const S t1 = dot(n1, P[0]);
+  V3<S> n2 = normalized(cross(Qw[1] - Qw[0], Qw[2] - Qw[0]));
+  const S t2 = dot(n2, Qw[0]);
+  V3<S> deep1[3], deep2[3];
+  unsigned num1 = 0, num2 = 0;
+  S pd1, pd2;
+  deepestPoints(Qw, n1, t1, pd2, deep2, num2);
+  deepestPoints(P, n2, t2, pd1, deep1, num1);
+  unsigned nc;
+  if (pd1 > pd2) {
+    nc = num2 < 2u ? num2 : 2u;
+    for (unsigned i = 0; i < nc; i++) pts[i] = deep2[i];
+    normal = n1;
+    depth = pd2;
+  } else {
+    nc = num1 < 2u ? num1 : 2u;
+    for (unsigned i = 0; i < nc; i++) pts[i] = deep1[i];
+    normal = -n2;
+    depth = pd1;
+  }
+  return nc;
+}
+
 constexpr int kBvhWarps = 8;        // warps per CTA
 constexpr int kStackCap = 1024;     // (node,node) pairs per warp
 constexpr int kLeafCap = 64;        // queued leaf pairs per warp
@@ -103,9 +161,13 @@ struct BvhArgs {
   int32_t* first_pair;
   unsigned long long* work_counter;
   unsigned long long* stats;  // [0] BV-pair tests, [1] leaf-pair tests (optional)
+  // contact generation (request.useDefaultPenetration()): first max_keep contacts of each query
+  uint32_t max_keep;
+  int32_t* out_ids;      // [n * max_keep * 2] = b1, b2
+  void* out_contacts;    // [n * max_keep * 7 S] = normal, pos, depth (world frame)
 };
 
-template <typename S>
+template <typename S, bool PEN>
 __global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
   extern __shared__ __align__(16) int2 s_bvh[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,11 +189,13 @@ __global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
     // relativeTransform (geometry-inl.h:433-434)
     M3<S> R;
     V3<S> t;
+    Pose<S> tf2w;  // SimplexIntersect hands tf2 to trianglePairIntersect as the contact frame (shape_pair_intersect-inl.h:266)
     {
       const Pose<S> tf1 = loadPose(static_cast<const S*>(a.poses1), q);
       const Pose<S> tf2 = loadPose(static_cast<const S*>(a.poses2), q);
       R = mulMtM(tf1.R, tf2.R);
       t = mulMtV(tf1.R, tf2.t - tf1.t);
+      tf2w = tf2;
     }
     uint32_t count = 0;
     int first_a = -1, first_b = -1;
@@ -192,6 +256,9 @@ __global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
         const int batch = nleaf < 32 ? nleaf : 32;
         bool hit = false;
         int2 lp = make_int2(-1, -1);
+        int pen_nc = 0;
+        S pen_depth = S(0);
+        V3<S> pen_normal = zero3<S>(), pen_p0 = zero3<S>(), pen_p1 = zero3<S>();
         if (lane < batch) {
           lp = leafq[nleaf - 1 - lane];
           V3<S> P[3], Q[3];
@@ -199,6 +266,18 @@ __global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
           loadTri(tris2, lp.y, Q);
           st_leaf++;
           hit = triTriIntersect(P, Q, R, t);
+          if (PEN && hit) {
+            // trianglePairIntersect with penetration (shape_pair_intersect-inl.h:201-252): <= 2 contacts per pair
+            V3<S> pts[2];
+            S depth;
+            V3<S> normal;
+            const unsigned nc = triTriContacts(P, Q, R, t, pts, depth, normal);
+            pen_nc = int(nc);
+            pen_depth = depth;
+            pen_normal = mulMV(tf2w.R, normal);
+            pen_p0 = nc > 0 ? apply(tf2w, pts[0]) : zero3<S>();
+            pen_p1 = nc > 1 ? apply(tf2w, pts[1]) : zero3<S>();
+          }
         }
         nleaf -= batch;
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
@@ -208,7 +287,34 @@ __global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
             first_a = __shfl_sync(0xffffffffu, lp.x, src);
             first_b = __shfl_sync(0xffffffffu, lp.y, src);
           }
-          count += uint32_t(__popc(hm));
+          if (PEN) {
+            int off = hit ? pen_nc : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int v = __shfl_up_sync(0xffffffffu, off, o);
+              if (lane >= o) off += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, off, 31);
+            off -= hit ? pen_nc : 0;
+            if (hit && a.out_ids) {
+              for (int k = 0; k < pen_nc; k++) {
+                const uint32_t slot = count + uint32_t(off + k);
+                if (slot < a.max_keep && slot < a.max_contacts) {
+                  const size_t r = q * a.max_keep + slot;
+                  a.out_ids[2 * r] = lp.x;
+                  a.out_ids[2 * r + 1] = lp.y;
+                  S* o7 = static_cast<S*>(a.out_contacts) + r * 7;
+                  const V3<S> pp = k == 0 ? pen_p0 : pen_p1;
+                  o7[0] = pen_normal.x; o7[1] = pen_normal.y; o7[2] = pen_normal.z;
+                  o7[3] = pp.x; o7[4] = pp.y; o7[5] = pp.z;
+                  o7[6] = pen_depth;
+                }
+              }
+            }
+            count += uint32_t(total);
+          } else {
+            count += uint32_t(__popc(hm));
+          }
           if (count >= a.max_contacts) {
             count = a.max_contacts;
             done = true;
@@ -244,7 +350,8 @@ static unsigned long long g_last_stats[2] = {0, 0};
 
 template <typename S>
 static int bvhCollideDev(Engine& e, const BvhDev* m1, const BvhDev* m2, const void* poses1, const void* poses2, size_t n,
-                         uint32_t max_contacts, uint32_t* counts, int32_t* first_pair) {
+                         uint32_t max_contacts, uint32_t* counts, int32_t* first_pair, bool pen = false, uint32_t max_keep = 0,
+                         int32_t* out_ids = nullptr, void* out_contacts = nullptr) {
   if (!g_bvh_counters) FCLB_CUDA(cudaMalloc(&g_bvh_counters, 4 * sizeof(unsigned long long)));
   FCLB_CUDA(cudaMemsetAsync(g_bvh_counters, 0, 4 * sizeof(unsigned long long), e.compute));
   BvhArgs a{};
@@ -260,14 +367,22 @@ static int bvhCollideDev(Engine& e, const BvhDev* m1, const BvhDev* m2, const vo
   a.first_pair = first_pair;
   a.work_counter = g_bvh_counters;
   a.stats = g_bvh_counters + 1;
+  a.max_keep = max_keep;
+  a.out_ids = out_ids;
+  a.out_contacts = out_contacts;
   const size_t need = (n + kBvhWarps - 1) / kBvhWarps;
   const size_t cap = size_t(e.sms) * 3;
   const int grid = int(need < cap ? need : cap);
   FCLB_CUDA(cudaEventRecord(e.ev_call0, e.compute));
   FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
   const size_t smem = size_t(kBvhWarps) * (kStackCap + kLeafCap) * sizeof(int2);
-  FCLB_CUDA(cudaFuncSetAttribute(bvhCollideKernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  bvhCollideKernel<S><<<grid, kBvhWarps * 32, smem, e.compute>>>(a);
+  if (pen) {
+    FCLB_CUDA(cudaFuncSetAttribute(bvhCollideKernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    bvhCollideKernel<S, true><<<grid, kBvhWarps * 32, smem, e.compute>>>(a);
+  } else {
+    FCLB_CUDA(cudaFuncSetAttribute(bvhCollideKernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    bvhCollideKernel<S, false><<<grid, kBvhWarps * 32, smem, e.compute>>>(a);
+  }
   FCLB_CUDA(cudaGetLastError());
   FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
   e.launches += 1;
@@ -475,6 +590,64 @@ int fclb_bvh_collide_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* 
   if (rc) return rc;
   FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
   if (out_first_pair) FCLB_CUDA(cudaMemcpyAsync(out_first_pair, base + o_fp, n * 8, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+int fclb_bvh_collide_contacts_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+                                        int scalar_type, const fclb_request* req, uint32_t max_keep, uint32_t* out_counts,
+                                        int32_t* out_ids, void* out_contacts) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto i1 = bvhTable().find(bvh1), i2 = bvhTable().find(bvh2);
+  if (i1 == bvhTable().end() || i2 == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown BVH handle");
+  if (i1->second->scalar_type != scalar_type || i2->second->scalar_type != scalar_type)
+    return fail(FCLB_ERR_BAD_ARG, "BVH was uploaded for a different scalar type");
+  if (!req || !out_counts || !out_ids || !out_contacts || max_keep == 0) return fail(FCLB_ERR_BAD_ARG, "null output / max_keep == 0");
+  if (req->penetration_mode != FCLB_PEN_DEFAULT_GJK_EPA)
+    return fail(FCLB_ERR_UNSUPPORTED, "fclb_bvh_collide_contacts_batch serves request.useDefaultPenetration()");
+  if (n == 0) return FCLB_OK;
+  if (!poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null pose array");
+  if (scalar_type == FCLB_F32)
+    return bvhCollideDev<float>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts, nullptr, true,
+                                max_keep, out_ids, out_contacts);
+  return bvhCollideDev<double>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts, nullptr, true,
+                               max_keep, out_ids, out_contacts);
+}
+
+int fclb_bvh_collide_contacts_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+                                         int scalar_type, const fclb_request* req, uint32_t max_keep, uint32_t* out_counts,
+                                         int32_t* out_ids, void* out_contacts) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!poses1 || !poses2 || !out_counts || !out_ids || !out_contacts || max_keep == 0) return fail(FCLB_ERR_BAD_ARG, "null array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t o_p1 = 0;
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_ids = alignUp(o_cnt + n * 4, 256);
+  const size_t o_ct = alignUp(o_ids + n * size_t(max_keep) * 8, 256);
+  const size_t total = alignUp(o_ct + n * size_t(max_keep) * 7 * ss, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemsetAsync(base + o_ids, 0xff, n * size_t(max_keep) * 8, e.compute));
+  FCLB_CUDA(cudaMemsetAsync(base + o_ct, 0, n * size_t(max_keep) * 7 * ss, e.compute));
+  rc = fclb_bvh_collide_contacts_batch_dev(bvh1, bvh2, base + o_p1, base + o_p2, n, scalar_type, req, max_keep,
+                                           reinterpret_cast<uint32_t*>(base + o_cnt), reinterpret_cast<int32_t*>(base + o_ids),
+                                           base + o_ct);
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(out_ids, base + o_ids, n * size_t(max_keep) * 8, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(out_contacts, base + o_ct, n * size_t(max_keep) * 7 * ss, cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }

@@ -30,6 +30,7 @@ EXPORTS = [
     "fclb_collide_batch_host", "fclb_collide_batch_dev",
     "fclb_gjk_epa_batch_host", "fclb_gjk_epa_batch_dev",
     "fclb_bvh_upload", "fclb_bvh_release", "fclb_bvh_collide_batch_host", "fclb_bvh_collide_batch_dev",
+    "fclb_bvh_collide_contacts_batch_host", "fclb_bvh_collide_contacts_batch_dev",
     "fclb_bvh_last_visit_counts", "fclb_bvh_build", "fclb_bvh_build_host", "fclb_bvh_info", "fclb_bvh_export",
     "fclb_bvh_shape_collide_batch_host", "fclb_bvh_shape_collide_batch_dev", "fclb_scene_last_visit_counts",
     "fclb_heightmap_upload", "fclb_heightmap_release", "fclb_heightmap_build_host",
@@ -177,6 +178,10 @@ def load() -> C.CDLL:
         sc2 = [C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, u32, vp, vp, vp]
         lib.fclb_scene_shape_contacts_batch_host.argtypes = sc2
         lib.fclb_scene_shape_contacts_batch_dev.argtypes = sc2
+    if hasattr(lib, "fclb_bvh_collide_contacts_batch_host"):
+        bc_args = [C.c_uint64, C.c_uint64, vp, vp, sz, C.c_int, vp, u32, vp, vp, vp]
+        lib.fclb_bvh_collide_contacts_batch_host.argtypes = bc_args
+        lib.fclb_bvh_collide_contacts_batch_dev.argtypes = bc_args
     _lib = lib
     return lib
 
@@ -570,3 +575,15 @@ def measure_fp_peak(scalar_type) -> float:
     v = C.c_double()
     check(load().fclb_measure_fp_peak(scalar_type, C.byref(v)))
     return v.value
+
+
+def bvh_collide_contacts_batch_host(bvh1, bvh2, poses1, poses2, scalar_type, request: Request, max_keep):
+    """fcl::collide(BVH, BVH) with request.useDefaultPenetration(): (counts, ids [n,k,2], contacts [n,k,7])."""
+    n = len(poses1)
+    counts = np.zeros(n, np.uint32)
+    ids = np.zeros((n, max_keep, 2), np.int32)
+    contacts = np.zeros((n, max_keep, 7), np_dtype(scalar_type))
+    check(load().fclb_bvh_collide_contacts_batch_host(bvh1, bvh2, _ptr(poses1), _ptr(poses2), n, scalar_type,
+                                                      C.cast(C.pointer(request), C.c_void_p), max_keep, _ptr(counts),
+                                                      _ptr(ids), _ptr(contacts)))
+    return counts, ids, contacts

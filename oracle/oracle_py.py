@@ -185,6 +185,19 @@ class RefOracle(_Oracle):
           _p(pair), threads)
         return counts, pair
 
+    def bvh_collide_contacts_batch(self, id1, id2, poses1, poses2, max_keep, threads=1, **req):
+        n = len(poses1)
+        counts = np.zeros(n, np.uint32)
+        ids = np.zeros((n, max_keep, 2), np.int32)
+        contacts = np.zeros((n, max_keep, 7), poses1.dtype)
+        r = _request(**req)
+        f = self.fn("bvh_collide_contacts_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p,
+                      C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(poses1.dtype), id1, id2, _p(poses1), _p(poses2), n, C.cast(C.pointer(r), C.c_void_p), max_keep, _p(counts),
+          _p(ids), _p(contacts), threads)
+        return counts, ids, contacts
+
     def bvh_visit_counts(self, id1, id2, poses1, poses2, threads=1):
         n = len(poses1)
         n_bv = np.zeros(n, np.uint64)

@@ -136,6 +136,40 @@ void collideBatch(int id1, int id2, const S* poses1, const S* poses2, size_t n, 
   });
 }
 
+// every contact of fcl::collide(BVH, BVH) with contact generation: ids (b1, b2) + {normal, pos, depth}
+template <typename S>
+void collideContactsBatch(int id1, int id2, const S* poses1, const S* poses2, size_t n, const RequestRec* rq,
+                          uint32_t max_keep, uint32_t* counts, int32_t* ids, S* contacts, int threads) {
+  const Model<S>* m1 = get<S>(id1);
+  const Model<S>* m2 = get<S>(id2);
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    fcl::CollisionRequest<S> req(rq->max_contacts);
+    req.useDefaultPenetration();
+    for (size_t q = b; q < e; q++) {
+      fcl::CollisionResult<S> res;
+      const size_t c = fcl::collide<S>(m1, loadPose<S>(poses1 + 12 * q), m2, loadPose<S>(poses2 + 12 * q), req, res);
+      counts[q] = uint32_t(c);
+      for (uint32_t k = 0; k < max_keep; k++) {
+        int32_t* id = ids + (q * max_keep + k) * 2;
+        S* o = contacts + (q * max_keep + k) * 7;
+        if (k < c) {
+          const auto& ct = res.getContact(k);
+          id[0] = int32_t(ct.b1);
+          id[1] = int32_t(ct.b2);
+          for (int j = 0; j < 3; j++) {
+            o[j] = ct.normal[j];
+            o[3 + j] = ct.pos[j];
+          }
+          o[6] = ct.penetration_depth;
+        } else {
+          id[0] = id[1] = -1;
+          for (int j = 0; j < 7; j++) o[j] = S(0);
+        }
+      }
+    }
+  });
+}
+
 // Instrumented replica of MeshIntersect's loop (bvh_solver-inl.h:90-160) in
 // all-contacts, no-penetration mode: counts BV-pair tests and leaf-pair tests.
 template <typename S>
@@ -212,6 +246,17 @@ int fclref_bvh_collide_batch(int scalar_type, int id1, int id2, const void* pose
   else
     collideBatch<double>(id1, id2, (const double*)poses1, (const double*)poses2, n, (const RequestRec*)request, counts,
                          first_pair, threads);
+  return 0;
+}
+int fclref_bvh_collide_contacts_batch(int scalar_type, int id1, int id2, const void* poses1, const void* poses2, size_t n,
+                                      const void* request, uint32_t max_keep, uint32_t* counts, int32_t* ids, void* contacts,
+                                      int threads) {
+  if (scalar_type == 0)
+    collideContactsBatch<float>(id1, id2, (const float*)poses1, (const float*)poses2, n, (const RequestRec*)request, max_keep,
+                                counts, ids, (float*)contacts, threads);
+  else
+    collideContactsBatch<double>(id1, id2, (const double*)poses1, (const double*)poses2, n, (const RequestRec*)request,
+                                 max_keep, counts, ids, (double*)contacts, threads);
   return 0;
 }
 int fclref_bvh_visit_counts(int scalar_type, int id1, int id2, const void* poses1, const void* poses2, size_t n,
