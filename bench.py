@@ -535,9 +535,9 @@ def run_reference(args, rank, world):
     oracle = load_oracle()
     threads = getattr(wl, "cpu_threads", os.cpu_count() or 1)
     fn = wl.cpu_run(oracle, threads)
-    m = wl.cpu_sample() if hasattr(wl, "cpu_sample") else wl.n
     for _ in range(args.warmup):
         fn()
+    m = wl.cpu_sample() if hasattr(wl, "cpu_sample") else wl.n  # (C5 learns its candidate count from a run)
     t = time.perf_counter()
     for _ in range(args.steps):
         fn()
@@ -710,13 +710,13 @@ def main():
             oracle = load_oracle()
             threads = getattr(wl, "cpu_threads", os.cpu_count() or 1)
             fn = wl.cpu_run(oracle, threads)
-            m = wl.cpu_sample() if hasattr(wl, "cpu_sample") else n
             best = None
             for _ in range(3):
                 t = time.perf_counter()
                 fn()
                 dt = time.perf_counter() - t
                 best = dt if best is None else min(best, dt)
+            m = wl.cpu_sample() if hasattr(wl, "cpu_sample") else n
             line["cpu_baseline"] = {"value": m / best, "unit": UNIT, "cores": threads, "kind": oracle.kind,
                                     "sample": f"{m} of the step's {n} queries, best of 3 ({best:.2f} s each)"}
         except Exception as ex:  # the CPU leg is a reported baseline, never the product path
