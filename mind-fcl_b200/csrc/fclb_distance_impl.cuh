@@ -6,6 +6,8 @@
 // (2 poses in, dist + 2 witness points + flag out); GJK pairs are FP-bound and
 // use the shared-memory simplex store of fclb_gjk.cuh.
 #pragma once
+#include <cstdlib>
+
 #include "fclb_gjk.cuh"
 #include "fclb_internal.h"
 #include "fclb_primitives.cuh"
@@ -307,6 +309,314 @@ __global__ void __launch_bounds__(kBlock, FCLB_GJK_MIN_BLOCKS) distanceGjkKernel
   }
 }
 
+// ---- GJK bucket, phase-binned scheduling -------------------------------------------
+// The state machine above keeps one query per lane, so the lanes of a warp sit in five different
+// phases (ncu: 5 of 32 lanes active per issued instruction).  Here a warp owns a POOL of query slots in
+// shared memory (simplex store, direction, closest point, Minkowski-difference transforms, phase) and in
+// every trip it picks the phase most of its slots are in, hands one such slot to each lane, and runs
+// the support + update of THAT phase only: the per-trip control flow is warp-uniform, what is left is
+// the divergence inside an update (simplex rank).  Queries are fetched in contiguous ranges from an
+// atomic cursor, so the pose reads are coalesced.  Per-query arithmetic and decisions are those of
+// the kernel above (same helpers), only the order in which queries advance differs.
+template <typename S>
+struct BinPool {
+  static constexpr int kSlots = sizeof(S) == 4 ? 64 : 48;  // query slots per warp
+  static constexpr int kWordsS = 24 + 16 + 21;             // simplex | d cur book p0 p1 w | toshape1 toshape0
+  static constexpr int kWordsU = 8;                        // q phase ord rankit plan pslots pair1 pair2
+  static constexpr size_t bytesPerWarp() { return size_t(kSlots) * (kWordsS * sizeof(S) + kWordsU * 4); }
+};
+
+template <typename S, int T0, int T1>
+__global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S tol, int max_iter, DistanceOut out,
+                                                                  unsigned long long* cursor) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NS = BinPool<S>::kSlots;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* wbase = smem_raw + size_t(warp) * BinPool<S>::bytesPerWarp();
+  S* fS = reinterpret_cast<S*>(wbase);                                        // [kWordsS][NS]
+  uint32_t* fU = reinterpret_cast<uint32_t*>(wbase + size_t(NS) * BinPool<S>::kWordsS * sizeof(S));  // [kWordsU][NS]
+  const ShapeD<S>* __restrict__ shapes = static_cast<const ShapeD<S>*>(b.shapes);
+  const ConvexD<S>* __restrict__ cvx = static_cast<const ConvexD<S>*>(b.convex);
+  const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
+  const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
+  const S tol_sq = tol * tol;
+  enum { U_Q = 0, U_PHASE, U_ORD, U_RANKIT, U_PLAN, U_PSLOTS, U_PAIR1, U_PAIR2 };
+  enum { F_D = 24, F_CUR = 27, F_BOOK = 30, F_P0 = 31, F_P1 = 34, F_W = 37, F_TS1 = 40, F_TS0R = 49, F_TS0T = 58 };
+  auto ldS = [&](int f, int slot) { return fS[f * NS + slot]; };
+  auto stS = [&](int f, int slot, S v) { fS[f * NS + slot] = v; };
+  auto ld3 = [&](int f, int slot) { return mk<S>(fS[f * NS + slot], fS[(f + 1) * NS + slot], fS[(f + 2) * NS + slot]); };
+  auto st3 = [&](int f, int slot, const V3<S>& v) {
+    fS[f * NS + slot] = v.x;
+    fS[(f + 1) * NS + slot] = v.y;
+    fS[(f + 2) * NS + slot] = v.z;
+  };
+  for (int k = lane; k < NS; k += 32) fU[U_PHASE * NS + k] = PH_FETCH;
+  __syncwarp();
+  bool more = true;  // queries left behind the cursor
+
+  while (true) {
+    // ---- census of the pool: which phase do most slots wait in?
+    unsigned masks[5][(NS + 31) / 32];
+    int cnt[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < (NS + 31) / 32; w++) {
+      const int k = w * 32 + lane;
+      const int ph = k < NS ? int(fU[U_PHASE * NS + k]) : -1;
+#pragma unroll
+      for (int p = 0; p < 5; p++) {
+        masks[p][w] = __ballot_sync(0xffffffffu, ph == p);
+        cnt[p] += __popc(masks[p][w]);
+      }
+    }
+    int best = -1, best_n = 0;
+#pragma unroll
+    for (int p = 4; p >= 0; p--) {  // ties go to the later phase (drains the pool)
+      if (p == PH_FETCH && !more) continue;
+      if (cnt[p] > best_n) {
+        best_n = cnt[p];
+        best = p;
+      }
+    }
+    if (best < 0) break;  // pool empty and nothing left to fetch
+    // ---- hand one slot of that phase to each lane
+    int slot = -1;
+    {
+      int want = lane;
+#pragma unroll
+      for (int w = 0; w < (NS + 31) / 32; w++) {
+        const int c = __popc(masks[best][w]);
+        if (slot < 0 && want >= 0 && want < c) slot = w * 32 + int(__fns(masks[best][w], 0, want + 1));
+        want -= c;
+      }
+    }
+    int n_act = best_n < 32 ? best_n : 32;
+
+    if (best == PH_FETCH) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(cursor, (unsigned long long)n_act);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + n_act >= b.count) more = false;
+      if (slot >= 0 && lane < n_act && base + lane < b.count) {
+        const size_t i = size_t(base) + lane;
+        const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
+        const fclb_pair pr = b.pairs[q];
+        MinkDiff<S, T0, T1> md;
+        md.setPoses(loadPose(poses1, q), loadPose(poses2, q));
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          stS(F_TS1 + k, slot, md.toshape1.m[k]);
+          stS(F_TS0R + k, slot, md.toshape0.R.m[k]);
+        }
+        st3(F_TS0T, slot, md.toshape0.t);
+        st3(F_D, slot, normalized(mk<S>(S(-1), S(0), S(0))));  // Evaluate(-guess), guess = (1,0,0)
+        fU[U_Q * NS + slot] = uint32_t(q);
+        fU[U_PAIR1 * NS + slot] = pr.shape1;
+        fU[U_PAIR2 * NS + slot] = pr.shape2;
+        fU[U_ORD * NS + slot] = 0;
+        fU[U_RANKIT * NS + slot] = 0;  // rank + 1 = 0 (rank -1), it = 0
+        fU[U_PHASE * NS + slot] = PH_BOOL_FIRST;
+      }
+      __syncwarp();
+      continue;
+    }
+
+    if (slot >= 0 && lane < n_act) {
+      // ---- load the slot
+      SlotStore<S> st;
+      st.base = fS + slot;
+      st.stride = NS;
+      MinkDiff<S, T0, T1> md;
+      md.s0 = bindShape(shapes, cvx, fU[U_PAIR1 * NS + slot]);
+      md.s1 = bindShape(shapes, cvx, fU[U_PAIR2 * NS + slot]);
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        md.toshape1.m[k] = ldS(F_TS1 + k, slot);
+        md.toshape0.R.m[k] = ldS(F_TS0R + k, slot);
+      }
+      md.toshape0.t = ld3(F_TS0T, slot);
+      V3<S> d = ld3(F_D, slot);
+      Simp simplex;
+      simplex.ord = fU[U_ORD * NS + slot];
+      const uint32_t rankit = fU[U_RANKIT * NS + slot];
+      simplex.rank = int(rankit & 0xffu) - 1;
+      int it = int(rankit >> 8);
+      int phase = best;
+
+      // ---- the single support site
+      const V3<S> s0 = md.support0(d);
+      const V3<S> s1 = md.support1(-d);
+
+      bool done = false, separated = false, valid = false, begin_extract = false;
+      V3<S> p0 = zero3<S>(), p1 = zero3<S>();
+      V3<S> cur = zero3<S>();
+      S book = S(0);
+
+      if (best == PH_EXTRACT) {
+        const uint32_t pl = fU[U_PLAN * NS + slot];
+        const int plan_n = int(pl & 0xfu);
+        const bool weighted = (pl >> 4) & 1u, pvalid = (pl >> 5) & 1u;
+        int ex_k = int(pl >> 8);
+        const uint32_t pslots = fU[U_PSLOTS * NS + slot];
+        if (!weighted) {
+          p0 = s0;
+          p1 = s1;
+        } else {
+          const S w = ldS(F_W + ex_k, slot);
+          if (ex_k == 0) {
+            p0 = s0 * w;
+            p1 = s1 * w;
+          } else {
+            p0 = ld3(F_P0, slot) + s0 * w;
+            p1 = ld3(F_P1, slot) + s1 * w;
+          }
+        }
+        ex_k += 1;
+        if (ex_k >= plan_n) {
+          done = true;
+          separated = true;
+          valid = pvalid;
+        } else {
+          st3(F_P0, slot, p0);
+          st3(F_P1, slot, p1);
+          st3(F_D, slot, st.dir((pslots >> (8 * ex_k)) & 0xff));
+          fU[U_PLAN * NS + slot] = (pl & 0xffu) | (uint32_t(ex_k) << 8);
+        }
+      } else {
+        const V3<S> v = s0 - s1;
+        bool to_dist = false;
+        if (best == PH_BOOL_FIRST) {  // gjk.hpp:73-88
+          addVertex(st, simplex, v, d);
+          if (sqnorm(v) <= tol_sq) {
+            done = true;
+          } else if (dot(v, d) < 0) {
+            to_dist = true;
+          } else {
+            d = d * S(-1);
+            it = 0;
+            phase = PH_BOOL;
+            if (it >= max_iter) done = true;
+          }
+        } else if (best == PH_BOOL) {  // gjk.hpp:92-141
+          it += 1;
+          if (dot(v, d) < 0) {
+            to_dist = true;
+          } else {
+            bool dup = false;
+            for (int j = 0; j < simplex.rank; j++)
+              if (sqnorm(st.vtx(slotOf(simplex, j)) - v) < tol_sq) dup = true;
+            if (dup || sqnorm(v) <= tol_sq) {
+              done = true;
+            } else {
+              addVertex(st, simplex, v, d);
+              const int ps = simplexProjection(st, simplex, d, tol);
+              if (ps != PROJ_CONTINUE || it >= max_iter) done = true;
+            }
+          }
+        } else {  // PH_DIST: gjk_distance.hpp:48-101
+          cur = ld3(F_CUR, slot);
+          book = ldS(F_BOOK, slot);
+          it += 1;
+          const S delta = dot(d, v - cur);
+          bool stop = delta < tol;
+          if (!stop) {
+            for (int j = 0; j < simplex.rank; j++)
+              if (sqnorm(st.vtx(slotOf(simplex, j)) - v) < tol_sq) stop = true;
+          }
+          if (stop) {
+            begin_extract = true;
+          } else {
+            addVertex(st, simplex, v, d);
+            const int us = minDistUpdate(st, simplex, cur, tol);
+            if (us == 0) {
+              begin_extract = true;
+            } else if (us == 1) {
+              const S nd = norm(cur);
+              const S improvement = book - nd;
+              if (improvement < tol || nd < tol) {
+                begin_extract = true;
+              } else {
+                book = nd;
+                d = (-cur) / book;
+                if (it >= max_iter) {
+                  done = true;
+                  separated = true;
+                  valid = false;
+                }
+              }
+            } else {
+              done = true;
+              separated = true;
+              valid = false;
+            }
+          }
+        }
+        if (to_dist) {  // process_separated_vertex (gjk.hpp:22-52) + distance prologue (gjk_distance.hpp:14-46)
+          simplex.rank = -1;
+          simplex.ord = 0;
+          addVertex(st, simplex, v, d);
+          cur = v;
+          book = norm(cur);
+          if (book <= tol) {
+            begin_extract = true;
+          } else {
+            d = (-cur) / book;
+            it = 0;
+            phase = PH_DIST;
+            if (it >= max_iter) {
+              done = true;
+              separated = true;
+              valid = false;
+            }
+          }
+        }
+        if (begin_extract) {
+          const ExtractPlan<S> plan = planExtraction(st, simplex);
+          if (plan.n == 0) {
+            done = true;
+            separated = true;
+            valid = false;
+          } else {
+            d = st.dir(plan.slots & 0xff);
+            phase = PH_EXTRACT;
+            fU[U_PLAN * NS + slot] = uint32_t(plan.n) | (plan.weighted ? 16u : 0u) | (plan.valid ? 32u : 0u);
+            fU[U_PSLOTS * NS + slot] = plan.slots;
+            stS(F_W, slot, plan.w0);
+            stS(F_W + 1, slot, plan.w1);
+            stS(F_W + 2, slot, plan.w2);
+          }
+        }
+        if (!done) {
+          st3(F_D, slot, d);
+          if (phase == PH_DIST) {
+            st3(F_CUR, slot, cur);
+            stS(F_BOOK, slot, book);
+          }
+          fU[U_ORD * NS + slot] = simplex.ord;
+          fU[U_RANKIT * NS + slot] = uint32_t(simplex.rank + 1) | (uint32_t(it) << 8);
+          fU[U_PHASE * NS + slot] = uint32_t(phase);
+        }
+      }
+
+      if (done) {
+        const size_t q = fU[U_Q * NS + slot];
+        S dist = S(-1);
+        V3<S> w1 = zero3<S>(), w2 = zero3<S>();
+        uint8_t ok = 0;
+        if (separated) {  // (p0, p1 stay zero on the paths where the reference returns without witness points)
+          const Pose<S> tf1 = loadPose(poses1, q);
+          dist = norm(p0 - p1);
+          w1 = apply(tf1, p0);
+          w2 = apply(tf1, p1);
+          ok = valid ? uint8_t(1) : uint8_t(3);
+        }
+        writeDistance(out, q, dist, w1, w2, ok);
+        fU[U_PHASE * NS + slot] = PH_FETCH;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 inline int gridFor(size_t count, int block, int ctas_per_sm) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -316,8 +626,36 @@ inline int gridFor(size_t count, int block, int ctas_per_sm) {
   return int(need < cap ? (need ? need : 1) : cap);
 }
 
+// FCLB_GJK_BINNED=0 selects the one-query-per-lane state machine (kept for comparison)
+inline bool gjkBinnedEnabled() {
+  static int v = [] {
+    const char* e = getenv("FCLB_GJK_BINNED");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+unsigned long long* gjkCursor();  // device counter (fclb_engine.cu)
+
 template <typename S, int T0, int T1>
 cudaError_t launchGjkDistance(const BatchView& b, const SolverParams& sp, const DistanceOut& out, cudaStream_t st) {
+  if (gjkBinnedEnabled()) {
+    unsigned long long* cursor = gjkCursor();
+    if (!cursor) return cudaErrorMemoryAllocation;
+    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    const size_t smem = BinPool<S>::bytesPerWarp() * (kBlock / 32);
+    auto kern = distanceGjkBinnedKernel<S, T0, T1>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    int per_sm = int((227 * 1024) / (smem + 1024));
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    const size_t need = (b.count + BinPool<S>::kSlots * (kBlock / 32) - 1) / (BinPool<S>::kSlots * (kBlock / 32));
+    int grid = gridFor(b.count, kBlock, per_sm);
+    if (size_t(grid) > need) grid = int(need ? need : 1);
+    kern<<<grid, kBlock, smem, st>>>(b, S(sp.gjk_tol), sp.gjk_max_iter, out, cursor);
+    return cudaGetLastError();
+  }
   const size_t smem = size_t(24) * sizeof(S) * kBlock;
   const int grid = gridFor(b.count, kBlock, 16);
   distanceGjkKernel<S, T0, T1><<<grid, kBlock, smem, st>>>(b, S(sp.gjk_tol), sp.gjk_max_iter, out);

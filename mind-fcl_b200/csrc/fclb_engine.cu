@@ -332,6 +332,12 @@ int ensureChunkEvents(Engine& e, int n) {
   return FCLB_OK;
 }
 
+unsigned long long* gjkCursor() {
+  static unsigned long long* d = nullptr;
+  if (!d && cudaMalloc(&d, sizeof(unsigned long long)) != cudaSuccess) d = nullptr;
+  return d;
+}
+
 int ensureStage(Engine& e, size_t bytes) {
   if (bytes <= e.stage_cap) return FCLB_OK;
   if (e.d_stage) cudaFree(e.d_stage);
