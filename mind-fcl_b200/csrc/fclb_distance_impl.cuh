@@ -320,8 +320,17 @@ __global__ void __launch_bounds__(kBlock, FCLB_GJK_MIN_BLOCKS) distanceGjkKernel
 // the kernel above (same helpers), only the order in which queries advance differs.
 template <typename S>
 struct BinPool {
-  static constexpr int kSlots = sizeof(S) == 4 ? 64 : 48;  // query slots per warp
-  static constexpr int kWordsS = 24 + 16 + 21;             // simplex | d cur book p0 p1 w | toshape1 toshape0
+  // query slots per warp.  Measured on C2 (B200, capsule/cylinder-box kernels, ms per 3.3M queries):
+  //   f32: 96 slots 3.6 | 80: 2.95 | 64: 2.70 | 60: 2.54 | 48: 2.70 | 40: 2.93   (60 slots = 53.8 KB per CTA = 4 CTAs per SM)
+  //   f64: 48 slots 8.5 | 36: 8.2 | 30: 7.6
+  // -- a fuller pool fills the chosen bin better, a smaller one buys occupancy; occupancy wins beyond ~60.
+#ifndef FCLB_GJK_SLOTS
+#define FCLB_GJK_SLOTS 60
+#endif
+  static constexpr int kSlots = sizeof(S) == 4 ? FCLB_GJK_SLOTS : FCLB_GJK_SLOTS / 2;
+  // simplex 24 | d 3 | {cur 3, book 1} aliased with {p0 3, p1 3, w 3} (distance loop vs witness extraction) 9 |
+  // toshape0 12 (toshape1 = transpose(toshape0.R) bit for bit: same products, same summation order)
+  static constexpr int kWordsS = 24 + 3 + 9 + 12;
   static constexpr int kWordsU = 8;                        // q phase ord rankit plan pslots pair1 pair2
   static constexpr size_t bytesPerWarp() { return size_t(kSlots) * (kWordsS * sizeof(S) + kWordsU * 4); }
 };
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
   const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
   const S tol_sq = tol * tol;
   enum { U_Q = 0, U_PHASE, U_ORD, U_RANKIT, U_PLAN, U_PSLOTS, U_PAIR1, U_PAIR2 };
-  enum { F_D = 24, F_CUR = 27, F_BOOK = 30, F_P0 = 31, F_P1 = 34, F_W = 37, F_TS1 = 40, F_TS0R = 49, F_TS0T = 58 };
+  enum { F_D = 24, F_CUR = 27, F_BOOK = 30, F_P0 = 27, F_P1 = 30, F_W = 33, F_TS0R = 36, F_TS0T = 45 };
   auto ldS = [&](int f, int slot) { return fS[f * NS + slot]; };
   auto stS = [&](int f, int slot, S v) { fS[f * NS + slot] = v; };
   auto ld3 = [&](int f, int slot) { return mk<S>(fS[f * NS + slot], fS[(f + 1) * NS + slot], fS[(f + 2) * NS + slot]); };
@@ -350,42 +359,60 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
     fS[(f + 1) * NS + slot] = v.y;
     fS[(f + 2) * NS + slot] = v.z;
   };
-  for (int k = lane; k < NS; k += 32) fU[U_PHASE * NS + k] = PH_FETCH;
+  // scheduling bins: the phase, and for the two iterating phases also the simplex rank the update starts
+  // from (the projection / sub-simplex search of rank 2, 3 and 4 simplices are three different codes)
+  // (measured: with 64 slots per warp the nine bins fill too thinly -- 3.6 ms against 2.7 ms for phase-only
+  // bins on C2 -- so the rank split is compiled out; the census below skips the unused bins)
+  constexpr bool kRankBins = false;
+  constexpr int kBins = 9;  // 0 FETCH, 1 BOOL_FIRST, 2..4 BOOL rank 1..3, 5..7 DIST rank 1..3, 8 EXTRACT
+  auto binOf = [](int phase, int rank) {
+    const int r = !kRankBins ? 1 : (rank < 1 ? 1 : (rank > 3 ? 3 : rank));  // (the phase must survive whatever the rank is)
+    return phase == PH_BOOL ? 1 + r : (phase == PH_DIST ? 4 + r : (phase == PH_EXTRACT ? 8 : phase));
+  };
+  for (int k = lane; k < NS; k += 32) fU[U_PHASE * NS + k] = 0;
   __syncwarp();
   bool more = true;  // queries left behind the cursor
 
   while (true) {
-    // ---- census of the pool: which phase do most slots wait in?
-    unsigned masks[5][(NS + 31) / 32];
-    int cnt[5] = {0, 0, 0, 0, 0};
+    // ---- census of the pool: which bin do most slots wait in?
+    unsigned masks[kBins][(NS + 31) / 32];
+    int cnt[kBins];
+#pragma unroll
+    for (int p = 0; p < kBins; p++) cnt[p] = 0;
 #pragma unroll
     for (int w = 0; w < (NS + 31) / 32; w++) {
       const int k = w * 32 + lane;
       const int ph = k < NS ? int(fU[U_PHASE * NS + k]) : -1;
 #pragma unroll
-      for (int p = 0; p < 5; p++) {
+      for (int p = 0; p < kBins; p++) {
+        if (!kRankBins && (p == 3 || p == 4 || p == 6 || p == 7)) {
+          masks[p][w] = 0;
+          continue;
+        }
         masks[p][w] = __ballot_sync(0xffffffffu, ph == p);
         cnt[p] += __popc(masks[p][w]);
       }
     }
-    int best = -1, best_n = 0;
+    int best_bin = -1, best_n = 0;
 #pragma unroll
-    for (int p = 4; p >= 0; p--) {  // ties go to the later phase (drains the pool)
-      if (p == PH_FETCH && !more) continue;
+    for (int p = kBins - 1; p >= 0; p--) {  // ties go to the later bin (drains the pool)
+      if (p == 0 && !more) continue;
       if (cnt[p] > best_n) {
         best_n = cnt[p];
-        best = p;
+        best_bin = p;
       }
     }
-    if (best < 0) break;  // pool empty and nothing left to fetch
+    if (best_bin < 0) break;  // pool empty and nothing left to fetch
+    const int best = best_bin == 0 ? PH_FETCH
+                                   : (best_bin == 1 ? PH_BOOL_FIRST : (best_bin <= 4 ? PH_BOOL : (best_bin <= 7 ? PH_DIST : PH_EXTRACT)));
     // ---- hand one slot of that phase to each lane
     int slot = -1;
     {
       int want = lane;
 #pragma unroll
       for (int w = 0; w < (NS + 31) / 32; w++) {
-        const int c = __popc(masks[best][w]);
-        if (slot < 0 && want >= 0 && want < c) slot = w * 32 + int(__fns(masks[best][w], 0, want + 1));
+        const int c = __popc(masks[best_bin][w]);
+        if (slot < 0 && want >= 0 && want < c) slot = w * 32 + int(__fns(masks[best_bin][w], 0, want + 1));
         want -= c;
       }
     }
@@ -403,10 +430,7 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
         MinkDiff<S, T0, T1> md;
         md.setPoses(loadPose(poses1, q), loadPose(poses2, q));
 #pragma unroll
-        for (int k = 0; k < 9; k++) {
-          stS(F_TS1 + k, slot, md.toshape1.m[k]);
-          stS(F_TS0R + k, slot, md.toshape0.R.m[k]);
-        }
+        for (int k = 0; k < 9; k++) stS(F_TS0R + k, slot, md.toshape0.R.m[k]);
         st3(F_TS0T, slot, md.toshape0.t);
         st3(F_D, slot, normalized(mk<S>(S(-1), S(0), S(0))));  // Evaluate(-guess), guess = (1,0,0)
         fU[U_Q * NS + slot] = uint32_t(q);
@@ -414,7 +438,7 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
         fU[U_PAIR2 * NS + slot] = pr.shape2;
         fU[U_ORD * NS + slot] = 0;
         fU[U_RANKIT * NS + slot] = 0;  // rank + 1 = 0 (rank -1), it = 0
-        fU[U_PHASE * NS + slot] = PH_BOOL_FIRST;
+        fU[U_PHASE * NS + slot] = 1;
       }
       __syncwarp();
       continue;
@@ -429,10 +453,8 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
       md.s0 = bindShape(shapes, cvx, fU[U_PAIR1 * NS + slot]);
       md.s1 = bindShape(shapes, cvx, fU[U_PAIR2 * NS + slot]);
 #pragma unroll
-      for (int k = 0; k < 9; k++) {
-        md.toshape1.m[k] = ldS(F_TS1 + k, slot);
-        md.toshape0.R.m[k] = ldS(F_TS0R + k, slot);
-      }
+      for (int k = 0; k < 9; k++) md.toshape0.R.m[k] = ldS(F_TS0R + k, slot);
+      md.toshape1 = transpose(md.toshape0.R);
       md.toshape0.t = ld3(F_TS0T, slot);
       V3<S> d = ld3(F_D, slot);
       Simp simplex;
@@ -593,7 +615,7 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
           }
           fU[U_ORD * NS + slot] = simplex.ord;
           fU[U_RANKIT * NS + slot] = uint32_t(simplex.rank + 1) | (uint32_t(it) << 8);
-          fU[U_PHASE * NS + slot] = uint32_t(phase);
+          fU[U_PHASE * NS + slot] = uint32_t(binOf(phase, simplex.rank));
         }
       }
 
@@ -610,7 +632,7 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
           ok = valid ? uint8_t(1) : uint8_t(3);
         }
         writeDistance(out, q, dist, w1, w2, ok);
-        fU[U_PHASE * NS + slot] = PH_FETCH;
+        fU[U_PHASE * NS + slot] = 0;
       }
     }
     __syncwarp();
@@ -648,7 +670,7 @@ cudaError_t launchGjkDistance(const BatchView& b, const SolverParams& sp, const 
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     int per_sm = int((227 * 1024) / (smem + 1024));
-    if (per_sm > 6) per_sm = 6;
+    if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     const size_t need = (b.count + BinPool<S>::kSlots * (kBlock / 32) - 1) / (BinPool<S>::kSlots * (kBlock / 32));
     int grid = gridFor(b.count, kBlock, per_sm);
