@@ -980,9 +980,12 @@ struct EpaWarp {
   }
 
   // evaluateFromInitializedPolytope (epa.hpp:137-237)
-  FCLB_DI int run(int max_iterations, S tol, S& depth, V3<S>& p0, V3<S>& p1) {
-    int iteration = 0;
-    while (true) {
+  // One iteration of evaluateFromInitializedPolytope's loop (epa.hpp:137-237).  Returns kEpaContinue or the
+  // final status.  Kept separate so that the tiles of a warp can take their iterations in lockstep.
+  static constexpr int kEpaContinue = -1;
+  int iteration = 0;
+  FCLB_DI int step(int max_iterations, S tol, S& depth, V3<S>& p0, V3<S>& p1) {
+    {
       Feature nf = nearest(false);
       if (nf.idx < 0) return EPA_FAILED;
       if (nf.cls == 0) {
@@ -1073,6 +1076,26 @@ struct EpaWarp {
         return EPA_ITER_LIMIT;
       }
     }
+    return kEpaContinue;
+  }
+  FCLB_DI int run(int max_iterations, S tol, S& depth, V3<S>& p0, V3<S>& p1) {
+    iteration = 0;
+    while (true) {
+      const int r = step(max_iterations, tol, depth, p0, p1);
+      if (r != kEpaContinue) return r;
+    }
+  }
+  // reset + simplexToPolytope: kEpaContinue when the iteration loop has to run
+  FCLB_DI int begin(const SlotStore<S>& st, const Simp& sx, S tol, S& depth, V3<S>& p0, V3<S>& p1) {
+    reset();
+    iteration = 0;
+    const int s2p = simplexToPolytope(st, sx, tol, p0, p1);
+    if (s2p == 2) return EPA_FAILED;
+    if (s2p == 1) {
+      depth = S(0);
+      return EPA_TOUCHING;
+    }
+    return kEpaContinue;
   }
 
   // EPA::Evaluate (epa.hpp:240-256) via evaluateFromUnInitializedPolytope (:116-135)
