@@ -388,6 +388,8 @@ __global__ void __launch_bounds__(kEpaThreads) epaKernel(BatchView b, S tol, int
     epa.sync();
   };
   while (true) {
+    int es = epa.kEpaContinue;
+    bool finished = false;
     if (!active && it < n_items) {
       w = defer.consume ? defer.item[it] : it;
       it += n_tiles;
@@ -407,21 +409,22 @@ __global__ void __launch_bounds__(kEpaThreads) epaKernel(BatchView b, S tol, int
       depth = S(0);
       p0 = zero3<S>();
       p1 = zero3<S>();
-      const int bs = epa.begin(st, sx, tol, depth, p0, p1);
-      if (bs == epa.kEpaContinue)
+      es = epa.begin(st, sx, tol, depth, p0, p1);
+      if (es == epa.kEpaContinue)
         active = true;
       else
-        finish(bs);
+        finished = true;
     }
-    if (!__any_sync(0xffffffffu, active || it < n_items)) break;
+    if (!__any_sync(0xffffffffu, active || finished || it < n_items)) break;
     __syncwarp();
     if (active) {
-      const int es = epa.step(max_iter, tol, depth, p0, p1);
+      es = epa.step(max_iter, tol, depth, p0, p1);
       if (es != epa.kEpaContinue) {
-        finish(es);
+        finished = true;
         active = false;
       }
     }
+    if (finished) finish(es);  // (one call site: the result path is ~1k SASS instructions)
   }
 }
 
