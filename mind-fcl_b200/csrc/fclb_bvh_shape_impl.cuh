@@ -80,14 +80,93 @@ FCLB_DI NodeD<S> fitObbPoints(int n, PointFn pt) {
   return bv;
 }
 
+// The same fit, warp-cooperative and bit-identical: the points are staged in shared memory (each lane
+// transforms every 32nd point), the nine covariance sums are accumulated by nine lanes, each in the
+// reference's sequential order, the Jacobi solve runs redundantly on every lane, and the extents -- pure
+// min / max, hence order-free -- are reduced across the lanes.  `pts`: 3 * n S of this warp's scratch.
+constexpr int kFitMaxPoints = 256;
+template <typename S, typename PointFn>
+FCLB_DI NodeD<S> fitObbPointsWarp(int n, PointFn pt, S* pts, int lane) {
+  for (int i = lane; i < n; i += 32) {
+    const V3<S> p = pt(i);
+    pts[3 * i] = p.x;
+    pts[3 * i + 1] = p.y;
+    pts[3 * i + 2] = p.z;
+  }
+  __syncwarp();
+  // lane k accumulates sum k: 0..2 = S1[x,y,z]; 3 = xx, 4 = yy, 5 = zz, 6 = xy, 7 = xz, 8 = yz
+  S acc = S(0);
+  if (lane < 9) {
+    const int a = lane < 3 ? lane : (lane == 3 ? 0 : (lane == 4 ? 1 : (lane == 5 ? 2 : (lane == 8 ? 1 : 0))));
+    const int b = lane == 3 ? 0 : (lane == 4 ? 1 : (lane == 5 ? 2 : (lane == 6 ? 1 : 2)));
+    if (lane < 3) {
+      for (int i = 0; i < n; i++) acc += pts[3 * i + a];
+    } else {
+      for (int i = 0; i < n; i++) acc += (pts[3 * i + a] * pts[3 * i + b]);
+    }
+  }
+  S sums[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) sums[k] = __shfl_sync(0xffffffffu, acc, k);
+  const int n_points = n;
+  S M[3][3];
+  M[0][0] = sums[3] - sums[0] * sums[0] / n_points;
+  M[1][1] = sums[4] - sums[1] * sums[1] / n_points;
+  M[2][2] = sums[5] - sums[2] * sums[2] / n_points;
+  M[0][1] = sums[6] - sums[0] * sums[1] / n_points;
+  M[1][2] = sums[8] - sums[1] * sums[2] / n_points;
+  M[0][2] = sums[7] - sums[0] * sums[2] / n_points;
+  M[1][0] = M[0][1];
+  M[2][0] = M[0][2];
+  M[2][1] = M[1][2];
+  S d[3] = {0, 0, 0}, vec[3][3];
+  if (!hostbuild::jacobi3<S>(M, d, vec)) {
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) vec[i][j] = (i == j) ? S(1) : S(0);
+  }
+  NodeD<S> bv;
+  hostbuild::axesFromEigen<S>(vec, d, bv.axis.m);
+  const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
+  V3<S> mn = mk<S>(big, big, big), mx = mk<S>(-big, -big, -big);
+  const V3<S> a0 = col(bv.axis, 0), a1 = col(bv.axis, 1), a2 = col(bv.axis, 2);
+  for (int i = lane; i < n; i += 32) {
+    const V3<S> p = mk<S>(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    const V3<S> proj = mk<S>(dot(a0, p), dot(a1, p), dot(a2, p));
+    if (proj.x > mx.x) mx.x = proj.x;
+    if (proj.x < mn.x) mn.x = proj.x;
+    if (proj.y > mx.y) mx.y = proj.y;
+    if (proj.y < mn.y) mn.y = proj.y;
+    if (proj.z > mx.z) mx.z = proj.z;
+    if (proj.z < mn.z) mn.z = proj.z;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    mx.x = fmax_(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, off));
+    mx.y = fmax_(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, off));
+    mx.z = fmax_(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, off));
+    mn.x = fmin_(mn.x, __shfl_xor_sync(0xffffffffu, mn.x, off));
+    mn.y = fmin_(mn.y, __shfl_xor_sync(0xffffffffu, mn.y, off));
+    mn.z = fmin_(mn.z, __shfl_xor_sync(0xffffffffu, mn.z, off));
+  }
+  __syncwarp();
+  const V3<S> o = mk<S>((mx.x + mn.x) / 2, (mx.y + mn.y) / 2, (mx.z + mn.z) / 2);
+  bv.To = mulMV(bv.axis, o);
+  bv.extent = mk<S>((mx.x - mn.x) * S(0.5), (mx.y - mn.y) * S(0.5), (mx.z - mn.z) * S(0.5));
+  bv.first_child = -1;
+  return bv;
+}
+
 // computeBV<OBBRSS<S>, Shape>(shape, tf, bv), OBB half
 template <typename S>
-FCLB_DI NodeD<S> shapeWorldObb(const ShapeInst<S>& sh, const BoundD<S>* __restrict__ bound, const Pose<S>& tf) {
+FCLB_DI NodeD<S> shapeWorldObb(const ShapeInst<S>& sh, const BoundD<S>* __restrict__ bound, const Pose<S>& tf, S* pts,
+                               int lane) {
   if (sh.type == ST_CONVEX) {
     const ConvexD<S>& c = *sh.cvx;
+    if (c.n_verts <= kFitMaxPoints)
+      return fitObbPointsWarp<S>(c.n_verts, [&](int i) { return apply(tf, loadVert(c.verts, i)); }, pts, lane);
     return fitObbPoints<S>(c.n_verts, [&](int i) { return apply(tf, loadVert(c.verts, i)); });
   }
-  return fitObbPoints<S>(bound->n, [&](int i) { return apply(tf, loadVert(bound->v, i)); });
+  return fitObbPointsWarp<S>(bound->n, [&](int i) { return apply(tf, loadVert(bound->v, i)); }, pts, lane);
 }
 
 // ---- sphere_triangle-inl.h:50-186 (boolean part) ----
@@ -272,6 +351,7 @@ __global__ void __launch_bounds__(kBsWarps * 32) bvhShapeCollideKernel(BvhShapeA
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* stack = s_bs + size_t(warp) * (kBsStackCap + kBsLeafCap);
   int* leafq = stack + kBsStackCap;
+  S* fit_pts = reinterpret_cast<S*>(s_bs + size_t(kBsWarps) * (kBsStackCap + kBsLeafCap)) + size_t(warp) * 3 * kFitMaxPoints;
   const S* __restrict__ nodes = static_cast<const S*>(a.nodes);
   const S* __restrict__ tris = static_cast<const S*>(a.tris);
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -293,7 +373,8 @@ __global__ void __launch_bounds__(kBsWarps * 32) bvhShapeCollideKernel(BvhShapeA
     ctx.tol = S(a.tol);
     ctx.max_iter = a.max_iter;
     // every lane fits the same OBB (uniform control flow, no shuffles needed)
-    const NodeD<S> shape_bv = shapeWorldObb(ctx.shape, static_cast<const BoundD<S>*>(a.bound) + sid, ctx.tf_shape);
+    const NodeD<S> shape_bv =
+        shapeWorldObb(ctx.shape, static_cast<const BoundD<S>*>(a.bound) + sid, ctx.tf_shape, fit_pts, lane);
 
     uint32_t count = 0;
     int first = -1;
@@ -386,11 +467,14 @@ __global__ void __launch_bounds__(kBsWarps * 32) bvhShapeCollideKernel(BvhShapeA
 
 template <typename S>
 cudaError_t launchBvhShape(int type0, const BvhShapeArgs& a, int grid, cudaStream_t st) {
-  const size_t smem = size_t(kBsWarps) * (kBsStackCap + kBsLeafCap) * sizeof(int);
+  const size_t smem = size_t(kBsWarps) * ((kBsStackCap + kBsLeafCap) * sizeof(int) + 3 * kFitMaxPoints * sizeof(S));
 #define FCLB_BS_CASE(T)                                                                                          \
-  case T:                                                                                                        \
+  case T: {                                                                                                      \
+    cudaError_t e_ = cudaFuncSetAttribute(bvhShapeCollideKernel<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); \
+    if (e_ != cudaSuccess) return e_;                                                                            \
     bvhShapeCollideKernel<S, T><<<grid, kBsWarps * 32, smem, st>>>(a);                                           \
-    break;
+    break;                                                                                                       \
+  }
   switch (type0) {
     FCLB_BS_CASE(ST_BOX)
     FCLB_BS_CASE(ST_SPHERE)
@@ -399,9 +483,12 @@ cudaError_t launchBvhShape(int type0, const BvhShapeArgs& a, int grid, cudaStrea
     FCLB_BS_CASE(ST_CONE)
     FCLB_BS_CASE(ST_CYLINDER)
     FCLB_BS_CASE(ST_CONVEX)
-    default:
+    default: {
+      cudaError_t e_ = cudaFuncSetAttribute(bvhShapeCollideKernel<S, ST_DYNAMIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e_ != cudaSuccess) return e_;
       bvhShapeCollideKernel<S, ST_DYNAMIC><<<grid, kBsWarps * 32, smem, st>>>(a);
       break;
+    }
   }
 #undef FCLB_BS_CASE
   return cudaGetLastError();
