@@ -35,6 +35,15 @@ struct Box6 {
   S mn[3], mx[3];
 };
 
+// Traversal node: both children's boxes, links and last covered leaf in ONE record (64 B in float, 128 B
+// in double), so a traversal step is one aligned fetch and tests two boxes.
+template <typename S>
+struct alignas(16) FatNode {
+  S lb[6], rb[6];
+  int lc, rc;  // >= 0 internal node, < 0 leaf ~index
+  int ll, rl;  // last leaf (Morton position) under each child
+};
+
 struct BpTree {
   int n = 0;
   int cap = 0;                    // objects the device arrays were allocated for
@@ -46,6 +55,7 @@ struct BpTree {
   int2* node_range = nullptr;     // first / last leaf covered
   int* parent = nullptr;          // [0, n-1): internal nodes, [n-1, 2n-1): leaves
   int* flags = nullptr;           // refit arrival counters
+  void* fat = nullptr;            // FatNode<S>[n-1], rebuilt after every refit
   std::unordered_map<uint64_t, int> pos_of;  // user id -> Morton position (host)
 };
 static std::map<fclb_handle, BpTree*>& bpTable() {
@@ -209,6 +219,30 @@ __global__ void bpRefitKernel(const Box6<S>* __restrict__ leaf_box, int n, const
   }
 }
 
+template <typename S>
+__global__ void bpPackKernel(const Box6<S>* __restrict__ leaf_box, const Box6<S>* __restrict__ node_box,
+                             const int2* __restrict__ node_child, const int2* __restrict__ node_range, int n_inner,
+                             FatNode<S>* fat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inner) return;
+  const int2 c = node_child[i];
+  const Box6<S> l = c.x >= 0 ? node_box[c.x] : leaf_box[~c.x];
+  const Box6<S> r = c.y >= 0 ? node_box[c.y] : leaf_box[~c.y];
+  FatNode<S> f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    f.lb[k] = l.mn[k];
+    f.lb[3 + k] = l.mx[k];
+    f.rb[k] = r.mn[k];
+    f.rb[3 + k] = r.mx[k];
+  }
+  f.lc = c.x;
+  f.rc = c.y;
+  f.ll = c.x >= 0 ? node_range[c.x].y : ~c.x;
+  f.rl = c.y >= 0 ? node_range[c.y].y : ~c.y;
+  fat[i] = f;
+}
+
 // AABB<S>::overlap (math/bv/AABB-inl.h:82-88)
 template <typename S>
 FCLB_DI bool boxOverlap(const Box6<S>& a, const Box6<S>& b) {
@@ -223,6 +257,7 @@ struct BpQueryArgs {
   const void* node_box;
   const int2* node_child;
   const int2* node_range;
+  const void* fat;          // FatNode<S>[n-1]
   int n;                    // leaves of the tree
   const void* query_box;    // Box6<S>[n_query]
   const uint64_t* query_id;
@@ -258,25 +293,26 @@ __global__ void __launch_bounds__(128) bpQueryKernel(BpQueryArgs a) {
         if (boxOverlap(qb, leaf_box[0])) emit(0);
       }
     } else {
+      const FatNode<S>* __restrict__ fat = static_cast<const FatNode<S>*>(a.fat);
       int stack[64];
       int sp = 0;
       stack[sp++] = 0;
       while (sp > 0) {
-        const int node = stack[--sp];
-        const int2 c = a.node_child[node];
+        const FatNode<S> nd = fat[stack[--sp]];
 #pragma unroll
         for (int side = 0; side < 2; side++) {
-          const int ch = side == 0 ? c.x : c.y;
-          if (ch < 0) {
-            const int leaf = ~ch;
-            if (a.self && leaf <= i) continue;
-            visits++;
-            if (boxOverlap(qb, leaf_box[leaf])) emit(leaf);
-          } else {
-            if (a.self && a.node_range[ch].y <= i) continue;
-            visits++;
-            if (boxOverlap(qb, node_box[ch]) && sp < 64) stack[sp++] = ch;
-          }
+          const int ch = side == 0 ? nd.lc : nd.rc;
+          const int last = side == 0 ? nd.ll : nd.rl;
+          if (a.self && last <= i) continue;  // self pairs once: only leaves behind the query's Morton position
+          const S* cb = side == 0 ? nd.lb : nd.rb;
+          visits++;
+          const bool hit = !(qb.mn[0] > cb[3] || qb.mn[1] > cb[4] || qb.mn[2] > cb[5] || qb.mx[0] < cb[0] ||
+                             qb.mx[1] < cb[1] || qb.mx[2] < cb[2]);
+          if (!hit) continue;
+          if (ch < 0)
+            emit(~ch);
+          else if (sp < 64)
+            stack[sp++] = ch;
         }
       }
     }
@@ -358,6 +394,7 @@ static void freeTree(BpTree* t) {
   cudaFree(t->node_range);
   cudaFree(t->parent);
   cudaFree(t->flags);
+  cudaFree(t->fat);
   delete t;
 }
 
@@ -370,7 +407,10 @@ static int refit(Engine& e, BpTree* t) {
   FCLB_CUDA(cudaMemsetAsync(t->flags, 0, size_t(t->n - 1) * sizeof(int), e.compute));
   bpRefitKernel<S><<<(t->n + 127) / 128, 128, 0, e.compute>>>(static_cast<const Box6<S>*>(t->leaf_box), t->n, t->node_child,
                                                               t->parent, static_cast<Box6<S>*>(t->node_box), t->flags);
-  e.launches += 1;
+  bpPackKernel<S><<<(t->n - 1 + 127) / 128, 128, 0, e.compute>>>(static_cast<const Box6<S>*>(t->leaf_box),
+                                                                 static_cast<const Box6<S>*>(t->node_box), t->node_child,
+                                                                 t->node_range, t->n - 1, static_cast<FatNode<S>*>(t->fat));
+  e.launches += 2;
   FCLB_CUDA(cudaGetLastError());
   return FCLB_OK;
 }
@@ -390,7 +430,8 @@ static int buildTreeDev(Engine& e, const void* d_boxes, const uint64_t* d_ids, i
   const Box6<S>* box = static_cast<const Box6<S>*>(d_boxes);
   if (t->cap < n || t->scalar_type != (sizeof(S) == 4 ? FCLB_F32 : FCLB_F64)) {
     cudaFree(t->leaf_box); cudaFree(t->leaf_id); cudaFree(t->node_box); cudaFree(t->node_child);
-    cudaFree(t->node_range); cudaFree(t->parent); cudaFree(t->flags);
+    cudaFree(t->node_range); cudaFree(t->parent); cudaFree(t->flags); cudaFree(t->fat);
+    t->fat = nullptr;
     t->leaf_box = t->node_box = nullptr;
     t->leaf_id = nullptr; t->node_child = t->node_range = nullptr; t->parent = t->flags = nullptr;
     t->cap = 0;
@@ -402,6 +443,7 @@ static int buildTreeDev(Engine& e, const void* d_boxes, const uint64_t* d_ids, i
     FCLB_CUDA(cudaMalloc(&t->node_range, size_t(ni) * sizeof(int2)));
     FCLB_CUDA(cudaMalloc(&t->parent, size_t(2 * n) * sizeof(int)));
     FCLB_CUDA(cudaMalloc(&t->flags, size_t(ni) * sizeof(int)));
+    FCLB_CUDA(cudaMalloc(&t->fat, size_t(ni) * sizeof(FatNode<S>)));
     t->cap = n;
   }
   t->n = n;
@@ -465,6 +507,7 @@ static int queryDev(Engine& e, const BpTree* t, const void* q_box, const uint64_
   a.node_box = t->node_box;
   a.node_child = t->node_child;
   a.node_range = t->node_range;
+  a.fat = t->fat;
   a.n = t->n;
   a.query_box = q_box;
   a.query_id = q_id;
