@@ -241,13 +241,18 @@ __global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
         }
         const unsigned em = __ballot_sync(0xffffffffu, expand);
         const unsigned lm = __ballot_sync(0xffffffffu, leaf);
+        if (sp + 2 * __popc(em) > kStackCap) {  // deeper than the depth-first head room: report, never corrupt
+          if (lane == 0) atomicAdd(&a.stats[2], 1ull);
+          done = true;
+          expand = false;
+        }
         if (expand) {
           const int pos = sp + 2 * __popc(em & lt_mask);
           stack[pos] = c0;
           stack[pos + 1] = c1;
         }
         if (leaf) leafq[nleaf + __popc(lm & lt_mask)] = c0;
-        sp += 2 * __popc(em);
+        if (!done) sp += 2 * __popc(em);
         nleaf += __popc(lm);
         __syncwarp();
       }
@@ -386,9 +391,13 @@ static int bvhCollideDev(Engine& e, const BvhDev* m1, const BvhDev* m2, const vo
   FCLB_CUDA(cudaGetLastError());
   FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
   e.launches += 1;
-  FCLB_CUDA(cudaMemcpyAsync(g_last_stats, g_bvh_counters + 1, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+  static unsigned long long h_stats[3];
+  FCLB_CUDA(cudaMemcpyAsync(h_stats, g_bvh_counters + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  g_last_stats[0] = h_stats[0];
+  g_last_stats[1] = h_stats[1];
+  if (h_stats[2]) return fail(FCLB_ERR_CAPACITY, "mesh-mesh traversal: BVH deeper than the per-warp pair stack allows");
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e.ev0, e.ev1);
   e.last_ms = ms;

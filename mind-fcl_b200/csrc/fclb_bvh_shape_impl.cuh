@@ -408,13 +408,18 @@ __global__ void __launch_bounds__(kBsWarps * 32) bvhShapeCollideKernel(BvhShapeA
         }
         const unsigned em = __ballot_sync(0xffffffffu, expand);
         const unsigned lm = __ballot_sync(0xffffffffu, leaf);
+        if (sp + 2 * __popc(em) > kBsStackCap) {  // deeper than the depth-first head room: report, never corrupt
+          if (lane == 0) atomicAdd(&a.stats[2], 1ull);
+          done = true;
+          expand = false;
+        }
         if (expand) {
           const int pos = sp + 2 * __popc(em & lt_mask);
           stack[pos] = c0;
           stack[pos + 1] = c0 + 1;
         }
         if (leaf) leafq[nleaf + __popc(lm & lt_mask)] = c0;
-        sp += 2 * __popc(em);
+        if (!done) sp += 2 * __popc(em);
         nleaf += __popc(lm);
         __syncwarp();
       }

@@ -128,6 +128,7 @@ struct OctCand {  // candidate voxel box + encodeOctree2Node
 
 constexpr int kOctWarps = kOctreeWarps;
 constexpr int kOctStack = 384;   // stack elements per warp
+constexpr int kOctDfsReserve = 7 * 16;  // head room of the depth-first fallback
 constexpr int kOctQueue = 160;   // queued candidate boxes per warp (< 32 left over + 16 popped leaves x 8 voxels)
 
 template <typename S, int T1>
@@ -226,9 +227,14 @@ __global__ void __launch_bounds__(kOctWarps * 32) octreeShapeKernel(OctreeArgs a
 
     while (!done && sp > 0) {
       // a popped element pushes <= 8 children and queues <= 8 boxes: bound both before popping
+      // (popping `take` and pushing 8 each leaves sp + 7 take).  Wide pops stop while kOctDfsReserve slots are
+      // still free; from there the warp pops one element at a time from the top, i.e. plain depth-first
+      // order, whose growth is bounded by 7 per remaining tree level (<= 16 levels: half shapes are uint16).
       int take = sp < 32 ? sp : 32;
-      const int room = (kOctStack - sp) / 8;
-      if (take > room) take = room < 1 ? 1 : room;
+      if (sp + 7 * take > kOctStack - kOctDfsReserve) {
+        const int fit = (kOctStack - kOctDfsReserve - sp) / 7;
+        take = fit < 1 ? 1 : fit;
+      }
       if (take * 8 > kOctQueue - nq) take = (kOctQueue - nq) / 8;
       if (take < 1) {  // queue nearly full: drain it first
         runLeaf(true);
@@ -282,6 +288,11 @@ __global__ void __launch_bounds__(kOctWarps * 32) octreeShapeKernel(OctreeArgs a
         }
       }
       const int tot_push = __shfl_sync(0xffffffffu, push_off, 31), tot_cand = __shfl_sync(0xffffffffu, cand_off, 31);
+      if (sp + tot_push > kOctStack) {  // deeper than the depth-first head room: report, never corrupt
+        if (lane == 0) atomicAdd(&a.stats[2], 1ull);
+        done = true;
+        break;
+      }
       push_off -= n_push;
       cand_off -= n_cand;
       if (have) {

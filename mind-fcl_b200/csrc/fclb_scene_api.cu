@@ -9,7 +9,7 @@
 namespace fclb {
 
 static unsigned long long* g_counters = nullptr;  // [0] work counter, [1..2] stats
-static unsigned long long g_stats[2] = {0, 0};
+static unsigned long long g_stats[3] = {0, 0, 0};
 
 struct ContactSink {  // pass 1 of the MPR penetration modes
   uint32_t max_keep = 0;
@@ -61,8 +61,9 @@ static int bvhShapeDev(Engine& e, const BvhDev* m, const ShapeTable* t, const ui
   FCLB_CUDA(launchBvhShape<S>(tableUniformType(t), a, grid, e.compute));
   FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
   e.launches += 1;
-  FCLB_CUDA(cudaMemcpyAsync(g_stats, g_counters + 1, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(g_stats, g_counters + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  if (g_stats[2]) return fail(FCLB_ERR_CAPACITY, "scene traversal: tree deeper than the per-warp stack allows");
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e.ev0, e.ev1);
   e.last_ms = ms;
@@ -134,8 +135,9 @@ static int heightmapShapeDev(Engine& e, const HeightmapDev* hm, const ShapeTable
   FCLB_CUDA(launchHeightmapShape<S>(tableUniformType(t), a, grid, e.compute));
   FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
   e.launches += 1;
-  FCLB_CUDA(cudaMemcpyAsync(g_stats, g_counters + 1, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(g_stats, g_counters + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  if (g_stats[2]) return fail(FCLB_ERR_CAPACITY, "scene traversal: tree deeper than the per-warp stack allows");
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e.ev0, e.ev1);
   e.last_ms = ms;
@@ -202,8 +204,9 @@ static int octreeShapeDev(Engine& e, const OctreeDev* o, const ShapeTable* t, co
   FCLB_CUDA(launchOctreeShape<S>(tableUniformType(t), a, grid, e.compute));
   FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
   e.launches += 1;
-  FCLB_CUDA(cudaMemcpyAsync(g_stats, g_counters + 1, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(g_stats, g_counters + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  if (g_stats[2]) return fail(FCLB_ERR_CAPACITY, "scene traversal: tree deeper than the per-warp stack allows");
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e.ev0, e.ev1);
   e.last_ms = ms;
