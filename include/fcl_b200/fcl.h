@@ -637,6 +637,9 @@ template <typename S>
 struct DistanceRequest {
   S gjk_tolerance = S(0);        // <= 0: constants<S>::gjk_default_tolerance()
   uint32_t gjk_max_iterations = 0;  // 0: 128
+  // true: detail::GJKSolver<S>::shapeSignedDistance (gjk_solver-inl.h:810-880) -- generic GJK, and for
+  // penetrating pairs min_distance = -(EPA depth) with the EPA witness points
+  bool enable_signed_distance = false;
 };
 template <typename S>
 struct DistanceResult {
@@ -664,10 +667,15 @@ void distanceBatch(const std::vector<CollisionQuery<S>>& queries, const Distance
   }
   fclb_handle table = 0;
   detail::check(fclb_shapes_upload(shapes.data(), uint32_t(shapes.size()), &table), "fclb_shapes_upload");
-  detail::check(fclb_distance_batch_host(table, pairs.data(), p1.data(), p2.data(), n, detail::scalarType<S>(),
-                                         double(request.gjk_tolerance), request.gjk_max_iterations, dist.data(),
-                                         w1.data(), w2.data(), ok.data()),
-                "fclb_distance_batch_host");
+  if (request.enable_signed_distance)
+    detail::check(fclb_signed_distance_batch_host(table, pairs.data(), p1.data(), p2.data(), n, detail::scalarType<S>(),
+                                                  dist.data(), w1.data(), w2.data(), ok.data()),
+                  "fclb_signed_distance_batch_host");
+  else
+    detail::check(fclb_distance_batch_host(table, pairs.data(), p1.data(), p2.data(), n, detail::scalarType<S>(),
+                                           double(request.gjk_tolerance), request.gjk_max_iterations, dist.data(),
+                                           w1.data(), w2.data(), ok.data()),
+                  "fclb_distance_batch_host");
   fclb_release(table);
   for (std::size_t q = 0; q < n; q++) {
     results[q].separated = ok[q] != 0;

@@ -130,6 +130,18 @@ int fclb_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const vo
                             size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
                             void* out_p1, void* out_p2, uint8_t* out_ok);
 
+/* Signed distance == detail::GJKSolver<S>::shapeSignedDistance (gjk_solver-inl.h:810-880): always the generic
+ * GJK (no closed forms), GJKSolver's default tolerances / limits (:1121-1130);
+ *   separated:   ok = 1, dist > 0, witness points as above
+ *   penetrating: ok = 1, dist = -(EPA depth), p1 / p2 = tf1 * EPA witness points
+ *   otherwise:   ok = 0, dist = -1 (EPA failed, or GJK neither separated nor intersecting) */
+int fclb_signed_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                                    size_t n, int scalar_type, void* out_dist, void* out_p1, void* out_p2,
+                                    uint8_t* out_ok);
+int fclb_signed_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                                   size_t n, int scalar_type, void* out_dist, void* out_p1, void* out_p2,
+                                   uint8_t* out_ok);
+
 /* fcl::collide semantics for shape-shape pairs
  * (collision_func_matrix-inl.h:340 ShapeShapeCollide -> shape_pair_intersect-inl.h:49).
  * out_contacts: max_keep records per query of 9 S = {b1, b2, normal[3], pos[3], depth}

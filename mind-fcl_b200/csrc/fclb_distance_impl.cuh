@@ -696,7 +696,7 @@ cudaError_t launchDistance(const BatchView& b, const SolverParams& sp, const Dis
                            int* n_launches) {
   if (b.count == 0) return cudaSuccess;
   if (n_launches) *n_launches += 1;
-  switch (closedKindOf(b.type1, b.type2)) {
+  switch (sp.generic_only ? CK_NONE : closedKindOf(b.type1, b.type2)) {
     case CK_SPHERE_BOX:
       return launchClosedDistance<S, CK_SPHERE_BOX>(b, sp, out, st);
     case CK_BOX_SPHERE:

@@ -353,6 +353,33 @@ int ensureStage(Engine& e, size_t bytes) {
 
 using namespace fclb;
 
+// GJKSolver::shapeSignedDistance (gjk_solver-inl.h:810-868) assembled from the two device paths: the generic GJK
+// distance answers the separated queries; for the others the GJK + EPA path gives the penetration, reported
+// as a negative distance with the EPA witness points mapped by tf1.
+template <typename S>
+__global__ void signedDistanceCombineKernel(const S* __restrict__ poses1, size_t n, const int32_t* __restrict__ gjk,
+                                            const int32_t* __restrict__ epa, const S* __restrict__ geom, S* dist, S* p1,
+                                            S* p2, uint8_t* ok) {
+  const size_t q = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (q >= n) return;
+  if (ok[q] == 1) return;  // Separated with valid witness points: already final
+  S d = S(-1);
+  V3<S> a = zero3<S>(), b = zero3<S>();
+  uint8_t r = 0;
+  if (gjk[q] == 0 /* GJK_Status::Intersect */ && epa[q] > 0 /* EPA ran and did not fail */) {
+    const Pose<S> tf1 = loadPose(poses1, q);
+    const S* g = geom + 7 * q;
+    d = -g[0];
+    a = apply(tf1, mk<S>(g[1], g[2], g[3]));
+    b = apply(tf1, mk<S>(g[4], g[5], g[6]));
+    r = 1;
+  }
+  if (dist) dist[q] = d;
+  if (p1) store3(p1, q, a);
+  if (p2) store3(p2, q, b);
+  ok[q] = r;
+}
+
 // FMA-chain microbenchmark: the FP32 / FP64 CUDA-core peak the compute-bound kernels are compared with
 // (SURVEY.md 8d asks for measured, not nominal, FP peaks).  16 independent accumulators per thread.
 template <typename S>
@@ -594,6 +621,97 @@ int fclb_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const vo
   DistanceOut out{out_dist, out_p1, out_p2, out_ok};
   if (scalar_type == FCLB_F32) return distanceDev<float>(e, t, pairs, poses1, poses2, n, sp, out);
   return distanceDev<double>(e, t, pairs, poses1, poses2, n, sp, out);
+}
+
+int fclb_signed_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                                   size_t n, int scalar_type, void* out_dist, void* out_p1, void* out_p2, uint8_t* out_ok) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  ShapeTable* t = findTable(e, shapes);
+  if (!t) return fail(FCLB_ERR_BAD_ARG, "fclb_signed_distance_batch: unknown shape table handle");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (n > 0xffffffffull) return fail(FCLB_ERR_CAPACITY, "batch larger than 2^32-1 queries: split it");
+  if (!pairs || !poses1 || !poses2 || !out_ok) return fail(FCLB_ERR_BAD_ARG, "fclb_signed_distance_batch: null array (out_ok is required)");
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  // pass 1: generic GJK distance (GJKSolver defaults: eps^(7/8), 128 iterations)
+  SolverParams sp = distanceParams(scalar_type, 0.0, 0);
+  sp.generic_only = 1;
+  DistanceOut out{out_dist, out_p1, out_p2, out_ok};
+  rc = scalar_type == FCLB_F32 ? distanceDev<float>(e, t, pairs, poses1, poses2, n, sp, out)
+                               : distanceDev<double>(e, t, pairs, poses1, poses2, n, sp, out);
+  if (rc) return rc;
+  // pass 2: GJK + EPA (256 faces, 255 iterations, eps^(7/8)) for the penetration of the others
+  int32_t *d_gjk = nullptr, *d_epa = nullptr;
+  void* d_geom = nullptr;
+  FCLB_CUDA(cudaMalloc(&d_gjk, n * 4));
+  FCLB_CUDA(cudaMalloc(&d_epa, n * 4));
+  FCLB_CUDA(cudaMalloc(&d_geom, n * 7 * ss));
+  fclb_request req{};
+  req.max_contacts = 1;
+  req.penetration_mode = FCLB_PEN_DEFAULT_GJK_EPA;
+  req.binary_tol = sp.eps78;
+  req.distance_tol = sp.eps78;
+  rc = fclb_gjk_epa_batch_dev(shapes, pairs, poses1, poses2, n, scalar_type, &req, d_gjk, d_epa, d_geom);
+  if (!rc) {
+    const int grid = int((n + 255) / 256);
+    if (scalar_type == FCLB_F32)
+      signedDistanceCombineKernel<float><<<grid, 256, 0, e.compute>>>(static_cast<const float*>(poses1), n, d_gjk, d_epa,
+                                                                    static_cast<const float*>(d_geom),
+                                                                    static_cast<float*>(out_dist), static_cast<float*>(out_p1),
+                                                                    static_cast<float*>(out_p2), out_ok);
+    else
+      signedDistanceCombineKernel<double><<<grid, 256, 0, e.compute>>>(static_cast<const double*>(poses1), n, d_gjk, d_epa,
+                                                                     static_cast<const double*>(d_geom),
+                                                                     static_cast<double*>(out_dist),
+                                                                     static_cast<double*>(out_p1), static_cast<double*>(out_p2),
+                                                                     out_ok);
+    e.launches += 1;
+    if (cudaStreamSynchronize(e.compute) != cudaSuccess) rc = fail(FCLB_ERR_CUDA, "signed distance combine failed");
+  }
+  cudaFree(d_gjk);
+  cudaFree(d_epa);
+  cudaFree(d_geom);
+  return rc;
+}
+
+int fclb_signed_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                                    size_t n, int scalar_type, void* out_dist, void* out_p1, void* out_p2, uint8_t* out_ok) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!pairs || !poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "fclb_signed_distance_batch: null input array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  char* base = nullptr;
+  const size_t o_pairs = 0;
+  const size_t o_p1 = alignUp(o_pairs + n * sizeof(fclb_pair), 256);
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_dist = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_w1 = alignUp(o_dist + n * ss, 256);
+  const size_t o_w2 = alignUp(o_w1 + n * 3 * ss, 256);
+  const size_t o_ok = alignUp(o_w2 + n * 3 * ss, 256);
+  const size_t total = alignUp(o_ok + n, 256);
+  FCLB_CUDA(cudaMalloc(reinterpret_cast<void**>(&base), total));  // (the engine's staging arena is used by the inner calls)
+  cudaMemcpyAsync(base + o_pairs, pairs, n * sizeof(fclb_pair), cudaMemcpyHostToDevice, e.compute);
+  cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute);
+  cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute);
+  rc = fclb_signed_distance_batch_dev(shapes, reinterpret_cast<const fclb_pair*>(base + o_pairs), base + o_p1, base + o_p2, n,
+                                      scalar_type, base + o_dist, base + o_w1, base + o_w2,
+                                      reinterpret_cast<uint8_t*>(base + o_ok));
+  if (!rc) {
+    if (out_dist) cudaMemcpyAsync(out_dist, base + o_dist, n * ss, cudaMemcpyDeviceToHost, e.compute);
+    if (out_p1) cudaMemcpyAsync(out_p1, base + o_w1, n * 3 * ss, cudaMemcpyDeviceToHost, e.compute);
+    if (out_p2) cudaMemcpyAsync(out_p2, base + o_w2, n * 3 * ss, cudaMemcpyDeviceToHost, e.compute);
+    if (out_ok) cudaMemcpyAsync(out_ok, base + o_ok, n, cudaMemcpyDeviceToHost, e.compute);
+    if (cudaStreamSynchronize(e.compute) != cudaSuccess) rc = fail(FCLB_ERR_CUDA, "signed distance copy-out failed");
+  }
+  cudaFree(base);
+  return rc;
 }
 
 int fclb_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,

@@ -40,6 +40,7 @@ struct SolverParams {
   int epa_max_faces;
   int epa_max_iter;
   double eps78;  // constants<S>::eps_78()
+  int generic_only = 0;  // 1: skip the closed-form distance routines (shapeSignedDistance has no specialisations)
 };
 
 // implemented in fclb_distance_f32.cu / fclb_distance_f64.cu

@@ -27,6 +27,7 @@ EXPORTS = [
     "fclb_memcpy_h2d", "fclb_memcpy_d2h", "fclb_synchronize",
     "fclb_convex_upload", "fclb_shapes_upload", "fclb_release",
     "fclb_distance_batch_host", "fclb_distance_batch_dev",
+    "fclb_signed_distance_batch_host", "fclb_signed_distance_batch_dev",
     "fclb_collide_batch_host", "fclb_collide_batch_dev",
     "fclb_gjk_epa_batch_host", "fclb_gjk_epa_batch_dev",
     "fclb_bvh_upload", "fclb_bvh_release", "fclb_bvh_collide_batch_host", "fclb_bvh_collide_batch_dev",
@@ -182,6 +183,10 @@ def load() -> C.CDLL:
         bc_args = [C.c_uint64, C.c_uint64, vp, vp, sz, C.c_int, vp, u32, vp, vp, vp]
         lib.fclb_bvh_collide_contacts_batch_host.argtypes = bc_args
         lib.fclb_bvh_collide_contacts_batch_dev.argtypes = bc_args
+    if hasattr(lib, "fclb_signed_distance_batch_host"):
+        sd_args = [C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp, vp]
+        lib.fclb_signed_distance_batch_host.argtypes = sd_args
+        lib.fclb_signed_distance_batch_dev.argtypes = sd_args
     _lib = lib
     return lib
 
@@ -587,3 +592,13 @@ def bvh_collide_contacts_batch_host(bvh1, bvh2, poses1, poses2, scalar_type, req
                                                       C.cast(C.pointer(request), C.c_void_p), max_keep, _ptr(counts),
                                                       _ptr(ids), _ptr(contacts)))
     return counts, ids, contacts
+
+
+def signed_distance_batch_host(table, pairs, poses1, poses2, scalar_type):
+    """GJKSolver::shapeSignedDistance per query: DistanceResult(dist, p1, p2, ok)."""
+    n = len(pairs)
+    dt = np_dtype(scalar_type)
+    out = DistanceResult(np.zeros(n, dt), np.zeros((n, 3), dt), np.zeros((n, 3), dt), np.zeros(n, np.uint8))
+    check(load().fclb_signed_distance_batch_host(table, _ptr(pairs), _ptr(poses1), _ptr(poses2), n, scalar_type,
+                                                 _ptr(out.dist), _ptr(out.p1), _ptr(out.p2), _ptr(out.ok)))
+    return out

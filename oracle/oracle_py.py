@@ -149,6 +149,21 @@ class RefOracle(_Oracle):
     path = REF_PATH
     kind = "reference"
 
+    def signed_distance_batch(self, shapes, pairs, poses1, poses2, threads=1):
+        n = len(pairs)
+        dt = poses1.dtype
+        dist = np.zeros(n, dt)
+        p1 = np.zeros((n, 3), dt)
+        p2 = np.zeros((n, 3), dt)
+        ok = np.zeros(n, np.uint8)
+        arr = _shape_array(shapes)
+        f = self.fn("signed_distance_batch")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                      C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(dt), C.cast(arr, C.c_void_p), len(shapes), _p(pairs), _p(poses1), _p(poses2), n, _p(dist), _p(p1), _p(p2),
+          _p(ok), threads)
+        return dist, p1, p2, ok
+
     # ---- meshes (reference BVHModel<OBBRSS<S>>) ----
     def bvh_create(self, verts, tris):
         verts = np.ascontiguousarray(verts, np.float64)

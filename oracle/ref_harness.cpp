@@ -169,6 +169,34 @@ int distanceBatch(const ShapeRec* shapes, int n_shapes, const PairRec* pairs, co
 }
 
 template <typename S>
+int signedDistanceBatch(const ShapeRec* shapes, int n_shapes, const PairRec* pairs, const S* poses1, const S* poses2,
+                        size_t n, S* dist, S* p1, S* p2, uint8_t* ok, int n_threads) {
+  std::vector<std::shared_ptr<fcl::ShapeBase<S>>> tab;
+  for (int i = 0; i < n_shapes; i++) tab.push_back(makeShape<S>(shapes[i]));
+  parallelFor(n, n_threads, [&](size_t b, size_t e, int) {
+    fcl::detail::GJKSolver<S> solver;
+    for (size_t q = b; q < e; q++) {
+      const auto tf1 = loadPose<S>(poses1 + 12 * q);
+      const auto tf2 = loadPose<S>(poses2 + 12 * q);
+      const fcl::ShapeBase<S>* s1 = tab[pairs[q].s1].get();
+      const fcl::ShapeBase<S>* s2 = tab[pairs[q].s2].get();
+      S d = S(0);
+      fcl::Vector3<S> a = fcl::Vector3<S>::Zero(), c = fcl::Vector3<S>::Zero();
+      const bool r = withShape<S>(s1, [&](const auto& sh1) {
+        return withShape<S>(s2, [&](const auto& sh2) { return solver.shapeSignedDistance(sh1, tf1, sh2, tf2, &d, &a, &c); });
+      });
+      dist[q] = d;
+      ok[q] = r ? 1 : 0;
+      for (int k = 0; k < 3; k++) {
+        p1[3 * q + k] = a[k];
+        p2[3 * q + k] = c[k];
+      }
+    }
+  });
+  return 0;
+}
+
+template <typename S>
 fcl::CollisionRequest<S> makeRequest(const RequestRec& r) {
   fcl::CollisionRequest<S> req(r.max_contacts);
   switch (r.penetration_mode) {
@@ -347,6 +375,16 @@ int fclref_gjk_epa_batch(int scalar_type, const void* shapes, int n_shapes, cons
 int fclref_hardware_threads(void) { return int(std::thread::hardware_concurrency()); }
 
 }  // extern "C"
+
+extern "C" int fclref_signed_distance_batch(int scalar_type, const void* shapes, int n_shapes, const void* pairs,
+                                            const void* poses1, const void* poses2, size_t n, void* dist, void* p1, void* p2,
+                                            uint8_t* ok, int threads) {
+  if (scalar_type == 0)
+    return signedDistanceBatch<float>((const ShapeRec*)shapes, n_shapes, (const PairRec*)pairs, (const float*)poses1,
+                                      (const float*)poses2, n, (float*)dist, (float*)p1, (float*)p2, ok, threads);
+  return signedDistanceBatch<double>((const ShapeRec*)shapes, n_shapes, (const PairRec*)pairs, (const double*)poses1,
+                                     (const double*)poses2, n, (double*)dist, (double*)p1, (double*)p2, ok, threads);
+}
 
 // shape factory for the other harness translation units (ref_harness_scene.cpp)
 namespace fclref {

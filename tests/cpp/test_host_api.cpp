@@ -39,6 +39,17 @@ void run() {
     distance<S>(&s1, I, &s2, at(40, 0, 0), req, res);
     EXPECT_TRUE(res.separated && std::fabs(res.min_distance - S(17.5)) < S(0.001));
   }
+  // signed distance: two unit spheres 1.5 apart penetrate by 0.5
+  {
+    Sphere<S> a(1), b(1);
+    DistanceRequest<S> req;
+    req.enable_signed_distance = true;
+    DistanceResult<S> res;
+    distance<S>(&a, I, &b, at(S(1.5), 0, 0), req, res);
+    EXPECT_TRUE(res.separated && std::fabs(res.min_distance + S(0.5)) < S(2e-3));
+    distance<S>(&a, I, &b, at(S(2.5), 0, 0), req, res);
+    EXPECT_TRUE(res.separated && std::fabs(res.min_distance - S(0.5)) < S(2e-3));
+  }
   // shapeDistance_cylindercylinder: GJK distance path
   {
     Cylinder<S> s1(5, 10), s2(5, 10);

@@ -132,3 +132,38 @@ def test_empty_and_single(fclb, ref_oracle):
     exp = ref_oracle.distance_batch(shapes, pairs, poses1, poses2)
     assert (r.ok[0] != 0) == (exp[3][0] != 0)
     fclb.release(table)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_signed_distance(fclb, ref_oracle, dtype):
+    """fclb_signed_distance_batch vs GJKSolver::shapeSignedDistance (gjk_solver-inl.h:810-880): generic GJK
+    distance when separated, -(EPA depth) with the EPA witness points when penetrating."""
+    st = fclb.F32 if dtype == np.float32 else fclb.F64
+    tol = 1e-4 if dtype == np.float32 else 1e-6
+    hull = scenes.ellipsoid_mesh(0.2, 0.3, 0.4)
+    shapes = [(scenes.SPHERE, 0, (0.25,)), (scenes.BOX, 0, (0.5, 0.4, 0.3)), (scenes.CAPSULE, 0, (0.15, 0.4)),
+              (scenes.CYLINDER, 0, (0.2, 0.4)), (scenes.CONVEX, fclb.convex_upload(*hull), ())]
+    rshapes = shapes[:4] + [(scenes.CONVEX, ref_oracle.register_convex(*hull), ())]
+    combos = [(0, 1), (1, 1), (2, 1), (3, 2), (4, 1), (4, 4), (0, 0)]
+    n = 21_000
+    rng = np.random.Generator(np.random.PCG64(77))
+    p1 = scenes.random_poses(rng, n, 0.45, dtype)
+    p2 = scenes.random_poses(rng, n, 0.45, dtype)
+    idx = np.arange(n) % len(combos)
+    pairs = scenes.make_pairs(np.array([combos[i][0] for i in idx], np.uint32), np.array([combos[i][1] for i in idx], np.uint32))
+    table = fclb.shapes_upload(shapes)
+    r = fclb.signed_distance_batch_host(table, pairs, p1, p2, st)
+    e_dist, e_p1, e_p2, e_ok = ref_oracle.signed_distance_batch(rshapes, pairs, p1, p2, threads=8)
+    mism = np.nonzero((r.ok != 0) != (e_ok != 0))[0]
+    both = (r.ok != 0) & (e_ok != 0)
+    pen = both & (e_dist < 0)
+    same = float(((r.dist[both] == e_dist[both]) & (r.p1[both] == e_p1[both]).all(axis=1)).mean())
+    dd = np.abs(r.dist[both] - e_dist[both])
+    dp = np.maximum(np.abs(r.p1[both] - e_p1[both]).max(axis=1), np.abs(r.p2[both] - e_p2[both]).max(axis=1))
+    print(f"[signed distance {np.dtype(dtype).name}] n={n} separated={int((both & ~pen).sum())} penetrating={int(pen.sum())} "
+          f"failed(ref)={int((e_ok == 0).sum())} flag mismatches={len(mism)}; bit-identical {same:.5f}; "
+          f"max |d dist| {dd.max():.2e} max |d witness| {dp.max():.2e}")
+    assert len(mism) <= max(1, n // 20000), mism[:10]
+    assert np.quantile(dd, 0.999) <= tol and np.quantile(dp, 0.999) <= 10 * tol
+    assert (r.dist[(r.ok == 0)] == -1).all()
+    fclb.release(table)
