@@ -22,6 +22,11 @@
 #include "fclb_bvh_build.h"
 #include "fclb_mpr.cuh"
 
+// 3 CTAs per SM (80 registers, no spills): 26.1 -> 25.4 ms on C4
+#ifndef FCLB_SCENE_MIN_BLOCKS
+#define FCLB_SCENE_MIN_BLOCKS 3
+#endif
+
 namespace fclb {
 
 // ---- fitn on the transformed bound vertices (math/bv/utility-inl.h:133-146) ----
@@ -346,7 +351,7 @@ constexpr int kBsStackCap = 1024;
 constexpr int kBsLeafCap = 64;
 
 template <typename S, int T0>
-__global__ void __launch_bounds__(kBsWarps * 32) bvhShapeCollideKernel(BvhShapeArgs a) {
+__global__ void __launch_bounds__(kBsWarps * 32, FCLB_SCENE_MIN_BLOCKS) bvhShapeCollideKernel(BvhShapeArgs a) {
   extern __shared__ __align__(16) int s_bs[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* stack = s_bs + size_t(warp) * (kBsStackCap + kBsLeafCap);
