@@ -142,7 +142,9 @@ FCLB_DI void cullPoints2(int n, const S p[], int m, int i0, int iret[]) {
 
 // box_box-inl.h:214-807 with maxc = 4 (boxBoxIntersect, :824-846).
 // Returns return_code (0 = separated); *n_contacts contacts are written.
-template <typename S>
+// SAT_ONLY: stop after the 15-axis separating test (the return code is already final; the contact
+// generation that follows is what the two-phase box-box kernel runs on the compacted colliding queries).
+template <typename S, bool SAT_ONLY = false>
 FCLB_DI int boxBox2(const V3<S>& side1, const Pose<S>& tf1, const V3<S>& side2, const Pose<S>& tf2, ContactPt<S> out[4],
                     int* n_contacts) {
   const S fudge_factor = S(1.05);
@@ -237,6 +239,7 @@ FCLB_DI int boxBox2(const V3<S>& side1, const Pose<S>& tf1, const V3<S>& side2, 
 #undef FCLB_BB_EDGE
 
   if (!code) return 0;
+  if (SAT_ONLY) return code;
 
   V3<S> normal;
   if (best_col_id != -1)

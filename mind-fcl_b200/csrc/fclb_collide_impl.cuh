@@ -230,6 +230,75 @@ __global__ void __launch_bounds__(kBlock) collideClosedKernel(BatchView b, Colli
   }
 }
 
+// ---- box-box, two phases ---------------------------------------------------------------
+// boxBox2 is a 15-axis SAT followed by ~300 lines of contact generation that only the colliding pairs reach
+// (ncu on the one-phase kernel: 4.6 of 32 lanes per issued instruction).  Phase 1 runs the SAT for every query
+// of a block-sized chunk and queues the colliding ones in shared memory; phase 2 runs the complete routine on
+// the compacted queue, a full block at a time.  Without contacts requested the SAT result is the answer
+// (boxBoxIntersect returns return_code != 0, box_box-inl.h:824-846) and phase 2 is skipped.
+template <typename S>
+__global__ void __launch_bounds__(kBlock) boxBoxCollideKernel(BatchView b, CollideOut out) {
+  __shared__ uint32_t queue[2 * kBlock];
+  __shared__ int qn;
+  const ShapeD<S>* __restrict__ shapes = static_cast<const ShapeD<S>*>(b.shapes);
+  const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
+  const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
+  const bool want = out.penetration != 0 && out.max_contacts != 0;
+  if (threadIdx.x == 0) qn = 0;
+  __syncthreads();
+  auto phase2 = [&](int first, int count) {
+    if (int(threadIdx.x) < count) {
+      const size_t q = queue[first + threadIdx.x];
+      const fclb_pair pr = b.pairs[q];
+      const ShapeD<S> a = shapes[pr.shape1];
+      const ShapeD<S> c = shapes[pr.shape2];
+      ContactPt<S> cp[4];
+      int n = 1;
+      const int code = boxBox2<S>(mk<S>(a.p[0], a.p[1], a.p[2]), loadPose(poses1, q), mk<S>(c.p[0], c.p[1], c.p[2]),
+                                  loadPose(poses2, q), cp, &n);
+      emitContacts<S>(out, q, code != 0, cp, n);
+    }
+  };
+  const size_t chunk = size_t(gridDim.x) * blockDim.x;
+  const size_t rounds = (b.count + chunk - 1) / chunk;
+  for (size_t r = 0; r < rounds; r++) {
+    const size_t i = r * chunk + blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    bool hit = false;
+    size_t q = 0;
+    if (i < b.count) {
+      q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
+      const fclb_pair pr = b.pairs[q];
+      const ShapeD<S> a = shapes[pr.shape1];
+      const ShapeD<S> c = shapes[pr.shape2];
+      ContactPt<S> cp[4];
+      int n = 0;
+      const int code = boxBox2<S, true>(mk<S>(a.p[0], a.p[1], a.p[2]), loadPose(poses1, q), mk<S>(c.p[0], c.p[1], c.p[2]),
+                                        loadPose(poses2, q), cp, &n);
+      hit = code != 0;
+      if (!hit || !want) emitContacts<S>(out, q, hit, cp, 0);  // final without contacts
+    }
+    if (want) {
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      int base = 0;
+      if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&qn, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (hit) queue[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = uint32_t(q);
+      __syncthreads();
+      if (qn >= kBlock) {
+        const int first = qn - kBlock;
+        phase2(first, kBlock);
+        __syncthreads();
+        if (threadIdx.x == 0) qn = first;
+        __syncthreads();
+      }
+    }
+  }
+  if (want) {
+    __syncthreads();
+    phase2(0, qn);
+  }
+}
+
 // ---- generic convex pairs: boolean stage -------------------------------------
 // mode bit 0: run MPR first (collide API without penetration, gjk_solver-inl.h:88-98)
 // mode bit 1: colliding queries go to the EPA work list

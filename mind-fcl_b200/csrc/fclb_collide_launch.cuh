@@ -1,6 +1,8 @@
 // fclb_collide_launch.cuh -- per-bucket launch logic of the collide path
 // (included by the per-scalar-type translation units).
 #pragma once
+#include <cstdlib>
+
 #include "fclb_collide_impl.cuh"
 #include "fclb_distance_impl.cuh"  // gridFor
 
@@ -66,8 +68,12 @@ cudaError_t launchCollide(const BatchView& b, const CollideLaunchArgs& a, cudaSt
         return launchClosedCollide<S, CC_SPHERE_CYLINDER>(b, a, st);
       case CC_CYLINDER_SPHERE:
         return launchClosedCollide<S, CC_CYLINDER_SPHERE>(b, a, st);
-      case CC_BOX_BOX:
-        return launchClosedCollide<S, CC_BOX_BOX>(b, a, st);
+      case CC_BOX_BOX: {
+        if (getenv("FCLB_BOXBOX_ONE_PHASE")) return launchClosedCollide<S, CC_BOX_BOX>(b, a, st);
+        const int grid = gridFor(b.count, kBlock, 12);
+        boxBoxCollideKernel<S><<<grid, kBlock, 0, st>>>(b, a.out);
+        return cudaGetLastError();
+      }
       default:
         break;
     }
