@@ -304,6 +304,28 @@ int fclb_scene_shape_contacts_batch_dev(int scene_kind, fclb_handle scene, fclb_
                                         const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
                                         const fclb_request* req, uint32_t max_keep, uint32_t* out_counts,
                                         int64_t* out_b1, void* out_contacts);
+/* ---- scene vs scene: heightmap / octree against heightmap / octree / mesh ------------------------
+ * fcl::collide(g1, tf1, g2, tf2, request, result) per query for the non-convex pairs of the collision matrix
+ * (collision_func_matrix-inl.h:774-857), boolean request (penetration_mode FCLB_PEN_DISABLED):
+ *   (HEIGHTMAP, HEIGHTMAP)  heightMapPairIntersect    traversal/heightmap/heightmap_solver_traverse-inl.h:189-296
+ *   (HEIGHTMAP, BVH)        heightMapBVHIntersect     :298-404
+ *   (HEIGHTMAP, OCTREE)     heightMapOctreeIntersect  :406-570
+ *   (OCTREE, BVH)           octreeBVHIntersect        traversal/octree2/octree2_solver_traverse-inl.h:138-288
+ *   (OCTREE, OCTREE)        octreePairIntersect       :290-447
+ * A contact is a leaf pair that passes the reference's leaf test: two boxes (pixel box, voxel box, fully
+ * occupied octree node) that the strict 15-axis FixedRotationBoxDisjoint does not separate
+ * (heightmap_solver_leaf-inl.h:33-68, octree2_solver_leaf-inl.h:85-404), or a box and a triangle with
+ * boxTriangleIntersect (heightmap_solver_leaf-inl.h:70-88, octree2_solver_leaf-inl.h:46-66).
+ *   out_counts[q]          = result.numContacts() = min(#leaf pairs hit, max_contacts)
+ *   out_b1/out_b2[q*max_keep + k] = Contact::b1 / b2 of the k-th stored contact (encodePixel,
+ *                            encodeOctree2Node, triangle id) or -1; both NULL = counts only
+ * Which contacts are the first max_keep follows the device traversal order, not the reference's. */
+int fclb_scene_pair_collide_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                       const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                       uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2);
+int fclb_scene_pair_collide_batch_dev(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                      const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                      uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2);
 /* node tests and leaf (shape-triangle / shape-pixel) tests of the most recent scene batch call */
 int fclb_scene_last_visit_counts(uint64_t* n_node, uint64_t* n_leaf);
 

@@ -160,4 +160,47 @@ struct ScenePenArgs {
 template <typename S>
 cudaError_t launchScenePenetration(const ScenePenArgs& a, cudaStream_t st);
 
+// scene-vs-scene pair traversal (fclb_scene_pair_impl.cuh, instantiated in fclb_scene_pair_f32/f64.cu)
+constexpr int kScenePairWarps = 2;
+struct HmView {           // LayeredHeightMap<S> on the device; layer 0 = bottom, layer k = k levels above it
+  const uint16_t* layers;
+  uint32_t off[16];       // element offset of layer k
+  uint16_t fx[16], fy[16];
+  int n_layers;
+  uint32_t half_x, half_y;  // bottom half shape
+  double res_x, res_y;      // bottom resolution (already rounded to S)
+};
+struct OctView {          // octree2::Octree<S> flat arrays (see OctreeArgs)
+  const uint32_t* children;
+  const uint8_t* inner_full;
+  const uint8_t* leaf_bits;
+  const uint8_t* pruned;
+  uint32_t n_inner, n_leaf;
+  int num_layers;
+  double root_box[6];
+};
+struct BvhView {
+  const void* nodes;
+  const void* tris;
+  int n_nodes;
+};
+struct ScenePairArgs {
+  int kind1, kind2;       // FCLB_SCENE_*; kind1 is a heightmap or an octree
+  HmView hm1, hm2;
+  OctView oct1, oct2;
+  BvhView bvh2;
+  const void* poses1;
+  const void* poses2;
+  size_t n;
+  uint32_t max_contacts;
+  uint32_t* counts;
+  uint32_t max_keep;
+  long long* out_b1;      // [n * max_keep] or nullptr
+  long long* out_b2;
+  unsigned long long* work_counter;
+  unsigned long long* stats;  // [0] node pairs tested, [1] leaf pairs tested, [2] stack overflows
+};
+template <typename S>
+cudaError_t launchScenePair(const ScenePairArgs& a, int grid, cudaStream_t st);
+
 }  // namespace fclb

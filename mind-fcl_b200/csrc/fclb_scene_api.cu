@@ -286,6 +286,105 @@ static int sceneContactsDev(Engine& e, int kind, fclb_handle scene, const ShapeT
   return FCLB_OK;
 }
 
+// fcl::collide between two scene geometries (heightmap / octree first, heightmap / octree / mesh second), boolean request
+static int fillHmView(const HeightmapDev* hm, int st, HmView& v) {
+  if (hm->off.size() > 16) return fail(FCLB_ERR_UNSUPPORTED, "scene pair: heightmap with more than 16 layers");
+  v.layers = hm->d_layers;
+  v.n_layers = int(hm->off.size());
+  for (size_t k = 0; k < hm->off.size(); k++) {
+    v.off[k] = uint32_t(hm->off[k]);
+    v.fx[k] = uint16_t(hm->fx[k]);
+    v.fy[k] = uint16_t(hm->fy[k]);
+  }
+  v.half_x = hm->half_x;
+  v.half_y = hm->half_y;
+  v.res_x = st == 0 ? double(float(hm->res_x)) : hm->res_x;
+  v.res_y = st == 0 ? double(float(hm->res_y)) : hm->res_y;
+  return FCLB_OK;
+}
+static void fillOctView(const OctreeDev* o, OctView& v) {
+  v.children = o->children;
+  v.inner_full = o->inner_full;
+  v.leaf_bits = o->leaf_bits;
+  v.pruned = o->pruned;
+  v.n_inner = o->n_inner;
+  v.n_leaf = o->n_leaf;
+  v.num_layers = o->num_layers;
+  for (int k = 0; k < 6; k++) v.root_box[k] = o->root_box[k];
+}
+
+template <typename S>
+static int scenePairDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                        const void* poses2, size_t n, const fclb_request* req, uint32_t max_keep, uint32_t* counts,
+                        long long* b1, long long* b2) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  ScenePairArgs a{};
+  a.kind1 = kind1;
+  a.kind2 = kind2;
+  size_t roots1 = 1, roots2 = 1;
+  for (int side = 0; side < 2; side++) {
+    const int kind = side == 0 ? kind1 : kind2;
+    const fclb_handle h = side == 0 ? scene1 : scene2;
+    if (kind == FCLB_SCENE_HEIGHTMAP) {
+      auto it = hmTable().find(h);
+      if (it == hmTable().end()) return fail(FCLB_ERR_BAD_ARG, "scene pair: unknown heightmap handle");
+      const int rc = fillHmView(it->second, st, side == 0 ? a.hm1 : a.hm2);
+      if (rc) return rc;
+      (side == 0 ? roots1 : roots2) = size_t(it->second->fx.back()) * it->second->fy.back();
+    } else if (kind == FCLB_SCENE_OCTREE) {
+      auto it = octTable().find(h);
+      if (it == octTable().end()) return fail(FCLB_ERR_BAD_ARG, "scene pair: unknown octree handle");
+      fillOctView(it->second, side == 0 ? a.oct1 : a.oct2);
+    } else if (kind == FCLB_SCENE_BVH && side == 1) {
+      auto it = bvhTable().find(h);
+      if (it == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "scene pair: unknown BVH handle");
+      if (it->second->scalar_type != st) return fail(FCLB_ERR_BAD_ARG, "BVH was uploaded for a different scalar type");
+      a.bvh2.nodes = it->second->nodes;
+      a.bvh2.tris = it->second->tris;
+      a.bvh2.n_nodes = it->second->n_nodes;
+    } else {
+      return fail(FCLB_ERR_UNSUPPORTED, "scene pair: supported pairs are heightmap-{heightmap, mesh, octree} and "
+                                        "octree-{mesh, octree}, in this argument order");
+    }
+  }
+  if (kind1 == FCLB_SCENE_OCTREE && kind2 == FCLB_SCENE_HEIGHTMAP)
+    return fail(FCLB_ERR_UNSUPPORTED, "scene pair: pass the heightmap first (heightMapOctreeIntersect)");
+  if (roots1 * roots2 > 256)
+    return fail(FCLB_ERR_CAPACITY, "scene pair: more than 256 top-layer pixel pairs (strongly non-square heightmaps)");
+  if (!g_counters) FCLB_CUDA(cudaMalloc(&g_counters, 4 * sizeof(unsigned long long)));
+  FCLB_CUDA(cudaMemsetAsync(g_counters, 0, 4 * sizeof(unsigned long long), e.compute));
+  a.poses1 = poses1;
+  a.poses2 = poses2;
+  a.n = n;
+  a.max_contacts = req->max_contacts;
+  a.counts = counts;
+  a.max_keep = b1 ? max_keep : 0;
+  a.out_b1 = b1;
+  a.out_b2 = b2;
+  a.work_counter = g_counters;
+  a.stats = g_counters + 1;
+  const size_t need = (n + kScenePairWarps - 1) / kScenePairWarps;
+  const size_t cap = size_t(e.sms) * 4;
+  const int grid = int(need < cap ? need : cap);
+  FCLB_CUDA(cudaEventRecord(e.ev_call0, e.compute));
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  FCLB_CUDA(launchScenePair<S>(a, grid, e.compute));
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  e.launches += 1;
+  FCLB_CUDA(cudaMemcpyAsync(g_stats, g_counters + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  if (g_stats[2]) return fail(FCLB_ERR_CAPACITY, "scene pair traversal: hierarchy deeper than the per-warp stack allows");
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.last_ms = ms;
+  e.last_call_ms = ms;
+  e.n_rec = 1;
+  e.rec_kind[0] = -5;
+  e.rec_count[0] = n;
+  e.rec_ms[0] = ms;
+  return FCLB_OK;
+}
+
 // FlatHeightMap<S>::updateHeightsByPointGenerationFunctor (flat_heightmap-inl.h:249-272)
 template <typename S>
 static void heightsFromPoints(const double* pts, size_t n, S res_x, S res_y, uint32_t half_x, uint32_t half_y,
@@ -704,6 +803,66 @@ int fclb_scene_shape_contacts_batch_host(int scene_kind, fclb_handle scene, fclb
   FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaMemcpyAsync(out_b1, base + o_b1, n * size_t(max_keep) * 8, cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaMemcpyAsync(out_contacts, base + o_ct, n * size_t(max_keep) * 7 * ss, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+int fclb_scene_pair_collide_batch_dev(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                      const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                      uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (!req || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null request / out_counts");
+  if ((out_b1 == nullptr) != (out_b2 == nullptr) || (out_b1 && max_keep == 0))
+    return fail(FCLB_ERR_BAD_ARG, "out_b1 / out_b2 go together and need max_keep > 0");
+  if (req->penetration_mode != FCLB_PEN_DISABLED)
+    return fail(FCLB_ERR_UNSUPPORTED, "scene-pair contact generation (penetration modes) is not on the device yet");
+  if (n == 0) return FCLB_OK;
+  if (!poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null pose array");
+  if (scalar_type == FCLB_F32)
+    return scenePairDev<float>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, req, max_keep, out_counts,
+                               reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2));
+  return scenePairDev<double>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, req, max_keep, out_counts,
+                              reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2));
+}
+
+int fclb_scene_pair_collide_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                       const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                       uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!poses1 || !poses2 || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t keep = out_b1 ? size_t(max_keep) : 0;
+  const size_t o_p1 = 0;
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_b1 = alignUp(o_cnt + n * 4, 256);
+  const size_t o_b2 = alignUp(o_b1 + n * keep * 8, 256);
+  const size_t total = alignUp(o_b2 + n * keep * 8, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  if (keep) FCLB_CUDA(cudaMemsetAsync(base + o_b1, 0xff, o_b2 + n * keep * 8 - o_b1, e.compute));
+  rc = fclb_scene_pair_collide_batch_dev(kind1, scene1, kind2, scene2, base + o_p1, base + o_p2, n, scalar_type, req, max_keep,
+                                         reinterpret_cast<uint32_t*>(base + o_cnt),
+                                         keep ? reinterpret_cast<int64_t*>(base + o_b1) : nullptr,
+                                         keep ? reinterpret_cast<int64_t*>(base + o_b2) : nullptr);
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  if (keep) {
+    FCLB_CUDA(cudaMemcpyAsync(out_b1, base + o_b1, n * keep * 8, cudaMemcpyDeviceToHost, e.compute));
+    FCLB_CUDA(cudaMemcpyAsync(out_b2, base + o_b2, n * keep * 8, cudaMemcpyDeviceToHost, e.compute));
+  }
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }

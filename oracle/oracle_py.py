@@ -322,6 +322,20 @@ class RefOracle(_Oracle):
           _p(poses_shape), n, C.cast(C.pointer(r), C.c_void_p), max_keep, _p(counts), _p(b1), _p(contacts), threads)
         return counts, b1, contacts
 
+    # ---- scene vs scene (heightmap / octree / mesh pairs) ----
+    def scene_pair_collide_batch(self, kind1, id1, kind2, id2, poses1, poses2, max_keep, threads=1, **req):
+        n = len(poses1)
+        counts = np.zeros(n, np.uint32)
+        b1 = np.zeros((n, max_keep), np.int64)
+        b2 = np.zeros((n, max_keep), np.int64)
+        r = _request(**req)
+        f = self.fn("scene_pair_collide_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(poses1.dtype), kind1, id1, kind2, id2, _p(poses1), _p(poses2), n, C.cast(C.pointer(r), C.c_void_p), max_keep,
+          _p(counts), _p(b1), _p(b2), threads)
+        return counts, b1, b2
+
     # ---- broadphase ----
     def compute_aabb_batch(self, shapes, shape_ids, poses):
         ids = np.ascontiguousarray(shape_ids, np.uint32)

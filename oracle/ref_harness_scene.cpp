@@ -251,6 +251,31 @@ void sceneContactsBatch(const fcl::CollisionGeometry<S>* scene, const ShapeRec* 
   });
 }
 
+// every contact of a scene-vs-scene query: counts + (b1, b2) of the first max_keep contacts
+template <typename S>
+void scenePairBatch(const fcl::CollisionGeometry<S>* g1, const fcl::CollisionGeometry<S>* g2, const S* poses1,
+                    const S* poses2, size_t n, const RequestRec* rq, uint32_t max_keep, uint32_t* counts, int64_t* b1,
+                    int64_t* b2, int threads) {
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    const fcl::CollisionRequest<S> req = makeRequest<S>(rq);
+    for (size_t q = b; q < e; q++) {
+      fcl::CollisionResult<S> res;
+      const size_t c = fcl::collide<S>(g1, loadPose<S>(poses1 + 12 * q), g2, loadPose<S>(poses2 + 12 * q), req, res);
+      counts[q] = uint32_t(c);
+      for (uint32_t k = 0; k < max_keep; k++) {
+        b1[q * max_keep + k] = k < c ? int64_t(res.getContact(k).b1) : -1;
+        b2[q * max_keep + k] = k < c ? int64_t(res.getContact(k).b2) : -1;
+      }
+    }
+  });
+}
+template <typename S>
+const fcl::CollisionGeometry<S>* sceneGeom(int kind, int id) {
+  return kind == 0   ? (const fcl::CollisionGeometry<S>*)Sel<S>::mesh(id)
+         : kind == 1 ? (const fcl::CollisionGeometry<S>*)getHm<S>(id)
+                     : (const fcl::CollisionGeometry<S>*)getOct<S>(id);
+}
+
 // ---- broadphase -----------------------------------------------------------------------
 template <typename S>
 struct TreeRec {
@@ -445,6 +470,19 @@ int fclref_scene_shape_contacts_batch(int scalar_type, int kind, int scene_id, c
                                (const double*)poses_shape, n, (const RequestRec*)request, max_keep, counts, b1,
                                (double*)contacts, threads);
   }
+  return 0;
+}
+
+/* fcl::collide between two scene geometries; kind: 0 mesh (BVHModel<OBBRSS>), 1 heightmap, 2 octree */
+int fclref_scene_pair_collide_batch(int scalar_type, int kind1, int id1, int kind2, int id2, const void* poses1,
+                                    const void* poses2, size_t n, const void* request, uint32_t max_keep, uint32_t* counts,
+                                    int64_t* b1, int64_t* b2, int threads) {
+  if (scalar_type == 0)
+    scenePairBatch<float>(sceneGeom<float>(kind1, id1), sceneGeom<float>(kind2, id2), (const float*)poses1,
+                          (const float*)poses2, n, (const RequestRec*)request, max_keep, counts, b1, b2, threads);
+  else
+    scenePairBatch<double>(sceneGeom<double>(kind1, id1), sceneGeom<double>(kind2, id2), (const double*)poses1,
+                           (const double*)poses2, n, (const RequestRec*)request, max_keep, counts, b1, b2, threads);
   return 0;
 }
 
