@@ -318,7 +318,9 @@ int fclb_scene_shape_contacts_batch_dev(int scene_kind, fclb_handle scene, fclb_
  * boxTriangleIntersect (heightmap_solver_leaf-inl.h:70-88, octree2_solver_leaf-inl.h:46-66).
  *   out_counts[q]          = result.numContacts() = min(#leaf pairs hit, max_contacts)
  *   out_b1/out_b2[q*max_keep + k] = Contact::b1 / b2 of the k-th stored contact (encodePixel,
- *                            encodeOctree2Node, triangle id) or -1; both NULL = counts only
+ *                            encodeOctree2Node, triangle id; the octree side of a (HEIGHTMAP, OCTREE)
+ *                            contact is the bare node_vector_index, as in the reference) or -1;
+ *                            both NULL = counts only
  * Which contacts are the first max_keep follows the device traversal order, not the reference's. */
 int fclb_scene_pair_collide_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                                        const void* poses2, size_t n, int scalar_type, const fclb_request* req,

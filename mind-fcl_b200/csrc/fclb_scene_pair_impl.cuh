@@ -308,7 +308,12 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
             const V3<S> h = mk<S>(S(0.5) * side.x, S(0.5) * side.y, S(0.5) * side.z);
             hit = boxTriangleOverlap(h, apply(toshape0, P[0]), apply(toshape0, P[1]), apply(toshape0, P[2]));
           } else {
-            c2 = SB::type::code(el.b);
+            // heightMapOctreeIntersect names the octree side by its bare node_vector_index
+            // (heightmap_solver_traverse-inl.h:489-512), the octree solvers by encodeOctree2Node
+            if constexpr (KA == FCLB_SCENE_HEIGHTMAP && KB == FCLB_SCENE_OCTREE)
+              c2 = (long long)el.b.index;
+            else
+              c2 = SB::type::code(el.b);
             hit = !fixedRotDisjointBoxes(fr, el.a.mn, el.a.mx, el.b.mn, el.b.mx, true);
           }
         }

@@ -7,7 +7,7 @@ reference on the same structures, for the five non-convex pairs of the collision
     octree-mesh           octreeBVHIntersect       (octree2_solver_traverse-inl.h:138)
     octree-octree         octreePairIntersect      (:290)
 Checked per query: the boolean (max_contacts = 1), the capped count (max_contacts = 3), the contact
-count with all contacts requested, and -- for every query whose contacts fit the kept list -- the SET of
+count with all contacts requested, and -- for every query whose contacts fit the kept list -- the multiset of
 (b1, b2) contact ids (encodePixel / encodeOctree2Node / triangle id).  Contact order follows the device
 traversal and is not compared.  float and double."""
 import numpy as np
@@ -65,10 +65,11 @@ def check_pair(fclb, ref_oracle, name, dtype, k1, ref1, dev1, k2, ref2, dev2, p1
         if mc > 3:
             n_sets = 0
             for q in np.nonzero((counts > 0) & (counts <= keep))[0]:
-                got = set(zip(b1[q, :counts[q]].tolist(), b2[q, :counts[q]].tolist()))
-                exp = set(zip(e_b1[q, :counts[q]].tolist(), e_b2[q, :counts[q]].tolist()))
-                assert len(got) == counts[q], (name, q, "duplicate contact ids")
-                assert got == exp, (name, q, sorted(got ^ exp)[:6])
+                # (a heightmap-octree contact names the octree side by its node index only, so the voxels of one
+                # partial leaf repeat an id pair: compare multisets)
+                got = sorted(zip(b1[q, :counts[q]].tolist(), b2[q, :counts[q]].tolist()))
+                exp = sorted(zip(e_b1[q, :counts[q]].tolist(), e_b2[q, :counts[q]].tolist()))
+                assert got == exp, (name, q, sorted(set(got) ^ set(exp))[:6])
                 n_sets += 1
             print(f"    contact-id sets identical for {n_sets} queries")
             assert n_sets > 0
