@@ -526,6 +526,43 @@ void collideBatch(const std::vector<CollisionQuery<S>>& queries, const Collision
       Q.tf1.toPose12(&p1[p1.size() - 12]);
       Q.tf2.toPose12(&p2[p2.size() - 12]);
       shape_q.push_back(q);
+    } else if (!Q.o1->isShape() && !Q.o2->isShape() &&
+               !(Q.o1->getNodeType() == BV_OBBRSS && Q.o2->getNodeType() == BV_OBBRSS)) {
+      // heightmap / octree against heightmap / octree / mesh: HeightMapPairCollide, HeightMapBVHCollide,
+      // HeightMapOctree2Collide, OcTree2BVHCollide, OcTree2Collide and their argument-swapped entries
+      // (collision_func_matrix-inl.h:794-812, 835-856).  The swapped entries run the same solver with the
+      // heightmap (resp. octree) first and keep that orientation in the contacts.
+      auto kindOf = [](const CollisionGeometry<S>* g) {
+        return g->getNodeType() == BV_OBBRSS ? FCLB_SCENE_BVH : (g->getNodeType() == GEOM_HEIGHTMAP ? FCLB_SCENE_HEIGHTMAP : FCLB_SCENE_OCTREE);
+      };
+      auto handleOf = [](const CollisionGeometry<S>* g) -> fclb_handle {
+        if (g->getNodeType() == BV_OBBRSS) return static_cast<const BVHModel<OBBRSS<S>>*>(g)->handle();
+        if (g->getNodeType() == GEOM_HEIGHTMAP) return static_cast<const HeightMapCollisionGeometry<S>*>(g)->handle();
+        return static_cast<const Octree2CollisionGeometry<S>*>(g)->handle();
+      };
+      const int k1 = kindOf(Q.o1), k2 = kindOf(Q.o2);
+      // canonical order of the device entry point: heightmap before octree before mesh
+      auto rank = [](int k) { return k == FCLB_SCENE_HEIGHTMAP ? 0 : (k == FCLB_SCENE_OCTREE ? 1 : 2); };
+      const bool swap = rank(k1) > rank(k2);
+      const CollisionGeometry<S>* g1 = swap ? Q.o2 : Q.o1;
+      const CollisionGeometry<S>* g2 = swap ? Q.o1 : Q.o2;
+      S a[12], b[12];
+      (swap ? Q.tf2 : Q.tf1).toPose12(a);
+      (swap ? Q.tf1 : Q.tf2).toPose12(b);
+      constexpr uint32_t kKeep = 64;
+      uint32_t count = 0;
+      int64_t ids1[kKeep], ids2[kKeep];
+      detail::check(fclb_scene_pair_collide_batch_host(kindOf(g1), handleOf(g1), kindOf(g2), handleOf(g2), a, b, 1,
+                                                       detail::scalarType<S>(), &req, kKeep, &count, ids1, ids2),
+                    "fclb_scene_pair_collide_batch_host");
+      for (uint32_t c = 0; c < count && c < kKeep; c++) {
+        Contact<S> ct;
+        ct.o1 = g1;
+        ct.o2 = g2;
+        ct.b1 = intptr_t(ids1[c]);
+        ct.b2 = intptr_t(ids2[c]);
+        results[q].addContact(ct);
+      }
     } else if (!Q.o1->isShape() && !Q.o2->isShape()) {
       const auto* m1 = static_cast<const BVHModel<OBBRSS<S>>*>(Q.o1);
       const auto* m2 = static_cast<const BVHModel<OBBRSS<S>>*>(Q.o2);

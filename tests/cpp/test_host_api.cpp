@@ -141,6 +141,22 @@ void runScene() {
     EXPECT_TRUE(on.numContacts() == 1 && on.getContact(0).b1 == ((8 << 16) | 8));  // encodePixel(x=8, y=8)
     EXPECT_TRUE(collide<S>(&hm, I, &box, at(S(0.05), S(0.05), S(0.6)), req, over) == 0);
     EXPECT_TRUE(collide<S>(&hm, I, &box, at(S(-0.3), S(0.05), S(0.3)), req, off) == 0);
+    // heightmap vs mesh (HeightMapBVHCollide / BVHHeightMapCollide): a 2 x 2 m sheet cutting the four columns at
+    // half height; shifted so that all four lie on the sheet's second triangle
+    BVHModel<OBBRSS<S>> sheet;
+    sheet.beginModel();
+    sheet.addSubModel({Vector3<S>(-1, -1, 0), Vector3<S>(1, -1, 0), Vector3<S>(1, 1, 0), Vector3<S>(-1, 1, 0)},
+                      {{0, 1, 2}, {0, 2, 3}});
+    sheet.endModel();
+    CollisionResult<S> cut, swapped, above;
+    EXPECT_TRUE(collide<S>(&hm, I, &sheet, at(0, S(-0.5), S(0.25)), req, cut) == 4);
+    for (std::size_t c = 0; c < cut.numContacts(); c++) {
+      const auto& ct = cut.getContact(c);
+      EXPECT_TRUE(ct.b2 == 1 && (ct.b1 >> 16) >= 8 && (ct.b1 >> 16) <= 11 && (ct.b1 & 0xffff) == 8);
+    }
+    EXPECT_TRUE(collide<S>(&sheet, at(0, S(-0.5), S(0.25)), &hm, I, req, swapped) == 4);
+    EXPECT_TRUE(swapped.numContacts() == 4 && swapped.getContact(0).o1 == &hm);
+    EXPECT_TRUE(collide<S>(&hm, I, &sheet, at(0, S(-0.5), S(0.6)), req, above) == 0);
   }
   {
     // directed penetration: two unit spheres 1.5 apart along x, escape direction +x => depth 0.5
