@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kEpaThreads) epaKernel(BatchView b, S tol, int
   uint32_t w = 0;
   MinkDiff<S, T0, T1> md;
   Pose<S> tf1;
-  EpaWarp<S, MinkDiff<S, T0, T1>, T> epa(md, poly_mem, pool_faces, warp_lane, nullptr);
+  EpaWarp<S, MinkDiff<S, T0, T1>, T> epa(md, poly_mem, pool_faces, defer.enabled != 0, warp_lane, nullptr);
   S depth = S(0);
   V3<S> p0 = zero3<S>(), p1 = zero3<S>();
   auto finish = [&](int es) {

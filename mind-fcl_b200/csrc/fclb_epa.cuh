@@ -171,18 +171,29 @@ struct PolyStore {
   S* f_d;
   uint8_t *f_alive, *f_in, *f_vis;  // vis: 0 unknown, 1 visible(in patch), 2 hidden, 3 "outside" but not reached
 
-  static __host__ __device__ size_t bytes(int max_faces) {
-    const size_t f = size_t(max_faces), v = size_t(1.51 * double(max_faces)), e = v;
+  // scratch of the parallel cone construction (expand): three lists of edge slots / vertices
+  uint16_t *e_tmp0, *e_tmp1, *e_tmp2;
+
+  // vertices: the reference's pool has floor(1.51 F) slots, but a closed triangulated polytope with E <= 1.51 F
+  // edges has V = (E + 6) / 3 <= F / 2 + 2 vertices.  The first-tier pool (compact_v) is sized for that; running out
+  // of it reports MallocFailed, which defers the query to the full-capacity tier like any other exhausted pool.
+  static __host__ __device__ int vertexCap(int max_faces, bool compact_v) {
+    const int full = int(1.51 * double(max_faces));
+    const int small = max_faces / 2 + 4;
+    return (compact_v && small < full) ? small : full;
+  }
+  static __host__ __device__ size_t bytes(int max_faces, bool compact_v) {
+    const size_t f = size_t(max_faces), v = size_t(vertexCap(max_faces, compact_v)), e = size_t(1.51 * double(max_faces));
     size_t b = 0;
     b += 7 * v * sizeof(S) + e * sizeof(S) + f * sizeof(S);
-    b += (2 * v + 5 * e + 7 * f) * sizeof(uint16_t);
+    b += (2 * v + 8 * e + 7 * f) * sizeof(uint16_t);
     b += 2 * v + 3 * e + 3 * f;
     return (b + 15) / 16 * 16;
   }
-  FCLB_DI void bind(unsigned char* base, int max_faces) {
+  FCLB_DI void bind(unsigned char* base, int max_faces, bool compact_v) {
     fcap = max_faces;
-    vcap = int(1.51 * double(max_faces));
-    ecap = vcap;
+    vcap = vertexCap(max_faces, compact_v);
+    ecap = int(1.51 * double(max_faces));
     S* ps = reinterpret_cast<S*>(base);
     vx = ps; ps += vcap;
     vy = ps; ps += vcap;
@@ -201,6 +212,9 @@ struct PolyStore {
     e_f0 = p16; p16 += ecap;
     e_f1 = p16; p16 += ecap;
     e_seq = p16; p16 += ecap;
+    e_tmp0 = p16; p16 += ecap;
+    e_tmp1 = p16; p16 += ecap;
+    e_tmp2 = p16; p16 += ecap;
     f_e0 = p16; p16 += fcap;
     f_e1 = p16; p16 += fcap;
     f_e2 = p16; p16 += fcap;
@@ -245,13 +259,13 @@ struct EpaWarp {
   int v_sq, e_sq, f_sq;     // next sequence numbers
   uint32_t* n_support;
 
-  FCLB_DI EpaWarp(const MD& sh, unsigned char* smem, int max_faces, int warp_lane, uint32_t* ns)
+  FCLB_DI EpaWarp(const MD& sh, unsigned char* smem, int max_faces, bool compact_v, int warp_lane, uint32_t* ns)
       : shape(sh),
         lane(warp_lane % T),
         tmask(T == 32 ? 0xffffffffu : (((1u << T) - 1u) << ((warp_lane / T) * T))),
         tshift((warp_lane / T) * T),
         n_support(ns) {
-    P.bind(smem, max_faces);
+    P.bind(smem, max_faces, compact_v);
   }
   // tile-scoped collectives
   FCLB_DI void sync() const { __syncwarp(tmask); }
@@ -300,6 +314,25 @@ struct EpaWarp {
       if (m) return base + __ffs(m) - 1;
     }
     return -1;
+  }
+
+  // `need` free slots of a pool into out[0 .. need): fresh slots first, then dead ones in ascending order
+  // (slot identity is unobservable).  The caller has checked that the pool has that many free slots.
+  FCLB_DI void gatherFree(const uint8_t* alive, int cap, int& hw, int need, uint16_t* out) const {
+    const int old_hw = hw;
+    const int fresh = need < cap - old_hw ? need : cap - old_hw;
+    for (int j = lane; j < fresh; j += T) out[j] = uint16_t(old_hw + j);
+    hw = old_hw + fresh;
+    int got = fresh;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < old_hw && got < need; base += T) {
+      const int i = base + lane;
+      const bool pred = i < old_hw && !alive[i];
+      const unsigned mask = ballot(pred);
+      const int pos = got + __popc(mask & lt);
+      if (pred && pos < need) out[pos] = uint16_t(i);
+      got += __popc(mask);
+    }
   }
 
   // AddNewVertex (epa_polytope.hpp:185-209)
@@ -383,34 +416,80 @@ struct EpaWarp {
     P.f_in[s] = md.in_simplex ? 1 : 0;
   }
 
-  // formNewTetrahedronPolytope (epa_simplex2polytope.hpp:177-215)
-  FCLB_DI bool formTetrahedron(const V3<S> v[4], const V3<S> d[4]) {
-    reset();
-    int vi[4];
-    for (int k = 0; k < 4; k++) vi[k] = addVertex(v[k], d[k]);
-    int e[6];
-    e[0] = addEdgeTopo(vi[0], vi[1]);
-    e[1] = addEdgeTopo(vi[1], vi[2]);
-    e[2] = addEdgeTopo(vi[2], vi[0]);
-    e[3] = addEdgeTopo(vi[3], vi[0]);
-    e[4] = addEdgeTopo(vi[3], vi[1]);
-    e[5] = addEdgeTopo(vi[3], vi[2]);
-    int f[4];
-    f[0] = addFaceTopo(e[0], e[1], e[2]);
-    f[1] = addFaceTopo(e[3], e[4], e[0]);
-    f[2] = addFaceTopo(e[4], e[5], e[1]);
-    f[3] = addFaceTopo(e[5], e[3], e[2]);
-    for (int k = lane; k < 10; k += T) {
-      if (k < 6) {
-        if (e[k] >= 0) fillEdge(e[k]);
-      } else if (f[k - 6] >= 0) {
-        fillFace(f[k - 6]);
-      }
+  // The two initial polytopes (formNewTetrahedronPolytope, epa_simplex2polytope.hpp:177-215, and the hexahedron
+  // of simplexToPolytope2, :300-380) are fixed sequences of AddNewVertex / AddNewEdge / AddNewFace on EMPTY pools,
+  // so the k-th vertex / edge / face lands in slot k with sequence number k, an edge's faces_of_edge[0 / 1] are the
+  // first / second face of the sequence that names it, and a face's vertices follow from its first two edges
+  // (epa_polytope.hpp:243-290).  The tiles write the whole structure in one parallel pass from these tables
+  // (4 bits per entry) instead of 14 / 26 serial allocations.
+  //   ev0 / ev1: vertices of edge k;  fe0 / fe1 / fe2: edges of face k
+  template <int NV>
+  FCLB_DI bool buildFromTables(const V3<S> (&v)[NV], const V3<S> (&d)[NV], int ne, int nf, unsigned long long ev0,
+                               unsigned long long ev1, unsigned long long fe0, unsigned long long fe1,
+                               unsigned long long fe2) {
+    // a pool too small for the sequence fails one of the reference's allocations => "Failed"
+    if (P.vcap < NV || P.ecap < ne || P.fcap < nf) return false;
+    auto nib = [](unsigned long long t, int k) { return int((t >> (4 * k)) & 0xfull); };
+    for (int k = lane; k < NV; k += T) {
+      V3<S> vv = v[0], dd = d[0];
+#pragma unroll
+      for (int j = 1; j < NV; j++)
+        if (j == k) {
+          vv = v[j];
+          dd = d[j];
+        }
+      P.vx[k] = vv.x; P.vy[k] = vv.y; P.vz[k] = vv.z;
+      P.dx[k] = dd.x; P.dy[k] = dd.y; P.dz[k] = dd.z;
+      P.vd[k] = sqnorm(vv);
+      P.v_seq[k] = uint16_t(k);
+      P.v_alive[k] = 1;
+    }
+    for (int k = lane; k < ne; k += T) {
+      P.e_v0[k] = uint16_t(nib(ev0, k));
+      P.e_v1[k] = uint16_t(nib(ev1, k));
+      int f0 = kNil, f1 = kNil;
+      for (int f = nf - 1; f >= 0; f--)
+        if (nib(fe0, f) == k || nib(fe1, f) == k || nib(fe2, f) == k) {
+          f1 = f0;
+          f0 = f;
+        }
+      P.e_f0[k] = uint16_t(f0);
+      P.e_f1[k] = uint16_t(f1);
+      P.e_seq[k] = uint16_t(k);
+      P.e_alive[k] = 1;
+      P.e_vis[k] = 0;
+    }
+    for (int k = lane; k < nf; k += T) {
+      const int e1 = nib(fe0, k), e2 = nib(fe1, k), e3 = nib(fe2, k);
+      const int a = nib(ev0, e1), b = nib(ev1, e1);
+      const int c = (nib(ev0, e2) != a && nib(ev0, e2) != b) ? nib(ev0, e2) : nib(ev1, e2);
+      P.f_e0[k] = uint16_t(e1);
+      P.f_e1[k] = uint16_t(e2);
+      P.f_e2[k] = uint16_t(e3);
+      P.f_a[k] = uint16_t(a);
+      P.f_b[k] = uint16_t(b);
+      P.f_c[k] = uint16_t(c);
+      P.f_seq[k] = uint16_t(k);
+      P.f_alive[k] = 1;
+      P.f_vis[k] = 0;
+    }
+    v_hw = v_n = v_sq = NV;
+    e_hw = e_n = e_sq = ne;
+    f_hw = f_n = f_sq = nf;
+    sync();
+    for (int k = lane; k < ne + nf; k += T) {
+      if (k < ne)
+        fillEdge(k);
+      else
+        fillFace(k - ne);
     }
     sync();
-    for (int k = 0; k < 4; k++)
-      if (f[k] < 0) return false;
     return true;
+  }
+  // formNewTetrahedronPolytope (epa_simplex2polytope.hpp:177-215): edges (0,1) (1,2) (2,0) (3,0) (3,1) (3,2),
+  // faces (e0,e1,e2) (e3,e4,e0) (e4,e5,e1) (e5,e3,e2)
+  FCLB_DI bool formTetrahedron(const V3<S> (&v)[4], const V3<S> (&d)[4]) {
+    return buildFromTables<4>(v, d, 6, 4, 0x333210ull, 0x210021ull, 0x5430ull, 0x3541ull, 0x2102ull);
   }
 
   // extractTouchingPoint (epa_simplex2polytope.hpp:11-43)
@@ -422,9 +501,10 @@ struct EpaWarp {
     p1 = mid;
   }
 
-  // simplexToPolytope3 (epa_simplex2polytope.hpp:135-175); 0 OK, 1 Touching, 2 Failed
-  FCLB_DI int simplexToPolytope3(const V3<S>& a, const V3<S>& da, const V3<S>& b, const V3<S>& db, const V3<S>& c,
-                                 const V3<S>& dc, S thr, V3<S>& p0, V3<S>& p1) {
+  // simplexToPolytope3 (epa_simplex2polytope.hpp:135-175): 1 Touching, 2 Failed, 3 = the tetrahedron to form is
+  // (v[0..2], fourth vertex written to v[3] / d[3])
+  FCLB_DI int simplexToPolytope3(V3<S> (&v)[4], V3<S> (&d)[4], S thr, V3<S>& p0, V3<S>& p1) {
+    const V3<S> a = v[0], b = v[1], c = v[2];
     const V3<S> ab = b - a, ac = c - a;
     V3<S> n = cross(ab, ac);
     if (sqnorm(n) <= S(0)) return 2;
@@ -442,13 +522,14 @@ struct EpaWarp {
       touchingPoint(dir1, p0, p1);
       return 1;
     }
-    V3<S> v[4] = {a, b, c, d0};
-    V3<S> d[4] = {da, db, dc, dir0};
-    if (!(d0_to_plane > d1_to_plane)) {
+    if (d0_to_plane > d1_to_plane) {
+      v[3] = d0;
+      d[3] = dir0;
+    } else {
       v[3] = d1;
       d[3] = dir1;
     }
-    return formTetrahedron(v, d) ? 0 : 2;
+    return 3;
   }
 
   // simplexToPolytope2 (epa_simplex2polytope.hpp:218-380)
@@ -511,47 +592,14 @@ struct EpaWarp {
       touchingPoint(dir3, p0, p1);
       return 1;
     }
-    reset();
-    int v[6];
-    v[0] = addVertex(a, da);
-    v[1] = addVertex(v0, dir0);
-    v[2] = addVertex(b, db);
-    v[3] = addVertex(v1, dir1);
-    v[4] = addVertex(v2, dir2);
-    v[5] = addVertex(v3, dir3);
-    int e[12];
-    e[0] = addEdgeTopo(v[0], v[1]);
-    e[1] = addEdgeTopo(v[1], v[2]);
-    e[2] = addEdgeTopo(v[2], v[3]);
-    e[3] = addEdgeTopo(v[3], v[0]);
-    e[4] = addEdgeTopo(v[4], v[0]);
-    e[5] = addEdgeTopo(v[4], v[1]);
-    e[6] = addEdgeTopo(v[4], v[2]);
-    e[7] = addEdgeTopo(v[4], v[3]);
-    e[8] = addEdgeTopo(v[5], v[0]);
-    e[9] = addEdgeTopo(v[5], v[1]);
-    e[10] = addEdgeTopo(v[5], v[2]);
-    e[11] = addEdgeTopo(v[5], v[3]);
-    int f[8];
-    f[0] = addFaceTopo(e[4], e[5], e[0]);
-    f[1] = addFaceTopo(e[5], e[6], e[1]);
-    f[2] = addFaceTopo(e[6], e[7], e[2]);
-    f[3] = addFaceTopo(e[7], e[4], e[3]);
-    f[4] = addFaceTopo(e[8], e[9], e[0]);
-    f[5] = addFaceTopo(e[9], e[10], e[1]);
-    f[6] = addFaceTopo(e[10], e[11], e[2]);
-    f[7] = addFaceTopo(e[11], e[8], e[3]);
-    for (int k = lane; k < 20; k += T) {
-      if (k < 12) {
-        if (e[k] >= 0) fillEdge(e[k]);
-      } else if (f[k - 12] >= 0) {
-        fillFace(f[k - 12]);
-      }
-    }
-    sync();
-    for (int k = 0; k < 8; k++)
-      if (f[k] < 0) return 2;
-    return 0;
+    // vertices a, v0, b, v1, v2, v3; edges (0,1) (1,2) (2,3) (3,0) (4,0) (4,1) (4,2) (4,3) (5,0) (5,1) (5,2) (5,3);
+    // faces (e4,e5,e0) (e5,e6,e1) (e6,e7,e2) (e7,e4,e3) (e8,e9,e0) (e9,e10,e1) (e10,e11,e2) (e11,e8,e3)  (:300-380)
+    const V3<S> pv[6] = {a, v0, b, v1, v2, v3};
+    const V3<S> pd[6] = {da, dir0, db, dir1, dir2, dir3};
+    return buildFromTables<6>(pv, pd, 12, 8, 0x555544443210ull, 0x321032100321ull, 0xba987654ull, 0x8ba94765ull,
+                              0x32103210ull)
+               ? 0
+               : 2;
   }
 
   // simplexToPolytope (epa_simplex2polytope.hpp:46-133)
@@ -572,6 +620,7 @@ struct EpaWarp {
         return 1;
       }
     }
+    int mode = sx.rank;  // 4: tetrahedron in v/d, 3: triangle in v[0..2], 2: segment, 1: point
     if (sx.rank == 4) {  // simplexToPolytope4 :96-133
       // the four faces are tried in the order abc, acd, abd, bcd; the first one
       // whose plane passes (almost) through the origin reduces to the triangle case
@@ -581,17 +630,21 @@ struct EpaWarp {
 #pragma unroll 1
       for (int k = 0; k < 4 && sel < 0; k++)
         if (pointToPlaneDistance(o, v[tri[k][0]], v[tri[k][1]], v[tri[k][2]]) < thr) sel = k;
-      if (sel < 0) return formTetrahedron(v, d) ? 0 : 2;
-      const int i0 = tri[sel][0], i1 = tri[sel][1], i2 = tri[sel][2];
-      const V3<S> ta = v[i0], tb = v[i1], tc = v[i2], tda = d[i0], tdb = d[i1], tdc = d[i2];
-      v[0] = ta; v[1] = tb; v[2] = tc;
-      d[0] = tda; d[1] = tdb; d[2] = tdc;
-      return simplexToPolytope3(v[0], d[0], v[1], d[1], v[2], d[2], thr, p0, p1);
-    } else if (sx.rank == 3) {
-      return simplexToPolytope3(v[0], d[0], v[1], d[1], v[2], d[2], thr, p0, p1);
-    } else if (sx.rank == 2) {
-      return simplexToPolytope2(v[0], d[0], v[1], d[1], thr, p0, p1);
+      if (sel >= 0) {
+        const int i0 = tri[sel][0], i1 = tri[sel][1], i2 = tri[sel][2];
+        const V3<S> ta = v[i0], tb = v[i1], tc = v[i2], tda = d[i0], tdb = d[i1], tdc = d[i2];
+        v[0] = ta; v[1] = tb; v[2] = tc;
+        d[0] = tda; d[1] = tdb; d[2] = tdc;
+        mode = 3;
+      }
     }
+    if (mode == 3) {
+      const int r = simplexToPolytope3(v, d, thr, p0, p1);
+      if (r != 3) return r;
+      mode = 4;
+    }
+    if (mode == 4) return formTetrahedron(v, d) ? 0 : 2;
+    if (mode == 2) return simplexToPolytope2(v[0], d[0], v[1], d[1], thr, p0, p1);
     supportBoth(d[0], p0, p1);
     return 1;
   }
@@ -821,80 +874,115 @@ struct EpaWarp {
     const int new_v = addVertex(nv, nd);
     if (new_v < 0) return 2;
 
-    // border edges in list order (newest first): repeatedly take the alive border
-    // edge with the largest sequence number below the previous one
-    bool ok = true;
-    int prev_seq = 0x7fffffff;
-    int first_new_e = -1, first_new_f = -1;
-    int made_e[2];
-    while (true) {
-      int best_seq = -1, best_idx = -1;
-      for (int i = lane; i < e_hw; i += T) {
-        if (P.e_alive[i] && P.e_vis[i] == 1) {
-          const int sq = P.e_seq[i];
-          if (sq < prev_seq && sq > best_seq) {
-            best_seq = sq;
-            best_idx = i;
-          }
-        }
-      }
-#pragma unroll
-      for (int off = T / 2; off > 0; off >>= 1) {
-        const int os = shflXor(best_seq, off);
-        const int oi = shflXor(best_idx, off);
-        if (os > best_seq) {
-          best_seq = os;
-          best_idx = oi;
-        }
-      }
-      if (best_idx < 0) break;
-      prev_seq = best_seq;
-      const int edge = best_idx;
-      // the two side edges (new_v, v_i), created on first use (:62-70)
-      for (int k = 0; k < 2; k++) {
-        const int vi = (k == 0) ? P.e_v0[edge] : P.e_v1[edge];
-        int ne = P.v_newedge[vi];
-        if (ne == kNil) {
-          ne = addEdgeTopo(new_v, vi);
-          if (ne >= 0) {
-            if (lane == 0) {
-              P.v_newedge[vi] = uint16_t(ne);
-              P.e_vis[ne] = 3;  // freshly made: distance record pending, not a border edge
-            }
-            if (first_new_e < 0) first_new_e = ne;
-            sync();
-          } else {
-            ne = -1;
-          }
-        }
-        made_e[k] = (ne == kNil) ? -1 : ne;
-      }
-      const int nf = addFaceTopo(edge, made_e[0], made_e[1]);
-      if (nf < 0) {
-        ok = false;  // keep walking like the reference does; the result is MallocFailed
-      } else {
-        if (lane == 0) P.f_vis[nf] = 4;  // distance record pending
-        if (first_new_f < 0) first_new_f = nf;
-        sync();
-      }
-    }
-    (void)first_new_e;
-    (void)first_new_f;
-    // distance records of the new cone, one element per lane
-    for (int i = lane; i < e_hw; i += T) {
-      if (P.e_alive[i] && P.e_vis[i] == 3) {
-        fillEdge(i);
-        P.e_vis[i] = 0;
-      }
-    }
-    for (int i = lane; i < f_hw; i += T) {
-      if (P.f_alive[i] && P.f_vis[i] == 4) {
-        fillFace(i);
-        P.f_vis[i] = 0;
-      }
+    // ---- the new cone (epa_polytope_expand.hpp:52-85), built in parallel ----
+    // The reference walks the edge list newest-first; for every border edge it creates the side edges
+    // (new_v, v_i) on first use of v_i and then the face (edge, side(v_0), side(v_1)).  Results depend on the
+    // creation ORDER (sequence numbers) and on which face is an edge's faces_of_edge[0 / 1], not on slots:
+    //   rank r of a border edge       = number of border edges with a larger sequence number
+    //   new face r                    = (border edge r, side(v0), side(v1)), face sequence f_sq + r
+    //   "first use" of a vertex       = smallest key 2 r + k over the border-edge ends (r, k) that touch it;
+    //   side edges are numbered in first-use order, their faces [0 / 1] are the two incident faces by rank.
+    // A vertex with more than two border-edge ends would give its side edge a third face ("wrong edge",
+    // epa_polytope.hpp:279-283), an exhausted edge / face pool fails an allocation: both end the evaluation with
+    // MallocFailed (epa.hpp:221-226) whatever the order, so they are detected up front.
+    const unsigned lt = (1u << lane) - 1u;
+    int m = 0;
+    for (int base = 0; base < e_hw; base += T) {
+      const int i = base + lane;
+      const bool pred = i < e_hw && P.e_alive[i] && P.e_vis[i] == 1;
+      const unsigned mask = ballot(pred);
+      if (pred) P.e_tmp0[m + __popc(mask & lt)] = uint16_t(i);
+      m += __popc(mask);
     }
     sync();
-    return ok ? 0 : 2;
+    for (int j = lane; j < m; j += T) {
+      const int ej = P.e_tmp0[j];
+      const int sj = P.e_seq[ej];
+      int r = 0;
+      for (int k = 0; k < m; k++) r += (int(P.e_seq[P.e_tmp0[k]]) > sj) ? 1 : 0;
+      P.e_tmp1[r] = uint16_t(ej);
+    }
+    sync();
+    // first uses, in key order: e_tmp0[ordinal of the side edge] = vertex (the unsorted list is dead by now)
+    int n_new = 0;
+    bool wrong = false;
+    for (int base = 0; base < 2 * m; base += T) {
+      const int t = base + lane;
+      bool first = false;
+      int vtx = 0;
+      if (t < 2 * m) {
+        const int e = P.e_tmp1[t >> 1];
+        vtx = (t & 1) ? P.e_v1[e] : P.e_v0[e];
+        first = true;
+        int occ = 0;
+        for (int u = 0; u < 2 * m; u++) {
+          const int eu = P.e_tmp1[u >> 1];
+          const int vu = (u & 1) ? P.e_v1[eu] : P.e_v0[eu];
+          if (vu == vtx) {
+            occ++;
+            if (u < t) first = false;
+          }
+        }
+        if (occ > 2) wrong = true;
+      }
+      const unsigned mask = ballot(first);
+      if (first) P.e_tmp0[n_new + __popc(mask & lt)] = uint16_t(vtx);
+      n_new += __popc(mask);
+    }
+    if (any(wrong)) return 2;
+    if (n_new > P.ecap - e_n || m > P.fcap - f_n) return 2;
+    sync();
+    gatherFree(P.e_alive, P.ecap, e_hw, n_new, P.e_tmp2);
+    sync();
+    for (int o = lane; o < n_new; o += T) {
+      const int sl = P.e_tmp2[o], vi = P.e_tmp0[o];
+      P.e_v0[sl] = uint16_t(new_v);
+      P.e_v1[sl] = uint16_t(vi);
+      P.e_f0[sl] = kNil;
+      P.e_f1[sl] = kNil;
+      P.e_seq[sl] = uint16_t(e_sq + o);
+      P.e_alive[sl] = 1;
+      P.e_vis[sl] = 0;
+      P.v_newedge[vi] = uint16_t(sl);
+      fillEdge(sl);
+    }
+    e_sq += n_new;
+    e_n += n_new;
+    sync();
+    gatherFree(P.f_alive, P.fcap, f_hw, m, P.e_tmp2);
+    sync();
+    for (int r = lane; r < m; r += T) {
+      const int sl = P.e_tmp2[r], edge = P.e_tmp1[r];
+      const int va = P.e_v0[edge], vb = P.e_v1[edge];
+      P.f_e0[sl] = uint16_t(edge);
+      P.f_e1[sl] = P.v_newedge[va];
+      P.f_e2[sl] = P.v_newedge[vb];
+      P.f_a[sl] = uint16_t(va);
+      P.f_b[sl] = uint16_t(vb);
+      P.f_c[sl] = uint16_t(new_v);
+      P.f_seq[sl] = uint16_t(f_sq + r);
+      P.f_alive[sl] = 1;
+      P.f_vis[sl] = 0;
+      P.e_f1[edge] = uint16_t(sl);  // removeAccordingToVisibility left the hidden face in slot 0
+      fillFace(sl);
+    }
+    for (int o = lane; o < n_new; o += T) {  // faces of the side edges, by rank
+      const int vi = P.e_tmp0[o], sl = P.v_newedge[vi];
+      int f0 = kNil, f1 = kNil;
+      for (int r = m - 1; r >= 0; r--) {
+        const int edge = P.e_tmp1[r];
+        if (P.e_v0[edge] == vi || P.e_v1[edge] == vi) {
+          f1 = f0;
+          f0 = P.e_tmp2[r];
+        }
+      }
+      P.e_f0[sl] = uint16_t(f0);
+      P.e_f1[sl] = uint16_t(f1);
+    }
+    f_sq += m;
+    f_n += m;
+    sync();
+    return 0;
   }
 
   struct RawFeature {  // epa.h:70-74

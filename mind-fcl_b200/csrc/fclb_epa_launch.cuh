@@ -28,7 +28,7 @@ inline int epaBlocksPerSmCap() {
 template <typename S, int T0, int T1, int T>
 cudaError_t launchEpaTier(const BatchView& b, const CollideLaunchArgs& a, int pool_faces, const EpaDefer& defer,
                           cudaStream_t st) {
-  const size_t poly = PolyStore<S>::bytes(pool_faces);
+  const size_t poly = PolyStore<S>::bytes(pool_faces, defer.enabled != 0);
   const size_t per_tile = epaTileBytes<S>(poly);
   const size_t esmem = per_tile * (kEpaThreads / T);
   auto kern = epaKernel<S, T0, T1, T>;
