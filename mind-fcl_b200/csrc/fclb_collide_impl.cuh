@@ -373,6 +373,11 @@ __global__ void __launch_bounds__(kBlock) convexBoolKernel(BatchView b, S tol, i
 // outgrows the pool is appended to `defer` and re-run from scratch by tier 2
 // (T = 32, the reference's capacity), so the reported status is always the one the
 // reference's pool size produces.
+#ifdef FCLB_EPA_MIN_BLOCKS
+#define FCLB_EPA_BOUNDS_TAIL , FCLB_EPA_MIN_BLOCKS
+#else
+#define FCLB_EPA_BOUNDS_TAIL
+#endif
 constexpr int kEpaThreads = 128;
 template <typename S>
 __host__ __device__ inline size_t epaTileBytes(size_t poly_bytes) {
@@ -387,7 +392,7 @@ struct EpaDefer {
 };
 
 template <typename S, int T0, int T1, int T>
-__global__ void __launch_bounds__(kEpaThreads) epaKernel(BatchView b, S tol, int pool_faces, int max_iter, int mode,
+__global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(BatchView b, S tol, int pool_faces, int max_iter, int mode,
                                                          CollideOut out, EpaWork work, EpaDefer defer,
                                                          size_t poly_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -305,39 +305,46 @@ struct EpaWarp {
     sync();
   }
 
-  // first dead slot of a pool (uniform result); -1 if the pool is full
-  FCLB_DI int allocSlot(const uint8_t* alive, int cap, int& hw) const {
-    if (hw < cap) return hw++;
-    for (int base = 0; base < cap; base += T) {
-      const int i = base + lane;
-      const unsigned m = ballot(i < cap && !alive[i]);
-      if (m) return base + __ffs(m) - 1;
+  // a dead slot of a pool (uniform result), recycled ones first (see gatherFree); -1 if the pool is full
+  FCLB_DI int allocSlot(const uint8_t* alive, int cap, int& hw, int n_alive) const {
+    if (n_alive < hw) {
+      for (int base = 0; base < hw; base += T) {
+        const int i = base + lane;
+        const unsigned m = ballot(i < hw && !alive[i]);
+        if (m) return base + __ffs(m) - 1;
+      }
     }
+    if (hw < cap) return hw++;
     return -1;
   }
 
-  // `need` free slots of a pool into out[0 .. need): fresh slots first, then dead ones in ascending order
-  // (slot identity is unobservable).  The caller has checked that the pool has that many free slots.
-  FCLB_DI void gatherFree(const uint8_t* alive, int cap, int& hw, int need, uint16_t* out) const {
-    const int old_hw = hw;
-    const int fresh = need < cap - old_hw ? need : cap - old_hw;
-    for (int j = lane; j < fresh; j += T) out[j] = uint16_t(old_hw + j);
-    hw = old_hw + fresh;
-    int got = fresh;
+  // `need` free slots of a pool into out[0 .. need): dead slots below the high-water mark first (ascending), then
+  // fresh ones -- slot identity is unobservable, and recycling first keeps the high-water marks (the trip counts of
+  // every per-element loop) at the live size of the polytope instead of the pool capacity.  The caller has checked
+  // that the pool has that many free slots.
+  FCLB_DI void gatherFree(const uint8_t* alive, int cap, int& hw, int n_alive, int need, uint16_t* out) const {
+    int got = 0;
     const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < old_hw && got < need; base += T) {
-      const int i = base + lane;
-      const bool pred = i < old_hw && !alive[i];
-      const unsigned mask = ballot(pred);
-      const int pos = got + __popc(mask & lt);
-      if (pred && pos < need) out[pos] = uint16_t(i);
-      got += __popc(mask);
+    if (n_alive < hw) {
+      for (int base = 0; base < hw && got < need; base += T) {
+        const int i = base + lane;
+        const bool pred = i < hw && !alive[i];
+        const unsigned mask = ballot(pred);
+        const int pos = got + __popc(mask & lt);
+        if (pred && pos < need) out[pos] = uint16_t(i);
+        got += __popc(mask);
+      }
+      if (got > need) got = need;
     }
+    const int fresh = need - got;
+    for (int j = lane; j < fresh; j += T) out[got + j] = uint16_t(hw + j);
+    hw += fresh;
+    (void)cap;
   }
 
   // AddNewVertex (epa_polytope.hpp:185-209)
   FCLB_DI int addVertex(const V3<S>& v, const V3<S>& d) {
-    const int s = allocSlot(P.v_alive, P.vcap, v_hw);
+    const int s = allocSlot(P.v_alive, P.vcap, v_hw, v_n);
     if (s < 0) return -1;
     if (lane == 0) {
       P.vx[s] = v.x; P.vy[s] = v.y; P.vz[s] = v.z;
@@ -354,7 +361,7 @@ struct EpaWarp {
   // topology part of AddNewEdge (:212-240); the distance record is filled by fillEdge
   FCLB_DI int addEdgeTopo(int v1, int v2) {
     if (v1 < 0 || v2 < 0) return -1;
-    const int s = allocSlot(P.e_alive, P.ecap, e_hw);
+    const int s = allocSlot(P.e_alive, P.ecap, e_hw, e_n);
     if (s < 0) return -1;
     if (lane == 0) {
       P.e_v0[s] = uint16_t(v1);
@@ -378,7 +385,7 @@ struct EpaWarp {
   // topology part of AddNewFace (:243-290). Returns slot, or -1 (malloc / "wrong edge").
   FCLB_DI int addFaceTopo(int e1, int e2, int e3) {
     if (e1 < 0 || e2 < 0 || e3 < 0) return -1;
-    const int s = allocSlot(P.f_alive, P.fcap, f_hw);
+    const int s = allocSlot(P.f_alive, P.fcap, f_hw, f_n);
     if (s < 0) return -1;
     bool ok = true;
     if (lane == 0) {
@@ -781,11 +788,8 @@ struct EpaWarp {
   // ExpandPolytope (epa_polytope_expand.hpp:33-91): 0 OK, 1 Failed, 2 MallocFailed
   FCLB_DI int expand(const V3<S>& nv, const V3<S>& nd, int start_face) {
     // initVisibilityCacheVariables + visibility predicate of EVERY face
-    for (int i = lane; i < v_hw; i += T) {
-      P.v_rm[i] = 1;
-      P.v_newedge[i] = kNil;
-    }
-    for (int i = lane; i < e_hw; i += T) P.e_vis[i] = 0;
+    // (cached_vertex2new_v_edge and the edges' cached_visibility are written before they are read below)
+    for (int i = lane; i < v_hw; i += T) P.v_rm[i] = 1;
     for (int i = lane; i < f_hw; i += T) {
       if (!P.f_alive[i]) continue;
       P.f_vis[i] = pointOutsideFace(i, nv, false) ? 3 : 2;  // 3 = outside (not reached yet), 2 = hidden
@@ -932,7 +936,7 @@ struct EpaWarp {
     if (any(wrong)) return 2;
     if (n_new > P.ecap - e_n || m > P.fcap - f_n) return 2;
     sync();
-    gatherFree(P.e_alive, P.ecap, e_hw, n_new, P.e_tmp2);
+    gatherFree(P.e_alive, P.ecap, e_hw, e_n, n_new, P.e_tmp2);
     sync();
     for (int o = lane; o < n_new; o += T) {
       const int sl = P.e_tmp2[o], vi = P.e_tmp0[o];
@@ -949,7 +953,7 @@ struct EpaWarp {
     e_sq += n_new;
     e_n += n_new;
     sync();
-    gatherFree(P.f_alive, P.fcap, f_hw, m, P.e_tmp2);
+    gatherFree(P.f_alive, P.fcap, f_hw, f_n, m, P.e_tmp2);
     sync();
     for (int r = lane; r < m; r += T) {
       const int sl = P.e_tmp2[r], edge = P.e_tmp1[r];
