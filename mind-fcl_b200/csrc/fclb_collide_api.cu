@@ -31,7 +31,7 @@ static int ensureWorkspace(size_t n, size_t ss) {
   FCLB_CUDA(cudaMalloc(&g_ws.query, cap * sizeof(uint32_t)));
   FCLB_CUDA(cudaMalloc(&g_ws.simplex, cap * 24 * 8));
   FCLB_CUDA(cudaMalloc(&g_ws.rank, cap * sizeof(int32_t)));
-  FCLB_CUDA(cudaMalloc(&g_ws.defer_count, sizeof(uint32_t)));
+  FCLB_CUDA(cudaMalloc(&g_ws.defer_count, 4 * sizeof(uint32_t)));  // deferred count, two work cursors, pad
   FCLB_CUDA(cudaMalloc(&g_ws.defer_item, cap * sizeof(uint32_t)));
   g_ws.cap = cap;
   g_ws.scalar = 8;

@@ -386,6 +386,7 @@ __host__ __device__ inline size_t epaTileBytes(size_t poly_bytes) {
 
 struct EpaDefer {
   uint32_t* count;  // device counter of deferred items
+  uint32_t* cursor; // device work cursor of this launch (tiles fetch items dynamically: EPA run times vary 100x)
   uint32_t* item;   // work-list indices
   int enabled;      // tier 1: defer on pool exhaustion; tier 2: 0
   int consume;      // tier 2: iterate the deferred list instead of the full work list
@@ -410,12 +411,13 @@ __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(Ba
   const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
   const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
   const uint32_t n_items = defer.consume ? *defer.count : min(*work.count, work.capacity);
-  const uint32_t n_tiles = gridDim.x * kTiles;
   // The tiles of a warp take their EPA iterations in LOCKSTEP: a warp-uniform loop whose body is "tiles
   // without a query fetch one and build its polytope; full-warp barrier; every tile with a query runs one
   // iteration".  (With a plain per-tile `for each query { evaluate }` the tiles drift apart after their first
-  // query and never reconverge: ncu showed 13 of 32 lanes per issued instruction.)
-  uint32_t it = blockIdx.x * kTiles + tile;
+  // query and never reconverge: ncu showed 13 of 32 lanes per issued instruction.)  Items come from a device-wide
+  // cursor: a query that runs to the iteration limit costs 100x the median, a static split would leave its tile
+  // the same share of the list as everyone else.
+  bool more = true;
   bool active = false;
   size_t q = 0;
   uint32_t w = 0;
@@ -464,9 +466,14 @@ __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(Ba
   while (true) {
     int es = epa.kEpaContinue;
     bool finished = false;
-    if (!active && it < n_items) {
+    uint32_t it = 0;
+    if (!active && more) {
+      if (lane == 0) it = atomicAdd(defer.cursor, 1u);
+      it = epa.shfl(it, 0);
+      more = it < n_items;
+    }
+    if (!active && more) {
       w = defer.consume ? defer.item[it] : it;
-      it += n_tiles;
       q = work.query[w];
       const fclb_pair pr = b.pairs[q];
       md.s0 = bindShape(shapes, cvx, pr.shape1);
@@ -489,7 +496,7 @@ __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(Ba
       else
         finished = true;
     }
-    if (!__any_sync(0xffffffffu, active || finished || it < n_items)) break;
+    if (!__any_sync(0xffffffffu, active || finished || more)) break;
     __syncwarp();
     if (active) {
       es = epa.step(max_iter, tol, depth, p0, p1);

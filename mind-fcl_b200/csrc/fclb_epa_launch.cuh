@@ -48,19 +48,22 @@ cudaError_t launchEpaTier(const BatchView& b, const CollideLaunchArgs& a, int po
 template <typename S, int T0, int T1>
 cudaError_t launchEpaT(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st) {
   EpaDefer d = a.defer;
-  cudaError_t e = cudaMemsetAsync(d.count, 0, sizeof(uint32_t), st);
+  cudaError_t e = cudaMemsetAsync(d.count, 0, 4 * sizeof(uint32_t), st);  // count + the tiers' work cursors
   if (e != cudaSuccess) return e;
   if (a.sp.epa_max_faces > tier1Faces()) {
     d.enabled = 1;
     d.consume = 0;
+    d.cursor = d.count + 1;
     e = launchEpaTier<S, T0, T1, 8>(b, a, tier1Faces(), d, st);
     if (e != cudaSuccess) return e;
     d.enabled = 0;
     d.consume = 1;
+    d.cursor = d.count + 2;
     return launchEpaTier<S, T0, T1, 32>(b, a, a.sp.epa_max_faces, d, st);
   }
   d.enabled = 0;
   d.consume = 0;
+  d.cursor = d.count + 1;
   return launchEpaTier<S, T0, T1, 8>(b, a, a.sp.epa_max_faces, d, st);
 }
 
