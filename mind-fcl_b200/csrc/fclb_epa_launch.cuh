@@ -45,6 +45,29 @@ cudaError_t launchEpaTier(const BatchView& b, const CollideLaunchArgs& a, int po
   return cudaGetLastError();
 }
 
+// lanes per query of the first tier; FCLB_EPA_TILE overrides it for tuning (4, 8 or 16; 0 = by pair kind).
+// Measured on B200 (profiles/r01_epa_sweep.txt): 8 lanes are best for Convex pairs (70 ms against 72 / 80 ms with
+// 4 / 16 on c1b_convex), 16 lanes for box pairs (7.0 ms against 7.5 / 9.2 ms with 8 / 4 on c1b, whose run time is
+// set by the few queries that run to the iteration limit, i.e. by the latency of one iteration).
+inline int tier1TileOverride() {
+  static int v = [] {
+    const char* e = getenv("FCLB_EPA_TILE");
+    const int x = e ? atoi(e) : 0;
+    return (x == 4 || x == 8 || x == 16) ? x : 0;
+  }();
+  return v;
+}
+template <typename S, int T0, int T1>
+cudaError_t launchEpaTier1(const BatchView& b, const CollideLaunchArgs& a, int pool_faces, const EpaDefer& defer,
+                           cudaStream_t st) {
+  const int tile = tier1TileOverride() ? tier1TileOverride() : ((T0 == ST_BOX && T1 == ST_BOX) ? 16 : 8);
+  switch (tile) {
+    case 4: return launchEpaTier<S, T0, T1, 4>(b, a, pool_faces, defer, st);
+    case 16: return launchEpaTier<S, T0, T1, 16>(b, a, pool_faces, defer, st);
+    default: return launchEpaTier<S, T0, T1, 8>(b, a, pool_faces, defer, st);
+  }
+}
+
 template <typename S, int T0, int T1>
 cudaError_t launchEpaT(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st) {
   EpaDefer d = a.defer;
@@ -54,7 +77,7 @@ cudaError_t launchEpaT(const BatchView& b, const CollideLaunchArgs& a, cudaStrea
     d.enabled = 1;
     d.consume = 0;
     d.cursor = d.count + 1;
-    e = launchEpaTier<S, T0, T1, 8>(b, a, tier1Faces(), d, st);
+    e = launchEpaTier1<S, T0, T1>(b, a, tier1Faces(), d, st);
     if (e != cudaSuccess) return e;
     d.enabled = 0;
     d.consume = 1;
@@ -64,7 +87,7 @@ cudaError_t launchEpaT(const BatchView& b, const CollideLaunchArgs& a, cudaStrea
   d.enabled = 0;
   d.consume = 0;
   d.cursor = d.count + 1;
-  return launchEpaTier<S, T0, T1, 8>(b, a, a.sp.epa_max_faces, d, st);
+  return launchEpaTier1<S, T0, T1>(b, a, a.sp.epa_max_faces, d, st);
 }
 
 template <typename S>
