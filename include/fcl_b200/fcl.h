@@ -552,15 +552,37 @@ void collideBatch(const std::vector<CollisionQuery<S>>& queries, const Collision
       constexpr uint32_t kKeep = 64;
       uint32_t count = 0;
       int64_t ids1[kKeep], ids2[kKeep];
-      detail::check(fclb_scene_pair_collide_batch_host(kindOf(g1), handleOf(g1), kindOf(g2), handleOf(g2), a, b, 1,
-                                                       detail::scalarType<S>(), &req, kKeep, &count, ids1, ids2),
-                    "fclb_scene_pair_collide_batch_host");
+      S rec[kKeep * 7];
+      const bool mpr_pen = req.penetration_mode == FCLB_PEN_DIRECTED || req.penetration_mode == FCLB_PEN_INCREMENTAL_MIN;
+      if (mpr_pen) {
+        // collisionPenetrationMPR (collision_penetration-inl.h:189-252).  In the canonical argument order the records
+        // are the reference's bit for bit.  With swapped arguments the reference runs MPR on (leaf of o1, leaf of o2)
+        // for the escape direction of o2; here the canonical pair is evaluated for the opposite direction and the
+        // normal negated -- the same penetration up to MPR's argument order, not bit-identical.
+        fclb_request r2 = req;
+        if (swap)
+          for (int k = 0; k < 3; k++) r2.dir[k] = -req.dir[k];
+        detail::check(fclb_scene_pair_contacts_batch_host(kindOf(g1), handleOf(g1), kindOf(g2), handleOf(g2), a, b, 1,
+                                                          detail::scalarType<S>(), &r2, kKeep, &count, ids1, ids2, rec),
+                      "fclb_scene_pair_contacts_batch_host");
+      } else {
+        detail::check(fclb_scene_pair_collide_batch_host(kindOf(g1), handleOf(g1), kindOf(g2), handleOf(g2), a, b, 1,
+                                                         detail::scalarType<S>(), &req, kKeep, &count, ids1, ids2),
+                      "fclb_scene_pair_collide_batch_host");
+      }
       for (uint32_t c = 0; c < count && c < kKeep; c++) {
         Contact<S> ct;
         ct.o1 = g1;
         ct.o2 = g2;
         ct.b1 = intptr_t(ids1[c]);
         ct.b2 = intptr_t(ids2[c]);
+        if (mpr_pen) {
+          const S* r = rec + 7 * c;
+          const S sgn = swap ? S(-1) : S(1);
+          ct.normal = Vector3<S>(sgn * r[0], sgn * r[1], sgn * r[2]);
+          ct.pos = Vector3<S>(r[3], r[4], r[5]);
+          ct.penetration_depth = r[6];
+        }
         results[q].addContact(ct);
       }
     } else if (!Q.o1->isShape() && !Q.o2->isShape()) {

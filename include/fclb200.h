@@ -328,6 +328,19 @@ int fclb_scene_pair_collide_batch_host(int kind1, fclb_handle scene1, int kind2,
 int fclb_scene_pair_collide_batch_dev(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                                       const void* poses2, size_t n, int scalar_type, const fclb_request* req,
                                       uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2);
+/* The same pairs with request.useDirectedPenetration(dir) / useIncrementalMinimumDistancePenetration(dir)
+ * (collisionPenetrationMPR, narrowphase/collision_penetration-inl.h:189-252): the boolean traversal, then
+ * computePenetrationMPR between the two leaf geometries of each contact (:34-95: a Box of Contact::o1_bv / o2_bv in
+ * the pose of its heightmap / octree, the mesh triangle b2 in the mesh pose).
+ *   out_contacts[(q*max_keep + k)*7 ..] = normal[3], pos[3], penetration_depth (depth -1: MPR reported failure) */
+int fclb_scene_pair_contacts_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                        const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                        uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2,
+                                        void* out_contacts);
+int fclb_scene_pair_contacts_batch_dev(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                       const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                       uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2,
+                                       void* out_contacts);
 /* node tests and leaf (shape-triangle / shape-pixel) tests of the most recent scene batch call */
 int fclb_scene_last_visit_counts(uint64_t* n_node, uint64_t* n_leaf);
 

@@ -197,10 +197,32 @@ struct ScenePairArgs {
   uint32_t max_keep;
   long long* out_b1;      // [n * max_keep] or nullptr
   long long* out_b2;
+  void* out_box1;         // [n * max_keep * 6 S] leaf boxes of side 1 / side 2 (Contact::o1_bv / o2_bv), or nullptr
+  void* out_box2;
   unsigned long long* work_counter;
   unsigned long long* stats;  // [0] node pairs tested, [1] leaf pairs tested, [2] stack overflows
 };
 template <typename S>
 cudaError_t launchScenePair(const ScenePairArgs& a, int grid, cudaStream_t st);
+
+// pass 2 of the MPR penetration modes for scene-pair contacts (fclb_scene_pen_impl.cuh)
+struct ScenePairPenArgs {
+  int leaf2_is_triangle;     // 1: side 2 is a mesh, b2 = triangle id of `tris`; 0: box from box2
+  const void* tris;
+  const void* poses1;
+  const void* poses2;
+  size_t n;
+  uint32_t max_keep;
+  const uint32_t* counts;
+  const long long* b2;
+  const void* box1;
+  const void* box2;
+  int incremental;
+  double dir[3];
+  double tol;
+  void* out_contacts;        // [n * max_keep * 7 S] = normal, pos, depth
+};
+template <typename S>
+cudaError_t launchScenePairPenetration(const ScenePairPenArgs& a, cudaStream_t st);
 
 }  // namespace fclb

@@ -316,7 +316,8 @@ static void fillOctView(const OctreeDev* o, OctView& v) {
 template <typename S>
 static int scenePairDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                         const void* poses2, size_t n, const fclb_request* req, uint32_t max_keep, uint32_t* counts,
-                        long long* b1, long long* b2) {
+                        long long* b1, long long* b2, void* box1 = nullptr, void* box2 = nullptr,
+                        const void** tris_out = nullptr) {
   const int st = sizeof(S) == 4 ? 0 : 1;
   ScenePairArgs a{};
   a.kind1 = kind1;
@@ -342,6 +343,7 @@ static int scenePairDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fcl
       a.bvh2.nodes = it->second->nodes;
       a.bvh2.tris = it->second->tris;
       a.bvh2.n_nodes = it->second->n_nodes;
+      if (tris_out) *tris_out = it->second->tris;
     } else {
       return fail(FCLB_ERR_UNSUPPORTED, "scene pair: supported pairs are heightmap-{heightmap, mesh, octree} and "
                                         "octree-{mesh, octree}, in this argument order");
@@ -361,6 +363,8 @@ static int scenePairDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fcl
   a.max_keep = b1 ? max_keep : 0;
   a.out_b1 = b1;
   a.out_b2 = b2;
+  a.out_box1 = box1;
+  a.out_box2 = box2;
   a.work_counter = g_counters;
   a.stats = g_counters + 1;
   const size_t need = (n + kScenePairWarps - 1) / kScenePairWarps;
@@ -382,6 +386,54 @@ static int scenePairDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fcl
   e.rec_kind[0] = -5;
   e.rec_count[0] = n;
   e.rec_ms[0] = ms;
+  return FCLB_OK;
+}
+
+// fcl::collide between two scene geometries with a DirectedPenetration / IncrementalMinimumPenetration request:
+// boolean pair traversal with a sink of ids + leaf boxes (pass 1), one MPR penetration per stored contact (pass 2)
+template <typename S>
+static int scenePairContactsDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                const void* poses2, size_t n, const fclb_request* req, uint32_t max_keep, uint32_t* counts,
+                                long long* b1, long long* b2, void* contacts) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  static void* d_box = nullptr;
+  static size_t d_box_cap = 0;
+  const size_t one = n * size_t(max_keep) * 6 * sizeof(S);
+  if (d_box_cap < 2 * one) {
+    cudaFree(d_box);
+    d_box = nullptr;
+    d_box_cap = 0;
+    FCLB_CUDA(cudaMalloc(&d_box, 2 * one));
+    d_box_cap = 2 * one;
+  }
+  void* box1 = d_box;
+  void* box2 = static_cast<char*>(d_box) + one;
+  fclb_request boolean_req = *req;
+  boolean_req.penetration_mode = FCLB_PEN_DISABLED;
+  const void* tris = nullptr;
+  int rc = scenePairDev<S>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, &boolean_req, max_keep, counts, b1, b2, box1,
+                           box2, &tris);
+  if (rc) return rc;
+  const SolverParams sp = solverParams(st, req->binary_tol, req->gjk_max_iter, req->distance_tol, req->epa_max_faces,
+                                       req->epa_max_iter, true);
+  ScenePairPenArgs p{};
+  p.leaf2_is_triangle = kind2 == FCLB_SCENE_BVH ? 1 : 0;
+  p.tris = tris;
+  p.poses1 = poses1;
+  p.poses2 = poses2;
+  p.n = n;
+  p.max_keep = max_keep;
+  p.counts = counts;
+  p.b2 = b2;
+  p.box1 = box1;
+  p.box2 = box2;
+  p.incremental = req->penetration_mode == FCLB_PEN_INCREMENTAL_MIN ? 1 : 0;
+  for (int k = 0; k < 3; k++) p.dir[k] = req->dir[k];
+  p.tol = sp.epa_tol;  // MPR(128, request.distanceTolerance())
+  p.out_contacts = contacts;
+  FCLB_CUDA(launchScenePairPenetration<S>(p, e.compute));
+  e.launches += 1;
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }
 
@@ -863,6 +915,70 @@ int fclb_scene_pair_collide_batch_host(int kind1, fclb_handle scene1, int kind2,
     FCLB_CUDA(cudaMemcpyAsync(out_b1, base + o_b1, n * keep * 8, cudaMemcpyDeviceToHost, e.compute));
     FCLB_CUDA(cudaMemcpyAsync(out_b2, base + o_b2, n * keep * 8, cudaMemcpyDeviceToHost, e.compute));
   }
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+int fclb_scene_pair_contacts_batch_dev(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                       const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                       uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2,
+                                       void* out_contacts) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (!req || !out_counts || !out_b1 || !out_b2 || !out_contacts || max_keep == 0)
+    return fail(FCLB_ERR_BAD_ARG, "null output / max_keep == 0");
+  if (req->penetration_mode != FCLB_PEN_DIRECTED && req->penetration_mode != FCLB_PEN_INCREMENTAL_MIN)
+    return fail(FCLB_ERR_UNSUPPORTED, "fclb_scene_pair_contacts_batch serves the MPR penetration modes "
+                                      "(FCLB_PEN_DIRECTED, FCLB_PEN_INCREMENTAL_MIN)");
+  if (n == 0) return FCLB_OK;
+  if (!poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null pose array");
+  if (scalar_type == FCLB_F32)
+    return scenePairContactsDev<float>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, req, max_keep, out_counts,
+                                       reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2),
+                                       out_contacts);
+  return scenePairContactsDev<double>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, req, max_keep, out_counts,
+                                      reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2),
+                                      out_contacts);
+}
+
+int fclb_scene_pair_contacts_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                        const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                        uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2,
+                                        void* out_contacts) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!poses1 || !poses2 || !out_counts || !out_b1 || !out_b2 || !out_contacts || max_keep == 0)
+    return fail(FCLB_ERR_BAD_ARG, "null array / max_keep == 0");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t keep = max_keep;
+  const size_t o_p1 = 0;
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_b1 = alignUp(o_cnt + n * 4, 256);
+  const size_t o_b2 = alignUp(o_b1 + n * keep * 8, 256);
+  const size_t o_ct = alignUp(o_b2 + n * keep * 8, 256);
+  const size_t total = alignUp(o_ct + n * keep * 7 * ss, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemsetAsync(base + o_b1, 0xff, o_b2 + n * keep * 8 - o_b1, e.compute));
+  rc = fclb_scene_pair_contacts_batch_dev(kind1, scene1, kind2, scene2, base + o_p1, base + o_p2, n, scalar_type, req, max_keep,
+                                          reinterpret_cast<uint32_t*>(base + o_cnt), reinterpret_cast<int64_t*>(base + o_b1),
+                                          reinterpret_cast<int64_t*>(base + o_b2), base + o_ct);
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(out_b1, base + o_b1, n * keep * 8, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(out_b2, base + o_b2, n * keep * 8, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(out_contacts, base + o_ct, n * keep * 7 * ss, cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }

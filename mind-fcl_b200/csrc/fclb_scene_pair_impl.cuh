@@ -289,8 +289,9 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
         const int batch = nq < 32 ? nq : 32;
         bool hit = false;
         long long c1 = -1, c2 = -1;
+        Elem el;
         if (lane < batch) {
-          const Elem el = queue[nq - 1 - lane];
+          el = queue[nq - 1 - lane];
           c1 = SA::type::code(el.a);
           st_leaf++;
           if constexpr (MESH) {
@@ -325,6 +326,22 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
             if (slot < a.max_keep && slot < a.max_contacts) {
               a.out_b1[q * a.max_keep + slot] = c1;
               a.out_b2[q * a.max_keep + slot] = c2;
+              if (a.out_box1) {  // Contact::o1_bv / o2_bv for the penetration pass
+                S* o1 = static_cast<S*>(a.out_box1) + (q * a.max_keep + slot) * 6;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                  o1[k] = el.a.mn[k];
+                  o1[3 + k] = el.a.mx[k];
+                }
+                if constexpr (!MESH) {
+                  S* o2 = static_cast<S*>(a.out_box2) + (q * a.max_keep + slot) * 6;
+#pragma unroll
+                  for (int k = 0; k < 3; k++) {
+                    o2[k] = el.b.mn[k];
+                    o2[3 + k] = el.b.mx[k];
+                  }
+                }
+              }
             }
           }
           count += uint32_t(__popc(hm));

@@ -2,4 +2,5 @@
 #include "fclb_scene_pen_impl.cuh"
 namespace fclb {
 template cudaError_t launchScenePenetration<double>(const ScenePenArgs&, cudaStream_t);
+template cudaError_t launchScenePairPenetration<double>(const ScenePairPenArgs&, cudaStream_t);
 }

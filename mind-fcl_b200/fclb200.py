@@ -40,6 +40,7 @@ EXPORTS = [
     "fclb_octree_shape_collide_batch_dev",
     "fclb_scene_shape_contacts_batch_host", "fclb_scene_shape_contacts_batch_dev",
     "fclb_scene_pair_collide_batch_host", "fclb_scene_pair_collide_batch_dev",
+    "fclb_scene_pair_contacts_batch_host", "fclb_scene_pair_contacts_batch_dev",
     "fclb_broadphase_build_host", "fclb_broadphase_build_dev", "fclb_broadphase_release",
     "fclb_broadphase_self_pairs_host", "fclb_broadphase_self_pairs_dev", "fclb_broadphase_tree_pairs_host",
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
@@ -184,6 +185,8 @@ def load() -> C.CDLL:
         sp_args = [C.c_int, C.c_uint64, C.c_int, C.c_uint64, vp, vp, sz, C.c_int, vp, u32, vp, vp, vp]
         lib.fclb_scene_pair_collide_batch_host.argtypes = sp_args
         lib.fclb_scene_pair_collide_batch_dev.argtypes = sp_args
+        lib.fclb_scene_pair_contacts_batch_host.argtypes = sp_args + [vp]
+        lib.fclb_scene_pair_contacts_batch_dev.argtypes = sp_args + [vp]
     if hasattr(lib, "fclb_bvh_collide_contacts_batch_host"):
         bc_args = [C.c_uint64, C.c_uint64, vp, vp, sz, C.c_int, vp, u32, vp, vp, vp]
         lib.fclb_bvh_collide_contacts_batch_host.argtypes = bc_args
@@ -590,6 +593,19 @@ def scene_pair_collide_batch_host(kind1, scene1, kind2, scene2, poses1, poses2, 
                                                     C.cast(C.pointer(request), C.c_void_p), max_keep, _ptr(counts),
                                                     _ptr(b1), _ptr(b2)))
     return counts, b1, b2
+
+
+def scene_pair_contacts_batch_host(kind1, scene1, kind2, scene2, poses1, poses2, scalar_type, request: Request, max_keep):
+    """fcl::collide(scene1, tf1, scene2, tf2) with an MPR penetration request: (counts, b1, b2 [n,k], contacts [n,k,7])."""
+    n = len(poses1)
+    counts = np.zeros(n, np.uint32)
+    b1 = np.zeros((n, max_keep), np.int64)
+    b2 = np.zeros((n, max_keep), np.int64)
+    contacts = np.zeros((n, max_keep, 7), np_dtype(scalar_type))
+    check(load().fclb_scene_pair_contacts_batch_host(kind1, scene1, kind2, scene2, _ptr(poses1), _ptr(poses2), n, scalar_type,
+                                                     C.cast(C.pointer(request), C.c_void_p), max_keep, _ptr(counts),
+                                                     _ptr(b1), _ptr(b2), _ptr(contacts)))
+    return counts, b1, b2, contacts
 
 
 def measure_fp_peak(scalar_type) -> float:

@@ -323,17 +323,21 @@ class RefOracle(_Oracle):
         return counts, b1, contacts
 
     # ---- scene vs scene (heightmap / octree / mesh pairs) ----
-    def scene_pair_collide_batch(self, kind1, id1, kind2, id2, poses1, poses2, max_keep, threads=1, **req):
+    def scene_pair_collide_batch(self, kind1, id1, kind2, id2, poses1, poses2, max_keep, threads=1, want_contacts=False,
+                                 **req):
         n = len(poses1)
         counts = np.zeros(n, np.uint32)
         b1 = np.zeros((n, max_keep), np.int64)
         b2 = np.zeros((n, max_keep), np.int64)
+        contacts = np.zeros((n, max_keep, 7), poses1.dtype) if want_contacts else None
         r = _request(**req)
         f = self.fn("scene_pair_collide_batch")
         f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
-                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         f(_st(poses1.dtype), kind1, id1, kind2, id2, _p(poses1), _p(poses2), n, C.cast(C.pointer(r), C.c_void_p), max_keep,
-          _p(counts), _p(b1), _p(b2), threads)
+          _p(counts), _p(b1), _p(b2), _p(contacts) if want_contacts else None, threads)
+        if want_contacts:
+            return counts, b1, b2, contacts
         return counts, b1, b2
 
     # ---- broadphase ----

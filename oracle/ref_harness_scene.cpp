@@ -255,7 +255,7 @@ void sceneContactsBatch(const fcl::CollisionGeometry<S>* scene, const ShapeRec* 
 template <typename S>
 void scenePairBatch(const fcl::CollisionGeometry<S>* g1, const fcl::CollisionGeometry<S>* g2, const S* poses1,
                     const S* poses2, size_t n, const RequestRec* rq, uint32_t max_keep, uint32_t* counts, int64_t* b1,
-                    int64_t* b2, int threads) {
+                    int64_t* b2, S* contacts, int threads) {
   parallelFor(n, threads, [&](size_t b, size_t e) {
     const fcl::CollisionRequest<S> req = makeRequest<S>(rq);
     for (size_t q = b; q < e; q++) {
@@ -265,6 +265,18 @@ void scenePairBatch(const fcl::CollisionGeometry<S>* g1, const fcl::CollisionGeo
       for (uint32_t k = 0; k < max_keep; k++) {
         b1[q * max_keep + k] = k < c ? int64_t(res.getContact(k).b1) : -1;
         b2[q * max_keep + k] = k < c ? int64_t(res.getContact(k).b2) : -1;
+        if (contacts) {
+          S* o = contacts + (q * max_keep + k) * 7;
+          for (int j = 0; j < 7; j++) o[j] = S(0);
+          if (k < c) {
+            const auto& ct = res.getContact(k);
+            for (int j = 0; j < 3; j++) {
+              o[j] = ct.normal[j];
+              o[3 + j] = ct.pos[j];
+            }
+            o[6] = ct.penetration_depth;
+          }
+        }
       }
     }
   });
@@ -476,13 +488,15 @@ int fclref_scene_shape_contacts_batch(int scalar_type, int kind, int scene_id, c
 /* fcl::collide between two scene geometries; kind: 0 mesh (BVHModel<OBBRSS>), 1 heightmap, 2 octree */
 int fclref_scene_pair_collide_batch(int scalar_type, int kind1, int id1, int kind2, int id2, const void* poses1,
                                     const void* poses2, size_t n, const void* request, uint32_t max_keep, uint32_t* counts,
-                                    int64_t* b1, int64_t* b2, int threads) {
+                                    int64_t* b1, int64_t* b2, void* contacts_or_null, int threads) {
   if (scalar_type == 0)
     scenePairBatch<float>(sceneGeom<float>(kind1, id1), sceneGeom<float>(kind2, id2), (const float*)poses1,
-                          (const float*)poses2, n, (const RequestRec*)request, max_keep, counts, b1, b2, threads);
+                          (const float*)poses2, n, (const RequestRec*)request, max_keep, counts, b1, b2,
+                          (float*)contacts_or_null, threads);
   else
     scenePairBatch<double>(sceneGeom<double>(kind1, id1), sceneGeom<double>(kind2, id2), (const double*)poses1,
-                           (const double*)poses2, n, (const RequestRec*)request, max_keep, counts, b1, b2, threads);
+                           (const double*)poses2, n, (const RequestRec*)request, max_keep, counts, b1, b2,
+                           (double*)contacts_or_null, threads);
   return 0;
 }
 

@@ -115,3 +115,60 @@ def test_scene_pairs(fclb, ref_oracle, dtype):
     for h in (octA, octB):
         fclb.octree_release(h)
     fclb.bvh_release(mesh)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_scene_pair_penetration(fclb, ref_oracle, dtype):
+    """DirectedPenetration / IncrementalMinimumPenetration requests on the five pair kinds
+    (collisionPenetrationMPR, collision_penetration-inl.h:189-252): counts identical, and the multiset of
+    contact records (b1, b2, normal, position, depth) bit-identical to the reference's for every query whose
+    contacts fit the kept list."""
+    st = fclb.F32 if dtype == np.float32 else fclb.F64
+    n, keep = 120, 2048
+    hidA, hmA = upload_heightmap(fclb, ref_oracle, scenes.terrain_points(40_000, 64 * RES), 64, dtype)
+    hidB, hmB = upload_heightmap(fclb, ref_oracle, blob_points(11, upper_half=True), 16, dtype)
+    oidA, octA = upload_octree(fclb, ref_oracle, octree_points(), 64, dtype)
+    oidB, octB = upload_octree(fclb, ref_oracle, blob_points(12), 16, dtype)
+    v, t = scenes.noisy_uv_sphere(n_lat=13, n_lon=24, radius=0.12, noise=0.02)
+    mid = ref_oracle.bvh_create(v, t)
+    obb, child, tri_verts = ref_oracle.bvh_export(mid, dtype)
+    mesh = fclb.bvh_upload(obb, child, tri_verts, st)
+    H, O, M = fclb.SCENE_HEIGHTMAP, fclb.SCENE_OCTREE, fclb.SCENE_BVH
+    cases = [
+        ("heightmap-heightmap", H, hidA, hmA, H, hidB, hmB, 0.05, 0.5, 5201),
+        ("heightmap-mesh", H, hidA, hmA, M, mid, mesh, 0.0, 0.6, 5202),
+        ("heightmap-octree", H, hidA, hmA, O, oidB, octB, 0.05, 0.6, 5203),
+        ("octree-mesh", O, oidA, octA, M, mid, mesh, -0.1, 0.45, 5204),
+        ("octree-octree", O, oidA, octA, O, oidB, octB, 0.0, 0.45, 5205),
+    ]
+    for name, k1, r1, d1, k2, r2, d2, zlo, zhi, seed in cases:
+        p1, p2 = scenes.heightmap_query_poses(n, dtype, 0.4, zlo, zhi, seed=seed)
+        for mode, direction in ((2, (0.0, 0.0, 1.0)), (3, (0.6, 0.0, 0.8))):
+            req = fclb.make_request(max_contacts=2**31 - 1, penetration_mode=mode, direction=direction)
+            counts, b1, b2, contacts = fclb.scene_pair_contacts_batch_host(k1, d1, k2, d2, p1, p2, st, req, keep)
+            e_counts, e_b1, e_b2, e_contacts = ref_oracle.scene_pair_collide_batch(
+                k1, r1, k2, r2, p1, p2, keep, threads=8, want_contacts=True, max_contacts=2**31 - 1, penetration_mode=mode,
+                direction=direction)
+            assert np.array_equal(counts, e_counts), (name, mode)
+            n_q = n_c = 0
+            for q in np.nonzero((counts > 0) & (counts <= keep))[0]:
+                k = int(counts[q])
+                got = sorted((int(b1[q, j]), int(b2[q, j])) + tuple(contacts[q, j].tolist()) for j in range(k))
+                exp = sorted((int(e_b1[q, j]), int(e_b2[q, j])) + tuple(e_contacts[q, j].tolist()) for j in range(k))
+                assert got == exp, (name, mode, q)
+                n_q += 1
+                n_c += k
+            print(f"[{name} mode={mode} {np.dtype(dtype).name}] colliding {int((counts > 0).sum())}, contacts "
+                  f"{int(counts.sum())}; records bit-identical for {n_c} contacts of {n_q} queries")
+            assert n_c > 0
+    req = fclb.make_request(max_contacts=2, penetration_mode=2, direction=(0.0, 0.0, 1.0))
+    p1, p2 = scenes.heightmap_query_poses(n, dtype, 0.4, 0.0, 0.4, seed=5301)
+    c2, _, _, _ = fclb.scene_pair_contacts_batch_host(H, hmA, M, mesh, p1, p2, st, req, 4)
+    assert (c2 <= 2).all() and c2.any()
+    with pytest.raises(fclb.FclbError):
+        fclb.scene_pair_contacts_batch_host(H, hmA, M, mesh, p1, p2, st, fclb.make_request(), 4)
+    for h in (hmA, hmB):
+        fclb.heightmap_release(h)
+    for h in (octA, octB):
+        fclb.octree_release(h)
+    fclb.bvh_release(mesh)
