@@ -246,6 +246,18 @@ int fclb_bvh_shape_collide_batch_dev(fclb_handle bvh, fclb_handle shapes, const 
 int fclb_heightmap_upload(const uint16_t* heights_mm, uint32_t full_x, uint32_t full_y, double resolution_x,
                           double resolution_y, uint32_t upper_bound_mm, fclb_handle* hm);
 int fclb_heightmap_release(fclb_handle hm);
+/* LayeredHeightMap<S> built ON THE DEVICE from a point cloud (n_points x 3 S, device / host pointer): the
+ * rasteriser of FlatHeightMap<S>::updateHeightsByPointGenerationFunctor (flat_heightmap-inl.h:249-272: per pixel the
+ * maximum of uint16(z * 1000) over its points, negative z and out-of-range points dropped) as one atomicMax per
+ * point, then the layer pyramid (layered_heightmap-inl.h:77-101).  Heights equal the reference's bit for bit
+ * (a maximum is order-free).  This is the step before the path: the scene changes every perception cycle. */
+int fclb_heightmap_build_dev(const void* points, size_t n_points, double resolution_x, double resolution_y,
+                             uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, fclb_handle* hm);
+int fclb_heightmap_build_points_host(const void* points, size_t n_points, double resolution_x, double resolution_y,
+                                     uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, fclb_handle* hm);
+/* shape of an uploaded / built map and a copy of one layer (0 = bottom, k = k levels above it) */
+int fclb_heightmap_info(fclb_handle hm, uint32_t* n_layers, uint32_t* full_x, uint32_t* full_y, uint32_t* upper_bound_mm);
+int fclb_heightmap_export(fclb_handle hm, uint32_t layer, uint16_t* heights_mm);
 /* Host-side mirror of FlatHeightMap<S>::updateHeightsByPointGenerationFunctor (flat_heightmap-inl.h:249-272):
  * rasterises n_points (x, y, z doubles, rounded once to S) into heights_mm (2*half_x * 2*half_y, caller-zeroed
  * or holding earlier heights).  Host only, no GPU needed. */

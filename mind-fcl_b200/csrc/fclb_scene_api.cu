@@ -456,6 +456,118 @@ static void heightsFromPoints(const double* pts, size_t n, S res_x, S res_y, uin
   }
 }
 
+
+// ---- LayeredHeightMap construction on the device ------------------------------------------------
+// FlatHeightMap<S>::updateHeightsByPointGenerationFunctor (flat_heightmap-inl.h:249-272) keeps, per pixel, the
+// maximum of uint16(z * 1000) over the points that fall into it: a maximum is order-free, so one thread per point
+// with an atomicMax gives the sequential loop's result exactly.  Heights are accumulated in a 32-bit grid (no 16-bit
+// atomics), packed to the uint16 bottom layer, and the coarser layers follow by 2x2 max pooling
+// (LayeredHeightMap::rebuildNextLayer, layered_heightmap-inl.h:77-101), one launch per layer.
+template <typename S>
+__global__ void hmRasterKernel(const S* __restrict__ pts, size_t n, S res_x, S res_y, int half_x, int half_y,
+                               uint32_t* __restrict__ grid) {
+  const int full_x = 2 * half_x, full_y = 2 * half_y;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const S px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+    if (pz < 0) continue;
+    const int x = int(floor(double(px / res_x)) + double(half_x));
+    const int y = int(floor(double(py / res_y)) + double(half_y));
+    if (x >= 0 && x < full_x && y >= 0 && y < full_y) {
+      const uint32_t z = uint32_t(uint16_t(int(pz * S(1000))));
+      atomicMax(&grid[size_t(y) * full_x + x], z);
+    }
+  }
+}
+__global__ void hmPackKernel(const uint32_t* __restrict__ grid, uint16_t* __restrict__ bottom, size_t n) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const uint32_t g = grid[i];
+    const uint16_t b = bottom[i];
+    bottom[i] = g > b ? uint16_t(g) : b;  // `if (heights[index] < z) heights[index] = z` on top of earlier heights
+  }
+}
+__global__ void hmPoolKernel(const uint16_t* __restrict__ down, uint32_t dfx, uint16_t* __restrict__ up, uint32_t ufx,
+                             uint32_t ufy) {
+  const size_t total = size_t(ufx) * ufy;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const uint32_t x = uint32_t(i % ufx), y = uint32_t(i / ufx);
+    const uint16_t* r0 = down + size_t(2 * y) * dfx + 2 * x;
+    const uint16_t* r1 = r0 + dfx;
+    const uint16_t a = r0[0] > r0[1] ? r0[0] : r0[1];
+    const uint16_t b = r1[0] > r1[1] ? r1[0] : r1[1];
+    up[i] = a > b ? a : b;
+  }
+}
+
+// layer shapes / offsets of a LayeredHeightMap with the given bottom half shape
+static void hmLayout(HeightmapDev* d, uint32_t hx, uint32_t hy, size_t* total) {
+  d->half_x = hx;
+  d->half_y = hy;
+  d->fx.clear();
+  d->fy.clear();
+  d->off.clear();
+  uint32_t fx = 2 * hx, fy = 2 * hy, nx = hx, ny = hy;
+  size_t t = 0;
+  while (true) {
+    d->fx.push_back(fx);
+    d->fy.push_back(fy);
+    d->off.push_back(t);
+    t += size_t(fx) * fy;
+    if (!(nx > 1 && ny > 1)) break;
+    fx /= 2;
+    fy /= 2;
+    nx /= 2;
+    ny /= 2;
+  }
+  *total = t;
+}
+
+template <typename S>
+static int heightmapBuildDev(Engine& e, const void* d_points, size_t n_points, double res_x, double res_y, uint32_t hx,
+                             uint32_t hy, fclb_handle* hm) {
+  HeightmapDev* d = new HeightmapDev();
+  d->res_x = res_x;
+  d->res_y = res_y;
+  size_t total = 0;
+  hmLayout(d, hx, hy, &total);
+  const size_t n_px = size_t(d->fx[0]) * d->fy[0];
+  uint32_t* grid = nullptr;
+  if (cudaMalloc(&d->d_layers, total * sizeof(uint16_t)) != cudaSuccess || cudaMalloc(&grid, n_px * sizeof(uint32_t)) != cudaSuccess) {
+    cudaFree(d->d_layers);
+    delete d;
+    return fail(FCLB_ERR_CUDA, "fclb_heightmap_build: cudaMalloc failed");
+  }
+  cudaMemsetAsync(d->d_layers, 0, n_px * sizeof(uint16_t), e.compute);
+  cudaMemsetAsync(grid, 0, n_px * sizeof(uint32_t), e.compute);
+  const int cap = e.sms * 16;
+  auto blocks = [&](size_t n) { return int(n / 256 + 1 < size_t(cap) ? n / 256 + 1 : size_t(cap)); };
+  hmRasterKernel<S><<<blocks(n_points), 256, 0, e.compute>>>(static_cast<const S*>(d_points), n_points, S(res_x), S(res_y),
+                                                            int(hx), int(hy), grid);
+  hmPackKernel<<<blocks(n_px), 256, 0, e.compute>>>(grid, d->d_layers, n_px);
+  for (size_t k = 1; k < d->off.size(); k++)
+    hmPoolKernel<<<blocks(size_t(d->fx[k]) * d->fy[k]), 256, 0, e.compute>>>(d->d_layers + d->off[k - 1], d->fx[k - 1],
+                                                                           d->d_layers + d->off[k], d->fx[k], d->fy[k]);
+  e.launches += 2 + (d->off.size() - 1);
+  // height_upper_bound_in_mm = the maximum height = the maximum of the (tiny) top layer
+  const size_t top = d->off.size() - 1;
+  std::vector<uint16_t> h_top(size_t(d->fx[top]) * d->fy[top]);
+  cudaError_t ce = cudaMemcpyAsync(h_top.data(), d->d_layers + d->off[top], h_top.size() * sizeof(uint16_t),
+                                   cudaMemcpyDeviceToHost, e.compute);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e.compute);
+  cudaFree(grid);
+  if (ce != cudaSuccess) {
+    cudaFree(d->d_layers);
+    delete d;
+    return fail(FCLB_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  uint32_t mx = 0;
+  for (uint16_t h : h_top) mx = h > mx ? h : mx;
+  d->upper_mm = mx;
+  const fclb_handle h = e.next_handle++;
+  hmTable()[h] = d;
+  *hm = h;
+  return FCLB_OK;
+}
+
 }  // namespace fclb
 
 using namespace fclb;
@@ -594,6 +706,62 @@ int fclb_heightmap_upload(const uint16_t* heights_mm, uint32_t full_x, uint32_t 
   const fclb_handle h = e.next_handle++;
   hmTable()[h] = d;
   *hm = h;
+  return FCLB_OK;
+}
+
+int fclb_heightmap_build_dev(const void* points, size_t n_points, double resolution_x, double resolution_y,
+                             uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, fclb_handle* hm) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (!hm || (n_points && !points) || half_shape_x == 0 || half_shape_y == 0 || half_shape_x > 32767 || half_shape_y > 32767 ||
+      (half_shape_x & (half_shape_x - 1)) || (half_shape_y & (half_shape_y - 1)))
+    return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_build_dev: bad argument (half shapes must be powers of two)");
+  if (!(resolution_x > 0) || !(resolution_y > 0)) return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_build_dev: bad resolution");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (scalar_type == FCLB_F32)
+    return heightmapBuildDev<float>(e, points, n_points, double(float(resolution_x)), double(float(resolution_y)), half_shape_x,
+                                    half_shape_y, hm);
+  return heightmapBuildDev<double>(e, points, n_points, resolution_x, resolution_y, half_shape_x, half_shape_y, hm);
+}
+
+int fclb_heightmap_build_points_host(const void* points, size_t n_points, double resolution_x, double resolution_y,
+                                     uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, fclb_handle* hm) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n_points && !points) return fail(FCLB_ERR_BAD_ARG, "null points");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t bytes = n_points * 3 * (scalar_type == FCLB_F32 ? 4 : 8);
+  rc = ensureStage(e, bytes ? bytes : 16);
+  if (rc) return rc;
+  if (bytes) FCLB_CUDA(cudaMemcpyAsync(e.d_stage, points, bytes, cudaMemcpyHostToDevice, e.compute));
+  return fclb_heightmap_build_dev(e.d_stage, n_points, resolution_x, resolution_y, half_shape_x, half_shape_y, scalar_type, hm);
+}
+
+int fclb_heightmap_info(fclb_handle hm, uint32_t* n_layers, uint32_t* full_x, uint32_t* full_y, uint32_t* upper_bound_mm) {
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = hmTable().find(hm);
+  if (it == hmTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_info: unknown handle");
+  if (n_layers) *n_layers = uint32_t(it->second->off.size());
+  if (full_x) *full_x = it->second->fx[0];
+  if (full_y) *full_y = it->second->fy[0];
+  if (upper_bound_mm) *upper_bound_mm = it->second->upper_mm;
+  return FCLB_OK;
+}
+
+int fclb_heightmap_export(fclb_handle hm, uint32_t layer, uint16_t* heights_mm) {
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = hmTable().find(hm);
+  if (it == hmTable().end() || !heights_mm) return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_export: unknown handle / null buffer");
+  const HeightmapDev* d = it->second;
+  if (layer >= d->off.size()) return fail(FCLB_ERR_BAD_ARG, "fclb_heightmap_export: no such layer");
+  FCLB_CUDA(cudaMemcpy(heights_mm, d->d_layers + d->off[layer], size_t(d->fx[layer]) * d->fy[layer] * sizeof(uint16_t),
+                       cudaMemcpyDeviceToHost));
   return FCLB_OK;
 }
 

@@ -35,6 +35,7 @@ EXPORTS = [
     "fclb_bvh_last_visit_counts", "fclb_bvh_build", "fclb_bvh_build_host", "fclb_bvh_info", "fclb_bvh_export",
     "fclb_bvh_shape_collide_batch_host", "fclb_bvh_shape_collide_batch_dev", "fclb_scene_last_visit_counts",
     "fclb_heightmap_upload", "fclb_heightmap_release", "fclb_heightmap_build_host",
+    "fclb_heightmap_build_dev", "fclb_heightmap_build_points_host", "fclb_heightmap_info", "fclb_heightmap_export",
     "fclb_heightmap_shape_collide_batch_host", "fclb_heightmap_shape_collide_batch_dev",
     "fclb_octree_upload", "fclb_octree_release", "fclb_octree_shape_collide_batch_host",
     "fclb_octree_shape_collide_batch_dev",
@@ -151,6 +152,12 @@ def load() -> C.CDLL:
         lib.fclb_heightmap_upload.argtypes = [vp, u32, u32, C.c_double, C.c_double, u32, C.POINTER(C.c_uint64)]
         lib.fclb_heightmap_release.argtypes = [C.c_uint64]
         lib.fclb_heightmap_build_host.argtypes = [vp, sz, C.c_double, C.c_double, u32, u32, C.c_int, vp]
+    if hasattr(lib, "fclb_heightmap_build_dev"):
+        hb_args = [vp, sz, C.c_double, C.c_double, u32, u32, C.c_int, C.POINTER(C.c_uint64)]
+        lib.fclb_heightmap_build_dev.argtypes = hb_args
+        lib.fclb_heightmap_build_points_host.argtypes = hb_args
+        lib.fclb_heightmap_info.argtypes = [C.c_uint64, vp, vp, vp, vp]
+        lib.fclb_heightmap_export.argtypes = [C.c_uint64, u32, vp]
         hs_args = [C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp]
         lib.fclb_heightmap_shape_collide_batch_host.argtypes = hs_args
         lib.fclb_heightmap_shape_collide_batch_dev.argtypes = hs_args
@@ -441,6 +448,36 @@ def heightmap_upload(heights, resolution, upper_bound_mm=0) -> int:
     check(load().fclb_heightmap_upload(_ptr(h), h.shape[1], h.shape[0], resolution, resolution, upper_bound_mm,
                                        C.byref(out)))
     return out.value
+
+
+def heightmap_build_points_host(points, resolution, half_shape, scalar_type) -> int:
+    """LayeredHeightMap built on the device from a host point cloud (n x 3, converted to the scalar type)."""
+    pts = np.ascontiguousarray(points, np_dtype(scalar_type))
+    out = C.c_uint64()
+    check(load().fclb_heightmap_build_points_host(_ptr(pts), len(pts), resolution, resolution, half_shape, half_shape,
+                                                  scalar_type, C.byref(out)))
+    return out.value
+
+
+def heightmap_build_dev(points_dev, n_points, resolution, half_shape, scalar_type) -> int:
+    """The same from a DEVICE point array (torch tensor / raw pointer, n x 3 of the scalar type)."""
+    out = C.c_uint64()
+    check(load().fclb_heightmap_build_dev(_ptr(points_dev), n_points, resolution, resolution, half_shape, half_shape,
+                                          scalar_type, C.byref(out)))
+    return out.value
+
+
+def heightmap_info(h: int):
+    v = (C.c_uint32 * 4)()
+    check(load().fclb_heightmap_info(h, C.byref(v, 0), C.byref(v, 4), C.byref(v, 8), C.byref(v, 12)))
+    return {"n_layers": v[0], "full_x": v[1], "full_y": v[2], "upper_bound_mm": v[3]}
+
+
+def heightmap_export(h: int, layer: int = 0) -> np.ndarray:
+    info = heightmap_info(h)
+    out = np.zeros((info["full_y"] >> layer, info["full_x"] >> layer), np.uint16)
+    check(load().fclb_heightmap_export(h, layer, _ptr(out)))
+    return out
 
 
 def heightmap_release(h: int) -> None:

@@ -83,8 +83,12 @@ def main():
                     f.write(f"{100 * a[1] / tot:6.2f} %  {a[1]:12.1f} us  {a[0]:4d} launches  {k}\n")
             os.system(f"cp {os.path.join(OUT, name)} {os.path.join(PROF, name)}")
             print("wrote", name)
-    with open(os.path.join(PROF, f"{tag}_ncu_traffic_raw.json"), "w") as f:
-        json.dump(traffic, f, indent=1)
+    # merge into the committed table: gpurun_out/ only holds the captures of the latest calls
+    path = os.path.join(PROF, f"{tag}_ncu_traffic_raw.json")
+    merged = json.load(open(path)) if os.path.exists(path) else {}
+    merged.update(traffic)
+    with open(path, "w") as f:
+        json.dump(merged, f, indent=1)
 
 
 if __name__ == "__main__":
