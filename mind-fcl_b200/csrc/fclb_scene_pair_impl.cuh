@@ -77,6 +77,51 @@ FCLB_DI bool fixedRotDisjointBoxes(const FixedRot<S>& f, const S* mn1, const S* 
   return false;
 }
 
+// Node-pair cull of the device traversal: the 15 axes of the OBB separating-axis test (math/bv/OBB-inl.h:319-436,
+// the same axes as FixedRotationBoxDisjoint) with a SLACK added to every radius.  The cull must never remove a node
+// pair above a leaf pair that the reference's leaf test accepts -- the leaf test, not this cull, decides what is
+// reported -- and the plain test is not safe for that: for nearly parallel boxes a cross axis compares a centre
+// distance that is rounding noise (~1e-7 |T| in float) with a radius of ~1e-6 * extent.  The slack, 1e-5 x the
+// magnitude of the coordinates involved, is far above that noise and far below a pixel / voxel; on the cross axes it
+// simply switches the axis off when the two edges are nearly parallel.
+template <typename S>
+FCLB_DI bool nodeObbDisjoint(const M3<S>& B, const V3<S>& T, const V3<S>& a, const V3<S>& b, S slack) {
+  M3<S> Bf;
+#pragma unroll
+  for (int i = 0; i < 9; i++) Bf.m[i] = fabs_(B.m[i]) + S(1e-6);
+  if (fabs_(T.x) > a.x + dot(row(Bf, 0), b) + slack) return true;
+  if (fabs_(T.y) > a.y + dot(row(Bf, 1), b) + slack) return true;
+  if (fabs_(T.z) > a.z + dot(row(Bf, 2), b) + slack) return true;
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    if (fabs_(dot(col(B, j), T)) > comp(b, j) + dot(col(Bf, j), a) + slack) return true;
+#define FCLB_NO_EDGE(SEXPR, RAD) \
+  if (fabs_(SEXPR) > (RAD) + slack) return true;
+  FCLB_NO_EDGE(T.z * B(1, 0) - T.y * B(2, 0), a.y * Bf(2, 0) + a.z * Bf(1, 0) + b.y * Bf(0, 2) + b.z * Bf(0, 1))
+  FCLB_NO_EDGE(T.z * B(1, 1) - T.y * B(2, 1), a.y * Bf(2, 1) + a.z * Bf(1, 1) + b.x * Bf(0, 2) + b.z * Bf(0, 0))
+  FCLB_NO_EDGE(T.z * B(1, 2) - T.y * B(2, 2), a.y * Bf(2, 2) + a.z * Bf(1, 2) + b.x * Bf(0, 1) + b.y * Bf(0, 0))
+  FCLB_NO_EDGE(T.x * B(2, 0) - T.z * B(0, 0), a.x * Bf(2, 0) + a.z * Bf(0, 0) + b.y * Bf(1, 2) + b.z * Bf(1, 1))
+  FCLB_NO_EDGE(T.x * B(2, 1) - T.z * B(0, 1), a.x * Bf(2, 1) + a.z * Bf(0, 1) + b.x * Bf(1, 2) + b.z * Bf(1, 0))
+  FCLB_NO_EDGE(T.x * B(2, 2) - T.z * B(0, 2), a.x * Bf(2, 2) + a.z * Bf(0, 2) + b.x * Bf(1, 1) + b.y * Bf(1, 0))
+  FCLB_NO_EDGE(T.y * B(0, 0) - T.x * B(1, 0), a.x * Bf(1, 0) + a.y * Bf(0, 0) + b.y * Bf(2, 2) + b.z * Bf(2, 1))
+  FCLB_NO_EDGE(T.y * B(0, 1) - T.x * B(1, 1), a.x * Bf(1, 1) + a.y * Bf(0, 1) + b.x * Bf(2, 2) + b.z * Bf(2, 0))
+  FCLB_NO_EDGE(T.y * B(0, 2) - T.x * B(1, 2), a.x * Bf(1, 2) + a.y * Bf(0, 2) + b.x * Bf(2, 1) + b.y * Bf(2, 0))
+#undef FCLB_NO_EDGE
+  return false;
+}
+
+template <typename S>
+FCLB_DI bool nodeBoxesDisjoint(const FixedRot<S>& f, const S* mn1, const S* mx1, const S* mn2, const S* mx2) {
+  const V3<S> c1 = mk<S>((mn1[0] + mx1[0]) * S(0.5), (mn1[1] + mx1[1]) * S(0.5), (mn1[2] + mx1[2]) * S(0.5));
+  const V3<S> a = mk<S>(S(0.5) * (mx1[0] - mn1[0]), S(0.5) * (mx1[1] - mn1[1]), S(0.5) * (mx1[2] - mn1[2]));
+  const V3<S> c2 = mk<S>((mn2[0] + mx2[0]) * S(0.5), (mn2[1] + mx2[1]) * S(0.5), (mn2[2] + mx2[2]) * S(0.5));
+  const V3<S> b = mk<S>(S(0.5) * (mx2[0] - mn2[0]), S(0.5) * (mx2[1] - mn2[1]), S(0.5) * (mx2[2] - mn2[2]));
+  const V3<S> T = (mulMV(f.R, c2) + f.t) - c1;
+  const S slack = S(1e-5) * (S(1) + fabs_(f.t.x) + fabs_(f.t.y) + fabs_(f.t.z) + fabs_(c1.x) + fabs_(c1.y) + fabs_(c1.z) +
+                             fabs_(c2.x) + fabs_(c2.y) + fabs_(c2.z));
+  return nodeObbDisjoint(f.R, T, a, b, slack);
+}
+
 // ---- the two box hierarchies -------------------------------------------------------------------
 // One traversal element of either hierarchy: the node's box in the scene frame + what is needed to
 // expand it and to name it in a contact.
@@ -218,10 +263,16 @@ struct PairElem<S, true> {
   int b, pad;
 };
 
-template <typename S>
-FCLB_DI S boxDiagSq(const BoxElem<S>& e) {
-  const S dx = e.mx[0] - e.mn[0], dy = e.mx[1] - e.mn[1], dz = e.mx[2] - e.mn[2];
-  return dx * dx + dy * dy + dz * dz;
+// Descent rule (ours; the reference's only fixes its visiting order): split the node whose REFINABLE extent is
+// larger -- a heightmap node only shrinks in x / y when it is split (its z range is the column height at every
+// layer), an octree node in all three axes, a mesh node is measured by its longest OBB side.
+template <typename S, int K>
+FCLB_DI S refinableSize(const BoxElem<S>& e) {
+  const S dx = e.mx[0] - e.mn[0], dy = e.mx[1] - e.mn[1];
+  const S m = dx > dy ? dx : dy;
+  if (K == FCLB_SCENE_HEIGHTMAP) return m;
+  const S dz = e.mx[2] - e.mn[2];
+  return m > dz ? m : dz;
 }
 
 constexpr int kPairWarps = kScenePairWarps;
@@ -284,8 +335,12 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
     }
     __syncwarp();
 
+    // A query that needs only a few more contacts (boolean collide: one) must not wait for a full batch of leaf
+    // pairs, nor expand 32 node pairs per level on the way down: the reference's depth-first walk reaches its first
+    // leaf pair after ~one node pair per level.  `eager`: flush the leaf queue after every step and pop narrowly.
+    const bool eager = a.max_contacts <= 8;
     auto runLeaf = [&](bool flush) {
-      while (!done && (nq >= 32 || (flush && nq > 0))) {
+      while (!done && (nq >= 32 || ((flush || eager) && nq > 0))) {
         const int batch = nq < 32 ? nq : 32;
         bool hit = false;
         long long c1 = -1, c2 = -1;
@@ -358,7 +413,8 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
       // a popped pair pushes <= 8 children and queues <= 1 leaf pair: bound both before popping.  Wide pops
       // stop while kPairDfsReserve slots are free; from there the warp pops one pair at a time from the top
       // (depth-first order, growth <= 7 per remaining level).
-      int take = sp < 32 ? sp : 32;
+      const int width = eager ? 4 : 32;
+      int take = sp < width ? sp : width;
       if (sp + 7 * take > kPairStack - kPairDfsReserve) {
         const int fit = (kPairStack - kPairDfsReserve - sp) / 7;
         take = fit < 1 ? 1 : fit;
@@ -385,18 +441,22 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
         const bool ta = (el.a.meta & 1u) != 0;
         if constexpr (MESH) {
           const NodeD<S> nd = loadNode(nodes, el.b);
-          NodeD<S> bx;  // the box as an OBB of frame 1
-#pragma unroll
-          for (int i = 0; i < 9; i++) bx.axis.m[i] = (i % 4 == 0) ? S(1) : S(0);
-          bx.To = mk<S>((el.a.mn[0] + el.a.mx[0]) * S(0.5), (el.a.mn[1] + el.a.mx[1]) * S(0.5), (el.a.mn[2] + el.a.mx[2]) * S(0.5));
-          bx.extent = mk<S>(S(0.5) * (el.a.mx[0] - el.a.mn[0]), S(0.5) * (el.a.mx[1] - el.a.mn[1]), S(0.5) * (el.a.mx[2] - el.a.mn[2]));
-          if (obbOverlap(fr.R, fr.t, bx, nd)) {
+          // the box as an OBB of frame 1 (identity axes): R = R0 * axis2, T = R0 * To2 + T0 - centre
+          const V3<S> ctr = mk<S>((el.a.mn[0] + el.a.mx[0]) * S(0.5), (el.a.mn[1] + el.a.mx[1]) * S(0.5), (el.a.mn[2] + el.a.mx[2]) * S(0.5));
+          const V3<S> half = mk<S>(S(0.5) * (el.a.mx[0] - el.a.mn[0]), S(0.5) * (el.a.mx[1] - el.a.mn[1]), S(0.5) * (el.a.mx[2] - el.a.mn[2]));
+          const M3<S> Rn = mulMM(fr.R, nd.axis);
+          const V3<S> Tn = (mulMV(fr.R, nd.To) + fr.t) - ctr;
+          const S slack = S(1e-5) * (S(1) + fabs_(ctr.x) + fabs_(ctr.y) + fabs_(ctr.z) + fabs_(fr.t.x) + fabs_(fr.t.y) + fabs_(fr.t.z) +
+                                     fabs_(nd.To.x) + fabs_(nd.To.y) + fabs_(nd.To.z));
+          if (!nodeObbDisjoint(Rn, Tn, half, nd.extent, slack)) {
             const bool tb = nd.first_child < 0;
             if (ta && tb) {
               cand = true;
               bc0 = -(nd.first_child + 1);
             } else {
-              on_a = tb || (!ta && boxDiagSq(el.a) > S(4) * sqnorm(nd.extent));
+              const S eb = nd.extent.x > nd.extent.y ? (nd.extent.x > nd.extent.z ? nd.extent.x : nd.extent.z)
+                                                      : (nd.extent.y > nd.extent.z ? nd.extent.y : nd.extent.z);
+              on_a = tb || (!ta && refinableSize<S, KA>(el.a) > S(2) * eb);
               if (on_a) {
                 mask = sideA.childMask(el.a);
                 n_push = __popc(mask);
@@ -407,12 +467,12 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
             }
           }
         } else {
-          if (!fixedRotDisjointBoxes(fr, el.a.mn, el.a.mx, el.b.mn, el.b.mx, false)) {
+          if (!nodeBoxesDisjoint(fr, el.a.mn, el.a.mx, el.b.mn, el.b.mx)) {
             const bool tb = (el.b.meta & 1u) != 0;
             if (ta && tb) {
               cand = true;
             } else {
-              on_a = tb || (!ta && boxDiagSq(el.a) > boxDiagSq(el.b));
+              on_a = tb || (!ta && refinableSize<S, KA>(el.a) > refinableSize<S, KB>(el.b));
               mask = on_a ? sideA.childMask(el.a) : sideB.childMask(el.b);
               n_push = __popc(mask);
             }
