@@ -25,10 +25,11 @@
 // What the reference REPORTS is the set of leaf pairs that pass the leaf test; the node-pair
 // tests above the leaves (6-axis / 15-axis SAT of the enclosing boxes, the sphere approximation
 // of octreePairTwoLeafNode) are conservative culls and the descent rule only fixes the visiting
-// order.  So the warp runs its own traversal: it pops up to 32 node pairs per step, culls them
-// with a conservative box test, pushes the children of the larger node (or queues the pair when
-// both are leaves) at prefix-sum offsets, and runs the reference's exact leaf test on 32 queued
-// pairs at a time.  Contact order follows the device traversal (declared).
+// order.  So the warp runs its own traversal: it pops up to 32 node pairs per step (4 when only a few contacts
+// are wanted), culls them with a slack-guarded 15-axis SAT that never removes a pair the leaf test would accept,
+// pushes the children of the node with the larger refinable extent (or queues the pair when both are leaves) at
+// prefix-sum offsets, and runs the reference's exact leaf test on the queued pairs, 32 at a time.  Contact order
+// follows the device traversal (declared).
 #pragma once
 #include "fclb_bvh_shape_impl.cuh"  // boxTriangleOverlap
 #include "fclb_octree_impl.cuh"     // FixedRot, makeFixedRot, rowDotAssoc, childAabb
