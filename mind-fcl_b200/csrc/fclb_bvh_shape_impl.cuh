@@ -346,6 +346,11 @@ FCLB_DI bool shapeTriangleHit(const LeafCtx<S>& c, const V3<S> P[3]) {
   }
 }
 
+// pop width of a query that wants only a few contacts; measured on C3 / C4 (B200): 32 -> 4.76 / 23.4 ms,
+// 16 -> 5.04 / 25.1 ms, 8 -> 5.85 / 28.7 ms (most of the work is proving the non-colliding queries separate)
+#ifndef FCLB_EAGER_WIDTH
+#define FCLB_EAGER_WIDTH 32
+#endif
 constexpr int kBsWarps = kBvhShapeWarps;
 constexpr int kBsStackCap = 1024;
 constexpr int kBsLeafCap = 64;
@@ -388,9 +393,12 @@ __global__ void __launch_bounds__(kBsWarps * 32, FCLB_SCENE_MIN_BLOCKS) bvhShape
     __syncwarp();
     bool done = (a.max_contacts == 0);
 
+    // few contacts wanted (boolean collide): narrow pops and an eager leaf stage, see fclb_bvh.cu
+    const bool eager = a.max_contacts <= 8;
+    const int width = eager ? FCLB_EAGER_WIDTH : 32;
     while (!done && (sp > 0 || nleaf > 0)) {
       if (sp > 0 && nleaf < 32) {
-        int take = sp < 32 ? sp : 32;
+        int take = sp < width ? sp : width;
         if (sp + take > kBsStackCap - 64) take = 1;
         int id = -1;
         if (lane < take) id = stack[sp - 1 - lane];
@@ -428,7 +436,7 @@ __global__ void __launch_bounds__(kBsWarps * 32, FCLB_SCENE_MIN_BLOCKS) bvhShape
         nleaf += __popc(lm);
         __syncwarp();
       }
-      if (nleaf >= 32 || (sp == 0 && nleaf > 0)) {
+      if (nleaf >= 32 || ((sp == 0 || eager) && nleaf > 0)) {
         const int batch = nleaf < 32 ? nleaf : 32;
         bool hit = false;
         int tri_id = -1;
