@@ -690,7 +690,10 @@ def main():
                    "each step re-reads them after %.0f MB of result writes" % (wl.h2d_bytes() / 1e6, wl.d2h_bytes() / 1e6),
                    "sharding": "queries sharded by rank, geometry replicated, no collective on the data path"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes(),
-                "d2h_bytes_per_step": wl.d2h_bytes(), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+                "d2h_bytes_per_step": wl.d2h_bytes(), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                # the host link is what bounds this number once copies and kernels overlap: bytes moved per
+                # second in each direction (PCIe is full duplex; Gen5 x16 peaks near 55-57 GB/s one way)
+                "h2d_gbs": wl.h2d_bytes() / (ms_e2e / e2e_steps) / 1e6, "d2h_gbs": wl.d2h_bytes() / (ms_e2e / e2e_steps) / 1e6},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
