@@ -1,5 +1,6 @@
 """Scene-pair kernels at scale (not a bench.py workload: BASELINE.json has no such config): a 1024^2 heightmap
-(10 layers, C4's terrain cloud) against a 10k-triangle mesh, a 64^3-voxel octree and a 128^2 heightmap, 2000 poses each,
+(10 layers, C4's terrain cloud) against a 10k-triangle mesh, a 64^3-cell octree and a 128^2 heightmap, and a
+256^3-cell octree against the mesh and the small octree, 2000 poses each,
 checked against the reference on every query and timed beside it (reference: all host threads)."""
 import sys, time, os
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,17 +27,25 @@ h2, up2 = ref.heightmap_export(hid2, dtype, 64)
 hm2 = fclb.heightmap_upload(h2, 0.005, up2)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 H, O, M = fclb.SCENE_HEIGHTMAP, fclb.SCENE_OCTREE, fclb.SCENE_BVH
-for name, k2, r2, d2 in (("heightmap(1024^2)-mesh(10k tris)", M, mid, mesh), ("heightmap(1024^2)-octree", O, oid, octree),
-                         ("heightmap(1024^2)-heightmap(128^2)", H, hid2, hm2)):
-    p1, p2 = scenes.heightmap_query_poses(n, dtype, 1.6, -0.3, 1.2, seed=61)
+# a large octree: the terrain cloud voxelised at 1 cm (256^3 cells) -- many fully occupied inner nodes are impossible
+# for a surface, so add a filled slab
+slab = octree_points()
+big_pts = np.ascontiguousarray(np.concatenate([pts[::2] * np.array([0.6, 0.6, 1.0]), slab]))
+oidA = ref.octree_create(big_pts, 0.01, 128)
+octA = fclb.octree_upload(*ref.octree_export(oidA, dtype))
+cases = [("heightmap(1024^2)-mesh(10k tris)", H, hid, hm, M, mid, mesh), ("heightmap(1024^2)-octree", H, hid, hm, O, oid, octree),
+         ("heightmap(1024^2)-heightmap(128^2)", H, hid, hm, H, hid2, hm2),
+         ("octree(256^3 cells)-mesh(10k tris)", O, oidA, octA, M, mid, mesh), ("octree(256^3 cells)-octree", O, oidA, octA, O, oid, octree)]
+for name, k1, r1, d1, k2, r2, d2 in cases:
+    p1, p2 = scenes.heightmap_query_poses(n, dtype, 1.6 if k1 == H else 1.0, -0.3, 1.2 if k1 == H else 0.6, seed=61)
     for mc in (1, 2**31 - 1):
         req = fclb.make_request(max_contacts=mc)
-        fclb.scene_pair_collide_batch_host(H, hm, k2, d2, p1, p2, st, req)  # warm-up
+        fclb.scene_pair_collide_batch_host(k1, d1, k2, d2, p1, p2, st, req)  # warm-up
         t0 = time.perf_counter()
-        c, _, _ = fclb.scene_pair_collide_batch_host(H, hm, k2, d2, p1, p2, st, req)
+        c, _, _ = fclb.scene_pair_collide_batch_host(k1, d1, k2, d2, p1, p2, st, req)
         t_gpu = time.perf_counter() - t0
         t0 = time.perf_counter()
-        e, _, _ = ref.scene_pair_collide_batch(1, hid, {M: 0, H: 1, O: 2}[k2], r2, p1, p2, 1, threads=threads, max_contacts=mc)
+        e, _, _ = ref.scene_pair_collide_batch({M: 0, H: 1, O: 2}[k1], r1, {M: 0, H: 1, O: 2}[k2], r2, p1, p2, 1, threads=threads, max_contacts=mc)
         t_cpu = time.perf_counter() - t0
         nn, nl = fclb.scene_last_visit_counts()
         diff = c.astype(np.int64) - e.astype(np.int64)
