@@ -600,15 +600,41 @@ int fclb_bvh_collide_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* 
   rc = ensureStage(e, total);
   if (rc) return rc;
   char* base = static_cast<char*>(e.d_stage);
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  rc = fclb_bvh_collide_batch_dev(bvh1, bvh2, base + o_p1, base + o_p2, n, scalar_type, req,
-                                  reinterpret_cast<uint32_t*>(base + o_cnt),
-                                  out_first_pair ? reinterpret_cast<int32_t*>(base + o_fp) : nullptr);
+  // Chunked three-stage pipeline, as fclb_distance_batch_host: every chunk's poses are queued on the copy-in stream up
+  // front, the compute stream waits per chunk, the copy-out stream drains a chunk's results while later chunks upload
+  // and traverse (queries are independent; per-query cost varies 100x, which the kernel's work counter absorbs).
+  const size_t chunk = e.host_chunk / 4 ? e.host_chunk / 4 : 1;
+  const int n_chunks = int((n + chunk - 1) / chunk);
+  rc = ensureChunkEvents(e, n_chunks);
   if (rc) return rc;
-  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
-  if (out_first_pair) FCLB_CUDA(cudaMemcpyAsync(out_first_pair, base + o_fp, n * 8, cudaMemcpyDeviceToHost, e.compute));
-  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  const char* h_p1 = static_cast<const char*>(poses1);
+  const char* h_p2 = static_cast<const char*>(poses2);
+  FCLB_CUDA(cudaStreamSynchronize(e.copy_out));  // the staging arena may still be read by an earlier call's copy-out
+  for (int c = 0; c < n_chunks; c++) {
+    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    FCLB_CUDA(cudaMemcpyAsync(base + o_p1 + b0 * 12 * ss, h_p1 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaMemcpyAsync(base + o_p2 + b0 * 12 * ss, h_p2 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaEventRecord(e.ev_in[c], e.copy_in));
+  }
+  unsigned long long visits[2] = {0, 0};
+  for (int c = 0; c < n_chunks; c++) {
+    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    FCLB_CUDA(cudaStreamWaitEvent(e.compute, e.ev_in[c], 0));
+    rc = fclb_bvh_collide_batch_dev(bvh1, bvh2, base + o_p1 + b0 * 12 * ss, base + o_p2 + b0 * 12 * ss, m, scalar_type, req,
+                                    reinterpret_cast<uint32_t*>(base + o_cnt) + b0,
+                                    out_first_pair ? reinterpret_cast<int32_t*>(base + o_fp) + 2 * b0 : nullptr);
+    if (rc) return rc;
+    visits[0] += g_last_stats[0];
+    visits[1] += g_last_stats[1];
+    FCLB_CUDA(cudaEventRecord(e.ev_done[c], e.compute));
+    FCLB_CUDA(cudaStreamWaitEvent(e.copy_out, e.ev_done[c], 0));
+    FCLB_CUDA(cudaMemcpyAsync(out_counts + b0, base + o_cnt + b0 * 4, m * 4, cudaMemcpyDeviceToHost, e.copy_out));
+    if (out_first_pair)
+      FCLB_CUDA(cudaMemcpyAsync(out_first_pair + 2 * b0, base + o_fp + b0 * 8, m * 8, cudaMemcpyDeviceToHost, e.copy_out));
+  }
+  g_last_stats[0] = visits[0];  // fclb_bvh_last_visit_counts: the whole call
+  g_last_stats[1] = visits[1];
+  FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
   return FCLB_OK;
 }
 
