@@ -556,6 +556,28 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """One process per GPU: run on (and therefore first-touch the pinned staging buffers of) the CPU socket the
+    GPU hangs off, so that the host side of the e2e copies does not cross the socket interconnect.  Best effort."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -587,6 +609,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     fclb.init(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -688,7 +711,8 @@ def main():
                    "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (wl.h2d_bytes() / 1e6)
                    if wl.h2d_bytes() > 200e6 else "inputs %.0f MB/step: smaller than L2 on purpose of the config; "
                    "each step re-reads them after %.0f MB of result writes" % (wl.h2d_bytes() / 1e6, wl.d2h_bytes() / 1e6),
-                   "sharding": "queries sharded by rank, geometry replicated, no collective on the data path"},
+                   "sharding": "queries sharded by rank, geometry replicated, no collective on the data path"
+                   + ("" if numa is None else "; rank processes bound to their GPU's NUMA node")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes(),
                 "d2h_bytes_per_step": wl.d2h_bytes(), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                 # the host link is what bounds this number once copies and kernels overlap: bytes moved per
