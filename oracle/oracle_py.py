@@ -276,6 +276,21 @@ class RefOracle(_Oracle):
         f.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_int]
         return int(f(_p(pts), len(pts), resolution, half_shape))
 
+    def octree_prune(self, oct_id, axis, center, extent):
+        """Octree2CollisionGeometry::pruneBy(OBB(axis, center, extent), rebuild=False): id of the pruned geometry."""
+        obb = np.concatenate([np.asarray(axis, np.float64).reshape(9), np.asarray(center, np.float64),
+                              np.asarray(extent, np.float64)])
+        f = self.fn("octree_prune")
+        f.argtypes = [C.c_int, C.c_void_p]
+        return int(f(oct_id, _p(np.ascontiguousarray(obb))))
+
+    def octree_export_pruned(self, oct_id, dtype, n_inner):
+        """prune_internal_nodes as bytes, or None when the geometry has no prune info"""
+        out = np.zeros(n_inner, np.uint8)
+        f = self.fn("octree_export_pruned")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        return out if f(oct_id, _st(dtype), _p(out)) else None
+
     def octree_export(self, oct_id, dtype):
         """(inner_children [n,8] u32, inner_full [n] u8, leaf_bits [m] u8, root_aabb [6] f64, n_layers)"""
         sizes = np.zeros(3, np.uint32)

@@ -170,8 +170,8 @@ void hmShapeBatch(int hm_id, const ShapeRec* shapes, uint32_t n_shapes, const ui
 
 // ---- octrees ---------------------------------------------------------------------------
 struct OctRec {
-  std::shared_ptr<fcl::Octree2CollisionGeometry<float>> f;
-  std::shared_ptr<fcl::Octree2CollisionGeometry<double>> d;
+  std::shared_ptr<const fcl::Octree2CollisionGeometry<float>> f;
+  std::shared_ptr<const fcl::Octree2CollisionGeometry<double>> d;
 };
 std::vector<OctRec>& octrees() {
   static std::vector<OctRec> t;
@@ -507,6 +507,37 @@ int fclref_octree_create(const double* points, size_t n_points, double resolutio
   octrees().push_back(r);
   return int(octrees().size()) - 1;
 }
+/* Octree2CollisionGeometry::pruneBy(obb, rebuild_octree = false) (octree_collision_geometry-inl.h, pruneOctreeByOBB,
+ * octree_prune-inl.h:10-103): a new geometry id sharing the tree, with prune info.  obb: axis[9] row-major, To[3], extent[3] */
+int fclref_octree_prune(int id, const double* obb) {
+  auto make = [&](auto tag) {
+    using S = decltype(tag);
+    fcl::OBB<S> bv;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) bv.axis(i, j) = S(obb[3 * i + j]);
+    for (int k = 0; k < 3; k++) {
+      bv.To[k] = S(obb[9 + k]);
+      bv.extent[k] = S(obb[12 + k]);
+    }
+    return bv;
+  };
+  OctRec r;
+  r.f = octrees().at(id).f->pruneBy(make(float(0)), false);
+  r.d = octrees().at(id).d->pruneBy(make(double(0)), false);
+  octrees().push_back(r);
+  return int(octrees().size()) - 1;
+}
+/* prune_internal_nodes as bytes; returns 0 when the geometry carries no prune info */
+int fclref_octree_export_pruned(int id, int scalar_type, uint8_t* pruned) {
+  auto dump = [&](const auto* g) {
+    const std::vector<bool>* p = g->prune_internal_nodes();
+    if (!p) return 0;
+    for (size_t i = 0; i < p->size(); i++) pruned[i] = (*p)[i] ? 1 : 0;
+    return 1;
+  };
+  return scalar_type == 0 ? dump(getOct<float>(id)) : dump(getOct<double>(id));
+}
+
 /* sizes[0..2] = n_inner, n_leaf, n_layers */
 int fclref_octree_sizes(int id, int scalar_type, uint32_t* sizes) {
   auto get = [&](const auto* g) {
