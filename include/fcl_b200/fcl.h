@@ -27,6 +27,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <iostream>
 #include <memory>
 #include <vector>
@@ -308,11 +309,67 @@ class HeightMapCollisionGeometry : public CollisionGeometry<S> {
   fclb_handle handle_ = 0;
 };
 
-// geometry/octree2/octree_collision_geometry.h: the octree is built by the caller (mind-fcl's octree2::Octree in
-// an integration) and handed over as its flat node arrays (see fclb_octree_upload).
+// geometry/octree2/octree.h: Octree<S>(bottom_resolution, bottom_half_shape) + rebuildTree(generator, n_points).
+// The tree lives on the host as the reference's flat node arrays, numbered as the reference numbers them
+// (fclb_octree_build_host), until it is wrapped in an Octree2CollisionGeometry, which uploads it.
+namespace octree2 {
+template <typename S>
+class Octree {
+ public:
+  using PointGenerationFunc = std::function<void(int index, S& x, S& y, S& z)>;
+  Octree(S bottom_resolution_xyz, std::uint16_t bottom_half_shape) : resolution_(bottom_resolution_xyz), half_(bottom_half_shape) {
+    rebuildTree([](int, S&, S&, S&) {}, 0);
+  }
+  // octree_construction-inl.h:181-205
+  void rebuildTree(const PointGenerationFunc& point_generator, int n_points) {
+    std::vector<double> pts(std::size_t(3) * n_points);
+    for (int i = 0; i < n_points; i++) {
+      S x, y, z;
+      point_generator(i, x, y, z);
+      pts[3 * std::size_t(i)] = double(x);
+      pts[3 * std::size_t(i) + 1] = double(y);
+      pts[3 * std::size_t(i) + 2] = double(z);
+    }
+    uint32_t n_inner = 0, n_leaf = 0;
+    const int st = detail::scalarType<S>();
+    int rc = fclb_octree_build_host(pts.data(), std::size_t(n_points), double(resolution_), half_, st, nullptr, nullptr, 0,
+                                    &n_inner, nullptr, 0, &n_leaf, root_aabb_.data(), &n_layers_);
+    if (rc != FCLB_ERR_CAPACITY) detail::check(rc ? rc : FCLB_ERR_BAD_ARG, "fclb_octree_build_host");
+    inner_children_.assign(std::size_t(8) * n_inner, 0);
+    inner_full_.assign(n_inner, 0);
+    leaf_bits_.assign(n_leaf ? n_leaf : 1, 0);
+    detail::check(fclb_octree_build_host(pts.data(), std::size_t(n_points), double(resolution_), half_, st, inner_children_.data(),
+                                         inner_full_.data(), n_inner, &n_inner, leaf_bits_.data(), uint32_t(leaf_bits_.size()),
+                                         &n_leaf, root_aabb_.data(), &n_layers_),
+                  "fclb_octree_build_host");
+    leaf_bits_.resize(n_leaf);
+  }
+  std::uint8_t n_layers() const { return std::uint8_t(n_layers_); }
+  std::size_t n_inner_nodes() const { return inner_full_.size(); }
+  std::size_t n_leaf_nodes() const { return leaf_bits_.size(); }
+  const std::vector<uint32_t>& inner_children() const { return inner_children_; }
+  const std::vector<uint8_t>& inner_nodes_fully_occupied() const { return inner_full_; }
+  const std::vector<uint8_t>& leaf_bits() const { return leaf_bits_; }
+  const std::array<double, 6>& root_aabb() const { return root_aabb_; }
+
+ private:
+  S resolution_;
+  std::uint16_t half_;
+  int n_layers_ = 0;
+  std::vector<uint32_t> inner_children_;
+  std::vector<uint8_t> inner_full_, leaf_bits_;
+  std::array<double, 6> root_aabb_{};
+};
+}  // namespace octree2
+
+// geometry/octree2/octree_collision_geometry.h: wraps an octree2::Octree built here, or the flat node arrays of an
+// octree the caller built with mind-fcl (see fclb_octree_upload).
 template <typename S>
 class Octree2CollisionGeometry : public CollisionGeometry<S> {
  public:
+  explicit Octree2CollisionGeometry(std::shared_ptr<const octree2::Octree<S>> octree)
+      : Octree2CollisionGeometry(octree->inner_children(), octree->inner_nodes_fully_occupied(), octree->leaf_bits(),
+                                 octree->root_aabb(), int(octree->n_layers())) {}
   Octree2CollisionGeometry(const std::vector<uint32_t>& inner_children, const std::vector<uint8_t>& inner_full,
                            const std::vector<uint8_t>& leaf_bits, const std::array<double, 6>& root_aabb, int n_layers) {
     detail::check(fclb_octree_upload(inner_children.data(), inner_full.data(), uint32_t(inner_full.size()), leaf_bits.data(),

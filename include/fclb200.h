@@ -289,6 +289,20 @@ int fclb_octree_upload(const uint32_t* inner_children, const uint8_t* inner_full
                        const uint8_t* leaf_bits, uint32_t n_leaf, const uint8_t* pruned_or_null,
                        const double* root_aabb, int num_layers, fclb_handle* octree);
 int fclb_octree_release(fclb_handle octree);
+/* Host-side mirror of octree2::Octree<S>(resolution, bottom_half_shape) + rebuildTree
+ * (geometry/octree2/octree-inl.h:15-142, octree_construction-inl.h:10-74,111-205): inserts n_points
+ * (x, y, z doubles, rounded once to S; out-of-range points dropped) in stream order, so inner / leaf nodes get the
+ * reference's numbering (the contact ids of the octree kernels), then sets the fully-occupied flags.
+ * bottom_half_shape: power of two >= 2.  Host only, no GPU needed.  Always writes *n_inner / *n_leaf (and
+ * root_aabb[6], *num_layers when non-NULL); returns FCLB_ERR_CAPACITY without writing the arrays when they are
+ * NULL or smaller than that -- call once for the sizes, once for the data. */
+int fclb_octree_build_host(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape,
+                           int scalar_type, uint32_t* inner_children, uint8_t* inner_full, uint32_t inner_capacity,
+                           uint32_t* n_inner, uint8_t* leaf_bits, uint32_t leaf_capacity, uint32_t* n_leaf,
+                           double* root_aabb, int* num_layers);
+/* the same builder followed by fclb_octree_upload (no prune mask) */
+int fclb_octree_build(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
+                      fclb_handle* octree);
 int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
                                          const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
                                          const fclb_request* req, uint32_t* out_counts, int64_t* out_first_node);

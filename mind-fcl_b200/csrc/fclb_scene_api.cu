@@ -4,6 +4,7 @@
 #include <cmath>
 
 #include "fclb_bvh.cuh"
+#include "fclb_octree_build.h"
 #include "fclb_shapes.cuh"
 
 namespace fclb {
@@ -872,6 +873,56 @@ int fclb_octree_upload(const uint32_t* inner_children, const uint8_t* inner_full
   octTable()[h] = d;
   *octree = h;
   return FCLB_OK;
+}
+
+namespace {
+int octreeBuildHostImpl(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
+                        fclb::hostbuild::OctreeHost& t, const char* who) {
+  if ((n_points && !points) || bottom_half_shape < 2 || bottom_half_shape > 16384 ||
+      (bottom_half_shape & (bottom_half_shape - 1)) || !(resolution > 0) || n_points > 0x7fffffffu)
+    return fail(FCLB_ERR_BAD_ARG, who);
+  if (scalar_type == FCLB_F32)
+    fclb::hostbuild::octreeFromPoints<float>(points, n_points, float(resolution), bottom_half_shape, t);
+  else if (scalar_type == FCLB_F64)
+    fclb::hostbuild::octreeFromPoints<double>(points, n_points, resolution, bottom_half_shape, t);
+  else
+    return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  return FCLB_OK;
+}
+}  // namespace
+
+int fclb_octree_build_host(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape,
+                           int scalar_type, uint32_t* inner_children, uint8_t* inner_full, uint32_t inner_capacity,
+                           uint32_t* n_inner, uint8_t* leaf_bits, uint32_t leaf_capacity, uint32_t* n_leaf,
+                           double* root_aabb, int* num_layers) {
+  if (!n_inner || !n_leaf) return fail(FCLB_ERR_BAD_ARG, "fclb_octree_build_host: bad argument");
+  fclb::hostbuild::OctreeHost t;
+  int rc = octreeBuildHostImpl(points, n_points, resolution, bottom_half_shape, scalar_type, t,
+                               "fclb_octree_build_host: bad argument (half shape: power of two >= 2)");
+  if (rc) return rc;
+  *n_inner = uint32_t(t.n_inner());
+  *n_leaf = uint32_t(t.leaf_bits.size());
+  if (num_layers) *num_layers = t.num_layers;
+  if (root_aabb)
+    for (int k = 0; k < 6; k++) root_aabb[k] = t.root_box[k];
+  if (!inner_children || !inner_full || !leaf_bits || inner_capacity < *n_inner || leaf_capacity < *n_leaf)
+    return fail(FCLB_ERR_CAPACITY, "fclb_octree_build_host: arrays too small (sizes returned)");
+  std::copy(t.children.begin(), t.children.end(), inner_children);
+  std::copy(t.full.begin(), t.full.end(), inner_full);
+  std::copy(t.leaf_bits.begin(), t.leaf_bits.end(), leaf_bits);
+  return FCLB_OK;
+}
+
+int fclb_octree_build(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
+                      fclb_handle* octree) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  fclb::hostbuild::OctreeHost t;
+  rc = octreeBuildHostImpl(points, n_points, resolution, bottom_half_shape, scalar_type, t,
+                           "fclb_octree_build: bad argument (half shape: power of two >= 2)");
+  if (rc) return rc;
+  return fclb_octree_upload(t.children.data(), t.full.data(), uint32_t(t.n_inner()), t.leaf_bits.data(),
+                            uint32_t(t.leaf_bits.size()), nullptr, t.root_box, t.num_layers, octree);
 }
 
 int fclb_octree_release(fclb_handle h) {

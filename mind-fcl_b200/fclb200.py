@@ -37,7 +37,8 @@ EXPORTS = [
     "fclb_heightmap_upload", "fclb_heightmap_release", "fclb_heightmap_build_host",
     "fclb_heightmap_build_dev", "fclb_heightmap_build_points_host", "fclb_heightmap_info", "fclb_heightmap_export",
     "fclb_heightmap_shape_collide_batch_host", "fclb_heightmap_shape_collide_batch_dev",
-    "fclb_octree_upload", "fclb_octree_release", "fclb_octree_shape_collide_batch_host",
+    "fclb_octree_upload", "fclb_octree_release", "fclb_octree_build_host", "fclb_octree_build",
+    "fclb_octree_shape_collide_batch_host",
     "fclb_octree_shape_collide_batch_dev",
     "fclb_scene_shape_contacts_batch_host", "fclb_scene_shape_contacts_batch_dev",
     "fclb_scene_pair_collide_batch_host", "fclb_scene_pair_collide_batch_dev",
@@ -181,6 +182,10 @@ def load() -> C.CDLL:
     if hasattr(lib, "fclb_octree_upload"):
         lib.fclb_octree_upload.argtypes = [vp, vp, u32, vp, u32, vp, vp, C.c_int, C.POINTER(C.c_uint64)]
         lib.fclb_octree_release.argtypes = [C.c_uint64]
+    if hasattr(lib, "fclb_octree_build_host"):
+        lib.fclb_octree_build_host.argtypes = [vp, sz, C.c_double, u32, C.c_int, vp, vp, u32, C.POINTER(u32), vp, u32,
+                                               C.POINTER(u32), vp, C.POINTER(C.c_int)]
+        lib.fclb_octree_build.argtypes = [vp, sz, C.c_double, u32, C.c_int, C.POINTER(C.c_uint64)]
         os_args = [C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp]
         lib.fclb_octree_shape_collide_batch_host.argtypes = os_args
         lib.fclb_octree_shape_collide_batch_dev.argtypes = os_args
@@ -584,6 +589,33 @@ def octree_upload(inner_children, inner_full, leaf_bits, root_aabb, n_layers, pr
     h = C.c_uint64()
     check(load().fclb_octree_upload(_ptr(ch), _ptr(full), len(full), _ptr(leaf), len(leaf), _ptr(pr), _ptr(root), n_layers,
                                     C.byref(h)))
+    return h.value
+
+
+def octree_build_host(points, resolution, half_shape, scalar_type):
+    """The host builder alone (no GPU) = octree2::Octree<S>(resolution, half_shape).rebuildTree(points):
+    (inner_children [n,8] u32, inner_full [n] u8, leaf_bits [m] u8, root_aabb [6] f64, n_layers)."""
+    pts = np.ascontiguousarray(points, np.float64)
+    ni, nl, layers = C.c_uint32(), C.c_uint32(), C.c_int()
+    root = np.zeros(6, np.float64)
+    fn = load().fclb_octree_build_host
+    rc = fn(_ptr(pts), len(pts), resolution, half_shape, scalar_type, None, None, 0, C.byref(ni), None, 0, C.byref(nl),
+            _ptr(root), C.byref(layers))
+    if rc != 5:  # FCLB_ERR_CAPACITY is the answer to the size query
+        check(rc if rc else 3)
+    ch = np.zeros((ni.value, 8), np.uint32)
+    full = np.zeros(ni.value, np.uint8)
+    leaf = np.zeros(max(nl.value, 1), np.uint8)
+    check(fn(_ptr(pts), len(pts), resolution, half_shape, scalar_type, _ptr(ch), _ptr(full), ni.value, C.byref(ni), _ptr(leaf),
+             len(leaf), C.byref(nl), _ptr(root), C.byref(layers)))
+    return ch, full, leaf[:nl.value], root, layers.value
+
+
+def octree_build(points, resolution, half_shape, scalar_type) -> int:
+    """octree_build_host + upload: a device octree straight from a point cloud."""
+    pts = np.ascontiguousarray(points, np.float64)
+    h = C.c_uint64()
+    check(load().fclb_octree_build(_ptr(pts), len(pts), resolution, half_shape, scalar_type, C.byref(h)))
     return h.value
 
 

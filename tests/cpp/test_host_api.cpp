@@ -159,6 +159,27 @@ void runScene() {
     EXPECT_TRUE(collide<S>(&hm, I, &sheet, at(0, S(-0.5), S(0.6)), req, above) == 0);
   }
   {
+    // octree2::Octree built from points (rebuildTree) and wrapped as the reference wraps it: four voxels in a row
+    auto tree = std::make_shared<octree2::Octree<S>>(S(0.1), std::uint16_t(8));  // 16^3 voxels, +-0.8 m
+    EXPECT_TRUE(tree->n_layers() == 5 && tree->n_inner_nodes() == 1 && tree->n_leaf_nodes() == 0);
+    tree->rebuildTree(
+        [](int i, S& x, S& y, S& z) {
+          x = S(0.05) + S(0.1) * S(i % 4);
+          y = S(0.05);
+          z = S(0.05);
+        },
+        8);  // every voxel named twice
+    EXPECT_TRUE(tree->n_inner_nodes() == 3 && tree->n_leaf_nodes() == 2);  // root + two levels above two 2x2x2 cells
+    EXPECT_TRUE(tree->leaf_bits()[0] == 3 && tree->leaf_bits()[1] == 3);
+    Octree2CollisionGeometry<S> oct(tree);
+    Box<S> small(S(0.06), S(0.06), S(0.06)), bar(S(0.5), S(0.06), S(0.06));
+    CollisionRequest<S> req(100);
+    CollisionResult<S> one, none, four;
+    EXPECT_TRUE(collide<S>(&oct, I, &small, at(S(0.05), S(0.05), S(0.05)), req, one) == 1);
+    EXPECT_TRUE(collide<S>(&oct, I, &small, at(S(0.05), S(0.05), S(0.5)), req, none) == 0);
+    EXPECT_TRUE(collide<S>(&oct, I, &bar, at(S(0.2), S(0.05), S(0.05)), req, four) == 4);
+  }
+  {
     // directed penetration: two unit spheres 1.5 apart along x, escape direction +x => depth 0.5
     Sphere<S> a(1), b(1);
     CollisionRequest<S> req(1);

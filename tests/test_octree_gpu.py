@@ -83,3 +83,30 @@ def test_octree_shape_every_type(fclb, ref_oracle, dtype):
     assert not c.any()
     fclb.release(table)
     fclb.octree_release(oct_h)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_octree_built_here(fclb, ref_oracle, dtype):
+    """fclb_octree_build (our host mirror of Octree<S>::rebuildTree + upload) instead of the reference's arrays:
+    counts AND the reported node ids (the reference's node numbering) equal the reference's."""
+    st = fclb.F32 if dtype == np.float32 else fclb.F64
+    pts = octree_points(11)
+    oid = ref_oracle.octree_create(pts, RES, HALF)
+    oct_h = fclb.octree_build(pts, RES, HALF, st)
+    shapes = list(PRIMS.values())
+    table = fclb.shapes_upload(shapes)
+    n = 4000
+    p_oct, p_sh = scenes.heightmap_query_poses(n, dtype, 0.4, -0.25, 0.25, seed=5100)
+    ids = (np.arange(n) % len(shapes)).astype(np.uint32)
+    for mc in (1, 2**31 - 1):
+        req = fclb.make_request(max_contacts=mc)
+        counts, node = fclb.octree_shape_collide_batch_host(oct_h, table, ids, p_oct, p_sh, st, req, want_node=True)
+        e_counts, e_node = ref_oracle.octree_shape_collide_batch(oid, shapes, ids, p_oct, p_sh, threads=8, max_contacts=mc)
+        assert np.array_equal(counts, e_counts)
+        assert ((node >= 0) == (e_counts > 0)).all()
+        single = e_counts == 1  # one contact: the id is determined
+        if mc > 1:
+            assert single.any() and np.array_equal(node[single], e_node[single])
+    print(f"[octree built here {np.dtype(dtype).name}] n={n} colliding={int((e_counts > 0).sum())} contacts={int(e_counts.sum())}")
+    fclb.release(table)
+    fclb.octree_release(oct_h)
