@@ -300,6 +300,15 @@ int fclb_octree_build_host(const double* points, size_t n_points, double resolut
                            int scalar_type, uint32_t* inner_children, uint8_t* inner_full, uint32_t inner_capacity,
                            uint32_t* n_inner, uint8_t* leaf_bits, uint32_t leaf_capacity, uint32_t* n_leaf,
                            double* root_aabb, int* num_layers);
+/* Host-side mirror of octree2::pruneOctreeByOBB (geometry/octree2/octree_prune-inl.h:10-103) = what
+ * Octree2CollisionGeometry::pruneBy(obb, rebuild_octree = false) computes: inner nodes inside the OBB are marked
+ * pruned, voxels whose centre is inside it are cleared from the leaf masks, and the fully-occupied flags are
+ * re-derived.  obb: axis[9] row-major (columns = box directions), To[3], extent[3].  pruned / inner_full / leaf_bits
+ * are IN-OUT (the OctreePruneInfo being extended): pass zeros and the tree's own flags / masks for a first prune, the
+ * previous outputs for a further one; upload the three with fclb_octree_upload.  Host only, no GPU needed. */
+int fclb_octree_prune_host(const uint32_t* inner_children, uint32_t n_inner, uint32_t n_leaf, const double* root_aabb,
+                           int num_layers, const double* obb, int scalar_type, uint8_t* pruned, uint8_t* inner_full,
+                           uint8_t* leaf_bits);
 /* the same builder followed by fclb_octree_upload (no prune mask) */
 int fclb_octree_build(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
                       fclb_handle* octree);

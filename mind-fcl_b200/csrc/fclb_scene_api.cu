@@ -925,6 +925,23 @@ int fclb_octree_build(const double* points, size_t n_points, double resolution, 
                             uint32_t(t.leaf_bits.size()), nullptr, t.root_box, t.num_layers, octree);
 }
 
+int fclb_octree_prune_host(const uint32_t* inner_children, uint32_t n_inner, uint32_t n_leaf, const double* root_aabb,
+                           int num_layers, const double* obb, int scalar_type, uint8_t* pruned, uint8_t* inner_full,
+                           uint8_t* leaf_bits) {
+  if (!inner_children || !n_inner || !root_aabb || num_layers < 3 || !obb || !pruned || !inner_full || (n_leaf && !leaf_bits))
+    return fail(FCLB_ERR_BAD_ARG, "fclb_octree_prune_host: bad argument");
+  for (size_t i = 0; i < size_t(8) * n_inner; i++)
+    if (inner_children[i] != 0xffffffffu && inner_children[i] >= (n_inner > n_leaf ? n_inner : n_leaf))
+      return fail(FCLB_ERR_BAD_ARG, "fclb_octree_prune_host: child index out of range");
+  if (scalar_type == FCLB_F32)
+    fclb::hostbuild::octreePrune<float>(inner_children, num_layers, root_aabb, obb, pruned, inner_full, leaf_bits);
+  else if (scalar_type == FCLB_F64)
+    fclb::hostbuild::octreePrune<double>(inner_children, num_layers, root_aabb, obb, pruned, inner_full, leaf_bits);
+  else
+    return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  return FCLB_OK;
+}
+
 int fclb_octree_release(fclb_handle h) {
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);

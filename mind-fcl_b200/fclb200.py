@@ -37,7 +37,7 @@ EXPORTS = [
     "fclb_heightmap_upload", "fclb_heightmap_release", "fclb_heightmap_build_host",
     "fclb_heightmap_build_dev", "fclb_heightmap_build_points_host", "fclb_heightmap_info", "fclb_heightmap_export",
     "fclb_heightmap_shape_collide_batch_host", "fclb_heightmap_shape_collide_batch_dev",
-    "fclb_octree_upload", "fclb_octree_release", "fclb_octree_build_host", "fclb_octree_build",
+    "fclb_octree_upload", "fclb_octree_release", "fclb_octree_build_host", "fclb_octree_build", "fclb_octree_prune_host",
     "fclb_octree_shape_collide_batch_host",
     "fclb_octree_shape_collide_batch_dev",
     "fclb_scene_shape_contacts_batch_host", "fclb_scene_shape_contacts_batch_dev",
@@ -186,6 +186,7 @@ def load() -> C.CDLL:
         lib.fclb_octree_build_host.argtypes = [vp, sz, C.c_double, u32, C.c_int, vp, vp, u32, C.POINTER(u32), vp, u32,
                                                C.POINTER(u32), vp, C.POINTER(C.c_int)]
         lib.fclb_octree_build.argtypes = [vp, sz, C.c_double, u32, C.c_int, C.POINTER(C.c_uint64)]
+        lib.fclb_octree_prune_host.argtypes = [vp, u32, u32, vp, C.c_int, vp, C.c_int, vp, vp, vp]
         os_args = [C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp]
         lib.fclb_octree_shape_collide_batch_host.argtypes = os_args
         lib.fclb_octree_shape_collide_batch_dev.argtypes = os_args
@@ -609,6 +610,22 @@ def octree_build_host(points, resolution, half_shape, scalar_type):
     check(fn(_ptr(pts), len(pts), resolution, half_shape, scalar_type, _ptr(ch), _ptr(full), ni.value, C.byref(ni), _ptr(leaf),
              len(leaf), C.byref(nl), _ptr(root), C.byref(layers)))
     return ch, full, leaf[:nl.value], root, layers.value
+
+
+def octree_prune_host(inner_children, inner_full, leaf_bits, root_aabb, n_layers, axis, center, extent, scalar_type,
+                      pruned=None):
+    """pruneOctreeByOBB on the flat arrays (no GPU): returns new (pruned, inner_full, leaf_bits); the inputs are kept.
+    Pass the previous outputs (and pruned) to prune further."""
+    ch = np.ascontiguousarray(inner_children, np.uint32)
+    full = np.array(inner_full, np.uint8)
+    leaf = np.array(leaf_bits, np.uint8)
+    pr = np.zeros(len(full), np.uint8) if pruned is None else np.array(pruned, np.uint8)
+    root = np.ascontiguousarray(root_aabb, np.float64)
+    obb = np.ascontiguousarray(np.concatenate([np.asarray(axis, np.float64).reshape(9), np.asarray(center, np.float64),
+                                               np.asarray(extent, np.float64)]))
+    check(load().fclb_octree_prune_host(_ptr(ch), len(full), len(leaf), _ptr(root), n_layers, _ptr(obb), scalar_type,
+                                        _ptr(pr), _ptr(full), _ptr(leaf)))
+    return pr, full, leaf
 
 
 def octree_build(points, resolution, half_shape, scalar_type) -> int:

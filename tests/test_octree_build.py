@@ -54,3 +54,50 @@ def test_tree_matches_reference(ref_oracle, half_shape, res, seed):
         assert np.array_equal(leaf, r_leaf)
         if half_shape == 64:
             assert full.any() and (leaf == 255).any() and (leaf != 255).any()
+
+
+@pytest.mark.parametrize("half_shape,res,seed", [(64, 0.01, 7), (16, 0.04, 8)])
+def test_prune_matches_reference(ref_oracle, half_shape, res, seed):
+    """fclb_octree_prune_host against Octree2CollisionGeometry::pruneBy(obb, rebuild=False) (pruneOctreeByOBB,
+    octree_prune-inl.h:10-103): prune mask, new leaf masks and new fully-occupied flags identical for chains of
+    cumulative prunes by random boxes -- incl. axis-aligned boxes whose faces lie ON voxel faces / centres, where
+    the float SSE association of OBB<float>::overlap decides -- float and double."""
+    import fclb200 as fclb
+    import scenes
+
+    pts = octree_points(seed)
+    oid = ref_oracle.octree_create(pts, res, half_shape)
+    rng = np.random.Generator(np.random.PCG64(100 + seed))
+    span = res * half_shape
+    n_chain, per_chain = 12, 3
+    total_pruned = total_leaf = 0
+    for c in range(n_chain):
+        ours = {}
+        for dt, st in ((np.float32, fclb.F32), (np.float64, fclb.F64)):
+            ch, full, leaf, root, layers = ref_oracle.octree_export(oid, dt)
+            ours[dt] = [ch, root, layers, None, full, leaf]
+        pid = oid
+        for k in range(per_chain):
+            if c % 3 == 0:  # lattice-aligned box: centre and extents multiples of half a voxel
+                axis = np.eye(3)
+                center = rng.integers(-half_shape, half_shape, 3) * res * 0.5
+                extent = rng.integers(1, half_shape, 3) * res * 0.5
+            else:
+                e = rng.uniform(-np.pi, np.pi, 3)
+                axis = scenes.euler_to_matrix(e[:1], e[1:2], e[2:3])[0]
+                center = rng.uniform(-0.6 * span, 0.6 * span, 3)
+                extent = rng.uniform(0.05 * span, 0.5 * span, 3)
+            pid = ref_oracle.octree_prune(pid, axis, center, extent)
+            for dt, st in ((np.float32, fclb.F32), (np.float64, fclb.F64)):
+                ch, root, layers, pruned, full, leaf = ours[dt]
+                pruned, full, leaf = fclb.octree_prune_host(ch, full, leaf, root, layers, axis, center, extent, st, pruned=pruned)
+                ours[dt][3:] = [pruned, full, leaf]
+                r_ch, r_full, r_leaf, _, _ = ref_oracle.octree_export(pid, dt)
+                r_pruned = ref_oracle.octree_export_pruned(pid, dt, len(r_full))
+                assert np.array_equal(pruned, r_pruned), (c, k, dt, np.nonzero(pruned != r_pruned)[0][:8])
+                assert np.array_equal(leaf, r_leaf), (c, k, dt, np.nonzero(leaf != r_leaf)[0][:8])
+                assert np.array_equal(full, r_full), (c, k, dt, np.nonzero(full != r_full)[0][:8])
+        total_pruned += int(ours[np.float32][3].sum())
+        total_leaf += int((ours[np.float32][5] != ref_oracle.octree_export(oid, np.float32)[2]).sum())
+    assert total_pruned > 0 and total_leaf > 0
+    print(f"prune chains: {total_pruned} inner nodes pruned, {total_leaf} leaf masks changed over {n_chain} chains")
