@@ -362,27 +362,64 @@ class Octree {
 };
 }  // namespace octree2
 
+// math/bv/OBB.h: the fields pruneBy reads (axis columns = box directions, centre To, half extents)
+template <typename S>
+struct OBB {
+  Matrix3<S> axis;
+  Vector3<S> To;
+  Vector3<S> extent;
+};
+
 // geometry/octree2/octree_collision_geometry.h: wraps an octree2::Octree built here, or the flat node arrays of an
-// octree the caller built with mind-fcl (see fclb_octree_upload).
+// octree the caller built with mind-fcl (see fclb_octree_upload).  The host arrays are kept so that pruneBy can
+// extend the prune info the way OctreePruneInfo does (octree_node.h:56-72).
 template <typename S>
 class Octree2CollisionGeometry : public CollisionGeometry<S> {
  public:
+  using ConstPtr = std::shared_ptr<const Octree2CollisionGeometry<S>>;
   explicit Octree2CollisionGeometry(std::shared_ptr<const octree2::Octree<S>> octree)
       : Octree2CollisionGeometry(octree->inner_children(), octree->inner_nodes_fully_occupied(), octree->leaf_bits(),
                                  octree->root_aabb(), int(octree->n_layers())) {}
   Octree2CollisionGeometry(const std::vector<uint32_t>& inner_children, const std::vector<uint8_t>& inner_full,
-                           const std::vector<uint8_t>& leaf_bits, const std::array<double, 6>& root_aabb, int n_layers) {
-    detail::check(fclb_octree_upload(inner_children.data(), inner_full.data(), uint32_t(inner_full.size()), leaf_bits.data(),
-                                     uint32_t(leaf_bits.size()), nullptr, root_aabb.data(), n_layers, &handle_),
+                           const std::vector<uint8_t>& leaf_bits, const std::array<double, 6>& root_aabb, int n_layers,
+                           const std::vector<uint8_t>& pruned = {})
+      : children_(inner_children), full_(inner_full), leaf_(leaf_bits), pruned_(pruned), root_(root_aabb), n_layers_(n_layers) {
+    detail::check(fclb_octree_upload(children_.data(), full_.data(), uint32_t(full_.size()), leaf_.data(), uint32_t(leaf_.size()),
+                                     pruned_.empty() ? nullptr : pruned_.data(), root_.data(), n_layers_, &handle_),
                   "fclb_octree_upload");
   }
   ~Octree2CollisionGeometry() override { fclb_octree_release(handle_); }
+  // pruneBy(obb, rebuild_octree = false), octree_collision_geometry-inl.h:97-130: a new geometry over the same nodes
+  // whose prune info is this one's extended by the box (pruneOctreeByOBB).  Consolidating the pruned tree into a
+  // renumbered one (rebuild_octree = true) is not offered.
+  ConstPtr pruneBy(const OBB<S>& obb, bool rebuild_octree = false) const {
+    if (rebuild_octree) detail::check(FCLB_ERR_UNSUPPORTED, "Octree2CollisionGeometry::pruneBy(rebuild_octree = true)");
+    double o[15];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) o[3 * i + j] = double(obb.axis(i, j));
+    for (int k = 0; k < 3; k++) {
+      o[9 + k] = double(obb.To[k]);
+      o[12 + k] = double(obb.extent[k]);
+    }
+    std::vector<uint8_t> pruned = pruned_.empty() ? std::vector<uint8_t>(full_.size(), 0) : pruned_, full = full_, leaf = leaf_;
+    detail::check(fclb_octree_prune_host(children_.data(), uint32_t(full.size()), uint32_t(leaf.size()), root_.data(), n_layers_, o,
+                                         detail::scalarType<S>(), pruned.data(), full.data(), leaf.data()),
+                  "fclb_octree_prune_host");
+    return std::make_shared<const Octree2CollisionGeometry<S>>(children_, full, leaf, root_, n_layers_, pruned);
+  }
   NODE_TYPE getNodeType() const override { return GEOM_OCTREE2; }
   bool isShape() const override { return false; }
   fclb_shape shapeRecord() const override { return fclb_shape{}; }
   fclb_handle handle() const { return handle_; }
+  const std::vector<uint8_t>& inner_nodes_fully_occupied() const { return full_; }
+  const std::vector<uint8_t>& leaf_bits() const { return leaf_; }
+  const std::vector<uint8_t>* prune_internal_nodes() const { return pruned_.empty() ? nullptr : &pruned_; }
 
  private:
+  std::vector<uint32_t> children_;
+  std::vector<uint8_t> full_, leaf_, pruned_;
+  std::array<double, 6> root_;
+  int n_layers_;
   fclb_handle handle_ = 0;
 };
 

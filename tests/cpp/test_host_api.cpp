@@ -178,6 +178,15 @@ void runScene() {
     EXPECT_TRUE(collide<S>(&oct, I, &small, at(S(0.05), S(0.05), S(0.05)), req, one) == 1);
     EXPECT_TRUE(collide<S>(&oct, I, &small, at(S(0.05), S(0.05), S(0.5)), req, none) == 0);
     EXPECT_TRUE(collide<S>(&oct, I, &bar, at(S(0.2), S(0.05), S(0.05)), req, four) == 4);
+    // pruneBy: cut the two voxels with x < 0.2 out of the tree
+    OBB<S> cut;
+    cut.To = Vector3<S>(S(0.1), S(0.05), S(0.05));
+    cut.extent = Vector3<S>(S(0.09), S(0.2), S(0.2));
+    auto rest = oct.pruneBy(cut, false);
+    EXPECT_TRUE(rest->prune_internal_nodes() != nullptr && rest->leaf_bits()[0] == 0 && rest->leaf_bits()[1] == 3);
+    CollisionResult<S> gone, two;
+    EXPECT_TRUE(collide<S>(rest.get(), I, &small, at(S(0.05), S(0.05), S(0.05)), req, gone) == 0);
+    EXPECT_TRUE(collide<S>(rest.get(), I, &bar, at(S(0.2), S(0.05), S(0.05)), req, two) == 2);
   }
   {
     // directed penetration: two unit spheres 1.5 apart along x, escape direction +x => depth 0.5

@@ -24,6 +24,12 @@ def pruned_octree(fclb, ref_oracle, dtype):
     pruned = ref_oracle.octree_export_pruned(pid, dtype, len(full))
     assert pruned is not None and pruned.any() and np.array_equal(ch, ch0)
     assert (leaf != leaf0).any() and (full != full0).any()
+    # the same two prunes through our host mirror of pruneOctreeByOBB: identical prune info
+    st = fclb.F32 if dtype == np.float32 else fclb.F64
+    m_pr, m_full, m_leaf = fclb.octree_prune_host(ch0, full0, leaf0, root, n_layers, axis, (0.05, -0.1, -0.05), (0.22, 0.15, 0.12), st)
+    m_pr, m_full, m_leaf = fclb.octree_prune_host(ch0, m_full, m_leaf, root, n_layers, np.eye(3), (-0.25, 0.2, 0.0), (0.1, 0.1, 0.3),
+                                                  st, pruned=m_pr)
+    assert np.array_equal(m_pr, pruned) and np.array_equal(m_full, full) and np.array_equal(m_leaf, leaf)
     print(f"pruned octree: {int(pruned.sum())} of {len(full)} inner nodes pruned, {int((leaf != leaf0).sum())} leaf masks "
           f"changed, fully occupied inner nodes {int(full0.sum())} -> {int(full.sum())}")
     return oid, pid, fclb.octree_upload(ch, full, leaf, root, n_layers, pruned=pruned)
