@@ -390,10 +390,9 @@ class Octree2CollisionGeometry : public CollisionGeometry<S> {
   }
   ~Octree2CollisionGeometry() override { fclb_octree_release(handle_); }
   // pruneBy(obb, rebuild_octree = false), octree_collision_geometry-inl.h:97-130: a new geometry over the same nodes
-  // whose prune info is this one's extended by the box (pruneOctreeByOBB).  Consolidating the pruned tree into a
-  // renumbered one (rebuild_octree = true) is not offered.
+  // whose prune info is this one's extended by the box (pruneOctreeByOBB); with rebuild_octree the pruned tree is
+  // consolidated into a renumbered one without prune info (Octree::rebuildAccordingToPruneInfo).
   ConstPtr pruneBy(const OBB<S>& obb, bool rebuild_octree = false) const {
-    if (rebuild_octree) detail::check(FCLB_ERR_UNSUPPORTED, "Octree2CollisionGeometry::pruneBy(rebuild_octree = true)");
     double o[15];
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) o[3 * i + j] = double(obb.axis(i, j));
@@ -405,7 +404,18 @@ class Octree2CollisionGeometry : public CollisionGeometry<S> {
     detail::check(fclb_octree_prune_host(children_.data(), uint32_t(full.size()), uint32_t(leaf.size()), root_.data(), n_layers_, o,
                                          detail::scalarType<S>(), pruned.data(), full.data(), leaf.data()),
                   "fclb_octree_prune_host");
-    return std::make_shared<const Octree2CollisionGeometry<S>>(children_, full, leaf, root_, n_layers_, pruned);
+    if (!rebuild_octree) return std::make_shared<const Octree2CollisionGeometry<S>>(children_, full, leaf, root_, n_layers_, pruned);
+    std::vector<uint32_t> n_children(children_.size());
+    std::vector<uint8_t> n_full(full.size()), n_leaf(leaf.size() ? leaf.size() : 1);
+    uint32_t ni = 0, nl = 0;
+    detail::check(fclb_octree_consolidate_host(children_.data(), uint32_t(full.size()), pruned.data(), leaf.data(),
+                                               uint32_t(leaf.size()), n_layers_, n_children.data(), n_full.data(), &ni,
+                                               n_leaf.data(), &nl),
+                  "fclb_octree_consolidate_host");
+    n_children.resize(std::size_t(8) * ni);
+    n_full.resize(ni);
+    n_leaf.resize(nl);
+    return std::make_shared<const Octree2CollisionGeometry<S>>(n_children, n_full, n_leaf, root_, n_layers_);
   }
   NODE_TYPE getNodeType() const override { return GEOM_OCTREE2; }
   bool isShape() const override { return false; }

@@ -309,6 +309,14 @@ int fclb_octree_build_host(const double* points, size_t n_points, double resolut
 int fclb_octree_prune_host(const uint32_t* inner_children, uint32_t n_inner, uint32_t n_leaf, const double* root_aabb,
                            int num_layers, const double* obb, int scalar_type, uint8_t* pruned, uint8_t* inner_full,
                            uint8_t* leaf_bits);
+/* Host-side mirror of Octree<S>::rebuildAccordingToPruneInfo (octree_construction-inl.h:247-369) = the
+ * rebuild_octree = true half of pruneBy: drops the pruned inner nodes and renumbers inner and leaf nodes exactly as the
+ * reference does, then re-derives the fully-occupied flags.  pruned / leaf_bits: the outputs of
+ * fclb_octree_prune_host.  The out arrays must hold n_inner x 8 / n_inner / n_leaf entries (the tree never grows);
+ * root box and layer count are unchanged.  Host only, no GPU needed. */
+int fclb_octree_consolidate_host(const uint32_t* inner_children, uint32_t n_inner, const uint8_t* pruned,
+                                 const uint8_t* leaf_bits, uint32_t n_leaf, int num_layers, uint32_t* out_children,
+                                 uint8_t* out_full, uint32_t* out_n_inner, uint8_t* out_leaf_bits, uint32_t* out_n_leaf);
 /* the same builder followed by fclb_octree_upload (no prune mask) */
 int fclb_octree_build(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
                       fclb_handle* octree);

@@ -364,5 +364,47 @@ void octreePrune(const uint32_t* children, int num_layers, const double root_box
   octUpdateFullPruned(children, pruned, leaf_bits, full, num_layers, 0, 0);
 }
 
+// Octree<S>::rebuildAccordingToPruneInfo (octree_construction-inl.h:247-369): the pruned tree consolidated into a
+// fresh, renumbered one.  Numbering follows the reference's LIFO task stack: an inner child gets its new index when
+// its parent is expanded, leaf nodes are appended when their parent is popped.
+inline void octreeConsolidate(const uint32_t* children, const uint8_t* pruned, const uint8_t* leaf_bits, int num_layers,
+                              OctreeHost& out) {
+  out.num_layers = num_layers;
+  out.children.assign(8, kOctInvalid);
+  out.full.assign(1, 0);
+  out.leaf_bits.clear();
+  if (pruned[0]) return;  // clearNodes(): a bare root
+  struct Task {
+    uint32_t node;
+    int depth;
+    uint32_t placement;
+  };
+  std::vector<Task> stack{{0u, 0, 0u}};
+  while (!stack.empty()) {
+    const Task t = stack.back();
+    stack.pop_back();
+    const uint32_t* ch = children + size_t(8) * t.node;
+    uint32_t fresh[8];
+    for (int i = 0; i < 8; i++) fresh[i] = kOctInvalid;
+    if (t.depth + 3 >= num_layers) {
+      for (int i = 0; i < 8; i++) {
+        if (ch[i] == kOctInvalid) continue;
+        fresh[i] = uint32_t(out.leaf_bits.size());
+        out.leaf_bits.push_back(leaf_bits[ch[i]]);
+      }
+    } else {
+      for (int i = 0; i < 8; i++) {
+        if (ch[i] == kOctInvalid || pruned[ch[i]]) continue;
+        fresh[i] = uint32_t(out.n_inner());
+        out.children.insert(out.children.end(), 8, kOctInvalid);
+        out.full.push_back(0);
+        stack.push_back({ch[i], t.depth + 1, fresh[i]});
+      }
+    }
+    for (int i = 0; i < 8; i++) out.children[size_t(8) * t.placement + i] = fresh[i];
+  }
+  octUpdateFull(out, 0, 0);
+}
+
 }  // namespace hostbuild
 }  // namespace fclb

@@ -942,6 +942,25 @@ int fclb_octree_prune_host(const uint32_t* inner_children, uint32_t n_inner, uin
   return FCLB_OK;
 }
 
+int fclb_octree_consolidate_host(const uint32_t* inner_children, uint32_t n_inner, const uint8_t* pruned,
+                                 const uint8_t* leaf_bits, uint32_t n_leaf, int num_layers, uint32_t* out_children,
+                                 uint8_t* out_full, uint32_t* out_n_inner, uint8_t* out_leaf_bits, uint32_t* out_n_leaf) {
+  if (!inner_children || !n_inner || !pruned || num_layers < 3 || (n_leaf && (!leaf_bits || !out_leaf_bits)) || !out_children ||
+      !out_full || !out_n_inner || !out_n_leaf)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_octree_consolidate_host: bad argument");
+  for (size_t i = 0; i < size_t(8) * n_inner; i++)
+    if (inner_children[i] != 0xffffffffu && inner_children[i] >= (n_inner > n_leaf ? n_inner : n_leaf))
+      return fail(FCLB_ERR_BAD_ARG, "fclb_octree_consolidate_host: child index out of range");
+  fclb::hostbuild::OctreeHost t;
+  fclb::hostbuild::octreeConsolidate(inner_children, pruned, leaf_bits, num_layers, t);
+  *out_n_inner = uint32_t(t.n_inner());
+  *out_n_leaf = uint32_t(t.leaf_bits.size());
+  std::copy(t.children.begin(), t.children.end(), out_children);
+  std::copy(t.full.begin(), t.full.end(), out_full);
+  std::copy(t.leaf_bits.begin(), t.leaf_bits.end(), out_leaf_bits);
+  return FCLB_OK;
+}
+
 int fclb_octree_release(fclb_handle h) {
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);

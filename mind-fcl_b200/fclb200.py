@@ -37,7 +37,7 @@ EXPORTS = [
     "fclb_heightmap_upload", "fclb_heightmap_release", "fclb_heightmap_build_host",
     "fclb_heightmap_build_dev", "fclb_heightmap_build_points_host", "fclb_heightmap_info", "fclb_heightmap_export",
     "fclb_heightmap_shape_collide_batch_host", "fclb_heightmap_shape_collide_batch_dev",
-    "fclb_octree_upload", "fclb_octree_release", "fclb_octree_build_host", "fclb_octree_build", "fclb_octree_prune_host",
+    "fclb_octree_upload", "fclb_octree_release", "fclb_octree_build_host", "fclb_octree_build", "fclb_octree_prune_host", "fclb_octree_consolidate_host",
     "fclb_octree_shape_collide_batch_host",
     "fclb_octree_shape_collide_batch_dev",
     "fclb_scene_shape_contacts_batch_host", "fclb_scene_shape_contacts_batch_dev",
@@ -187,6 +187,7 @@ def load() -> C.CDLL:
                                                C.POINTER(u32), vp, C.POINTER(C.c_int)]
         lib.fclb_octree_build.argtypes = [vp, sz, C.c_double, u32, C.c_int, C.POINTER(C.c_uint64)]
         lib.fclb_octree_prune_host.argtypes = [vp, u32, u32, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+        lib.fclb_octree_consolidate_host.argtypes = [vp, u32, vp, vp, u32, C.c_int, vp, vp, C.POINTER(u32), vp, C.POINTER(u32)]
         os_args = [C.c_uint64, C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp]
         lib.fclb_octree_shape_collide_batch_host.argtypes = os_args
         lib.fclb_octree_shape_collide_batch_dev.argtypes = os_args
@@ -626,6 +627,20 @@ def octree_prune_host(inner_children, inner_full, leaf_bits, root_aabb, n_layers
     check(load().fclb_octree_prune_host(_ptr(ch), len(full), len(leaf), _ptr(root), n_layers, _ptr(obb), scalar_type,
                                         _ptr(pr), _ptr(full), _ptr(leaf)))
     return pr, full, leaf
+
+
+def octree_consolidate_host(inner_children, pruned, leaf_bits, n_layers):
+    """Octree::rebuildAccordingToPruneInfo on the flat arrays (no GPU): (inner_children [n',8], inner_full [n'], leaf_bits [m'])."""
+    ch = np.ascontiguousarray(inner_children, np.uint32)
+    pr = np.ascontiguousarray(pruned, np.uint8)
+    leaf = np.ascontiguousarray(leaf_bits, np.uint8)
+    o_ch = np.zeros_like(ch)
+    o_full = np.zeros(len(pr), np.uint8)
+    o_leaf = np.zeros(max(len(leaf), 1), np.uint8)
+    ni, nl = C.c_uint32(), C.c_uint32()
+    check(load().fclb_octree_consolidate_host(_ptr(ch), len(pr), _ptr(pr), _ptr(leaf), len(leaf), n_layers, _ptr(o_ch), _ptr(o_full),
+                                              C.byref(ni), _ptr(o_leaf), C.byref(nl)))
+    return o_ch[:ni.value].copy(), o_full[:ni.value].copy(), o_leaf[:nl.value].copy()
 
 
 def octree_build(points, resolution, half_shape, scalar_type) -> int:

@@ -284,6 +284,14 @@ class RefOracle(_Oracle):
         f.argtypes = [C.c_int, C.c_void_p]
         return int(f(oct_id, _p(np.ascontiguousarray(obb))))
 
+    def octree_prune_rebuild(self, oct_id, axis, center, extent):
+        """Octree2CollisionGeometry::pruneBy(OBB, rebuild=True): id of the consolidated, renumbered geometry."""
+        obb = np.concatenate([np.asarray(axis, np.float64).reshape(9), np.asarray(center, np.float64),
+                              np.asarray(extent, np.float64)])
+        f = self.fn("octree_prune_rebuild")
+        f.argtypes = [C.c_int, C.c_void_p]
+        return int(f(oct_id, _p(np.ascontiguousarray(obb))))
+
     def octree_export_pruned(self, oct_id, dtype, n_inner):
         """prune_internal_nodes as bytes, or None when the geometry has no prune info"""
         out = np.zeros(n_inner, np.uint8)

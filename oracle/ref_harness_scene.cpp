@@ -527,6 +527,26 @@ int fclref_octree_prune(int id, const double* obb) {
   octrees().push_back(r);
   return int(octrees().size()) - 1;
 }
+/* Octree2CollisionGeometry::pruneBy(obb, rebuild_octree = true): the pruned tree consolidated into a renumbered
+ * octree (Octree::rebuildAccordingToPruneInfo, octree_construction-inl.h:247-369); a new geometry id */
+int fclref_octree_prune_rebuild(int id, const double* obb) {
+  auto make = [&](auto tag) {
+    using S = decltype(tag);
+    fcl::OBB<S> bv;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) bv.axis(i, j) = S(obb[3 * i + j]);
+    for (int k = 0; k < 3; k++) {
+      bv.To[k] = S(obb[9 + k]);
+      bv.extent[k] = S(obb[12 + k]);
+    }
+    return bv;
+  };
+  OctRec r;
+  r.f = octrees().at(id).f->pruneBy(make(float(0)), true);
+  r.d = octrees().at(id).d->pruneBy(make(double(0)), true);
+  octrees().push_back(r);
+  return int(octrees().size()) - 1;
+}
 /* prune_internal_nodes as bytes; returns 0 when the geometry carries no prune info */
 int fclref_octree_export_pruned(int id, int scalar_type, uint8_t* pruned) {
   auto dump = [&](const auto* g) {

@@ -187,6 +187,11 @@ void runScene() {
     CollisionResult<S> gone, two;
     EXPECT_TRUE(collide<S>(rest.get(), I, &small, at(S(0.05), S(0.05), S(0.05)), req, gone) == 0);
     EXPECT_TRUE(collide<S>(rest.get(), I, &bar, at(S(0.2), S(0.05), S(0.05)), req, two) == 2);
+    auto rebuilt = oct.pruneBy(cut, true);  // consolidated: same voxels, no prune info
+    CollisionResult<S> gone2, two2;
+    EXPECT_TRUE(rebuilt->prune_internal_nodes() == nullptr && rebuilt->leaf_bits().size() == 2);
+    EXPECT_TRUE(collide<S>(rebuilt.get(), I, &small, at(S(0.05), S(0.05), S(0.05)), req, gone2) == 0);
+    EXPECT_TRUE(collide<S>(rebuilt.get(), I, &bar, at(S(0.2), S(0.05), S(0.05)), req, two2) == 2);
   }
   {
     // directed penetration: two unit spheres 1.5 apart along x, escape direction +x => depth 0.5

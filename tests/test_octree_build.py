@@ -101,3 +101,44 @@ def test_prune_matches_reference(ref_oracle, half_shape, res, seed):
         total_leaf += int((ours[np.float32][5] != ref_oracle.octree_export(oid, np.float32)[2]).sum())
     assert total_pruned > 0 and total_leaf > 0
     print(f"prune chains: {total_pruned} inner nodes pruned, {total_leaf} leaf masks changed over {n_chain} chains")
+
+
+@pytest.mark.parametrize("half_shape,res,seed", [(64, 0.01, 7), (16, 0.04, 8)])
+def test_consolidate_matches_reference(ref_oracle, half_shape, res, seed):
+    """fclb_octree_prune_host + fclb_octree_consolidate_host against pruneBy(obb, rebuild_octree=True)
+    (Octree::rebuildAccordingToPruneInfo, octree_construction-inl.h:247-369): the renumbered inner / leaf arrays and
+    the re-derived fully-occupied flags are identical, incl. a second prune of the consolidated tree and a prune
+    that removes everything."""
+    import fclb200 as fclb
+    import scenes
+
+    oid = ref_oracle.octree_create(octree_points(seed), res, half_shape)
+    span = res * half_shape
+    rng = np.random.Generator(np.random.PCG64(200 + seed))
+    boxes = []
+    for _ in range(6):
+        e = rng.uniform(-np.pi, np.pi, 3)
+        boxes.append((scenes.euler_to_matrix(e[:1], e[1:2], e[2:3])[0], rng.uniform(-0.5 * span, 0.5 * span, 3),
+                      rng.uniform(0.1 * span, 0.45 * span, 3)))
+    boxes.append((np.eye(3), np.zeros(3), np.full(3, 3 * span)))  # swallows the root
+    for dt, st in ((np.float32, fclb.F32), (np.float64, fclb.F64)):
+        dropped = 0
+        for bi, (axis, center, extent) in enumerate(boxes):
+            rid = ref_oracle.octree_prune_rebuild(oid, axis, center, extent)
+            ch, full, leaf, root, layers = ref_oracle.octree_export(oid, dt)
+            for again in range(2):  # the consolidated tree pruned once more by the next box
+                pr, n_full, n_leaf = fclb.octree_prune_host(ch, full, leaf, root, layers, axis, center, extent, st)
+                c_ch, c_full, c_leaf = fclb.octree_consolidate_host(ch, pr, n_leaf, layers)
+                r_ch, r_full, r_leaf, r_root, r_layers = ref_oracle.octree_export(rid, dt)
+                assert ref_oracle.octree_export_pruned(rid, dt, len(r_full)) is None
+                assert r_layers == layers and np.array_equal(r_root, root)
+                assert c_ch.shape == r_ch.shape and np.array_equal(c_ch, r_ch), (bi, again, dt)
+                assert np.array_equal(c_full, r_full) and np.array_equal(c_leaf, r_leaf), (bi, again, dt)
+                dropped += len(full) - len(c_full)
+                if again == 0:
+                    axis, center, extent = boxes[(bi + 1) % 6]
+                    rid = ref_oracle.octree_prune_rebuild(rid, axis, center, extent)
+                    ch, full, leaf = c_ch, c_full, c_leaf
+            if bi == len(boxes) - 1:
+                assert c_ch.shape == (1, 8) and (c_ch == 0xFFFFFFFF).all() and len(c_leaf) == 0
+        assert dropped > 0
