@@ -256,6 +256,28 @@ inline bool pruneObbContainsBox(const PruneObb<S>& o, const S c[3], const S e[3]
   return true;
 }
 
+// every child link reachable from the root (pruned subtrees skipped when a mask is given) stays inside its layer's array
+inline bool octLinksInRange(const uint32_t* children, uint32_t n_inner, uint32_t n_leaf, int num_layers, const uint8_t* pruned) {
+  struct N {
+    uint32_t node;
+    int depth;
+  };
+  std::vector<N> stack{{0u, 0}};
+  while (!stack.empty()) {
+    const N t = stack.back();
+    stack.pop_back();
+    if (pruned && pruned[t.node]) continue;
+    const bool child_leaf = t.depth + 3 >= num_layers;
+    for (int c = 0; c < 8; c++) {
+      const uint32_t k = children[size_t(8) * t.node + c];
+      if (k == kOctInvalid) continue;
+      if (k >= (child_leaf ? n_leaf : n_inner)) return false;
+      if (!child_leaf) stack.push_back({k, t.depth + 1});
+    }
+  }
+  return true;
+}
+
 // updateRecursive with prune info (octree_construction-inl.h:111-172): a pruned node is not full and is not entered
 inline bool octUpdateFullPruned(const uint32_t* children, const uint8_t* pruned, const uint8_t* leaf_bits, uint8_t* full,
                                 int num_layers, uint32_t node, int depth) {
@@ -287,9 +309,10 @@ inline bool octUpdateFullPruned(const uint32_t* children, const uint8_t* pruned,
 // pruneOctreeByOBB on the flat arrays.  pruned / full / leaf_bits are the OctreePruneInfo being extended
 // (prune_internal_nodes, new_inner_nodes_fully_occupied, new_leaf_nodes): zeros + the tree's own flags and masks
 // for a first prune, the previous outputs for a further one.
+// Returns false (arrays partly updated) when a child link points outside its layer's array.
 template <typename S>
-void octreePrune(const uint32_t* children, int num_layers, const double root_box[6], const double obb15[15], uint8_t* pruned,
-                 uint8_t* full, uint8_t* leaf_bits) {
+bool octreePrune(const uint32_t* children, uint32_t n_inner, uint32_t n_leaf, int num_layers, const double root_box[6],
+                 const double obb15[15], uint8_t* pruned, uint8_t* full, uint8_t* leaf_bits) {
   PruneObb<S> o;
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) o.axis[i][j] = S(obb15[3 * i + j]);
@@ -358,22 +381,25 @@ void octreePrune(const uint32_t* children, int num_layers, const double root_box
       g.node = ch[ci];
       g.depth = f.depth + 1;
       g.leaf = f.depth + 3 >= num_layers;
+      if (g.node >= (g.leaf ? n_leaf : n_inner)) return false;
       stack.push_back(g);
     }
   }
   octUpdateFullPruned(children, pruned, leaf_bits, full, num_layers, 0, 0);
+  return true;
 }
 
 // Octree<S>::rebuildAccordingToPruneInfo (octree_construction-inl.h:247-369): the pruned tree consolidated into a
 // fresh, renumbered one.  Numbering follows the reference's LIFO task stack: an inner child gets its new index when
 // its parent is expanded, leaf nodes are appended when their parent is popped.
-inline void octreeConsolidate(const uint32_t* children, const uint8_t* pruned, const uint8_t* leaf_bits, int num_layers,
-                              OctreeHost& out) {
+inline bool octreeConsolidate(const uint32_t* children, uint32_t n_inner, uint32_t n_leaf, const uint8_t* pruned,
+                              const uint8_t* leaf_bits, int num_layers, OctreeHost& out) {
+  if (!octLinksInRange(children, n_inner, n_leaf, num_layers, pruned)) return false;
   out.num_layers = num_layers;
   out.children.assign(8, kOctInvalid);
   out.full.assign(1, 0);
   out.leaf_bits.clear();
-  if (pruned[0]) return;  // clearNodes(): a bare root
+  if (pruned[0]) return true;  // clearNodes(): a bare root
   struct Task {
     uint32_t node;
     int depth;
@@ -404,6 +430,7 @@ inline void octreeConsolidate(const uint32_t* children, const uint8_t* pruned, c
     for (int i = 0; i < 8; i++) out.children[size_t(8) * t.placement + i] = fresh[i];
   }
   octUpdateFull(out, 0, 0);
+  return true;
 }
 
 }  // namespace hostbuild

@@ -930,16 +930,14 @@ int fclb_octree_prune_host(const uint32_t* inner_children, uint32_t n_inner, uin
                            uint8_t* leaf_bits) {
   if (!inner_children || !n_inner || !root_aabb || num_layers < 3 || !obb || !pruned || !inner_full || (n_leaf && !leaf_bits))
     return fail(FCLB_ERR_BAD_ARG, "fclb_octree_prune_host: bad argument");
-  for (size_t i = 0; i < size_t(8) * n_inner; i++)
-    if (inner_children[i] != 0xffffffffu && inner_children[i] >= (n_inner > n_leaf ? n_inner : n_leaf))
-      return fail(FCLB_ERR_BAD_ARG, "fclb_octree_prune_host: child index out of range");
-  if (scalar_type == FCLB_F32)
-    fclb::hostbuild::octreePrune<float>(inner_children, num_layers, root_aabb, obb, pruned, inner_full, leaf_bits);
-  else if (scalar_type == FCLB_F64)
-    fclb::hostbuild::octreePrune<double>(inner_children, num_layers, root_aabb, obb, pruned, inner_full, leaf_bits);
-  else
-    return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
-  return FCLB_OK;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (!fclb::hostbuild::octLinksInRange(inner_children, n_inner, n_leaf, num_layers, nullptr))
+    return fail(FCLB_ERR_BAD_ARG, "fclb_octree_prune_host: child index out of range");
+  const bool ok = scalar_type == FCLB_F32 ? fclb::hostbuild::octreePrune<float>(inner_children, n_inner, n_leaf, num_layers, root_aabb,
+                                                                               obb, pruned, inner_full, leaf_bits)
+                                          : fclb::hostbuild::octreePrune<double>(inner_children, n_inner, n_leaf, num_layers, root_aabb,
+                                                                                obb, pruned, inner_full, leaf_bits);
+  return ok ? FCLB_OK : fail(FCLB_ERR_BAD_ARG, "fclb_octree_prune_host: child index out of range");
 }
 
 int fclb_octree_consolidate_host(const uint32_t* inner_children, uint32_t n_inner, const uint8_t* pruned,
@@ -948,11 +946,9 @@ int fclb_octree_consolidate_host(const uint32_t* inner_children, uint32_t n_inne
   if (!inner_children || !n_inner || !pruned || num_layers < 3 || (n_leaf && (!leaf_bits || !out_leaf_bits)) || !out_children ||
       !out_full || !out_n_inner || !out_n_leaf)
     return fail(FCLB_ERR_BAD_ARG, "fclb_octree_consolidate_host: bad argument");
-  for (size_t i = 0; i < size_t(8) * n_inner; i++)
-    if (inner_children[i] != 0xffffffffu && inner_children[i] >= (n_inner > n_leaf ? n_inner : n_leaf))
-      return fail(FCLB_ERR_BAD_ARG, "fclb_octree_consolidate_host: child index out of range");
   fclb::hostbuild::OctreeHost t;
-  fclb::hostbuild::octreeConsolidate(inner_children, pruned, leaf_bits, num_layers, t);
+  if (!fclb::hostbuild::octreeConsolidate(inner_children, n_inner, n_leaf, pruned, leaf_bits, num_layers, t))
+    return fail(FCLB_ERR_BAD_ARG, "fclb_octree_consolidate_host: child index out of range");
   *out_n_inner = uint32_t(t.n_inner());
   *out_n_leaf = uint32_t(t.leaf_bits.size());
   std::copy(t.children.begin(), t.children.end(), out_children);

@@ -142,3 +142,23 @@ def test_consolidate_matches_reference(ref_oracle, half_shape, res, seed):
             if bi == len(boxes) - 1:
                 assert c_ch.shape == (1, 8) and (c_ch == 0xFFFFFFFF).all() and len(c_leaf) == 0
         assert dropped > 0
+
+
+def test_malformed_links_are_rejected():
+    import fclb200 as fclb
+
+    pts = octree_points(7)
+    ch, full, leaf, root, layers = fclb.octree_build_host(pts, 0.01, 64, fclb.F64)
+    bad = ch.copy()
+    bad[0, np.nonzero(ch[0] != 0xFFFFFFFF)[0][0]] = len(full)  # an inner link one past the inner array
+    with pytest.raises(fclb.FclbError):
+        fclb.octree_prune_host(bad, full, leaf, root, layers, np.eye(3), (0, 0, 0), (0.1, 0.1, 0.1), fclb.F64)
+    with pytest.raises(fclb.FclbError):
+        fclb.octree_consolidate_host(bad, np.zeros(len(full), np.uint8), leaf, layers)
+    # a leaf-layer link past the leaf array (but inside the inner array's range)
+    parents = np.nonzero((ch != 0xFFFFFFFF).any(1))[0]
+    deep = parents[-1]  # the last inner node was created on the way to a leaf: its children are leaf links
+    bad = ch.copy()
+    bad[deep, np.nonzero(ch[deep] != 0xFFFFFFFF)[0][0]] = len(leaf)
+    with pytest.raises(fclb.FclbError):
+        fclb.octree_prune_host(bad, full, leaf, root, layers, np.eye(3), (0, 0, 0), (0.1, 0.1, 0.1), fclb.F32)
