@@ -848,9 +848,8 @@ int fclb_octree_upload(const uint32_t* inner_children, const uint8_t* inner_full
   if (rc) return rc;
   if (!octree || !root_aabb || num_layers < 2 || (n_inner && (!inner_children || !inner_full)) || (n_leaf && !leaf_bits))
     return fail(FCLB_ERR_BAD_ARG, "fclb_octree_upload: bad argument");
-  for (size_t i = 0; i < size_t(8) * n_inner; i++)
-    if (inner_children[i] != 0xffffffffu && inner_children[i] >= (n_inner > n_leaf ? n_inner : n_leaf))
-      return fail(FCLB_ERR_BAD_ARG, "fclb_octree_upload: child index out of range");
+  if (n_inner && !fclb::hostbuild::octLinksInRange(inner_children, n_inner, n_leaf, num_layers, nullptr))
+    return fail(FCLB_ERR_BAD_ARG, "fclb_octree_upload: child index out of range");
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
   OctreeDev* d = new OctreeDev();
