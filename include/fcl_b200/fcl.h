@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -343,6 +344,28 @@ class Octree {
                                          &n_leaf, root_aabb_.data(), &n_layers_),
                   "fclb_octree_build_host");
     leaf_bits_.resize(n_leaf);
+  }
+  // isPointOccupied / isVoxelOccupied (octree-inl.h:118-142,194-228): voxel coordinate in S, then a descent that stops
+  // at a fully occupied inner node
+  bool isPointOccupied(const Vector3<S>& point) const {
+    const S inv = S(1.0) / resolution_;
+    int v[3];
+    for (int k = 0; k < 3; k++) {
+      v[k] = int(std::floor(point[k] * inv) + S(int(half_)));
+      if (v[k] < 0 || v[k] >= 2 * int(half_)) return false;
+    }
+    std::uint32_t node = 0;
+    for (int depth = 0;; depth++) {
+      if (inner_full_[node]) return true;
+      const int diff = n_layers_ - depth - 2;
+      const int c = ((v[0] >> diff) & 1) | (((v[1] >> diff) & 1) << 1) | (((v[2] >> diff) & 1) << 2);
+      const std::uint32_t child = inner_children_[std::size_t(8) * node + c];
+      if (child == 0xffffffffu) return false;
+      node = child;
+      if (depth + 3 >= n_layers_) break;
+    }
+    const int c = (v[0] & 1) | ((v[1] & 1) << 1) | ((v[2] & 1) << 2);
+    return (leaf_bits_[node] >> c) & 1;
   }
   std::uint8_t n_layers() const { return std::uint8_t(n_layers_); }
   std::size_t n_inner_nodes() const { return inner_full_.size(); }

@@ -171,6 +171,9 @@ void runScene() {
         8);  // every voxel named twice
     EXPECT_TRUE(tree->n_inner_nodes() == 3 && tree->n_leaf_nodes() == 2);  // root + two levels above two 2x2x2 cells
     EXPECT_TRUE(tree->leaf_bits()[0] == 3 && tree->leaf_bits()[1] == 3);
+    EXPECT_TRUE(tree->isPointOccupied(Vector3<S>(S(0.17), S(0.02), S(0.09))) && tree->isPointOccupied(Vector3<S>(S(0.35), S(0.05), S(0.05))));
+    EXPECT_TRUE(!tree->isPointOccupied(Vector3<S>(S(0.45), S(0.05), S(0.05))) && !tree->isPointOccupied(Vector3<S>(S(0.05), S(0.15), S(0.05))) &&
+                !tree->isPointOccupied(Vector3<S>(S(-0.05), S(0.05), S(0.05))) && !tree->isPointOccupied(Vector3<S>(S(0.9), 0, 0)));
     Octree2CollisionGeometry<S> oct(tree);
     Box<S> small(S(0.06), S(0.06), S(0.06)), bar(S(0.5), S(0.06), S(0.06));
     CollisionRequest<S> req(100);

@@ -162,3 +162,17 @@ def test_malformed_links_are_rejected():
     bad[deep, np.nonzero(ch[deep] != 0xFFFFFFFF)[0][0]] = len(leaf)
     with pytest.raises(fclb.FclbError):
         fclb.octree_prune_host(bad, full, leaf, root, layers, np.eye(3), (0, 0, 0), (0.1, 0.1, 0.1), fclb.F32)
+
+
+def test_cpp_octree_mirror_host_only(tmp_path):
+    """include/fcl_b200/fcl.h octree2::Octree<S> (rebuildTree, isPointOccupied) compiled with g++ and run without a GPU."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "mind-fcl_b200")
+    exe = str(tmp_path / "test_octree_host")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "test_octree_host.cpp"),
+                    "-L", lib_dir, "-lfclb200", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout
