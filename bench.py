@@ -553,7 +553,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def bind_to_gpu_numa_node(torch, local_rank):
@@ -578,6 +578,18 @@ def bind_to_gpu_numa_node(torch, local_rank):
     return None
 
 
+_OUT = sys.stdout
+
+
+def claim_stdout():
+    """Only the JSON line may reach stdout: anything else written to fd 1 (NCCL prints its version banner there when
+    the box sets NCCL_DEBUG) is sent to stderr for the rest of the run."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -589,6 +601,7 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3)
     if args.queries <= 0:
         args.queries = {"c2": 10_000_000, "c4": 100_000, "c5": 100_000}.get(args.workload, 1_000_000)
@@ -750,7 +763,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
