@@ -32,8 +32,42 @@ def mixed(n, dtype, combos, extent, seed):
     return pairs, p1, p2
 
 
+def octree_golden(ref):
+    """Octree construction, two cumulative prunes and the consolidated tree of the second, as the reference builds them
+    (Octree::rebuildTree, pruneOctreeByOBB, rebuildAccordingToPruneInfo): tests/test_octree_build.py::test_golden."""
+    rng = np.random.Generator(np.random.PCG64(31))
+    res, half = 0.04, 16
+    g = np.arange(-10, 10) * res + res / 2
+    X, Y, Z = np.meshgrid(g, g, np.arange(-6, 6) * res + res / 2, indexing="ij")
+    keep = Z < 0.08 * np.sin(5 * X) * np.cos(4 * Y)
+    pts = np.ascontiguousarray(np.concatenate([np.stack([X[keep], Y[keep], Z[keep]], 1), rng.uniform(-0.7, 0.7, size=(600, 3))]))
+    e = np.array([0.3, 0.2, 0.5])
+    boxes = [(scenes.euler_to_matrix(e[:1], e[1:2], e[2:3])[0], np.array([0.05, -0.1, -0.05]), np.array([0.22, 0.15, 0.12])),
+             (np.eye(3), np.array([-0.24, 0.2, 0.0]), np.array([0.12, 0.12, 0.3]))]
+    out = {"points": pts, "resolution": res, "half_shape": half,
+           "obb": np.array([np.concatenate([a.reshape(9), c, x]) for a, c, x in boxes])}
+    oid = ref.octree_create(pts, res, half)
+    p1 = ref.octree_prune(oid, *boxes[0])
+    p2 = ref.octree_prune(p1, *boxes[1])
+    r2 = ref.octree_prune_rebuild(p1, *boxes[1])
+    for dtype, tag in ((np.float32, "f32"), (np.float64, "f64")):
+        for name, gid in (("tree", oid), ("prune1", p1), ("prune2", p2), ("rebuilt", r2)):
+            ch, full, leaf, root, layers = ref.octree_export(gid, dtype)
+            out[f"{name}_children_{tag}"], out[f"{name}_full_{tag}"], out[f"{name}_leaf_{tag}"] = ch, full, leaf
+            out[f"root_{tag}"], out["layers"] = root, layers
+            pr = ref.octree_export_pruned(gid, dtype, len(full))
+            if pr is not None:
+                out[f"{name}_pruned_{tag}"] = pr
+    np.savez_compressed(os.path.join(HERE, "octree.npz"), **out)
+    print("octree.npz:", len(pts), "points,", len(out["tree_full_f32"]), "inner /", len(out["tree_leaf_f32"]), "leaf nodes,",
+          int(out["prune2_pruned_f32"].sum()), "pruned,", len(out["rebuilt_full_f32"]), "inner after consolidation")
+
+
 def main():
     ref = oracle_py.RefOracle()
+    if sys.argv[1:] == ["octree"]:
+        return octree_golden(ref)
+    octree_golden(ref)
     for dtype, tag in ((np.float32, "f32"), (np.float64, "f64")):
         # distance: C2 mix + every closed-form specialisation
         shapes, pairs, p1, p2 = scenes.config_c2(3000, dtype, seed=77)

@@ -176,3 +176,30 @@ def test_cpp_octree_mirror_host_only(tmp_path):
                     "-L", lib_dir, "-lfclb200", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout
+
+
+def test_golden():
+    """The committed fixture tests/golden/octree.npz (made by tests/golden/make_golden.py from the reference itself):
+    build, two cumulative prunes and the consolidated tree, without the reference library at hand."""
+    import os
+
+    import fclb200 as fclb
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "octree.npz"))
+    res, half, layers = float(g["resolution"]), int(g["half_shape"]), int(g["layers"])
+    for tag, st in (("f32", fclb.F32), ("f64", fclb.F64)):
+        ch, full, leaf, root, n_layers = fclb.octree_build_host(g["points"], res, half, st)
+        assert n_layers == layers and np.array_equal(root, g[f"root_{tag}"])
+        assert np.array_equal(ch, g[f"tree_children_{tag}"]) and np.array_equal(full, g[f"tree_full_{tag}"])
+        assert np.array_equal(leaf, g[f"tree_leaf_{tag}"])
+        pr = None
+        for k, name in enumerate(("prune1", "prune2")):
+            o = g["obb"][k]
+            pr, full, leaf = fclb.octree_prune_host(ch, full, leaf, root, layers, o[:9].reshape(3, 3), o[9:12], o[12:15], st, pruned=pr)
+            assert np.array_equal(pr, g[f"{name}_pruned_{tag}"]) and np.array_equal(full, g[f"{name}_full_{tag}"])
+            assert np.array_equal(leaf, g[f"{name}_leaf_{tag}"])
+        # pruneBy(second box, rebuild=True) on the once-pruned geometry = consolidation of the twice-pruned arrays
+        c_ch, c_full, c_leaf = fclb.octree_consolidate_host(ch, pr, leaf, layers)
+        assert np.array_equal(c_ch, g[f"rebuilt_children_{tag}"]) and np.array_equal(c_full, g[f"rebuilt_full_{tag}"])
+        assert np.array_equal(c_leaf, g[f"rebuilt_leaf_{tag}"])
+        assert pr.any() and len(c_full) < len(full)
