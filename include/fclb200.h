@@ -295,7 +295,8 @@ int fclb_octree_release(fclb_handle octree);
  * reference's numbering (the contact ids of the octree kernels), then sets the fully-occupied flags.
  * bottom_half_shape: power of two >= 2.  Host only, no GPU needed.  Always writes *n_inner / *n_leaf (and
  * root_aabb[6], *num_layers when non-NULL); returns FCLB_ERR_CAPACITY without writing the arrays when they are
- * NULL or smaller than that -- call once for the sizes, once for the data. */
+ * NULL or smaller than that -- call once for the sizes, once for the data (the size query keeps its tree for a data
+ * call that follows on the same thread with the same arguments, so the points are inserted once). */
 int fclb_octree_build_host(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape,
                            int scalar_type, uint32_t* inner_children, uint8_t* inner_full, uint32_t inner_capacity,
                            uint32_t* n_inner, uint8_t* leaf_bits, uint32_t leaf_capacity, uint32_t* n_leaf,

@@ -895,10 +895,58 @@ int fclb_octree_build_host(const double* points, size_t n_points, double resolut
                            uint32_t* n_inner, uint8_t* leaf_bits, uint32_t leaf_capacity, uint32_t* n_leaf,
                            double* root_aabb, int* num_layers) {
   if (!n_inner || !n_leaf) return fail(FCLB_ERR_BAD_ARG, "fclb_octree_build_host: bad argument");
-  fclb::hostbuild::OctreeHost t;
-  int rc = octreeBuildHostImpl(points, n_points, resolution, bottom_half_shape, scalar_type, t,
-                               "fclb_octree_build_host: bad argument (half shape: power of two >= 2)");
-  if (rc) return rc;
+  // The size query keeps its tree for the data call that follows on the same thread with the same arguments (and the
+  // same first / middle / last point), so the usual two-call sequence inserts the points once.
+  struct Stash {
+    bool valid = false;
+    const double* points = nullptr;
+    size_t n = 0;
+    double res = 0, probe[9] = {0};
+    uint32_t half = 0;
+    int st = 0;
+    fclb::hostbuild::OctreeHost tree;
+  };
+  static thread_local Stash stash;
+  auto sameCall = [&]() {
+    if (!stash.valid || stash.points != points || stash.n != n_points || stash.res != resolution ||
+        stash.half != bottom_half_shape || stash.st != scalar_type)
+      return false;
+    const size_t at[3] = {0, n_points / 2, n_points ? n_points - 1 : 0};
+    for (int k = 0; k < 3 && n_points; k++)
+      for (int c = 0; c < 3; c++)
+        if (stash.probe[3 * k + c] != points[3 * at[k] + c]) return false;
+    return true;
+  };
+  const bool size_query = !inner_children || !inner_full || !leaf_bits;
+  fclb::hostbuild::OctreeHost local;
+  fclb::hostbuild::OctreeHost& t = (size_query || sameCall()) ? stash.tree : local;
+  if (!(&t == &stash.tree && !size_query)) {  // not a reuse: build
+    stash.valid = false;
+    int rc = octreeBuildHostImpl(points, n_points, resolution, bottom_half_shape, scalar_type, t,
+                                 "fclb_octree_build_host: bad argument (half shape: power of two >= 2)");
+    if (rc) return rc;
+    if (size_query) {
+      stash.valid = true;
+      stash.points = points;
+      stash.n = n_points;
+      stash.res = resolution;
+      stash.half = bottom_half_shape;
+      stash.st = scalar_type;
+      const size_t at[3] = {0, n_points / 2, n_points ? n_points - 1 : 0};
+      for (int k = 0; k < 3 && n_points; k++)
+        for (int c = 0; c < 3; c++) stash.probe[3 * k + c] = points[3 * at[k] + c];
+    }
+  }
+  struct Drop {  // a data call consumes the stash whatever its outcome
+    Stash& s;
+    bool drop;
+    ~Drop() {
+      if (drop) {
+        s.valid = false;
+        s.tree = fclb::hostbuild::OctreeHost();
+      }
+    }
+  } drop{stash, !size_query};
   *n_inner = uint32_t(t.n_inner());
   *n_leaf = uint32_t(t.leaf_bits.size());
   if (num_layers) *num_layers = t.num_layers;
