@@ -11,6 +11,7 @@
 // Every function cites the reference file:line it restates
 // (paths relative to /root/reference/include/fcl/).
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -33,6 +34,30 @@ struct PairRec {
   uint32_t s1, s2;
 };
 
+// Work counters of the generic GJK path (the flop / query model is built from counts that are
+// deterministic properties of the input, taken on the CPU restatement).  Active only inside fclport_gjk_work_counters.
+struct WorkCounters {
+  uint64_t queries = 0;
+  uint64_t support_vertices = 0;  // MinkowskiDiff::supportVertex evaluations (two shape supports each)
+  uint64_t extract_supports = 0;  // single-shape supports of the witness extraction (gjk_distance.hpp:376-470)
+  uint64_t convex_dots = 0;       // d . v evaluations inside Convex::findExtremeVertex (both variants)
+  uint64_t project[5] = {0, 0, 0, 0, 0};  // simplexProjection{2,3,4} calls by simplex rank at entry (boolean loop)
+  uint64_t update[5] = {0, 0, 0, 0, 0};   // computeMinDistanceAndUpdateSimplex calls by rank at entry (distance loop)
+  uint64_t separated = 0;
+  void add(const WorkCounters& o) {
+    queries += o.queries;
+    support_vertices += o.support_vertices;
+    extract_supports += o.extract_supports;
+    convex_dots += o.convex_dots;
+    for (int k = 0; k < 5; k++) {
+      project[k] += o.project[k];
+      update[k] += o.update[k];
+    }
+    separated += o.separated;
+  }
+};
+static thread_local WorkCounters* t_cnt = nullptr;
+
 // ---------------------------------------------------------------------------
 // Convex<S>  (geometry/shape/convex-inl.h)
 template <typename T>
@@ -47,6 +72,7 @@ struct ConvexData {
   int extremeNaive(const Vec3<T>& d) const {
     int best = 0;
     T best_v = d.dot(verts[0]);
+    if (t_cnt) t_cnt->convex_dots += verts.size();
     for (int i = 1; i < int(verts.size()); i++) {
       const T v = d.dot(verts[i]);
       if (v > best_v) {
@@ -70,6 +96,7 @@ struct ConvexData {
     }
     int ext = init;
     T ext_v = d.dot(verts[ext]);
+    if (t_cnt) t_cnt->convex_dots += 1;
     int parent0 = init, parent1 = init;
     bool keep = true;
     while (keep) {
@@ -79,6 +106,7 @@ struct ConvexData {
         const int nb = nbr[k];
         if (nb == parent0 || nb == parent1) continue;
         const T nv = d.dot(verts[nb]);
+        if (t_cnt) t_cnt->convex_dots += 1;
         if (nv > ext_v) {
           parent1 = ext;
           keep = true;
@@ -229,7 +257,10 @@ struct MinkowskiDiff {
     n_support++;
     return toshape0 * supportOf(shapes[1], toshape1 * d);
   }
-  Vec3<T> support(const Vec3<T>& d) const { return support0(d) - support1(-d); }
+  Vec3<T> support(const Vec3<T>& d) const {
+    if (t_cnt) t_cnt->support_vertices += 1;
+    return support0(d) - support1(-d);
+  }
   Vec3<T> interior() const { return interiorOf(shapes[0]) - toshape0 * interiorOf(shapes[1]); }
   // gjk_solver-inl.h:79-85
   void setPoses(const Xform<T>& tf1, const Xform<T>& tf2) {
@@ -314,6 +345,7 @@ class Gjk {
   }
 
   int project(Simplex<T>& s, Vec3<T>& dir) const {
+    if (t_cnt && s.rank >= 0 && s.rank < 5) t_cnt->project[s.rank] += 1;
     if (s.rank == 2) return project2(s, dir);
     if (s.rank == 3) return project3(s, dir);
     return project4(s, dir);
@@ -535,6 +567,7 @@ class Gjk {
   }
   // :109-126
   int update(Simplex<T>& s, Vec3<T>& out) const {
+    if (t_cnt && s.rank >= 0 && s.rank < 5) t_cnt->update[s.rank] += 1;
     if (s.rank == 1) {
       out = s.vertices[0].vertex;
       return U_OK;
@@ -553,6 +586,7 @@ class Gjk {
   // extractSeparationPointNoSubSimplex, :376-470
   bool extract(const MinkowskiDiff<T>& shape, const Simplex<T>& s, Vec3<T>& p0, Vec3<T>& p1) const {
     const T bary_tol = T(1e-3);
+    if (t_cnt && s.rank >= 1 && s.rank <= 3) t_cnt->extract_supports += 2 * uint64_t(s.rank);
     if (s.rank == 4 || s.rank <= 0) return false;
     if (s.rank == 1) {
       const auto& v = s.vertices[0];
@@ -916,9 +950,49 @@ int distanceBatch(const ShapeRec* shapes, int n_shapes, const PairRec* pairs, co
   return 0;
 }
 
-}  // namespace orc
+// The generic GJK path of every query (closed forms bypassed), with the work counters on: boolean GJK with the solver's
+// guess, plus the distance refinement + witness extraction when want_distance.
+template <typename T>
+int gjkWorkCounters(const ShapeRec* shapes, int n_shapes, const PairRec* pairs, const T* poses1, const T* poses2, size_t n,
+                    double gjk_tol, uint32_t gjk_max_iter, int want_distance, uint64_t* out, int threads) {
+  const ShapeTable<T> tab(shapes, n_shapes);
+  const T tol = gjk_tol > 0 ? T(gjk_tol) : eps78<T>();
+  const size_t its = gjk_max_iter ? gjk_max_iter : 128;
+  std::vector<WorkCounters> per(size_t(std::max(1, threads)));
+  std::atomic<int> next{0};
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    WorkCounters& c = per[size_t(next.fetch_add(1)) % per.size()];
+    t_cnt = &c;
+    for (size_t q = b; q < e; q++) {
+      const Xform<T> tf1 = loadPose(poses1 + 12 * q), tf2 = loadPose(poses2 + 12 * q);
+      MinkowskiDiff<T> shape;
+      shape.shapes[0] = tab.geoms[pairs[q].s1];
+      shape.shapes[1] = tab.geoms[pairs[q].s2];
+      shape.setPoses(tf1, tf2);
+      Gjk<T> gjk(its, tol);
+      Simplex<T> simplex;
+      typename Gjk<T>::DistOut d;
+      const Vec3<T> guess(1, 0, 0);
+      const GjkStatus st = gjk.evaluate(shape, simplex, -guess, want_distance ? &d : nullptr);
+      c.queries += 1;
+      if (st == GJK_SEPARATED) c.separated += 1;
+    }
+    t_cnt = nullptr;
+  });
+  WorkCounters tot;
+  for (const auto& c : per) tot.add(c);
+  out[0] = tot.queries;
+  out[1] = tot.support_vertices;
+  out[2] = tot.extract_supports;
+  out[3] = tot.convex_dots;
+  for (int k = 0; k < 5; k++) out[4 + k] = tot.project[k];
+  for (int k = 0; k < 5; k++) out[9 + k] = tot.update[k];
+  out[14] = tot.separated;
+  out[15] = 0;
+  return 0;
+}
 
-#include "fcl_oracle_collide.inc"
+}  // namespace orc
 
 extern "C" {
 
@@ -942,6 +1016,19 @@ int fclport_distance_batch(int scalar_type, const void* shapes, int n_shapes, co
   return distanceBatch<double>((const ShapeRec*)shapes, n_shapes, (const PairRec*)pairs, (const double*)poses1,
                                (const double*)poses2, n, gjk_tol, gjk_max_iter, (double*)dist, (double*)p1,
                                (double*)p2, ok, n_threads);
+}
+
+// out[16]: queries, supportVertex evaluations, extraction supports, convex dot products, project calls by rank [5],
+// distance-update calls by rank [5], separated queries, 0
+int fclport_gjk_work_counters(int scalar_type, const void* shapes, int n_shapes, const void* pairs, const void* poses1,
+                              const void* poses2, size_t n, double gjk_tol, uint32_t gjk_max_iter, int want_distance,
+                              uint64_t* out, int n_threads) {
+  using namespace orc;
+  if (scalar_type == 0)
+    return gjkWorkCounters<float>((const ShapeRec*)shapes, n_shapes, (const PairRec*)pairs, (const float*)poses1,
+                                  (const float*)poses2, n, gjk_tol, gjk_max_iter, want_distance, out, n_threads);
+  return gjkWorkCounters<double>((const ShapeRec*)shapes, n_shapes, (const PairRec*)pairs, (const double*)poses1,
+                                 (const double*)poses2, n, gjk_tol, gjk_max_iter, want_distance, out, n_threads);
 }
 
 int fclport_hardware_threads(void) { return int(std::thread::hardware_concurrency()); }

@@ -8,12 +8,11 @@ near-touching pairs; depths, normals and positions within TOL.
 import numpy as np
 import pytest
 
+import parity_util
 import scenes
 
 pytestmark = pytest.mark.gpu
 
-TOL = {np.float32: 1e-4, np.float64: 1e-6}
-EPS_TOUCH = {np.float32: 1e-4, np.float64: 1e-6}
 B, S, E, C, K, Y, V = scenes.BOX, scenes.SPHERE, scenes.ELLIPSOID, scenes.CAPSULE, scenes.CONE, scenes.CYLINDER, scenes.CONVEX
 
 
@@ -31,14 +30,6 @@ def mixed_batch(n, dtype, shapes, combos, extent, seed):
     return pairs, poses1, poses2, idx
 
 
-def check_counts(got, exp, depth_hint, dtype, label):
-    mism = np.nonzero(got != exp)[0]
-    unexplained = [int(q) for q in mism if not (depth_hint[q] <= EPS_TOUCH[dtype])]
-    print(f"[{label}] n={len(exp)} colliding={int((exp > 0).sum())} count mismatches={len(mism)} "
-          f"listed={mism[:12].tolist()} unexplained={len(unexplained)}")
-    assert not unexplained, unexplained[:10]
-
-
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("penetration", [0, 1])
 def test_closed_form_collide(fclb, ref_oracle, dtype, penetration):
@@ -51,40 +42,10 @@ def test_closed_form_collide(fclb, ref_oracle, dtype, penetration):
     for max_contacts in (1, 4):
         req = fclb.make_request(max_contacts=max_contacts, penetration_mode=penetration)
         counts, contacts = fclb.collide_batch_host(table, pairs, p1, p2, st_of(fclb, dtype), req, max_keep=4)
-        e_counts, e_contacts = ref_oracle.collide_batch(shapes, pairs, p1, p2, max_keep=4, threads=8,
-                                                        max_contacts=max_contacts, penetration_mode=penetration)
-        # a count mismatch is explained when the deepest contact of the side that collides is ~0 deep
-        hint = np.maximum(np.abs(contacts[:, :, 8]).max(axis=1), np.abs(e_contacts[:, :, 8]).max(axis=1))
-        if not penetration:
-            hint = np.zeros(n) + 1.0
-        label = f"closed {np.dtype(dtype).name} pen={penetration} max={max_contacts}"
-        if penetration:
-            check_counts(counts, e_counts, hint, dtype, label)
-        else:
-            mism = np.nonzero(counts != e_counts)[0]
-            print(f"[{label}] boolean mismatches: {len(mism)} {mism[:10].tolist()}")
-            assert len(mism) <= n * 1e-5
-        if penetration:
-            same = counts == e_counts
-            for k, combo in enumerate(combos):
-                sel = same & (idx == k) & (e_counts > 0)
-                if not sel.any():
-                    continue
-                g = contacts[sel]
-                ex = e_contacts[sel]
-                if combo == (1, 5):
-                    # box-box: the contact SET must match; compare per slot (same order expected)
-                    m = np.arange(4)[None, :] < e_counts[sel][:, None]
-                    diff = np.abs(g - ex)[m]
-                    frac_exact = float((g[m] == ex[m]).all(axis=-1).mean())
-                    bad = (diff.max(axis=-1) > TOL[dtype])
-                    print(f"   box-box: {int(sel.sum())} colliding, contact records identical {frac_exact:.5f}, "
-                          f"beyond tol: {int(bad.sum())} (cullPoints2 atan2 ties)")
-                    assert bad.mean() <= 2e-3
-                else:
-                    d = np.abs(g[:, 0, 2:] - ex[:, 0, 2:]).max()
-                    print(f"   combo {combo}: {int(sel.sum())} colliding, max |contact diff| {d:.3e}")
-                    assert d <= TOL[dtype]
+        kw = dict(max_contacts=max_contacts, penetration_mode=penetration)
+        e_counts, e_contacts = ref_oracle.collide_batch(shapes, pairs, p1, p2, max_keep=4, threads=8, **kw)
+        parity_util.check_collide(ref_oracle, "test_closed_form_collide", f"closed-form pairs pen={penetration} max={max_contacts}",
+                                  dtype, shapes, pairs, p1, p2, (counts, contacts), (e_counts, e_contacts), kw, 4)
     fclb.release(table)
 
 
@@ -111,7 +72,8 @@ def test_gjk_boolean_and_epa(fclb, ref_oracle, dtype):
         req = fclb.make_request(max_contacts=1, penetration_mode=1)
         gjk, epa, geom = fclb.gjk_epa_batch_host(table, pairs, p1, p2, st_of(fclb, dtype), req)
         e_gjk, e_epa, _, e_geom, _ = ref_oracle.gjk_epa_batch(shapes, pairs, p1, p2, threads=8)
-        report_gjk_epa(name, dtype, gjk, epa, geom, e_gjk, e_epa, e_geom)
+        parity_util.check_gjk_epa(ref_oracle, "test_gjk_boolean_and_epa", name, dtype, shapes, pairs, p1, p2, (gjk, epa, geom),
+                                  (e_gjk, e_epa, e_geom))
         fclb.release(table)
     # convex-convex (58-vertex walk support vs 16-vertex scan support)
     shapes = [(V, slots[0], ()), (V, slots[1], ())]
@@ -122,26 +84,9 @@ def test_gjk_boolean_and_epa(fclb, ref_oracle, dtype):
     req = fclb.make_request(max_contacts=1, penetration_mode=1)
     gjk, epa, geom = fclb.gjk_epa_batch_host(table, pairs, p1, p2, st_of(fclb, dtype), req)
     e_gjk, e_epa, _, e_geom, _ = ref_oracle.gjk_epa_batch(oshapes, pairs, p1, p2, threads=8)
-    report_gjk_epa("convex-convex", dtype, gjk, epa, geom, e_gjk, e_epa, e_geom)
+    parity_util.check_gjk_epa(ref_oracle, "test_gjk_boolean_and_epa", "convex-convex", dtype, oshapes, pairs, p1, p2,
+                              (gjk, epa, geom), (e_gjk, e_epa, e_geom))
     fclb.release(table)
-
-
-def report_gjk_epa(name, dtype, gjk, epa, geom, e_gjk, e_epa, e_geom):
-    n = len(gjk)
-    gm = np.nonzero(gjk != e_gjk)[0]
-    print(f"[{name} {np.dtype(dtype).name}] n={n} intersect={int((e_gjk == 0).sum())} GJK status mismatches={len(gm)} {gm[:8].tolist()}")
-    assert len(gm) <= max(2, n * 2e-5), "GJK status must match the reference (allowing knife-edge pairs)"
-    both = (gjk == 0) & (e_gjk == 0)
-    em = np.nonzero(both & (epa != e_epa))[0]
-    print(f"   EPA status mismatches={len(em)} {em[:8].tolist()}  status histogram ours={np.bincount(epa[both] + 1, minlength=6).tolist()} ref={np.bincount(e_epa[both] + 1, minlength=6).tolist()}")
-    ok = both & (epa == e_epa) & (e_epa != 0)
-    dd = np.abs(geom[ok, 0] - e_geom[ok, 0])
-    ident = float((geom[ok] == e_geom[ok]).all(axis=1).mean()) if ok.any() else 1.0
-    print(f"   depth: max diff {dd.max() if dd.size else 0:.3e}; records bit-identical {ident:.5f}")
-    assert len(em) <= max(2, both.sum() * 1e-3)
-    assert dd.size == 0 or np.quantile(dd, 0.999) <= TOL[dtype]
-    pw = np.abs(geom[ok, 1:] - e_geom[ok, 1:]).max(axis=1)
-    print(f"   witness points: max diff {pw.max() if pw.size else 0:.3e}, >tol: {int((pw > 10 * TOL[dtype]).sum())}")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -157,16 +102,7 @@ def test_generic_collide_api(fclb, ref_oracle, dtype, penetration):
     counts, contacts = fclb.collide_batch_host(table, pairs, p1, p2, st_of(fclb, dtype), req, max_keep=1)
     e_counts, e_contacts = ref_oracle.collide_batch(shapes, pairs, p1, p2, max_keep=1, threads=8, max_contacts=1,
                                                     penetration_mode=penetration)
-    mism = np.nonzero(counts != e_counts)[0]
-    print(f"[generic collide {np.dtype(dtype).name} pen={penetration}] n={n} colliding={int((e_counts > 0).sum())} "
-          f"mismatches={len(mism)} {mism[:10].tolist()}")
-    assert len(mism) <= max(2, n * 3e-5)
-    if penetration:
-        sel = (counts == 1) & (e_counts == 1)
-        dd = np.abs(contacts[sel, 0, 8] - e_contacts[sel, 0, 8])
-        dn = np.abs(contacts[sel, 0, 2:5] - e_contacts[sel, 0, 2:5]).max(axis=1)
-        ident = float((contacts[sel, 0, 2:] == e_contacts[sel, 0, 2:]).all(axis=1).mean())
-        print(f"   depth max diff {dd.max():.3e} (q99.9 {np.quantile(dd, 0.999):.3e}); normal max diff {dn.max():.3e}; "
-              f"contact records bit-identical {ident:.5f}")
-        assert np.quantile(dd, 0.999) <= TOL[dtype]
+    parity_util.check_collide(ref_oracle, "test_generic_collide_api", f"generic pairs pen={penetration}", dtype, shapes, pairs,
+                              p1, p2, (counts, contacts), (e_counts, e_contacts),
+                              dict(max_contacts=1, penetration_mode=penetration), 1)
     fclb.release(table)

@@ -9,50 +9,16 @@ and witness points within TOL.
 import numpy as np
 import pytest
 
+import parity_util
 import scenes
 
 pytestmark = pytest.mark.gpu
 
-# stated tolerances (SURVEY.md 8d "Parity reporting")
-TOL = {np.float32: 1e-4, np.float64: 1e-6}
-EPS_TOUCH = {np.float32: 1e-4, np.float64: 1e-6}
+TOL = parity_util.TOL
 
 
-def compare_distance(got, exp, dtype, label):
-    g_dist, g_p1, g_p2, g_ok = got
-    e_dist, e_p1, e_p2, e_ok = exp
-    n = len(e_ok)
-    g_sep = g_ok != 0
-    e_sep = e_ok != 0
-    mism = np.nonzero(g_sep != e_sep)[0]
-    # a flag mismatch is explained only when the side that says "separated"
-    # reports a distance below EPS (the pair is within EPS of touching)
-    unexplained = []
-    for q in mism:
-        d = g_dist[q] if g_sep[q] else e_dist[q]
-        if not (0 <= d <= EPS_TOUCH[dtype]):
-            unexplained.append(int(q))
-    print(f"[{label}] n={n} separated={int(e_sep.sum())} flag mismatches={len(mism)} "
-          f"(near-touching, listed: {mism[:16].tolist()}) unexplained={len(unexplained)}")
-    assert not unexplained, f"unexplained flag mismatches at {unexplained[:10]}"
-    both = g_sep & e_sep
-    valid = both & (g_ok == 1)
-    dd = np.abs(g_dist[both] - e_dist[both])
-    print(f"[{label}] max |dist diff| = {dd.max() if dd.size else 0:.3e}; "
-          f"bit-identical dist: {int((g_dist[both] == e_dist[both]).sum())}/{int(both.sum())}; "
-          f"witness-invalid (reference returns uninitialised points): {int((both & (g_ok == 3)).sum())}")
-    assert dd.size == 0 or dd.max() <= TOL[dtype]
-    # witness points: compare only where the reference's extraction is valid
-    if valid.any():
-        w1 = np.abs(g_p1[valid] - e_p1[valid]).max()
-        w2 = np.abs(g_p2[valid] - e_p2[valid]).max()
-        print(f"[{label}] max witness diff p1={w1:.3e} p2={w2:.3e}")
-        # witness points of a flat closest feature are not unique; check them through
-        # the distance they realise instead of coordinate-wise when they differ
-        realised = np.linalg.norm(g_p1[valid] - g_p2[valid], axis=1)
-        assert np.abs(realised - g_dist[valid]).max() <= 10 * TOL[dtype]
-    not_sep = ~g_sep & ~e_sep
-    assert np.all(g_dist[not_sep] == -1)
+def compare_distance(ref_oracle, shapes, pairs, poses1, poses2, got, exp, dtype, label, test):
+    parity_util.check_distance(ref_oracle, test, label, dtype, shapes, pairs, poses1, poses2, got, exp)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -63,7 +29,8 @@ def test_c2_mixed_primitive_distance(fclb, ref_oracle, dtype):
     st = fclb.F32 if dtype == np.float32 else fclb.F64
     r = fclb.distance_batch_host(table, pairs, poses1, poses2, st)
     exp = ref_oracle.distance_batch(shapes, pairs, poses1, poses2, threads=8)
-    compare_distance((r.dist, r.p1, r.p2, r.ok), exp, dtype, f"C2 {np.dtype(dtype).name}")
+    compare_distance(ref_oracle, shapes, pairs, poses1, poses2, (r.dist, r.p1, r.p2, r.ok), exp, dtype, "C2 at 300k",
+                     "test_c2_mixed_primitive_distance")
     for k, name in enumerate(("sphere-box", "capsule-box", "cylinder-box")):
         sel = np.arange(n) % 3 == k
         same = (r.dist[sel] == exp[0][sel]).mean()
@@ -94,8 +61,9 @@ def test_closed_form_pairs(fclb, ref_oracle, dtype):
     assert np.array_equal(r.ok[cc] != 0, exp[3][cc] != 0)
     assert np.abs(r.dist[cc] - exp[0][cc]).max() <= TOL[dtype]
     keep = ~cc
-    compare_distance((r.dist[keep], r.p1[keep], r.p2[keep], r.ok[keep]), tuple(a[keep] for a in exp), dtype,
-                     f"closed-form {np.dtype(dtype).name}")
+    compare_distance(ref_oracle, shapes, np.ascontiguousarray(pairs[keep]), np.ascontiguousarray(poses1[keep]),
+                     np.ascontiguousarray(poses2[keep]), (r.dist[keep], r.p1[keep], r.p2[keep], r.ok[keep]),
+                     tuple(a[keep] for a in exp), dtype, "closed-form distance pairs", "test_closed_form_pairs")
     fclb.release(table)
 
 
@@ -154,16 +122,24 @@ def test_signed_distance(fclb, ref_oracle, dtype):
     table = fclb.shapes_upload(shapes)
     r = fclb.signed_distance_batch_host(table, pairs, p1, p2, st)
     e_dist, e_p1, e_p2, e_ok = ref_oracle.signed_distance_batch(rshapes, pairs, p1, p2, threads=8)
+    # ok flag: listed + classified (the flag flips when GJK neither separates nor intersects, or EPA fails: near touching)
     mism = np.nonzero((r.ok != 0) != (e_ok != 0))[0]
+    listed, unexplained = parity_util.classify_touching(ref_oracle, rshapes, pairs, p1, p2, mism, dtype, r.ok, e_ok, "ok flag")
     both = (r.ok != 0) & (e_ok != 0)
     pen = both & (e_dist < 0)
     same = float(((r.dist[both] == e_dist[both]) & (r.p1[both] == e_p1[both]).all(axis=1)).mean())
-    dd = np.abs(r.dist[both] - e_dist[both])
-    dp = np.maximum(np.abs(r.p1[both] - e_p1[both]).max(axis=1), np.abs(r.p2[both] - e_p2[both]).max(axis=1))
-    print(f"[signed distance {np.dtype(dtype).name}] n={n} separated={int((both & ~pen).sum())} penetrating={int(pen.sum())} "
-          f"failed(ref)={int((e_ok == 0).sum())} flag mismatches={len(mism)}; bit-identical {same:.5f}; "
-          f"max |d dist| {dd.max():.2e} max |d witness| {dp.max():.2e}")
-    assert len(mism) <= max(1, n // 20000), mism[:10]
-    assert np.quantile(dd, 0.999) <= tol and np.quantile(dp, 0.999) <= 10 * tol
+    dd = np.where(both, np.abs(r.dist - e_dist), 0.0)
+    bad = np.nonzero(dd > tol)[0]
+    if bad.size:
+        sub = lambda a: np.ascontiguousarray(a[bad])
+        d64 = ref_oracle.signed_distance_batch(rshapes, sub(pairs), sub(p1).astype(np.float64), sub(p2).astype(np.float64))[0]
+        l2, u2 = parity_util.classify_continuous(bad, r.dist[bad], e_dist[bad], {"in double": d64}, dtype, "signed distance")
+        listed += l2
+        unexplained += u2
+    dp = np.where(both, np.maximum(np.abs(r.p1 - e_p1).max(axis=1), np.abs(r.p2 - e_p2).max(axis=1)), 0.0)
+    parity_util.record("test_signed_distance", "7 pair kinds incl. convex", dtype, n, "ok flags, signed distances", listed,
+                       {"separated": int((both & ~pen).sum()), "penetrating": int(pen.sum()), "records_bit_identical_fraction": same,
+                        "max_distance_diff": float(dd.max()), "max_witness_diff": float(dp.max()), "unexplained": len(unexplained)})
+    assert not unexplained, unexplained[:5]
     assert (r.dist[(r.ok == 0)] == -1).all()
     fclb.release(table)
