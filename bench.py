@@ -245,11 +245,36 @@ class Workload:
                                                 threads=threads, **self.req_kw)
         return lambda: oracle.gjk_epa_batch(shapes, self.pairs, self.poses1, self.poses2, threads=threads)
 
+    # -- roofline ------------------------------------------------------------------
+    def shape_types(self):
+        shapes = self.shapes if self.shapes is not None else [(scenes.CONVEX, 0, ()), (scenes.CONVEX, 1, ())]
+        return np.asarray([s[0] for s in shapes], np.int64)
+
+    def bucket_mask(self, t1, t2):
+        ty = self.shape_types()
+        return (ty[self.pairs["shape1"]] == t1) & (ty[self.pairs["shape2"]] == t2)
+
+    def bound_of(self, top):
+        """closed-form buckets move bytes; the iterative GJK / EPA buckets issue flops"""
+        t1, t2 = top.get("t1", -1), top.get("t2", -1)
+        closed_distance = {(1, 0), (0, 1), (1, 3), (3, 1), (1, 5), (5, 1), (1, 1), (3, 3)}
+        closed_collide = closed_distance - {(3, 3)} | {(0, 0)}
+        if self.kind == "distance" and (t1, t2) in closed_distance:
+            return "hbm"
+        if self.kind == "collide" and (t1, t2) in closed_collide:
+            return "hbm"
+        return "fp32" if self.dtype_name == "f32" else "fp64"
+
+    def teardown(self):
+        self.fclb.release(self.table)
+        self.d_out = self.h_out = self.d_pairs = self.d_p1 = self.d_p2 = self.h_pairs = self.h_p1 = self.h_p2 = None
+
 
 class MeshWorkload:
     """C3: fcl::collide(BVHModel<OBBRSS>, BVHModel<OBBRSS>) per relative pose, boolean (max_contacts=1)."""
 
     kind = "bvh_collide"
+    bound = "l2"
 
     def __init__(self, name, n, dtype_name, seed):
         self.name = name
@@ -318,12 +343,21 @@ class MeshWorkload:
         return lambda: oracle.bvh_collide_batch(ids[0], ids[1], self.poses1[:m], self.poses2[:m], threads=threads,
                                                 want_pair=False, max_contacts=1)
 
+    def kernel_records(self):
+        return [{"kernel": "bvh_collide", "queries": self.n, "avg_ms": self.fclb.last_kernel_ms(),
+                 "bytes_per_query": self.algorithmic_bytes_per_query()}]
+
+    def teardown(self):
+        for h in self.handles:
+            self.fclb.bvh_release(h)
+
 
 class ArmSceneWorkload:
     """C4: n configurations x 7 convex links, each link tested against the scene mesh (mesh-shape
     traversal) and against the heightmap (heightmap-shape scan): 14 n narrowphase queries per step."""
 
     kind = "scene_collide"
+    bound = "l2"
 
     def __init__(self, name, n, dtype_name, seed):
         self.name = name
@@ -438,14 +472,19 @@ class ArmSceneWorkload:
                                                  threads=threads, want_pixel=False, max_contacts=1)
         return run
 
+    def teardown(self):
+        self.fclb.bvh_release(self.bvh)
+        self.fclb.heightmap_release(self.hm)
+        self.fclb.release(self.table)
+
 
 class BroadphaseWorkload:
     """C5: per scene computeAABB + tree build + SelfCollision + boolean collide on every candidate.
     A step processes `scenes_per_step` scenes; the metric counts candidate pairs (narrowphase queries)."""
 
     kind = "scene_self_collide"
+    bound = "hbm"
     SCENES = 8
-    cpu_threads = 1  # BinaryAABB_Tree::SelfCollision + its callback is one sequential loop in the reference
 
     def __init__(self, name, n, dtype_name, seed):
         self.name = name
@@ -506,15 +545,34 @@ class BroadphaseWorkload:
                 "objects_per_sec_broadphase_plus_narrowphase": None}
 
     def cpu_sample(self):
-        return self.cand[0] if self.cand[0] else self.n_objects * 4
+        return getattr(self, "cpu_cand", 0) or self.n_objects * 4 * self.SCENES
 
     def cpu_run(self, oracle, threads):
-        shapes, ids, poses = self.scenes[0]
+        """BinaryAABB_Tree::SelfCollision + its fcl::collide callback is one sequential loop per scene in the reference;
+        the CPU arm runs the step's scenes in parallel, one host thread per scene."""
+        self.cpu_threads_used = min(threads, self.SCENES)
 
         def run():
-            hits, cand = oracle.scene_self_collide(shapes, ids, poses)
-            self.cand[0] = self.cand[0] or cand
+            out = [0] * self.SCENES
+
+            def one(k):
+                shapes, ids, poses = self.scenes[k]
+                out[k] = oracle.scene_self_collide(shapes, ids, poses)[1]
+            ts = [threading.Thread(target=one, args=(k,)) for k in range(self.SCENES)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            self.cpu_cand = sum(out)
         return run
+
+    def kernel_records(self):
+        ms = getattr(self, "measured_step_ms", 0.0)
+        return [{"kernel": "scene_self_collide (8 scenes: aabb, sort, hierarchy, pairs, gather, narrowphase)", "queries": self.n,
+                 "avg_ms": ms, "bytes_per_query": self.algorithmic_bytes_per_query()}]
+
+    def teardown(self):
+        self.fclb.release(self.table)
 
 
 def make_workload(name, n, dtype_name, seed):
@@ -525,6 +583,89 @@ def make_workload(name, n, dtype_name, seed):
     if name == "c5":
         return BroadphaseWorkload(name, n, dtype_name, seed)
     return Workload(name, n, dtype_name, seed)
+
+
+DEFAULT_QUERIES = {"c2": 10_000_000, "c4": 100_000, "c5": 100_000}
+
+
+def default_queries(name):
+    return DEFAULT_QUERIES.get(name, 1_000_000)
+
+
+# ---- SURVEY.md 8(d) flop / query model for the GJK / EPA buckets -----------------------------------------------
+# flop/query = n_sup * F_sup + n_gjk * F_proj + n_epa * (F_epa0 + F_scan * (V + E + F)), all counts taken from the CPU
+# oracles on the bench seed (deterministic properties of the input), constants as SURVEY.md fixes them.
+F_PROJ = {1: 0, 2: 40, 3: 120, 4: 270}
+F_EPA0, F_SCAN, F_DOT = 400, 2, 5
+SHAPE_NAMES = {0: "box", 1: "sphere", 2: "ellipsoid", 3: "capsule", 4: "cone", 5: "cylinder", 6: "convex", 7: "triangle"}
+
+
+def f_sup(t1, t2):
+    if t1 == 6 or t2 == 6:
+        return 33  # the two transforms; the Convex dot products are counted separately (5 flop each)
+    if t1 == 0 and t2 == 0:
+        return 48
+    return 60
+
+
+def flop_model(wl, t1, t2, sel, want_distance, with_epa, sample=200_000):
+    """flop / query of one (type1, type2) bucket of a shape-pair workload, from the oracles' counters on the first
+    `sample` queries of the bucket.  Returns None when no oracle is built."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ctypes as C
+        import oracle_py
+        port = oracle_py.PortOracle() if oracle_py.have_port() else None
+        ref = oracle_py.RefOracle() if oracle_py.have_ref() else None
+    except Exception:
+        return None
+    if port is None:
+        return None
+    idx = np.nonzero(sel)[0][:sample]
+    if idx.size == 0:
+        return None
+    shapes = wl.shapes
+    if wl.convex is not None:
+        slots = [port.register_convex(*m) for m in wl.convex]
+        shapes = [(scenes.CONVEX, slots[0], ()), (scenes.CONVEX, slots[1], ())]
+    pairs = np.ascontiguousarray(wl.pairs[idx])
+    p1, p2 = np.ascontiguousarray(wl.poses1[idx]), np.ascontiguousarray(wl.poses2[idx])
+    out = np.zeros(16, np.uint64)
+    arr = oracle_py._shape_array(shapes)
+    f = port.fn("gjk_work_counters")
+    f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_uint32,
+                  C.c_int, C.c_void_p, C.c_int]
+    tol = 0.0 if want_distance else 1e-6  # shapeDistance: eps^(7/8); the collide / gjk_epa path: 1e-6
+    f(oracle_py._st(p1.dtype), C.cast(arr, C.c_void_p), len(shapes), oracle_py._p(pairs), oracle_py._p(p1), oracle_py._p(p2),
+      len(idx), tol, 0, 1 if want_distance else 0, oracle_py._p(out), os.cpu_count() or 1)
+    m = float(out[0])
+    sv, ex, dots = float(out[1]), float(out[2]), float(out[3])
+    proj = {r: float(out[4 + r]) for r in range(5)}
+    upd = {r: float(out[9 + r]) for r in range(5)}
+    fs = f_sup(t1, t2)
+    flops = sv * fs + ex * fs / 2 + dots * F_DOT
+    flops += sum(proj[r] * F_PROJ.get(r, 0) for r in proj) + sum(upd[r] * F_PROJ.get(r, 0) for r in upd)
+    model = {"sample_queries": int(m), "n_sup_per_query": (sv + ex / 2) / m, "n_gjk_per_query": sum(proj.values()) / m,
+             "n_dist_per_query": sum(upd.values()) / m, "convex_dots_per_query": dots / m, "F_sup": fs,
+             "F_proj_rank2/3/4": [40, 120, 270], "gjk_flop_per_query": flops / m}
+    if with_epa and ref is not None:
+        rshapes = wl.shapes
+        if wl.convex is not None:
+            slots = [ref.register_convex(*mm) for mm in wl.convex]
+            rshapes = [(scenes.CONVEX, slots[0], ()), (scenes.CONVEX, slots[1], ())]
+        _, epa, _, _, iters = ref.gjk_epa_batch(rshapes, pairs, p1, p2, threads=os.cpu_count() or 1)
+        k = iters[:, 1].astype(np.float64) / 2.0  # EPA supportVertex evaluations = expansions (+ the initial polytope's)
+        dots_per_sup = dots / max(sv, 1.0)
+        # a closed triangulated polytope after i expansions: V = 4 + i, F = 4 + 2 i, E = 6 + 3 i  (Euler), so the
+        # nearest-feature scans of k iterations touch sum_i (14 + 6 i) = 14 k + 3 k (k - 1) elements
+        scan = 14.0 * k + 3.0 * k * (k - 1.0)
+        epa_flops = k * (F_EPA0 + fs + dots_per_sup * F_DOT) + F_SCAN * scan
+        model.update({"n_epa_per_query": float(k.mean()), "epa_flop_per_query": float(epa_flops.mean()),
+                      "mean_V+E+F_scanned_per_iteration": float(scan.sum() / max(k.sum(), 1.0)),
+                      "F_epa0": F_EPA0, "F_scan": F_SCAN, "intersecting_fraction": float((epa >= 0).mean())})
+        flops += float(epa_flops.sum())
+    model["flop_per_query"] = flops / m
+    return model
 
 
 def run_reference(args, rank, world):
@@ -542,12 +683,14 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         fn()
     el = time.perf_counter() - t
+    m = wl.cpu_sample() if hasattr(wl, "cpu_sample") else wl.n
     v = m * args.steps / el
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "queries_per_step": wl.n, "note": "host CPU only; GPUs idle"},
+        "config": {"workload": WORKLOADS[args.workload], "queries_per_step": wl.n, "queries_per_gpu_per_step": wl.n,
+                   "note": "host CPU only; GPUs idle"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": oracle.kind,
                          "sample": f"{m} of the step's {wl.n} queries per step, {args.steps} timed steps"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -590,6 +733,182 @@ def claim_stdout():
     os.dup2(2, 1)
 
 
+class Ctx:
+    """Everything a measurement needs: torch, the process group, the engine's stream, measured peaks."""
+
+    def __init__(self, torch, dist, fclb, dev, rank, world, local_rank):
+        self.torch, self.dist, self.fclb, self.dev = torch, dist, fclb, dev
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.stream = torch.cuda.ExternalStream(fclb.stream_ptr(), device=dev)
+        self.hbm_peak, self.hbm_src = measured_peaks()
+        self.fp_peak = {}
+        self.l2_peak = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def peaks(self):
+        """FP32 / FP64 FMA-chain and L2 read-bandwidth microbenchmarks, run once on this device."""
+        if not self.fp_peak:
+            f = self.fclb
+            try:
+                self.fp_peak = {"f32": f.measure_fp_peak(f.F32), "f64": f.measure_fp_peak(f.F64)}
+                self.l2_peak = f.measure_l2_bandwidth()
+            except Exception as ex:
+                self.fp_peak = {"error": str(ex)}
+        return self.fp_peak, self.l2_peak
+
+    def timed(self, fn, steps, warmup):
+        torch, fclb = self.torch, self.fclb
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        self.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        launches0 = fclb.launch_count()
+        per_launch = {}
+        t0 = time.time()
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+            for (t1_, t2_, cnt, ms) in fclb.last_launches():
+                per_launch.setdefault((t1_, t2_, cnt), []).append(ms)
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        self.barrier()
+        ms_total = self.max_over_ranks(e0.elapsed_time(e1))
+        return ms_total, fclb.launch_count() - launches0, per_launch, (t0, t1)
+
+
+def build_roofline(ctx, wl, args_dtype, kern, with_model):
+    """Roofline of the dominant kernel against the ceiling that binds it (hbm / l2 / fp32 / fp64), with the per-bucket
+    list inside.  `kern`: [{kernel, queries, avg_ms[, bytes_per_query][, t1, t2]}], sorted by time."""
+    if not kern:
+        return None
+    fp_peak, l2_peak = ctx.peaks()
+    top = kern[0]
+    bpq = top.get("bytes_per_query", wl.algorithmic_bytes_per_query())
+    sec = top["avg_ms"] * 1e-3
+    hbm_gbs = top["queries"] * bpq / sec / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            rec = json.load(f).get(top["kernel"] + ":" + args_dtype)
+        if rec:  # one ncu --set full capture of this kernel, scaled linearly to this launch's query count
+            traffic = rec["bytes"] * top["queries"] / rec["queries"]
+    bound = getattr(wl, "bound", None) or wl.bound_of(top)
+    roof = {"kernel": top["kernel"], "queries_per_launch": top["queries"], "avg_launch_ms": top["avg_ms"], "traffic": traffic}
+    hbm_view = {"achieved": hbm_gbs, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": hbm_gbs / ctx.hbm_peak,
+                "algorithmic_bytes_per_query": bpq, "peak_source": ctx.hbm_src}
+    if bound in ("fp32", "fp64") and with_model and "t1" in top:
+        model = flop_model(wl, top["t1"], top["t2"], wl.bucket_mask(top["t1"], top["t2"]), wl.kind == "distance",
+                           wl.kind == "gjk_epa")
+        peak = fp_peak.get("f32" if bound == "fp32" else "f64") if isinstance(fp_peak, dict) else None
+        if model and peak:
+            ach = top["queries"] * model["flop_per_query"] / sec / 1e12
+            roof.update({"bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "peak_source": "measured here: FMA chain, 16 accumulators per thread (an FMA counted as 2 flop; the "
+                                        "product is compiled --fmad=false for parity with the reference, which halves what "
+                                        "a mul+add stream can reach)",
+                         "flop_model": model, "hbm_view": hbm_view})
+    if "bound" not in roof and bound == "l2" and l2_peak:
+        roof.update({"bound": "l2", "achieved": hbm_gbs, "peak": l2_peak, "unit": "GB/s", "frac": hbm_gbs / l2_peak,
+                     "peak_source": "measured here: 32 MB L2-resident buffer streamed by every SM with 128-bit loads",
+                     "algorithmic_bytes_per_query": bpq, "hbm_view": hbm_view})
+    if "bound" not in roof:
+        roof.update({"bound": "hbm", **hbm_view})
+    roof["note"] = wl.roof_note() if hasattr(wl, "roof_note") else (
+        "closed-form buckets are HBM-bound (bytes = 2 poses + result record); the iterative GJK / EPA buckets are bound by "
+        "FP32 / FP64 issue and SIMT divergence: their fraction is the SURVEY.md 8(d) flop model over the measured FMA peak")
+    for k in kern:
+        b = k.get("bytes_per_query", bpq)
+        k["hbm_gbs"] = k["queries"] * b / (k["avg_ms"] * 1e-3) / 1e9
+        k["hbm_frac"] = k["hbm_gbs"] / ctx.hbm_peak
+        k.pop("t1", None)
+        k.pop("t2", None)
+    roof["kernels"] = kern
+    return roof
+
+
+def measure(ctx, name, queries, dtype, steps, warmup, seed, with_cpu, with_model, clock_sampler=None):
+    """One workload, the full record: device-resident value, e2e through the host-buffer C ABI, roofline, CPU baseline."""
+    torch, fclb = ctx.torch, ctx.fclb
+    wl = make_workload(name, queries, dtype, seed=seed)
+    wl.setup(fclb, torch, ctx.dev)
+    torch.cuda.synchronize()
+    if clock_sampler:
+        clock_sampler.start()
+    ms_dev, launches, per_launch, win = ctx.timed(wl.step_dev, steps, warmup)
+    clocks = clock_sampler.stop(*win) if clock_sampler else None
+    e2e_steps = max(3, steps // 2)
+    ms_e2e, _, _, _ = ctx.timed(wl.step_host, e2e_steps, 3)
+    n = wl.n  # (C5 learns its candidate-pair count from the run itself)
+    total_n = ctx.sum_over_ranks(n)
+    value = total_n * steps / (ms_dev * 1e-3)
+    e2e_value = total_n * e2e_steps / (ms_e2e * 1e-3)
+
+    kern = []
+    for (t1_, t2_, cnt), v in per_launch.items():
+        label = f"{wl.kind}[{SHAPE_NAMES.get(t1_, '?')}-{SHAPE_NAMES.get(t2_, '?')}]" if t1_ >= 0 else wl.kind
+        kern.append({"kernel": label, "queries": cnt, "avg_ms": float(np.mean(v)), "t1": t1_, "t2": t2_})
+    wl.measured_step_ms = ms_dev / steps
+    if hasattr(wl, "kernel_records"):
+        kern = wl.kernel_records()
+    kern.sort(key=lambda k: -k["avg_ms"])
+    roof = build_roofline(ctx, wl, dtype, kern, with_model and ctx.rank == 0)
+    rec = {
+        "workload": name, "value": value, "unit": UNIT, "ms_per_step": ms_dev / steps, "steps": steps, "dtype": dtype,
+        "config": {"workload": WORKLOADS[name], "queries_per_gpu_per_step": n, "queries_per_step": n,
+                   "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (wl.h2d_bytes() / 1e6)
+                   if wl.h2d_bytes() > 200e6 else "inputs %.0f MB/step: smaller than L2 on purpose of the config; "
+                   "each step re-reads them after %.0f MB of result writes" % (wl.h2d_bytes() / 1e6, wl.d2h_bytes() / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes(),
+                "d2h_bytes_per_step": wl.d2h_bytes(), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                # the host link is what bounds this number once copies and kernels overlap: bytes moved per
+                # second in each direction (PCIe is full duplex; Gen5 x16 peaks near 55-57 GB/s one way)
+                "h2d_gbs": wl.h2d_bytes() / (ms_e2e / e2e_steps) / 1e6, "d2h_gbs": wl.d2h_bytes() / (ms_e2e / e2e_steps) / 1e6},
+        "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
+    }
+    if hasattr(wl, "extra"):
+        rec["config"].update(wl.extra())
+    if with_cpu and ctx.rank == 0:
+        try:
+            oracle = load_oracle()
+            threads = getattr(wl, "cpu_threads", os.cpu_count() or 1)
+            fn = wl.cpu_run(oracle, threads)
+            best = None
+            for _ in range(3 if name == "c2" else 2):
+                t = time.perf_counter()
+                fn()
+                dt = time.perf_counter() - t
+                best = dt if best is None else min(best, dt)
+            m = wl.cpu_sample() if hasattr(wl, "cpu_sample") else n
+            rec["cpu_baseline"] = {"value": m / best, "unit": UNIT, "cores": threads, "kind": oracle.kind,
+                                   "sample": f"{m} of the step's {n} queries, best of {3 if name == 'c2' else 2} ({best:.2f} s each)"}
+        except Exception as ex:  # the CPU leg is a reported baseline, never the product path
+            rec["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
+    wl.teardown()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -599,12 +918,16 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: the config's size)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU gets the config's batch; strong: ONE batch of the config's size sharded by query index")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the per-config records of the other workloads")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3)
+    explicit_queries = args.queries > 0
     if args.queries <= 0:
-        args.queries = {"c2": 10_000_000, "c4": 100_000, "c5": 100_000}.get(args.workload, 1_000_000)
+        args.queries = default_queries(args.workload)
 
     rank = env_int("RANK", 0)
     world = env_int("WORLD_SIZE", 1)
@@ -627,145 +950,62 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    ctx = Ctx(torch, dist, fclb, dev, rank, world, local_rank)
 
-    # each rank owns its own shard of the job: independent queries, replicated geometry
-    wl = make_workload(args.workload, args.queries, args.dtype, seed=rank)
-    wl.setup(fclb, torch, dev)
-    n = wl.n
-    torch.cuda.synchronize()
-    stream = torch.cuda.ExternalStream(fclb.stream_ptr(), device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        launches0 = fclb.launch_count()
-        per_launch = {}
-        t0 = time.time()
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-            for (t1_, t2_, cnt, ms) in fclb.last_launches():
-                per_launch.setdefault((t1_, t2_, cnt), []).append(ms)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        t1 = time.time()
-        barrier()
-        ms_total = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_total = float(t.item())
-        return ms_total, fclb.launch_count() - launches0, per_launch, (t0, t1)
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms_dev, launches, per_launch, win = timed(wl.step_dev, args.steps, args.warmup)
-    clocks = sampler.stop(*win) if rank == 0 else None
-    e2e_steps = max(3, args.steps // 2)
-    ms_e2e, _, _, _ = timed(wl.step_host, e2e_steps, 3)
-
-    n = wl.n  # (C5 learns its candidate-pair count from the run itself)
-    total_n = n * world
-    if world > 1:
-        tn = torch.tensor([float(n)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tn, op=dist.ReduceOp.SUM)
-        total_n = float(tn.item())
-    value = total_n * args.steps / (ms_dev * 1e-3)
-    e2e_value = total_n * e2e_steps / (ms_e2e * 1e-3)
-
-    # dominant kernel of the step and its roofline
-    names = {0: "box", 1: "sphere", 2: "ellipsoid", 3: "capsule", 4: "cone", 5: "cylinder", 6: "convex", 7: "triangle"}
-    kern = []
-    for (t1_, t2_, cnt), v in per_launch.items():
-        label = f"{wl.kind}[{names.get(t1_, '?')}-{names.get(t2_, '?')}]" if t1_ >= 0 else wl.kind
-        kern.append({"kernel": label, "queries": cnt, "avg_ms": float(np.mean(v))})
-    if hasattr(wl, "kernel_records"):
-        kern = wl.kernel_records()
-    kern.sort(key=lambda k: -k["avg_ms"])
-    peak, peak_src = measured_peaks()
-    bpq = wl.algorithmic_bytes_per_query()
-    roof = None
-    if kern:
-        top = kern[0]
-        bpq = top.get("bytes_per_query", bpq)
-        achieved = top["queries"] * bpq / (top["avg_ms"] * 1e-3) / 1e9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(prof):
-            with open(prof) as f:
-                rec = json.load(f).get(top["kernel"] + ":" + args.dtype)
-            if rec:  # one ncu capture, scaled linearly to this launch's query count
-                traffic = rec["bytes"] * top["queries"] / rec["queries"]
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": top["kernel"], "peak_source": peak_src,
-                "algorithmic_bytes_per_query": bpq, "queries_per_launch": top["queries"],
-                "avg_launch_ms": top["avg_ms"],
-                "note": wl.roof_note() if hasattr(wl, "roof_note") else
-                "iterative GJK/EPA buckets are FP32/FP64-issue and latency bound, not HBM bound (DESIGN.md 4.3); "
-                "closed-form buckets are the HBM-bound kernels; per-bucket figures under 'kernels'"}
-        for k in kern:
-            k["hbm_gbs"] = k["queries"] * k.get("bytes_per_query", bpq) / (k["avg_ms"] * 1e-3) / 1e9
-            k["hbm_frac"] = k["hbm_gbs"] / peak
-
+    # each rank owns its own shard of the job: independent queries, replicated geometry, no collective on the data path
+    per_gpu = args.queries
+    if args.scaling == "strong":
+        per_gpu = shard_size(args.queries, rank, world)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    head = measure(ctx, args.workload, per_gpu, args.dtype, args.steps, args.warmup, seed=rank,
+                   with_cpu=(world == 1 and not args.no_cpu_baseline), with_model=True, clock_sampler=sampler)
+    fp_peak, l2_peak = ctx.peaks()
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "queries_per_gpu_per_step": n,
-                   "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (wl.h2d_bytes() / 1e6)
-                   if wl.h2d_bytes() > 200e6 else "inputs %.0f MB/step: smaller than L2 on purpose of the config; "
-                   "each step re-reads them after %.0f MB of result writes" % (wl.h2d_bytes() / 1e6, wl.d2h_bytes() / 1e6),
-                   "sharding": "queries sharded by rank, geometry replicated, no collective on the data path"
-                   + ("" if numa is None else "; rank processes bound to their GPU's NUMA node")},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes(),
-                "d2h_bytes_per_step": wl.d2h_bytes(), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                # the host link is what bounds this number once copies and kernels overlap: bytes moved per
-                # second in each direction (PCIe is full duplex; Gen5 x16 peaks near 55-57 GB/s one way)
-                "h2d_gbs": wl.h2d_bytes() / (ms_e2e / e2e_steps) / 1e6, "d2h_gbs": wl.d2h_bytes() / (ms_e2e / e2e_steps) / 1e6},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roof,
-        "kernels": kern,
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": head["config"], "e2e": head["e2e"],
+        "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "roofline": head["roofline"],
+        "kernels": (head["roofline"] or {}).get("kernels"),
     }
-
-    if hasattr(wl, "extra"):
-        line["config"].update(wl.extra())
+    line["config"]["sharding"] = ("queries sharded by rank, geometry replicated, no collective on the data path"
+                                  + ("" if numa is None else "; rank processes bound to their GPU's NUMA node"))
+    if "cpu_baseline" in head:
+        line["cpu_baseline"] = head["cpu_baseline"]
     if rank == 0:
-        try:  # measured CUDA-core FMA peaks: the denominators for the compute-bound GJK / MPR / EPA kernels
-            line["fp_peak_measured"] = {"fp32_tflops": fclb.measure_fp_peak(fclb.F32), "fp64_tflops": fclb.measure_fp_peak(fclb.F64),
-                                        "how": "FMA chain, 16 accumulators per thread, 8 CTAs x 256 threads per SM, best of 5"}
-        except Exception as ex:
-            line["fp_peak_measured"] = {"error": str(ex)}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            oracle = load_oracle()
-            threads = getattr(wl, "cpu_threads", os.cpu_count() or 1)
-            fn = wl.cpu_run(oracle, threads)
-            best = None
-            for _ in range(3):
-                t = time.perf_counter()
-                fn()
-                dt = time.perf_counter() - t
-                best = dt if best is None else min(best, dt)
-            m = wl.cpu_sample() if hasattr(wl, "cpu_sample") else n
-            line["cpu_baseline"] = {"value": m / best, "unit": UNIT, "cores": threads, "kind": oracle.kind,
-                                    "sample": f"{m} of the step's {n} queries, best of 3 ({best:.2f} s each)"}
-        except Exception as ex:  # the CPU leg is a reported baseline, never the product path
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
+        line["fp_peak_measured"] = {"fp32_tflops": (fp_peak or {}).get("f32"), "fp64_tflops": (fp_peak or {}).get("f64"),
+                                    "l2_read_gbs": l2_peak,
+                                    "how": "FMA chain, 16 accumulators per thread, 8 CTAs x 256 threads per SM, best of 5; "
+                                           "L2: 32 MB resident buffer, 128-bit loads, all SMs"}
+    # the same job as ONE batch of the config's size sharded by query index over the N GPUs (strong scaling): the
+    # north star's "query batch sharded across the GPUs of one box"
+    if world > 1 and args.scaling == "weak" and not explicit_queries:
+        st = measure(ctx, args.workload, shard_size(args.queries, rank, world), args.dtype, max(3, args.steps // 2), 3,
+                     seed=rank, with_cpu=False, with_model=False)
+        line["strong_scaling"] = {"total_queries_per_step": args.queries, "value": st["value"], "ms_per_step": st["ms_per_step"],
+                                  "e2e": st["e2e"], "note": "one batch of the config's size, sharded by contiguous query range"}
+    # every other config of BASELINE.json at its full size, one record each (N = 1 only: keeps the scaling runs short)
+    if world == 1 and not args.no_workloads and args.workload == "c2" and not explicit_queries:
+        others = []
+        for name in ("c1a", "c1b", "c1b_convex", "c3", "c4", "c5"):
+            try:
+                r = measure(ctx, name, default_queries(name), args.dtype, min(args.steps, 5), 3, seed=0,
+                            with_cpu=not args.no_cpu_baseline, with_model=True)
+                r.pop("clocks", None)
+                others.append(r)
+            except Exception as ex:
+                others.append({"workload": name, "error": f"{type(ex).__name__}: {ex}"})
+        line["workloads"] = others
 
     if rank == 0:
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def shard_size(total, rank, world):
+    """contiguous query-index ranges, remainder to the first ranks (mind-fcl_b200/sharding.py)"""
+    base, rem = divmod(total, world)
+    return base + (1 if rank < rem else 0)
 
 
 if __name__ == "__main__":

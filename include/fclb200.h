@@ -443,6 +443,9 @@ int fclb_scene_self_collide_dev(fclb_handle shapes, const uint32_t* shape_ids, c
 /* measured FP32 / FP64 FMA throughput of the bound device (FMA-chain microbenchmark, TFLOP/s):
  * the denominator for the compute-bound GJK / MPR / EPA kernels */
 int fclb_measure_fp_peak(int scalar_type, double* tflops);
+/* measured L2 read bandwidth (GB/s; 32 MB L2-resident buffer streamed by every SM with 128-bit loads): the denominator
+ * for the traversal kernels, whose node / triangle / pixel arrays are L2-resident */
+int fclb_measure_l2_bandwidth(double* gbs);
 
 /* kernel launches issued by this process so far (bench.py's gpu_launches) */
 uint64_t fclb_launch_count(void);

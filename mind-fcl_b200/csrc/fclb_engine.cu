@@ -397,6 +397,23 @@ __global__ void __launch_bounds__(256) fmaPeakKernel(S* out, int iters, S a, S b
   if (sum == S(-12345)) out[0] = sum;  // keep the chain alive
 }
 
+// L2 read-bandwidth microbenchmark: every CTA streams the same 32 MB buffer (L2-resident after the first pass) with
+// 128-bit ld.global.cg loads -- the ceiling for the traversal kernels, whose node / triangle arrays live in L2.
+__global__ void __launch_bounds__(256) l2ReadKernel(const uint4* __restrict__ buf, size_t n_vec, int passes, uint4* out) {
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (int p = 0; p < passes; p++) {
+    for (size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x + size_t(p) * 977) % stride; i < n_vec; i += stride) {
+      const uint4 v = __ldcg(buf + i);
+      acc.x ^= v.x;
+      acc.y ^= v.y;
+      acc.z ^= v.z;
+      acc.w ^= v.w;
+    }
+  }
+  if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) out[0] = acc;  // keep the loads alive
+}
+
 extern "C" {
 
 const char* fclb_last_error(void) { return g_err.c_str(); }
@@ -502,6 +519,33 @@ int fclb_measure_fp_peak(int scalar_type, double* tflops) {
   cudaFree(d_out);
   const double flops = 2.0 * 16.0 * double(iters) * double(grid) * double(block);
   *tflops = flops / (double(best_ms) * 1e-3) / 1e12;
+  return FCLB_OK;
+}
+
+int fclb_measure_l2_bandwidth(double* gbs) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (!gbs) return fail(FCLB_ERR_BAD_ARG, "fclb_measure_l2_bandwidth: null argument");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t bytes = size_t(32) << 20, n_vec = bytes / sizeof(uint4);
+  uint4* d = nullptr;
+  FCLB_CUDA(cudaMalloc(&d, bytes + sizeof(uint4)));
+  FCLB_CUDA(cudaMemsetAsync(d, 1, bytes + sizeof(uint4), e.compute));
+  const int grid = e.sms * 8, passes = 16;
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+    l2ReadKernel<<<grid, 256, 0, e.compute>>>(d, n_vec, passes, d + n_vec);
+    FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+    e.launches += 1;
+  }
+  cudaFree(d);
+  *gbs = double(bytes) * passes / (double(best_ms) * 1e-3) / 1e9;
   return FCLB_OK;
 }
 

@@ -48,7 +48,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
-    "fclb_measure_fp_peak", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
+    "fclb_measure_fp_peak", "fclb_measure_l2_bandwidth", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
 
@@ -713,6 +713,13 @@ def measure_fp_peak(scalar_type) -> float:
     """FMA-chain microbenchmark on the bound device, TFLOP/s."""
     v = C.c_double()
     check(load().fclb_measure_fp_peak(scalar_type, C.byref(v)))
+    return v.value
+
+
+def measure_l2_bandwidth() -> float:
+    """measured L2 read bandwidth of the bound device, GB/s"""
+    v = C.c_double()
+    check(load().fclb_measure_l2_bandwidth(C.byref(v)))
     return v.value
 
 
