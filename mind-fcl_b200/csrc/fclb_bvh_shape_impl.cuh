@@ -20,7 +20,9 @@
 #include "fclb_bound.h"
 #include "fclb_bvh.cuh"
 #include "fclb_bvh_build.h"
+#include "fclb_leafcand.cuh"
 #include "fclb_mpr.cuh"
+#include "fclb_sphere_triangle.cuh"
 
 // 3 CTAs per SM (80 registers, no spills): 26.1 -> 25.4 ms on C4
 #ifndef FCLB_SCENE_MIN_BLOCKS
@@ -172,81 +174,6 @@ FCLB_DI NodeD<S> shapeWorldObb(const ShapeInst<S>& sh, const BoundD<S>* __restri
     return fitObbPoints<S>(c.n_verts, [&](int i) { return apply(tf, loadVert(c.verts, i)); });
   }
   return fitObbPointsWarp<S>(bound->n, [&](int i) { return apply(tf, loadVert(bound->v, i)); }, pts, lane);
-}
-
-// ---- sphere_triangle-inl.h:50-186 (boolean part) ----
-template <typename S>
-FCLB_DI S segmentSqrDistance(const V3<S>& from, const V3<S>& to, const V3<S>& p, V3<S>& nearest) {
-  V3<S> diff = p - from;
-  const V3<S> v = to - from;
-  S t = dot(v, diff);
-  if (t > 0) {
-    const S dotVV = dot(v, v);
-    if (t < dotVV) {
-      t /= dotVV;
-      diff = diff - v * t;
-    } else {
-      t = 1;
-      diff = diff - v;
-    }
-  } else {
-    t = 0;
-  }
-  nearest = from + v * t;
-  return dot(diff, diff);
-}
-template <typename S>
-FCLB_DI bool projectInTriangle(const V3<S>& p1, const V3<S>& p2, const V3<S>& p3, const V3<S>& normal, const V3<S>& p) {
-  const V3<S> edge1 = p2 - p1, edge2 = p3 - p2, edge3 = p1 - p3;
-  const V3<S> p1_to_p = p - p1, p2_to_p = p - p2, p3_to_p = p - p3;
-  const S r1 = dot(cross(edge1, normal), p1_to_p);
-  const S r2 = dot(cross(edge2, normal), p2_to_p);
-  const S r3 = dot(cross(edge3, normal), p3_to_p);
-  return (r1 > 0 && r2 > 0 && r3 > 0) || (r1 <= 0 && r2 <= 0 && r3 <= 0);
-}
-template <typename S>
-FCLB_DI bool sphereTriangleIntersect(S radius, const V3<S>& center, const V3<S>& P1, const V3<S>& P2, const V3<S>& P3) {
-  V3<S> normal = normalized(cross(P2 - P1, P3 - P1));
-  const S radius_with_threshold = radius + numeric_eps<S>::value();
-  const V3<S> p1_to_center = center - P1;
-  S distance_from_plane = dot(p1_to_center, normal);
-  if (distance_from_plane < 0) {
-    distance_from_plane *= -1;
-    normal = normal * S(-1);
-  }
-  const bool is_inside_contact_plane = (distance_from_plane < radius_with_threshold);
-  bool has_contact = false;
-  V3<S> contact_point = zero3<S>();
-  if (is_inside_contact_plane) {
-    if (projectInTriangle(P1, P2, P3, normal, center)) {
-      has_contact = true;
-      contact_point = center - normal * distance_from_plane;
-    } else {
-      const S contact_capsule_radius_sqr = radius_with_threshold * radius_with_threshold;
-      V3<S> nearest_on_edge;
-      S distance_sqr = segmentSqrDistance(P1, P2, center, nearest_on_edge);
-      if (distance_sqr < contact_capsule_radius_sqr) {
-        has_contact = true;
-        contact_point = nearest_on_edge;
-      }
-      distance_sqr = segmentSqrDistance(P2, P3, center, nearest_on_edge);
-      if (distance_sqr < contact_capsule_radius_sqr) {
-        has_contact = true;
-        contact_point = nearest_on_edge;
-      }
-      distance_sqr = segmentSqrDistance(P3, P1, center, nearest_on_edge);
-      if (distance_sqr < contact_capsule_radius_sqr) {
-        has_contact = true;
-        contact_point = nearest_on_edge;
-      }
-    }
-  }
-  if (has_contact) {
-    const V3<S> contact_to_center = contact_point - center;
-    const S distance_sqr = sqnorm(contact_to_center);
-    if (distance_sqr < radius_with_threshold * radius_with_threshold) return true;
-  }
-  return false;
 }
 
 // ---- box_triangle-inl.h:8-150 ----
@@ -440,8 +367,10 @@ __global__ void __launch_bounds__(kBsWarps * 32, FCLB_SCENE_MIN_BLOCKS) bvhShape
         const int batch = nleaf < 32 ? nleaf : 32;
         bool hit = false;
         int tri_id = -1;
-        if (lane < batch) {
-          tri_id = leafq[nleaf - 1 - lane];
+        if (lane < batch) tri_id = leafq[nleaf - 1 - lane];
+        if (a.cand.count) {  // candidate mode: the leaf batch decides (ShapeSimplexIntersect with contacts)
+          candAppend<S>(a.cand, lane < batch, uint32_t(q), tri_id, -1, nullptr, nullptr);
+        } else if (lane < batch) {
           V3<S> P[3];
           loadTri(tris, tri_id, P);
           st_leaf++;

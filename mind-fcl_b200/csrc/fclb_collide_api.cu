@@ -59,6 +59,7 @@ static int collideDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const vo
     b.pairs = pairs;
     b.poses1 = poses1;
     b.poses2 = poses2;
+    b.tris = base.tris;
     b.perm = (uniform >= 0) ? nullptr : e.d_perm;
     b.begin = (uniform >= 0) ? 0 : offsets[k];
     b.count = counts[k];
@@ -88,6 +89,10 @@ static int collideDev(Engine& e, ShapeTable* t, const fclb_pair* pairs, const vo
   return FCLB_OK;
 }
 
+static int runCollideTable(Engine& e, ShapeTable* t, const void* tris, const fclb_pair* pairs, const void* poses1,
+                           const void* poses2, size_t n, int scalar_type, const fclb_request* req, int api_mode,
+                           CollideOut out);
+
 static int runCollide(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2, size_t n,
                       int scalar_type, const fclb_request* req, int api_mode, CollideOut out) {
   int rc = ensureInit();
@@ -96,6 +101,31 @@ static int runCollide(fclb_handle shapes, const fclb_pair* pairs, const void* po
   std::lock_guard<std::recursive_mutex> lk(e.mu);
   ShapeTable* t = findTable(e, shapes);
   if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
+  return runCollideTable(e, t, nullptr, pairs, poses1, poses2, n, scalar_type, req, api_mode, out);
+}
+
+// Leaf batch of the scene contact path (fclb_scene_gjk.cu): the reference's leaf routine ShapeIntersect /
+// ShapeSimplexIntersect with contacts == fcl::collide on (leaf geometry, shape) pairs.  d_table: a device ShapeD<S>
+// table that holds the caller's shapes followed by one Box / Triangle entry per leaf; contacts: 4 x 9 S per item.
+int collideLeafBatch(Engine& e, void* d_table, const void* tris, const fclb_pair* pairs, const void* poses1,
+                     const void* poses2, size_t m, int scalar_type, const fclb_request* req, void* contacts,
+                     uint32_t* counts) {
+  ShapeTable tmp;
+  tmp.d_shapes[scalar_type == FCLB_F32 ? 0 : 1] = d_table;
+  fclb_request r = *req;
+  r.max_contacts = 4;  // every contact of the leaf (boxBox2 makes up to four); the scatter pass clips to the free space
+  r.penetration_mode = FCLB_PEN_DEFAULT_GJK_EPA;
+  CollideOut out{};
+  out.contacts = contacts;
+  out.counts = counts;
+  out.max_keep = 4;
+  return runCollideTable(e, &tmp, tris, pairs, poses1, poses2, m, scalar_type, &r, 0, out);
+}
+
+static int runCollideTable(Engine& e, ShapeTable* t, const void* tris, const fclb_pair* pairs, const void* poses1,
+                           const void* poses2, size_t n, int scalar_type, const fclb_request* req, int api_mode,
+                           CollideOut out) {
+  int rc = FCLB_OK;
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
   if (!req) return fail(FCLB_ERR_BAD_ARG, "null request");
   if (n == 0) return FCLB_OK;
@@ -108,6 +138,7 @@ static int runCollide(fclb_handle shapes, const fclb_pair* pairs, const void* po
   CollideLaunchArgs a{};
   a.sp = solverParams(scalar_type, req->binary_tol, req->gjk_max_iter, req->distance_tol, req->epa_max_faces,
                       req->epa_max_iter, true);
+  a.tris = tris;
   a.out = out;
   a.out.max_contacts = req->max_contacts;
   a.out.penetration = (req->penetration_mode == FCLB_PEN_DEFAULT_GJK_EPA) ? 1 : 0;

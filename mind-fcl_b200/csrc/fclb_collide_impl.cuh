@@ -19,6 +19,7 @@
 #include "fclb_internal.h"
 #include "fclb_mpr.cuh"
 #include "fclb_mpr_pen.cuh"
+#include "fclb_sphere_triangle.cuh"
 
 namespace fclb {
 
@@ -173,7 +174,8 @@ enum ClosedCollide : int {
   CC_BOX_SPHERE,
   CC_SPHERE_CYLINDER,
   CC_CYLINDER_SPHERE,
-  CC_BOX_BOX
+  CC_BOX_BOX,
+  CC_SPHERE_TRIANGLE  // leaf batches only: ShapeTransformedTriangleIntersectIndepImpl<S, Sphere<S>> (gjk_solver-inl.h:570-581)
 };
 inline int closedCollideOf(int t1, int t2) {
   if (t1 == ST_SPHERE && t2 == ST_SPHERE) return CC_SPHERE_SPHERE;
@@ -184,6 +186,7 @@ inline int closedCollideOf(int t1, int t2) {
   if (t1 == ST_SPHERE && t2 == ST_CYLINDER) return CC_SPHERE_CYLINDER;
   if (t1 == ST_CYLINDER && t2 == ST_SPHERE) return CC_CYLINDER_SPHERE;
   if (t1 == ST_BOX && t2 == ST_BOX) return CC_BOX_BOX;
+  if (t1 == ST_SPHERE && t2 == ST_TRIANGLE) return CC_SPHERE_TRIANGLE;
   return CC_NONE;
 }
 
@@ -224,6 +227,10 @@ __global__ void __launch_bounds__(kBlock) collideClosedKernel(BatchView b, Colli
     } else if (CC == CC_BOX_BOX) {
       const int code = boxBox2(mk<S>(a.p[0], a.p[1], a.p[2]), tf1, mk<S>(c.p[0], c.p[1], c.p[2]), tf2, cp, &n);
       hit = code != 0;
+    } else if (CC == CC_SPHERE_TRIANGLE) {
+      const S* t = static_cast<const S*>(b.tris) + size_t(12) * size_t(c.geom);
+      hit = sphereTriangleContact(a.p[0], tf1.t, apply(tf2, mk<S>(t[0], t[1], t[2])), apply(tf2, mk<S>(t[4], t[5], t[6])),
+                                  apply(tf2, mk<S>(t[8], t[9], t[10])), cp[0]);
     }
     if (flip && want && hit) cp[0].normal = -cp[0].normal;  // flipNormal (gjk_solver-inl.h:186-197)
     emitContacts<S>(out, q, hit, cp, n);
@@ -318,8 +325,8 @@ __global__ void __launch_bounds__(kBlock) convexBoolKernel(BatchView b, S tol, i
     const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
     const fclb_pair pr = b.pairs[q];
     MinkDiff<S, T0, T1> md;
-    md.s0 = bindShape(shapes, cvx, pr.shape1);
-    md.s1 = bindShape(shapes, cvx, pr.shape2);
+    md.s0 = bindShape(shapes, cvx, pr.shape1, static_cast<const S*>(b.tris));
+    md.s1 = bindShape(shapes, cvx, pr.shape2, static_cast<const S*>(b.tris));
     md.setPoses(loadPose(poses1, q), loadPose(poses2, q));
     int decided = -1;  // -1 undecided, 0 no collision, 1 collision
     if (mode & 1) {
@@ -476,8 +483,8 @@ __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(Ba
       w = defer.consume ? defer.item[it] : it;
       q = work.query[w];
       const fclb_pair pr = b.pairs[q];
-      md.s0 = bindShape(shapes, cvx, pr.shape1);
-      md.s1 = bindShape(shapes, cvx, pr.shape2);
+      md.s0 = bindShape(shapes, cvx, pr.shape1, static_cast<const S*>(b.tris));
+      md.s1 = bindShape(shapes, cvx, pr.shape2, static_cast<const S*>(b.tris));
       tf1 = loadPose(poses1, q);
       md.setPoses(tf1, loadPose(poses2, q));
       // GJK simplex -> slots 0..rank-1
@@ -544,6 +551,7 @@ struct CollideLaunchArgs {
   EpaDefer defer;
   int pen_mode = 0;  // FCLB_PEN_DIRECTED / FCLB_PEN_INCREMENTAL_MIN: run the MPR penetration stage after the boolean
   double pen_dir[3] = {0, 0, 0};
+  const void* tris = nullptr;  // leaf batches: triangle array behind the table's ST_TRIANGLE entries
 };
 
 // implemented in fclb_collide_f32.cu / fclb_collide_f64.cu (MPR penetration stage of one bucket)

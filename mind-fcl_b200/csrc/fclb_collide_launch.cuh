@@ -68,6 +68,9 @@ cudaError_t launchCollide(const BatchView& b, const CollideLaunchArgs& a, cudaSt
         return launchClosedCollide<S, CC_SPHERE_CYLINDER>(b, a, st);
       case CC_CYLINDER_SPHERE:
         return launchClosedCollide<S, CC_CYLINDER_SPHERE>(b, a, st);
+      case CC_SPHERE_TRIANGLE:
+        if (b.tris) return launchClosedCollide<S, CC_SPHERE_TRIANGLE>(b, a, st);
+        break;
       case CC_BOX_BOX: {
         if (getenv("FCLB_BOXBOX_ONE_PHASE")) return launchClosedCollide<S, CC_BOX_BOX>(b, a, st);
         const int grid = gridFor(b.count, kBlock, 12);

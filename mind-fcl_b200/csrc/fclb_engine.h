@@ -88,4 +88,9 @@ template <typename S>
 int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs, size_t n, uint32_t* counts,
                 uint32_t* offsets, int* uniform_kind);
 
+// leaf batch of the scene contact path: see fclb_collide_api.cu
+int collideLeafBatch(Engine& e, void* d_table, const void* tris, const fclb_pair* pairs, const void* poses1,
+                     const void* poses2, size_t m, int scalar_type, const fclb_request* req, void* contacts,
+                     uint32_t* counts);
+
 }  // namespace fclb

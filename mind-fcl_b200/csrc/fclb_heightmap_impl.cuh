@@ -29,6 +29,7 @@
 #include "fclb_boxbox.cuh"
 #include "fclb_gjk.cuh"
 #include "fclb_internal.h"
+#include "fclb_leafcand.cuh"
 #include "fclb_mpr.cuh"
 #include "fclb_primitives_intersect.cuh"
 
@@ -204,9 +205,13 @@ __global__ void __launch_bounds__(kHmWarps * 32, FCLB_HM_MIN_BLOCKS) heightmapSh
           tf_box.R = tf_hm.R;
           tf_box.t = mulMV(tf_hm.R, center) + tf_hm.t;
           st_leaf++;
-          hit = boxShapeHit<S, T1>(side, tf_box, sh, tf_shape, S(a.tol), a.max_iter, st);
+          if (!a.cand.count) hit = boxShapeHit<S, T1>(side, tf_box, sh, tf_shape, S(a.tol), a.max_iter, st);
           hb_min = bmin;
           hb_max = bmax;
+        }
+        if (a.cand.count) {  // candidate mode: the leaf batch decides (ShapeIntersect<Box, Shape> with contacts)
+          const S hb[6] = {hb_min.x, hb_min.y, hb_min.z, hb_max.x, hb_max.y, hb_max.z};
+          candAppend<S>(a.cand, lane < batch, uint32_t(q), (long long)pc, -1, hb, nullptr);
         }
         nq -= batch;
         const unsigned hm = __ballot_sync(0xffffffffu, hit);

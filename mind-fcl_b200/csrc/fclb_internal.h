@@ -18,6 +18,7 @@ constexpr int kBlock = 128;                       // threads per CTA for per-que
 struct BatchView {
   const void* shapes;   // ShapeD<S>[]
   const void* convex;   // ConvexD<S>[]
+  const void* tris;     // device BVH triangle array (12 S per triangle) behind ST_TRIANGLE table entries, or nullptr
   const fclb_pair* pairs;
   const void* poses1;
   const void* poses2;
@@ -48,6 +49,19 @@ template <typename S>
 cudaError_t launchDistance(const BatchView& b, const SolverParams& sp, const DistanceOut& out, cudaStream_t st,
                            int* n_launches);
 
+// Leaf-candidate sink of the scene traversals (DefaultGJK_EPA requests): every leaf / leaf pair that survives the node
+// culls is appended here WITHOUT a leaf test; the leaf batch (fclb_scene_gjk.cu) then runs the reference's leaf routine
+// (ShapeIntersect / ShapeSimplexIntersect with contacts) on each through the shape-pair collide pipeline.
+struct LeafCandSink {
+  unsigned long long* count = nullptr;  // device counter (may exceed cap: the call is then repeated with a larger buffer)
+  unsigned long long cap = 0;
+  uint32_t* q = nullptr;                // query of the candidate
+  long long* b1 = nullptr;              // leaf id on side 1 (triangle id, encodePixel, encodeOctree2Node)
+  long long* b2 = nullptr;              // leaf id on side 2 (scene pairs) or unused
+  void* box1 = nullptr;                 // [cap * 6 S] leaf box of side 1 in its scene frame (heightmap / octree), or nullptr
+  void* box2 = nullptr;                 // [cap * 6 S] leaf box of side 2 (scene pairs with a box hierarchy on side 2)
+};
+
 constexpr int kBvhShapeWarps = 8;  // warps per CTA of the mesh-shape kernel
 // mesh-shape traversal (fclb_bvh_shape_impl.cuh, instantiated in fclb_bvh_shape_f32/f64.cu)
 struct BvhShapeArgs {
@@ -71,6 +85,7 @@ struct BvhShapeArgs {
   void* out_box;       // [n * max_keep * 6 S] leaf box in the scene frame (heightmap / octree), or nullptr
   unsigned long long* work_counter;
   unsigned long long* stats;  // [0] node tests, [1] leaf tests
+  LeafCandSink cand;          // candidate mode (cand.count != nullptr): leaves are appended, not tested
 };
 
 template <typename S>
@@ -103,6 +118,7 @@ struct HeightmapArgs {
   void* out_box;       // [n * max_keep * 6 S] leaf box in the scene frame (heightmap / octree), or nullptr
   unsigned long long* work_counter;
   unsigned long long* stats;  // [0] pixels read, [1] pixel boxes tested
+  LeafCandSink cand;          // candidate mode (cand.count != nullptr): pixel boxes are appended, not tested
 };
 template <typename S>
 cudaError_t launchHeightmapShape(int type1, const HeightmapArgs& a, int grid, cudaStream_t st);
@@ -134,6 +150,7 @@ struct OctreeArgs {
   void* out_box;       // [n * max_keep * 6 S] leaf box in the scene frame (heightmap / octree), or nullptr
   unsigned long long* work_counter;
   unsigned long long* stats;       // [0] node boxes tested, [1] voxel boxes tested
+  LeafCandSink cand;               // candidate mode (cand.count != nullptr): voxel boxes are appended, not tested
 };
 template <typename S>
 cudaError_t launchOctreeShape(int type1, const OctreeArgs& a, int grid, cudaStream_t st);
@@ -201,6 +218,7 @@ struct ScenePairArgs {
   void* out_box2;
   unsigned long long* work_counter;
   unsigned long long* stats;  // [0] node pairs tested, [1] leaf pairs tested, [2] stack overflows
+  LeafCandSink cand;          // candidate mode (cand.count != nullptr): leaf pairs are appended, not tested
 };
 template <typename S>
 cudaError_t launchScenePair(const ScenePairArgs& a, int grid, cudaStream_t st);

@@ -197,7 +197,11 @@ __global__ void __launch_bounds__(kOctWarps * 32) octreeShapeKernel(OctreeArgs a
           tf_box.R = tf_oct.R;
           tf_box.t = mulMV(tf_oct.R, center) + tf_oct.t;
           st_leaf++;
-          hit = boxShapeHit<S, T1>(side, tf_box, sh, tf_shape, S(a.tol), a.max_iter, st);
+          if (!a.cand.count) hit = boxShapeHit<S, T1>(side, tf_box, sh, tf_shape, S(a.tol), a.max_iter, st);
+        }
+        if (a.cand.count) {  // candidate mode: the leaf batch decides (ShapeIntersect<Box, Shape> with contacts)
+          const S hb[6] = {c.mn[0], c.mn[1], c.mn[2], c.mx[0], c.mx[1], c.mx[2]};
+          candAppend<S>(a.cand, lane < batch, uint32_t(q), code, -1, hb, nullptr);
         }
         nq -= batch;
         const unsigned hm = __ballot_sync(0xffffffffu, hit);

@@ -3,8 +3,11 @@
 // Kernels: fclb_bvh_shape_impl.cuh (instantiated in fclb_bvh_shape_f32/f64.cu).
 #include <cmath>
 
+#include <cub/cub.cuh>
+
 #include "fclb_bvh.cuh"
 #include "fclb_octree_build.h"
+#include "fclb_scene_gjk_impl.cuh"
 #include "fclb_shapes.cuh"
 
 namespace fclb {
@@ -16,6 +19,7 @@ struct ContactSink {  // pass 1 of the MPR penetration modes
   uint32_t max_keep = 0;
   long long* b1 = nullptr;
   void* box = nullptr;
+  LeafCandSink cand;  // candidate mode of the DefaultGJK_EPA path (fclb_scene_gjk_impl.cuh)
 };
 
 static int tableUniformType(const ShapeTable* t) {
@@ -52,6 +56,7 @@ static int bvhShapeDev(Engine& e, const BvhDev* m, const ShapeTable* t, const ui
   a.max_keep = sink.max_keep;
   a.out_b1 = sink.b1;
   a.out_box = sink.box;
+  a.cand = sink.cand;
   a.work_counter = g_counters;
   a.stats = g_counters + 1;
   const size_t need = (n + kBvhShapeWarps - 1) / kBvhShapeWarps;
@@ -126,6 +131,7 @@ static int heightmapShapeDev(Engine& e, const HeightmapDev* hm, const ShapeTable
   a.max_keep = sink.max_keep;
   a.out_b1 = sink.b1;
   a.out_box = sink.box;
+  a.cand = sink.cand;
   a.work_counter = g_counters;
   a.stats = g_counters + 1;
   const size_t need = (n + kHeightmapWarps - 1) / kHeightmapWarps;
@@ -195,6 +201,7 @@ static int octreeShapeDev(Engine& e, const OctreeDev* o, const ShapeTable* t, co
   a.max_keep = sink.max_keep;
   a.out_b1 = sink.b1;
   a.out_box = sink.box;
+  a.cand = sink.cand;
   a.work_counter = g_counters;
   a.stats = g_counters + 1;
   const size_t need = (n + kOctreeWarps - 1) / kOctreeWarps;
@@ -318,7 +325,7 @@ template <typename S>
 static int scenePairDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                         const void* poses2, size_t n, const fclb_request* req, uint32_t max_keep, uint32_t* counts,
                         long long* b1, long long* b2, void* box1 = nullptr, void* box2 = nullptr,
-                        const void** tris_out = nullptr) {
+                        const void** tris_out = nullptr, const LeafCandSink* cand = nullptr) {
   const int st = sizeof(S) == 4 ? 0 : 1;
   ScenePairArgs a{};
   a.kind1 = kind1;
@@ -366,6 +373,7 @@ static int scenePairDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fcl
   a.out_b2 = b2;
   a.out_box1 = box1;
   a.out_box2 = box2;
+  if (cand) a.cand = *cand;
   a.work_counter = g_counters;
   a.stats = g_counters + 1;
   const size_t need = (n + kScenePairWarps - 1) / kScenePairWarps;
@@ -439,6 +447,305 @@ static int scenePairContactsDev(Engine& e, int kind1, fclb_handle scene1, int ki
 }
 
 // FlatHeightMap<S>::updateHeightsByPointGenerationFunctor (flat_heightmap-inl.h:249-272)
+// ---- DefaultGJK_EPA requests on scene geometries: candidate traversal + leaf batch (fclb_scene_gjk_impl.cuh) -----
+namespace {
+struct DevBuf {  // scope-bound device allocation
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    return cudaMalloc(&p, bytes ? bytes : 16);
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+}  // namespace
+
+// kind1 / scene1: the scene geometry (scene-shape) or side 1 (scene pair); kind2 < 0: scene-shape with table / shape_ids
+template <typename S>
+static int sceneGjkContactsDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const ShapeTable* t,
+                               const uint32_t* shape_ids, const void* poses_a, const void* poses_b, size_t n,
+                               const fclb_request* req, uint32_t max_keep, uint32_t* counts, long long* out_b1,
+                               long long* out_b2, void* contacts) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  const bool pair = kind2 >= 0;
+  if (max_keep == 0 || !out_b1 || !contacts) return fail(FCLB_ERR_BAD_ARG, "scene contacts: max_keep, id and contact arrays are required");
+  if (pair && !out_b2) return fail(FCLB_ERR_BAD_ARG, "scene pair contacts: out_b2 is required");
+  const void* tris = nullptr;
+  int mode = 0;
+  if (!pair) {
+    mode = kind1 == FCLB_SCENE_BVH ? 0 : 1;
+  } else {
+    mode = kind2 == FCLB_SCENE_BVH ? 3 : 2;
+  }
+  fclb_request all = *req;  // pass 1: every leaf that survives the node culls
+  all.penetration_mode = FCLB_PEN_DISABLED;
+  all.max_contacts = 0x7fffffffu;
+  const size_t ps = 12 * sizeof(S);
+  size_t cap = std::max<size_t>(size_t(1) << 16, std::min<size_t>(n * 32, size_t(1) << 24));
+  const size_t cap_max = size_t(1) << 25;  // candidates per chunk (leaf batch of ~300 B per item)
+  DevBuf d_count, d_cq, d_cb1, d_cb2, d_box1, d_box2, d_scratch;
+  FCLB_CUDA(d_count.alloc(sizeof(unsigned long long)));
+  FCLB_CUDA(d_scratch.alloc(n * sizeof(uint32_t)));
+  auto allocCand = [&](size_t c) -> int {
+    FCLB_CUDA(d_cq.alloc(c * 4));
+    FCLB_CUDA(d_cb1.alloc(c * 8));
+    FCLB_CUDA(d_cb2.alloc(c * 8));
+    FCLB_CUDA(d_box1.alloc(c * 6 * sizeof(S)));
+    FCLB_CUDA(d_box2.alloc(c * 6 * sizeof(S)));
+    return FCLB_OK;
+  };
+  int rc = allocCand(cap);
+  if (rc) return rc;
+  // query chunks: a chunk whose candidates exceed the per-chunk budget is halved and run again
+  std::vector<std::pair<size_t, size_t>> todo{{0, n}};
+  while (!todo.empty()) {
+    const size_t c0 = todo.back().first, c1 = todo.back().second;
+    todo.pop_back();
+    const size_t nc = c1 - c0;
+    unsigned long long m64 = 0;
+    while (true) {
+      FCLB_CUDA(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), e.compute));
+      LeafCandSink cs;
+      cs.count = d_count.as<unsigned long long>();
+      cs.cap = cap;
+      cs.q = d_cq.as<uint32_t>();
+      cs.b1 = d_cb1.as<long long>();
+      cs.b2 = pair ? d_cb2.as<long long>() : nullptr;
+      cs.box1 = mode == 0 ? nullptr : d_box1.p;
+      cs.box2 = mode == 2 ? d_box2.p : nullptr;
+      const char* pa = static_cast<const char*>(poses_a) + c0 * ps;
+      const char* pb = static_cast<const char*>(poses_b) + c0 * ps;
+      if (!pair) {
+        ContactSink sink;
+        sink.cand = cs;
+        if (kind1 == FCLB_SCENE_BVH) {
+          auto it = bvhTable().find(scene1);
+          if (it == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown BVH handle");
+          if (it->second->scalar_type != st) return fail(FCLB_ERR_BAD_ARG, "BVH was uploaded for a different scalar type");
+          tris = it->second->tris;
+          rc = bvhShapeDev<S>(e, it->second, t, shape_ids + c0, pa, pb, nc, &all, d_scratch.as<uint32_t>(), nullptr, sink);
+        } else if (kind1 == FCLB_SCENE_HEIGHTMAP) {
+          auto it = hmTable().find(scene1);
+          if (it == hmTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown heightmap handle");
+          rc = heightmapShapeDev<S>(e, it->second, t, shape_ids + c0, pa, pb, nc, &all, d_scratch.as<uint32_t>(), nullptr, sink);
+        } else if (kind1 == FCLB_SCENE_OCTREE) {
+          auto it = octTable().find(scene1);
+          if (it == octTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown octree handle");
+          rc = octreeShapeDev<S>(e, it->second, t, shape_ids + c0, pa, pb, nc, &all, d_scratch.as<uint32_t>(), nullptr, sink);
+        } else {
+          return fail(FCLB_ERR_BAD_ARG, "unknown scene kind");
+        }
+      } else {
+        rc = scenePairDev<S>(e, kind1, scene1, kind2, scene2, pa, pb, nc, &all, 0, d_scratch.as<uint32_t>(), nullptr, nullptr,
+                             nullptr, nullptr, &tris, &cs);
+      }
+      if (rc) return rc;
+      FCLB_CUDA(cudaMemcpyAsync(&m64, d_count.p, sizeof(m64), cudaMemcpyDeviceToHost, e.compute));
+      FCLB_CUDA(cudaStreamSynchronize(e.compute));
+      if (m64 <= cap) break;
+      if (m64 > cap_max && nc > 1) break;  // split the chunk instead of growing
+      cap = size_t(m64) + size_t(m64) / 8;
+      rc = allocCand(cap);
+      if (rc) return rc;
+    }
+    if (m64 > cap) {  // over budget: halve
+      const size_t mid = c0 + nc / 2;
+      todo.push_back({mid, c1});
+      todo.push_back({c0, mid});
+      continue;
+    }
+    const size_t m = size_t(m64);
+    DevBuf d_qcount, d_qoff, d_itemq, d_ib1, d_ib2, d_flags, d_lc, d_lcnt;
+    FCLB_CUDA(d_qcount.alloc(nc * 4));
+    FCLB_CUDA(d_qoff.alloc(nc * 4));
+    FCLB_CUDA(cudaMemsetAsync(d_qcount.p, 0, nc * 4, e.compute));
+    FCLB_CUDA(cudaMemsetAsync(d_qoff.p, 0, nc * 4, e.compute));
+    if (m > 0) {
+      // (query, b1, b2) order: least significant key first, stable radix passes
+      DevBuf d_ka, d_kb, d_va, d_vb, d_tmp;
+      FCLB_CUDA(d_ka.alloc(m * 8));
+      FCLB_CUDA(d_kb.alloc(m * 8));
+      FCLB_CUDA(d_va.alloc(m * 4));
+      FCLB_CUDA(d_vb.alloc(m * 4));
+      size_t tmp_bytes = 0;
+      FCLB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_ka.as<unsigned long long>(), d_kb.as<unsigned long long>(),
+                                                d_va.as<uint32_t>(), d_vb.as<uint32_t>(), int(m), 0, 64, e.compute));
+      FCLB_CUDA(d_tmp.alloc(tmp_bytes));
+      const int g = int(std::min<size_t>((m + 255) / 256, size_t(e.sms) * 8));
+      iotaKernel<<<g, 256, 0, e.compute>>>(d_va.as<uint32_t>(), m);
+      uint32_t* cur = d_va.as<uint32_t>();
+      uint32_t* nxt = d_vb.as<uint32_t>();
+      auto pass = [&](int which, int bits) -> int {
+        if (which == 2)
+          gatherU32Kernel<<<g, 256, 0, e.compute>>>(d_cq.as<uint32_t>(), cur, m, d_ka.as<unsigned long long>());
+        else
+          gatherI64Kernel<<<g, 256, 0, e.compute>>>(which == 0 ? d_cb2.as<long long>() : d_cb1.as<long long>(), cur, m,
+                                                    d_ka.as<unsigned long long>());
+        FCLB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_ka.as<unsigned long long>(), d_kb.as<unsigned long long>(),
+                                                  cur, nxt, int(m), 0, bits, e.compute));
+        std::swap(cur, nxt);
+        e.launches += 3;
+        return FCLB_OK;
+      };
+      if (pair && (rc = pass(0, 64))) return rc;
+      if ((rc = pass(1, 64))) return rc;
+      if ((rc = pass(2, 32))) return rc;
+      // the leaf batch
+      const uint32_t n_user = pair ? 0u : t->n;
+      DevBuf d_table, d_pairs, d_p1, d_p2;
+      FCLB_CUDA(d_table.alloc((size_t(n_user) + 2 * m) * sizeof(ShapeD<S>)));
+      FCLB_CUDA(d_pairs.alloc(m * sizeof(fclb_pair)));
+      FCLB_CUDA(d_p1.alloc(m * ps));
+      FCLB_CUDA(d_p2.alloc(m * ps));
+      FCLB_CUDA(d_itemq.alloc(m * 4));
+      FCLB_CUDA(d_ib1.alloc(m * 8));
+      FCLB_CUDA(d_ib2.alloc(m * 8));
+      FCLB_CUDA(d_flags.alloc(m));
+      FCLB_CUDA(d_lc.alloc(m * 4 * 9 * sizeof(S)));
+      FCLB_CUDA(d_lcnt.alloc(m * 4));
+      if (n_user)
+        FCLB_CUDA(cudaMemcpyAsync(d_table.p, t->d_shapes[st], size_t(n_user) * sizeof(ShapeD<S>), cudaMemcpyDeviceToDevice,
+                                  e.compute));
+      LeafBuildArgs<S> b{};
+      b.mode = mode;
+      b.octree_pair = pair && kind1 == FCLB_SCENE_OCTREE && kind2 == FCLB_SCENE_OCTREE;
+      b.m = m;
+      b.q_base = c0;
+      b.order = cur;
+      b.cq = d_cq.as<uint32_t>();
+      b.cb1 = d_cb1.as<long long>();
+      b.cb2 = pair ? d_cb2.as<long long>() : nullptr;
+      b.box1 = d_box1.as<S>();
+      b.box2 = d_box2.as<S>();
+      b.shape_ids = shape_ids;
+      b.poses_a = static_cast<const S*>(poses_a);
+      b.poses_b = static_cast<const S*>(poses_b);
+      b.n_user = n_user;
+      b.table = d_table.as<ShapeD<S>>();
+      b.pairs = d_pairs.as<fclb_pair>();
+      b.p1 = d_p1.as<S>();
+      b.p2 = d_p2.as<S>();
+      b.item_q = d_itemq.as<uint32_t>();
+      b.item_b1 = d_ib1.as<long long>();
+      b.item_b2 = d_ib2.as<long long>();
+      b.item_flags = d_flags.as<uint8_t>();
+      b.q_count = d_qcount.as<uint32_t>();
+      leafBatchBuildKernel<S><<<g, 256, 0, e.compute>>>(b);
+      e.launches += 2;
+      FCLB_CUDA(cudaGetLastError());
+      rc = collideLeafBatch(e, d_table.p, tris, d_pairs.as<fclb_pair>(), d_p1.p, d_p2.p, m, st, req, d_lc.p, d_lcnt.as<uint32_t>());
+      if (rc) return rc;
+      size_t scan_bytes = 0;
+      FCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_qcount.as<uint32_t>(), d_qoff.as<uint32_t>(), int(nc), e.compute));
+      DevBuf d_scan;
+      FCLB_CUDA(d_scan.alloc(scan_bytes));
+      FCLB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan.p, scan_bytes, d_qcount.as<uint32_t>(), d_qoff.as<uint32_t>(), int(nc), e.compute));
+      e.launches += 1;
+      FCLB_CUDA(cudaStreamSynchronize(e.compute));  // (d_scan and the sort buffers go out of scope below)
+    }
+    LeafScatterArgs<S> sc{};
+    sc.n_chunk = nc;
+    sc.q_base = c0;
+    sc.q_off = d_qoff.as<uint32_t>();
+    sc.q_count = d_qcount.as<uint32_t>();
+    sc.item_b1 = d_ib1.as<long long>();
+    sc.item_b2 = d_ib2.as<long long>();
+    sc.item_flags = d_flags.as<uint8_t>();
+    sc.leaf_contacts = d_lc.as<S>();
+    sc.leaf_counts = d_lcnt.as<uint32_t>();
+    sc.max_contacts = req->max_contacts;
+    sc.max_keep = max_keep;
+    sc.counts = counts;
+    sc.out_b1 = out_b1;
+    sc.out_b2 = out_b2;
+    sc.out_contacts = static_cast<S*>(contacts);
+    const int gs = int(std::min<size_t>((nc + 127) / 128, size_t(e.sms) * 16));
+    leafBatchScatterKernel<S><<<gs, 128, 0, e.compute>>>(sc);
+    e.launches += 1;
+    FCLB_CUDA(cudaGetLastError());
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  }
+  return FCLB_OK;
+}
+
+// request.penetration_mode != Disabled against a scene geometry: MPR modes -> boolean traversal + per-contact MPR
+// (sceneContactsDev); DefaultGJK_EPA -> candidate traversal + leaf batch (sceneGjkContactsDev)
+static int sceneShapeContactsAny(Engine& e, int kind, fclb_handle scene, const ShapeTable* t, const uint32_t* shape_ids,
+                                 const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
+                                 const fclb_request* req, uint32_t max_keep, uint32_t* counts, long long* b1, void* contacts) {
+  if (req->max_contacts == 0) {
+    FCLB_CUDA(cudaMemsetAsync(counts, 0, n * sizeof(uint32_t), e.compute));
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+    return FCLB_OK;
+  }
+  if (req->penetration_mode == FCLB_PEN_DEFAULT_GJK_EPA) {
+    if (scalar_type == FCLB_F32)
+      return sceneGjkContactsDev<float>(e, kind, scene, -1, 0, t, shape_ids, poses_scene, poses_shape, n, req, max_keep, counts, b1,
+                                        nullptr, contacts);
+    return sceneGjkContactsDev<double>(e, kind, scene, -1, 0, t, shape_ids, poses_scene, poses_shape, n, req, max_keep, counts, b1,
+                                       nullptr, contacts);
+  }
+  if (scalar_type == FCLB_F32)
+    return sceneContactsDev<float>(e, kind, scene, t, shape_ids, poses_scene, poses_shape, n, req, max_keep, counts, b1, contacts);
+  return sceneContactsDev<double>(e, kind, scene, t, shape_ids, poses_scene, poses_shape, n, req, max_keep, counts, b1, contacts);
+}
+
+static int scenePairContactsAny(Engine& e, int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                const void* poses2, size_t n, int scalar_type, const fclb_request* req, uint32_t max_keep,
+                                uint32_t* counts, long long* b1, long long* b2, void* contacts) {
+  if (req->max_contacts == 0) {
+    FCLB_CUDA(cudaMemsetAsync(counts, 0, n * sizeof(uint32_t), e.compute));
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+    return FCLB_OK;
+  }
+  if (req->penetration_mode == FCLB_PEN_DEFAULT_GJK_EPA) {
+    if (kind1 == FCLB_SCENE_OCTREE && kind2 == FCLB_SCENE_HEIGHTMAP)
+      return fail(FCLB_ERR_UNSUPPORTED, "scene pair: pass the heightmap first (heightMapOctreeIntersect)");
+    if (scalar_type == FCLB_F32)
+      return sceneGjkContactsDev<float>(e, kind1, scene1, kind2, scene2, nullptr, nullptr, poses1, poses2, n, req, max_keep, counts,
+                                        b1, b2, contacts);
+    return sceneGjkContactsDev<double>(e, kind1, scene1, kind2, scene2, nullptr, nullptr, poses1, poses2, n, req, max_keep, counts,
+                                       b1, b2, contacts);
+  }
+  if (scalar_type == FCLB_F32)
+    return scenePairContactsDev<float>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, req, max_keep, counts, b1, b2, contacts);
+  return scenePairContactsDev<double>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, req, max_keep, counts, b1, b2, contacts);
+}
+
+__global__ void narrowFirstIdKernel(const long long* __restrict__ b1, const uint32_t* __restrict__ counts, size_t n, int32_t* out32,
+                                    long long* out64) {
+  for (size_t q = blockIdx.x * size_t(blockDim.x) + threadIdx.x; q < n; q += size_t(gridDim.x) * blockDim.x) {
+    const long long v = counts[q] ? b1[q] : -1;
+    if (out32) out32[q] = int32_t(v);
+    if (out64) out64[q] = v;
+  }
+}
+
+// the boolean / counting entry points with a penetration request: the contact path with one kept contact per query
+static int sceneShapeCountsViaContacts(Engine& e, int kind, fclb_handle scene, const ShapeTable* t, const uint32_t* shape_ids,
+                                       const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
+                                       const fclb_request* req, uint32_t* counts, int32_t* first32, long long* first64) {
+  DevBuf tb1, tc;
+  FCLB_CUDA(tb1.alloc(n * 8));
+  FCLB_CUDA(tc.alloc(n * 7 * 8));
+  const int rc = sceneShapeContactsAny(e, kind, scene, t, shape_ids, poses_scene, poses_shape, n, scalar_type, req, 1, counts,
+                                       tb1.as<long long>(), tc.p);
+  if (rc) return rc;
+  if (first32 || first64) {
+    const int g = int(std::min<size_t>((n + 255) / 256, size_t(e.sms) * 8));
+    narrowFirstIdKernel<<<g, 256, 0, e.compute>>>(tb1.as<long long>(), counts, n, first32, first64);
+    e.launches += 1;
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  }
+  return FCLB_OK;
+}
+
 template <typename S>
 static void heightsFromPoints(const double* pts, size_t n, S res_x, S res_y, uint32_t half_x, uint32_t half_y,
                               uint16_t* heights) {
@@ -589,10 +896,11 @@ int fclb_bvh_shape_collide_batch_dev(fclb_handle bvh, fclb_handle shapes, const 
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
   if (it->second->scalar_type != scalar_type) return fail(FCLB_ERR_BAD_ARG, "BVH was uploaded for a different scalar type");
   if (!req || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null request / out_counts");
-  if (req->penetration_mode != FCLB_PEN_DISABLED)
-    return fail(FCLB_ERR_UNSUPPORTED, "mesh-shape contact generation (penetration modes) is not on the device yet");
   if (n == 0) return FCLB_OK;
   if (!shape_ids || !poses_mesh || !poses_shape) return fail(FCLB_ERR_BAD_ARG, "null input array");
+  if (req->penetration_mode != FCLB_PEN_DISABLED)  // contacts are generated (and dropped): numContacts is the contact path's
+    return sceneShapeCountsViaContacts(e, FCLB_SCENE_BVH, bvh, t, shape_ids, poses_mesh, poses_shape, n, scalar_type, req,
+                                       out_counts, out_first_tri, nullptr);
   if (scalar_type == FCLB_F32)
     return bvhShapeDev<float>(e, it->second, t, shape_ids, poses_mesh, poses_shape, n, req, out_counts, out_first_tri);
   return bvhShapeDev<double>(e, it->second, t, shape_ids, poses_mesh, poses_shape, n, req, out_counts, out_first_tri);
@@ -790,10 +1098,11 @@ int fclb_heightmap_shape_collide_batch_dev(fclb_handle hm, fclb_handle shapes, c
   if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
   if (!req || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null request / out_counts");
-  if (req->penetration_mode != FCLB_PEN_DISABLED)
-    return fail(FCLB_ERR_UNSUPPORTED, "heightmap-shape contact generation (penetration modes) is not on the device yet");
   if (n == 0) return FCLB_OK;
   if (!shape_ids || !poses_hm || !poses_shape) return fail(FCLB_ERR_BAD_ARG, "null input array");
+  if (req->penetration_mode != FCLB_PEN_DISABLED)
+    return sceneShapeCountsViaContacts(e, FCLB_SCENE_HEIGHTMAP, hm, t, shape_ids, poses_hm, poses_shape, n, scalar_type, req,
+                                       out_counts, out_first_pixel, nullptr);
   if (scalar_type == FCLB_F32)
     return heightmapShapeDev<float>(e, it->second, t, shape_ids, poses_hm, poses_shape, n, req, out_counts,
                                     out_first_pixel);
@@ -1031,8 +1340,6 @@ int fclb_octree_shape_collide_batch_dev(fclb_handle octree, fclb_handle shapes, 
   if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
   if (!req || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null request / out_counts");
-  if (req->penetration_mode != FCLB_PEN_DISABLED)
-    return fail(FCLB_ERR_UNSUPPORTED, "octree-shape contact generation (penetration modes) is not on the device yet");
   if (n == 0) return FCLB_OK;
   if (!shape_ids || !poses_octree || !poses_shape) return fail(FCLB_ERR_BAD_ARG, "null input array");
   for (uint32_t i = 0; i < t->n; i++)
@@ -1042,6 +1349,9 @@ int fclb_octree_shape_collide_batch_dev(fclb_handle octree, fclb_handle shapes, 
         return fail(FCLB_ERR_UNSUPPORTED, "octree-shape: Convex with 1, 2, 3 or 6 vertices uses the special OBB fitters "
                                           "(math/bv/utility-inl.h:63-131), which are not on the device");
     }
+  if (req->penetration_mode != FCLB_PEN_DISABLED)
+    return sceneShapeCountsViaContacts(e, FCLB_SCENE_OCTREE, octree, t, shape_ids, poses_octree, poses_shape, n, scalar_type, req,
+                                       out_counts, nullptr, reinterpret_cast<long long*>(out_first_node));
   if (scalar_type == FCLB_F32)
     return octreeShapeDev<float>(e, it->second, t, shape_ids, poses_octree, poses_shape, n, req, out_counts,
                                  reinterpret_cast<long long*>(out_first_node));
@@ -1100,16 +1410,12 @@ int fclb_scene_shape_contacts_batch_dev(int scene_kind, fclb_handle scene, fclb_
   if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
   if (!req || !out_counts || !out_b1 || !out_contacts || max_keep == 0) return fail(FCLB_ERR_BAD_ARG, "null output / max_keep == 0");
-  if (req->penetration_mode != FCLB_PEN_DIRECTED && req->penetration_mode != FCLB_PEN_INCREMENTAL_MIN)
-    return fail(FCLB_ERR_UNSUPPORTED, "fclb_scene_shape_contacts_batch serves the MPR penetration modes "
-                                      "(FCLB_PEN_DIRECTED, FCLB_PEN_INCREMENTAL_MIN)");
+  if (req->penetration_mode == FCLB_PEN_DISABLED || req->penetration_mode > FCLB_PEN_INCREMENTAL_MIN)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_scene_shape_contacts_batch: the request must enable a penetration mode");
   if (n == 0) return FCLB_OK;
   if (!shape_ids || !poses_scene || !poses_shape) return fail(FCLB_ERR_BAD_ARG, "null input array");
-  if (scalar_type == FCLB_F32)
-    return sceneContactsDev<float>(e, scene_kind, scene, t, shape_ids, poses_scene, poses_shape, n, req, max_keep, out_counts,
-                                   reinterpret_cast<long long*>(out_b1), out_contacts);
-  return sceneContactsDev<double>(e, scene_kind, scene, t, shape_ids, poses_scene, poses_shape, n, req, max_keep, out_counts,
-                                  reinterpret_cast<long long*>(out_b1), out_contacts);
+  return sceneShapeContactsAny(e, scene_kind, scene, t, shape_ids, poses_scene, poses_shape, n, scalar_type, req, max_keep,
+                               out_counts, reinterpret_cast<long long*>(out_b1), out_contacts);
 }
 
 int fclb_scene_shape_contacts_batch_host(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
@@ -1168,10 +1474,18 @@ int fclb_scene_pair_collide_batch_dev(int kind1, fclb_handle scene1, int kind2, 
   if (!req || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null request / out_counts");
   if ((out_b1 == nullptr) != (out_b2 == nullptr) || (out_b1 && max_keep == 0))
     return fail(FCLB_ERR_BAD_ARG, "out_b1 / out_b2 go together and need max_keep > 0");
-  if (req->penetration_mode != FCLB_PEN_DISABLED)
-    return fail(FCLB_ERR_UNSUPPORTED, "scene-pair contact generation (penetration modes) is not on the device yet");
   if (n == 0) return FCLB_OK;
   if (!poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null pose array");
+  if (req->penetration_mode != FCLB_PEN_DISABLED) {  // contacts are generated (and dropped): counts / ids of the contact path
+    const uint32_t keep = out_b1 ? max_keep : 1;
+    DevBuf tb1, tb2, tc;
+    FCLB_CUDA(tb1.alloc(n * size_t(keep) * 8));
+    FCLB_CUDA(tb2.alloc(n * size_t(keep) * 8));
+    FCLB_CUDA(tc.alloc(n * size_t(keep) * 7 * 8));
+    return scenePairContactsAny(e, kind1, scene1, kind2, scene2, poses1, poses2, n, scalar_type, req, keep, out_counts,
+                                out_b1 ? reinterpret_cast<long long*>(out_b1) : tb1.as<long long>(),
+                                out_b2 ? reinterpret_cast<long long*>(out_b2) : tb2.as<long long>(), tc.p);
+  }
   if (scalar_type == FCLB_F32)
     return scenePairDev<float>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, req, max_keep, out_counts,
                                reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2));
@@ -1228,18 +1542,12 @@ int fclb_scene_pair_contacts_batch_dev(int kind1, fclb_handle scene1, int kind2,
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
   if (!req || !out_counts || !out_b1 || !out_b2 || !out_contacts || max_keep == 0)
     return fail(FCLB_ERR_BAD_ARG, "null output / max_keep == 0");
-  if (req->penetration_mode != FCLB_PEN_DIRECTED && req->penetration_mode != FCLB_PEN_INCREMENTAL_MIN)
-    return fail(FCLB_ERR_UNSUPPORTED, "fclb_scene_pair_contacts_batch serves the MPR penetration modes "
-                                      "(FCLB_PEN_DIRECTED, FCLB_PEN_INCREMENTAL_MIN)");
+  if (req->penetration_mode == FCLB_PEN_DISABLED || req->penetration_mode > FCLB_PEN_INCREMENTAL_MIN)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_scene_pair_contacts_batch: the request must enable a penetration mode");
   if (n == 0) return FCLB_OK;
   if (!poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null pose array");
-  if (scalar_type == FCLB_F32)
-    return scenePairContactsDev<float>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, req, max_keep, out_counts,
-                                       reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2),
-                                       out_contacts);
-  return scenePairContactsDev<double>(e, kind1, scene1, kind2, scene2, poses1, poses2, n, req, max_keep, out_counts,
-                                      reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2),
-                                      out_contacts);
+  return scenePairContactsAny(e, kind1, scene1, kind2, scene2, poses1, poses2, n, scalar_type, req, max_keep, out_counts,
+                              reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2), out_contacts);
 }
 
 int fclb_scene_pair_contacts_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,

@@ -32,6 +32,7 @@
 // follows the device traversal (declared).
 #pragma once
 #include "fclb_bvh_shape_impl.cuh"  // boxTriangleOverlap
+#include "fclb_leafcand.cuh"
 #include "fclb_octree_impl.cuh"     // FixedRot, makeFixedRot, rowDotAssoc, childAabb
 
 namespace fclb {
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
             V3<S> P[3];
             loadTri(tris, el.b, P);
             const V3<S> h = mk<S>(S(0.5) * side.x, S(0.5) * side.y, S(0.5) * side.z);
-            hit = boxTriangleOverlap(h, apply(toshape0, P[0]), apply(toshape0, P[1]), apply(toshape0, P[2]));
+            if (!a.cand.count) hit = boxTriangleOverlap(h, apply(toshape0, P[0]), apply(toshape0, P[1]), apply(toshape0, P[2]));
           } else {
             // heightMapOctreeIntersect names the octree side by its bare node_vector_index
             // (heightmap_solver_traverse-inl.h:489-512), the octree solvers by encodeOctree2Node
@@ -371,8 +372,23 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
               c2 = (long long)el.b.index;
             else
               c2 = SB::type::code(el.b);
-            hit = !fixedRotDisjointBoxes(fr, el.a.mn, el.a.mx, el.b.mn, el.b.mx, true);
+            if (!a.cand.count) hit = !fixedRotDisjointBoxes(fr, el.a.mn, el.a.mx, el.b.mn, el.b.mx, true);
           }
+        }
+        if (a.cand.count) {  // candidate mode: the leaf batch decides (boxBox2 / box-triangle GJK + EPA with contacts)
+          S hb1[6], hb2[6];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            hb1[k] = el.a.mn[k];
+            hb1[3 + k] = el.a.mx[k];
+            if constexpr (!MESH) {
+              hb2[k] = el.b.mn[k];
+              hb2[3 + k] = el.b.mx[k];
+            } else {
+              hb2[k] = hb2[3 + k] = S(0);
+            }
+          }
+          candAppend<S>(a.cand, lane < batch, uint32_t(q), c1, c2, hb1, MESH ? nullptr : hb2);
         }
         nq -= batch;
         const unsigned hm = __ballot_sync(0xffffffffu, hit);

@@ -209,8 +209,11 @@ FCLB_DI V3<S> interiorOf(const ShapeInst<S>& s) {
   return zero3<S>();
 }
 
+// tris: the device BVH triangle array (12 S per triangle: 3 x {x, y, z, pad}) behind ST_TRIANGLE entries of a leaf-batch
+// table (geom = triangle id), or nullptr when the table holds no triangles.
 template <typename S>
-FCLB_DI ShapeInst<S> bindShape(const ShapeD<S>* __restrict__ tab, const ConvexD<S>* __restrict__ cvx, uint32_t idx) {
+FCLB_DI ShapeInst<S> bindShape(const ShapeD<S>* __restrict__ tab, const ConvexD<S>* __restrict__ cvx, uint32_t idx,
+                               const S* __restrict__ tris = nullptr) {
   ShapeInst<S> s;
   const ShapeD<S> r = tab[idx];
   s.type = r.type;
@@ -218,6 +221,11 @@ FCLB_DI ShapeInst<S> bindShape(const ShapeD<S>* __restrict__ tab, const ConvexD<
   s.p1 = r.p[1];
   s.p2 = r.p[2];
   s.cvx = (r.type == ST_CONVEX) ? (cvx + r.geom) : nullptr;
+  if (r.type == ST_TRIANGLE && tris) {
+    const S* t = tris + size_t(12) * size_t(r.geom);
+#pragma unroll
+    for (int v = 0; v < 3; v++) s.tri[v] = mk<S>(t[4 * v], t[4 * v + 1], t[4 * v + 2]);
+  }
   return s;
 }
 
