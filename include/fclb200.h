@@ -92,6 +92,15 @@ typedef uint64_t fclb_handle;
 /* ---- engine ------------------------------------------------------------ */
 int fclb_init(int device);             /* bind the calling process to one GPU (one process per GPU) */
 int fclb_device_count(void);           /* 0 when no CUDA device is visible */
+/* One process, several GPUs (SURVEY.md 8b "fclb_init(int n_devices)", 8e): one engine -- streams, scratch, a replica
+ * of every geometry uploaded afterwards -- per device (n_devices <= 0: every visible device).  Every *_host batch entry
+ * point then shards its batch by contiguous query range over the devices, one host thread per device, each device
+ * writing its slice of the caller's (pinned) output arrays; there is no collective.  *_dev entry points, the
+ * broadphase trees and fclb_scene_self_collide_* act on the calling thread's current device (fclb_set_device).
+ * Call before the first upload. */
+int fclb_init_devices(int n_devices);
+int fclb_num_devices(void);            /* engines created so far */
+int fclb_set_device(int slot);         /* thread-local: the engine later calls of this thread use */
 const char* fclb_last_error(void);     /* thread-local message for the last non-zero return */
 const char* fclb_version(void);
 

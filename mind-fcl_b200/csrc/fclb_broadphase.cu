@@ -59,8 +59,8 @@ struct BpTree {
   std::unordered_map<uint64_t, int> pos_of;  // user id -> Morton position (host)
 };
 static std::map<fclb_handle, BpTree*>& bpTable() {
-  static std::map<fclb_handle, BpTree*> t;
-  return t;
+  static std::map<fclb_handle, BpTree*> t[kMaxDevices];
+  return t[currentSlot()];
 }
 
 __device__ __forceinline__ double atomicMinD(double* addr, double v) {
@@ -398,8 +398,15 @@ static void freeTree(BpTree* t) {
   delete t;
 }
 
-static unsigned long long* g_bp_counters = nullptr;  // [0] pair count, [1] visits
-static uint64_t g_bp_last_visits = 0;
+struct BpCounters {
+  unsigned long long* counters = nullptr;  // device: [0] pair count, [1] visits
+  uint64_t last_visits = 0;
+  void* d_in = nullptr;  // staging of fclb_scene_self_collide_host
+  size_t d_in_cap = 0;
+};
+static PerDevice<BpCounters> g_bp_pd;
+#define g_bp_counters (g_bp_pd.get().counters)
+#define g_bp_last_visits (g_bp_pd.get().last_visits)
 
 template <typename S>
 static int refit(Engine& e, BpTree* t) {
@@ -422,7 +429,8 @@ struct BpScratch {
   void* tmp = nullptr;
   size_t cap_n = 0, cap_tmp = 0;
 };
-static BpScratch g_bp_scratch;
+static PerDevice<BpScratch> g_bp_scratch_pd;
+#define g_bp_scratch (g_bp_scratch_pd.get())
 
 // boxes / ids: DEVICE pointers.  A tree whose arrays already hold `cap` >= n objects is rebuilt in place.
 template <typename S>
@@ -555,7 +563,8 @@ struct SceneWs {
   size_t cap_pairs = 0, pair_scalar = 0;
   unsigned long long* hits = nullptr;
 };
-static SceneWs g_scene;
+static PerDevice<SceneWs> g_scene_ws_pd;
+#define g_scene (g_scene_ws_pd.get())
 
 template <typename S>
 static int sceneSelfCollide(Engine& e, fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n,
@@ -649,7 +658,7 @@ int fclb_broadphase_build_dev(const void* aabbs, const uint64_t* user_ids, size_
     freeTree(t);
     return rc;
   }
-  const fclb_handle h = e.next_handle++;
+  const fclb_handle h = newHandle();
   bpTable()[h] = t;
   *tree = h;
   return FCLB_OK;
@@ -678,7 +687,7 @@ int fclb_broadphase_build_host(const void* aabbs, const uint64_t* user_ids, size
     freeTree(t);
     return rc;
   }
-  const fclb_handle h = e.next_handle++;
+  const fclb_handle h = newHandle();
   bpTable()[h] = t;
   *tree = h;
   return FCLB_OK;
@@ -885,8 +894,8 @@ int fclb_scene_self_collide_host(fclb_handle shapes, const uint32_t* shape_ids, 
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
   const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
-  static void* d_in = nullptr;
-  static size_t d_in_cap = 0;
+  void*& d_in = g_bp_pd.get().d_in;
+  size_t& d_in_cap = g_bp_pd.get().d_in_cap;
   const size_t o_p = alignUp(n * 4, 256), total = o_p + n * 12 * ss;
   if (d_in_cap < total) {
     cudaFree(d_in);
@@ -929,7 +938,7 @@ int fclb_compute_aabb_batch_dev(fclb_handle shapes, const uint32_t* shape_ids, c
   return FCLB_OK;
 }
 
-int fclb_compute_aabb_batch_host(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n, int scalar_type,
+static int compute_aabb_batch_host_one(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n, int scalar_type,
                                  void* out_aabbs) {
   int rc = ensureInit();
   if (rc) return rc;
@@ -950,6 +959,13 @@ int fclb_compute_aabb_batch_host(fclb_handle shapes, const uint32_t* shape_ids, 
   if (rc) return rc;
   FCLB_CUDA(cudaMemcpy(out_aabbs, base + o_out, n * 6 * ss, cudaMemcpyDeviceToHost));
   return FCLB_OK;
+}
+int fclb_compute_aabb_batch_host(fclb_handle shapes, const uint32_t* shape_ids, const void* poses, size_t n, int scalar_type,
+                                 void* out_aabbs) {
+  if (engineCount() <= 1) return compute_aabb_batch_host_one(shapes, shape_ids, poses, n, scalar_type, out_aabbs);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return compute_aabb_batch_host_one(shapes, offT(shape_ids, b), offPtr(poses, b * 12 * ss), m_, scalar_type, offPtr(out_aabbs, b * 6 * ss)); });
 }
 
 /* candidate (object id, object id) pairs -> the per-query arrays of fclb_collide_batch_dev. DEVICE pointers. */

@@ -35,8 +35,8 @@
 namespace fclb {
 
 std::map<fclb_handle, BvhDev*>& bvhTable() {
-  static std::map<fclb_handle, BvhDev*> t;
-  return t;
+  static std::map<fclb_handle, BvhDev*> t[kMaxDevices];
+  return t[currentSlot()];
 }
 
 // project6 (intersect-inl.h:1082-1105); std::min(a,b) = (b<a)?b:a, std::max(a,b) = (a<b)?b:a
@@ -327,6 +327,14 @@ __global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
             }
             count += uint32_t(total);
           } else {
+            if (hit && a.out_ids) {  // boolean request with more than one contact wanted: the ids of every kept pair
+              const uint32_t slot = count + uint32_t(__popc(hm & ((1u << lane) - 1u)));
+              if (slot < a.max_keep && slot < a.max_contacts) {
+                const size_t r = q * a.max_keep + slot;
+                a.out_ids[2 * r] = lp.x;
+                a.out_ids[2 * r + 1] = lp.y;
+              }
+            }
             count += uint32_t(__popc(hm));
           }
           if (count >= a.max_contacts) {
@@ -359,8 +367,14 @@ __global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
   }
 }
 
-static unsigned long long* g_bvh_counters = nullptr;  // [0] work counter, [1..2] stats
-static unsigned long long g_last_stats[2] = {0, 0};
+struct BvhStats {
+  unsigned long long* counters = nullptr;  // device: [0] work counter, [1..2] stats
+  unsigned long long last[2] = {0, 0};
+  unsigned long long host[3] = {0, 0, 0};
+};
+static PerDevice<BvhStats> g_bvh_pd;
+#define g_bvh_counters (g_bvh_pd.get().counters)
+#define g_last_stats (g_bvh_pd.get().last)
 
 template <typename S>
 static int bvhCollideDev(Engine& e, const BvhDev* m1, const BvhDev* m2, const void* poses1, const void* poses2, size_t n,
@@ -400,7 +414,7 @@ static int bvhCollideDev(Engine& e, const BvhDev* m1, const BvhDev* m2, const vo
   FCLB_CUDA(cudaGetLastError());
   FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
   e.launches += 1;
-  static unsigned long long h_stats[3];
+  unsigned long long* h_stats = g_bvh_pd.get().host;
   FCLB_CUDA(cudaMemcpyAsync(h_stats, g_bvh_counters + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
@@ -454,7 +468,7 @@ using namespace fclb;
 
 extern "C" {
 
-int fclb_bvh_upload(const void* obb, const int32_t* first_child, int n_nodes, const void* tri_verts, int n_tris,
+static int bvh_upload_one(const void* obb, const int32_t* first_child, int n_nodes, const void* tri_verts, int n_tris,
                     int scalar_type, fclb_handle* h) {
   int rc = ensureInit();
   if (rc) return rc;
@@ -478,13 +492,22 @@ int fclb_bvh_upload(const void* obb, const int32_t* first_child, int n_nodes, co
     delete d;
     return rc;
   }
-  const fclb_handle hd = e.next_handle++;
+  const fclb_handle hd = newHandle();
   bvhTable()[hd] = d;
   *h = hd;
   return FCLB_OK;
 }
+int fclb_bvh_upload(const void* obb, const int32_t* first_child, int n_nodes, const void* tri_verts, int n_tris,
+                    int scalar_type, fclb_handle* h) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return bvh_upload_one(obb, first_child, n_nodes, tri_verts, n_tris, scalar_type, h); });
+}
 
+// the tree is built once on the host (mirror of BVHModel::endModel) and uploaded to every device
 int fclb_bvh_build(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type, fclb_handle* h) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
   if (!verts || !tris || !h || n_verts <= 0 || n_tris <= 0) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build: null or empty input");
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
   for (size_t i = 0; i < size_t(3) * n_tris; i++)
@@ -492,11 +515,15 @@ int fclb_bvh_build(const double* verts, int n_verts, const int32_t* tris, int n_
   if (scalar_type == FCLB_F32) {
     hostbuild::TreeOut<float> t;
     hostbuild::buildObbTree<float>(verts, n_verts, tris, n_tris, t);
-    return fclb_bvh_upload(t.obb.data(), t.first_child.data(), int(t.first_child.size()), t.tri.data(), n_tris, scalar_type, h);
+    return forEachDevice([&] {
+      return bvh_upload_one(t.obb.data(), t.first_child.data(), int(t.first_child.size()), t.tri.data(), n_tris, scalar_type, h);
+    });
   }
   hostbuild::TreeOut<double> t;
   hostbuild::buildObbTree<double>(verts, n_verts, tris, n_tris, t);
-  return fclb_bvh_upload(t.obb.data(), t.first_child.data(), int(t.first_child.size()), t.tri.data(), n_tris, scalar_type, h);
+  return forEachDevice([&] {
+    return bvh_upload_one(t.obb.data(), t.first_child.data(), int(t.first_child.size()), t.tri.data(), n_tris, scalar_type, h);
+  });
 }
 
 int fclb_bvh_build_host(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type, void* obb,
@@ -546,7 +573,7 @@ int fclb_bvh_export(fclb_handle h, void* obb, int32_t* first_child, void* tri_ve
   return FCLB_OK;
 }
 
-int fclb_bvh_release(fclb_handle h) {
+static int bvh_release_one(fclb_handle h) {
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
   auto it = bvhTable().find(h);
@@ -556,6 +583,11 @@ int fclb_bvh_release(fclb_handle h) {
   delete it->second;
   bvhTable().erase(it);
   return FCLB_OK;
+}
+int fclb_bvh_release(fclb_handle h) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return bvh_release_one(h); });
 }
 
 int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
@@ -581,7 +613,7 @@ int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* p
                                out_first_pair);
 }
 
-int fclb_bvh_collide_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+static int bvh_collide_batch_host_one(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
                                 int scalar_type, const fclb_request* req, uint32_t* out_counts,
                                 int32_t* out_first_pair) {
   int rc = ensureInit();
@@ -637,6 +669,14 @@ int fclb_bvh_collide_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* 
   FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
   return FCLB_OK;
 }
+int fclb_bvh_collide_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+                                int scalar_type, const fclb_request* req, uint32_t* out_counts,
+                                int32_t* out_first_pair) {
+  if (engineCount() <= 1) return bvh_collide_batch_host_one(bvh1, bvh2, poses1, poses2, n, scalar_type, req, out_counts, out_first_pair);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return bvh_collide_batch_host_one(bvh1, bvh2, offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, req, offT(out_counts, b), offT(out_first_pair, 2 * b)); });
+}
 
 int fclb_bvh_collide_contacts_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
                                         int scalar_type, const fclb_request* req, uint32_t max_keep, uint32_t* out_counts,
@@ -650,18 +690,20 @@ int fclb_bvh_collide_contacts_batch_dev(fclb_handle bvh1, fclb_handle bvh2, cons
   if (i1->second->scalar_type != scalar_type || i2->second->scalar_type != scalar_type)
     return fail(FCLB_ERR_BAD_ARG, "BVH was uploaded for a different scalar type");
   if (!req || !out_counts || !out_ids || !out_contacts || max_keep == 0) return fail(FCLB_ERR_BAD_ARG, "null output / max_keep == 0");
-  if (req->penetration_mode != FCLB_PEN_DEFAULT_GJK_EPA)
-    return fail(FCLB_ERR_UNSUPPORTED, "fclb_bvh_collide_contacts_batch serves request.useDefaultPenetration()");
+  if (req->penetration_mode != FCLB_PEN_DEFAULT_GJK_EPA && req->penetration_mode != FCLB_PEN_DISABLED)
+    return fail(FCLB_ERR_UNSUPPORTED, "fclb_bvh_collide_contacts_batch serves boolean requests (ids only) and "
+                                      "request.useDefaultPenetration(); the MPR penetration modes are not built for mesh pairs");
   if (n == 0) return FCLB_OK;
   if (!poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null pose array");
+  const bool pen = req->penetration_mode == FCLB_PEN_DEFAULT_GJK_EPA;
   if (scalar_type == FCLB_F32)
-    return bvhCollideDev<float>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts, nullptr, true,
+    return bvhCollideDev<float>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts, nullptr, pen,
                                 max_keep, out_ids, out_contacts);
-  return bvhCollideDev<double>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts, nullptr, true,
+  return bvhCollideDev<double>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts, nullptr, pen,
                                max_keep, out_ids, out_contacts);
 }
 
-int fclb_bvh_collide_contacts_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+static int bvh_collide_contacts_batch_host_one(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
                                          int scalar_type, const fclb_request* req, uint32_t max_keep, uint32_t* out_counts,
                                          int32_t* out_ids, void* out_contacts) {
   int rc = ensureInit();
@@ -694,6 +736,14 @@ int fclb_bvh_collide_contacts_batch_host(fclb_handle bvh1, fclb_handle bvh2, con
   FCLB_CUDA(cudaMemcpyAsync(out_contacts, base + o_ct, n * size_t(max_keep) * 7 * ss, cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
+}
+int fclb_bvh_collide_contacts_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
+                                         int scalar_type, const fclb_request* req, uint32_t max_keep, uint32_t* out_counts,
+                                         int32_t* out_ids, void* out_contacts) {
+  if (engineCount() <= 1) return bvh_collide_contacts_batch_host_one(bvh1, bvh2, poses1, poses2, n, scalar_type, req, max_keep, out_counts, out_ids, out_contacts);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return bvh_collide_contacts_batch_host_one(bvh1, bvh2, offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, req, max_keep, offT(out_counts, b), offT(out_ids, b * size_t(max_keep) * 2), offPtr(out_contacts, b * size_t(max_keep) * 7 * ss)); });
 }
 
 int fclb_bvh_last_visit_counts(uint64_t* n_bv, uint64_t* n_leaf) {

@@ -15,7 +15,8 @@ struct CollideWorkspace {
   size_t cap = 0;      // queries
   size_t scalar = 0;   // bytes per scalar the simplex buffer was sized for
 };
-static CollideWorkspace g_ws;
+static PerDevice<CollideWorkspace> g_ws_pd;
+#define g_ws (g_ws_pd.get())
 
 static int ensureWorkspace(size_t n, size_t ss) {
   if (n <= g_ws.cap && ss <= g_ws.scalar) return FCLB_OK;
@@ -232,12 +233,20 @@ int fclb_collide_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const voi
   return runCollide(shapes, pairs, poses1, poses2, n, scalar_type, req, 0, out);
 }
 
-int fclb_collide_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+static int collide_batch_host_one(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
                             size_t n, int scalar_type, const fclb_request* req, uint32_t max_keep, void* out_contacts,
                             uint32_t* out_counts) {
   if (!out_counts) return fail(FCLB_ERR_BAD_ARG, "fclb_collide_batch: out_counts is required");
   return runCollideHost(shapes, pairs, poses1, poses2, n, scalar_type, req, 0, max_keep, out_contacts, out_counts,
                         nullptr, nullptr, nullptr);
+}
+int fclb_collide_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                            size_t n, int scalar_type, const fclb_request* req, uint32_t max_keep, void* out_contacts,
+                            uint32_t* out_counts) {
+  if (engineCount() <= 1) return collide_batch_host_one(shapes, pairs, poses1, poses2, n, scalar_type, req, max_keep, out_contacts, out_counts);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return collide_batch_host_one(shapes, offT(pairs, b), offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, req, max_keep, offPtr(out_contacts, b * size_t(max_keep) * 9 * ss), offT(out_counts, b)); });
 }
 
 int fclb_gjk_epa_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
@@ -251,12 +260,20 @@ int fclb_gjk_epa_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const voi
   return runCollide(shapes, pairs, poses1, poses2, n, scalar_type, req, 1, out);
 }
 
-int fclb_gjk_epa_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+static int gjk_epa_batch_host_one(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
                             size_t n, int scalar_type, const fclb_request* req, int32_t* out_gjk, int32_t* out_epa,
                             void* out_geom) {
   if (!out_gjk) return fail(FCLB_ERR_BAD_ARG, "fclb_gjk_epa_batch: out_gjk is required");
   return runCollideHost(shapes, pairs, poses1, poses2, n, scalar_type, req, 1, 0, nullptr, nullptr, out_gjk, out_epa,
                         out_geom);
+}
+int fclb_gjk_epa_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                            size_t n, int scalar_type, const fclb_request* req, int32_t* out_gjk, int32_t* out_epa,
+                            void* out_geom) {
+  if (engineCount() <= 1) return gjk_epa_batch_host_one(shapes, pairs, poses1, poses2, n, scalar_type, req, out_gjk, out_epa, out_geom);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return gjk_epa_batch_host_one(shapes, offT(pairs, b), offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, req, offT(out_gjk, b), offT(out_epa, b), offPtr(out_geom, b * 7 * ss)); });
 }
 
 }  // extern "C"

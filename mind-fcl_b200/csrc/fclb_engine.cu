@@ -17,6 +17,7 @@
 #include <mutex>
 #include <set>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -32,15 +33,81 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 
+static Engine* g_engines[kMaxDevices] = {};
+static std::atomic<int> g_n_engines{0};
+static std::mutex g_engines_mu;
+static thread_local int t_slot = 0;
+
 Engine& eng() {
-  static Engine e;
-  return e;
+  Engine* e = g_engines[t_slot];
+  if (!e) {
+    std::lock_guard<std::mutex> lk(g_engines_mu);
+    if (!g_engines[t_slot]) {
+      g_engines[t_slot] = new Engine();
+      g_engines[t_slot]->slot = t_slot;
+    }
+    e = g_engines[t_slot];
+  }
+  return *e;
 }
+static std::atomic<fclb_handle> g_next_handle{1};
+static thread_local fclb_handle t_forced_handle = 0;  // forEachDevice: the handle the first replica got
+static thread_local fclb_handle t_last_handle = 0;
+fclb_handle newHandle() {
+  t_last_handle = t_forced_handle ? t_forced_handle : g_next_handle.fetch_add(1);
+  return t_last_handle;
+}
+void beginReplicas() { t_forced_handle = 0; t_last_handle = 0; }
+void nextReplica() { t_forced_handle = t_last_handle; }
+void endReplicas() { t_forced_handle = 0; }
+int engineCount() { return g_n_engines.load(); }
+int currentSlot() { return t_slot; }
+int setSlot(int slot) {
+  if (slot < 0 || slot >= kMaxDevices || !g_engines[slot] || !g_engines[slot]->ready)
+    return fail(FCLB_ERR_BAD_ARG, "device slot not initialised (fclb_init_devices)");
+  t_slot = slot;
+  FCLB_CUDA(cudaSetDevice(g_engines[slot]->device));
+  return FCLB_OK;
+}
+const std::string& lastErrorString() { return g_err; }
+void setLastErrorString(const std::string& s) { g_err = s; }
 
 int ensureInit() {
   Engine& e = eng();
-  if (e.ready) return FCLB_OK;
+  if (e.ready) {
+    // CUDA's current device is per host thread: a thread that never touched the library starts on device 0
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != e.device) FCLB_CUDA(cudaSetDevice(e.device));
+    return FCLB_OK;
+  }
   return fclb_init(-1);
+}
+
+int shardOverDevices(size_t n, const std::function<int(size_t, size_t)>& fn) {
+  const int nd = engineCount();
+  if (nd <= 1 || n < size_t(nd)) return fn(0, n);
+  const int home = currentSlot();
+  std::vector<int> rcs(size_t(nd), FCLB_OK);
+  std::vector<std::string> msgs{size_t(nd)};
+  std::vector<std::thread> ts;
+  const size_t base = n / size_t(nd), rem = n % size_t(nd);
+  size_t begin = 0;
+  for (int s = 0; s < nd; s++) {
+    const size_t cnt = base + (size_t(s) < rem ? 1 : 0);
+    const size_t b = begin;
+    begin += cnt;
+    ts.emplace_back([&, s, b, cnt] {
+      int rc = setSlot(s);
+      if (rc == FCLB_OK && cnt) rc = fn(b, cnt);
+      rcs[size_t(s)] = rc;
+      if (rc) msgs[size_t(s)] = g_err;
+    });
+  }
+  for (auto& t : ts) t.join();
+  setSlot(home);
+  for (int s = 0; s < nd; s++)
+    if (rcs[size_t(s)]) return fail(rcs[size_t(s)], "device " + std::to_string(s) + ": " + msgs[size_t(s)]);
+  return FCLB_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -333,9 +400,10 @@ int ensureChunkEvents(Engine& e, int n) {
 }
 
 unsigned long long* gjkCursor() {
-  static unsigned long long* d = nullptr;
-  if (!d && cudaMalloc(&d, sizeof(unsigned long long)) != cudaSuccess) d = nullptr;
-  return d;
+  static unsigned long long* d[kMaxDevices] = {};
+  unsigned long long*& p = d[currentSlot()];
+  if (!p && cudaMalloc(&p, sizeof(unsigned long long)) != cudaSuccess) p = nullptr;
+  return p;
 }
 
 int ensureStage(Engine& e, size_t bytes) {
@@ -428,15 +496,8 @@ int fclb_device_count(void) {
   return n;
 }
 
-int fclb_init(int device) {
-  Engine& e = eng();
-  std::lock_guard<std::recursive_mutex> lk(e.mu);
-  if (e.ready && (device < 0 || device == e.device)) return FCLB_OK;
-  if (e.ready) return fail(FCLB_ERR_BAD_ARG, "fclb_init: engine already bound to another device (one process per GPU)");
-  const int n = fclb_device_count();
-  if (n <= 0) return fail(FCLB_ERR_NO_DEVICE, "no CUDA device visible: libfclb200 has no CPU fallback");
-  if (device < 0) device = 0;
-  if (device >= n) return fail(FCLB_ERR_BAD_ARG, "fclb_init: device index out of range");
+// streams, events and scratch of one engine on `device` (the caller holds the engine's mutex)
+static int initEngine(Engine& e, int device) {
   FCLB_CUDA(cudaSetDevice(device));
   e.device = device;
   FCLB_CUDA(cudaDeviceGetAttribute(&e.sms, cudaDevAttrMultiProcessorCount, device));
@@ -448,15 +509,63 @@ int fclb_init(int device) {
   FCLB_CUDA(cudaEventCreate(&e.ev_call0));
   for (int i = 0; i <= Engine::kMaxRec; i++) FCLB_CUDA(cudaEventCreate(&e.rec_ev[i]));
   FCLB_CUDA(cudaMalloc(&e.d_hist, 2 * kNumKinds * sizeof(uint32_t)));
-  FCLB_CUDA(cudaMallocHost(&e.h_hist, 2 * kNumKinds * sizeof(uint32_t)));
+  FCLB_CUDA(cudaHostAlloc(&e.h_hist, 2 * kNumKinds * sizeof(uint32_t), cudaHostAllocPortable));
   e.ready = true;
   return FCLB_OK;
 }
 
+int fclb_init(int device) {
+  const int home = t_slot;
+  t_slot = 0;  // the one-GPU-per-process binding is slot 0
+  Engine& e = eng();
+  t_slot = home;
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (e.ready && (device < 0 || device == e.device)) return FCLB_OK;
+  if (e.ready) return fail(FCLB_ERR_BAD_ARG, "fclb_init: engine already bound to another device (one process per GPU)");
+  const int n = fclb_device_count();
+  if (n <= 0) return fail(FCLB_ERR_NO_DEVICE, "no CUDA device visible: libfclb200 has no CPU fallback");
+  if (device < 0) device = 0;
+  if (device >= n) return fail(FCLB_ERR_BAD_ARG, "fclb_init: device index out of range");
+  const int rc = initEngine(e, device);
+  if (rc) return rc;
+  if (g_n_engines.load() < 1) g_n_engines.store(1);
+  return FCLB_OK;
+}
+
+// SURVEY.md 8(b) fclb_init(int n_devices): enumerate the GPUs of the box, one engine (streams, scratch, replicas of every
+// geometry uploaded afterwards) per device.  n_devices <= 0: every visible device.  Must precede the first upload.
+int fclb_init_devices(int n_devices) {
+  const int n = fclb_device_count();
+  if (n <= 0) return fail(FCLB_ERR_NO_DEVICE, "no CUDA device visible: libfclb200 has no CPU fallback");
+  if (n_devices <= 0 || n_devices > n) n_devices = n;
+  if (n_devices > kMaxDevices) n_devices = kMaxDevices;
+  const int home = t_slot;
+  int rc = FCLB_OK;
+  for (int s = 0; s < n_devices && rc == FCLB_OK; s++) {
+    t_slot = s;
+    Engine& e = eng();
+    std::lock_guard<std::recursive_mutex> lk(e.mu);
+    if (e.ready) {
+      if (e.device != s) rc = fail(FCLB_ERR_BAD_ARG, "fclb_init_devices: slot 0 is already bound to another GPU by fclb_init");
+      continue;
+    }
+    if (s > 0 && (!g_engines[0]->tables.empty() || !g_engines[0]->convex.empty()))
+      rc = fail(FCLB_ERR_BAD_ARG, "fclb_init_devices must be called before the first geometry upload");
+    else
+      rc = initEngine(e, s);
+  }
+  t_slot = home;
+  if (rc) return rc;
+  if (g_n_engines.load() < n_devices) g_n_engines.store(n_devices);
+  return setSlot(home);
+}
+int fclb_num_devices(void) { return g_n_engines.load(); }
+int fclb_set_device(int slot) { return setSlot(slot); }
+
 int fclb_host_alloc(void** p, size_t bytes) {
   int rc = ensureInit();
   if (rc) return rc;
-  FCLB_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+  FCLB_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));  // usable by every engine's copy streams
   return FCLB_OK;
 }
 int fclb_host_free(void* p) {
@@ -549,7 +658,7 @@ int fclb_measure_l2_bandwidth(double* gbs) {
   return FCLB_OK;
 }
 
-int fclb_convex_upload(const double* verts, int n_verts, const int* faces, int faces_len, int num_faces,
+static int convex_upload_one(const double* verts, int n_verts, const int* faces, int faces_len, int num_faces,
                        uint32_t* slot) {
   int rc = ensureInit();
   if (rc) return rc;
@@ -610,8 +719,14 @@ int fclb_convex_upload(const double* verts, int n_verts, const int* faces, int f
   *slot = uint32_t(e.convex.size() - 1);
   return uploadConvexTables(e);
 }
+int fclb_convex_upload(const double* verts, int n_verts, const int* faces, int faces_len, int num_faces,
+                       uint32_t* slot) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return convex_upload_one(verts, n_verts, faces, faces_len, num_faces, slot); });
+}
 
-int fclb_shapes_upload(const fclb_shape* shapes, uint32_t n_shapes, fclb_handle* table) {
+static int shapes_upload_one(const fclb_shape* shapes, uint32_t n_shapes, fclb_handle* table) {
   int rc = ensureInit();
   if (rc) return rc;
   if (!shapes || !table || n_shapes == 0) return fail(FCLB_ERR_BAD_ARG, "fclb_shapes_upload: null or empty input");
@@ -626,13 +741,18 @@ int fclb_shapes_upload(const fclb_shape* shapes, uint32_t n_shapes, fclb_handle*
     delete t;
     return rc;
   }
-  const fclb_handle h = e.next_handle++;
+  const fclb_handle h = newHandle();
   e.tables[h] = t;
   *table = h;
   return FCLB_OK;
 }
+int fclb_shapes_upload(const fclb_shape* shapes, uint32_t n_shapes, fclb_handle* table) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return shapes_upload_one(shapes, n_shapes, table); });
+}
 
-int fclb_release(fclb_handle h) {
+static int release_one(fclb_handle h) {
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
   auto it = e.tables.find(h);
@@ -646,6 +766,11 @@ int fclb_release(fclb_handle h) {
   delete it->second;
   e.tables.erase(it);
   return FCLB_OK;
+}
+int fclb_release(fclb_handle h) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return release_one(h); });
 }
 
 int fclb_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
@@ -721,7 +846,7 @@ int fclb_signed_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, c
   return rc;
 }
 
-int fclb_signed_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+static int signed_distance_batch_host_one(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
                                     size_t n, int scalar_type, void* out_dist, void* out_p1, void* out_p2, uint8_t* out_ok) {
   int rc = ensureInit();
   if (rc) return rc;
@@ -757,8 +882,15 @@ int fclb_signed_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, 
   cudaFree(base);
   return rc;
 }
+int fclb_signed_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                                    size_t n, int scalar_type, void* out_dist, void* out_p1, void* out_p2, uint8_t* out_ok) {
+  if (engineCount() <= 1) return signed_distance_batch_host_one(shapes, pairs, poses1, poses2, n, scalar_type, out_dist, out_p1, out_p2, out_ok);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return signed_distance_batch_host_one(shapes, offT(pairs, b), offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, offPtr(out_dist, b * ss), offPtr(out_p1, b * 3 * ss), offPtr(out_p2, b * 3 * ss), offT(out_ok, b)); });
+}
 
-int fclb_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+static int distance_batch_host_one(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
                              size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
                              void* out_p1, void* out_p2, uint8_t* out_ok) {
   int rc = ensureInit();
@@ -829,6 +961,14 @@ int fclb_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const v
   }
   FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
   return FCLB_OK;
+}
+int fclb_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                             size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
+                             void* out_p1, void* out_p2, uint8_t* out_ok) {
+  if (engineCount() <= 1) return distance_batch_host_one(shapes, pairs, poses1, poses2, n, scalar_type, gjk_tol, gjk_max_iter, out_dist, out_p1, out_p2, out_ok);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return distance_batch_host_one(shapes, offT(pairs, b), offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, gjk_tol, gjk_max_iter, offPtr(out_dist, b * ss), offPtr(out_p1, b * 3 * ss), offPtr(out_p2, b * 3 * ss), offT(out_ok, b)); });
 }
 
 // (collide / gjk_epa entry points: fclb_collide_api.cu)

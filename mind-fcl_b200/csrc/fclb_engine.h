@@ -2,6 +2,7 @@
 // (fclb_engine.cu, fclb_collide_api.cu, fclb_bvh_api.cu).  Internal.
 #pragma once
 #include <atomic>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -39,10 +40,16 @@ struct ShapeTable {
   uint64_t convex_epoch = 0;
 };
 
+constexpr int kMaxDevices = 16;
+
+// One engine per GPU.  A process either binds ONE GPU (fclb_init: one process per GPU, the torchrun layout) or
+// enumerates several (fclb_init_devices: one process, the batch of a *_host call sharded by query index across the
+// engines, geometry replicated on every device).  The calling thread's current engine is thread-local.
 struct Engine {
   std::recursive_mutex mu;
   bool ready = false;
   int device = -1;
+  int slot = 0;
   int sms = 148;
   cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -50,7 +57,6 @@ struct Engine {
   void* d_convex_tab[2] = {nullptr, nullptr};  // ConvexD<S>[]
   uint64_t convex_epoch = 0;
   std::map<fclb_handle, ShapeTable*> tables;
-  fclb_handle next_handle = 1;
   // scratch for bucketing
   uint32_t* d_perm = nullptr;
   uint8_t* d_kind = nullptr;
@@ -74,7 +80,51 @@ struct Engine {
   int n_rec = 0;
   cudaEvent_t ev_call0 = nullptr;
 };
-Engine& eng();
+Engine& eng();            // engine of the calling thread's current device slot
+int engineCount();        // engines created by fclb_init / fclb_init_devices (>= 1 once initialised)
+int currentSlot();
+int setSlot(int slot);    // thread-local: later calls of this thread go to engine `slot` (cudaSetDevice included)
+const std::string& lastErrorString();
+void setLastErrorString(const std::string& s);
+
+// process-global scratch that must exist once per device
+template <typename T>
+struct PerDevice {
+  T v[kMaxDevices];
+  T& get() { return v[currentSlot()]; }
+};
+
+// run fn() once per engine (geometry uploads / releases: every device holds a replica under the same handle)
+void beginReplicas();
+void nextReplica();
+void endReplicas();
+template <typename Fn>
+int forEachDevice(Fn&& fn) {
+  const int n = engineCount();
+  if (n <= 1) return fn();
+  const int home = currentSlot();
+  int rc = FCLB_OK;
+  beginReplicas();
+  for (int s = 0; s < n && rc == FCLB_OK; s++) {
+    rc = setSlot(s);
+    if (rc == FCLB_OK) rc = fn();
+    nextReplica();  // the other replicas are filed under the first one's handle
+  }
+  endReplicas();
+  setSlot(home);
+  return rc;
+}
+inline const void* offPtr(const void* p, size_t bytes) { return p ? static_cast<const char*>(p) + bytes : nullptr; }
+inline void* offPtr(void* p, size_t bytes) { return p ? static_cast<char*>(p) + bytes : nullptr; }
+template <typename T>
+inline T* offT(T* p, size_t elems) { return p ? p + elems : nullptr; }
+
+// shard [0, n) by contiguous query range over the engines, one host thread per device; fn(begin, count) runs the
+// single-device implementation on its slice.  Returns the first non-zero code (message copied to the caller's thread).
+int shardOverDevices(size_t n, const std::function<int(size_t, size_t)>& fn);
+
+// Handles are process-wide: the replicas of one geometry on every device share one handle value.
+fclb_handle newHandle();
 
 int ensureInit();
 ShapeTable* findTable(Engine& e, fclb_handle h);

@@ -12,8 +12,17 @@
 
 namespace fclb {
 
-static unsigned long long* g_counters = nullptr;  // [0] work counter, [1..2] stats
-static unsigned long long g_stats[3] = {0, 0, 0};
+struct SceneStats {
+  unsigned long long* counters = nullptr;  // device: [0] work counter, [1..2] stats
+  unsigned long long stats[3] = {0, 0, 0};
+  void* d_box = nullptr;       // pass-1 leaf boxes of the MPR penetration path (scene-shape)
+  size_t d_box_cap = 0;
+  void* d_box_pair = nullptr;  // ... (scene pairs)
+  size_t d_box_pair_cap = 0;
+};
+static PerDevice<SceneStats> g_scene_pd;
+#define g_counters (g_scene_pd.get().counters)
+#define g_stats (g_scene_pd.get().stats)
 
 struct ContactSink {  // pass 1 of the MPR penetration modes
   uint32_t max_keep = 0;
@@ -91,8 +100,8 @@ struct HeightmapDev {
   double res_x = 0, res_y = 0;
 };
 static std::map<fclb_handle, HeightmapDev*>& hmTable() {
-  static std::map<fclb_handle, HeightmapDev*> t;
-  return t;
+  static std::map<fclb_handle, HeightmapDev*> t[kMaxDevices];
+  return t[currentSlot()];
 }
 
 template <typename S>
@@ -165,8 +174,8 @@ struct OctreeDev {
   double root_box[6] = {0, 0, 0, 0, 0, 0};
 };
 static std::map<fclb_handle, OctreeDev*>& octTable() {
-  static std::map<fclb_handle, OctreeDev*> t;
-  return t;
+  static std::map<fclb_handle, OctreeDev*> t[kMaxDevices];
+  return t[currentSlot()];
 }
 
 template <typename S>
@@ -233,8 +242,8 @@ static int sceneContactsDev(Engine& e, int kind, fclb_handle scene, const ShapeT
                             const void* poses_scene, const void* poses_shape, size_t n, const fclb_request* req,
                             uint32_t max_keep, uint32_t* counts, long long* b1, void* contacts) {
   const int st = sizeof(S) == 4 ? 0 : 1;
-  static void* d_box = nullptr;
-  static size_t d_box_cap = 0;
+  void*& d_box = g_scene_pd.get().d_box;
+  size_t& d_box_cap = g_scene_pd.get().d_box_cap;
   const size_t box_bytes = n * size_t(max_keep) * 6 * sizeof(S);
   if (kind != FCLB_SCENE_BVH && d_box_cap < box_bytes) {
     cudaFree(d_box);
@@ -405,8 +414,8 @@ static int scenePairContactsDev(Engine& e, int kind1, fclb_handle scene1, int ki
                                 const void* poses2, size_t n, const fclb_request* req, uint32_t max_keep, uint32_t* counts,
                                 long long* b1, long long* b2, void* contacts) {
   const int st = sizeof(S) == 4 ? 0 : 1;
-  static void* d_box = nullptr;
-  static size_t d_box_cap = 0;
+  void*& d_box = g_scene_pd.get().d_box_pair;
+  size_t& d_box_cap = g_scene_pd.get().d_box_pair_cap;
   const size_t one = n * size_t(max_keep) * 6 * sizeof(S);
   if (d_box_cap < 2 * one) {
     cudaFree(d_box);
@@ -870,7 +879,7 @@ static int heightmapBuildDev(Engine& e, const void* d_points, size_t n_points, d
   uint32_t mx = 0;
   for (uint16_t h : h_top) mx = h > mx ? h : mx;
   d->upper_mm = mx;
-  const fclb_handle h = e.next_handle++;
+  const fclb_handle h = newHandle();
   hmTable()[h] = d;
   *hm = h;
   return FCLB_OK;
@@ -906,7 +915,7 @@ int fclb_bvh_shape_collide_batch_dev(fclb_handle bvh, fclb_handle shapes, const 
   return bvhShapeDev<double>(e, it->second, t, shape_ids, poses_mesh, poses_shape, n, req, out_counts, out_first_tri);
 }
 
-int fclb_bvh_shape_collide_batch_host(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids, const void* poses_mesh,
+static int bvh_shape_collide_batch_host_one(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids, const void* poses_mesh,
                                       const void* poses_shape, size_t n, int scalar_type, const fclb_request* req,
                                       uint32_t* out_counts, int32_t* out_first_tri) {
   int rc = ensureInit();
@@ -944,6 +953,14 @@ int fclb_bvh_shape_collide_batch_host(fclb_handle bvh, fclb_handle shapes, const
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }
+int fclb_bvh_shape_collide_batch_host(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids, const void* poses_mesh,
+                                      const void* poses_shape, size_t n, int scalar_type, const fclb_request* req,
+                                      uint32_t* out_counts, int32_t* out_first_tri) {
+  if (engineCount() <= 1) return bvh_shape_collide_batch_host_one(bvh, shapes, shape_ids, poses_mesh, poses_shape, n, scalar_type, req, out_counts, out_first_tri);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return bvh_shape_collide_batch_host_one(bvh, shapes, offT(shape_ids, b), offPtr(poses_mesh, b * 12 * ss), offPtr(poses_shape, b * 12 * ss), m_, scalar_type, req, offT(out_counts, b), offT(out_first_tri, b)); });
+}
 
 int fclb_heightmap_build_host(const double* points, size_t n_points, double resolution_x, double resolution_y,
                               uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, uint16_t* heights_mm) {
@@ -958,7 +975,7 @@ int fclb_heightmap_build_host(const double* points, size_t n_points, double reso
   return FCLB_OK;
 }
 
-int fclb_heightmap_upload(const uint16_t* heights_mm, uint32_t full_x, uint32_t full_y, double resolution_x,
+static int heightmap_upload_one(const uint16_t* heights_mm, uint32_t full_x, uint32_t full_y, double resolution_x,
                           double resolution_y, uint32_t upper_bound_mm, fclb_handle* hm) {
   int rc = ensureInit();
   if (rc) return rc;
@@ -1012,10 +1029,16 @@ int fclb_heightmap_upload(const uint16_t* heights_mm, uint32_t full_x, uint32_t 
   }
   for (size_t k = 0; k < layers.size(); k++)
     cudaMemcpy(d->d_layers + d->off[k], layers[k].data(), layers[k].size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
-  const fclb_handle h = e.next_handle++;
+  const fclb_handle h = newHandle();
   hmTable()[h] = d;
   *hm = h;
   return FCLB_OK;
+}
+int fclb_heightmap_upload(const uint16_t* heights_mm, uint32_t full_x, uint32_t full_y, double resolution_x,
+                          double resolution_y, uint32_t upper_bound_mm, fclb_handle* hm) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return heightmap_upload_one(heights_mm, full_x, full_y, resolution_x, resolution_y, upper_bound_mm, hm); });
 }
 
 int fclb_heightmap_build_dev(const void* points, size_t n_points, double resolution_x, double resolution_y,
@@ -1035,7 +1058,7 @@ int fclb_heightmap_build_dev(const void* points, size_t n_points, double resolut
   return heightmapBuildDev<double>(e, points, n_points, resolution_x, resolution_y, half_shape_x, half_shape_y, hm);
 }
 
-int fclb_heightmap_build_points_host(const void* points, size_t n_points, double resolution_x, double resolution_y,
+static int heightmap_build_points_host_one(const void* points, size_t n_points, double resolution_x, double resolution_y,
                                      uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, fclb_handle* hm) {
   int rc = ensureInit();
   if (rc) return rc;
@@ -1048,6 +1071,12 @@ int fclb_heightmap_build_points_host(const void* points, size_t n_points, double
   if (rc) return rc;
   if (bytes) FCLB_CUDA(cudaMemcpyAsync(e.d_stage, points, bytes, cudaMemcpyHostToDevice, e.compute));
   return fclb_heightmap_build_dev(e.d_stage, n_points, resolution_x, resolution_y, half_shape_x, half_shape_y, scalar_type, hm);
+}
+int fclb_heightmap_build_points_host(const void* points, size_t n_points, double resolution_x, double resolution_y,
+                                     uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, fclb_handle* hm) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return heightmap_build_points_host_one(points, n_points, resolution_x, resolution_y, half_shape_x, half_shape_y, scalar_type, hm); });
 }
 
 int fclb_heightmap_info(fclb_handle hm, uint32_t* n_layers, uint32_t* full_x, uint32_t* full_y, uint32_t* upper_bound_mm) {
@@ -1074,7 +1103,7 @@ int fclb_heightmap_export(fclb_handle hm, uint32_t layer, uint16_t* heights_mm) 
   return FCLB_OK;
 }
 
-int fclb_heightmap_release(fclb_handle h) {
+static int heightmap_release_one(fclb_handle h) {
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
   auto it = hmTable().find(h);
@@ -1083,6 +1112,11 @@ int fclb_heightmap_release(fclb_handle h) {
   delete it->second;
   hmTable().erase(it);
   return FCLB_OK;
+}
+int fclb_heightmap_release(fclb_handle h) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return heightmap_release_one(h); });
 }
 
 int fclb_heightmap_shape_collide_batch_dev(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
@@ -1110,7 +1144,7 @@ int fclb_heightmap_shape_collide_batch_dev(fclb_handle hm, fclb_handle shapes, c
                                    out_first_pixel);
 }
 
-int fclb_heightmap_shape_collide_batch_host(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
+static int heightmap_shape_collide_batch_host_one(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
                                             const void* poses_hm, const void* poses_shape, size_t n, int scalar_type,
                                             const fclb_request* req, uint32_t* out_counts, int32_t* out_first_pixel) {
   int rc = ensureInit();
@@ -1149,8 +1183,16 @@ int fclb_heightmap_shape_collide_batch_host(fclb_handle hm, fclb_handle shapes, 
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }
+int fclb_heightmap_shape_collide_batch_host(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
+                                            const void* poses_hm, const void* poses_shape, size_t n, int scalar_type,
+                                            const fclb_request* req, uint32_t* out_counts, int32_t* out_first_pixel) {
+  if (engineCount() <= 1) return heightmap_shape_collide_batch_host_one(hm, shapes, shape_ids, poses_hm, poses_shape, n, scalar_type, req, out_counts, out_first_pixel);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return heightmap_shape_collide_batch_host_one(hm, shapes, offT(shape_ids, b), offPtr(poses_hm, b * 12 * ss), offPtr(poses_shape, b * 12 * ss), m_, scalar_type, req, offT(out_counts, b), offT(out_first_pixel, b)); });
+}
 
-int fclb_octree_upload(const uint32_t* inner_children, const uint8_t* inner_full, uint32_t n_inner, const uint8_t* leaf_bits,
+static int octree_upload_one(const uint32_t* inner_children, const uint8_t* inner_full, uint32_t n_inner, const uint8_t* leaf_bits,
                        uint32_t n_leaf, const uint8_t* pruned_or_null, const double* root_aabb, int num_layers,
                        fclb_handle* octree) {
   int rc = ensureInit();
@@ -1177,10 +1219,17 @@ int fclb_octree_upload(const uint32_t* inner_children, const uint8_t* inner_full
     delete d;
     return fail(FCLB_ERR_CUDA, "fclb_octree_upload: device allocation / copy failed");
   }
-  const fclb_handle h = e.next_handle++;
+  const fclb_handle h = newHandle();
   octTable()[h] = d;
   *octree = h;
   return FCLB_OK;
+}
+int fclb_octree_upload(const uint32_t* inner_children, const uint8_t* inner_full, uint32_t n_inner, const uint8_t* leaf_bits,
+                       uint32_t n_leaf, const uint8_t* pruned_or_null, const double* root_aabb, int num_layers,
+                       fclb_handle* octree) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return octree_upload_one(inner_children, inner_full, n_inner, leaf_bits, n_leaf, pruned_or_null, root_aabb, num_layers, octree); });
 }
 
 namespace {
@@ -1269,6 +1318,7 @@ int fclb_octree_build_host(const double* points, size_t n_points, double resolut
   return FCLB_OK;
 }
 
+// the tree is built once on the host (mirror of Octree::rebuildTree) and uploaded to every device
 int fclb_octree_build(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
                       fclb_handle* octree) {
   int rc = ensureInit();
@@ -1277,8 +1327,10 @@ int fclb_octree_build(const double* points, size_t n_points, double resolution, 
   rc = octreeBuildHostImpl(points, n_points, resolution, bottom_half_shape, scalar_type, t,
                            "fclb_octree_build: bad argument (half shape: power of two >= 2)");
   if (rc) return rc;
-  return fclb_octree_upload(t.children.data(), t.full.data(), uint32_t(t.n_inner()), t.leaf_bits.data(),
-                            uint32_t(t.leaf_bits.size()), nullptr, t.root_box, t.num_layers, octree);
+  return forEachDevice([&] {
+    return octree_upload_one(t.children.data(), t.full.data(), uint32_t(t.n_inner()), t.leaf_bits.data(),
+                             uint32_t(t.leaf_bits.size()), nullptr, t.root_box, t.num_layers, octree);
+  });
 }
 
 int fclb_octree_prune_host(const uint32_t* inner_children, uint32_t n_inner, uint32_t n_leaf, const double* root_aabb,
@@ -1313,7 +1365,7 @@ int fclb_octree_consolidate_host(const uint32_t* inner_children, uint32_t n_inne
   return FCLB_OK;
 }
 
-int fclb_octree_release(fclb_handle h) {
+static int octree_release_one(fclb_handle h) {
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
   auto it = octTable().find(h);
@@ -1325,6 +1377,11 @@ int fclb_octree_release(fclb_handle h) {
   delete it->second;
   octTable().erase(it);
   return FCLB_OK;
+}
+int fclb_octree_release(fclb_handle h) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return octree_release_one(h); });
 }
 
 int fclb_octree_shape_collide_batch_dev(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
@@ -1359,7 +1416,7 @@ int fclb_octree_shape_collide_batch_dev(fclb_handle octree, fclb_handle shapes, 
                                 reinterpret_cast<long long*>(out_first_node));
 }
 
-int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
+static int octree_shape_collide_batch_host_one(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
                                          const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
                                          const fclb_request* req, uint32_t* out_counts, int64_t* out_first_node) {
   int rc = ensureInit();
@@ -1397,6 +1454,14 @@ int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes,
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }
+int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
+                                         const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
+                                         const fclb_request* req, uint32_t* out_counts, int64_t* out_first_node) {
+  if (engineCount() <= 1) return octree_shape_collide_batch_host_one(octree, shapes, shape_ids, poses_octree, poses_shape, n, scalar_type, req, out_counts, out_first_node);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return octree_shape_collide_batch_host_one(octree, shapes, offT(shape_ids, b), offPtr(poses_octree, b * 12 * ss), offPtr(poses_shape, b * 12 * ss), m_, scalar_type, req, offT(out_counts, b), offT(out_first_node, b)); });
+}
 
 int fclb_scene_shape_contacts_batch_dev(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
                                         const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
@@ -1418,7 +1483,7 @@ int fclb_scene_shape_contacts_batch_dev(int scene_kind, fclb_handle scene, fclb_
                                out_counts, reinterpret_cast<long long*>(out_b1), out_contacts);
 }
 
-int fclb_scene_shape_contacts_batch_host(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+static int scene_shape_contacts_batch_host_one(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
                                          const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
                                          const fclb_request* req, uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1,
                                          void* out_contacts) {
@@ -1462,6 +1527,15 @@ int fclb_scene_shape_contacts_batch_host(int scene_kind, fclb_handle scene, fclb
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }
+int fclb_scene_shape_contacts_batch_host(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                         const void* poses_scene, const void* poses_shape, size_t n, int scalar_type,
+                                         const fclb_request* req, uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1,
+                                         void* out_contacts) {
+  if (engineCount() <= 1) return scene_shape_contacts_batch_host_one(scene_kind, scene, shapes, shape_ids, poses_scene, poses_shape, n, scalar_type, req, max_keep, out_counts, out_b1, out_contacts);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return scene_shape_contacts_batch_host_one(scene_kind, scene, shapes, offT(shape_ids, b), offPtr(poses_scene, b * 12 * ss), offPtr(poses_shape, b * 12 * ss), m_, scalar_type, req, max_keep, offT(out_counts, b), offT(out_b1, b * size_t(max_keep)), offPtr(out_contacts, b * size_t(max_keep) * 7 * ss)); });
+}
 
 int fclb_scene_pair_collide_batch_dev(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                                       const void* poses2, size_t n, int scalar_type, const fclb_request* req,
@@ -1493,7 +1567,7 @@ int fclb_scene_pair_collide_batch_dev(int kind1, fclb_handle scene1, int kind2, 
                               reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2));
 }
 
-int fclb_scene_pair_collide_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+static int scene_pair_collide_batch_host_one(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                                        const void* poses2, size_t n, int scalar_type, const fclb_request* req,
                                        uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2) {
   int rc = ensureInit();
@@ -1530,6 +1604,14 @@ int fclb_scene_pair_collide_batch_host(int kind1, fclb_handle scene1, int kind2,
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
 }
+int fclb_scene_pair_collide_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                       const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                       uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2) {
+  if (engineCount() <= 1) return scene_pair_collide_batch_host_one(kind1, scene1, kind2, scene2, poses1, poses2, n, scalar_type, req, max_keep, out_counts, out_b1, out_b2);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return scene_pair_collide_batch_host_one(kind1, scene1, kind2, scene2, offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, req, max_keep, offT(out_counts, b), offT(out_b1, b * size_t(max_keep)), offT(out_b2, b * size_t(max_keep))); });
+}
 
 int fclb_scene_pair_contacts_batch_dev(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                                        const void* poses2, size_t n, int scalar_type, const fclb_request* req,
@@ -1550,7 +1632,7 @@ int fclb_scene_pair_contacts_batch_dev(int kind1, fclb_handle scene1, int kind2,
                               reinterpret_cast<long long*>(out_b1), reinterpret_cast<long long*>(out_b2), out_contacts);
 }
 
-int fclb_scene_pair_contacts_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+static int scene_pair_contacts_batch_host_one(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                                         const void* poses2, size_t n, int scalar_type, const fclb_request* req,
                                         uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2,
                                         void* out_contacts) {
@@ -1587,6 +1669,15 @@ int fclb_scene_pair_contacts_batch_host(int kind1, fclb_handle scene1, int kind2
   FCLB_CUDA(cudaMemcpyAsync(out_contacts, base + o_ct, n * keep * 7 * ss, cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   return FCLB_OK;
+}
+int fclb_scene_pair_contacts_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                        const void* poses2, size_t n, int scalar_type, const fclb_request* req,
+                                        uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2,
+                                        void* out_contacts) {
+  if (engineCount() <= 1) return scene_pair_contacts_batch_host_one(kind1, scene1, kind2, scene2, poses1, poses2, n, scalar_type, req, max_keep, out_counts, out_b1, out_b2, out_contacts);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  (void)ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) { return scene_pair_contacts_batch_host_one(kind1, scene1, kind2, scene2, offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, req, max_keep, offT(out_counts, b), offT(out_b1, b * size_t(max_keep)), offT(out_b2, b * size_t(max_keep)), offPtr(out_contacts, b * size_t(max_keep) * 7 * ss)); });
 }
 
 /* node / leaf tests executed by the most recent mesh-shape or heightmap-shape batch call */

@@ -48,6 +48,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
+    "fclb_init_devices", "fclb_num_devices", "fclb_set_device",
     "fclb_measure_fp_peak", "fclb_measure_l2_bandwidth", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -239,6 +240,12 @@ def np_dtype(scalar_type):
 
 def init(device: int = 0) -> None:
     check(load().fclb_init(device))
+
+
+def init_devices(n: int = 0) -> int:
+    """one process, n GPUs (0: all visible): *_host batch calls shard by query index; returns the engine count"""
+    check(load().fclb_init_devices(n))
+    return int(load().fclb_num_devices())
 
 
 def convex_upload(verts: np.ndarray, faces: np.ndarray, num_faces: int) -> int:
