@@ -625,6 +625,43 @@ struct CollisionQuery {
   Transform3<S> tf2;
 };
 
+namespace detail {
+// batched C-ABI calls issued so far (tests: a batch of queries on one geometry pair must cost ONE call)
+inline std::size_t& abiBatchCalls() {
+  static std::size_t n = 0;
+  return n;
+}
+// rc of a batched call: UNSUPPORTED / BAD_ARG / CAPACITY are reported the reference's way (a warning, no contacts,
+// collision-inl.h:91-110); a missing device or a CUDA fault aborts (there is no CPU path to fall back to)
+inline bool batchOk(int rc, const char* what) {
+  abiBatchCalls() += 1;
+  if (rc == FCLB_OK) return true;
+  if (rc == FCLB_ERR_NO_DEVICE || rc == FCLB_ERR_CUDA) check(rc, what);
+  std::cerr << "Warning: " << what << ": " << fclb_last_error() << std::endl;
+  return false;
+}
+template <typename S>
+inline int sceneKind(const CollisionGeometry<S>* g) {
+  return g->getNodeType() == BV_OBBRSS ? FCLB_SCENE_BVH : (g->getNodeType() == GEOM_HEIGHTMAP ? FCLB_SCENE_HEIGHTMAP : FCLB_SCENE_OCTREE);
+}
+template <typename S>
+inline fclb_handle sceneHandle(const CollisionGeometry<S>* g) {
+  if (g->getNodeType() == BV_OBBRSS) return static_cast<const BVHModel<OBBRSS<S>>*>(g)->handle();
+  if (g->getNodeType() == GEOM_HEIGHTMAP) return static_cast<const HeightMapCollisionGeometry<S>*>(g)->handle();
+  return static_cast<const Octree2CollisionGeometry<S>*>(g)->handle();
+}
+// contacts kept per query by one batched call; a query that reports more is served by a second call sized to fit
+inline uint32_t firstKeep(uint32_t max_contacts) { return max_contacts < 8 ? max_contacts : 8; }
+}  // namespace detail
+
+// Every query of the batch goes to the device in as few C-ABI calls as its geometry allows: all shape-shape queries in
+// ONE call (one shape table), every other query grouped by its (geometry, geometry) handle pair with ONE call per
+// group.  Dispatch follows the reference's table (collision_func_matrix-inl.h:720-857) incl. its argument swaps:
+//   (Shape, BVH)        collide() swaps the arguments (collision-inl.h:91-100): o1 = mesh, the normal is the one
+//                       MeshShapeIntersect writes (reverse_normal = true, bvh_solver-inl.h:55-66)
+//   (Shape, HeightMap), (Shape, Octree2), (BVH, HeightMap), (BVH, Octree2), (Octree2, HeightMap)
+//                       forward to the scene-first solver, which writes o1 = the heightmap / octree with no reversal
+//                       (collision_func_matrix-inl.h:60-78,774-792,815-833)
 template <typename S>
 void collideBatch(const std::vector<CollisionQuery<S>>& queries, const CollisionRequest<S>& request,
                   std::vector<CollisionResult<S>>& results) {
@@ -635,170 +672,268 @@ void collideBatch(const std::vector<CollisionQuery<S>>& queries, const Collision
     return;
   }
   if (n == 0) return;
-  // split: shape-shape queries go through one shape table, mesh-mesh queries per mesh pair
-  std::vector<fclb_shape> shapes;
-  std::vector<fclb_pair> pairs;
-  std::vector<S> p1, p2;
-  std::vector<std::size_t> shape_q;
   const fclb_request req = request.toAbi();
+  const int st = detail::scalarType<S>();
+  const bool pen = req.penetration_mode != FCLB_PEN_DISABLED;
+  const bool mpr_pen = req.penetration_mode == FCLB_PEN_DIRECTED || req.penetration_mode == FCLB_PEN_INCREMENTAL_MIN;
+
+  // ---- classify -----------------------------------------------------------------------------------------------
+  struct Group {
+    int kind = 0;  // 0 mesh-mesh, 1 scene-shape, 2 scene-scene
+    int k1 = 0, k2 = 0;
+    fclb_handle h1 = 0, h2 = 0;
+    const CollisionGeometry<S>*g1 = nullptr, *g2 = nullptr;
+    bool swapped = false;  // scene-scene: the device call has the arguments in the other order
+    std::vector<std::size_t> q;
+  };
+  std::vector<Group> groups;
+  auto groupOf = [&](int kind, int k1, fclb_handle h1, int k2, fclb_handle h2, bool swapped, const CollisionGeometry<S>* g1,
+                     const CollisionGeometry<S>* g2) -> Group& {
+    for (auto& g : groups)
+      if (g.kind == kind && g.k1 == k1 && g.h1 == h1 && g.k2 == k2 && g.h2 == h2 && g.swapped == swapped) return g;
+    groups.emplace_back();
+    Group& g = groups.back();
+    g.kind = kind; g.k1 = k1; g.h1 = h1; g.k2 = k2; g.h2 = h2; g.swapped = swapped; g.g1 = g1; g.g2 = g2;
+    return g;
+  };
+  std::vector<std::size_t> shape_q;
   for (std::size_t q = 0; q < n; q++) {
     const auto& Q = queries[q];
-    if (Q.o1->isShape() && Q.o2->isShape()) {
-      fclb_pair pr{uint32_t(shapes.size()), uint32_t(shapes.size() + 1)};
-      shapes.push_back(Q.o1->shapeRecord());
-      shapes.push_back(Q.o2->shapeRecord());
-      pairs.push_back(pr);
-      p1.resize(p1.size() + 12);
-      p2.resize(p2.size() + 12);
-      Q.tf1.toPose12(&p1[p1.size() - 12]);
-      Q.tf2.toPose12(&p2[p2.size() - 12]);
+    const bool s1 = Q.o1->isShape(), s2 = Q.o2->isShape();
+    if (s1 && s2) {
       shape_q.push_back(q);
-    } else if (!Q.o1->isShape() && !Q.o2->isShape() &&
-               !(Q.o1->getNodeType() == BV_OBBRSS && Q.o2->getNodeType() == BV_OBBRSS)) {
-      // heightmap / octree against heightmap / octree / mesh: HeightMapPairCollide, HeightMapBVHCollide,
-      // HeightMapOctree2Collide, OcTree2BVHCollide, OcTree2Collide and their argument-swapped entries
-      // (collision_func_matrix-inl.h:794-812, 835-856).  The swapped entries run the same solver with the
-      // heightmap (resp. octree) first and keep that orientation in the contacts.
-      auto kindOf = [](const CollisionGeometry<S>* g) {
-        return g->getNodeType() == BV_OBBRSS ? FCLB_SCENE_BVH : (g->getNodeType() == GEOM_HEIGHTMAP ? FCLB_SCENE_HEIGHTMAP : FCLB_SCENE_OCTREE);
-      };
-      auto handleOf = [](const CollisionGeometry<S>* g) -> fclb_handle {
-        if (g->getNodeType() == BV_OBBRSS) return static_cast<const BVHModel<OBBRSS<S>>*>(g)->handle();
-        if (g->getNodeType() == GEOM_HEIGHTMAP) return static_cast<const HeightMapCollisionGeometry<S>*>(g)->handle();
-        return static_cast<const Octree2CollisionGeometry<S>*>(g)->handle();
-      };
-      const int k1 = kindOf(Q.o1), k2 = kindOf(Q.o2);
-      // canonical order of the device entry point: heightmap before octree before mesh
-      auto rank = [](int k) { return k == FCLB_SCENE_HEIGHTMAP ? 0 : (k == FCLB_SCENE_OCTREE ? 1 : 2); };
-      const bool swap = rank(k1) > rank(k2);
-      const CollisionGeometry<S>* g1 = swap ? Q.o2 : Q.o1;
-      const CollisionGeometry<S>* g2 = swap ? Q.o1 : Q.o2;
-      S a[12], b[12];
-      (swap ? Q.tf2 : Q.tf1).toPose12(a);
-      (swap ? Q.tf1 : Q.tf2).toPose12(b);
-      constexpr uint32_t kKeep = 64;
-      uint32_t count = 0;
-      int64_t ids1[kKeep], ids2[kKeep];
-      S rec[kKeep * 7];
-      const bool mpr_pen = req.penetration_mode == FCLB_PEN_DIRECTED || req.penetration_mode == FCLB_PEN_INCREMENTAL_MIN;
-      if (mpr_pen) {
-        // collisionPenetrationMPR (collision_penetration-inl.h:189-252).  In the canonical argument order the records
-        // are the reference's bit for bit.  With swapped arguments the reference runs MPR on (leaf of o1, leaf of o2)
-        // for the escape direction of o2; here the canonical pair is evaluated for the opposite direction and the
-        // normal negated -- the same penetration up to MPR's argument order, not bit-identical.
-        fclb_request r2 = req;
-        if (swap)
-          for (int k = 0; k < 3; k++) r2.dir[k] = -req.dir[k];
-        detail::check(fclb_scene_pair_contacts_batch_host(kindOf(g1), handleOf(g1), kindOf(g2), handleOf(g2), a, b, 1,
-                                                          detail::scalarType<S>(), &r2, kKeep, &count, ids1, ids2, rec),
-                      "fclb_scene_pair_contacts_batch_host");
+    } else if (!s1 && !s2) {
+      const int k1 = detail::sceneKind(Q.o1), k2 = detail::sceneKind(Q.o2);
+      if (k1 == FCLB_SCENE_BVH && k2 == FCLB_SCENE_BVH) {
+        groupOf(0, k1, detail::sceneHandle(Q.o1), k2, detail::sceneHandle(Q.o2), false, Q.o1, Q.o2).q.push_back(q);
       } else {
-        detail::check(fclb_scene_pair_collide_batch_host(kindOf(g1), handleOf(g1), kindOf(g2), handleOf(g2), a, b, 1,
-                                                         detail::scalarType<S>(), &req, kKeep, &count, ids1, ids2),
-                      "fclb_scene_pair_collide_batch_host");
-      }
-      for (uint32_t c = 0; c < count && c < kKeep; c++) {
-        Contact<S> ct;
-        ct.o1 = g1;
-        ct.o2 = g2;
-        ct.b1 = intptr_t(ids1[c]);
-        ct.b2 = intptr_t(ids2[c]);
-        if (mpr_pen) {
-          const S* r = rec + 7 * c;
-          const S sgn = swap ? S(-1) : S(1);
-          ct.normal = Vector3<S>(sgn * r[0], sgn * r[1], sgn * r[2]);
-          ct.pos = Vector3<S>(r[3], r[4], r[5]);
-          ct.penetration_depth = r[6];
-        }
-        results[q].addContact(ct);
-      }
-    } else if (!Q.o1->isShape() && !Q.o2->isShape()) {
-      const auto* m1 = static_cast<const BVHModel<OBBRSS<S>>*>(Q.o1);
-      const auto* m2 = static_cast<const BVHModel<OBBRSS<S>>*>(Q.o2);
-      S a[12], b[12];
-      Q.tf1.toPose12(a);
-      Q.tf2.toPose12(b);
-      uint32_t count = 0;
-      int32_t pair_ids[2] = {-1, -1};
-      detail::check(fclb_bvh_collide_batch_host(m1->handle(), m2->handle(), a, b, 1, detail::scalarType<S>(), &req,
-                                                &count, pair_ids),
-                    "fclb_bvh_collide_batch_host");
-      for (uint32_t c = 0; c < count && c < 1; c++) {
-        Contact<S> ct;
-        ct.o1 = Q.o1;
-        ct.o2 = Q.o2;
-        ct.b1 = pair_ids[0];
-        ct.b2 = pair_ids[1];
-        results[q].addContact(ct);
-      }
-    } else if (!Q.o1->isShape() && Q.o2->isShape()) {
-      // scene geometry vs shape: BVHShapeCollider / HeightMapShapeCollide / OcTree2ShapeCollide
-      // (collision_func_matrix-inl.h:754-762, 815-823, 774-782)
-      const fclb_shape rec = Q.o2->shapeRecord();
-      fclb_handle one = 0;
-      detail::check(fclb_shapes_upload(&rec, 1, &one), "fclb_shapes_upload");
-      S a[12], b[12];
-      Q.tf1.toPose12(a);
-      Q.tf2.toPose12(b);
-      const uint32_t sid = 0;
-      uint32_t count = 0;
-      int64_t b1 = -1;
-      const int st = detail::scalarType<S>();
-      if (Q.o1->getNodeType() == BV_OBBRSS) {
-        int32_t tri = -1;
-        detail::check(fclb_bvh_shape_collide_batch_host(static_cast<const BVHModel<OBBRSS<S>>*>(Q.o1)->handle(), one, &sid, a,
-                                                        b, 1, st, &req, &count, &tri),
-                      "fclb_bvh_shape_collide_batch_host");
-        b1 = tri;
-      } else if (Q.o1->getNodeType() == GEOM_HEIGHTMAP) {
-        int32_t pix = -1;
-        detail::check(fclb_heightmap_shape_collide_batch_host(static_cast<const HeightMapCollisionGeometry<S>*>(Q.o1)->handle(),
-                                                              one, &sid, a, b, 1, st, &req, &count, &pix),
-                      "fclb_heightmap_shape_collide_batch_host");
-        b1 = pix;
-      } else {
-        detail::check(fclb_octree_shape_collide_batch_host(static_cast<const Octree2CollisionGeometry<S>*>(Q.o1)->handle(), one,
-                                                           &sid, a, b, 1, st, &req, &count, &b1),
-                      "fclb_octree_shape_collide_batch_host");
-      }
-      fclb_release(one);
-      // the device reports the count and ONE contact id; further contacts repeat that id
-      for (uint32_t c = 0; c < count; c++) {
-        Contact<S> ct;
-        ct.o1 = Q.o1;
-        ct.o2 = Q.o2;
-        ct.b1 = intptr_t(b1);
-        results[q].addContact(ct);
-        if (c >= 63) break;
+        auto rank = [](int k) { return k == FCLB_SCENE_HEIGHTMAP ? 0 : (k == FCLB_SCENE_OCTREE ? 1 : 2); };
+        const bool swap = rank(k1) > rank(k2);
+        const CollisionGeometry<S>* a = swap ? Q.o2 : Q.o1;
+        const CollisionGeometry<S>* b = swap ? Q.o1 : Q.o2;
+        groupOf(2, detail::sceneKind(a), detail::sceneHandle(a), detail::sceneKind(b), detail::sceneHandle(b), swap, a, b).q.push_back(q);
       }
     } else {
-      std::cerr << "Warning: collision function between node type " << Q.o1->getNodeType() << " and node type "
-                << Q.o2->getNodeType() << " is not supported" << std::endl;
+      const CollisionGeometry<S>* scene = s1 ? Q.o2 : Q.o1;
+      groupOf(1, detail::sceneKind(scene), detail::sceneHandle(scene), -1, 0, false, scene, nullptr).q.push_back(q);
     }
   }
-  if (pairs.empty()) return;
-  fclb_handle table = 0;
-  detail::check(fclb_shapes_upload(shapes.data(), uint32_t(shapes.size()), &table), "fclb_shapes_upload");
-  const uint32_t keep = req.max_contacts < 4 ? req.max_contacts : 4;
-  std::vector<S> contacts(pairs.size() * keep * 9);
-  std::vector<uint32_t> counts(pairs.size());
-  detail::check(fclb_collide_batch_host(table, pairs.data(), p1.data(), p2.data(), pairs.size(),
-                                        detail::scalarType<S>(), &req, keep, contacts.data(), counts.data()),
-                "fclb_collide_batch_host");
-  fclb_release(table);
-  for (std::size_t i = 0; i < pairs.size(); i++) {
-    const std::size_t q = shape_q[i];
-    for (uint32_t c = 0; c < counts[i] && c < keep; c++) {
-      const S* r = &contacts[(i * keep + c) * 9];
-      Contact<S> ct;
-      ct.o1 = queries[q].o1;
-      ct.o2 = queries[q].o2;
-      ct.normal = Vector3<S>(r[2], r[3], r[4]);
-      ct.pos = Vector3<S>(r[5], r[6], r[7]);
-      ct.penetration_depth = r[8];
-      results[q].addContact(ct);
+
+  // ---- shape-shape: one table (one entry per distinct geometry object), one call ---------------------------------
+  std::vector<fclb_shape> shapes;
+  std::vector<const CollisionGeometry<S>*> shape_objs;
+  auto shapeIndex = [&](const CollisionGeometry<S>* g) -> uint32_t {
+    for (std::size_t i = shape_objs.size(); i-- > 0 && shape_objs.size() - i <= 64;)  // recent objects first (bounded scan)
+      if (shape_objs[i] == g) return uint32_t(i);
+    shape_objs.push_back(g);
+    shapes.push_back(g->shapeRecord());
+    return uint32_t(shapes.size() - 1);
+  };
+  if (!shape_q.empty()) {
+    const std::size_t m = shape_q.size();
+    std::vector<fclb_pair> pairs(m);
+    std::vector<S> p1(12 * m), p2(12 * m);
+    for (std::size_t i = 0; i < m; i++) {
+      const auto& Q = queries[shape_q[i]];
+      pairs[i] = fclb_pair{shapeIndex(Q.o1), shapeIndex(Q.o2)};
+      Q.tf1.toPose12(&p1[12 * i]);
+      Q.tf2.toPose12(&p2[12 * i]);
+    }
+    fclb_handle table = 0;
+    detail::check(fclb_shapes_upload(shapes.data(), uint32_t(shapes.size()), &table), "fclb_shapes_upload");
+    const uint32_t keep = req.max_contacts < 4 ? req.max_contacts : 4;  // a shape pair has at most four contacts (boxBox2)
+    std::vector<S> contacts(m * keep * 9);
+    std::vector<uint32_t> counts(m, 0);
+    if (detail::batchOk(fclb_collide_batch_host(table, pairs.data(), p1.data(), p2.data(), m, st, &req, keep, contacts.data(),
+                                                counts.data()),
+                        "fclb_collide_batch_host")) {
+      for (std::size_t i = 0; i < m; i++) {
+        const std::size_t q = shape_q[i];
+        for (uint32_t c = 0; c < counts[i] && c < keep; c++) {
+          const S* r = &contacts[(i * keep + c) * 9];
+          Contact<S> ct;
+          ct.o1 = queries[q].o1;
+          ct.o2 = queries[q].o2;
+          if (pen) {
+            ct.normal = Vector3<S>(r[2], r[3], r[4]);
+            ct.pos = Vector3<S>(r[5], r[6], r[7]);
+            ct.penetration_depth = r[8];
+          }
+          results[q].addContact(ct);
+        }
+      }
+    }
+    fclb_release(table);
+    shapes.clear();
+    shape_objs.clear();
+  }
+
+  // ---- one call per (geometry, geometry) group --------------------------------------------------------------------
+  for (const Group& g : groups) {
+    const std::size_t m = g.q.size();
+    std::vector<S> pa(12 * m), pb(12 * m);
+    std::vector<uint32_t> counts(m, 0);
+    uint32_t keep = detail::firstKeep(req.max_contacts);
+    if (g.kind == 0) {  // BVHModel<OBBRSS> x BVHModel<OBBRSS> (collision_func_matrix-inl.h:544-572)
+      for (std::size_t i = 0; i < m; i++) {
+        queries[g.q[i]].tf1.toPose12(&pa[12 * i]);
+        queries[g.q[i]].tf2.toPose12(&pb[12 * i]);
+      }
+      if (mpr_pen) {
+        std::cerr << "Warning: MPR penetration modes between two meshes are not supported by the device path" << std::endl;
+        continue;
+      }
+      std::vector<int32_t> ids;
+      std::vector<S> rec;
+      bool ok = true;
+      for (int pass = 0; pass < 2 && ok; pass++) {
+        ids.assign(m * keep * 2, -1);
+        rec.assign(m * keep * 7, S(0));
+        ok = detail::batchOk(fclb_bvh_collide_contacts_batch_host(g.h1, g.h2, pa.data(), pb.data(), m, st, &req, keep, counts.data(),
+                                                                  ids.data(), rec.data()),
+                             "fclb_bvh_collide_contacts_batch_host");
+        const uint32_t most = ok && m ? *std::max_element(counts.begin(), counts.end()) : 0;
+        if (most <= keep) break;
+        keep = most;
+      }
+      if (!ok) continue;
+      for (std::size_t i = 0; i < m; i++)
+        for (uint32_t c = 0; c < counts[i] && c < keep; c++) {
+          Contact<S> ct;
+          ct.o1 = g.g1;
+          ct.o2 = g.g2;
+          ct.b1 = ids[(i * keep + c) * 2];
+          ct.b2 = ids[(i * keep + c) * 2 + 1];
+          if (pen) {
+            const S* r = &rec[(i * keep + c) * 7];
+            ct.normal = Vector3<S>(r[0], r[1], r[2]);
+            ct.pos = Vector3<S>(r[3], r[4], r[5]);
+            ct.penetration_depth = r[6];
+          }
+          results[g.q[i]].addContact(ct);
+        }
+    } else if (g.kind == 1) {  // scene geometry x shape, either argument order
+      std::vector<uint32_t> sid(m);
+      for (std::size_t i = 0; i < m; i++) {
+        const auto& Q = queries[g.q[i]];
+        const bool shape_first = Q.o1->isShape();
+        const CollisionGeometry<S>* shape = shape_first ? Q.o1 : Q.o2;
+        sid[i] = shapeIndex(shape);
+        (shape_first ? Q.tf2 : Q.tf1).toPose12(&pa[12 * i]);
+        (shape_first ? Q.tf1 : Q.tf2).toPose12(&pb[12 * i]);
+      }
+      fclb_handle table = 0;
+      detail::check(fclb_shapes_upload(shapes.data(), uint32_t(shapes.size()), &table), "fclb_shapes_upload");
+      std::vector<int64_t> b1;
+      std::vector<S> rec;
+      bool ok = true;
+      for (int pass = 0; pass < 2 && ok; pass++) {
+        b1.assign(m * keep, -1);
+        rec.assign(m * keep * 7, S(0));
+        ok = detail::batchOk(fclb_scene_shape_contacts_batch_host(g.k1, g.h1, table, sid.data(), pa.data(), pb.data(), m, st, &req,
+                                                                  keep, counts.data(), b1.data(), rec.data()),
+                             "fclb_scene_shape_contacts_batch_host");
+        const uint32_t most = ok && m ? *std::max_element(counts.begin(), counts.end()) : 0;
+        if (most <= keep) break;
+        keep = most;
+      }
+      fclb_release(table);
+      shapes.clear();
+      shape_objs.clear();
+      if (!ok) continue;
+      for (std::size_t i = 0; i < m; i++) {
+        const auto& Q = queries[g.q[i]];
+        const CollisionGeometry<S>* shape = Q.o1->isShape() ? Q.o1 : Q.o2;
+        for (uint32_t c = 0; c < counts[i] && c < keep; c++) {
+          Contact<S> ct;
+          ct.o1 = g.g1;  // the mesh / heightmap / octree, whatever the argument order (see above)
+          ct.o2 = shape;
+          ct.b1 = intptr_t(b1[i * keep + c]);
+          if (pen) {
+            const S* r = &rec[(i * keep + c) * 7];
+            ct.normal = Vector3<S>(r[0], r[1], r[2]);
+            ct.pos = Vector3<S>(r[3], r[4], r[5]);
+            ct.penetration_depth = r[6];
+          }
+          results[g.q[i]].addContact(ct);
+        }
+      }
+    } else {  // heightmap / octree against heightmap / octree / mesh (collision_func_matrix-inl.h:794-812, 835-856)
+      for (std::size_t i = 0; i < m; i++) {
+        const auto& Q = queries[g.q[i]];
+        (g.swapped ? Q.tf2 : Q.tf1).toPose12(&pa[12 * i]);
+        (g.swapped ? Q.tf1 : Q.tf2).toPose12(&pb[12 * i]);
+      }
+      // collisionPenetrationMPR (collision_penetration-inl.h:189-252).  In the canonical argument order the records are
+      // the reference's bit for bit.  With swapped arguments the reference runs MPR on (leaf of o1, leaf of o2) for the
+      // escape direction of o2; here the canonical pair is evaluated for the opposite direction and the normal negated
+      // -- the same penetration up to MPR's argument order, not bit-identical.
+      fclb_request r2 = req;
+      if (mpr_pen && g.swapped)
+        for (int k = 0; k < 3; k++) r2.dir[k] = -req.dir[k];
+      std::vector<int64_t> b1, b2;
+      std::vector<S> rec;
+      bool ok = true;
+      for (int pass = 0; pass < 2 && ok; pass++) {
+        b1.assign(m * keep, -1);
+        b2.assign(m * keep, -1);
+        if (pen) {
+          rec.assign(m * keep * 7, S(0));
+          ok = detail::batchOk(fclb_scene_pair_contacts_batch_host(g.k1, g.h1, g.k2, g.h2, pa.data(), pb.data(), m, st, &r2, keep,
+                                                                   counts.data(), b1.data(), b2.data(), rec.data()),
+                               "fclb_scene_pair_contacts_batch_host");
+        } else {
+          ok = detail::batchOk(fclb_scene_pair_collide_batch_host(g.k1, g.h1, g.k2, g.h2, pa.data(), pb.data(), m, st, &req, keep,
+                                                                  counts.data(), b1.data(), b2.data()),
+                               "fclb_scene_pair_collide_batch_host");
+        }
+        const uint32_t most = ok && m ? *std::max_element(counts.begin(), counts.end()) : 0;
+        if (most <= keep) break;
+        keep = most;
+      }
+      if (!ok) continue;
+      for (std::size_t i = 0; i < m; i++)
+        for (uint32_t c = 0; c < counts[i] && c < keep; c++) {
+          Contact<S> ct;
+          ct.o1 = g.g1;
+          ct.o2 = g.g2;
+          ct.b1 = intptr_t(b1[i * keep + c]);
+          ct.b2 = intptr_t(b2[i * keep + c]);
+          if (pen) {
+            const S* r = &rec[(i * keep + c) * 7];
+            const S sgn = (mpr_pen && g.swapped) ? S(-1) : S(1);
+            ct.normal = Vector3<S>(sgn * r[0], sgn * r[1], sgn * r[2]);
+            ct.pos = Vector3<S>(r[3], r[4], r[5]);
+            ct.penetration_depth = r[6];
+          }
+          results[g.q[i]].addContact(ct);
+        }
     }
   }
+}
+
+// CollisionResult with a UserContactProcessFunctor (narrowphase/collision_result.h:56-73): callbacks cannot cross the C ABI,
+// so the device returns the contacts and the functor runs on the host over them, in order -- keep decides whether the
+// contact is stored, stop ends the query.  The functor sees up to `device_contacts` contacts per query.
+template <typename S>
+using UserContactProcessFunctor = std::function<void(const Contact<S>& contact, bool& keep, bool& stop)>;
+template <typename S>
+void collideBatch(const std::vector<CollisionQuery<S>>& queries, const CollisionRequest<S>& request,
+                  const UserContactProcessFunctor<S>& functor, std::vector<CollisionResult<S>>& results,
+                  std::size_t device_contacts = 1024) {
+  CollisionRequest<S> wide = request;
+  wide.setMaxContactCount(std::max(request.maxNumContacts(), device_contacts));
+  std::vector<CollisionResult<S>> all;
+  collideBatch(queries, wide, all);
+  results.assign(queries.size(), CollisionResult<S>());
+  for (std::size_t q = 0; q < queries.size(); q++)
+    for (const auto& c : all[q].getContacts()) {
+      bool keep = true, stop = false;
+      functor(c, keep, stop);
+      if (keep) results[q].addContact(c);
+      // terminationConditionSatisfied (collision_result-inl.h:84-98)
+      if (stop || (results[q].numContacts() > 0 && results[q].numContacts() >= request.maxNumContacts())) break;
+    }
 }
 
 // fcl::collide, single pair (reference narrowphase/collision_interface-inl.h:13-32)

@@ -213,7 +213,8 @@ int fclb_bvh_collide_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* 
 int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
                                int scalar_type, const fclb_request* req, uint32_t* out_counts,
                                int32_t* out_first_pair);
-/* fcl::collide(BVH, BVH) with request.useDefaultPenetration(): contact generation of
+/* fcl::collide(BVH, BVH) with every kept contact.  Boolean request: ids only (b1, b2 of every kept triangle pair, the
+ * contact records are not written).  request.useDefaultPenetration(): contact generation of
  * Intersect::intersect_Triangle (traversal/collision/intersect-inl.h:795-888) through trianglePairIntersect
  * (shape_pair_intersect-inl.h:201-252): up to two contact points per intersecting triangle pair, sharing one
  * normal and depth.
@@ -237,8 +238,9 @@ int fclb_bvh_last_visit_counts(uint64_t* n_bv, uint64_t* n_leaf);
  * (collision_func_matrix-inl.h:390-408 -> OrientedNodeBVHSolver::MeshShapeIntersect,
  * traversal/collision/bvh_solver-inl.h:8-72; leaf = GJKSolver::shapeTriangleIntersect,
  * gjk_solver-inl.h:540-600).  shape_ids[q] indexes the shape table.
- * request.penetration_mode must be FCLB_PEN_DISABLED (boolean / counting collide):
- *   out_counts[q]    = result.numContacts() = min(#triangles hit, max_contacts)
+ * out_counts[q] = result.numContacts() for ANY request mode (with a penetration request the contacts are generated
+ * as in fclb_scene_shape_contacts_batch and dropped); for a boolean request:
+ *   out_counts[q]    = min(#triangles hit, max_contacts)
  *   out_first_tri[q] = b1 of ONE hit triangle or -1 (optional; not necessarily the DFS-first) */
 int fclb_bvh_shape_collide_batch_host(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids,
                                       const void* poses_mesh, const void* poses_shape, size_t n, int scalar_type,
@@ -274,7 +276,7 @@ int fclb_heightmap_build_host(const double* points, size_t n_points, double reso
                               uint32_t half_shape_x, uint32_t half_shape_y, int scalar_type, uint16_t* heights_mm);
 /* fcl::collide(HeightMapCollisionGeometry, tf_hm, Shape, tf_shape, request, result) per query
  * (collision_func_matrix-inl.h:99-118 -> heightmap_solver_traverse-inl.h:23-118; leaf = pixel Box vs Shape,
- * heightmap_solver_leaf-inl.h:10-31).  request.penetration_mode must be FCLB_PEN_DISABLED:
+ * heightmap_solver_leaf-inl.h:10-31).  Any request mode (see fclb_bvh_shape_collide_batch); boolean request:
  *   out_counts[q]      = result.numContacts() = min(#pixel boxes hit, max_contacts)
  *   out_first_pixel[q] = b1 = encodePixel (x << 16 | y, heightmap_types.h:53-58) of ONE hit pixel or -1 */
 int fclb_heightmap_shape_collide_batch_host(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
@@ -291,7 +293,7 @@ int fclb_heightmap_shape_collide_batch_dev(fclb_handle hm, fclb_handle shapes, c
  *   pruned_or_null   OctreePruneInfo::prune_internal_nodes as bytes, or NULL
  *   root_aabb        root_bv(): min xyz, max xyz;  num_layers = n_layers()
  * fcl::collide(Octree2CollisionGeometry, tf_octree, Shape, tf_shape, request, result) per query
- * (collision_func_matrix-inl.h:253-273 -> octree2_solver_traverse-inl.h:12-136); penetration must be disabled:
+ * (collision_func_matrix-inl.h:253-273 -> octree2_solver_traverse-inl.h:12-136); any request mode; boolean request:
  *   out_counts[q]     = result.numContacts() = min(#voxel boxes hit, max_contacts)
  *   out_first_node[q] = b1 = encodeOctree2Node (octree2_solver_leaf-inl.h:10-20) of ONE hit box or -1 */
 int fclb_octree_upload(const uint32_t* inner_children, const uint8_t* inner_full, uint32_t n_inner,
@@ -336,16 +338,23 @@ int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes,
 int fclb_octree_shape_collide_batch_dev(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
                                         const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
                                         const fclb_request* req, uint32_t* out_counts, int64_t* out_first_node);
-/* ---- MPR penetration for scene contacts ---------------------------------------------------
- * fcl::collide(scene geometry, tf1, Shape, tf2, request, result) with request.useDirectedPenetration(dir) or
- * useIncrementalMinimumDistancePenetration(dir) (collision_interface-inl.h:22-30 -> collisionPenetrationMPR,
- * narrowphase/collision_penetration-inl.h:189-252): the boolean traversal, then computePenetrationMPR
- * between the contact's leaf geometry (the mesh triangle / the pixel or voxel Box, :34-95) and the shape.
+/* ---- every contact of a scene-vs-shape query ---------------------------------------------------
+ * fcl::collide(scene geometry, tf1, Shape, tf2, request, result) with ALL its contacts, for every request mode:
+ *   FCLB_PEN_DISABLED            the boolean traversal; ids only (the contact records are zero)
+ *   FCLB_PEN_DEFAULT_GJK_EPA     request.useDefaultPenetration(): each leaf runs the shape-pair leaf stage with contacts --
+ *                                ShapeSimplexIntersect -> shapeTriangleIntersect (GJK + EPA; Sphere: closed form) for a
+ *                                mesh triangle (bvh_solver-inl.h:52-66, gjk_solver-inl.h:479-581), ShapeIntersect<Box, Shape>
+ *                                (boxBox2 / closed forms / GJK + EPA) for a pixel or voxel box
+ *                                (heightmap_solver_leaf-inl.h:10-31, octree2_solver_leaf-inl.h:22-44)
+ *   FCLB_PEN_DIRECTED / _INCREMENTAL_MIN  collisionPenetrationMPR (narrowphase/collision_penetration-inl.h:189-252):
+ *                                the boolean traversal, then computePenetrationMPR between the contact's leaf geometry
+ *                                (the mesh triangle / the pixel or voxel Box, :34-95) and the shape
  *   out_counts[q]              = result.numContacts() (<= request.max_contacts)
  *   out_b1[q*max_keep + k]     = Contact::b1 of the k-th stored contact (triangle id, encodePixel,
  *                                encodeOctree2Node) or -1; k < min(count, max_keep)
  *   out_contacts[(q*max_keep + k)*7 ..] = normal[3], pos[3], penetration_depth (depth -1: MPR reported failure)
- * Which contacts are the first max_keep follows the device traversal order, not the reference's DFS order. */
+ * Which contacts are the first max_keep follows the device (MPR modes: traversal order; DefaultGJK_EPA: ascending b1),
+ * not the reference's DFS order. */
 #define FCLB_SCENE_BVH 0
 #define FCLB_SCENE_HEIGHTMAP 1
 #define FCLB_SCENE_OCTREE 2
@@ -381,10 +390,12 @@ int fclb_scene_pair_collide_batch_host(int kind1, fclb_handle scene1, int kind2,
 int fclb_scene_pair_collide_batch_dev(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                                       const void* poses2, size_t n, int scalar_type, const fclb_request* req,
                                       uint32_t max_keep, uint32_t* out_counts, int64_t* out_b1, int64_t* out_b2);
-/* The same pairs with request.useDirectedPenetration(dir) / useIncrementalMinimumDistancePenetration(dir)
+/* The same pairs with a penetration request.  useDirectedPenetration(dir) / useIncrementalMinimumDistancePenetration(dir)
  * (collisionPenetrationMPR, narrowphase/collision_penetration-inl.h:189-252): the boolean traversal, then
  * computePenetrationMPR between the two leaf geometries of each contact (:34-95: a Box of Contact::o1_bv / o2_bv in
- * the pose of its heightmap / octree, the mesh triangle b2 in the mesh pose).
+ * the pose of its heightmap / octree, the mesh triangle b2 in the mesh pose).  useDefaultPenetration(): every leaf pair
+ * runs ShapeIntersect<Box, Box> (boxBox2, up to four contacts) or ShapeSimplexIntersect<Box> (GJK + EPA) on the two leaf
+ * geometries (heightmap_solver_leaf-inl.h:56-88, octree2_solver_leaf-inl.h:46-404, incl. the reverse_tree12 cases).
  *   out_contacts[(q*max_keep + k)*7 ..] = normal[3], pos[3], penetration_depth (depth -1: MPR reported failure) */
 int fclb_scene_pair_contacts_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                                         const void* poses2, size_t n, int scalar_type, const fclb_request* req,

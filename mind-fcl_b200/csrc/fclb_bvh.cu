@@ -477,8 +477,10 @@ static int bvh_upload_one(const void* obb, const int32_t* first_child, int n_nod
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
   for (int i = 0; i < n_nodes; i++) {
     const int fc = first_child[i];
-    if (fc >= 0 ? (fc + 1 >= n_nodes || fc == 0) : (-(fc + 1) >= n_tris))
-      return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_upload: child / primitive index out of range");
+    // children follow their parent in the array (BVHModel::recursiveBuildTree numbers them that way,
+    // BVH_model-inl.h:470-560): anything else could be a cycle or a shared subtree
+    if (fc >= 0 ? (fc + 1 >= n_nodes || fc <= i) : (-(fc + 1) >= n_tris))
+      return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_upload: child / primitive index out of range (children must follow their parent)");
   }
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
@@ -655,7 +657,11 @@ static int bvh_collide_batch_host_one(fclb_handle bvh1, fclb_handle bvh2, const 
     rc = fclb_bvh_collide_batch_dev(bvh1, bvh2, base + o_p1 + b0 * 12 * ss, base + o_p2 + b0 * 12 * ss, m, scalar_type, req,
                                     reinterpret_cast<uint32_t*>(base + o_cnt) + b0,
                                     out_first_pair ? reinterpret_cast<int32_t*>(base + o_fp) + 2 * b0 : nullptr);
-    if (rc) return rc;
+    if (rc) {  // drain the queued copies before the caller gets its buffers back
+      cudaStreamSynchronize(e.copy_in);
+      cudaStreamSynchronize(e.copy_out);
+      return rc;
+    }
     visits[0] += g_last_stats[0];
     visits[1] += g_last_stats[1];
     FCLB_CUDA(cudaEventRecord(e.ev_done[c], e.compute));

@@ -110,8 +110,9 @@ static int runCollide(fclb_handle shapes, const fclb_pair* pairs, const void* po
 // table that holds the caller's shapes followed by one Box / Triangle entry per leaf; contacts: 4 x 9 S per item.
 int collideLeafBatch(Engine& e, void* d_table, const void* tris, const fclb_pair* pairs, const void* poses1,
                      const void* poses2, size_t m, int scalar_type, const fclb_request* req, void* contacts,
-                     uint32_t* counts) {
+                     uint32_t* counts, uint32_t n_table) {
   ShapeTable tmp;
+  tmp.n = n_table;
   tmp.d_shapes[scalar_type == FCLB_F32 ? 0 : 1] = d_table;
   fclb_request r = *req;
   r.max_contacts = 4;  // every contact of the leaf (boxBox2 makes up to four); the scatter pass clips to the free space

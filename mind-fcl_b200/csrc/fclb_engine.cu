@@ -113,13 +113,17 @@ int shardOverDevices(size_t n, const std::function<int(size_t, size_t)>& fn) {
 // ---------------------------------------------------------------------------
 // bucketing kernels
 template <typename S>
-__global__ void classifyKernel(const ShapeD<S>* __restrict__ shapes, const fclb_pair* __restrict__ pairs, size_t n,
-                               uint8_t* __restrict__ kind, uint32_t* __restrict__ hist) {
+__global__ void classifyKernel(const ShapeD<S>* __restrict__ shapes, uint32_t n_shapes, const fclb_pair* __restrict__ pairs,
+                               size_t n, uint8_t* __restrict__ kind, uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[kNumKinds];
   for (int i = threadIdx.x; i < kNumKinds; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   for (size_t q = blockIdx.x * size_t(blockDim.x) + threadIdx.x; q < n; q += size_t(gridDim.x) * blockDim.x) {
-    const fclb_pair p = pairs[q];
+    fclb_pair p = pairs[q];
+    if (p.shape1 >= n_shapes || p.shape2 >= n_shapes) {  // reported as FCLB_ERR_BAD_ARG; never read out of bounds
+      atomicAdd(&hist[2 * kNumKinds], 1u);
+      p.shape1 = p.shape2 = 0;
+    }
     const int k = (shapes[p.shape1].type & 7) * kNumTypes + (shapes[p.shape2].type & 7);
     kind[q] = uint8_t(k);
     atomicAdd(&sh[k], 1u);
@@ -290,15 +294,16 @@ int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs, size_t
   const int st = sizeof(S) == 4 ? 0 : 1;
   int rc = ensureScratch(e, n);
   if (rc) return rc;
-  FCLB_CUDA(cudaMemsetAsync(e.d_hist, 0, 2 * kNumKinds * sizeof(uint32_t), e.compute));
+  FCLB_CUDA(cudaMemsetAsync(e.d_hist, 0, (2 * kNumKinds + 1) * sizeof(uint32_t), e.compute));
   const int block = 256;
   const int grid = int(std::min<size_t>((n + block - 1) / block, size_t(e.sms) * 8));
-  classifyKernel<S><<<grid, block, 0, e.compute>>>(static_cast<const ShapeD<S>*>(t->d_shapes[st]), d_pairs, n, e.d_kind,
+  classifyKernel<S><<<grid, block, 0, e.compute>>>(static_cast<const ShapeD<S>*>(t->d_shapes[st]), t->n, d_pairs, n, e.d_kind,
                                                    e.d_hist);
   scanKernel<<<1, 32, 0, e.compute>>>(e.d_hist);
   e.launches += 2;
-  FCLB_CUDA(cudaMemcpyAsync(e.h_hist, e.d_hist, 2 * kNumKinds * sizeof(uint32_t), cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(e.h_hist, e.d_hist, (2 * kNumKinds + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  if (e.h_hist[2 * kNumKinds]) return fail(FCLB_ERR_BAD_ARG, "a pair names a shape index outside the shape table");
   *uniform_kind = -1;
   for (int k = 0; k < kNumKinds; k++) {
     counts[k] = e.h_hist[k];
@@ -508,8 +513,8 @@ static int initEngine(Engine& e, int device) {
   FCLB_CUDA(cudaEventCreate(&e.ev1));
   FCLB_CUDA(cudaEventCreate(&e.ev_call0));
   for (int i = 0; i <= Engine::kMaxRec; i++) FCLB_CUDA(cudaEventCreate(&e.rec_ev[i]));
-  FCLB_CUDA(cudaMalloc(&e.d_hist, 2 * kNumKinds * sizeof(uint32_t)));
-  FCLB_CUDA(cudaHostAlloc(&e.h_hist, 2 * kNumKinds * sizeof(uint32_t), cudaHostAllocPortable));
+  FCLB_CUDA(cudaMalloc(&e.d_hist, (2 * kNumKinds + 1) * sizeof(uint32_t)));
+  FCLB_CUDA(cudaHostAlloc(&e.h_hist, (2 * kNumKinds + 1) * sizeof(uint32_t), cudaHostAllocPortable));
   e.ready = true;
   return FCLB_OK;
 }
@@ -945,7 +950,11 @@ static int distance_batch_host_one(fclb_handle shapes, const fclb_pair* pairs, c
                                  out_dist ? base + o_dist + b0 * ss : nullptr, out_p1 ? base + o_w1 + b0 * 3 * ss : nullptr,
                                  out_p2 ? base + o_w2 + b0 * 3 * ss : nullptr,
                                  out_ok ? reinterpret_cast<uint8_t*>(base + o_ok) + b0 : nullptr);
-    if (rc) return rc;
+    if (rc) {  // drain the queued copies before the caller gets its buffers back
+      cudaStreamSynchronize(e.copy_in);
+      cudaStreamSynchronize(e.copy_out);
+      return rc;
+    }
     FCLB_CUDA(cudaEventRecord(e.ev_done[c], e.compute));
     FCLB_CUDA(cudaStreamWaitEvent(e.copy_out, e.ev_done[c], 0));
     if (out_dist)

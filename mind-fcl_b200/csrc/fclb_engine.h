@@ -141,6 +141,6 @@ int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs, size_t
 // leaf batch of the scene contact path: see fclb_collide_api.cu
 int collideLeafBatch(Engine& e, void* d_table, const void* tris, const fclb_pair* pairs, const void* poses1,
                      const void* poses2, size_t m, int scalar_type, const fclb_request* req, void* contacts,
-                     uint32_t* counts);
+                     uint32_t* counts, uint32_t n_table);
 
 }  // namespace fclb

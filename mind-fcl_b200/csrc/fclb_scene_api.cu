@@ -2,6 +2,7 @@
 //   fclb_bvh_shape_collide_batch_{dev,host}   mesh (BVHModel<OBBRSS>) vs convex shape
 // Kernels: fclb_bvh_shape_impl.cuh (instantiated in fclb_bvh_shape_f32/f64.cu).
 #include <cmath>
+#include <cstring>
 
 #include <cub/cub.cuh>
 
@@ -278,6 +279,11 @@ static int sceneContactsDev(Engine& e, int kind, fclb_handle scene, const ShapeT
     return fail(FCLB_ERR_BAD_ARG, "unknown scene kind");
   }
   if (rc) return rc;
+  if (req->penetration_mode == FCLB_PEN_DISABLED) {  // boolean request: ids only, no contact geometry
+    FCLB_CUDA(cudaMemsetAsync(contacts, 0, n * size_t(max_keep) * 7 * sizeof(S), e.compute));
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+    return FCLB_OK;
+  }
   const SolverParams sp = solverParams(st, req->binary_tol, req->gjk_max_iter, req->distance_tol, req->epa_max_faces,
                                        req->epa_max_iter, true);
   ScenePenArgs p{};
@@ -648,7 +654,8 @@ static int sceneGjkContactsDev(Engine& e, int kind1, fclb_handle scene1, int kin
       leafBatchBuildKernel<S><<<g, 256, 0, e.compute>>>(b);
       e.launches += 2;
       FCLB_CUDA(cudaGetLastError());
-      rc = collideLeafBatch(e, d_table.p, tris, d_pairs.as<fclb_pair>(), d_p1.p, d_p2.p, m, st, req, d_lc.p, d_lcnt.as<uint32_t>());
+      rc = collideLeafBatch(e, d_table.p, tris, d_pairs.as<fclb_pair>(), d_p1.p, d_p2.p, m, st, req, d_lc.p, d_lcnt.as<uint32_t>(),
+                             uint32_t(n_user + 2 * m));
       if (rc) return rc;
       size_t scan_bytes = 0;
       FCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_qcount.as<uint32_t>(), d_qoff.as<uint32_t>(), int(nc), e.compute));
@@ -1253,27 +1260,34 @@ int fclb_octree_build_host(const double* points, size_t n_points, double resolut
                            uint32_t* n_inner, uint8_t* leaf_bits, uint32_t leaf_capacity, uint32_t* n_leaf,
                            double* root_aabb, int* num_layers) {
   if (!n_inner || !n_leaf) return fail(FCLB_ERR_BAD_ARG, "fclb_octree_build_host: bad argument");
-  // The size query keeps its tree for the data call that follows on the same thread with the same arguments (and the
-  // same first / middle / last point), so the usual two-call sequence inserts the points once.
+  // The size query keeps its tree for the data call that follows on the same thread with the same arguments AND the
+  // same point data (a 64-bit hash of the whole buffer: a cloud rewritten in place, or another buffer at the same
+  // address, is a different call), so the usual two-call sequence inserts the points once.
   struct Stash {
     bool valid = false;
     const double* points = nullptr;
     size_t n = 0;
-    double res = 0, probe[9] = {0};
+    double res = 0;
+    uint64_t hash = 0;
     uint32_t half = 0;
     int st = 0;
     fclb::hostbuild::OctreeHost tree;
   };
   static thread_local Stash stash;
+  auto hashPoints = [&]() {
+    uint64_t h = 0x9e3779b97f4a7c15ull ^ uint64_t(n_points);
+    const size_t words = n_points * 3;
+    for (size_t i = 0; i < words; i++) {
+      uint64_t w;
+      std::memcpy(&w, points + i, 8);
+      h = (h ^ w) * 0xff51afd7ed558ccdull;
+      h ^= h >> 29;
+    }
+    return h;
+  };
   auto sameCall = [&]() {
-    if (!stash.valid || stash.points != points || stash.n != n_points || stash.res != resolution ||
-        stash.half != bottom_half_shape || stash.st != scalar_type)
-      return false;
-    const size_t at[3] = {0, n_points / 2, n_points ? n_points - 1 : 0};
-    for (int k = 0; k < 3 && n_points; k++)
-      for (int c = 0; c < 3; c++)
-        if (stash.probe[3 * k + c] != points[3 * at[k] + c]) return false;
-    return true;
+    return stash.valid && stash.points == points && stash.n == n_points && stash.res == resolution &&
+           stash.half == bottom_half_shape && stash.st == scalar_type && stash.hash == hashPoints();
   };
   const bool size_query = !inner_children || !inner_full || !leaf_bits;
   fclb::hostbuild::OctreeHost local;
@@ -1290,9 +1304,7 @@ int fclb_octree_build_host(const double* points, size_t n_points, double resolut
       stash.res = resolution;
       stash.half = bottom_half_shape;
       stash.st = scalar_type;
-      const size_t at[3] = {0, n_points / 2, n_points ? n_points - 1 : 0};
-      for (int k = 0; k < 3 && n_points; k++)
-        for (int c = 0; c < 3; c++) stash.probe[3 * k + c] = points[3 * at[k] + c];
+      stash.hash = hashPoints();
     }
   }
   struct Drop {  // a data call consumes the stash whatever its outcome
@@ -1475,8 +1487,8 @@ int fclb_scene_shape_contacts_batch_dev(int scene_kind, fclb_handle scene, fclb_
   if (!t) return fail(FCLB_ERR_BAD_ARG, "unknown shape table handle");
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
   if (!req || !out_counts || !out_b1 || !out_contacts || max_keep == 0) return fail(FCLB_ERR_BAD_ARG, "null output / max_keep == 0");
-  if (req->penetration_mode == FCLB_PEN_DISABLED || req->penetration_mode > FCLB_PEN_INCREMENTAL_MIN)
-    return fail(FCLB_ERR_BAD_ARG, "fclb_scene_shape_contacts_batch: the request must enable a penetration mode");
+  if (req->penetration_mode > FCLB_PEN_INCREMENTAL_MIN)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_scene_shape_contacts_batch: unknown penetration mode");
   if (n == 0) return FCLB_OK;
   if (!shape_ids || !poses_scene || !poses_shape) return fail(FCLB_ERR_BAD_ARG, "null input array");
   return sceneShapeContactsAny(e, scene_kind, scene, t, shape_ids, poses_scene, poses_shape, n, scalar_type, req, max_keep,

@@ -2,8 +2,11 @@
 // (test/test_fcl_geometric_shapes.cpp shapeDistance_*, test_fcl_collision_penetration.cpp):
 // known answers through fcl::collide / fcl::distance of include/fcl_b200/fcl.h.
 // Built and run by tests/test_host_api_gpu.py on the GPU box.
+#include <array>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
+#include <vector>
 
 #include "fcl_b200/fcl.h"
 
@@ -243,7 +246,168 @@ void runScene() {
   }
 }
 
-int main() {
+// Batched dispatch of scene queries (include/fcl_b200/fcl.h collideBatch): ONE C-ABI call per (geometry, geometry)
+// group, the reference's argument swaps, contact records for penetration requests, the host-side contact functor.
+template <typename S>
+void runBatch() {
+  using namespace fcl;
+  Transform3<S> I = Transform3<S>::Identity();
+  auto at = [](S x, S y, S z) {
+    Transform3<S> t;
+    t.translation() = Vector3<S>(x, y, z);
+    return t;
+  };
+  BVHModel<OBBRSS<S>> floor;
+  floor.beginModel();
+  floor.addSubModel({Vector3<S>(-1, -1, 0), Vector3<S>(1, -1, 0), Vector3<S>(1, 1, 0), Vector3<S>(-1, 1, 0)}, {{0, 1, 2}, {0, 2, 3}});
+  floor.endModel();
+  Sphere<S> ball(S(0.25));
+  Box<S> brick(S(0.3), S(0.2), S(0.1));
+  // 10k mesh-shape queries, alternating argument order and shape: exactly one batched call
+  std::vector<CollisionQuery<S>> qs;
+  for (int i = 0; i < 10000; i++) {
+    const S x = S(-0.9) + S(1.8) * S(i % 100) / S(99), z = S(-0.1) + S(0.5) * S(i / 100) / S(99);
+    const CollisionGeometry<S>* shape = (i % 3) ? static_cast<const CollisionGeometry<S>*>(&ball) : &brick;
+    if (i & 1)
+      qs.push_back({shape, at(x, S(0.3), z), &floor, I});  // (Shape, BVH): collide() swaps (collision-inl.h:91-100)
+    else
+      qs.push_back({&floor, I, shape, at(x, S(0.3), z)});
+  }
+  CollisionRequest<S> all(100);
+  std::vector<CollisionResult<S>> res;
+  const std::size_t calls0 = detail::abiBatchCalls();
+  collideBatch(qs, all, res);
+  EXPECT_TRUE(detail::abiBatchCalls() - calls0 == 1);
+  std::size_t hits = 0;
+  for (std::size_t i = 0; i < qs.size(); i++) {
+    hits += res[i].numContacts();
+    for (const auto& c : res[i].getContacts()) EXPECT_TRUE(c.o1 == &floor && (c.b1 == 0 || c.b1 == 1));
+    // a query and its argument-swapped twin (same pose, one row later in the grid is a different pose: compare with single calls)
+  }
+  EXPECT_TRUE(hits > 1000);
+  for (int i : {0, 1, 2, 3, 4999, 5000, 9999}) {  // the batch equals the single calls, whichever argument order
+    CollisionResult<S> one;
+    const auto& Q = qs[std::size_t(i)];
+    const bool shape_first = Q.o1->isShape();
+    const std::size_t n1 = shape_first ? collide<S>(Q.o2, Q.tf2, Q.o1, Q.tf1, all, one) : collide<S>(Q.o1, Q.tf1, Q.o2, Q.tf2, all, one);
+    EXPECT_TRUE(n1 == res[std::size_t(i)].numContacts());
+  }
+  // penetration request on the same batch: contact records are filled, still one call
+  CollisionRequest<S> pen(100);
+  pen.useDefaultPenetration();
+  std::vector<CollisionResult<S>> pres;
+  const std::size_t calls1 = detail::abiBatchCalls();
+  collideBatch(qs, pen, pres);
+  EXPECT_TRUE(detail::abiBatchCalls() - calls1 == 1);
+  std::size_t with_depth = 0;
+  for (const auto& r : pres)
+    for (const auto& c : r.getContacts()) {
+      const S nn = c.normal[0] * c.normal[0] + c.normal[1] * c.normal[1] + c.normal[2] * c.normal[2];
+      EXPECT_TRUE(std::fabs(nn - 1) < S(1e-4));
+      with_depth++;
+    }
+  EXPECT_TRUE(with_depth > 1000);
+  // heightmap / octree with the shape first (ShapeHeightMapCollide, ShapeOcTree2Collide): o1 is still the scene geometry
+  auto map = std::make_shared<heightmap::LayeredHeightMap<S>>(S(0.1), uint16_t(8));
+  map->updateHeightsByPointGenerationFunctor([](int i, S& x, S& y, S& z) { x = S(0.05) + S(0.1) * S(i % 4); y = S(0.05); z = S(0.5); }, 4);
+  HeightMapCollisionGeometry<S> hm(map);
+  auto tree = std::make_shared<octree2::Octree<S>>(S(0.1), std::uint16_t(8));
+  tree->rebuildTree([](int i, S& x, S& y, S& z) { x = S(0.05) + S(0.1) * S(i % 4); y = S(0.05); z = S(0.05); }, 4);
+  Octree2CollisionGeometry<S> oct(tree);
+  Box<S> bar(S(0.5), S(0.06), S(0.06));
+  CollisionResult<S> a, b, c, d;
+  EXPECT_TRUE(collide<S>(&hm, I, &bar, at(S(0.2), S(0.05), S(0.3)), all, a) == 4);
+  EXPECT_TRUE(collide<S>(&bar, at(S(0.2), S(0.05), S(0.3)), &hm, I, all, b) == 4 && b.getContact(0).o1 == &hm && b.getContact(0).o2 == &bar);
+  EXPECT_TRUE(collide<S>(&oct, I, &bar, at(S(0.2), S(0.05), S(0.05)), all, c) == 4);
+  EXPECT_TRUE(collide<S>(&bar, at(S(0.2), S(0.05), S(0.05)), &oct, I, all, d) == 4 && d.getContact(0).o1 == &oct);
+  // DefaultGJK_EPA against a heightmap: box-box leaves make up to four contacts each (boxBox2), none is refused
+  CollisionResult<S> e;
+  EXPECT_TRUE(collide<S>(&hm, I, &bar, at(S(0.2), S(0.05), S(0.3)), pen, e) >= 4);
+  for (const auto& ct : e.getContacts()) EXPECT_TRUE(ct.penetration_depth >= 0 && (ct.b1 & 0xffff) == 8);
+  // UserContactProcessFunctor on the host: keep only contacts on triangle 1, stop after two
+  std::vector<CollisionQuery<S>> one_q{{&floor, I, &ball, at(0, 0, S(0.1))}};
+  std::vector<CollisionResult<S>> fr;
+  int seen = 0;
+  collideBatch<S>(one_q, all, [&](const Contact<S>& ct, bool& keep, bool& stop) { seen++; keep = ct.b1 == 1; stop = false; }, fr);
+  EXPECT_TRUE(seen == 2 && fr[0].numContacts() == 1 && fr[0].getContact(0).b1 == 1);
+}
+
+// Contacts against the reference: the Python test writes a mesh, a box, poses and the contacts fcl::collide of the
+// reference (oracle/_ref) reports with useDefaultPenetration(); every contact must come back bit for bit.
+static void runReferenceFile(const char* path) {
+  using namespace fcl;
+  using S = double;
+  std::FILE* f = std::fopen(path, "rb");
+  if (!f) {
+    std::printf("FAILED: cannot open %s\n", path);
+    failures++;
+    return;
+  }
+  int32_t hdr[4];
+  EXPECT_TRUE(std::fread(hdr, 4, 4, f) == 4);
+  const int nv = hdr[0], nt = hdr[1], nq = hdr[2], keep = hdr[3];
+  std::vector<double> verts(3 * std::size_t(nv)), side(3), pm(12 * std::size_t(nq)), ps(12 * std::size_t(nq)),
+      contacts(7 * std::size_t(nq) * keep);
+  std::vector<int32_t> tris(3 * std::size_t(nt));
+  std::vector<uint32_t> counts(nq);
+  std::vector<int64_t> b1(std::size_t(nq) * keep);
+  bool ok = std::fread(verts.data(), 8, verts.size(), f) == verts.size() && std::fread(tris.data(), 4, tris.size(), f) == tris.size() &&
+            std::fread(side.data(), 8, 3, f) == 3 && std::fread(pm.data(), 8, pm.size(), f) == pm.size() &&
+            std::fread(ps.data(), 8, ps.size(), f) == ps.size() && std::fread(counts.data(), 4, counts.size(), f) == counts.size() &&
+            std::fread(b1.data(), 8, b1.size(), f) == b1.size() && std::fread(contacts.data(), 8, contacts.size(), f) == contacts.size();
+  std::fclose(f);
+  EXPECT_TRUE(ok);
+  if (!ok) return;
+  BVHModel<OBBRSS<S>> mesh;
+  std::vector<Vector3<S>> pts;
+  std::vector<std::array<int, 3>> tri;
+  for (int i = 0; i < nv; i++) pts.emplace_back(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]);
+  for (int i = 0; i < nt; i++) tri.push_back({tris[3 * i], tris[3 * i + 1], tris[3 * i + 2]});
+  mesh.beginModel();
+  mesh.addSubModel(pts, tri);
+  mesh.endModel();
+  Box<S> box(side[0], side[1], side[2]);
+  auto pose = [](const double* p) {
+    Transform3<S> t;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) t.linear()(i, j) = p[3 * i + j];
+    for (int i = 0; i < 3; i++) t.translation()[i] = p[9 + i];
+    return t;
+  };
+  std::vector<CollisionQuery<S>> qs;
+  for (int q = 0; q < nq; q++) {
+    if (q & 1)
+      qs.push_back({&box, pose(&ps[12 * q]), &mesh, pose(&pm[12 * q])});
+    else
+      qs.push_back({&mesh, pose(&pm[12 * q]), &box, pose(&ps[12 * q])});
+  }
+  CollisionRequest<S> req{std::size_t(keep)};
+  req.useDefaultPenetration();
+  std::vector<CollisionResult<S>> res;
+  collideBatch(qs, req, res);
+  std::size_t compared = 0, bad = 0;
+  for (int q = 0; q < nq; q++) {
+    EXPECT_TRUE(res[q].numContacts() == counts[q]);
+    if (res[q].numContacts() != counts[q]) continue;
+    for (const auto& c : res[q].getContacts()) {
+      bool found = false;
+      for (uint32_t k = 0; k < counts[q] && !found; k++) {
+        const double* r = &contacts[(std::size_t(q) * keep + k) * 7];
+        found = b1[std::size_t(q) * keep + k] == int64_t(c.b1) && r[0] == c.normal[0] && r[1] == c.normal[1] && r[2] == c.normal[2] &&
+                r[3] == c.pos[0] && r[4] == c.pos[1] && r[5] == c.pos[2] && r[6] == c.penetration_depth;
+      }
+      compared++;
+      if (!found) bad++;
+    }
+  }
+  std::printf("reference file: %d queries, %zu contacts compared, %zu not bit-identical\n", nq, compared, bad);
+  EXPECT_TRUE(compared > 0 && bad == 0);
+}
+
+int main(int argc, char** argv) {
+  runBatch<float>();
+  runBatch<double>();
+  if (argc > 1) runReferenceFile(argv[1]);
   run<float>();
   run<double>();
   runScene<float>();

@@ -77,7 +77,9 @@ def test_mesh_shape_edge_cases(fclb, ref_oracle):
     assert not c.any()
     with pytest.raises(fclb.FclbError):
         fclb.bvh_shape_collide_batch_host(bvh, table, ids + 5, pm, ps, st, fclb.make_request())
-    with pytest.raises(fclb.FclbError):  # penetration modes are not on the device for meshes
-        fclb.bvh_shape_collide_batch_host(bvh, table, ids, pm, ps, st, fclb.make_request(penetration_mode=1))
+    # a penetration request through the counting entry point: numContacts of the contact path (tests/test_scene_gjk_epa_gpu.py)
+    c_pen, _ = fclb.bvh_shape_collide_batch_host(bvh, table, ids, pm, ps, st, fclb.make_request(max_contacts=2**31 - 1, penetration_mode=1))
+    c_bool, _ = fclb.bvh_shape_collide_batch_host(bvh, table, ids, pm, ps, st, fclb.make_request(max_contacts=2**31 - 1))
+    assert ((c_pen > 0) == (c_bool > 0)).mean() > 0.99
     fclb.release(table)
     fclb.bvh_release(bvh)

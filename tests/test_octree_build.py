@@ -203,3 +203,32 @@ def test_golden():
         assert np.array_equal(c_ch, g[f"rebuilt_children_{tag}"]) and np.array_equal(c_full, g[f"rebuilt_full_{tag}"])
         assert np.array_equal(c_leaf, g[f"rebuilt_leaf_{tag}"])
         assert pr.any() and len(c_full) < len(full)
+
+
+def test_size_query_tree_is_not_reused_for_other_points():
+    """The size query keeps its tree for the data call only when the point DATA is the same (full hash): a cloud rewritten in
+    place between the two calls must be built afresh (round-1 advisor finding: 3 probe points let a stale tree through)."""
+    import ctypes as C
+
+    import fclb200 as fclb
+
+    rng = np.random.Generator(np.random.PCG64(99))
+    pts = np.ascontiguousarray(rng.uniform(-0.6, 0.6, size=(500, 3)))
+    lib = fclb.load()
+    ni, nl, layers = C.c_uint32(), C.c_uint32(), C.c_int()
+    root = np.zeros(6, np.float64)
+    P = fclb._ptr
+    rc = lib.fclb_octree_build_host(P(pts), len(pts), 0.01, 64, fclb.F64, None, None, 0, C.byref(ni), None, 0, C.byref(nl), P(root),
+                                    C.byref(layers))
+    assert rc == 5
+    pts[1:499] *= 0.5  # same address, same first / middle-ish / last point pattern is not enough: data changed
+    cap_i, cap_l = 4096, 4096
+    ch = np.zeros((cap_i, 8), np.uint32)
+    full = np.zeros(cap_i, np.uint8)
+    leaf = np.zeros(cap_l, np.uint8)
+    rc = lib.fclb_octree_build_host(P(pts), len(pts), 0.01, 64, fclb.F64, P(ch), P(full), cap_i, C.byref(ni), P(leaf), cap_l,
+                                    C.byref(nl), P(root), C.byref(layers))
+    assert rc == 0
+    fresh = fclb.octree_build_host(pts.copy(), 0.01, 64, fclb.F64)
+    assert ni.value == len(fresh[1]) and nl.value == len(fresh[2])
+    assert np.array_equal(ch[:ni.value], fresh[0]) and np.array_equal(leaf[:nl.value], fresh[2])

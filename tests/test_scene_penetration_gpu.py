@@ -74,8 +74,11 @@ def test_scene_contact_penetration(fclb, ref_oracle, dtype):
         req = fclb.make_request(max_contacts=2, penetration_mode=2, direction=(0.0, 0.0, 1.0))
         c2, _, _ = fclb.scene_shape_contacts_batch_host(kind, handle, table, ids, ps, psh, st, req, 4)
         assert np.array_equal(c2, np.minimum(e_counts, 2))
-    with pytest.raises(fclb.FclbError):
-        fclb.scene_shape_contacts_batch_host(fclb.SCENE_BVH, bvh, table, ids, p_mesh, p_shape, st, fclb.make_request(), 4)
+    # a boolean request through the same entry point: the ids of every kept contact, no contact geometry
+    cb, bb, ctb = fclb.scene_shape_contacts_batch_host(fclb.SCENE_BVH, bvh, table, ids, p_mesh, p_shape, st,
+                                                       fclb.make_request(max_contacts=2**31 - 1), KEEP)
+    eb, _ = ref_oracle.mesh_shape_collide_batch(mid, rshapes, ids, p_mesh, p_shape, threads=8, max_contacts=2**31 - 1)
+    assert np.array_equal(cb, eb) and not ctb.any() and (bb[cb > 0, 0] >= 0).all()
     fclb.bvh_release(bvh)
     fclb.heightmap_release(hm)
     fclb.octree_release(octree)
