@@ -385,7 +385,16 @@ __global__ void __launch_bounds__(kBlock) convexBoolKernel(BatchView b, S tol, i
 #else
 #define FCLB_EPA_BOUNDS_TAIL
 #endif
-constexpr int kEpaThreads = 128;
+#ifndef FCLB_EPA_THREADS
+#define FCLB_EPA_THREADS 128
+#endif
+// FCLB_EPA_CTA_SYNC: every warp of the CTA starts its lockstep iteration together (one __syncthreads per iteration), so
+// the instruction lines one warp fetches are the ones the others need next -- the kernel is instruction-fetch bound
+// (ncu: 9.8 issue slots lost to stall_no_instruction per issued instruction with free-running warps).
+#ifndef FCLB_EPA_CTA_SYNC
+#define FCLB_EPA_CTA_SYNC 0
+#endif
+constexpr int kEpaThreads = FCLB_EPA_THREADS;
 template <typename S>
 __host__ __device__ inline size_t epaTileBytes(size_t poly_bytes) {
   return (poly_bytes + 24 * sizeof(S) + 16 + 127) / 128 * 128 + 32;
@@ -503,8 +512,12 @@ __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(Ba
       else
         finished = true;
     }
+#if FCLB_EPA_CTA_SYNC
+    if (!__syncthreads_or(active || finished || more)) break;
+#else
     if (!__any_sync(0xffffffffu, active || finished || more)) break;
     __syncwarp();
+#endif
     if (active) {
       es = epa.step(max_iter, tol, depth, p0, p1);
       if (es != epa.kEpaContinue) {

@@ -14,7 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfclb200.so")
+LIB_PATH = os.environ.get("FCLB_LIB") or os.path.join(_HERE, "libfclb200.so")  # FCLB_LIB: an experimental build (profiles/scripts)
 
 F32, F64 = 0, 1
 BOX, SPHERE, ELLIPSOID, CAPSULE, CONE, CYLINDER, CONVEX = range(7)
