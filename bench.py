@@ -144,8 +144,13 @@ class Workload:
         self.np_dtype = np.float32 if dtype_name == "f32" else np.float64
         self.sb = 4 if dtype_name == "f32" else 8
         self.convex = None
+        self.qt1 = self.qt2 = None
         if name == "c2":
-            self.shapes, self.pairs, self.poses1, self.poses2 = scenes.config_c2(n, self.np_dtype, seed=2001 + seed)
+            # poses are generated as unit quaternion + translation (FCLB_POSE_QT7, 28 B in float) and expanded with Eigen's
+            # toRotationMatrix arithmetic: the 12-S arrays are what the device-resident path, the 12-S host path and the
+            # CPU reference read; the QT7 arrays are what the headline host path sends over PCIe
+            self.shapes, self.pairs, self.qt1, self.qt2 = scenes.config_c2_qt(n, self.np_dtype, seed=2001 + seed)
+            self.poses1, self.poses2 = scenes.expand_qt7(self.qt1), scenes.expand_qt7(self.qt2)
             self.kind = "distance"
         elif name in ("c1a", "c1b"):
             self.shapes, self.pairs, self.poses1, self.poses2 = scenes.config_c1_boxes(n, self.np_dtype, seed=1001 + seed)
@@ -161,6 +166,8 @@ class Workload:
 
     # -- bytes ---------------------------------------------------------------
     def h2d_bytes(self):
+        if self.qt1 is not None:
+            return self.n * (14 * self.sb + 8)
         return self.n * (24 * self.sb + 8)
 
     def d2h_bytes(self):
@@ -193,6 +200,8 @@ class Workload:
         self.h_pairs = pin(self.pairs.view(np.uint32).reshape(n, 2).view(np.int32))
         self.h_p1, self.h_p2 = pin(self.poses1), pin(self.poses2)
         self.d_pairs, self.d_p1, self.d_p2 = self.h_pairs.to(dev), self.h_p1.to(dev), self.h_p2.to(dev)
+        if self.qt1 is not None:
+            self.h_q1, self.h_q2 = pin(self.qt1), pin(self.qt2)
 
         def bufs(device, pinned):
             mk = (lambda *sh, dtype: torch.empty(*sh, dtype=dtype).pin_memory()) if pinned else \
@@ -214,6 +223,8 @@ class Workload:
         P = f._ptr
         if self.kind == "distance":
             fn = lib.fclb_distance_batch_host if host else lib.fclb_distance_batch_dev
+            if host and self.qt1 is not None and not getattr(self, "force_pose12", False):
+                fn, p1, p2 = lib.fclb_distance_batch_qt_host, self.h_q1, self.h_q2
             f.check(fn(self.table, P(pairs), P(p1), P(p2), self.n, self.st, 0.0, 0, P(out[0]), P(out[1]), P(out[2]), P(out[3])))
         elif self.kind == "collide":
             fn = lib.fclb_collide_batch_host if host else lib.fclb_collide_batch_dev
@@ -268,6 +279,7 @@ class Workload:
     def teardown(self):
         self.fclb.release(self.table)
         self.d_out = self.h_out = self.d_pairs = self.d_p1 = self.d_p2 = self.h_pairs = self.h_p1 = self.h_p2 = None
+        self.h_q1 = self.h_q2 = None
 
 
 class MeshWorkload:
@@ -860,6 +872,11 @@ def measure(ctx, name, queries, dtype, steps, warmup, seed, with_cpu, with_model
     clocks = clock_sampler.stop(*win) if clock_sampler else None
     e2e_steps = max(3, steps // 2)
     ms_e2e, _, _, _ = ctx.timed(wl.step_host, e2e_steps, 3)
+    ms_e2e12 = None
+    if getattr(wl, "qt1", None) is not None:  # the same host call with 12-S poses, for comparison
+        wl.force_pose12 = True
+        ms_e2e12, _, _, _ = ctx.timed(wl.step_host, e2e_steps, 2)
+        wl.force_pose12 = False
     n = wl.n  # (C5 learns its candidate-pair count from the run itself)
     total_n = ctx.sum_over_ranks(n)
     value = total_n * steps / (ms_dev * 1e-3)
@@ -887,6 +904,11 @@ def measure(ctx, name, queries, dtype, steps, warmup, seed, with_cpu, with_model
                 "h2d_gbs": wl.h2d_bytes() / (ms_e2e / e2e_steps) / 1e6, "d2h_gbs": wl.d2h_bytes() / (ms_e2e / e2e_steps) / 1e6},
         "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
     }
+    if ms_e2e12 is not None:
+        rec["e2e"]["pose_encoding"] = ("FCLB_POSE_QT7: unit quaternion + translation, 7 S per pose, expanded on the device with "
+                                       "Eigen's toRotationMatrix arithmetic (results bit-identical to the 12-S call)")
+        rec["e2e"]["with_12S_poses"] = {"value": total_n * e2e_steps / (ms_e2e12 * 1e-3), "ms_per_step": ms_e2e12 / e2e_steps,
+                                        "h2d_bytes_per_step": n * (24 * wl.sb + 8)}
     if hasattr(wl, "extra"):
         rec["config"].update(wl.extra())
     if with_cpu and ctx.rank == 0:

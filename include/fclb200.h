@@ -139,6 +139,20 @@ int fclb_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const vo
                             size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
                             void* out_p1, void* out_p2, uint8_t* out_ok);
 
+/* Compact pose encoding for the host link.  FCLB_POSE_QT7: 7 S per pose = unit quaternion x, y, z, w then translation
+ * x, y, z (28 B instead of 48 B in float).  The device expands it with the arithmetic of Eigen's
+ * QuaternionBase::toRotationMatrix in S, i.e. to exactly the tf.linear() of a Transform3<S> built from that quaternion
+ * (mind-fcl's tests build their poses that way: test/test_fcl_utility.h generateRandomTransform), then runs the same
+ * kernels: results are those of the 12-S entry point on the expanded poses, bit for bit.  The PCIe-bound host path moves
+ * 64 B instead of 104 B per query. */
+#define FCLB_POSE_RT12 0
+#define FCLB_POSE_QT7 1
+int fclb_distance_batch_qt_host(fclb_handle shapes, const fclb_pair* pairs, const void* qt_poses1, const void* qt_poses2,
+                                size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
+                                void* out_p1, void* out_p2, uint8_t* out_ok);
+/* the expansion alone (DEVICE pointers): n poses of 7 S -> n poses of 12 S */
+int fclb_expand_poses_dev(const void* qt_poses, size_t n, int scalar_type, void* out_poses12);
+
 /* Signed distance == detail::GJKSolver<S>::shapeSignedDistance (gjk_solver-inl.h:810-880): always the generic
  * GJK (no closed forms), GJKSolver's default tolerances / limits (:1121-1130);
  *   separated:   ok = 1, dist > 0, witness points as above
@@ -197,6 +211,14 @@ int fclb_bvh_build(const double* verts, int n_verts, const int32_t* tris, int n_
  * 15*(2*n_tris-1) S / (2*n_tris-1) / 9*n_tris S entries; *n_nodes = nodes written. */
 int fclb_bvh_build_host(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type, void* obb,
                         int32_t* first_child, void* tri_verts, int* n_nodes);
+/* Refit ON THE DEVICE: BVHModel::beginReplaceModel / replaceSubModel / endReplaceModel(refit = true, bottomup = false)
+ * (geometry/bvh/BVH_model-inl.h:318-375 -> refitTreeTopDown :624-637): the vertices move, the topology stays, every node
+ * is fitted again from the triangles it covers with the OBBRSS fitter of build time (detail/BV_fitter-inl.h:324-345).
+ * tri_verts: the new 9 S per triangle, indexed by primitive id (HOST pointer for _host, DEVICE pointer for _dev).  One
+ * warp per node; the node OBBs equal the reference's refit bit for bit.  The step before the path for a deforming /
+ * re-perceived scene mesh: no host rebuild, no re-upload of the tree. */
+int fclb_bvh_refit_host(fclb_handle bvh, const void* tri_verts, int n_tris);
+int fclb_bvh_refit_dev(fclb_handle bvh, const void* tri_verts, int n_tris);
 int fclb_bvh_info(fclb_handle bvh, int* n_nodes, int* n_tris, int* scalar_type);
 /* copies the tree back in the fclb_bvh_upload layout (any pointer may be NULL) */
 int fclb_bvh_export(fclb_handle bvh, void* obb, int32_t* first_child, void* tri_verts);

@@ -432,6 +432,159 @@ static int bvhCollideDev(Engine& e, const BvhDev* m1, const BvhDev* m2, const vo
   return FCLB_OK;
 }
 
+// ---- refit: BVHModel::refitTree(bottomup = false) (BVH_model-inl.h:624-637) ---------------------------------------
+// Every node is fitted again from the primitives it covers with the tree's topology unchanged: the OBBRSS fitter of
+// build time (detail/BV_fitter-inl.h:324-345: covariance of the triangle corners -> eigen_old -> axisFromEigen ->
+// extent and centre along the axes).  One warp per node.  The nine covariance sums are sequential in the reference
+// (math/geometry-inl.h:713-780) and their rounding depends on that order, so lane k < 9 accumulates sum k over the
+// node's primitives in primitive_indices_ order; the 3x3 Jacobi solve runs on every lane; the extents are minima /
+// maxima (order-free) and are reduced across the lanes.  Results are bit-identical to the reference's refit.
+template <typename S>
+__global__ void __launch_bounds__(256) bvhRefitKernel(S* __restrict__ nodes, const S* __restrict__ tris, const int2* __restrict__ range,
+                                                      const int* __restrict__ prim, int n_nodes) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int node = warp; node < n_nodes; node += n_warps) {
+    const int2 r = range[node];
+    // which scalars of a triangle this lane's sum needs: S1[k] (lanes 0-2), c00 c11 c22 c01 c02 c12 (lanes 3-8)
+    const int a = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 0 : lane == 7 ? 0 : 1);
+    const int b = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : lane == 7 ? 2 : 2);
+    S acc = S(0);
+    if (lane < 9) {
+      for (int i = 0; i < r.y; i++) {
+        const S* t = tris + size_t(12) * size_t(prim[r.x + i]);
+        const S p1a = t[a], p2a = t[4 + a], p3a = t[8 + a];
+        if (lane < 3) {
+          acc += (p1a + p2a) + p3a;
+        } else {
+          const S p1b = t[b], p2b = t[4 + b], p3b = t[8 + b];
+          acc += (p1a * p1b + p2a * p2b + p3a * p3b);
+        }
+      }
+    }
+    S sums[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) sums[k] = __shfl_sync(0xffffffffu, acc, k);
+    const int n_points = 3 * r.y;
+    S M[3][3];
+    M[0][0] = sums[3] - sums[0] * sums[0] / n_points;
+    M[1][1] = sums[4] - sums[1] * sums[1] / n_points;
+    M[2][2] = sums[5] - sums[2] * sums[2] / n_points;
+    M[0][1] = sums[6] - sums[0] * sums[1] / n_points;
+    M[1][2] = sums[8] - sums[1] * sums[2] / n_points;
+    M[0][2] = sums[7] - sums[0] * sums[2] / n_points;
+    M[1][0] = M[0][1];
+    M[2][0] = M[0][2];
+    M[2][1] = M[1][2];
+    S d[3] = {0, 0, 0}, vec[3][3];
+    if (!hostbuild::jacobi3<S>(M, d, vec)) {
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) vec[i][j] = (i == j) ? S(1) : S(0);
+    }
+    S ax[9];
+    hostbuild::axesFromEigen<S>(vec, d, ax);
+    const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
+    S mn[3] = {big, big, big}, mx[3] = {-big, -big, -big};
+    for (int i = lane; i < 3 * r.y; i += 32) {  // one triangle corner per lane and round
+      const S* p = tris + size_t(12) * size_t(prim[r.x + i / 3]) + 4 * (i % 3);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const S proj = (ax[0 + k] * p[0] + ax[3 + k] * p[1]) + ax[6 + k] * p[2];
+        if (proj > mx[k]) mx[k] = proj;
+        if (proj < mn[k]) mn[k] = proj;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const S omx = __shfl_xor_sync(0xffffffffu, mx[k], off), omn = __shfl_xor_sync(0xffffffffu, mn[k], off);
+        if (omx > mx[k]) mx[k] = omx;
+        if (omn < mn[k]) mn[k] = omn;
+      }
+    if (lane == 0) {
+      S* o = nodes + size_t(16) * size_t(node);
+#pragma unroll
+      for (int k = 0; k < 9; k++) o[k] = ax[k];
+      S c[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) c[k] = (mx[k] + mn[k]) / 2;
+#pragma unroll
+      for (int rr = 0; rr < 3; rr++) o[9 + rr] = (ax[3 * rr] * c[0] + ax[3 * rr + 1] * c[1]) + ax[3 * rr + 2] * c[2];
+#pragma unroll
+      for (int k = 0; k < 3; k++) o[12 + k] = (mx[k] - mn[k]) / 2;
+    }
+  }
+}
+
+// 9 S per triangle (upload layout) -> the 12 S device records
+template <typename S>
+__global__ void triRepackKernel(const S* __restrict__ in9, int n_tris, S* __restrict__ out12) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < size_t(n_tris) * 3; i += size_t(gridDim.x) * blockDim.x) {
+    const S* p = in9 + 3 * i;
+    S* o = out12 + 4 * i;
+    o[0] = p[0];
+    o[1] = p[1];
+    o[2] = p[2];
+    o[3] = S(0);
+  }
+}
+
+// first_primitive / num_primitives and primitive_indices_ from the child links: an explicit-stack DFS, left child first
+static void deriveRanges(const int32_t* first_child, int n_nodes, int n_tris, std::vector<int2>& range, std::vector<int>& prim) {
+  range.assign(size_t(n_nodes), make_int2(0, 0));
+  prim.clear();
+  prim.reserve(size_t(n_tris));
+  std::vector<std::pair<int, int>> stack;  // (node, state: 0 = enter, 1 = leave)
+  stack.push_back({0, 0});
+  while (!stack.empty()) {
+    const auto top = stack.back();
+    stack.pop_back();
+    const int node = top.first;
+    if (top.second == 1) {
+      range[size_t(node)].y = int(prim.size()) - range[size_t(node)].x;
+      continue;
+    }
+    range[size_t(node)].x = int(prim.size());
+    const int fc = first_child[node];
+    if (fc < 0) {
+      prim.push_back(-(fc + 1));
+      range[size_t(node)].y = 1;
+      continue;
+    }
+    stack.push_back({node, 1});
+    stack.push_back({fc + 1, 0});
+    stack.push_back({fc, 0});
+  }
+}
+
+template <typename S>
+static int refitDev(Engine& e, BvhDev* d, const void* d_tri9) {
+  const int g = int(std::min<size_t>((size_t(d->n_tris) * 3 + 255) / 256, size_t(e.sms) * 8));
+  triRepackKernel<S><<<g, 256, 0, e.compute>>>(static_cast<const S*>(d_tri9), d->n_tris, static_cast<S*>(d->tris));
+  const int warps_per_cta = 8;
+  const int grid = int(std::min<size_t>((size_t(d->n_nodes) + warps_per_cta - 1) / warps_per_cta, size_t(e.sms) * 16));
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  bvhRefitKernel<S><<<grid, warps_per_cta * 32, 0, e.compute>>>(static_cast<S*>(d->nodes), static_cast<const S*>(d->tris), d->d_range,
+                                                               d->d_prim, d->n_nodes);
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  e.launches += 2;
+  FCLB_CUDA(cudaGetLastError());
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.last_ms = e.last_call_ms = ms;
+  // keep the host mirror of fclb_bvh_export current
+  std::vector<S> nodes(size_t(16) * d->n_nodes);
+  FCLB_CUDA(cudaMemcpy(nodes.data(), d->nodes, nodes.size() * sizeof(S), cudaMemcpyDeviceToHost));
+  S* ho = reinterpret_cast<S*>(d->h_obb.data());
+  for (int i = 0; i < d->n_nodes; i++)
+    for (int k = 0; k < 15; k++) ho[size_t(15) * i + k] = nodes[size_t(16) * i + k];
+  FCLB_CUDA(cudaMemcpy(d->h_tri.data(), d_tri9, d->h_tri.size(), cudaMemcpyDeviceToHost));
+  return FCLB_OK;
+}
+
 template <typename S>
 static int uploadBvh(BvhDev* d, const void* obb, const int32_t* first_child, int n_nodes, const void* tri, int n_tris) {
   const S* o = static_cast<const S*>(obb);
@@ -459,6 +612,14 @@ static int uploadBvh(BvhDev* d, const void* obb, const int32_t* first_child, int
   d->h_obb.assign(reinterpret_cast<const unsigned char*>(o), reinterpret_cast<const unsigned char*>(o + size_t(15) * n_nodes));
   d->h_tri.assign(reinterpret_cast<const unsigned char*>(tv), reinterpret_cast<const unsigned char*>(tv + size_t(9) * n_tris));
   d->h_child.assign(first_child, first_child + n_nodes);
+  std::vector<int2> range;
+  std::vector<int> prim;
+  deriveRanges(first_child, n_nodes, n_tris, range, prim);
+  if (int(prim.size()) != n_tris) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_upload: the leaves do not cover every triangle exactly once");
+  FCLB_CUDA(cudaMalloc(&d->d_range, range.size() * sizeof(int2)));
+  FCLB_CUDA(cudaMalloc(&d->d_prim, prim.size() * sizeof(int)));
+  FCLB_CUDA(cudaMemcpy(d->d_range, range.data(), range.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  FCLB_CUDA(cudaMemcpy(d->d_prim, prim.data(), prim.size() * sizeof(int), cudaMemcpyHostToDevice));
   return FCLB_OK;
 }
 
@@ -582,6 +743,8 @@ static int bvh_release_one(fclb_handle h) {
   if (it == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_release: unknown handle");
   cudaFree(it->second->nodes);
   cudaFree(it->second->tris);
+  cudaFree(it->second->d_range);
+  cudaFree(it->second->d_prim);
   delete it->second;
   bvhTable().erase(it);
   return FCLB_OK;
@@ -591,6 +754,34 @@ int fclb_bvh_release(fclb_handle h) {
   if (rc_init_) return rc_init_;
   return forEachDevice([&] { return bvh_release_one(h); });
 }
+
+// BVHModel::beginReplaceModel / replaceSubModel / endReplaceModel(refit = true, bottomup = false): the vertices move, the
+// topology stays; every node OBB is fitted again on the device (bvhRefitKernel).
+static int bvh_refit_one(fclb_handle bvh, const void* tri_verts, int n_tris, int on_device) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  auto it = bvhTable().find(bvh);
+  if (it == bvhTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_refit: unknown BVH handle");
+  BvhDev* d = it->second;
+  if (!tri_verts || n_tris != d->n_tris) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_refit: the replaced model must have the same triangles");
+  const size_t bytes = size_t(9) * n_tris * (d->scalar_type == FCLB_F32 ? 4 : 8);
+  const void* d_in = tri_verts;
+  if (!on_device) {
+    rc = ensureStage(e, bytes);
+    if (rc) return rc;
+    FCLB_CUDA(cudaMemcpyAsync(e.d_stage, tri_verts, bytes, cudaMemcpyHostToDevice, e.compute));
+    d_in = e.d_stage;
+  }
+  return d->scalar_type == FCLB_F32 ? refitDev<float>(e, d, d_in) : refitDev<double>(e, d, d_in);
+}
+int fclb_bvh_refit_host(fclb_handle bvh, const void* tri_verts, int n_tris) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return bvh_refit_one(bvh, tri_verts, n_tris, 0); });
+}
+int fclb_bvh_refit_dev(fclb_handle bvh, const void* tri_verts, int n_tris) { return bvh_refit_one(bvh, tri_verts, n_tris, 1); }
 
 int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
                                int scalar_type, const fclb_request* req, uint32_t* out_counts,

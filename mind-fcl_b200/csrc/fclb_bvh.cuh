@@ -20,6 +20,10 @@ struct BvhDev {
   // host copy in the upload layout (fclb_bvh_export)
   std::vector<unsigned char> h_obb, h_tri;
   std::vector<int32_t> h_child;
+  // refit (fclb_bvh_refit_*): BVNodeBase::first_primitive / num_primitives of every node and primitive_indices_, derived
+  // from the child links (the leaves of a subtree, left to right, are its slice of primitive_indices_)
+  int2* d_range = nullptr;  // [n_nodes] (first, count)
+  int* d_prim = nullptr;    // [n_tris]
 };
 
 std::map<fclb_handle, BvhDev*>& bvhTable();  // fclb_bvh.cu

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -470,6 +471,44 @@ __global__ void __launch_bounds__(256) fmaPeakKernel(S* out, int iters, S a, S b
   if (sum == S(-12345)) out[0] = sum;  // keep the chain alive
 }
 
+// FCLB_POSE_QT7 -> the 12 S pose the kernels read: Eigen's QuaternionBase::toRotationMatrix arithmetic in S (no FMA
+// contraction in this file), so that the expanded pose equals tf.linear() of a Transform3<S> the caller would have built
+// from the same quaternion.  28 B instead of 48 B per pose cross PCIe.
+template <typename S>
+__global__ void expandQt7Kernel(const S* __restrict__ qt, size_t n, S* __restrict__ out) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const S* q = qt + 7 * i;
+    const S x = q[0], y = q[1], z = q[2], w = q[3];
+    const S tx = S(2) * x, ty = S(2) * y, tz = S(2) * z;
+    const S twx = tx * w, twy = ty * w, twz = tz * w;
+    const S txx = tx * x, txy = ty * x, txz = tz * x;
+    const S tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    S* o = out + 12 * i;
+    o[0] = S(1) - (tyy + tzz);
+    o[1] = txy - twz;
+    o[2] = txz + twy;
+    o[3] = txy + twz;
+    o[4] = S(1) - (txx + tzz);
+    o[5] = tyz - twx;
+    o[6] = txz - twy;
+    o[7] = tyz + twx;
+    o[8] = S(1) - (txx + tyy);
+    o[9] = q[4];
+    o[10] = q[5];
+    o[11] = q[6];
+  }
+}
+static int launchExpandQt7(Engine& e, int scalar_type, const void* qt, size_t n, void* out) {
+  const int grid = int(std::min<size_t>((n + 255) / 256, size_t(e.sms) * 16));
+  if (scalar_type == FCLB_F32)
+    expandQt7Kernel<float><<<grid, 256, 0, e.compute>>>(static_cast<const float*>(qt), n, static_cast<float*>(out));
+  else
+    expandQt7Kernel<double><<<grid, 256, 0, e.compute>>>(static_cast<const double*>(qt), n, static_cast<double*>(out));
+  e.launches += 1;
+  FCLB_CUDA(cudaGetLastError());
+  return FCLB_OK;
+}
+
 // L2 read-bandwidth microbenchmark: every CTA streams the same 32 MB buffer (L2-resident after the first pass) with
 // 128-bit ld.global.cg loads -- the ceiling for the traversal kernels, whose node / triangle arrays live in L2.
 __global__ void __launch_bounds__(256) l2ReadKernel(const uint4* __restrict__ buf, size_t n_vec, int passes, uint4* out) {
@@ -515,6 +554,10 @@ static int initEngine(Engine& e, int device) {
   for (int i = 0; i <= Engine::kMaxRec; i++) FCLB_CUDA(cudaEventCreate(&e.rec_ev[i]));
   FCLB_CUDA(cudaMalloc(&e.d_hist, (2 * kNumKinds + 1) * sizeof(uint32_t)));
   FCLB_CUDA(cudaHostAlloc(&e.h_hist, (2 * kNumKinds + 1) * sizeof(uint32_t), cudaHostAllocPortable));
+  if (const char* hc = getenv("FCLB_HOST_CHUNK")) {  // queries per pipeline stage of the *_host entry points (tuning)
+    const long long v = atoll(hc);
+    if (v >= 1024) e.host_chunk = size_t(v);
+  }
   e.ready = true;
   return FCLB_OK;
 }
@@ -895,9 +938,9 @@ int fclb_signed_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, 
   return shardOverDevices(n, [&](size_t b, size_t m_) { return signed_distance_batch_host_one(shapes, offT(pairs, b), offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, offPtr(out_dist, b * ss), offPtr(out_p1, b * 3 * ss), offPtr(out_p2, b * 3 * ss), offT(out_ok, b)); });
 }
 
-static int distance_batch_host_one(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
-                             size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
-                             void* out_p1, void* out_p2, uint8_t* out_ok) {
+static int distance_batch_host_fmt(int pose_format, fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                                   size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
+                                   void* out_p1, void* out_p2, uint8_t* out_ok) {
   int rc = ensureInit();
   if (rc) return rc;
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
@@ -914,10 +957,15 @@ static int distance_batch_host_one(fclb_handle shapes, const fclb_pair* pairs, c
   const size_t o_w1 = alignUp(o_dist + n * ss, 256);
   const size_t o_w2 = alignUp(o_w1 + n * 3 * ss, 256);
   const size_t o_ok = alignUp(o_w2 + n * 3 * ss, 256);
-  const size_t total = alignUp(o_ok + n, 256);
+  const bool qt = pose_format == FCLB_POSE_QT7;
+  const size_t hp = (qt ? 7 : 12) * ss;  // bytes per pose on the host side
+  const size_t o_q1 = alignUp(o_ok + n, 256);
+  const size_t o_q2 = alignUp(o_q1 + (qt ? n * hp : 0), 256);
+  const size_t total = alignUp(o_q2 + (qt ? n * hp : 0), 256);
   rc = ensureStage(e, total);
   if (rc) return rc;
   char* base = static_cast<char*>(e.d_stage);
+  const size_t in1 = qt ? o_q1 : o_p1, in2 = qt ? o_q2 : o_p2;  // where the host poses land
   // Chunked three-stage pipeline: all H2D copies are queued up front on the copy-in
   // stream (one event per chunk); the compute stream waits per chunk, runs the
   // bucketed kernels, and the copy-out stream drains each chunk's results while later
@@ -936,15 +984,18 @@ static int distance_batch_host_one(fclb_handle shapes, const fclb_pair* pairs, c
     const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
     FCLB_CUDA(cudaMemcpyAsync(base + o_pairs + b0 * sizeof(fclb_pair), h_pairs + b0 * sizeof(fclb_pair),
                               m * sizeof(fclb_pair), cudaMemcpyHostToDevice, e.copy_in));
-    FCLB_CUDA(cudaMemcpyAsync(base + o_p1 + b0 * 12 * ss, h_p1 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice,
-                              e.copy_in));
-    FCLB_CUDA(cudaMemcpyAsync(base + o_p2 + b0 * 12 * ss, h_p2 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice,
-                              e.copy_in));
+    FCLB_CUDA(cudaMemcpyAsync(base + in1 + b0 * hp, h_p1 + b0 * hp, m * hp, cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaMemcpyAsync(base + in2 + b0 * hp, h_p2 + b0 * hp, m * hp, cudaMemcpyHostToDevice, e.copy_in));
     FCLB_CUDA(cudaEventRecord(e.ev_in[c], e.copy_in));
   }
   for (int c = 0; c < n_chunks; c++) {
     const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
     FCLB_CUDA(cudaStreamWaitEvent(e.compute, e.ev_in[c], 0));
+    if (qt) {
+      rc = launchExpandQt7(e, scalar_type, base + o_q1 + b0 * hp, m, base + o_p1 + b0 * 12 * ss);
+      if (!rc) rc = launchExpandQt7(e, scalar_type, base + o_q2 + b0 * hp, m, base + o_p2 + b0 * 12 * ss);
+      if (rc) return rc;
+    }
     rc = fclb_distance_batch_dev(shapes, reinterpret_cast<const fclb_pair*>(base + o_pairs) + b0, base + o_p1 + b0 * 12 * ss,
                                  base + o_p2 + b0 * 12 * ss, m, scalar_type, gjk_tol, gjk_max_iter,
                                  out_dist ? base + o_dist + b0 * ss : nullptr, out_p1 ? base + o_w1 + b0 * 3 * ss : nullptr,
@@ -971,13 +1022,44 @@ static int distance_batch_host_one(fclb_handle shapes, const fclb_pair* pairs, c
   FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
   return FCLB_OK;
 }
+static int distance_batch_host_any(int pose_format, fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                                   size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist, void* out_p1,
+                                   void* out_p2, uint8_t* out_ok) {
+  if (engineCount() <= 1)
+    return distance_batch_host_fmt(pose_format, shapes, pairs, poses1, poses2, n, scalar_type, gjk_tol, gjk_max_iter, out_dist, out_p1,
+                                   out_p2, out_ok);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t hp = (pose_format == FCLB_POSE_QT7 ? 7 : 12) * ss;
+  return shardOverDevices(n, [&](size_t b, size_t m_) {
+    return distance_batch_host_fmt(pose_format, shapes, offT(pairs, b), offPtr(poses1, b * hp), offPtr(poses2, b * hp), m_, scalar_type,
+                                   gjk_tol, gjk_max_iter, offPtr(out_dist, b * ss), offPtr(out_p1, b * 3 * ss),
+                                   offPtr(out_p2, b * 3 * ss), offT(out_ok, b));
+  });
+}
 int fclb_distance_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
                              size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
                              void* out_p1, void* out_p2, uint8_t* out_ok) {
-  if (engineCount() <= 1) return distance_batch_host_one(shapes, pairs, poses1, poses2, n, scalar_type, gjk_tol, gjk_max_iter, out_dist, out_p1, out_p2, out_ok);
-  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
-  (void)ss;
-  return shardOverDevices(n, [&](size_t b, size_t m_) { return distance_batch_host_one(shapes, offT(pairs, b), offPtr(poses1, b * 12 * ss), offPtr(poses2, b * 12 * ss), m_, scalar_type, gjk_tol, gjk_max_iter, offPtr(out_dist, b * ss), offPtr(out_p1, b * 3 * ss), offPtr(out_p2, b * 3 * ss), offT(out_ok, b)); });
+  return distance_batch_host_any(FCLB_POSE_RT12, shapes, pairs, poses1, poses2, n, scalar_type, gjk_tol, gjk_max_iter, out_dist, out_p1,
+                                 out_p2, out_ok);
+}
+int fclb_distance_batch_qt_host(fclb_handle shapes, const fclb_pair* pairs, const void* qt_poses1, const void* qt_poses2,
+                                size_t n, int scalar_type, double gjk_tol, uint32_t gjk_max_iter, void* out_dist,
+                                void* out_p1, void* out_p2, uint8_t* out_ok) {
+  return distance_batch_host_any(FCLB_POSE_QT7, shapes, pairs, qt_poses1, qt_poses2, n, scalar_type, gjk_tol, gjk_max_iter, out_dist,
+                                 out_p1, out_p2, out_ok);
+}
+int fclb_expand_poses_dev(const void* qt_poses, size_t n, int scalar_type, void* out_poses12) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!qt_poses || !out_poses12) return fail(FCLB_ERR_BAD_ARG, "fclb_expand_poses_dev: null array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  rc = launchExpandQt7(e, scalar_type, qt_poses, n, out_poses12);
+  if (rc) return rc;
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
 }
 
 // (collide / gjk_epa entry points: fclb_collide_api.cu)

@@ -66,7 +66,7 @@ struct Engine {
   // staging for host entry points
   void* d_stage = nullptr;
   size_t stage_cap = 0;
-  size_t host_chunk = size_t(1) << 20;  // queries per pipeline stage of the *_host entry points
+  size_t host_chunk = size_t(1) << 21;  // queries per pipeline stage of the *_host entry points
   std::vector<cudaEvent_t> ev_in, ev_done;
   std::atomic<uint64_t> launches{0};
   double last_ms = 0.0;       // kernels of the last call (bucketing excluded)

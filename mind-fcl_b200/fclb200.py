@@ -48,7 +48,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
-    "fclb_init_devices", "fclb_num_devices", "fclb_set_device",
+    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
     "fclb_measure_fp_peak", "fclb_measure_l2_bandwidth", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -126,6 +126,9 @@ def load() -> C.CDLL:
     lib.fclb_release.argtypes = [C.c_uint64]
     dist_args = [C.c_uint64, vp, vp, vp, sz, C.c_int, C.c_double, u32, vp, vp, vp, vp]
     lib.fclb_distance_batch_host.argtypes = dist_args
+    if hasattr(lib, "fclb_distance_batch_qt_host"):
+        lib.fclb_distance_batch_qt_host.argtypes = dist_args
+        lib.fclb_expand_poses_dev.argtypes = [vp, sz, C.c_int, vp]
     lib.fclb_distance_batch_dev.argtypes = dist_args
     col_args = [C.c_uint64, vp, vp, vp, sz, C.c_int, vp, u32, vp, vp]
     ge_args = [C.c_uint64, vp, vp, vp, sz, C.c_int, vp, vp, vp, vp]
@@ -286,6 +289,16 @@ def distance_batch_host(table, pairs, poses1, poses2, scalar_type, gjk_tol=0.0, 
     return out
 
 
+def distance_batch_qt_host(table, pairs, qt1, qt2, scalar_type, gjk_tol=0.0, gjk_max_iter=0):
+    """distance_batch_host with FCLB_POSE_QT7 poses (n x 7: quaternion x, y, z, w, translation)"""
+    n = len(pairs)
+    dt = np_dtype(scalar_type)
+    out = DistanceResult(np.zeros(n, dt), np.zeros((n, 3), dt), np.zeros((n, 3), dt), np.zeros(n, np.uint8))
+    check(load().fclb_distance_batch_qt_host(table, _ptr(pairs), _ptr(qt1), _ptr(qt2), n, scalar_type, gjk_tol, gjk_max_iter,
+                                             _ptr(out.dist), _ptr(out.p1), _ptr(out.p2), _ptr(out.ok)))
+    return out
+
+
 def distance_batch_dev(table, pairs, poses1, poses2, n, scalar_type, dist, p1, p2, ok, gjk_tol=0.0, gjk_max_iter=0):
     """Device-buffer call: every array argument is a CUDA tensor or raw device pointer."""
     check(load().fclb_distance_batch_dev(table, _ptr(pairs), _ptr(poses1), _ptr(poses2), n, scalar_type, gjk_tol,
@@ -383,6 +396,13 @@ def bvh_build_host(verts: np.ndarray, tris: np.ndarray, scalar_type):
     check(load().fclb_bvh_build_host(_ptr(v), len(v), _ptr(t), len(t), scalar_type, _ptr(obb), _ptr(fc), _ptr(tv),
                                      C.byref(n)))
     return obb[:n.value], fc[:n.value], tv
+
+
+def bvh_refit_host(h: int, tri_verts: np.ndarray) -> None:
+    """refit on the device from the new triangle corners (n_tris x 9, the tree's scalar type)"""
+    t = np.ascontiguousarray(tri_verts)
+    load().fclb_bvh_refit_host.argtypes = [C.c_uint64, C.c_void_p, C.c_int]
+    check(load().fclb_bvh_refit_host(h, _ptr(t), len(t)))
 
 
 def bvh_export(h: int):

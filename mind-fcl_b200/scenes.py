@@ -64,6 +64,52 @@ def config_c2(n: int, dtype, seed: int = 2001):
     return shapes, make_pairs(s1, s2), poses1, poses2
 
 
+def expand_qt7(qt: np.ndarray) -> np.ndarray:
+    """FCLB_POSE_QT7 (n x 7: unit quaternion x, y, z, w, translation) -> 12-S poses, with the arithmetic of Eigen's
+    QuaternionBase::toRotationMatrix evaluated in the array's own scalar type (what the device does)."""
+    S = qt.dtype.type
+    x, y, z, w = qt[:, 0], qt[:, 1], qt[:, 2], qt[:, 3]
+    tx, ty, tz = S(2) * x, S(2) * y, S(2) * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    out = np.empty((len(qt), 12), qt.dtype)
+    out[:, 0] = S(1) - (tyy + tzz)
+    out[:, 1] = txy - twz
+    out[:, 2] = txz + twy
+    out[:, 3] = txy + twz
+    out[:, 4] = S(1) - (txx + tzz)
+    out[:, 5] = tyz - twx
+    out[:, 6] = txz - twy
+    out[:, 7] = tyz + twx
+    out[:, 8] = S(1) - (txx + tyy)
+    out[:, 9:] = qt[:, 4:]
+    return np.ascontiguousarray(out)
+
+
+def random_poses_qt(rng: np.random.Generator, n: int, extent: float, dtype) -> np.ndarray:
+    """n poses as unit quaternion + translation (uniform rotations, translation uniform in [-extent, extent]^3),
+    rounded ONCE to the scalar type: the shared input of every implementation (expand_qt7 gives the 12-S form)."""
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    out = np.empty((n, 7), np.float64)
+    out[:, :4] = q
+    out[:, 4:] = rng.uniform(-extent, extent, size=(n, 3))
+    return np.ascontiguousarray(out.astype(dtype))
+
+
+def config_c2_qt(n: int, dtype, seed: int = 2001):
+    """C2 with poses in the compact FCLB_POSE_QT7 encoding: (shapes, pairs, qt1, qt2); the 12-S poses every other
+    implementation reads are expand_qt7(qt)."""
+    shapes = [(SPHERE, 0, (0.05,)), (CAPSULE, 0, (0.05, 0.2)), (CYLINDER, 0, (0.05, 0.2)), (BOX, 0, (0.2, 0.2, 0.2))]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    qt1 = random_poses_qt(rng, n, 0.5, dtype)
+    qt2 = random_poses_qt(rng, n, 0.5, dtype)
+    s1 = (np.arange(n) % 3).astype(np.uint32)
+    s2 = np.full(n, 3, np.uint32)
+    return shapes, make_pairs(s1, s2), qt1, qt2
+
+
 def config_c1_boxes(n: int, dtype, seed: int = 1001):
     """C1: Box(2,1,0.5) vs Box(1,1,1), both poses uniform in [-2,2]^3
     (matches test/cvx_collide/test_epa2_with_gjk2.cpp:76-80)."""

@@ -172,6 +172,14 @@ class RefOracle(_Oracle):
         f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         return int(f(_p(verts), len(verts), _p(tris), len(tris)))
 
+    def bvh_refit(self, mesh_id, verts, bottomup=False):
+        """beginReplaceModel / replaceSubModel / endReplaceModel(refit=True, bottomup) on the stored model"""
+        verts = np.ascontiguousarray(verts, np.float64)
+        f = self.fn("bvh_refit")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int]
+        rc = int(f(mesh_id, _p(verts), len(verts), 1 if bottomup else 0))
+        assert rc == 0, rc
+
     def bvh_export(self, mesh_id, dtype):
         st = _st(dtype)
         fn_nodes = self.fn("bvh_num_nodes")

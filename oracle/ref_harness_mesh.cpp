@@ -227,6 +227,23 @@ int fclref_bvh_create(const double* verts, int n_verts, const int* tris, int n_t
   meshes().push_back(r);
   return int(meshes().size()) - 1;
 }
+// BVHModel::beginReplaceModel / replaceSubModel / endReplaceModel(refit = true, bottomup) on BOTH scalar instances:
+// the vertices are replaced (same count, same triangles), the hierarchy keeps its topology
+// (geometry/bvh/BVH_model-inl.h:318-375, refitTree :568-637)
+int fclref_bvh_refit(int id, const double* verts, int n_verts, int bottomup) {
+  auto run = [&](auto* model) {
+    using S = typename std::remove_pointer<decltype(model)>::type::S;
+    std::vector<fcl::Vector3<S>> pts;
+    for (int i = 0; i < n_verts; i++) pts.emplace_back(S(verts[3 * i]), S(verts[3 * i + 1]), S(verts[3 * i + 2]));
+    int rc = model->beginReplaceModel();
+    if (rc == 0) rc = model->replaceSubModel(pts);
+    if (rc == 0) rc = model->endReplaceModel(true, bottomup != 0);
+    return rc;
+  };
+  const int r1 = run(get<float>(id));
+  const int r2 = run(get<double>(id));
+  return r1 ? r1 : r2;
+}
 int fclref_bvh_num_nodes(int id, int scalar_type) {
   return scalar_type == 0 ? get<float>(id)->getNumBVs() : get<double>(id)->getNumBVs();
 }

@@ -143,3 +143,25 @@ def test_signed_distance(fclb, ref_oracle, dtype):
     assert not unexplained, unexplained[:5]
     assert (r.dist[(r.ok == 0)] == -1).all()
     fclb.release(table)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_qt7_pose_encoding(fclb, ref_oracle, dtype):
+    """FCLB_POSE_QT7 host entry point: the device expands quaternion + translation with Eigen's toRotationMatrix arithmetic
+    in S; results equal the 12-S entry point on the expanded poses bit for bit, and the reference's on the same poses."""
+    n = 200_000
+    st = fclb.F32 if dtype == np.float32 else fclb.F64
+    shapes, pairs, qt1, qt2 = scenes.config_c2_qt(n, dtype)
+    p1, p2 = scenes.expand_qt7(qt1), scenes.expand_qt7(qt2)
+    table = fclb.shapes_upload(shapes)
+    a = fclb.distance_batch_qt_host(table, pairs, qt1, qt2, st)
+    b = fclb.distance_batch_host(table, pairs, p1, p2, st)
+    for x, y in ((a.dist, b.dist), (a.p1, b.p1), (a.p2, b.p2), (a.ok, b.ok)):
+        assert np.array_equal(x, y)
+    exp = ref_oracle.distance_batch(shapes, pairs, p1, p2, threads=8)
+    compare_distance(ref_oracle, shapes, pairs, p1, p2, (a.dist, a.p1, a.p2, a.ok), exp, dtype, "C2 200k, QT7 poses",
+                     "test_qt7_pose_encoding")
+    # the rotation the device builds is orthonormal to rounding
+    R = p1[:1000, :9].reshape(-1, 3, 3).astype(np.float64)
+    assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < (1e-5 if dtype == np.float32 else 1e-13)
+    fclb.release(table)
