@@ -953,6 +953,118 @@ std::size_t collide(const CollisionObject<S>* o1, const CollisionObject<S>* o2, 
                  request, result);
 }
 
+// ---- translational continuous collision (narrowphase/continuous_collision.h:15-21), shape pairs -------------------------
+// detail/ccd/ccd_typedef.h, ccd_request.h, ccd_contact.h, ccd_result.h
+template <typename S>
+struct TranslationalDisplacement {
+  Vector3<S> unit_axis_in_shape1;
+  S scalar_displacement{0};
+};
+template <typename S>
+struct Interval {
+  S lower_bound{S(-1)};
+  S upper_bound{S(-1)};
+};
+enum class TimeOfCollisionRequestType { kNotRequested, kBoxApproximate, kOneTocSample };
+template <typename S>
+struct ContinuousCollisionRequest {
+  TimeOfCollisionRequestType request_type{TimeOfCollisionRequestType::kNotRequested};
+  std::size_t num_max_contacts{1};
+  S zero_movement_tolerance{S(1e-4)};
+  S gjk_tolerance{S(1e-6)};
+  int max_gjk_iterations{128};
+};
+template <typename S>
+struct ContinuousCollisionContact {
+  const CollisionGeometry<S>* o1{nullptr};
+  const CollisionGeometry<S>* o2{nullptr};
+  static constexpr std::int64_t NONE = -1;
+  std::int64_t b1{NONE};
+  std::int64_t b2{NONE};
+  Interval<S> toc{};
+};
+template <typename S>
+struct ContinuousCollisionResult {
+  void AddContact(const ContinuousCollisionContact<S>& c) { contacts_.push_back(c); }
+  void ClearContact() { contacts_.clear(); }
+  std::size_t num_contacts() const { return contacts_.size(); }
+  const std::vector<ContinuousCollisionContact<S>>& raw_contacts() const { return contacts_; }
+
+ private:
+  std::vector<ContinuousCollisionContact<S>> contacts_;
+};
+template <typename S>
+struct ContinuousCollisionQuery {
+  const CollisionGeometry<S>* o1;
+  Transform3<S> tf1;
+  TranslationalDisplacement<S> o1_displacement;
+  const CollisionGeometry<S>* o2;
+  Transform3<S> tf2;
+};
+// one C-ABI call for the whole batch; scene geometries are not served by the device path yet (warning, no contact)
+template <typename S>
+void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queries, const ContinuousCollisionRequest<S>& request,
+                           std::vector<ContinuousCollisionResult<S>>& results) {
+  const std::size_t n = queries.size();
+  results.assign(n, ContinuousCollisionResult<S>());
+  if (n == 0 || request.num_max_contacts == 0) return;
+  std::vector<fclb_shape> shapes;
+  std::vector<fclb_pair> pairs;
+  std::vector<S> p1, p2, disp;
+  std::vector<std::size_t> idx;
+  for (std::size_t q = 0; q < n; q++) {
+    const auto& Q = queries[q];
+    if (!Q.o1->isShape() || !Q.o2->isShape()) {
+      std::cerr << "Warning: collision function between node type " << Q.o1->getNodeType() << " and node type " << Q.o2->getNodeType()
+                << " is not supported" << std::endl;
+      continue;
+    }
+    pairs.push_back(fclb_pair{uint32_t(shapes.size()), uint32_t(shapes.size() + 1)});
+    shapes.push_back(Q.o1->shapeRecord());
+    shapes.push_back(Q.o2->shapeRecord());
+    p1.resize(p1.size() + 12);
+    p2.resize(p2.size() + 12);
+    Q.tf1.toPose12(&p1[p1.size() - 12]);
+    Q.tf2.toPose12(&p2[p2.size() - 12]);
+    for (int k = 0; k < 3; k++) disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
+    disp.push_back(Q.o1_displacement.scalar_displacement);
+    idx.push_back(q);
+  }
+  if (pairs.empty()) return;
+  fclb_handle table = 0;
+  detail::check(fclb_shapes_upload(shapes.data(), uint32_t(shapes.size()), &table), "fclb_shapes_upload");
+  fclb_ccd_request rq{};
+  rq.request_type = uint32_t(request.request_type);
+  rq.max_contacts = uint32_t(request.num_max_contacts);
+  rq.zero_movement_tolerance = double(request.zero_movement_tolerance);
+  rq.gjk_tolerance = double(request.gjk_tolerance);
+  rq.max_gjk_iterations = request.max_gjk_iterations;
+  std::vector<uint8_t> hit(pairs.size());
+  std::vector<S> toc(2 * pairs.size());
+  if (detail::batchOk(fclb_translational_ccd_batch_host(table, pairs.data(), p1.data(), p2.data(), disp.data(), pairs.size(),
+                                                        detail::scalarType<S>(), &rq, hit.data(), toc.data()),
+                      "fclb_translational_ccd_batch_host"))
+    for (std::size_t i = 0; i < pairs.size(); i++)
+      if (hit[i]) {
+        ContinuousCollisionContact<S> c;
+        c.o1 = queries[idx[i]].o1;
+        c.o2 = queries[idx[i]].o2;
+        c.toc.lower_bound = toc[2 * i];
+        c.toc.upper_bound = toc[2 * i + 1];
+        results[idx[i]].AddContact(c);
+      }
+  fclb_release(table);
+}
+template <typename S>
+void translational_ccd(const CollisionGeometry<S>* o1, const Transform3<S>& tf1, const TranslationalDisplacement<S>& o1_displacement,
+                       const CollisionGeometry<S>* o2, const Transform3<S>& tf2, const ContinuousCollisionRequest<S>& request,
+                       ContinuousCollisionResult<S>& result) {
+  std::vector<ContinuousCollisionQuery<S>> q{{o1, tf1, o1_displacement, o2, tf2}};
+  std::vector<ContinuousCollisionResult<S>> r;
+  translationalCcdBatch(q, request, r);
+  for (const auto& c : r[0].raw_contacts()) result.AddContact(c);
+}
+
 // ---- distance (added API; semantics of detail::GJKSolver<S>::shapeDistance) -----------
 template <typename S>
 struct DistanceRequest {

@@ -189,6 +189,36 @@ int fclb_gjk_epa_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const voi
                            size_t n, int scalar_type, const fclb_request* req, int32_t* out_gjk, int32_t* out_epa,
                            void* out_geom);
 
+/* ---- translational continuous collision, shape vs shape -------------------------------------------
+ * fcl::translational_ccd(o1, tf1, o1_displacement, o2, tf2, request, result) per query
+ * (narrowphase/continuous_collision-inl.h:21-36 -> ShapePairTranslationalCollisionSolver::RunShapePair,
+ * detail/ccd/shape_pair_ccd-inl.h:139-170): does shape 1, translated along displacement, ever touch shape 2?
+ *   Box-Box                 the swept-box separating-axis test with its time-of-collision interval
+ *                           (BoxPairTranslationalCCD::IsDisjoint, box_pair_ccd-inl.h), whatever the request type
+ *   every other pair        MPR on the Minkowski difference of (shape 1 swept, shape 2) (gjk_ccd-inl.h:21-114);
+ *                           kBoxApproximate first runs the swept-box test on the shapes' local AABBs (toc = its
+ *                           interval), kOneTocSample derives one time sample from MPR's final portal (:116-186)
+ * displacements: 4 S per query = TranslationalDisplacement{unit_axis_in_shape1 xyz, scalar_displacement}.
+ *   out_hit[q] = 1 when a contact is reported;  out_toc[2q..] = ContinuousCollisionContact::toc (lower, upper),
+ *   (-1, -1) when the request type computes none.  Bit-identical to the reference (tests/test_ccd_gpu.py). */
+#define FCLB_CCD_NOT_REQUESTED 0
+#define FCLB_CCD_BOX_APPROXIMATE 1
+#define FCLB_CCD_ONE_TOC_SAMPLE 2
+typedef struct {
+  uint32_t request_type;           /* FCLB_CCD_* = TimeOfCollisionRequestType (detail/ccd/ccd_request.h:10-16) */
+  uint32_t max_contacts;           /* num_max_contacts; a shape pair has at most one contact */
+  double zero_movement_tolerance;  /* <= 0 => 1e-4 */
+  double gjk_tolerance;            /* <= 0 => 1e-6 */
+  int32_t max_gjk_iterations;      /* <= 0 => 128 */
+  uint32_t flags;                  /* reserved, 0 */
+} fclb_ccd_request;
+int fclb_translational_ccd_batch_host(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                                      const void* displacements, size_t n, int scalar_type, const fclb_ccd_request* req,
+                                      uint8_t* out_hit, void* out_toc);
+int fclb_translational_ccd_batch_dev(fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,
+                                     const void* displacements, size_t n, int scalar_type, const fclb_ccd_request* req,
+                                     uint8_t* out_hit, void* out_toc);
+
 /* ---- meshes: BVHModel<OBBRSS<S>> flattened by the caller ------------------------
  * (reference geometry/bvh/BVH_model.h:63-196, BV_node_base.h:50-82).  Only the
  * OBB half of OBBRSS is ever read by collide (math/bv/OBBRSS-inl.h:130-135).

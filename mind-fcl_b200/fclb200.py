@@ -48,7 +48,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
-    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
+    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
     "fclb_measure_fp_peak", "fclb_measure_l2_bandwidth", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -741,6 +741,26 @@ def measure_fp_peak(scalar_type) -> float:
     v = C.c_double()
     check(load().fclb_measure_fp_peak(scalar_type, C.byref(v)))
     return v.value
+
+
+class CcdRequest(C.Structure):
+    _fields_ = [("request_type", C.c_uint32), ("max_contacts", C.c_uint32), ("zero_movement_tolerance", C.c_double),
+                ("gjk_tolerance", C.c_double), ("max_gjk_iterations", C.c_int32), ("flags", C.c_uint32)]
+
+
+def translational_ccd_batch_host(table, pairs, poses1, poses2, displacements, scalar_type, request_type=0, zero_tol=0.0,
+                                 gjk_tol=0.0, max_iter=0):
+    """fcl::translational_ccd per query (shape pairs): (hit u8 [n], toc [n, 2])"""
+    n = len(pairs)
+    dt = np_dtype(scalar_type)
+    hit = np.zeros(n, np.uint8)
+    toc = np.zeros((n, 2), dt)
+    r = CcdRequest(request_type, 1, zero_tol, gjk_tol, max_iter, 0)
+    fn = load().fclb_translational_ccd_batch_host
+    fn.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    check(fn(table, _ptr(pairs), _ptr(poses1), _ptr(poses2), _ptr(displacements), n, scalar_type, C.cast(C.pointer(r), C.c_void_p),
+             _ptr(hit), _ptr(toc)))
+    return hit, toc
 
 
 def measure_l2_bandwidth() -> float:

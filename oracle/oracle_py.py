@@ -164,6 +164,21 @@ class RefOracle(_Oracle):
           _p(ok), threads)
         return dist, p1, p2, ok
 
+    def translational_ccd_batch(self, shapes, pairs, poses1, poses2, disp, request_type=0, zero_tol=0.0, gjk_tol=0.0, max_iter=0,
+                                threads=1):
+        """fcl::translational_ccd per query: (hit u8 [n], toc [n, 2])"""
+        n = len(pairs)
+        dt = poses1.dtype
+        hit = np.zeros(n, np.uint8)
+        toc = np.zeros((n, 2), dt)
+        arr = _shape_array(shapes)
+        f = self.fn("translational_ccd_batch")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double,
+                      C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(dt), C.cast(arr, C.c_void_p), len(shapes), _p(pairs), _p(poses1), _p(poses2), _p(disp), n, request_type, zero_tol,
+          gjk_tol, max_iter, _p(hit), _p(toc), threads)
+        return hit, toc
+
     # ---- meshes (reference BVHModel<OBBRSS<S>>) ----
     def bvh_create(self, verts, tris):
         verts = np.ascontiguousarray(verts, np.float64)

@@ -386,6 +386,56 @@ extern "C" int fclref_signed_distance_batch(int scalar_type, const void* shapes,
                                      (const double*)poses2, n, (double*)dist, (double*)p1, (double*)p2, ok, threads);
 }
 
+// fcl::translational_ccd(shape, tf1, displacement, shape, tf2, request, result) per query
+// (narrowphase/continuous_collision-inl.h:21-36).  disp: 4 S per query = unit axis in shape 1's frame, scalar.
+// out_hit: 1 when a contact is reported; out_toc: ContinuousCollisionContact::toc (lower, upper) or (-1, -1).
+template <typename S>
+int translationalCcdBatch(const ShapeRec* shapes, int n_shapes, const PairRec* pairs, const S* poses1, const S* poses2,
+                          const S* disp, size_t n, int request_type, double zero_tol, double gjk_tol, int max_iter,
+                          uint8_t* out_hit, S* out_toc, int n_threads) {
+  std::vector<std::shared_ptr<fcl::ShapeBase<S>>> tab;
+  for (int i = 0; i < n_shapes; i++) {
+    tab.push_back(makeShape<S>(shapes[i]));
+    tab.back()->computeLocalAABB();  // kBoxApproximate reads aabb_local; the reference's own CCD tests prepare it the same way
+  }
+  parallelFor(n, n_threads, [&](size_t b, size_t e, int) {
+    fcl::ContinuousCollisionRequest<S> req;
+    req.request_type = static_cast<fcl::TimeOfCollisionRequestType>(request_type);
+    req.num_max_contacts = 1;
+    if (zero_tol > 0) req.zero_movement_tolerance = S(zero_tol);
+    if (gjk_tol > 0) req.gjk_tolerance = S(gjk_tol);
+    if (max_iter > 0) req.max_gjk_iterations = max_iter;
+    for (size_t q = b; q < e; q++) {
+      const auto tf1 = loadPose<S>(poses1 + 12 * q);
+      const auto tf2 = loadPose<S>(poses2 + 12 * q);
+      fcl::TranslationalDisplacement<S> d;
+      d.unit_axis_in_shape1 = fcl::Vector3<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]);
+      d.scalar_displacement = disp[4 * q + 3];
+      fcl::ContinuousCollisionResult<S> res;
+      fcl::translational_ccd<S>(tab[pairs[q].s1].get(), tf1, d, tab[pairs[q].s2].get(), tf2, req, res);
+      const bool hit = res.num_contacts() > 0;
+      out_hit[q] = hit ? 1 : 0;
+      if (out_toc) {
+        out_toc[2 * q] = hit ? res.raw_contacts()[0].toc.lower_bound : S(-1);
+        out_toc[2 * q + 1] = hit ? res.raw_contacts()[0].toc.upper_bound : S(-1);
+      }
+    }
+  });
+  return 0;
+}
+extern "C" int fclref_translational_ccd_batch(int scalar_type, const void* shapes, int n_shapes, const void* pairs,
+                                              const void* poses1, const void* poses2, const void* disp, size_t n,
+                                              int request_type, double zero_tol, double gjk_tol, int max_iter,
+                                              uint8_t* out_hit, void* out_toc, int threads) {
+  if (scalar_type == 0)
+    return translationalCcdBatch<float>((const ShapeRec*)shapes, n_shapes, (const PairRec*)pairs, (const float*)poses1,
+                                        (const float*)poses2, (const float*)disp, n, request_type, zero_tol, gjk_tol, max_iter,
+                                        out_hit, (float*)out_toc, threads);
+  return translationalCcdBatch<double>((const ShapeRec*)shapes, n_shapes, (const PairRec*)pairs, (const double*)poses1,
+                                       (const double*)poses2, (const double*)disp, n, request_type, zero_tol, gjk_tol, max_iter,
+                                       out_hit, (double*)out_toc, threads);
+}
+
 // shape factory for the other harness translation units (ref_harness_scene.cpp)
 namespace fclref {
 std::shared_ptr<fcl::ShapeBase<float>> makeShapeF(const void* rec) { return makeShape<float>(*static_cast<const ShapeRec*>(rec)); }

@@ -324,6 +324,25 @@ void runBatch() {
   CollisionResult<S> e;
   EXPECT_TRUE(collide<S>(&hm, I, &bar, at(S(0.2), S(0.05), S(0.3)), pen, e) >= 4);
   for (const auto& ct : e.getContacts()) EXPECT_TRUE(ct.penetration_depth >= 0 && (ct.b1 & 0xffff) == 8);
+  // translational continuous collision: a unit sphere sweeping 3 m along +x meets a box 2 m ahead; 0.5 m does not reach it
+  {
+    Sphere<S> mover(S(0.5));
+    Box<S> wall(S(0.2), 2, 2);
+    TranslationalDisplacement<S> far_sweep, short_sweep;
+    far_sweep.unit_axis_in_shape1 = short_sweep.unit_axis_in_shape1 = Vector3<S>(1, 0, 0);
+    far_sweep.scalar_displacement = 3;
+    short_sweep.scalar_displacement = S(0.5);
+    ContinuousCollisionRequest<S> creq;
+    creq.request_type = TimeOfCollisionRequestType::kBoxApproximate;
+    ContinuousCollisionResult<S> hit_r, miss_r;
+    translational_ccd<S>(&mover, I, far_sweep, &wall, at(2, 0, 0), creq, hit_r);
+    translational_ccd<S>(&mover, I, short_sweep, &wall, at(2, 0, 0), creq, miss_r);
+    EXPECT_TRUE(hit_r.num_contacts() == 1 && miss_r.num_contacts() == 0);
+    if (hit_r.num_contacts() == 1) {  // first touch after 1.4 m of 3 m, last after 2.6 m
+      const auto& toc = hit_r.raw_contacts()[0].toc;
+      EXPECT_TRUE(std::fabs(toc.lower_bound - S(1.4 / 3.0)) < S(1e-4) && std::fabs(toc.upper_bound - S(2.6 / 3.0)) < S(1e-4));
+    }
+  }
   // UserContactProcessFunctor on the host: keep only contacts on triangle 1, stop after two
   std::vector<CollisionQuery<S>> one_q{{&floor, I, &ball, at(0, 0, S(0.1))}};
   std::vector<CollisionResult<S>> fr;
