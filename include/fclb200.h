@@ -381,6 +381,18 @@ int fclb_octree_prune_host(const uint32_t* inner_children, uint32_t n_inner, uin
 int fclb_octree_consolidate_host(const uint32_t* inner_children, uint32_t n_inner, const uint8_t* pruned,
                                  const uint8_t* leaf_bits, uint32_t n_leaf, int num_layers, uint32_t* out_children,
                                  uint8_t* out_full, uint32_t* out_n_inner, uint8_t* out_leaf_bits, uint32_t* out_n_leaf);
+/* octree2::Octree<S>::rebuildTree ON THE DEVICE (points: n x 3 S, DEVICE pointer for _dev, HOST pointer for
+ * _points_host), with the reference's node numbering: a node's creation time in the reference is (index of the first
+ * point of the stream that reaches it, its depth), so the device sorts the voxel path keys, folds them level by level
+ * into unique prefixes with their first point, and ranks the nodes by that creation time -- no sequential insert.
+ * inner_children / inner_full / leaf_bits equal the reference's arrays (and the host mirror's) exactly, so contact ids
+ * are unchanged.  fclb_octree_export / _info hand the arrays back. */
+int fclb_octree_build_dev(const void* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
+                          fclb_handle* octree);
+int fclb_octree_build_points_host(const void* points, size_t n_points, double resolution, uint32_t bottom_half_shape,
+                                  int scalar_type, fclb_handle* octree);
+int fclb_octree_info(fclb_handle octree, uint32_t* n_inner, uint32_t* n_leaf, int* num_layers, double* root_aabb);
+int fclb_octree_export(fclb_handle octree, uint32_t* inner_children, uint8_t* inner_full, uint8_t* leaf_bits);
 /* the same builder followed by fclb_octree_upload (no prune mask) */
 int fclb_octree_build(const double* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
                       fclb_handle* octree);

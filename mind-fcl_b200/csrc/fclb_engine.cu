@@ -552,6 +552,13 @@ static int initEngine(Engine& e, int device) {
   FCLB_CUDA(cudaEventCreate(&e.ev1));
   FCLB_CUDA(cudaEventCreate(&e.ev_call0));
   for (int i = 0; i <= Engine::kMaxRec; i++) FCLB_CUDA(cudaEventCreate(&e.rec_ev[i]));
+  {  // keep the stream-ordered pool's memory across synchronisations (the builders allocate their scratch from it)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   FCLB_CUDA(cudaMalloc(&e.d_hist, (2 * kNumKinds + 1) * sizeof(uint32_t)));
   FCLB_CUDA(cudaHostAlloc(&e.h_hist, (2 * kNumKinds + 1) * sizeof(uint32_t), cudaHostAllocPortable));
   if (const char* hc = getenv("FCLB_HOST_CHUNK")) {  // queries per pipeline stage of the *_host entry points (tuning)

@@ -8,6 +8,7 @@
 
 #include "fclb_bvh.cuh"
 #include "fclb_octree_build.h"
+#include "fclb_octree_build_dev.cuh"
 #include "fclb_scene_gjk_impl.cuh"
 #include "fclb_shapes.cuh"
 
@@ -464,15 +465,33 @@ static int scenePairContactsDev(Engine& e, int kind1, fclb_handle scene1, int ki
 // FlatHeightMap<S>::updateHeightsByPointGenerationFunctor (flat_heightmap-inl.h:249-272)
 // ---- DefaultGJK_EPA requests on scene geometries: candidate traversal + leaf batch (fclb_scene_gjk_impl.cuh) -----
 namespace {
-struct DevBuf {  // scope-bound device allocation
+struct DevBuf {  // scope-bound device allocation; stream-ordered (pooled) when a stream is given
   void* p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
+  cudaStream_t stream = nullptr;
+  bool pooled = false;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { reset(); }
+  void reset() {
+    if (p) {
+      if (pooled)
+        cudaFreeAsync(p, stream);
+      else
+        cudaFree(p);
+    }
+    p = nullptr;
   }
   cudaError_t alloc(size_t bytes) {
-    if (p) cudaFree(p);
-    p = nullptr;
+    reset();
+    pooled = false;
     return cudaMalloc(&p, bytes ? bytes : 16);
+  }
+  cudaError_t alloc(size_t bytes, cudaStream_t st) {
+    reset();
+    pooled = true;
+    stream = st;
+    return cudaMallocAsync(&p, bytes ? bytes : 16, st);
   }
   template <typename T>
   T* as() const {
@@ -505,14 +524,14 @@ static int sceneGjkContactsDev(Engine& e, int kind1, fclb_handle scene1, int kin
   size_t cap = std::max<size_t>(size_t(1) << 16, std::min<size_t>(n * 32, size_t(1) << 24));
   const size_t cap_max = size_t(1) << 25;  // candidates per chunk (leaf batch of ~300 B per item)
   DevBuf d_count, d_cq, d_cb1, d_cb2, d_box1, d_box2, d_scratch;
-  FCLB_CUDA(d_count.alloc(sizeof(unsigned long long)));
-  FCLB_CUDA(d_scratch.alloc(n * sizeof(uint32_t)));
+  FCLB_CUDA(d_count.alloc(sizeof(unsigned long long), e.compute));
+  FCLB_CUDA(d_scratch.alloc(n * sizeof(uint32_t), e.compute));
   auto allocCand = [&](size_t c) -> int {
-    FCLB_CUDA(d_cq.alloc(c * 4));
-    FCLB_CUDA(d_cb1.alloc(c * 8));
-    FCLB_CUDA(d_cb2.alloc(c * 8));
-    FCLB_CUDA(d_box1.alloc(c * 6 * sizeof(S)));
-    FCLB_CUDA(d_box2.alloc(c * 6 * sizeof(S)));
+    FCLB_CUDA(d_cq.alloc(c * 4, e.compute));
+    FCLB_CUDA(d_cb1.alloc(c * 8, e.compute));
+    FCLB_CUDA(d_cb2.alloc(c * 8, e.compute));
+    FCLB_CUDA(d_box1.alloc(c * 6 * sizeof(S), e.compute));
+    FCLB_CUDA(d_box2.alloc(c * 6 * sizeof(S), e.compute));
     return FCLB_OK;
   };
   int rc = allocCand(cap);
@@ -577,21 +596,21 @@ static int sceneGjkContactsDev(Engine& e, int kind1, fclb_handle scene1, int kin
     }
     const size_t m = size_t(m64);
     DevBuf d_qcount, d_qoff, d_itemq, d_ib1, d_ib2, d_flags, d_lc, d_lcnt;
-    FCLB_CUDA(d_qcount.alloc(nc * 4));
-    FCLB_CUDA(d_qoff.alloc(nc * 4));
+    FCLB_CUDA(d_qcount.alloc(nc * 4, e.compute));
+    FCLB_CUDA(d_qoff.alloc(nc * 4, e.compute));
     FCLB_CUDA(cudaMemsetAsync(d_qcount.p, 0, nc * 4, e.compute));
     FCLB_CUDA(cudaMemsetAsync(d_qoff.p, 0, nc * 4, e.compute));
     if (m > 0) {
       // (query, b1, b2) order: least significant key first, stable radix passes
       DevBuf d_ka, d_kb, d_va, d_vb, d_tmp;
-      FCLB_CUDA(d_ka.alloc(m * 8));
-      FCLB_CUDA(d_kb.alloc(m * 8));
-      FCLB_CUDA(d_va.alloc(m * 4));
-      FCLB_CUDA(d_vb.alloc(m * 4));
+      FCLB_CUDA(d_ka.alloc(m * 8, e.compute));
+      FCLB_CUDA(d_kb.alloc(m * 8, e.compute));
+      FCLB_CUDA(d_va.alloc(m * 4, e.compute));
+      FCLB_CUDA(d_vb.alloc(m * 4, e.compute));
       size_t tmp_bytes = 0;
       FCLB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_ka.as<unsigned long long>(), d_kb.as<unsigned long long>(),
                                                 d_va.as<uint32_t>(), d_vb.as<uint32_t>(), int(m), 0, 64, e.compute));
-      FCLB_CUDA(d_tmp.alloc(tmp_bytes));
+      FCLB_CUDA(d_tmp.alloc(tmp_bytes, e.compute));
       const int g = int(std::min<size_t>((m + 255) / 256, size_t(e.sms) * 8));
       iotaKernel<<<g, 256, 0, e.compute>>>(d_va.as<uint32_t>(), m);
       uint32_t* cur = d_va.as<uint32_t>();
@@ -614,16 +633,16 @@ static int sceneGjkContactsDev(Engine& e, int kind1, fclb_handle scene1, int kin
       // the leaf batch
       const uint32_t n_user = pair ? 0u : t->n;
       DevBuf d_table, d_pairs, d_p1, d_p2;
-      FCLB_CUDA(d_table.alloc((size_t(n_user) + 2 * m) * sizeof(ShapeD<S>)));
-      FCLB_CUDA(d_pairs.alloc(m * sizeof(fclb_pair)));
-      FCLB_CUDA(d_p1.alloc(m * ps));
-      FCLB_CUDA(d_p2.alloc(m * ps));
-      FCLB_CUDA(d_itemq.alloc(m * 4));
-      FCLB_CUDA(d_ib1.alloc(m * 8));
-      FCLB_CUDA(d_ib2.alloc(m * 8));
-      FCLB_CUDA(d_flags.alloc(m));
-      FCLB_CUDA(d_lc.alloc(m * 4 * 9 * sizeof(S)));
-      FCLB_CUDA(d_lcnt.alloc(m * 4));
+      FCLB_CUDA(d_table.alloc((size_t(n_user) + 2 * m) * sizeof(ShapeD<S>), e.compute));
+      FCLB_CUDA(d_pairs.alloc(m * sizeof(fclb_pair), e.compute));
+      FCLB_CUDA(d_p1.alloc(m * ps, e.compute));
+      FCLB_CUDA(d_p2.alloc(m * ps, e.compute));
+      FCLB_CUDA(d_itemq.alloc(m * 4, e.compute));
+      FCLB_CUDA(d_ib1.alloc(m * 8, e.compute));
+      FCLB_CUDA(d_ib2.alloc(m * 8, e.compute));
+      FCLB_CUDA(d_flags.alloc(m, e.compute));
+      FCLB_CUDA(d_lc.alloc(m * 4 * 9 * sizeof(S), e.compute));
+      FCLB_CUDA(d_lcnt.alloc(m * 4, e.compute));
       if (n_user)
         FCLB_CUDA(cudaMemcpyAsync(d_table.p, t->d_shapes[st], size_t(n_user) * sizeof(ShapeD<S>), cudaMemcpyDeviceToDevice,
                                   e.compute));
@@ -660,7 +679,7 @@ static int sceneGjkContactsDev(Engine& e, int kind1, fclb_handle scene1, int kin
       size_t scan_bytes = 0;
       FCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_qcount.as<uint32_t>(), d_qoff.as<uint32_t>(), int(nc), e.compute));
       DevBuf d_scan;
-      FCLB_CUDA(d_scan.alloc(scan_bytes));
+      FCLB_CUDA(d_scan.alloc(scan_bytes, e.compute));
       FCLB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan.p, scan_bytes, d_qcount.as<uint32_t>(), d_qoff.as<uint32_t>(), int(nc), e.compute));
       e.launches += 1;
       FCLB_CUDA(cudaStreamSynchronize(e.compute));  // (d_scan and the sort buffers go out of scope below)
@@ -759,6 +778,206 @@ static int sceneShapeCountsViaContacts(Engine& e, int kind, fclb_handle scene, c
     e.launches += 1;
     FCLB_CUDA(cudaStreamSynchronize(e.compute));
   }
+  return FCLB_OK;
+}
+
+// ---- octree2::Octree<S>::rebuildTree on the device (fclb_octree_build_dev.cuh) -------------------------------------
+static int octAllocLevel(std::vector<OctLevel>& levels, std::vector<DevBuf>& bufs, int l, uint32_t n, cudaStream_t st) {
+  OctLevel& v = levels[size_t(l)];
+  v.n = n;
+  FCLB_CUDA(bufs[size_t(4 * l)].alloc(size_t(n) * 8, st));
+  FCLB_CUDA(bufs[size_t(4 * l + 1)].alloc(size_t(n) * 4, st));
+  FCLB_CUDA(bufs[size_t(4 * l + 2)].alloc(size_t(n) * 4, st));
+  FCLB_CUDA(bufs[size_t(4 * l + 3)].alloc(size_t(n) * 4, st));
+  v.key = bufs[size_t(4 * l)].as<unsigned long long>();
+  v.first = bufs[size_t(4 * l + 1)].as<uint32_t>();
+  v.parent = bufs[size_t(4 * l + 2)].as<uint32_t>();
+  v.index = bufs[size_t(4 * l + 3)].as<uint32_t>();
+  return FCLB_OK;
+}
+
+template <typename S>
+static int octreeBuildDev(Engine& e, const void* d_points, size_t n_points, double resolution, uint32_t bottom_half, OctreeDev* out) {
+  int log2h = 0;
+  while ((1u << log2h) < bottom_half) log2h++;
+  const int L = log2h + 2;
+  out->num_layers = L;
+  const S res = S(resolution);
+  const S inv = S(1.0) / res;
+  const S mx = res * S(bottom_half);
+  for (int k = 0; k < 3; k++) {
+    out->root_box[k] = double(-mx);
+    out->root_box[3 + k] = double(mx);
+  }
+  cudaStream_t st = e.compute;
+  auto grid = [&](size_t n) { return int(std::min<size_t>((n + 255) / 256, size_t(e.sms) * 8)); };
+  uint32_t n_valid = 0;
+  DevBuf k0, i0, k1, i1, tmp, head, scanned;
+  size_t tmp_bytes = 0;
+  if (n_points) {
+    FCLB_CUDA(k0.alloc(n_points * 8, st));
+    FCLB_CUDA(i0.alloc(n_points * 4, st));
+    FCLB_CUDA(k1.alloc(n_points * 8, st));
+    FCLB_CUDA(i1.alloc(n_points * 4, st));
+    octKeyKernel<S><<<grid(n_points), 256, 0, st>>>(static_cast<const S*>(d_points), n_points, inv, int(bottom_half), L,
+                                                    k0.as<unsigned long long>(), i0.as<uint32_t>());
+    FCLB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0.as<unsigned long long>(), k1.as<unsigned long long>(), i0.as<uint32_t>(),
+                                              i1.as<uint32_t>(), int(n_points), 0, 64, st));
+    size_t scan_bytes = 0;
+    FCLB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(n_points), st));
+    FCLB_CUDA(tmp.alloc(std::max(tmp_bytes, scan_bytes), st));
+    tmp_bytes = std::max(tmp_bytes, scan_bytes);
+    FCLB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k0.as<unsigned long long>(), k1.as<unsigned long long>(), i0.as<uint32_t>(),
+                                              i1.as<uint32_t>(), int(n_points), 0, 64, st));
+    e.launches += 2;
+    // points outside the grid carry the key ~0 and sort last
+    std::vector<unsigned long long> probe(1);
+    size_t lo = 0, hi = n_points;  // first position whose key is ~0 (binary search with single-word reads)
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      FCLB_CUDA(cudaMemcpyAsync(probe.data(), k1.as<unsigned long long>() + mid, 8, cudaMemcpyDeviceToHost, st));
+      FCLB_CUDA(cudaStreamSynchronize(st));
+      if (probe[0] == ~0ull) hi = mid; else lo = mid + 1;
+    }
+    n_valid = uint32_t(lo);
+    FCLB_CUDA(head.alloc(size_t(n_points) * 4, st));
+    FCLB_CUDA(scanned.alloc(size_t(n_points) * 4, st));
+  }
+  // levels[l]: unique prefixes of l triplets; l = L - 1 voxels, l = L - 2 leaf nodes, 1 .. L - 3 inner nodes
+  std::vector<OctLevel> levels(static_cast<size_t>(L));
+  OctLevel* lv = levels.data();
+  std::vector<DevBuf> bufs(static_cast<size_t>(L) * 4);
+  auto allocLevel = [&](int l, uint32_t n) -> int { return octAllocLevel(levels, bufs, l, n, st); };
+  auto lastOf = [&](const uint32_t* d_scanned, uint32_t n, uint32_t* out_v) -> int {
+    FCLB_CUDA(cudaMemcpyAsync(out_v, d_scanned + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    FCLB_CUDA(cudaStreamSynchronize(st));
+    return FCLB_OK;
+  };
+  int rc = FCLB_OK;
+  if (n_valid) {
+    uint32_t n_vox = 0;
+    octHeadKernel<<<grid(n_valid), 256, 0, st>>>(k1.as<unsigned long long>(), n_valid, 0, head.as<uint32_t>());
+    FCLB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, head.as<uint32_t>(), scanned.as<uint32_t>(), int(n_valid), st));
+    if ((rc = lastOf(scanned.as<uint32_t>(), n_valid, &n_vox))) return rc;
+    if ((rc = allocLevel(L - 1, n_vox))) return rc;
+    octUniqueKernel<<<grid(n_valid), 256, 0, st>>>(k1.as<unsigned long long>(), i1.as<uint32_t>(), scanned.as<uint32_t>(), n_valid,
+                                                   lv[L - 1].key, lv[L - 1].first);
+    e.launches += 3;
+    for (int l = L - 1; l >= 2; l--) {  // fold level l into level l - 1
+      const uint32_t n = lv[l].n;
+      uint32_t n_par = 0;
+      octHeadKernel<<<grid(n), 256, 0, st>>>(lv[l].key, n, 3, head.as<uint32_t>());
+      FCLB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, head.as<uint32_t>(), scanned.as<uint32_t>(), int(n), st));
+      if ((rc = lastOf(scanned.as<uint32_t>(), n, &n_par))) return rc;
+      if ((rc = allocLevel(l - 1, n_par))) return rc;
+      octFillKernel<<<grid(n_par), 256, 0, st>>>(lv[l - 1].first, n_par, 0xffffffffu);
+      octFoldKernel<<<grid(n), 256, 0, st>>>(lv[l].key, lv[l].first, scanned.as<uint32_t>(), n, 3, lv[l - 1].key, lv[l - 1].first, lv[l].parent);
+      e.launches += 4;
+    }
+  }
+  // ---- node numbering: creation time = (first point, depth)
+  uint32_t n_inner = 1, n_leaf = n_valid ? lv[L - 2].n : 0;
+  std::vector<uint32_t> offset(size_t(L), 0);
+  uint32_t n_ranked = 0;
+  for (int l = 1; l <= L - 3; l++) {
+    offset[l] = n_ranked;
+    n_ranked += lv[l].n;
+  }
+  n_inner += n_ranked;
+  DevBuf rk0, rk1, rv0, rv1, flat;
+  if (n_ranked) {
+    FCLB_CUDA(rk0.alloc(size_t(n_ranked) * 8, st));
+    FCLB_CUDA(rk1.alloc(size_t(n_ranked) * 8, st));
+    FCLB_CUDA(rv0.alloc(size_t(n_ranked) * 4, st));
+    FCLB_CUDA(rv1.alloc(size_t(n_ranked) * 4, st));
+    FCLB_CUDA(flat.alloc(size_t(n_ranked) * 4, st));
+    for (int l = 1; l <= L - 3; l++)
+      if (lv[l].n) octRankKeyKernel<<<grid(lv[l].n), 256, 0, st>>>(lv[l].first, lv[l].n, l, offset[l], rk0.as<unsigned long long>(), rv0.as<uint32_t>());
+    FCLB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, rk0.as<unsigned long long>(), rk1.as<unsigned long long>(), rv0.as<uint32_t>(),
+                                              rv1.as<uint32_t>(), int(n_ranked), 0, 40, st));
+    octAssignIndexKernel<<<grid(n_ranked), 256, 0, st>>>(rv1.as<uint32_t>(), n_ranked, 1u, flat.as<uint32_t>());
+    for (int l = 1; l <= L - 3; l++)
+      if (lv[l].n) FCLB_CUDA(cudaMemcpyAsync(lv[l].index, flat.as<uint32_t>() + offset[l], size_t(lv[l].n) * 4, cudaMemcpyDeviceToDevice, st));
+    e.launches += 3;
+  }
+  DevBuf lk0, lk1, lv0, lv1;
+  if (n_leaf) {
+    FCLB_CUDA(lk0.alloc(size_t(n_leaf) * 8, st));
+    FCLB_CUDA(lk1.alloc(size_t(n_leaf) * 8, st));
+    FCLB_CUDA(lv0.alloc(size_t(n_leaf) * 4, st));
+    FCLB_CUDA(lv1.alloc(size_t(n_leaf) * 4, st));
+    octRankKeyKernel<<<grid(n_leaf), 256, 0, st>>>(lv[L - 2].first, n_leaf, 0, 0, lk0.as<unsigned long long>(), lv0.as<uint32_t>());
+    FCLB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, lk0.as<unsigned long long>(), lk1.as<unsigned long long>(), lv0.as<uint32_t>(),
+                                              lv1.as<uint32_t>(), int(n_leaf), 0, 40, st));
+    octAssignIndexKernel<<<grid(n_leaf), 256, 0, st>>>(lv1.as<uint32_t>(), n_leaf, 0u, lv[L - 2].index);
+    e.launches += 3;
+  }
+  // ---- the reference's flat arrays
+  out->n_inner = n_inner;
+  out->n_leaf = n_leaf;
+  FCLB_CUDA(cudaMalloc(&out->children, size_t(32) * n_inner));
+  FCLB_CUDA(cudaMalloc(&out->inner_full, n_inner));
+  FCLB_CUDA(cudaMalloc(&out->leaf_bits, n_leaf ? n_leaf : 1));
+  FCLB_CUDA(cudaMemsetAsync(out->children, 0xff, size_t(32) * n_inner, st));
+  FCLB_CUDA(cudaMemsetAsync(out->inner_full, 0, n_inner, st));
+  if (n_valid) {
+    for (int l = 1; l <= L - 2; l++) {
+      if (!lv[l].n) continue;
+      if (l == 1) {
+        // (level 1 has no parent array: every item hangs off the root)
+        octFillKernel<<<grid(lv[l].n), 256, 0, st>>>(lv[l].parent, lv[l].n, 0u);
+      }
+      octLinkKernel<<<grid(lv[l].n), 256, 0, st>>>(lv[l].key, lv[l].parent, lv[l].index, lv[l].n, l == 1 ? nullptr : lv[l - 1].index,
+                                                   out->children);
+      e.launches += 1;
+    }
+    DevBuf bits32;
+    FCLB_CUDA(bits32.alloc(size_t(n_leaf) * 4, st));
+    FCLB_CUDA(cudaMemsetAsync(bits32.p, 0, size_t(n_leaf) * 4, st));
+    octLeafBitsKernel<<<grid(lv[L - 1].n), 256, 0, st>>>(lv[L - 1].key, lv[L - 1].parent, lv[L - 1].n, lv[L - 2].index, bits32.as<uint32_t>());
+    octNarrowKernel<<<grid(n_leaf), 256, 0, st>>>(bits32.as<uint32_t>(), n_leaf, out->leaf_bits);
+    for (int d = L - 3; d >= 0; d--) {
+      const uint32_t n = d == 0 ? 1u : lv[d].n;
+      if (n) octFullKernel<<<grid(n), 256, 0, st>>>(d == 0 ? nullptr : lv[d].index, n, out->children, d == L - 3 ? 1 : 0, out->leaf_bits, out->inner_full);
+    }
+    e.launches += 3;
+    FCLB_CUDA(cudaGetLastError());
+    FCLB_CUDA(cudaStreamSynchronize(st));  // (bits32 and the level buffers go out of scope)
+  }
+  FCLB_CUDA(cudaGetLastError());
+  FCLB_CUDA(cudaStreamSynchronize(st));
+  return FCLB_OK;
+}
+
+static int octreeBuildDevEntry(const void* d_points, size_t n_points, double resolution, uint32_t bottom_half, int scalar_type,
+                               fclb_handle* octree) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (!octree || (n_points && !d_points) || bottom_half < 2 || bottom_half > 16384 || (bottom_half & (bottom_half - 1)) ||
+      !(resolution > 0) || n_points > 0x7fffffffu)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_octree_build_dev: bad argument (half shape: power of two >= 2)");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  OctreeDev* d = new OctreeDev();
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  rc = scalar_type == FCLB_F32 ? octreeBuildDev<float>(e, d_points, n_points, resolution, bottom_half, d)
+                               : octreeBuildDev<double>(e, d_points, n_points, resolution, bottom_half, d);
+  if (rc) {
+    cudaFree(d->children);
+    cudaFree(d->inner_full);
+    cudaFree(d->leaf_bits);
+    delete d;
+    return rc;
+  }
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.last_ms = e.last_call_ms = ms;
+  const fclb_handle h = newHandle();
+  octTable()[h] = d;
+  *octree = h;
   return FCLB_OK;
 }
 
@@ -1343,6 +1562,52 @@ int fclb_octree_build(const double* points, size_t n_points, double resolution, 
     return octree_upload_one(t.children.data(), t.full.data(), uint32_t(t.n_inner()), t.leaf_bits.data(),
                              uint32_t(t.leaf_bits.size()), nullptr, t.root_box, t.num_layers, octree);
   });
+}
+
+int fclb_octree_build_dev(const void* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
+                          fclb_handle* octree) {
+  return octreeBuildDevEntry(points, n_points, resolution, bottom_half_shape, scalar_type, octree);
+}
+static int octree_build_points_host_one(const void* points, size_t n_points, double resolution, uint32_t bottom_half_shape,
+                                        int scalar_type, fclb_handle* octree) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n_points && !points) return fail(FCLB_ERR_BAD_ARG, "null points");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  const size_t bytes = n_points * 3 * (scalar_type == FCLB_F32 ? 4 : 8);
+  DevBuf pts;
+  FCLB_CUDA(pts.alloc(bytes));
+  if (bytes) FCLB_CUDA(cudaMemcpyAsync(pts.p, points, bytes, cudaMemcpyHostToDevice, e.compute));
+  return octreeBuildDevEntry(pts.p, n_points, resolution, bottom_half_shape, scalar_type, octree);
+}
+int fclb_octree_build_points_host(const void* points, size_t n_points, double resolution, uint32_t bottom_half_shape, int scalar_type,
+                                  fclb_handle* octree) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return octree_build_points_host_one(points, n_points, resolution, bottom_half_shape, scalar_type, octree); });
+}
+int fclb_octree_info(fclb_handle octree, uint32_t* n_inner, uint32_t* n_leaf, int* num_layers, double* root_aabb) {
+  auto it = octTable().find(octree);
+  if (it == octTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_octree_info: unknown octree handle");
+  if (n_inner) *n_inner = it->second->n_inner;
+  if (n_leaf) *n_leaf = it->second->n_leaf;
+  if (num_layers) *num_layers = it->second->num_layers;
+  if (root_aabb)
+    for (int k = 0; k < 6; k++) root_aabb[k] = it->second->root_box[k];
+  return FCLB_OK;
+}
+int fclb_octree_export(fclb_handle octree, uint32_t* inner_children, uint8_t* inner_full, uint8_t* leaf_bits) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  auto it = octTable().find(octree);
+  if (it == octTable().end()) return fail(FCLB_ERR_BAD_ARG, "fclb_octree_export: unknown octree handle");
+  const OctreeDev* d = it->second;
+  if (inner_children) FCLB_CUDA(cudaMemcpy(inner_children, d->children, size_t(32) * d->n_inner, cudaMemcpyDeviceToHost));
+  if (inner_full) FCLB_CUDA(cudaMemcpy(inner_full, d->inner_full, d->n_inner, cudaMemcpyDeviceToHost));
+  if (leaf_bits && d->n_leaf) FCLB_CUDA(cudaMemcpy(leaf_bits, d->leaf_bits, d->n_leaf, cudaMemcpyDeviceToHost));
+  return FCLB_OK;
 }
 
 int fclb_octree_prune_host(const uint32_t* inner_children, uint32_t n_inner, uint32_t n_leaf, const double* root_aabb,

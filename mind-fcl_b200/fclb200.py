@@ -48,7 +48,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
-    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
+    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_octree_build_dev", "fclb_octree_build_points_host", "fclb_octree_info", "fclb_octree_export", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
     "fclb_measure_fp_peak", "fclb_measure_l2_bandwidth", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -676,6 +676,32 @@ def octree_build(points, resolution, half_shape, scalar_type) -> int:
     h = C.c_uint64()
     check(load().fclb_octree_build(_ptr(pts), len(pts), resolution, half_shape, scalar_type, C.byref(h)))
     return h.value
+
+
+def octree_build_points_host(points, resolution, half_shape, scalar_type) -> int:
+    """Octree<S>::rebuildTree on the device from host points (n x 3, rounded once to S)"""
+    pts = np.ascontiguousarray(np.asarray(points, np.float64).astype(np_dtype(scalar_type)))
+    h = C.c_uint64()
+    fn = load().fclb_octree_build_points_host
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+    check(fn(_ptr(pts), len(pts), resolution, half_shape, scalar_type, C.byref(h)))
+    return h.value
+
+
+def octree_export(h: int):
+    """(inner_children [n,8] u32, inner_full [n] u8, leaf_bits [m] u8, root_aabb [6], n_layers) of a device octree"""
+    ni, nl, layers = C.c_uint32(), C.c_uint32(), C.c_int()
+    root = np.zeros(6, np.float64)
+    info = load().fclb_octree_info
+    info.argtypes = [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.c_void_p]
+    check(info(h, C.byref(ni), C.byref(nl), C.byref(layers), _ptr(root)))
+    ch = np.zeros((ni.value, 8), np.uint32)
+    full = np.zeros(ni.value, np.uint8)
+    leaf = np.zeros(nl.value, np.uint8)
+    ex = load().fclb_octree_export
+    ex.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    check(ex(h, _ptr(ch), _ptr(full), _ptr(leaf)))
+    return ch, full, leaf, root, layers.value
 
 
 def octree_release(h: int) -> None:
