@@ -335,13 +335,25 @@ struct BinPool {
   static constexpr size_t bytesPerWarp() { return size_t(kSlots) * (kWordsS * sizeof(S) + kWordsU * 4); }
 };
 
-template <typename S, int T0, int T1>
-__global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S tol, int max_iter, DistanceOut out,
-                                                                  unsigned long long* cursor) {
+// kCta: the four warps of a CTA share ONE pool (4 x kSlots slots) and the bins are (phase, simplex rank): with 240 slots
+// the nine bins fill to about a warp each, so a trip runs one projection code (rank 2, 3 or 4) on full warps.  Every
+// trip the warps publish the bin masks of their slice, and each warp derives the same list of work units (bin, 32
+// consecutive members) from them and takes the unit with its own index -- two CTA barriers per trip, no atomics.
+#ifndef FCLB_GJK_CTA_WARPS
+#define FCLB_GJK_CTA_WARPS 4
+#endif
+template <typename S, int T0, int T1, int kCtaWarps>
+__global__ void __launch_bounds__(kCtaWarps ? kCtaWarps * 32 : kBlock)
+    distanceGjkBinnedKernel(BatchView b, S tol, int max_iter, DistanceOut out, unsigned long long* cursor) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NS = BinPool<S>::kSlots;
+  constexpr bool kCta = kCtaWarps != 0;
+  constexpr int kWarps = kCta ? kCtaWarps : kBlock / 32;
+  constexpr int kPool = BinPool<S>::kSlots * (kBlock / 32);   // slots per CTA (the same shared memory in both modes)
+  constexpr int NW = kCta ? kPool / kWarps : BinPool<S>::kSlots;  // slots per warp slice
+  constexpr int NS = kCta ? NW * kWarps : NW;            // slots addressed by one warp
+  constexpr int W2 = (NW + 31) / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* wbase = smem_raw + size_t(warp) * BinPool<S>::bytesPerWarp();
+  unsigned char* wbase = kCta ? smem_raw : smem_raw + size_t(warp) * BinPool<S>::bytesPerWarp();
   S* fS = reinterpret_cast<S*>(wbase);                                        // [kWordsS][NS]
   uint32_t* fU = reinterpret_cast<uint32_t*>(wbase + size_t(NS) * BinPool<S>::kWordsS * sizeof(S));  // [kWordsU][NS]
   const ShapeD<S>* __restrict__ shapes = static_cast<const ShapeD<S>*>(b.shapes);
@@ -363,17 +375,195 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
   // from (the projection / sub-simplex search of rank 2, 3 and 4 simplices are three different codes)
   // (measured: with 64 slots per warp the nine bins fill too thinly -- 3.6 ms against 2.7 ms for phase-only
   // bins on C2 -- so the rank split is compiled out; the census below skips the unused bins)
-  constexpr bool kRankBins = false;
+  constexpr bool kRankBins = kCta;
+#ifndef FCLB_GJK_ASYNC
+#define FCLB_GJK_ASYNC 0
+#endif
+  constexpr bool kAsync = FCLB_GJK_ASYNC != 0;
   constexpr int kBins = 9;  // 0 FETCH, 1 BOOL_FIRST, 2..4 BOOL rank 1..3, 5..7 DIST rank 1..3, 8 EXTRACT
   auto binOf = [](int phase, int rank) {
     const int r = !kRankBins ? 1 : (rank < 1 ? 1 : (rank > 3 ? 3 : rank));  // (the phase must survive whatever the rank is)
     return phase == PH_BOOL ? 1 + r : (phase == PH_DIST ? 4 + r : (phase == PH_EXTRACT ? 8 : phase));
   };
-  for (int k = lane; k < NS; k += 32) fU[U_PHASE * NS + k] = 0;
-  __syncwarp();
+  __shared__ unsigned s_mask[kCta ? kWarps : 1][kBins][W2];
+  __shared__ int s_more, s_next;
+#ifndef FCLB_GJK_MIN_FILL
+#define FCLB_GJK_MIN_FILL 1
+#endif
+#ifndef FCLB_GJK_SHARE_UNITS
+#define FCLB_GJK_SHARE_UNITS 0
+#endif
+  constexpr bool kShareUnits = FCLB_GJK_SHARE_UNITS != 0;
+  constexpr int kMinFill = FCLB_GJK_MIN_FILL;
+  bool trip_open = false;  // (CTA pool) inside a trip: the unit list below is valid
+  int u_nfull = 0, u_rem = 0, u_incl = 0, u_total_full = 0, u_rank = 0, u_count = 0;
+  if (kCta) {
+    for (int k = threadIdx.x; k < NS; k += kWarps * 32) fU[U_PHASE * NS + k] = 0;
+    if (threadIdx.x == 0) s_more = 1;
+  } else {
+    for (int k = lane; k < NS; k += 32) fU[U_PHASE * NS + k] = 0;
+    __syncwarp();
+  }
   bool more = true;  // queries left behind the cursor
 
+  if (kCta && kAsync) __syncthreads();
+
   while (true) {
+    int best_bin = -1, best_n = 0, slot = -1;
+    if (kCta && kAsync) {
+      // ---- no barriers: a warp reads all slot states, takes the fullest bin and CLAIMS its members with a
+      // compare-and-swap on the state word (another warp may have been faster; that lane then idles this trip)
+      constexpr int J = (NS + 31) / 32;
+      volatile uint32_t* vstate = fU + U_PHASE * NS;
+      uint32_t stv[J];
+      unsigned long long acc = 0;
+      unsigned acc8 = 0;
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        const int k = j * 32 + lane;
+        stv[j] = k < NS ? vstate[k] : 0xffu;
+        if (stv[j] < 8u) acc += 1ull << (8 * stv[j]);
+        else if (stv[j] == 8u) acc8 += 1;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        acc8 += __shfl_xor_sync(0xffffffffu, acc8, o);
+      }
+      more = *reinterpret_cast<volatile int*>(&s_more) != 0;
+#pragma unroll
+      for (int p = kBins - 1; p >= 0; p--) {
+        if (p == 0 && !more) continue;
+        const int c = p == 8 ? int(acc8) : int((acc >> (8 * p)) & 0xffu);
+        if (c > best_n) {
+          best_n = c;
+          best_bin = p;
+        }
+      }
+      if (best_bin < 0) break;  // nothing unclaimed and nothing to fetch: the warps holding claimed slots finish them
+      const int take = best_n < 32 ? best_n : 32;
+      // members in slot order, this warp starts a quarter (1/kWarps) of the way round so that two warps on the same bin collide less
+      int want = lane < take ? (lane + (warp * best_n) / kWarps) % best_n : -1;
+      unsigned sel = 0;
+      int sel_base = 0, sel_want = -1;
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        const unsigned m = __ballot_sync(0xffffffffu, stv[j] == uint32_t(best_bin));
+        const int c = __popc(m);
+        if (sel_want < 0 && want >= 0 && want < c) {
+          sel = m;
+          sel_base = j * 32;
+          sel_want = want;
+        }
+        want -= c;
+      }
+      if (sel_want >= 0) {
+        slot = sel_base + int(__fns(sel, 0, sel_want + 1));
+        if (atomicCAS(const_cast<uint32_t*>(&vstate[slot]), uint32_t(best_bin), 0xffu) != uint32_t(best_bin)) slot = -1;
+      }
+      __threadfence_block();
+      best_n = take;
+    } else if (kCta) {
+      if (!trip_open) {
+        __syncthreads();  // the slot states the other warps wrote in the previous trip
+        more = *reinterpret_cast<volatile int*>(&s_more) != 0;  // (read between the barriers: fetching warps clear it after the second)
+        if (threadIdx.x == 0) s_next = 0;
+#pragma unroll
+        for (int w = 0; w < W2; w++) {
+          const int k = w * 32 + lane;
+          const int ph = k < NW ? int(fU[U_PHASE * NS + warp * NW + k]) : -1;
+#pragma unroll
+          for (int p = 0; p < kBins; p++) {
+            const unsigned m = __ballot_sync(0xffffffffu, ph == p);
+            if (lane == p) s_mask[warp][p][w] = m;
+          }
+        }
+        __syncthreads();
+        // lane l < kBins speaks for bin kBins-1-l.  The trip's work units, the same list in every warp: the full ones
+        // (32 members) from the last bin down, then the partial ones, largest first, as long as they fill
+        // kMinFill lanes (a thinner bin waits for more members unless nothing else is left)
+        const int mybin = kBins - 1 - lane;
+        int T = 0;
+        if (lane < kBins && !(mybin == 0 && !more)) {
+#pragma unroll
+          for (int w4 = 0; w4 < kWarps; w4++)
+#pragma unroll
+            for (int w = 0; w < W2; w++) T += __popc(s_mask[w4][mybin][w]);
+        }
+        if (__ballot_sync(0xffffffffu, T > 0) == 0) break;  // pool empty and nothing left to fetch (the same in every warp)
+        u_nfull = T >> 5;
+        u_rem = T & 31;
+        int incl = u_nfull;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        u_incl = incl;
+        u_total_full = __shfl_sync(0xffffffffu, incl, kBins - 1);
+        u_rank = -1;  // (ranked below, only by a warp that draws a partial unit)
+        const int n_fill = __popc(__ballot_sync(0xffffffffu, lane < kBins && u_rem >= kMinFill));
+        u_count = u_total_full + (n_fill > 0 ? n_fill : (u_total_full == 0 ? 1 : 0));
+        trip_open = true;
+      }
+      // ---- this warp's unit of the trip.  FCLB_GJK_SHARE_UNITS=1 lets the warps draw ALL the trip's units from a counter
+      // instead (measured on C2 f32: 3.2 ms per launch against 2.2 ms -- working through the thin bins costs more
+      // than the barrier wait it saves), so by default a trip runs its kWarps best units and the rest stay for later
+      int u = warp;
+      if (kShareUnits) {
+        if (lane == 0) u = atomicAdd(&s_next, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+      } else {
+        trip_open = false;
+      }
+      if (u >= u_count) {
+        trip_open = false;
+        continue;
+      }
+      int start = 0;
+      if (u < u_total_full) {
+        const unsigned owner = __ballot_sync(0xffffffffu, lane < kBins && u >= u_incl - u_nfull && u < u_incl);
+        const int l = __ffs(owner) - 1;
+        best_bin = kBins - 1 - l;
+        start = 32 * (u - __shfl_sync(0xffffffffu, u_incl - u_nfull, l));
+        best_n = 32;
+      } else {
+        if (u_rank < 0) {
+          u_rank = 0;
+#pragma unroll
+          for (int l2 = 0; l2 < kBins; l2++) {
+            const int o = __shfl_sync(0xffffffffu, u_rem, l2);
+            if (o > u_rem || (o == u_rem && l2 < lane)) u_rank += 1;
+          }
+        }
+        const unsigned owner = __ballot_sync(0xffffffffu, lane < kBins && u_rem > 0 && u_rank == u - u_total_full);
+        if (owner) {
+          const int l = __ffs(owner) - 1;
+          best_bin = kBins - 1 - l;
+          start = 32 * __shfl_sync(0xffffffffu, u_nfull, l);
+          best_n = __shfl_sync(0xffffffffu, u_rem, l);
+        }
+      }
+      if (best_bin >= 0) {
+        int want = lane < best_n ? start + lane : -1;
+        unsigned sel = 0;
+        int sel_base = 0, sel_want = -1;
+#pragma unroll
+        for (int w4 = 0; w4 < kWarps; w4++)
+#pragma unroll
+          for (int w = 0; w < W2; w++) {
+            const unsigned m = s_mask[w4][best_bin][w];
+            const int c = __popc(m);
+            if (sel_want < 0 && want >= 0 && want < c) {
+              sel = m;
+              sel_base = w4 * NW + w * 32;
+              sel_want = want;
+            }
+            want -= c;
+          }
+        if (sel_want >= 0) slot = sel_base + int(__fns(sel, 0, sel_want + 1));
+      }
+    } else {
     // ---- census of the pool: which bin do most slots wait in?
     unsigned masks[kBins][(NS + 31) / 32];
     int cnt[kBins];
@@ -393,7 +583,6 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
         cnt[p] += __popc(masks[p][w]);
       }
     }
-    int best_bin = -1, best_n = 0;
 #pragma unroll
     for (int p = kBins - 1; p >= 0; p--) {  // ties go to the later bin (drains the pool)
       if (p == 0 && !more) continue;
@@ -403,10 +592,7 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
       }
     }
     if (best_bin < 0) break;  // pool empty and nothing left to fetch
-    const int best = best_bin == 0 ? PH_FETCH
-                                   : (best_bin == 1 ? PH_BOOL_FIRST : (best_bin <= 4 ? PH_BOOL : (best_bin <= 7 ? PH_DIST : PH_EXTRACT)));
     // ---- hand one slot of that phase to each lane
-    int slot = -1;
     {
       int want = lane;
 #pragma unroll
@@ -416,15 +602,30 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
         want -= c;
       }
     }
+    }
+    const int best = best_bin <= 0 ? PH_FETCH
+                                   : (best_bin == 1 ? PH_BOOL_FIRST : (best_bin <= 4 ? PH_BOOL : (best_bin <= 7 ? PH_DIST : PH_EXTRACT)));
+    if (kCta && best_bin < 0) continue;  // no unit for this warp in this trip
     int n_act = best_n < 32 ? best_n : 32;
 
     if (best == PH_FETCH) {
+      int idx = lane;  // which of the fetched queries this lane takes
+      if (kCta && kAsync) {
+        const unsigned got = __ballot_sync(0xffffffffu, slot >= 0);
+        n_act = __popc(got);
+        idx = slot >= 0 ? __popc(got & ((1u << lane) - 1u)) : 32;
+        if (n_act == 0) continue;
+      }
       unsigned long long base = 0;
       if (lane == 0) base = atomicAdd(cursor, (unsigned long long)n_act);
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (base + n_act >= b.count) more = false;
-      if (slot >= 0 && lane < n_act && base + lane < b.count) {
-        const size_t i = size_t(base) + lane;
+      if (base + n_act >= b.count) {
+        more = false;
+        if (kCta && lane == 0) *reinterpret_cast<volatile int*>(&s_more) = 0;
+      }
+      if (kCta && kAsync && slot >= 0 && base + idx >= b.count) fU[U_PHASE * NS + slot] = 0;  // claimed for nothing
+      if (slot >= 0 && idx < n_act && base + idx < b.count) {
+        const size_t i = size_t(base) + idx;
         const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
         const fclb_pair pr = b.pairs[q];
         MinkDiff<S, T0, T1> md;
@@ -438,9 +639,10 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
         fU[U_PAIR2 * NS + slot] = pr.shape2;
         fU[U_ORD * NS + slot] = 0;
         fU[U_RANKIT * NS + slot] = 0;  // rank + 1 = 0 (rank -1), it = 0
-        fU[U_PHASE * NS + slot] = 1;
+        if (kCta && kAsync) __threadfence_block();  // the slot's fields before its state
+        *reinterpret_cast<volatile uint32_t*>(&fU[U_PHASE * NS + slot]) = 1;
       }
-      __syncwarp();
+      if (!kCta) __syncwarp();
       continue;
     }
 
@@ -502,6 +704,10 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
           st3(F_P1, slot, p1);
           st3(F_D, slot, st.dir((pslots >> (8 * ex_k)) & 0xff));
           fU[U_PLAN * NS + slot] = (pl & 0xffu) | (uint32_t(ex_k) << 8);
+          if (kCta && kAsync) {  // back to the extraction bin (the claim had overwritten the state)
+            __threadfence_block();
+            *reinterpret_cast<volatile uint32_t*>(&fU[U_PHASE * NS + slot]) = 8u;
+          }
         }
       } else {
         const V3<S> v = s0 - s1;
@@ -615,7 +821,8 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
           }
           fU[U_ORD * NS + slot] = simplex.ord;
           fU[U_RANKIT * NS + slot] = uint32_t(simplex.rank + 1) | (uint32_t(it) << 8);
-          fU[U_PHASE * NS + slot] = uint32_t(binOf(phase, simplex.rank));
+          if (kCta && kAsync) __threadfence_block();
+          *reinterpret_cast<volatile uint32_t*>(&fU[U_PHASE * NS + slot]) = uint32_t(binOf(phase, simplex.rank));
         }
       }
 
@@ -632,10 +839,11 @@ __global__ void __launch_bounds__(kBlock) distanceGjkBinnedKernel(BatchView b, S
           ok = valid ? uint8_t(1) : uint8_t(3);
         }
         writeDistance(out, q, dist, w1, w2, ok);
-        fU[U_PHASE * NS + slot] = 0;
+        if (kCta && kAsync) __threadfence_block();
+        *reinterpret_cast<volatile uint32_t*>(&fU[U_PHASE * NS + slot]) = 0;
       }
     }
-    __syncwarp();
+    if (!kCta) __syncwarp();
   }
 }
 
@@ -649,13 +857,14 @@ inline int gridFor(size_t count, int block, int ctas_per_sm) {
 }
 
 // FCLB_GJK_BINNED=0 selects the one-query-per-lane state machine (kept for comparison)
-inline bool gjkBinnedEnabled() {
+inline int gjkBinnedMode() {
   static int v = [] {
     const char* e = getenv("FCLB_GJK_BINNED");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 2;
   }();
-  return v != 0;
+  return v;  // 0 one query per lane | 1 per-warp pool, phase bins | 2 CTA-wide pool, (phase, rank) bins
 }
+inline bool gjkBinnedEnabled() { return gjkBinnedMode() != 0; }
 unsigned long long* gjkCursor();  // device counter (fclb_engine.cu)
 
 template <typename S, int T0, int T1>
@@ -666,7 +875,9 @@ cudaError_t launchGjkDistance(const BatchView& b, const SolverParams& sp, const 
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     const size_t smem = BinPool<S>::bytesPerWarp() * (kBlock / 32);
-    auto kern = distanceGjkBinnedKernel<S, T0, T1>;
+    const bool cta = gjkBinnedMode() == 2;
+    auto kern = cta ? distanceGjkBinnedKernel<S, T0, T1, FCLB_GJK_CTA_WARPS> : distanceGjkBinnedKernel<S, T0, T1, 0>;
+    const int block = cta ? FCLB_GJK_CTA_WARPS * 32 : kBlock;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     int per_sm = int((227 * 1024) / (smem + 1024));
@@ -675,7 +886,7 @@ cudaError_t launchGjkDistance(const BatchView& b, const SolverParams& sp, const 
     const size_t need = (b.count + BinPool<S>::kSlots * (kBlock / 32) - 1) / (BinPool<S>::kSlots * (kBlock / 32));
     int grid = gridFor(b.count, kBlock, per_sm);
     if (size_t(grid) > need) grid = int(need ? need : 1);
-    kern<<<grid, kBlock, smem, st>>>(b, S(sp.gjk_tol), sp.gjk_max_iter, out, cursor);
+    kern<<<grid, block, smem, st>>>(b, S(sp.gjk_tol), sp.gjk_max_iter, out, cursor);
     return cudaGetLastError();
   }
   const size_t smem = size_t(24) * sizeof(S) * kBlock;
