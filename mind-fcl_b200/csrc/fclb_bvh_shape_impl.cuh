@@ -173,7 +173,7 @@ FCLB_DI NodeD<S> shapeWorldObb(const ShapeInst<S>& sh, const BoundD<S>* __restri
       return fitObbPointsWarp<S>(c.n_verts, [&](int i) { return apply(tf, loadVert(c.verts, i)); }, pts, lane);
     return fitObbPoints<S>(c.n_verts, [&](int i) { return apply(tf, loadVert(c.verts, i)); });
   }
-  return fitObbPointsWarp<S>(bound->n, [&](int i) { return apply(tf, loadVert(bound->v, i)); }, pts, lane);
+  return fitObbPointsWarp<S>(bound->n, [&](int i) { return apply(tf, loadVert3(bound->v, i)); }, pts, lane);
 }
 
 // ---- box_triangle-inl.h:8-150 ----

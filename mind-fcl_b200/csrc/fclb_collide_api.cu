@@ -32,7 +32,7 @@ static int ensureWorkspace(size_t n, size_t ss) {
   FCLB_CUDA(cudaMalloc(&g_ws.query, cap * sizeof(uint32_t)));
   FCLB_CUDA(cudaMalloc(&g_ws.simplex, cap * 24 * 8));
   FCLB_CUDA(cudaMalloc(&g_ws.rank, cap * sizeof(int32_t)));
-  FCLB_CUDA(cudaMalloc(&g_ws.defer_count, 4 * sizeof(uint32_t)));  // deferred count, two work cursors, pad
+  FCLB_CUDA(cudaMalloc(&g_ws.defer_count, 8 * sizeof(uint32_t)));  // EpaDefer words: count, cursors, done flag
   FCLB_CUDA(cudaMalloc(&g_ws.defer_item, cap * sizeof(uint32_t)));
   g_ws.cap = cap;
   g_ws.scalar = 8;
@@ -159,6 +159,10 @@ static int runCollideTable(Engine& e, ShapeTable* t, const void* tris, const fcl
   a.work.rank = g_ws.rank;
   a.work.capacity = uint32_t(g_ws.cap);
   a.defer.count = g_ws.defer_count;
+  a.aux = e.aux;
+  a.ev_aux0 = e.ev_aux0;
+  a.ev_aux1 = e.ev_aux1;
+  a.item_capacity = g_ws.cap;
   a.defer.item = g_ws.defer_item;
   a.defer.enabled = 0;
   a.defer.consume = 0;

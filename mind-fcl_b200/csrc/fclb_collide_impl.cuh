@@ -401,17 +401,20 @@ __host__ __device__ inline size_t epaTileBytes(size_t poly_bytes) {
 }
 
 struct EpaDefer {
-  uint32_t* count;  // device counter of deferred items
+  uint32_t* count;  // device words: [0] deferred items, [1] tier-1 cursor, [2] tier-2 cursor, [3] early consumers' cursor, [4] tier 1 done
   uint32_t* cursor; // device work cursor of this launch (tiles fetch items dynamically: EPA run times vary 100x)
-  uint32_t* item;   // work-list indices
+  uint32_t* item;   // work-list indices of the deferred queries; kEpaItemEmpty until written, kEpaItemTaken once a consumer owns it
   int enabled;      // tier 1: defer on pool exhaustion; tier 2: 0
-  int consume;      // tier 2: iterate the deferred list instead of the full work list
+  int consume;      // 1 tier 2: iterate the deferred list instead of the full work list; 2 early tier-2 consumer: runs BESIDE
+                    // tier 1 on another stream and takes items as they are published (a query that runs to the iteration
+                    // limit costs 255 iterations x 14 us = 3.5 ms of latency -- started inside tier 1's run time instead of after it)
 };
+constexpr uint32_t kEpaItemEmpty = 0xffffffffu, kEpaItemTaken = 0xfffffffeu;
 
 template <typename S, int T0, int T1, int T>
 __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(BatchView b, S tol, int pool_faces, int max_iter, int mode,
                                                          CollideOut out, EpaWork work, EpaDefer defer,
-                                                         size_t poly_bytes) {
+                                                         size_t poly_bytes, int tier1_iters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kTiles = kEpaThreads / T;
   const int warp_lane = threadIdx.x & 31, tile = threadIdx.x / T, lane = threadIdx.x % T;
@@ -437,6 +440,7 @@ __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(Ba
   bool active = false;
   size_t q = 0;
   uint32_t w = 0;
+  int n_steps = 0;
   MinkDiff<S, T0, T1> md;
   Pose<S> tf1;
   EpaWarp<S, MinkDiff<S, T0, T1>, T> epa(md, poly_mem, pool_faces, defer.enabled != 0, warp_lane, nullptr);
@@ -484,12 +488,50 @@ __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(Ba
     bool finished = false;
     uint32_t it = 0;
     if (!active && more) {
-      if (lane == 0) it = atomicAdd(defer.cursor, 1u);
-      it = epa.shfl(it, 0);
-      more = it < n_items;
+      if (!defer.consume) {
+        if (lane == 0) it = atomicAdd(defer.cursor, 1u);
+        it = epa.shfl(it, 0);
+        more = it < n_items;
+      } else {
+        // deferred list: an item belongs to whoever swaps kEpaItemTaken into its slot (tier 2 and the early consumers share it)
+        uint32_t got = kEpaItemEmpty;
+        if (lane == 0) {
+          volatile uint32_t* items = defer.item;
+          volatile uint32_t* words = defer.count;
+          uint32_t beat = words[1], idle = 0;
+          while (true) {
+            const uint32_t i = atomicAdd(defer.cursor, 1u);
+            if (defer.consume == 1 && i >= n_items) break;
+            uint32_t wv = items[i];
+            while (defer.consume == 2 && wv == kEpaItemEmpty) {  // not published yet
+              if (words[4]) {  // tier 1 has ended: whatever it deferred is visible now
+                wv = items[i];
+                break;
+              }
+              const uint32_t now = words[1];  // tier 1's cursor moves while it runs; if it stands still (tier 1 not co-scheduled,
+              if (now != beat) {              // e.g. launches serialised by a profiler) give up -- tier 2 proper takes the rest
+                beat = now;
+                idle = 0;
+              } else if (++idle > 4000u) {
+                break;
+              }
+              __nanosleep(500);
+              wv = items[i];
+            }
+            if (wv == kEpaItemEmpty) break;
+            if (wv != kEpaItemTaken && atomicCAS(defer.item + i, wv, kEpaItemTaken) == wv) {
+              got = wv;
+              break;
+            }
+          }
+        }
+        got = epa.shfl(got, 0);
+        more = got != kEpaItemEmpty;
+        it = got;
+      }
     }
     if (!active && more) {
-      w = defer.consume ? defer.item[it] : it;
+      w = it;
       q = work.query[w];
       const fclb_pair pr = b.pairs[q];
       md.s0 = bindShape(shapes, cvx, pr.shape1, static_cast<const S*>(b.tris));
@@ -507,6 +549,7 @@ __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(Ba
       p0 = zero3<S>();
       p1 = zero3<S>();
       es = epa.begin(st, sx, tol, depth, p0, p1);
+      n_steps = 0;
       if (es == epa.kEpaContinue)
         active = true;
       else
@@ -521,6 +564,12 @@ __global__ void __launch_bounds__(kEpaThreads FCLB_EPA_BOUNDS_TAIL) epaKernel(Ba
     if (active) {
       es = epa.step(max_iter, tol, depth, p0, p1);
       if (es != epa.kEpaContinue) {
+        finished = true;
+        active = false;
+      } else if (defer.enabled && ++n_steps >= tier1_iters) {
+        // a query still running after tier1_iters iterations (0.003 % of box pairs, 0.07 % of the Convex pairs of C1b) most
+        // likely runs to the iteration limit: hand it to tier 2 (which restarts it) instead of pinning this tile for 255 iterations
+        es = EPA_MALLOC_FAILED;
         finished = true;
         active = false;
       }
@@ -565,6 +614,9 @@ struct CollideLaunchArgs {
   int pen_mode = 0;  // FCLB_PEN_DIRECTED / FCLB_PEN_INCREMENTAL_MIN: run the MPR penetration stage after the boolean
   double pen_dir[3] = {0, 0, 0};
   const void* tris = nullptr;  // leaf batches: triangle array behind the table's ST_TRIANGLE entries
+  cudaStream_t aux = nullptr;  // second stream + fork/join events for the early EPA tier-2 consumers (null: not used)
+  cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
+  size_t item_capacity = 0;    // entries behind defer.item
 };
 
 // implemented in fclb_collide_f32.cu / fclb_collide_f64.cu (MPR penetration stage of one bucket)

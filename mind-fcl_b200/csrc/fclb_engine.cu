@@ -195,6 +195,7 @@ static int uploadConvexTables(Engine& e) {
       tf[i].verts = static_cast<const float*>(c.d_verts[0]);
       td[i].verts = static_cast<const double*>(c.d_verts[1]);
       tf[i].nbr = td[i].nbr = c.d_nbr;
+      tf[i].vinfo = td[i].vinfo = static_cast<const int2*>(c.d_vinfo);
       tf[i].n_verts = td[i].n_verts = c.n_verts;
       tf[i].walk = td[i].walk = c.walk;
       for (int k = 0; k < 6; k++) {
@@ -548,6 +549,9 @@ static int initEngine(Engine& e, int device) {
   FCLB_CUDA(cudaStreamCreateWithFlags(&e.compute, cudaStreamNonBlocking));
   FCLB_CUDA(cudaStreamCreateWithFlags(&e.copy_in, cudaStreamNonBlocking));
   FCLB_CUDA(cudaStreamCreateWithFlags(&e.copy_out, cudaStreamNonBlocking));
+  FCLB_CUDA(cudaStreamCreateWithFlags(&e.aux, cudaStreamNonBlocking));
+  FCLB_CUDA(cudaEventCreateWithFlags(&e.ev_aux0, cudaEventDisableTiming));
+  FCLB_CUDA(cudaEventCreateWithFlags(&e.ev_aux1, cudaEventDisableTiming));
   FCLB_CUDA(cudaEventCreate(&e.ev0));
   FCLB_CUDA(cudaEventCreate(&e.ev1));
   FCLB_CUDA(cudaEventCreate(&e.ev_call0));
@@ -763,12 +767,26 @@ static int convex_upload_one(const double* verts, int n_verts, const int* faces,
   std::vector<double> vdd;
   convexDerive<float>(vd, n_verts, c.seed[0], c.interior[0], vf);
   convexDerive<double>(vd, n_verts, c.seed[1], c.interior[1], vdd);
-  FCLB_CUDA(cudaMalloc(&c.d_verts[0], vf.size() * sizeof(float)));
-  FCLB_CUDA(cudaMalloc(&c.d_verts[1], vdd.size() * sizeof(double)));
+  // device layout: 4 S per vertex (one 128-bit load), and (first neighbour, count) per vertex beside the CSR
+  std::vector<float> vf4(size_t(4) * n_verts, 0.f);
+  std::vector<double> vd4(size_t(4) * n_verts, 0.0);
+  std::vector<int> vinfo(size_t(2) * n_verts);
+  for (int v = 0; v < n_verts; v++) {
+    for (int k = 0; k < 3; k++) {
+      vf4[4 * size_t(v) + k] = vf[3 * size_t(v) + k];
+      vd4[4 * size_t(v) + k] = vdd[3 * size_t(v) + k];
+    }
+    vinfo[2 * size_t(v)] = csr[v] + 1;
+    vinfo[2 * size_t(v) + 1] = csr[csr[v]];
+  }
+  FCLB_CUDA(cudaMalloc(&c.d_verts[0], vf4.size() * sizeof(float)));
+  FCLB_CUDA(cudaMalloc(&c.d_verts[1], vd4.size() * sizeof(double)));
   FCLB_CUDA(cudaMalloc(&c.d_nbr, csr.size() * sizeof(int)));
-  FCLB_CUDA(cudaMemcpy(c.d_verts[0], vf.data(), vf.size() * sizeof(float), cudaMemcpyHostToDevice));
-  FCLB_CUDA(cudaMemcpy(c.d_verts[1], vdd.data(), vdd.size() * sizeof(double), cudaMemcpyHostToDevice));
+  FCLB_CUDA(cudaMalloc(&c.d_vinfo, vinfo.size() * sizeof(int)));
+  FCLB_CUDA(cudaMemcpy(c.d_verts[0], vf4.data(), vf4.size() * sizeof(float), cudaMemcpyHostToDevice));
+  FCLB_CUDA(cudaMemcpy(c.d_verts[1], vd4.data(), vd4.size() * sizeof(double), cudaMemcpyHostToDevice));
   FCLB_CUDA(cudaMemcpy(c.d_nbr, csr.data(), csr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  FCLB_CUDA(cudaMemcpy(c.d_vinfo, vinfo.data(), vinfo.size() * sizeof(int), cudaMemcpyHostToDevice));
   e.convex.push_back(c);
   e.convex_epoch++;
   *slot = uint32_t(e.convex.size() - 1);

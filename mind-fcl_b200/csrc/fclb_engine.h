@@ -24,6 +24,7 @@ struct ConvexHost {
   // per scalar type device arrays
   void* d_verts[2] = {nullptr, nullptr};
   int* d_nbr = nullptr;
+  void* d_vinfo = nullptr;  // int2 per vertex: (first neighbour offset, count)
   int n_verts = 0;
   std::vector<double> h_verts;  // 3 per vertex, as uploaded
   int walk = 0;
@@ -52,6 +53,8 @@ struct Engine {
   int slot = 0;
   int sms = 148;
   cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+  cudaStream_t aux = nullptr;                     // early EPA tier-2 consumers run here, beside tier 1 on `compute`
+  cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<ConvexHost> convex;
   void* d_convex_tab[2] = {nullptr, nullptr};  // ConvexD<S>[]

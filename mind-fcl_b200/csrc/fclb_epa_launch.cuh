@@ -16,6 +16,15 @@ inline int tier1Faces() {
   }();
   return v;
 }
+// tier 1 hands a query to tier 2 after this many EPA iterations (FCLB_EPA_TIER1_ITERS; the reference's limit is 255)
+inline int tier1Iters() {
+  static int v = [] {
+    const char* e = getenv("FCLB_EPA_TIER1_ITERS");
+    const int x = e ? atoi(e) : 0;
+    return x >= 1 ? x : 32;
+  }();
+  return v;
+}
 inline int epaBlocksPerSmCap() {
   static int v = [] {
     const char* e = getenv("FCLB_EPA_BLOCKS_PER_SM");
@@ -27,7 +36,7 @@ inline int epaBlocksPerSmCap() {
 
 template <typename S, int T0, int T1, int T>
 cudaError_t launchEpaTier(const BatchView& b, const CollideLaunchArgs& a, int pool_faces, const EpaDefer& defer,
-                          cudaStream_t st) {
+                          cudaStream_t st, int grid_override = 0) {
   const size_t poly = PolyStore<S>::bytes(pool_faces, defer.enabled != 0);
   const size_t per_tile = epaTileBytes<S>(poly);
   const size_t esmem = per_tile * (kEpaThreads / T);
@@ -40,8 +49,8 @@ cudaError_t launchEpaTier(const BatchView& b, const CollideLaunchArgs& a, int po
   int per_sm = int((227 * 1024) / (esmem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > epaBlocksPerSmCap()) per_sm = epaBlocksPerSmCap();
-  kern<<<sms * per_sm, kEpaThreads, esmem, st>>>(b, S(a.sp.epa_tol), pool_faces, a.sp.epa_max_iter, a.mode, a.out,
-                                                 a.work, defer, poly);
+  kern<<<grid_override > 0 ? grid_override : sms * per_sm, kEpaThreads, esmem, st>>>(b, S(a.sp.epa_tol), pool_faces, a.sp.epa_max_iter, a.mode, a.out,
+                                                 a.work, defer, poly, tier1Iters());
   return cudaGetLastError();
 }
 
@@ -68,21 +77,52 @@ cudaError_t launchEpaTier1(const BatchView& b, const CollideLaunchArgs& a, int p
   }
 }
 
+// FCLB_EPA_EARLY_TIER2=0 turns the early consumers off (tier 2 then starts after tier 1, as in round 1)
+inline int epaEarlyTier2Ctas() {
+  static int v = [] {
+    const char* e = getenv("FCLB_EPA_EARLY_TIER2");
+    return e ? atoi(e) : 0;  // CTAs of 4 warps beside tier 1 (measured on C1b: 7.79 -> 7.70 ms with 37 CTAs, within noise on Convex pairs: off by default)
+  }();
+  return v;
+}
+
 template <typename S, int T0, int T1>
 cudaError_t launchEpaT(const BatchView& b, const CollideLaunchArgs& a, cudaStream_t st) {
   EpaDefer d = a.defer;
-  cudaError_t e = cudaMemsetAsync(d.count, 0, 4 * sizeof(uint32_t), st);  // count + the tiers' work cursors
+  cudaError_t e = cudaMemsetAsync(d.count, 0, 8 * sizeof(uint32_t), st);  // count, the work cursors, the done flag
   if (e != cudaSuccess) return e;
   if (a.sp.epa_max_faces > tier1Faces()) {
+    const bool early = a.aux && a.ev_aux0 && a.ev_aux1 && epaEarlyTier2Ctas() > 0 && b.count >= 4096 && a.item_capacity >= b.count;
+    if (early) {
+      // the early consumers: the tier-2 kernel on a small grid, launched BEFORE tier 1 on the second stream; they wait
+      // for deferred items to appear in the list (kEpaItemEmpty until then) and stop when tier 1 has ended
+      e = cudaMemsetAsync(d.item, 0xff, b.count * sizeof(uint32_t), st);
+      if (e != cudaSuccess) return e;
+      if ((e = cudaEventRecord(a.ev_aux0, st)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(a.aux, a.ev_aux0, 0)) != cudaSuccess) return e;
+      EpaDefer c = d;
+      c.enabled = 0;
+      c.consume = 2;
+      c.cursor = d.count + 3;
+      e = launchEpaTier<S, T0, T1, 32>(b, a, a.sp.epa_max_faces, c, a.aux, epaEarlyTier2Ctas());
+      if (e != cudaSuccess) return e;
+    }
     d.enabled = 1;
     d.consume = 0;
     d.cursor = d.count + 1;
     e = launchEpaTier1<S, T0, T1>(b, a, tier1Faces(), d, st);
     if (e != cudaSuccess) return e;
+    if (early && (e = cudaMemsetAsync(d.count + 4, 0xff, sizeof(uint32_t), st)) != cudaSuccess) return e;  // "tier 1 has ended"
     d.enabled = 0;
     d.consume = 1;
     d.cursor = d.count + 2;
-    return launchEpaTier<S, T0, T1, 32>(b, a, a.sp.epa_max_faces, d, st);
+    e = launchEpaTier<S, T0, T1, 32>(b, a, a.sp.epa_max_faces, d, st);
+    if (e != cudaSuccess) return e;
+    if (early) {
+      if ((e = cudaEventRecord(a.ev_aux1, a.aux)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(st, a.ev_aux1, 0)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
   }
   d.enabled = 0;
   d.consume = 0;

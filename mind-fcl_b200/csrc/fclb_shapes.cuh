@@ -33,8 +33,9 @@ enum ShapeType : int {
 // (convex-inl.h:153-200) and the mean-vertex interior point (convex-inl.h:64-71).
 template <typename S>
 struct ConvexD {
-  const S* verts;
-  const int* nbr;
+  const S* verts;     // 4 S per vertex: x, y, z, pad
+  const int* nbr;     // the reference's CSR: nbr[v] = offset of {count, neighbours...}
+  const int2* vinfo;  // per vertex: (offset of its first neighbour in nbr, neighbour count)
   int n_verts;
   int walk;  // find_extreme_via_neighbors_
   int seed[6];
@@ -57,9 +58,47 @@ struct ShapeInst {
   V3<S> tri[3];           // ST_TRIANGLE (vertices in the shape's own frame)
 };
 
+#ifndef FCLB_CVX_UNROLL
+#define FCLB_CVX_UNROLL 1
+#endif
+#ifndef FCLB_CVX_OLDWALK
+#define FCLB_CVX_OLDWALK 0
+#endif
+#ifndef FCLB_CVX_EAGER
+#define FCLB_CVX_EAGER 1
+#endif
+// plain 3-S-per-point arrays (bounding vertices of the primitive shapes)
 template <typename S>
-FCLB_DI V3<S> loadVert(const S* __restrict__ v, int i) {
+FCLB_DI V3<S> loadVert3(const S* __restrict__ v, int i) {
   return mk<S>(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+}
+// Convex vertices are stored 4 S apart (x, y, z, pad) so that one vertex is one 128-bit load (two for double)
+#ifndef FCLB_CVX_LOAD
+#define FCLB_CVX_LOAD 1  // 0 one 128-bit __ldg | 1 one plain 128-bit load | 2 three scalar loads
+#endif
+FCLB_DI V3<float> loadVert(const float* __restrict__ v, int i) {
+#if FCLB_CVX_LOAD == 2
+  return mk<float>(v[4 * i], v[4 * i + 1], v[4 * i + 2]);
+#elif FCLB_CVX_LOAD == 1
+  const float4 t = *(reinterpret_cast<const float4*>(v) + i);
+  return mk<float>(t.x, t.y, t.z);
+#else
+  const float4 t = __ldg(reinterpret_cast<const float4*>(v) + i);
+  return mk<float>(t.x, t.y, t.z);
+#endif
+}
+FCLB_DI V3<double> loadVert(const double* __restrict__ v, int i) {
+#if FCLB_CVX_LOAD == 2
+  return mk<double>(v[4 * i], v[4 * i + 1], v[4 * i + 2]);
+#elif FCLB_CVX_LOAD == 1
+  const double2 a = *(reinterpret_cast<const double2*>(v) + 2 * i);
+  const double2 b = *(reinterpret_cast<const double2*>(v) + 2 * i + 1);
+  return mk<double>(a.x, a.y, b.x);
+#else
+  const double2 a = __ldg(reinterpret_cast<const double2*>(v) + 2 * i);
+  const double2 b = __ldg(reinterpret_cast<const double2*>(v) + 2 * i + 1);
+  return mk<double>(a.x, a.y, b.x);
+#endif
 }
 
 // convex-inl.h:133-150 : linear scan, first maximum wins (strict >)
@@ -67,6 +106,9 @@ template <typename S>
 FCLB_DI int convexExtremeNaive(const ConvexD<S>& c, const V3<S>& d) {
   int best = 0;
   S best_v = dot(d, loadVert(c.verts, 0));
+#if FCLB_CVX_UNROLL
+#pragma unroll 4
+#endif
   for (int i = 1; i < c.n_verts; i++) {
     const S v = dot(d, loadVert(c.verts, i));
     if (v > best_v) {
@@ -101,13 +143,32 @@ FCLB_DI int convexExtremeWalk(const ConvexD<S>& c, const V3<S>& d) {
   bool keep = true;
   while (keep) {
     keep = false;
-    const int start = c.nbr[ext];
-    const int count = c.nbr[start];
+#if FCLB_CVX_OLDWALK
+    int2 span;
+    span.x = c.nbr[ext] + 1;
+    span.y = c.nbr[span.x - 1];
+#else
+    const int2 span = __ldg(c.vinfo + ext);  // (offset of the first neighbour in nbr, neighbour count)
+#endif
     const int old_ext = ext;
-    for (int k = start + 1; k <= start + count; k++) {
-      const int nb = c.nbr[k];
+#if FCLB_CVX_UNROLL
+#pragma unroll 4
+#endif
+    for (int k = 0; k < span.y; k++) {
+#if FCLB_CVX_OLDWALK
+      const int nb = c.nbr[span.x + k];
+#else
+      const int nb = __ldg(c.nbr + span.x + k);
+#endif
+#if FCLB_CVX_EAGER
+      // the neighbour's vertex is fetched whether or not it is one of the two parents: the loads of one vertex's
+      // neighbours then do not depend on the walk's decisions and overlap
+      const S nv = dot(d, loadVert(c.verts, nb));
+      if (nb == parent0 || nb == parent1) continue;
+#else
       if (nb == parent0 || nb == parent1) continue;
       const S nv = dot(d, loadVert(c.verts, nb));
+#endif
       if (nv > ext_v) {
         parent1 = ext;
         keep = true;
