@@ -275,6 +275,10 @@ FCLB_DI bool shapeTriangleHit(const LeafCtx<S>& c, const V3<S> P[3]) {
 
 // pop width of a query that wants only a few contacts; measured on C3 / C4 (B200): 32 -> 4.76 / 23.4 ms,
 // 16 -> 5.04 / 25.1 ms, 8 -> 5.85 / 28.7 ms (most of the work is proving the non-colliding queries separate)
+// the eager leaf stage (few contacts wanted) runs as soon as this many triangles are queued
+#ifndef FCLB_EAGER_LEAF_MIN
+#define FCLB_EAGER_LEAF_MIN 1
+#endif
 #ifndef FCLB_EAGER_WIDTH
 #define FCLB_EAGER_WIDTH 32
 #endif
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(kBsWarps * 32, FCLB_SCENE_MIN_BLOCKS) bvhShape
         nleaf += __popc(lm);
         __syncwarp();
       }
-      if (nleaf >= 32 || ((sp == 0 || eager) && nleaf > 0)) {
+      if (nleaf >= 32 || (sp == 0 && nleaf > 0) || (eager && nleaf >= FCLB_EAGER_LEAF_MIN)) {
         const int batch = nleaf < 32 ? nleaf : 32;
         bool hit = false;
         int tri_id = -1;
