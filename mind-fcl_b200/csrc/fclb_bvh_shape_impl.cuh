@@ -416,9 +416,211 @@ __global__ void __launch_bounds__(kBsWarps * 32, FCLB_SCENE_MIN_BLOCKS) bvhShape
   }
 }
 
+#ifndef FCLB_MESH_SHAPE_PACKED_KERNEL
+#define FCLB_MESH_SHAPE_PACKED_KERNEL 0
+#endif
+#if FCLB_MESH_SHAPE_PACKED_KERNEL
+// ---- boolean queries, four per warp ----------------------------------------------------------------
+// A boolean mesh-shape query (max_contacts == 1, no contact sink) keeps 8.5 of 32 lanes busy in its node tests and 2.5 in
+// its leaf tests (ncu, C4): the frontier of a depth-first walk that stops at the first hit is narrow.  Here a warp runs
+// FOUR queries, one per group of 8 lanes, through ONE warp-uniform loop: every trip each group pops up to 8 nodes of its
+// own stack, tests them, pushes the children, and tests the triangles it found.  A group that finishes takes the next
+// query from the work counter (its OBB fit runs on all 32 lanes, as in the kernel above).  Same node / leaf tests and
+// the same answer per query; `first_tri` is a colliding triangle, as above not necessarily the depth-first one.
+// MEASURED (B200, C4 mesh-shape launch, same box): 51.9 ms against 24.8 ms for the one-query-per-warp kernel -- a trip now
+// lasts as long as its slowest group (an MPR leaf test in one group stalls the node tests of the other three, and every
+// refill runs its OBB fit in front of all four), which costs more than the fuller lanes give back.  Compiled out
+// (-DFCLB_MESH_SHAPE_PACKED_KERNEL=1 builds it, FCLB_MESH_SHAPE_PACKED=1 selects it); kept as the record of the experiment.
+constexpr int kBpGroups = 4, kBpLanes = 8;
+constexpr int kBpStackCap = (kBsStackCap + kBsLeafCap) / kBpGroups;  // 272 per group; near the cap a group pops one node per trip
+
+template <typename S, int T0>
+__global__ void __launch_bounds__(kBsWarps * 32, FCLB_SCENE_MIN_BLOCKS) bvhShapePackedKernel(BvhShapeArgs a) {
+  extern __shared__ __align__(16) int s_bs[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / kBpLanes, li = lane % kBpLanes;
+  int* stack = s_bs + size_t(warp) * (kBsStackCap + kBsLeafCap) + grp * kBpStackCap;
+  S* fit_pts = reinterpret_cast<S*>(s_bs + size_t(kBsWarps) * (kBsStackCap + kBsLeafCap)) + size_t(warp) * 3 * kFitMaxPoints;
+  const S* __restrict__ nodes = static_cast<const S*>(a.nodes);
+  const S* __restrict__ tris = static_cast<const S*>(a.tris);
+  const unsigned gshift = unsigned(grp * kBpLanes);
+  const unsigned lt_in_group = (1u << li) - 1u;
+  unsigned long long st_bv = 0, st_leaf = 0;
+  bool more = true;
+
+  LeafCtx<S> ctx;
+  NodeD<S> shape_bv;
+  bool active = false;
+  size_t q = 0;
+  int sp = 0;
+  uint32_t count = 0;
+  int first = -1;
+
+  while (true) {
+    // ---- refill: every idle group takes one query; the fits run one after the other on the whole warp
+    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    if (more && idle) {
+      unsigned need = 0;
+#pragma unroll
+      for (int g = 0; g < kBpGroups; g++)
+        if ((idle >> (g * kBpLanes)) & 1u) need |= 1u << g;
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      int k = 0;
+#pragma unroll
+      for (int g = 0; g < kBpGroups; g++) {
+        if (!((need >> g) & 1u)) continue;
+        const unsigned long long q64 = base + k;
+        k++;
+        if (q64 >= a.n) {
+          more = false;
+          continue;
+        }
+        LeafCtx<S> c;
+        const uint32_t sid = a.shape_ids[q64];
+        c.shape = bindShape(static_cast<const ShapeD<S>*>(a.shapes), static_cast<const ConvexD<S>*>(a.convex), sid);
+        c.tf_mesh = loadPose(static_cast<const S*>(a.poses_mesh), size_t(q64));
+        c.tf_shape = loadPose(static_cast<const S*>(a.poses_shape), size_t(q64));
+        c.toshape1 = mulMtM(c.tf_mesh.R, c.tf_shape.R);
+        c.toshape0 = compose(inverse(c.tf_shape), c.tf_mesh);
+        c.tol = S(a.tol);
+        c.max_iter = a.max_iter;
+        const NodeD<S> bv = shapeWorldObb(c.shape, static_cast<const BoundD<S>*>(a.bound) + sid, c.tf_shape, fit_pts, lane);
+        __syncwarp();
+        if (grp == g) {
+          ctx = c;
+          shape_bv = bv;
+          q = size_t(q64);
+          active = true;
+          sp = 1;
+          count = 0;
+          first = -1;
+          if (li == 0) stack[0] = 0;
+        }
+      }
+      __syncwarp();
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0) break;
+
+    // ---- one step of every active group: pop <= 8 nodes, test, push children, collect triangles
+    int take = 0;
+    if (active) {
+      take = sp < kBpLanes ? sp : kBpLanes;
+      if (sp + take > kBpStackCap - 2 * kBpLanes) take = 1;
+    }
+    int id = -1;
+    if (li < take) id = stack[sp - 1 - li];
+    sp -= take;
+    __syncwarp();
+    bool expand = false, leaf = false;
+    int c0 = 0;
+    if (li < take) {
+      const NodeD<S> nd = loadNode(nodes, id);
+      st_bv++;
+      if (obbOverlap(ctx.tf_mesh.R, ctx.tf_mesh.t, shape_bv, nd)) {
+        if (nd.first_child < 0) {
+          leaf = true;
+          c0 = -(nd.first_child + 1);
+        } else {
+          expand = true;
+          c0 = nd.first_child;
+        }
+      }
+    }
+    const unsigned em = (__ballot_sync(0xffffffffu, expand) >> gshift) & 0xffu;
+    bool overflow = false;
+    if (active && sp + 2 * __popc(em) > kBpStackCap) {  // deeper than the head room: report, never corrupt
+      overflow = true;
+      expand = false;
+    }
+    if (expand) {
+      const int pos = sp + 2 * __popc(em & lt_in_group);
+      stack[pos] = c0;
+      stack[pos + 1] = c0 + 1;
+    }
+    if (active && !overflow) sp += 2 * __popc(em);
+    // the triangles found in this step are tested right away, by the lanes that found them
+    bool hit = false;
+    if (leaf) {
+      V3<S> P[3];
+      loadTri(tris, c0, P);
+      st_leaf++;
+      hit = shapeTriangleHit<S, T0>(ctx, P);
+    }
+    const unsigned hm = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xffu;
+    const int hit_tri = __shfl_sync(0xffffffffu, c0, hm ? int(gshift) + __ffs(hm) - 1 : lane);
+    bool finished = false;
+    if (active) {
+      if (hm) {
+        first = hit_tri;
+        count = 1;
+        finished = true;
+      } else if (sp == 0 || overflow) {
+        finished = true;
+      }
+      if (overflow && li == 0) atomicAdd(&a.stats[2], 1ull);
+    }
+    if (finished) {
+      if (li == 0) {
+        a.counts[q] = count;
+        if (a.first_tri) a.first_tri[q] = first;
+      }
+      active = false;
+    }
+    __syncwarp();
+  }
+  if (a.stats) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      st_bv += __shfl_xor_sync(0xffffffffu, st_bv, off);
+      st_leaf += __shfl_xor_sync(0xffffffffu, st_leaf, off);
+    }
+    if (lane == 0) {
+      atomicAdd(&a.stats[0], st_bv);
+      atomicAdd(&a.stats[1], st_leaf);
+    }
+  }
+}
+
+// FCLB_MESH_SHAPE_PACKED=0 keeps boolean queries on the one-query-per-warp kernel
+inline bool meshShapePackedEnabled() {
+  static int v = [] {
+    const char* e = getenv("FCLB_MESH_SHAPE_PACKED");
+    return e ? atoi(e) : 0;
+  }();
+  return v != 0;
+}
+
+#endif
+
 template <typename S>
 cudaError_t launchBvhShape(int type0, const BvhShapeArgs& a, int grid, cudaStream_t st) {
   const size_t smem = size_t(kBsWarps) * ((kBsStackCap + kBsLeafCap) * sizeof(int) + 3 * kFitMaxPoints * sizeof(S));
+#if FCLB_MESH_SHAPE_PACKED_KERNEL
+  const bool packed = meshShapePackedEnabled() && a.max_contacts == 1 && !a.out_b1 && !a.out_box && !a.cand.count && a.stats;
+  if (packed) {
+#define FCLB_BP_CASE(T)                                                                                          \
+  case T: {                                                                                                      \
+    cudaError_t e_ = cudaFuncSetAttribute(bvhShapePackedKernel<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); \
+    if (e_ != cudaSuccess) return e_;                                                                            \
+    bvhShapePackedKernel<S, T><<<grid, kBsWarps * 32, smem, st>>>(a);                                            \
+    return cudaGetLastError();                                                                                   \
+  }
+    switch (type0) {
+      FCLB_BP_CASE(ST_BOX)
+      FCLB_BP_CASE(ST_SPHERE)
+      FCLB_BP_CASE(ST_CONVEX)
+      default: {
+        cudaError_t e_ = cudaFuncSetAttribute(bvhShapePackedKernel<S, ST_DYNAMIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e_ != cudaSuccess) return e_;
+        bvhShapePackedKernel<S, ST_DYNAMIC><<<grid, kBsWarps * 32, smem, st>>>(a);
+        return cudaGetLastError();
+      }
+    }
+#undef FCLB_BP_CASE
+  }
+#endif
 #define FCLB_BS_CASE(T)                                                                                          \
   case T: {                                                                                                      \
     cudaError_t e_ = cudaFuncSetAttribute(bvhShapeCollideKernel<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); \
