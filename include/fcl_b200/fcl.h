@@ -30,6 +30,7 @@
 #include <cstdlib>
 #include <functional>
 #include <iostream>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -1001,59 +1002,125 @@ struct ContinuousCollisionQuery {
   const CollisionGeometry<S>* o2;
   Transform3<S> tf2;
 };
-// one C-ABI call for the whole batch; scene geometries are not served by the device path yet (warning, no contact)
+// one C-ABI call for the shape pairs of the batch and one per mesh for its (shape, mesh) / (mesh, shape) queries
+// (the reference's CCD matrix serves OBB trees, translational_collision_func_matrix-inl.h:469-489; our BVHModel<OBBRSS>
+// has the same hierarchy, see fclb_translational_ccd_mesh_batch_host); heightmap / octree queries are not on the
+// device path yet (warning, no contact)
 template <typename S>
 void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queries, const ContinuousCollisionRequest<S>& request,
                            std::vector<ContinuousCollisionResult<S>>& results) {
   const std::size_t n = queries.size();
   results.assign(n, ContinuousCollisionResult<S>());
   if (n == 0 || request.num_max_contacts == 0) return;
+  fclb_ccd_request rq{};
+  rq.request_type = uint32_t(request.request_type);
+  rq.max_contacts = uint32_t(std::min<std::size_t>(request.num_max_contacts, 0xffffffffu));
+  rq.zero_movement_tolerance = double(request.zero_movement_tolerance);
+  rq.gjk_tolerance = double(request.gjk_tolerance);
+  rq.max_gjk_iterations = request.max_gjk_iterations;
   std::vector<fclb_shape> shapes;
   std::vector<fclb_pair> pairs;
   std::vector<S> p1, p2, disp;
   std::vector<std::size_t> idx;
+  struct MeshGroup {
+    bool mesh_moves;
+    std::vector<fclb_shape> shapes;
+    std::vector<uint32_t> ids;
+    std::vector<S> pose_shape, pose_mesh, disp;
+    std::vector<std::size_t> idx;
+  };
+  std::map<std::pair<fclb_handle, bool>, MeshGroup> meshes;
+  auto push12 = [](std::vector<S>& v, const Transform3<S>& tf) {
+    v.resize(v.size() + 12);
+    tf.toPose12(&v[v.size() - 12]);
+  };
   for (std::size_t q = 0; q < n; q++) {
     const auto& Q = queries[q];
-    if (!Q.o1->isShape() || !Q.o2->isShape()) {
+    const bool s1 = Q.o1->isShape(), s2 = Q.o2->isShape();
+    const bool m1 = Q.o1->getNodeType() == BV_OBBRSS, m2 = Q.o2->getNodeType() == BV_OBBRSS;
+    if (s1 && s2) {
+      pairs.push_back(fclb_pair{uint32_t(shapes.size()), uint32_t(shapes.size() + 1)});
+      shapes.push_back(Q.o1->shapeRecord());
+      shapes.push_back(Q.o2->shapeRecord());
+      push12(p1, Q.tf1);
+      push12(p2, Q.tf2);
+      for (int k = 0; k < 3; k++) disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
+      disp.push_back(Q.o1_displacement.scalar_displacement);
+      idx.push_back(q);
+    } else if ((s1 && m2) || (m1 && s2)) {
+      const bool mesh_moves = m1;
+      const CollisionGeometry<S>* shape = s1 ? Q.o1 : Q.o2;
+      const CollisionGeometry<S>* mesh = s1 ? Q.o2 : Q.o1;
+      MeshGroup& g = meshes[std::make_pair(detail::sceneHandle(mesh), mesh_moves)];
+      g.mesh_moves = mesh_moves;
+      g.ids.push_back(uint32_t(g.shapes.size()));
+      g.shapes.push_back(shape->shapeRecord());
+      push12(g.pose_shape, s1 ? Q.tf1 : Q.tf2);
+      push12(g.pose_mesh, s1 ? Q.tf2 : Q.tf1);
+      for (int k = 0; k < 3; k++) g.disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
+      g.disp.push_back(Q.o1_displacement.scalar_displacement);
+      g.idx.push_back(q);
+    } else {
       std::cerr << "Warning: collision function between node type " << Q.o1->getNodeType() << " and node type " << Q.o2->getNodeType()
                 << " is not supported" << std::endl;
-      continue;
     }
-    pairs.push_back(fclb_pair{uint32_t(shapes.size()), uint32_t(shapes.size() + 1)});
-    shapes.push_back(Q.o1->shapeRecord());
-    shapes.push_back(Q.o2->shapeRecord());
-    p1.resize(p1.size() + 12);
-    p2.resize(p2.size() + 12);
-    Q.tf1.toPose12(&p1[p1.size() - 12]);
-    Q.tf2.toPose12(&p2[p2.size() - 12]);
-    for (int k = 0; k < 3; k++) disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
-    disp.push_back(Q.o1_displacement.scalar_displacement);
-    idx.push_back(q);
   }
-  if (pairs.empty()) return;
-  fclb_handle table = 0;
-  detail::check(fclb_shapes_upload(shapes.data(), uint32_t(shapes.size()), &table), "fclb_shapes_upload");
-  fclb_ccd_request rq{};
-  rq.request_type = uint32_t(request.request_type);
-  rq.max_contacts = uint32_t(request.num_max_contacts);
-  rq.zero_movement_tolerance = double(request.zero_movement_tolerance);
-  rq.gjk_tolerance = double(request.gjk_tolerance);
-  rq.max_gjk_iterations = request.max_gjk_iterations;
-  std::vector<uint8_t> hit(pairs.size());
-  std::vector<S> toc(2 * pairs.size());
-  if (detail::batchOk(fclb_translational_ccd_batch_host(table, pairs.data(), p1.data(), p2.data(), disp.data(), pairs.size(),
-                                                        detail::scalarType<S>(), &rq, hit.data(), toc.data()),
-                      "fclb_translational_ccd_batch_host"))
-    for (std::size_t i = 0; i < pairs.size(); i++)
-      if (hit[i]) {
-        ContinuousCollisionContact<S> c;
-        c.o1 = queries[idx[i]].o1;
-        c.o2 = queries[idx[i]].o2;
-        c.toc.lower_bound = toc[2 * i];
-        c.toc.upper_bound = toc[2 * i + 1];
-        results[idx[i]].AddContact(c);
+  if (!pairs.empty()) {
+    fclb_handle table = 0;
+    detail::check(fclb_shapes_upload(shapes.data(), uint32_t(shapes.size()), &table), "fclb_shapes_upload");
+    std::vector<uint8_t> hit(pairs.size());
+    std::vector<S> toc(2 * pairs.size());
+    if (detail::batchOk(fclb_translational_ccd_batch_host(table, pairs.data(), p1.data(), p2.data(), disp.data(), pairs.size(),
+                                                          detail::scalarType<S>(), &rq, hit.data(), toc.data()),
+                        "fclb_translational_ccd_batch_host"))
+      for (std::size_t i = 0; i < pairs.size(); i++)
+        if (hit[i]) {
+          ContinuousCollisionContact<S> c;
+          c.o1 = queries[idx[i]].o1;
+          c.o2 = queries[idx[i]].o2;
+          c.toc.lower_bound = toc[2 * i];
+          c.toc.upper_bound = toc[2 * i + 1];
+          results[idx[i]].AddContact(c);
+        }
+    fclb_release(table);
+  }
+  for (auto& kv : meshes) {
+    MeshGroup& g = kv.second;
+    const std::size_t m = g.ids.size();
+    fclb_handle table = 0;
+    detail::check(fclb_shapes_upload(g.shapes.data(), uint32_t(g.shapes.size()), &table), "fclb_shapes_upload");
+    uint32_t keep = uint32_t(std::min<std::size_t>(request.num_max_contacts, 64));
+    std::vector<uint32_t> counts(m);
+    std::vector<int64_t> prim;
+    std::vector<S> toc;
+    for (int pass = 0; pass < 2; pass++) {  // a second pass with room for the largest count, when 64 were not enough
+      prim.assign(m * keep, -1);
+      toc.assign(m * keep * 2, S(-1));
+      if (!detail::batchOk(fclb_translational_ccd_mesh_batch_host(kv.first.first, table, g.ids.data(), g.pose_shape.data(),
+                                                                  g.pose_mesh.data(), g.disp.data(), m, detail::scalarType<S>(), &rq,
+                                                                  g.mesh_moves ? 1 : 0, keep, counts.data(), prim.data(), toc.data()),
+                           "fclb_translational_ccd_mesh_batch_host")) {
+        counts.assign(m, 0);
+        break;
       }
-  fclb_release(table);
+      const uint32_t most = *std::max_element(counts.begin(), counts.end());
+      if (most <= keep) break;
+      keep = most;
+    }
+    for (std::size_t i = 0; i < m; i++)
+      for (uint32_t k = 0; k < counts[i] && k < keep; k++) {
+        // both matrix entries report o1 = the shape, o2 = the mesh, b2 = triangle id (bvh_ccd_solver-inl.h:199-204, :572-584)
+        const auto& Q = queries[g.idx[i]];
+        ContinuousCollisionContact<S> c;
+        c.o1 = g.mesh_moves ? Q.o2 : Q.o1;
+        c.o2 = g.mesh_moves ? Q.o1 : Q.o2;
+        c.b2 = prim[i * keep + k];
+        c.toc.lower_bound = toc[(i * keep + k) * 2];
+        c.toc.upper_bound = toc[(i * keep + k) * 2 + 1];
+        results[g.idx[i]].AddContact(c);
+      }
+    fclb_release(table);
+  }
 }
 template <typename S>
 void translational_ccd(const CollisionGeometry<S>* o1, const Transform3<S>& tf1, const TranslationalDisplacement<S>& o1_displacement,

@@ -219,6 +219,34 @@ int fclb_translational_ccd_batch_dev(fclb_handle shapes, const fclb_pair* pairs,
                                      const void* displacements, size_t n, int scalar_type, const fclb_ccd_request* req,
                                      uint8_t* out_hit, void* out_toc);
 
+/* ---- translational continuous collision, shape vs mesh ----------------------------------------------
+ * fcl::translational_ccd(shape, tf_shape, displacement, BVHModel<OBB<S>>, tf_mesh, request, result) per query
+ * (matrix entries ShapeBVH_ / BVH_ShapeTranslationalCollideImpl<Shape, OBB<S>>,
+ * detail/ccd/translational_collision_func_matrix-inl.h:469-487 -> bvh_ccd_solver-inl.h:120-218 RunSweptBV): the mesh's
+ * OBB tree is walked with the swept-box test (BoxPairTranslationalCCD::IsDisjoint, every node narrowing its parent's
+ * time-of-collision interval) and every surviving triangle runs the swept-volume MPR against the shape
+ * (RunShapeSimplex, shape_pair_ccd-inl.h:196-212).  `bvh` is a handle of fclb_bvh_upload / fclb_bvh_build: the
+ * reference's BVHModel<OBB<S>> has the same hierarchy and internal boxes, its leaf boxes (3-point fit) are derived
+ * from the triangles on the device.
+ *   displacements  4 S per query: unit axis + scalar displacement of the MOVING object, in its own frame
+ *   mesh_moves     0: the shape moves (fcl::translational_ccd(shape, ..., mesh, ...));
+ *                  1: the mesh moves (fcl::translational_ccd(mesh, ..., shape, ...), RunMeshShape :572-584)
+ *   out_counts[q]  ContinuousCollisionResult::num_contacts(), at most req->max_contacts
+ *   out_prim[q * max_keep + k], out_toc[(q * max_keep + k) * 2 ..]   ContinuousCollisionContact::b2 (triangle id)
+ *                  and ::toc of the k-th contact IN THE REFERENCE'S ORDER (its depth-first walk visits the right
+ *                  child first and stops at max_contacts); -1 beyond the count.  toc is the leaf's swept-box
+ *                  interval (kNotRequested, kBoxApproximate) or MPR's time sample (kOneTocSample).
+ * Convex shapes with exactly 1, 2, 3 or 6 vertices return FCLB_ERR_UNSUPPORTED (computeBV<OBB, Convex> uses the
+ * small-set fits for them).  Bit-identical to the reference (tests/test_ccd_mesh_gpu.py). */
+int fclb_translational_ccd_mesh_batch_host(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids,
+                                           const void* poses_shape, const void* poses_mesh, const void* displacements,
+                                           size_t n, int scalar_type, const fclb_ccd_request* req, int mesh_moves,
+                                           uint32_t max_keep, uint32_t* out_counts, int64_t* out_prim, void* out_toc);
+int fclb_translational_ccd_mesh_batch_dev(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids,
+                                          const void* poses_shape, const void* poses_mesh, const void* displacements,
+                                          size_t n, int scalar_type, const fclb_ccd_request* req, int mesh_moves,
+                                          uint32_t max_keep, uint32_t* out_counts, int64_t* out_prim, void* out_toc);
+
 /* ---- meshes: BVHModel<OBBRSS<S>> flattened by the caller ------------------------
  * (reference geometry/bvh/BVH_model.h:63-196, BV_node_base.h:50-82).  Only the
  * OBB half of OBBRSS is ever read by collide (math/bv/OBBRSS-inl.h:130-135).

@@ -745,6 +745,7 @@ static int bvh_release_one(fclb_handle h) {
   cudaFree(it->second->tris);
   cudaFree(it->second->d_range);
   cudaFree(it->second->d_prim);
+  cudaFree(it->second->d_dfs_rank);
   delete it->second;
   bvhTable().erase(it);
   return FCLB_OK;

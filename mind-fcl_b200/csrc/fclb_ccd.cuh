@@ -188,15 +188,18 @@ FCLB_DI bool tocOnAxis(S h1, S abs_disp, bool pos, S h2, S off, TocInterval<S>& 
 // box directions), unit_axis: displacement direction in box 1's frame.
 template <typename S>
 FCLB_DI bool boxPairCcdDisjoint(const M3<S>& axis1, const V3<S>& To1, const V3<S>& ext1, const V3<S>& unit_axis, S scalar_disp,
-                                const M3<S>& axis2, const V3<S>& To2, const V3<S>& ext2, TocInterval<S>& interval, S zero_tol) {
+                                const M3<S>& axis2, const V3<S>& To2, const V3<S>& ext2, TocInterval<S>& interval, S zero_tol,
+                                bool keep_init = false) {  // keep_init: `interval` holds init_toc_interval_bound (:378-392)
   const V3<S> t_world = To2 - To1;
   const V3<S> t21 = mulMtV(axis1, t_world);
   const M3<S> R = mulMtM(axis1, axis2);  // rotation_2in1
   M3<S> Rabs;
 #pragma unroll
   for (int i = 0; i < 9; i++) Rabs.m[i] = fabs_(R.m[i]);
-  interval.lo = S(0.0);
-  interval.hi = S(1.0);
+  if (!keep_init) {
+    interval.lo = S(0.0);
+    interval.hi = S(1.0);
+  }
   {  // box-1 axes
     const V3<S> disp1 = unit_axis * scalar_disp;
     const V3<S> h2 = mulMV(Rabs, ext2);

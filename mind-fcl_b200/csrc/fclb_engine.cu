@@ -888,6 +888,16 @@ int fclb_signed_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, c
   // pass 2: GJK + EPA (256 faces, 255 iterations, eps^(7/8)) for the penetration of the others
   int32_t *d_gjk = nullptr, *d_epa = nullptr;
   void* d_geom = nullptr;
+  struct Scratch {  // freed on every return path, the early ones of FCLB_CUDA included
+    int32_t*& a;
+    int32_t*& b;
+    void*& c;
+    ~Scratch() {
+      cudaFree(a);
+      cudaFree(b);
+      cudaFree(c);
+    }
+  } scratch{d_gjk, d_epa, d_geom};
   FCLB_CUDA(cudaMalloc(&d_gjk, n * 4));
   FCLB_CUDA(cudaMalloc(&d_epa, n * 4));
   FCLB_CUDA(cudaMalloc(&d_geom, n * 7 * ss));
@@ -913,9 +923,6 @@ int fclb_signed_distance_batch_dev(fclb_handle shapes, const fclb_pair* pairs, c
     e.launches += 1;
     if (cudaStreamSynchronize(e.compute) != cudaSuccess) rc = fail(FCLB_ERR_CUDA, "signed distance combine failed");
   }
-  cudaFree(d_gjk);
-  cudaFree(d_epa);
-  cudaFree(d_geom);
   return rc;
 }
 

@@ -179,6 +179,40 @@ class RefOracle(_Oracle):
           gjk_tol, max_iter, _p(hit), _p(toc), threads)
         return hit, toc
 
+
+    # ---- translational continuous collision, shape vs mesh (reference BVHModel<OBB<S>>) ----
+    def bvh_obb_create(self, verts, tris):
+        verts = np.ascontiguousarray(verts, np.float64)
+        tris = np.ascontiguousarray(tris, np.int32)
+        f = self.fn("bvh_obb_create")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        return int(f(_p(verts), len(verts), _p(tris), len(tris)))
+
+    def bvh_obb_export(self, mesh_id, n_nodes, dtype):
+        obb = np.zeros((n_nodes, 15), dtype)
+        child = np.zeros(n_nodes, np.int32)
+        f = self.fn("bvh_obb_export")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        f(mesh_id, _st(dtype), _p(obb), _p(child))
+        return obb, child
+
+    def translational_ccd_mesh_batch(self, mesh_id, shapes, shape_ids, poses_shape, poses_mesh, disp, request_type=0,
+                                     max_contacts=1, zero_tol=0.0, mesh_moves=False, keep=8, threads=1):
+        """fcl::translational_ccd(shape, mesh) per query: (counts u32 [n], primitive ids i64 [n, keep], toc [n, keep, 2])"""
+        n = len(shape_ids)
+        dt = poses_shape.dtype
+        counts = np.zeros(n, np.uint32)
+        prim = np.full((n, keep), -1, np.int64)
+        toc = np.full((n, keep, 2), -1, dt)
+        arr = _shape_array(shapes)
+        ids = np.ascontiguousarray(shape_ids, np.uint32)
+        f = self.fn("translational_ccd_mesh_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                      C.c_uint32, C.c_double, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(dt), mesh_id, C.cast(arr, C.c_void_p), len(shapes), _p(ids), _p(poses_shape), _p(poses_mesh), _p(disp), n,
+          request_type, max_contacts, zero_tol, 1 if mesh_moves else 0, keep, _p(counts), _p(prim), _p(toc), threads)
+        return counts, prim, toc
+
     # ---- meshes (reference BVHModel<OBBRSS<S>>) ----
     def bvh_create(self, verts, tris):
         verts = np.ascontiguousarray(verts, np.float64)

@@ -287,6 +287,138 @@ int fclref_bvh_visit_counts(int scalar_type, int id1, int id2, const void* poses
 
 }  // extern "C"
 
+
+// ---- translational continuous collision, shape vs mesh -----------------------------------------
+// fcl::translational_ccd(shape, tf_shape, displacement, BVHModel<OBB<S>>, tf_mesh, request, result)
+// (narrowphase/continuous_collision-inl.h; matrix entry ShapeBVH_TranslationalCollideImpl<Shape, OBB<S>>,
+// detail/ccd/translational_collision_func_matrix-inl.h:469-477 -> bvh_ccd_solver-inl.h RunSweptBV).  The CCD matrix
+// has OBB and AABB trees only, so the mesh is built as BVHModel<OBB<S>> (same builder, same OBBs as the OBB half of
+// the OBBRSS tree: fclref_bvh_obb_export lets the tests check that).
+namespace fclref {
+std::shared_ptr<fcl::ShapeBase<float>> makeShapeF(const void* rec);
+std::shared_ptr<fcl::ShapeBase<double>> makeShapeD(const void* rec);
+}  // namespace fclref
+namespace {
+struct ShapeRecM {  // = ShapeRec of ref_harness.cpp
+  int32_t type;
+  uint32_t convex;
+  double p[3];
+};
+template <typename S>
+using ObbModel = fcl::BVHModel<fcl::OBB<S>>;
+struct ObbMeshRec {
+  std::shared_ptr<ObbModel<float>> f;
+  std::shared_ptr<ObbModel<double>> d;
+};
+std::vector<ObbMeshRec>& obbMeshes() {
+  static std::vector<ObbMeshRec> m;
+  return m;
+}
+template <typename S>
+std::shared_ptr<ObbModel<S>> buildObb(const double* verts, int n_verts, const int* tris, int n_tris) {
+  std::vector<fcl::Vector3<S>> pts;
+  std::vector<fcl::MeshSimplex> simp;
+  for (int i = 0; i < n_verts; i++) pts.emplace_back(S(verts[3 * i]), S(verts[3 * i + 1]), S(verts[3 * i + 2]));
+  for (int i = 0; i < n_tris; i++) simp.emplace_back(tris[3 * i], tris[3 * i + 1], tris[3 * i + 2]);
+  auto m = std::make_shared<ObbModel<S>>();
+  m->beginModel();
+  m->addSubModel(pts, simp);
+  m->endModel();
+  m->computeLocalAABB();
+  return m;
+}
+template <typename S>
+struct ObbOf;
+template <>
+struct ObbOf<float> {
+  static ObbModel<float>* get(int id) { return obbMeshes().at(id).f.get(); }
+  static std::shared_ptr<fcl::ShapeBase<float>> shape(const ShapeRecM* r) { return fclref::makeShapeF(r); }
+};
+template <>
+struct ObbOf<double> {
+  static ObbModel<double>* get(int id) { return obbMeshes().at(id).d.get(); }
+  static std::shared_ptr<fcl::ShapeBase<double>> shape(const ShapeRecM* r) { return fclref::makeShapeD(r); }
+};
+
+template <typename S>
+void ccdMeshBatch(int id, const ShapeRecM* shapes, int n_shapes, const uint32_t* shape_ids, const S* poses_shape,
+                  const S* poses_mesh, const S* disp, size_t n, int request_type, uint32_t max_contacts, double zero_tol,
+                  int mesh_moves, uint32_t keep, uint32_t* counts, int64_t* prim, S* toc, int threads) {
+  std::vector<std::shared_ptr<fcl::ShapeBase<S>>> tab;
+  for (int i = 0; i < n_shapes; i++) {
+    tab.push_back(ObbOf<S>::shape(shapes + i));
+    tab.back()->computeLocalAABB();
+  }
+  const ObbModel<S>* mesh = ObbOf<S>::get(id);
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    fcl::ContinuousCollisionRequest<S> req;
+    req.request_type = static_cast<fcl::TimeOfCollisionRequestType>(request_type);
+    req.num_max_contacts = max_contacts;
+    if (zero_tol > 0) req.zero_movement_tolerance = S(zero_tol);
+    for (size_t q = b; q < e; q++) {
+      const auto tf_s = loadPose<S>(poses_shape + 12 * q);
+      const auto tf_m = loadPose<S>(poses_mesh + 12 * q);
+      fcl::TranslationalDisplacement<S> d;
+      d.unit_axis_in_shape1 = fcl::Vector3<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]);
+      d.scalar_displacement = disp[4 * q + 3];
+      fcl::ContinuousCollisionResult<S> res;
+      if (mesh_moves)  // the displacement is the MESH's, in the mesh frame (matrix entry [BV_OBB][GEOM_x])
+        fcl::translational_ccd<S>(mesh, tf_m, d, tab[shape_ids[q]].get(), tf_s, req, res);
+      else
+        fcl::translational_ccd<S>(tab[shape_ids[q]].get(), tf_s, d, mesh, tf_m, req, res);
+      counts[q] = uint32_t(res.num_contacts());
+      for (uint32_t k = 0; k < keep && k < res.num_contacts(); k++) {
+        const auto& c = res.raw_contacts()[k];
+        prim[size_t(q) * keep + k] = c.b2;
+        toc[(size_t(q) * keep + k) * 2] = c.toc.lower_bound;
+        toc[(size_t(q) * keep + k) * 2 + 1] = c.toc.upper_bound;
+      }
+    }
+  });
+}
+}  // namespace
+
+extern "C" int fclref_bvh_obb_create(const double* verts, int n_verts, const int* tris, int n_tris) {
+  ObbMeshRec r;
+  r.f = buildObb<float>(verts, n_verts, tris, n_tris);
+  r.d = buildObb<double>(verts, n_verts, tris, n_tris);
+  obbMeshes().push_back(r);
+  return int(obbMeshes().size()) - 1;
+}
+// 15 S per node (axis row-major, To, extent) + first_child, as fclref_bvh_export does for the OBBRSS model
+extern "C" int fclref_bvh_obb_export(int id, int scalar_type, void* obb, int32_t* child) {
+  auto run = [&](auto* m, auto* out) {
+    for (int i = 0; i < m->getNumBVs(); i++) {
+      const auto& nd = m->getBV(i);
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) out[15 * i + 3 * r + c] = nd.bv.axis(r, c);
+      for (int k = 0; k < 3; k++) out[15 * i + 9 + k] = nd.bv.To[k];
+      for (int k = 0; k < 3; k++) out[15 * i + 12 + k] = nd.bv.extent[k];
+      child[i] = nd.first_child;
+    }
+  };
+  if (scalar_type == 0)
+    run(ObbOf<float>::get(id), (float*)obb);
+  else
+    run(ObbOf<double>::get(id), (double*)obb);
+  return 0;
+}
+extern "C" int fclref_translational_ccd_mesh_batch(int scalar_type, int id, const void* shapes, int n_shapes,
+                                                   const uint32_t* shape_ids, const void* poses_shape, const void* poses_mesh,
+                                                   const void* disp, size_t n, int request_type, uint32_t max_contacts,
+                                                   double zero_tol, int mesh_moves, uint32_t keep, uint32_t* counts,
+                                                   int64_t* prim, void* toc, int threads) {
+  if (scalar_type == 0)
+    ccdMeshBatch<float>(id, (const ShapeRecM*)shapes, n_shapes, shape_ids, (const float*)poses_shape, (const float*)poses_mesh,
+                        (const float*)disp, n, request_type, max_contacts, zero_tol, mesh_moves, keep, counts, prim, (float*)toc,
+                        threads);
+  else
+    ccdMeshBatch<double>(id, (const ShapeRecM*)shapes, n_shapes, shape_ids, (const double*)poses_shape,
+                         (const double*)poses_mesh, (const double*)disp, n, request_type, max_contacts, zero_tol, mesh_moves, keep,
+                         counts, prim, (double*)toc, threads);
+  return 0;
+}
+
 // mesh registry access for the other harness translation units (ref_harness_scene.cpp)
 namespace fclref {
 const fcl::BVHModel<fcl::OBBRSS<float>>* meshF(int id) { return get<float>(id); }

@@ -343,6 +343,30 @@ void runBatch() {
       EXPECT_TRUE(std::fabs(toc.lower_bound - S(1.4 / 3.0)) < S(1e-4) && std::fabs(toc.upper_bound - S(2.6 / 3.0)) < S(1e-4));
     }
   }
+  // the same against a mesh, both argument orders: a sphere dropping 2 m onto the two-triangle floor touches both triangles
+  // (contacts in the reference's order: right child first), a sideways sweep above it touches none
+  {
+    Sphere<S> mover(S(0.25));
+    TranslationalDisplacement<S> down, sideways, up;
+    down.unit_axis_in_shape1 = Vector3<S>(0, 0, -1);
+    up.unit_axis_in_shape1 = Vector3<S>(0, 0, 1);
+    sideways.unit_axis_in_shape1 = Vector3<S>(1, 0, 0);
+    down.scalar_displacement = up.scalar_displacement = 2;
+    sideways.scalar_displacement = 1;
+    ContinuousCollisionRequest<S> creq;
+    creq.num_max_contacts = 8;
+    ContinuousCollisionResult<S> hit_r, miss_r, mesh_up;
+    translational_ccd<S>(&mover, at(0, 0, 1), down, &floor, I, creq, hit_r);
+    translational_ccd<S>(&mover, at(0, 0, 1), sideways, &floor, I, creq, miss_r);
+    translational_ccd<S>(&floor, I, up, &mover, at(0, 0, 1), creq, mesh_up);  // the floor rises instead
+    EXPECT_TRUE(hit_r.num_contacts() == 2 && miss_r.num_contacts() == 0 && mesh_up.num_contacts() == 2);
+    if (hit_r.num_contacts() == 2 && mesh_up.num_contacts() == 2) {
+      const auto& c0 = hit_r.raw_contacts()[0];
+      EXPECT_TRUE(c0.o1 == &mover && c0.o2 == &floor && c0.b2 >= 0 && c0.b2 < 2 && c0.b2 != hit_r.raw_contacts()[1].b2);
+      EXPECT_TRUE(c0.toc.lower_bound > S(0.3) && c0.toc.lower_bound < S(0.4));  // first touch after 0.75 m of 2 m
+      EXPECT_TRUE(mesh_up.raw_contacts()[0].o1 == &mover && mesh_up.raw_contacts()[0].b2 == c0.b2);
+    }
+  }
   // UserContactProcessFunctor on the host: keep only contacts on triangle 1, stop after two
   std::vector<CollisionQuery<S>> one_q{{&floor, I, &ball, at(0, 0, S(0.1))}};
   std::vector<CollisionResult<S>> fr;
