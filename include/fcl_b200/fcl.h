@@ -1002,7 +1002,8 @@ struct ContinuousCollisionQuery {
   const CollisionGeometry<S>* o2;
   Transform3<S> tf2;
 };
-// one C-ABI call for the shape pairs of the batch and one per mesh for its (shape, mesh) / (mesh, shape) queries
+// one C-ABI call for the shape pairs of the batch, one per mesh for its (shape, mesh) / (mesh, shape) queries and one per
+// pair of meshes
 // (the reference's CCD matrix serves OBB trees, translational_collision_func_matrix-inl.h:469-489; our BVHModel<OBBRSS>
 // has the same hierarchy, see fclb_translational_ccd_mesh_batch_host); heightmap / octree queries are not on the
 // device path yet (warning, no contact)
@@ -1030,6 +1031,11 @@ void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queri
     std::vector<std::size_t> idx;
   };
   std::map<std::pair<fclb_handle, bool>, MeshGroup> meshes;
+  struct PairGroup {
+    std::vector<S> pose1, pose2, disp;
+    std::vector<std::size_t> idx;
+  };
+  std::map<std::pair<fclb_handle, fclb_handle>, PairGroup> mesh_pairs;
   auto push12 = [](std::vector<S>& v, const Transform3<S>& tf) {
     v.resize(v.size() + 12);
     tf.toPose12(&v[v.size() - 12]);
@@ -1060,10 +1066,51 @@ void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queri
       for (int k = 0; k < 3; k++) g.disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
       g.disp.push_back(Q.o1_displacement.scalar_displacement);
       g.idx.push_back(q);
+    } else if (m1 && m2) {
+      PairGroup& g = mesh_pairs[std::make_pair(detail::sceneHandle(Q.o1), detail::sceneHandle(Q.o2))];
+      push12(g.pose1, Q.tf1);
+      push12(g.pose2, Q.tf2);
+      for (int k = 0; k < 3; k++) g.disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
+      g.disp.push_back(Q.o1_displacement.scalar_displacement);
+      g.idx.push_back(q);
     } else {
       std::cerr << "Warning: collision function between node type " << Q.o1->getNodeType() << " and node type " << Q.o2->getNodeType()
                 << " is not supported" << std::endl;
     }
+  }
+  for (auto& kv : mesh_pairs) {
+    PairGroup& g = kv.second;
+    const std::size_t m = g.idx.size();
+    uint32_t keep = uint32_t(std::min<std::size_t>(request.num_max_contacts, 64));
+    std::vector<uint32_t> counts(m);
+    std::vector<int64_t> prim;
+    std::vector<S> toc;
+    for (int pass = 0; pass < 2; pass++) {
+      prim.assign(m * keep * 2, -1);
+      toc.assign(m * keep * 2, S(-1));
+      if (!detail::batchOk(fclb_translational_ccd_mesh_pair_batch_host(kv.first.first, kv.first.second, g.pose1.data(), g.pose2.data(),
+                                                                       g.disp.data(), m, detail::scalarType<S>(), &rq, keep,
+                                                                       counts.data(), prim.data(), toc.data()),
+                           "fclb_translational_ccd_mesh_pair_batch_host")) {
+        counts.assign(m, 0);
+        break;
+      }
+      const uint32_t most = *std::max_element(counts.begin(), counts.end());
+      if (most <= keep) break;
+      keep = most;
+    }
+    for (std::size_t i = 0; i < m; i++)
+      for (uint32_t k = 0; k < counts[i] && k < keep; k++) {
+        const auto& Q = queries[g.idx[i]];
+        ContinuousCollisionContact<S> c;
+        c.o1 = Q.o1;
+        c.o2 = Q.o2;
+        c.b1 = prim[(i * keep + k) * 2];
+        c.b2 = prim[(i * keep + k) * 2 + 1];
+        c.toc.lower_bound = toc[(i * keep + k) * 2];
+        c.toc.upper_bound = toc[(i * keep + k) * 2 + 1];
+        results[g.idx[i]].AddContact(c);
+      }
   }
   if (!pairs.empty()) {
     fclb_handle table = 0;

@@ -247,6 +247,19 @@ int fclb_translational_ccd_mesh_batch_dev(fclb_handle bvh, fclb_handle shapes, c
                                           size_t n, int scalar_type, const fclb_ccd_request* req, int mesh_moves,
                                           uint32_t max_keep, uint32_t* out_counts, int64_t* out_prim, void* out_toc);
 
+/* mesh vs mesh: fcl::translational_ccd(BVHModel<OBB<S>>, tf1, displacement, BVHModel<OBB<S>>, tf2, request, result)
+ * (TranslationalDisplacementBVH_PairSolverImpl<S, OBB<S>>, bvh_ccd_solver-inl.h:425-551): the walk over node PAIRS, the
+ * swept-volume MPR of (triangle 1 swept, triangle 2) per surviving leaf pair.  displacements: mesh 1's, in its frame.
+ * out_prim[(q * max_keep + k) * 2 ..] = (b1, b2) triangle ids of the k-th contact in the reference's order. */
+int fclb_translational_ccd_mesh_pair_batch_host(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2,
+                                                const void* displacements, size_t n, int scalar_type,
+                                                const fclb_ccd_request* req, uint32_t max_keep, uint32_t* out_counts,
+                                                int64_t* out_prim, void* out_toc);
+int fclb_translational_ccd_mesh_pair_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2,
+                                               const void* displacements, size_t n, int scalar_type,
+                                               const fclb_ccd_request* req, uint32_t max_keep, uint32_t* out_counts,
+                                               int64_t* out_prim, void* out_toc);
+
 /* ---- meshes: BVHModel<OBBRSS<S>> flattened by the caller ------------------------
  * (reference geometry/bvh/BVH_model.h:63-196, BV_node_base.h:50-82).  Only the
  * OBB half of OBBRSS is ever read by collide (math/bv/OBBRSS-inl.h:130-135).

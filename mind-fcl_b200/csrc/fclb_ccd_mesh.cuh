@@ -349,4 +349,260 @@ __global__ void ccdMeshSelectKernel(const unsigned long long* __restrict__ keys,
   }
 }
 
+// ---- mesh vs mesh ------------------------------------------------------------------------------------
+// TranslationalDisplacementBVH_PairSolverImpl<S, OBB<S>>::Run (bvh_ccd_solver-inl.h:425-551): the same walk over PAIRS of
+// nodes; the first tree is descended when the second node is a leaf, or when both are internal and the first box is
+// the larger one (extent.squaredNorm()).  A leaf pair runs RunSimplexPair (shape_pair_ccd-inl.h:214-244): swept-volume
+// MPR of (triangle 1 swept, triangle 2).  The reference's visiting order is encoded per candidate as its PATH: one bit
+// per descent step (0 = the child popped first, i.e. the right one), most significant bit first, so that sorting the
+// hits of a query by path reproduces the order in which the reference's early-terminating walk reports them.
+struct CcdMeshPairArgs {
+  const void* nodes1;
+  const void* tris1;
+  const void* nodes2;
+  const void* tris2;
+  const void* poses1;
+  const void* poses2;
+  const void* disp;  // 4 S per query: unit axis in mesh 1's frame, scalar displacement
+  size_t n;
+  int request_type;
+  double zero_tol, gjk_tol;
+  int max_iter;
+  uint32_t* cand_count;  // [0] appended, [1] stack overflows, [2] paths longer than 64 steps
+  uint32_t cand_cap;
+  uint32_t* cand_q;
+  int2* cand_tri;
+  void* cand_iv;
+  unsigned long long* cand_path;
+  unsigned long long* work_counter;
+  uint32_t* qkey;       // per candidate: the query, 0xffffffff when the triangles are not hit
+  void* cand_toc;
+};
+
+constexpr int kCpStackCap = 512;
+
+template <typename S>
+struct CcdPairStack {  // one warp's slice
+  int2* id;
+  S* iv;
+  unsigned long long* path;
+  unsigned char* depth;
+};
+
+template <typename S>
+__global__ void __launch_bounds__(kCmWarps * 32) ccdMeshPairTraverseKernel(CcdMeshPairArgs a) {
+  extern __shared__ __align__(16) unsigned char s_cp[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long* st_path = reinterpret_cast<unsigned long long*>(s_cp) + size_t(warp) * kCpStackCap;
+  int2* st_id = reinterpret_cast<int2*>(s_cp + size_t(kCmWarps) * kCpStackCap * 8) + size_t(warp) * kCpStackCap;
+  S* st_iv = reinterpret_cast<S*>(s_cp + size_t(kCmWarps) * kCpStackCap * 16) + size_t(warp) * kCpStackCap * 2;
+  unsigned char* st_depth = s_cp + size_t(kCmWarps) * kCpStackCap * (16 + 2 * sizeof(S)) + size_t(warp) * kCpStackCap;
+  const S* __restrict__ nodes1 = static_cast<const S*>(a.nodes1);
+  const S* __restrict__ nodes2 = static_cast<const S*>(a.nodes2);
+  const S* __restrict__ tris1 = static_cast<const S*>(a.tris1);
+  const S* __restrict__ tris2 = static_cast<const S*>(a.tris2);
+  const S* __restrict__ disp = static_cast<const S*>(a.disp);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const S zero_tol = S(a.zero_tol);
+  while (true) {
+    unsigned long long q64 = 0;
+    if (lane == 0) q64 = atomicAdd(a.work_counter, 1ull);
+    q64 = __shfl_sync(0xffffffffu, q64, 0);
+    if (q64 >= a.n) break;
+    const size_t q = size_t(q64);
+    const Pose<S> tf1 = loadPose(static_cast<const S*>(a.poses1), q);
+    const Pose<S> tf2 = loadPose(static_cast<const S*>(a.poses2), q);
+    const V3<S> axis_world = mulMV(tf1.R, mk<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]));
+    const S scalar = disp[4 * q + 3];
+    int sp = 1;
+    if (lane == 0) {
+      st_id[0] = make_int2(0, 0);
+      st_iv[0] = S(0.0);
+      st_iv[1] = S(1.0);
+      st_path[0] = 0ull;
+      st_depth[0] = 0;
+    }
+    __syncwarp();
+    bool overflow = false;
+    while (sp > 0) {
+      int take = sp < 32 ? sp : 32;
+      if (sp + take > kCpStackCap - 64) take = 1;
+      int2 id = make_int2(-1, -1);
+      TocInterval<S> iv;
+      iv.lo = iv.hi = S(0);
+      unsigned long long path = 0;
+      int depth = 0;
+      if (lane < take) {
+        const int e = sp - 1 - lane;
+        id = st_id[e];
+        iv.lo = st_iv[2 * e];
+        iv.hi = st_iv[2 * e + 1];
+        path = st_path[e];
+        depth = st_depth[e];
+      }
+      sp -= take;
+      __syncwarp();
+      bool expand = false, leaf = false, too_deep = false;
+      int2 c_first = make_int2(0, 0), c_second = make_int2(0, 0);
+      int2 tri = make_int2(0, 0);
+      if (lane < take) {
+        NodeD<S> n1 = loadNode(nodes1, id.x), n2 = loadNode(nodes2, id.y);
+        const bool leaf1 = n1.first_child < 0, leaf2 = n2.first_child < 0;
+        const S size1 = sqnorm(n1.extent), size2 = sqnorm(n2.extent);  // (of the stored boxes: compared only when both are internal)
+        if (leaf1) {
+          V3<S> P[3];
+          loadTri(tris1, -(n1.first_child + 1), P);
+          fitObb3(P, n1.axis, n1.To, n1.extent);
+        }
+        if (leaf2) {
+          V3<S> P[3];
+          loadTri(tris2, -(n2.first_child + 1), P);
+          fitObb3(P, n2.axis, n2.To, n2.extent);
+        }
+        M3<S> a1, a2;
+        V3<S> t1, t2;
+        obbToWorld(tf1, n1.axis, n1.To, a1, t1);
+        obbToWorld(tf2, n2.axis, n2.To, a2, t2);
+        const V3<S> unit1 = mulMtV(a1, axis_world);
+        if (!boxPairCcdDisjoint(a1, t1, n1.extent, unit1, scalar, a2, t2, n2.extent, iv, zero_tol, true)) {
+          if (leaf1 && leaf2) {
+            leaf = true;
+            tri = make_int2(-(n1.first_child + 1), -(n2.first_child + 1));
+          } else if (depth >= 64) {
+            too_deep = true;
+          } else {
+            expand = true;
+            const bool on1 = leaf2 || (!leaf1 && size1 > size2);
+            // pushed left then right: the right child (second) is popped first
+            c_first = on1 ? make_int2(n1.first_child, id.y) : make_int2(id.x, n2.first_child);
+            c_second = on1 ? make_int2(n1.first_child + 1, id.y) : make_int2(id.x, n2.first_child + 1);
+          }
+        }
+      }
+      const unsigned em = __ballot_sync(0xffffffffu, expand);
+      const unsigned lm = __ballot_sync(0xffffffffu, leaf);
+      if (__any_sync(0xffffffffu, too_deep)) {
+        if (lane == 0) atomicAdd(a.cand_count + 2, 1u);
+        overflow = true;
+      }
+      if (sp + 2 * __popc(em) > kCpStackCap) {
+        overflow = true;
+        expand = false;
+      }
+      if (expand && !overflow) {
+        const int pos = sp + 2 * __popc(em & lt_mask);
+        st_id[pos] = c_first;       // left: visited second -> path bit 1
+        st_id[pos + 1] = c_second;  // right: visited first -> path bit 0
+        st_iv[2 * pos] = iv.lo;
+        st_iv[2 * pos + 1] = iv.hi;
+        st_iv[2 * pos + 2] = iv.lo;
+        st_iv[2 * pos + 3] = iv.hi;
+        st_path[pos] = path | (1ull << (63 - depth));
+        st_path[pos + 1] = path;
+        st_depth[pos] = st_depth[pos + 1] = (unsigned char)(depth + 1);
+      }
+      if (!overflow) sp += 2 * __popc(em);
+      if (lm) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.cand_count, uint32_t(__popc(lm)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (leaf) {
+          const uint32_t slot = base + uint32_t(__popc(lm & lt_mask));
+          if (slot < a.cand_cap) {
+            a.cand_q[slot] = uint32_t(q);
+            a.cand_tri[slot] = tri;
+            S* o = static_cast<S*>(a.cand_iv) + 2 * size_t(slot);
+            o[0] = iv.lo;
+            o[1] = iv.hi;
+            a.cand_path[slot] = path;
+          }
+        }
+      }
+      __syncwarp();
+      if (overflow) break;
+    }
+    if (overflow && lane == 0) atomicAdd(a.cand_count + 1, 1u);
+    __syncwarp();
+  }
+}
+
+// RunShapePair<TriangleP, TriangleP> per candidate
+template <typename S>
+__global__ void __launch_bounds__(kBlock) ccdMeshPairLeafKernel(CcdMeshPairArgs a, uint32_t n_cand) {
+  const S* __restrict__ disp = static_cast<const S*>(a.disp);
+  const S tol = S(a.gjk_tol);
+  for (size_t c = blockIdx.x * size_t(blockDim.x) + threadIdx.x; c < n_cand; c += size_t(gridDim.x) * blockDim.x) {
+    const size_t q = a.cand_q[c];
+    const int2 tri = a.cand_tri[c];
+    const Pose<S> tf1 = loadPose(static_cast<const S*>(a.poses1), q);
+    const Pose<S> tf2 = loadPose(static_cast<const S*>(a.poses2), q);
+    SweptMinkDiff<S, ST_TRIANGLE, ST_TRIANGLE> sm;
+    sm.md.s0.type = sm.md.s1.type = ST_TRIANGLE;
+    sm.md.s0.cvx = sm.md.s1.cvx = nullptr;
+    loadTri(static_cast<const S*>(a.tris1), tri.x, sm.md.s0.tri);
+    loadTri(static_cast<const S*>(a.tris2), tri.y, sm.md.s1.tri);
+    sm.md.setPoses(tf1, tf2);
+    sm.disp = mk<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]) * disp[4 * q + 3];
+    const S* ivp = static_cast<const S*>(a.cand_iv) + 2 * c;
+    TocInterval<S> toc;
+    toc.lo = ivp[0];
+    toc.hi = ivp[1];
+    bool hit;
+    if (a.request_type == CCD_ONE_TOC_SAMPLE) {
+      MprIntersectData<S> data;
+      hit = mprIntersectData<S>(sm, a.max_iter, tol, data) == MPR_INTERSECT;
+      if (hit) {
+        const S t = oneTocSample(sm.disp, data);
+        if (t >= 0) toc.lo = toc.hi = t;
+      }
+    } else {
+      hit = mprIntersect<S>(sm, a.max_iter, tol, nullptr) == MPR_INTERSECT;
+    }
+    a.qkey[c] = hit ? uint32_t(q) : 0xffffffffu;
+    S* o = static_cast<S*>(a.cand_toc) + 2 * c;
+    o[0] = toc.lo;
+    o[1] = toc.hi;
+  }
+}
+
+__global__ void ccdGatherKeyKernel(const uint32_t* __restrict__ qkey, const uint32_t* __restrict__ order, uint32_t n, uint32_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = qkey[order[i]];
+}
+
+// after the stable sorts by path, then by query: the first max_contacts hits of every query
+template <typename S>
+__global__ void ccdMeshPairSelectKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order, uint32_t n_cand,
+                                        const int2* __restrict__ cand_tri, const S* __restrict__ cand_toc, uint32_t max_contacts,
+                                        uint32_t keep, uint32_t* __restrict__ counts, long long* __restrict__ prim,
+                                        S* __restrict__ toc) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n_cand) return;
+  const uint32_t q = keys[i];
+  if (q == 0xffffffffu) return;
+  auto lowerBound = [&](unsigned long long v) {
+    size_t lo = 0, hi = n_cand;
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if ((unsigned long long)keys[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  const size_t first = lowerBound(q);
+  const size_t k = i - first;
+  if (k == 0) {
+    const size_t cnt = lowerBound((unsigned long long)q + 1) - first;
+    counts[q] = uint32_t(cnt < max_contacts ? cnt : max_contacts);
+  }
+  if (k < max_contacts && k < keep) {
+    const uint32_t c = order[i];
+    prim[(size_t(q) * keep + k) * 2] = cand_tri[c].x;
+    prim[(size_t(q) * keep + k) * 2 + 1] = cand_tri[c].y;
+    if (toc) {
+      toc[(size_t(q) * keep + k) * 2] = cand_toc[2 * size_t(c)];
+      toc[(size_t(q) * keep + k) * 2 + 1] = cand_toc[2 * size_t(c) + 1];
+    }
+  }
+}
+
 }  // namespace fclb

@@ -213,6 +213,21 @@ class RefOracle(_Oracle):
           request_type, max_contacts, zero_tol, 1 if mesh_moves else 0, keep, _p(counts), _p(prim), _p(toc), threads)
         return counts, prim, toc
 
+    def translational_ccd_mesh_pair_batch(self, mesh1, mesh2, poses1, poses2, disp, request_type=0, max_contacts=1, zero_tol=0.0,
+                                          keep=8, threads=1):
+        """fcl::translational_ccd(mesh, mesh) per query: (counts [n], (b1, b2) i64 [n, keep, 2], toc [n, keep, 2])"""
+        n = len(poses1)
+        dt = poses1.dtype
+        counts = np.zeros(n, np.uint32)
+        prim = np.full((n, keep, 2), -1, np.int64)
+        toc = np.full((n, keep, 2), -1, dt)
+        f = self.fn("translational_ccd_mesh_pair_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_double,
+                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(dt), mesh1, mesh2, _p(poses1), _p(poses2), _p(disp), n, request_type, max_contacts, zero_tol, keep, _p(counts),
+          _p(prim), _p(toc), threads)
+        return counts, prim, toc
+
     # ---- meshes (reference BVHModel<OBBRSS<S>>) ----
     def bvh_create(self, verts, tris):
         verts = np.ascontiguousarray(verts, np.float64)

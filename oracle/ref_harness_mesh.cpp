@@ -419,6 +419,52 @@ extern "C" int fclref_translational_ccd_mesh_batch(int scalar_type, int id, cons
   return 0;
 }
 
+// fcl::translational_ccd(BVHModel<OBB>, tf1, displacement, BVHModel<OBB>, tf2, request, result)
+// (TranslationalDisplacementBVH_PairSolverImpl<S, OBB<S>>, bvh_ccd_solver-inl.h:425-551): contacts (b1, b2, toc) in order
+namespace {
+template <typename S>
+void ccdMeshPairBatch(int id1, int id2, const S* poses1, const S* poses2, const S* disp, size_t n, int request_type,
+                      uint32_t max_contacts, double zero_tol, uint32_t keep, uint32_t* counts, int64_t* prim, S* toc, int threads) {
+  const ObbModel<S>* m1 = ObbOf<S>::get(id1);
+  const ObbModel<S>* m2 = ObbOf<S>::get(id2);
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    fcl::ContinuousCollisionRequest<S> req;
+    req.request_type = static_cast<fcl::TimeOfCollisionRequestType>(request_type);
+    req.num_max_contacts = max_contacts;
+    if (zero_tol > 0) req.zero_movement_tolerance = S(zero_tol);
+    for (size_t q = b; q < e; q++) {
+      const auto tf1 = loadPose<S>(poses1 + 12 * q);
+      const auto tf2 = loadPose<S>(poses2 + 12 * q);
+      fcl::TranslationalDisplacement<S> d;
+      d.unit_axis_in_shape1 = fcl::Vector3<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]);
+      d.scalar_displacement = disp[4 * q + 3];
+      fcl::ContinuousCollisionResult<S> res;
+      fcl::translational_ccd<S>(m1, tf1, d, m2, tf2, req, res);
+      counts[q] = uint32_t(res.num_contacts());
+      for (uint32_t k = 0; k < keep && k < res.num_contacts(); k++) {
+        const auto& c = res.raw_contacts()[k];
+        prim[(size_t(q) * keep + k) * 2] = c.b1;
+        prim[(size_t(q) * keep + k) * 2 + 1] = c.b2;
+        toc[(size_t(q) * keep + k) * 2] = c.toc.lower_bound;
+        toc[(size_t(q) * keep + k) * 2 + 1] = c.toc.upper_bound;
+      }
+    }
+  });
+}
+}  // namespace
+extern "C" int fclref_translational_ccd_mesh_pair_batch(int scalar_type, int id1, int id2, const void* poses1, const void* poses2,
+                                                        const void* disp, size_t n, int request_type, uint32_t max_contacts,
+                                                        double zero_tol, uint32_t keep, uint32_t* counts, int64_t* prim, void* toc,
+                                                        int threads) {
+  if (scalar_type == 0)
+    ccdMeshPairBatch<float>(id1, id2, (const float*)poses1, (const float*)poses2, (const float*)disp, n, request_type, max_contacts,
+                            zero_tol, keep, counts, prim, (float*)toc, threads);
+  else
+    ccdMeshPairBatch<double>(id1, id2, (const double*)poses1, (const double*)poses2, (const double*)disp, n, request_type,
+                             max_contacts, zero_tol, keep, counts, prim, (double*)toc, threads);
+  return 0;
+}
+
 // mesh registry access for the other harness translation units (ref_harness_scene.cpp)
 namespace fclref {
 const fcl::BVHModel<fcl::OBBRSS<float>>* meshF(int id) { return get<float>(id); }

@@ -367,6 +367,24 @@ void runBatch() {
       EXPECT_TRUE(mesh_up.raw_contacts()[0].o1 == &mover && mesh_up.raw_contacts()[0].b2 == c0.b2);
     }
   }
+  // mesh vs mesh: a second floor 1 m above the first, moving 2 m down, meets it (4 triangle pairs at most); moving up it does not
+  {
+    BVHModel<OBBRSS<S>> lid;
+    lid.beginModel();
+    lid.addSubModel({Vector3<S>(-1, -1, 0), Vector3<S>(1, -1, 0), Vector3<S>(1, 1, 0), Vector3<S>(-1, 1, 0)}, {{0, 1, 2}, {0, 2, 3}});
+    lid.endModel();
+    TranslationalDisplacement<S> down, up;
+    down.unit_axis_in_shape1 = Vector3<S>(0, 0, -1);
+    up.unit_axis_in_shape1 = Vector3<S>(0, 0, 1);
+    down.scalar_displacement = up.scalar_displacement = 2;
+    ContinuousCollisionRequest<S> creq;
+    creq.num_max_contacts = 16;
+    ContinuousCollisionResult<S> hit_r, miss_r;
+    translational_ccd<S>(&lid, at(0, 0, 1), down, &floor, I, creq, hit_r);
+    translational_ccd<S>(&lid, at(0, 0, 1), up, &floor, I, creq, miss_r);
+    EXPECT_TRUE(hit_r.num_contacts() >= 2 && hit_r.num_contacts() <= 4 && miss_r.num_contacts() == 0);
+    for (const auto& ct : hit_r.raw_contacts()) EXPECT_TRUE(ct.o1 == &lid && ct.o2 == &floor && ct.b1 >= 0 && ct.b1 < 2 && ct.b2 >= 0 && ct.b2 < 2);
+  }
   // UserContactProcessFunctor on the host: keep only contacts on triangle 1, stop after two
   std::vector<CollisionQuery<S>> one_q{{&floor, I, &ball, at(0, 0, S(0.1))}};
   std::vector<CollisionResult<S>> fr;

@@ -57,3 +57,43 @@ def test_shape_mesh_ccd(fclb, ref_oracle, dtype):
         assert int((ec > 0).sum()) > 500
     fclb.release(table)
     fclb.bvh_release(bvh)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_mesh_pair_ccd(fclb, ref_oracle, dtype):
+    """fclb_translational_ccd_mesh_pair_batch_host against fcl::translational_ccd(BVHModel<OBB>, BVHModel<OBB>)
+    (bvh_ccd_solver-inl.h:425-551): counts, (b1, b2) in the reference's order, toc bit-identical."""
+    st = fclb.F32 if dtype == np.float32 else fclb.F64
+    v1, t1 = scenes.noisy_uv_sphere(n_lat=9, n_lon=14, radius=0.4, noise=0.05)
+    v2, t2 = scenes.noisy_torus(n_major=20, n_minor=10) if hasattr(scenes, "noisy_torus") else scenes.noisy_uv_sphere(n_lat=11, n_lon=16)
+    b1 = fclb.bvh_build(v1, t1, st)
+    b2 = fclb.bvh_build(v2, t2, st)
+    o1 = ref_oracle.bvh_obb_create(v1, t1)
+    o2 = ref_oracle.bvh_obb_create(v2, t2)
+    n, keep = 1500, 64
+    rng = np.random.Generator(np.random.PCG64(21))
+    p1 = scenes.random_poses(rng, n, 1.2, dtype)
+    p2 = scenes.random_poses(rng, n, 0.3, dtype)
+    ax = rng.normal(size=(n, 3))
+    ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    disp = np.concatenate([ax, rng.uniform(0.05, 1.5, size=(n, 1))], axis=1).astype(dtype)
+    for request_type in (0, 1, 2):
+        for max_contacts in (1, 5, 100000):
+            c, prim, toc = fclb.translational_ccd_mesh_pair_batch_host(b1, b2, p1, p2, disp, st, request_type=request_type,
+                                                                       max_contacts=max_contacts, max_keep=keep)
+            ec, eprim, etoc = ref_oracle.translational_ccd_mesh_pair_batch(o1, o2, p1, p2, disp, request_type=request_type,
+                                                                           max_contacts=max_contacts, keep=keep, threads=8)
+            bad = np.nonzero(c != ec)[0]
+            listed = [{"query": int(q), "ours": int(c[q]), "reference": int(ec[q])} for q in bad[:20]]
+            same_ids, same_toc = np.array_equal(prim, eprim), np.array_equal(toc, etoc)
+            parity_util.record("test_mesh_pair_ccd", f"two meshes ({len(t1)} / {len(t2)} triangles), request {request_type}, "
+                               f"max_contacts {max_contacts}", dtype, n, "contact counts, (b1, b2) in the reference's order, toc intervals",
+                               listed, {"queries_with_contacts": int((ec > 0).sum()), "contacts": int(ec.sum()),
+                                        "count_mismatches": int(bad.size), "ids_identical": bool(same_ids),
+                                        "toc_identical": bool(same_toc)})
+            assert bad.size == 0, listed[:5]
+            assert same_ids, np.argwhere(prim != eprim)[:5]
+            assert same_toc, (np.argwhere(toc != etoc)[:5], np.abs(toc - etoc).max())
+        assert int((ec > 0).sum()) > 100
+    fclb.bvh_release(b1)
+    fclb.bvh_release(b2)
