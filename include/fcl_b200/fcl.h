@@ -975,6 +975,12 @@ struct ContinuousCollisionRequest {
   S gjk_tolerance{S(1e-6)};
   int max_gjk_iterations{128};
 };
+// math/bv/AABB.h: the two corners, as far as the contacts need them
+template <typename S>
+struct AABB {
+  Vector3<S> min_{S(0), S(0), S(0)};
+  Vector3<S> max_{S(0), S(0), S(0)};
+};
 template <typename S>
 struct ContinuousCollisionContact {
   const CollisionGeometry<S>* o1{nullptr};
@@ -982,6 +988,8 @@ struct ContinuousCollisionContact {
   static constexpr std::int64_t NONE = -1;
   std::int64_t b1{NONE};
   std::int64_t b2{NONE};
+  AABB<S> o1_bv{};  // heightmap / octree contacts: the pixel's / node's box (ccd_contact.h:24-30)
+  AABB<S> o2_bv{};
   Interval<S> toc{};
 };
 template <typename S>
@@ -1003,10 +1011,10 @@ struct ContinuousCollisionQuery {
   Transform3<S> tf2;
 };
 // one C-ABI call for the shape pairs of the batch, one per mesh for its (shape, mesh) / (mesh, shape) queries and one per
-// pair of meshes
+// pair of meshes, one per heightmap / octree for its shape queries
 // (the reference's CCD matrix serves OBB trees, translational_collision_func_matrix-inl.h:469-489; our BVHModel<OBBRSS>
-// has the same hierarchy, see fclb_translational_ccd_mesh_batch_host); heightmap / octree queries are not on the
-// device path yet (warning, no contact)
+// has the same hierarchy, see fclb_translational_ccd_mesh_batch_host); heightmap / octree vs mesh / heightmap / octree
+// queries are not on the device path yet (warning, no contact)
 template <typename S>
 void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queries, const ContinuousCollisionRequest<S>& request,
                            std::vector<ContinuousCollisionResult<S>>& results) {
@@ -1025,12 +1033,13 @@ void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queri
   std::vector<std::size_t> idx;
   struct MeshGroup {
     bool mesh_moves;
+    int kind = FCLB_SCENE_BVH;
     std::vector<fclb_shape> shapes;
     std::vector<uint32_t> ids;
     std::vector<S> pose_shape, pose_mesh, disp;
     std::vector<std::size_t> idx;
   };
-  std::map<std::pair<fclb_handle, bool>, MeshGroup> meshes;
+  std::map<std::pair<fclb_handle, bool>, MeshGroup> meshes, scenes;
   struct PairGroup {
     std::vector<S> pose1, pose2, disp;
     std::vector<std::size_t> idx;
@@ -1044,6 +1053,8 @@ void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queri
     const auto& Q = queries[q];
     const bool s1 = Q.o1->isShape(), s2 = Q.o2->isShape();
     const bool m1 = Q.o1->getNodeType() == BV_OBBRSS, m2 = Q.o2->getNodeType() == BV_OBBRSS;
+    const bool g1 = Q.o1->getNodeType() == GEOM_HEIGHTMAP || Q.o1->getNodeType() == GEOM_OCTREE2;
+    const bool g2 = Q.o2->getNodeType() == GEOM_HEIGHTMAP || Q.o2->getNodeType() == GEOM_OCTREE2;
     if (s1 && s2) {
       pairs.push_back(fclb_pair{uint32_t(shapes.size()), uint32_t(shapes.size() + 1)});
       shapes.push_back(Q.o1->shapeRecord());
@@ -1059,6 +1070,20 @@ void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queri
       const CollisionGeometry<S>* mesh = s1 ? Q.o2 : Q.o1;
       MeshGroup& g = meshes[std::make_pair(detail::sceneHandle(mesh), mesh_moves)];
       g.mesh_moves = mesh_moves;
+      g.ids.push_back(uint32_t(g.shapes.size()));
+      g.shapes.push_back(shape->shapeRecord());
+      push12(g.pose_shape, s1 ? Q.tf1 : Q.tf2);
+      push12(g.pose_mesh, s1 ? Q.tf2 : Q.tf1);
+      for (int k = 0; k < 3; k++) g.disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
+      g.disp.push_back(Q.o1_displacement.scalar_displacement);
+      g.idx.push_back(q);
+    } else if ((s1 && g2) || (g1 && s2)) {  // shape vs heightmap / octree, either order
+      const bool scene_moves = g1;
+      const CollisionGeometry<S>* shape = s1 ? Q.o1 : Q.o2;
+      const CollisionGeometry<S>* scene = s1 ? Q.o2 : Q.o1;
+      MeshGroup& g = scenes[std::make_pair(detail::sceneHandle(scene), scene_moves)];
+      g.mesh_moves = scene_moves;
+      g.kind = detail::sceneKind(scene);
       g.ids.push_back(uint32_t(g.shapes.size()));
       g.shapes.push_back(shape->shapeRecord());
       push12(g.pose_shape, s1 ? Q.tf1 : Q.tf2);
@@ -1129,6 +1154,48 @@ void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queri
           c.toc.upper_bound = toc[2 * i + 1];
           results[idx[i]].AddContact(c);
         }
+    fclb_release(table);
+  }
+  for (auto& kv : scenes) {  // heightmap / octree: the contact names the pixel / node (b2) and carries its box (o2_bv)
+    MeshGroup& g = kv.second;
+    const std::size_t m = g.ids.size();
+    fclb_handle table = 0;
+    detail::check(fclb_shapes_upload(g.shapes.data(), uint32_t(g.shapes.size()), &table), "fclb_shapes_upload");
+    uint32_t keep = uint32_t(std::min<std::size_t>(request.num_max_contacts, 64));
+    std::vector<uint32_t> counts(m);
+    std::vector<int64_t> code;
+    std::vector<S> toc, box;
+    for (int pass = 0; pass < 2; pass++) {
+      code.assign(m * keep, -1);
+      toc.assign(m * keep * 2, S(-1));
+      box.assign(m * keep * 6, S(0));
+      if (!detail::batchOk(fclb_translational_ccd_scene_batch_host(g.kind, kv.first.first, table, g.ids.data(), g.pose_shape.data(),
+                                                                   g.pose_mesh.data(), g.disp.data(), m, detail::scalarType<S>(), &rq,
+                                                                   g.mesh_moves ? 1 : 0, keep, counts.data(), code.data(), toc.data(),
+                                                                   box.data()),
+                           "fclb_translational_ccd_scene_batch_host")) {
+        counts.assign(m, 0);
+        break;
+      }
+      const uint32_t most = *std::max_element(counts.begin(), counts.end());
+      if (most <= keep) break;
+      keep = most;
+    }
+    for (std::size_t i = 0; i < m; i++)
+      for (uint32_t k = 0; k < counts[i] && k < keep; k++) {
+        const auto& Q = queries[g.idx[i]];
+        ContinuousCollisionContact<S> c;
+        c.o1 = g.mesh_moves ? Q.o2 : Q.o1;  // both entries report o1 = the shape, o2 = the scene geometry
+        c.o2 = g.mesh_moves ? Q.o1 : Q.o2;
+        c.b2 = code[i * keep + k];
+        c.toc.lower_bound = toc[(i * keep + k) * 2];
+        c.toc.upper_bound = toc[(i * keep + k) * 2 + 1];
+        for (int j = 0; j < 3; j++) {
+          c.o2_bv.min_[j] = box[(i * keep + k) * 6 + j];
+          c.o2_bv.max_[j] = box[(i * keep + k) * 6 + 3 + j];
+        }
+        results[g.idx[i]].AddContact(c);
+      }
     fclb_release(table);
   }
   for (auto& kv : meshes) {

@@ -260,6 +260,27 @@ int fclb_translational_ccd_mesh_pair_batch_dev(fclb_handle bvh1, fclb_handle bvh
                                                const fclb_ccd_request* req, uint32_t max_keep, uint32_t* out_counts,
                                                int64_t* out_prim, void* out_toc);
 
+/* shape vs heightmap / octree: fcl::translational_ccd(shape, tf_shape, displacement, scene, tf_scene, request, result) and the
+ * scene-first entry (TranslationalDisplacementHeightMapSolver::RunShapeHeightMap / RunHeightMapShape,
+ * detail/ccd/heightmap_ccd_solver-inl.h:8-166; TranslationalDisplacementOctreeSolver::RunShapeOctree / RunOctreeShape,
+ * detail/ccd/octree2_ccd_solver-inl.h:58-260): the scene's box hierarchy is walked with the fixed-orientation swept-box
+ * test (box_pair_ccd_fixed_orientation-inl.h), every surviving pixel / voxel / fully occupied node runs
+ * RunShapePair<Shape, Box> with the request's type.  scene_kind: FCLB_SCENE_HEIGHTMAP or FCLB_SCENE_OCTREE.
+ *   scene_moves    0: the shape moves; 1: the scene moves (displacement in the scene's frame)
+ *   out_code       ContinuousCollisionContact::b2 per contact: encodePixel / encodeOctree2Node, in the reference's order
+ *   out_toc        2 S per contact (or (-1, -1) when the request type computes none)
+ *   out_box        6 S per contact: ContinuousCollisionContact::o2_bv (min xyz, max xyz, scene frame); may be NULL */
+int fclb_translational_ccd_scene_batch_host(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                            const void* poses_shape, const void* poses_scene, const void* displacements,
+                                            size_t n, int scalar_type, const fclb_ccd_request* req, int scene_moves,
+                                            uint32_t max_keep, uint32_t* out_counts, int64_t* out_code, void* out_toc,
+                                            void* out_box);
+int fclb_translational_ccd_scene_batch_dev(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                           const void* poses_shape, const void* poses_scene, const void* displacements,
+                                           size_t n, int scalar_type, const fclb_ccd_request* req, int scene_moves,
+                                           uint32_t max_keep, uint32_t* out_counts, int64_t* out_code, void* out_toc,
+                                           void* out_box);
+
 /* ---- meshes: BVHModel<OBBRSS<S>> flattened by the caller ------------------------
  * (reference geometry/bvh/BVH_model.h:63-196, BV_node_base.h:50-82).  Only the
  * OBB half of OBBRSS is ever read by collide (math/bv/OBBRSS-inl.h:130-135).

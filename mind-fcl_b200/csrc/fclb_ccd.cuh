@@ -263,6 +263,47 @@ struct CcdArgs {
   void* toc;            // 2 S per query (lower, upper) or nullptr
 };
 
+// ShapePairTranslationalCollisionImpl<S, Shape1, Shape2>::RunIntersect (shape_pair_ccd-inl.h:55-137) for one pair: the
+// Box-Box specialisation, or the generic swept-volume MPR with the request type's extras.  l1 / l2: aabb_local of the
+// two shapes (read by kBoxApproximate only).  Returns the hit flag; toc as RunIntersect leaves it.
+template <typename S>
+FCLB_DI bool ccdShapePairEval(const ShapeInst<S>& s1, const LocalAabbD<S>& l1, const Pose<S>& tf1, const ShapeInst<S>& s2,
+                              const LocalAabbD<S>& l2, const Pose<S>& tf2, const V3<S>& unit_axis, S scalar_disp, int request_type,
+                              S zero_tol, S tol, int max_iter, TocInterval<S>& toc) {
+  toc.lo = toc.hi = S(-1.0);
+  if (s1.type == ST_BOX && s2.type == ST_BOX) {  // computeBV<OBB, Box> + the swept box test, whatever the request type
+    const V3<S> e1 = mk<S>(s1.p0, s1.p1, s1.p2) * S(0.5), e2 = mk<S>(s2.p0, s2.p1, s2.p2) * S(0.5);
+    return !boxPairCcdDisjoint(tf1.R, tf1.t, e1, unit_axis, scalar_disp, tf2.R, tf2.t, e2, toc, zero_tol);
+  }
+  SweptMinkDiff<S, ST_DYNAMIC, ST_DYNAMIC> sm;
+  sm.md.s0 = s1;
+  sm.md.s1 = s2;
+  sm.md.setPoses(tf1, tf2);
+  sm.disp = unit_axis * scalar_disp;
+  if (request_type == CCD_BOX_APPROXIMATE) {  // convertBV(aabb_local, tf) boxes first (:98-110)
+    auto obbOf = [](const LocalAabbD<S>& l, const Pose<S>& tf, V3<S>& To, V3<S>& ext) {
+      const V3<S> c = mk<S>(l.center[0], l.center[1], l.center[2]);
+      To = mk<S>(((tf.R.m[0] * c.x + tf.R.m[1] * c.y) + tf.R.m[2] * c.z) + tf.t.x,
+                 ((tf.R.m[3] * c.x + tf.R.m[4] * c.y) + tf.R.m[5] * c.z) + tf.t.y,
+                 ((tf.R.m[6] * c.x + tf.R.m[7] * c.y) + tf.R.m[8] * c.z) + tf.t.z);
+      ext = mk<S>((l.mx[0] - l.mn[0]) * S(0.5), (l.mx[1] - l.mn[1]) * S(0.5), (l.mx[2] - l.mn[2]) * S(0.5));
+    };
+    V3<S> To1, e1, To2, e2;
+    obbOf(l1, tf1, To1, e1);
+    obbOf(l2, tf2, To2, e2);
+    if (boxPairCcdDisjoint(tf1.R, To1, e1, unit_axis, scalar_disp, tf2.R, To2, e2, toc, zero_tol)) return false;
+  }
+  if (request_type == CCD_ONE_TOC_SAMPLE) {
+    MprIntersectData<S> data;
+    const bool hit = mprIntersectData<S>(sm, max_iter, tol, data) == MPR_INTERSECT;
+    if (hit) toc.lo = toc.hi = oneTocSample(sm.disp, data);
+    return hit;
+  }
+  const bool hit = mprIntersect<S>(sm, max_iter, tol, nullptr) == MPR_INTERSECT;
+  if (request_type == CCD_NOT_REQUESTED) toc.lo = toc.hi = S(-1.0);
+  return hit;
+}
+
 // ShapePairTranslationalCollisionSolver::RunShapePair for one query (shape_pair_ccd-inl.h:139-170)
 template <typename S>
 __global__ void __launch_bounds__(kBlock) translationalCcdKernel(CcdArgs a) {
@@ -277,46 +318,9 @@ __global__ void __launch_bounds__(kBlock) translationalCcdKernel(CcdArgs a) {
     const Pose<S> tf2 = loadPose(static_cast<const S*>(a.poses2), q);
     const V3<S> unit_axis = mk<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]);
     const S scalar_disp = disp[4 * q + 3];
-    const ShapeD<S> r1 = shapes[pr.shape1], r2 = shapes[pr.shape2];
     TocInterval<S> toc;
-    toc.lo = toc.hi = S(-1.0);
-    bool hit = false;
-    if (r1.type == ST_BOX && r2.type == ST_BOX) {  // computeBV<OBB, Box> + the swept box test, whatever the request type
-      const V3<S> e1 = mk<S>(r1.p[0], r1.p[1], r1.p[2]) * S(0.5), e2 = mk<S>(r2.p[0], r2.p[1], r2.p[2]) * S(0.5);
-      hit = !boxPairCcdDisjoint(tf1.R, tf1.t, e1, unit_axis, scalar_disp, tf2.R, tf2.t, e2, toc, zero_tol);
-    } else {
-      SweptMinkDiff<S, ST_DYNAMIC, ST_DYNAMIC> sm;
-      sm.md.s0 = bindShape(shapes, cvx, pr.shape1);
-      sm.md.s1 = bindShape(shapes, cvx, pr.shape2);
-      sm.md.setPoses(tf1, tf2);
-      sm.disp = unit_axis * scalar_disp;
-      bool run_mpr = true;
-      if (a.request_type == CCD_BOX_APPROXIMATE) {  // convertBV(aabb_local, tf) boxes first (:98-110)
-        const LocalAabbD<S> l1 = local[pr.shape1], l2 = local[pr.shape2];
-        auto obbOf = [](const LocalAabbD<S>& l, const Pose<S>& tf, V3<S>& To, V3<S>& ext) {
-          const V3<S> c = mk<S>(l.center[0], l.center[1], l.center[2]);
-          To = mk<S>(((tf.R.m[0] * c.x + tf.R.m[1] * c.y) + tf.R.m[2] * c.z) + tf.t.x,
-                     ((tf.R.m[3] * c.x + tf.R.m[4] * c.y) + tf.R.m[5] * c.z) + tf.t.y,
-                     ((tf.R.m[6] * c.x + tf.R.m[7] * c.y) + tf.R.m[8] * c.z) + tf.t.z);
-          ext = mk<S>((l.mx[0] - l.mn[0]) * S(0.5), (l.mx[1] - l.mn[1]) * S(0.5), (l.mx[2] - l.mn[2]) * S(0.5));
-        };
-        V3<S> To1, e1, To2, e2;
-        obbOf(l1, tf1, To1, e1);
-        obbOf(l2, tf2, To2, e2);
-        if (boxPairCcdDisjoint(tf1.R, To1, e1, unit_axis, scalar_disp, tf2.R, To2, e2, toc, zero_tol)) run_mpr = false;
-      }
-      if (run_mpr) {
-        if (a.request_type == CCD_ONE_TOC_SAMPLE) {
-          MprIntersectData<S> data;
-          const int st = mprIntersectData<S>(sm, a.max_iter, tol, data);
-          hit = st == MPR_INTERSECT;
-          if (hit) toc.lo = toc.hi = oneTocSample(sm.disp, data);
-        } else {
-          hit = mprIntersect<S>(sm, a.max_iter, tol, nullptr) == MPR_INTERSECT;
-          if (a.request_type == CCD_NOT_REQUESTED) toc.lo = toc.hi = S(-1.0);
-        }
-      }
-    }
+    const bool hit = ccdShapePairEval<S>(bindShape(shapes, cvx, pr.shape1), local[pr.shape1], tf1, bindShape(shapes, cvx, pr.shape2),
+                                         local[pr.shape2], tf2, unit_axis, scalar_disp, a.request_type, zero_tol, tol, a.max_iter, toc);
     a.hit[q] = hit ? 1 : 0;
     if (a.toc) {
       S* o = static_cast<S*>(a.toc) + 2 * q;
@@ -326,6 +330,81 @@ __global__ void __launch_bounds__(kBlock) translationalCcdKernel(CcdArgs a) {
       o[1] = valid ? toc.hi : S(-1.0);
     }
   }
+}
+
+// FixedOrientationBoxPairTranslationalCCD (box_pair_ccd_fixed_orientation-inl.h): box 1 = an AABB in frame 1 that moves
+// along `unit` (frame 1), box 2 = an AABB in frame 2; R / t = frame 2 in frame 1.  Same 15 axes as above, but every face
+// axis goes through the scalar interval routine with its own early exit (the OBB form evaluates three at once).
+template <typename S>
+struct FixedCcd {
+  M3<S> R;
+  V3<S> t, unit;
+  S scalar;
+};
+template <typename S>
+FCLB_DI bool scaleAndIntersect(TocInterval<S>& interval, TocInterval<S> t, S abs_disp, S zero_tol) {
+  if (abs_disp < zero_tol) {  // ScaleIntervalBoxDisjoint (box_pair_ccd-inl.h:92-104)
+    t.lo = S(0);
+    t.hi = S(1);
+  } else {
+    t.lo /= abs_disp;
+    t.hi /= abs_disp;
+  }
+  interval.intersect(t);
+  return interval.empty(S(0.0));
+}
+// aabb1 / aabb2 given as min / max; `interval` holds the parent's interval on entry (:57-86)
+template <typename S>
+FCLB_DI bool fixedCcdDisjoint(const FixedCcd<S>& f, const V3<S>& mn1, const V3<S>& mx1, const V3<S>& mn2, const V3<S>& mx2,
+                              TocInterval<S>& interval, S zero_tol) {
+  const V3<S> c1 = (mn1 + mx1) * S(0.5), h1 = S(0.5) * (mx1 - mn1);
+  const V3<S> c2 = (mn2 + mx2) * S(0.5), h2 = S(0.5) * (mx2 - mn2);
+  const V3<S> trans = (mulMV(f.R, c2) + f.t) - c1;
+  M3<S> Rabs;
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rabs.m[i] = fabs_(f.R.m[i]);
+  {  // box-1 axes
+    const V3<S> r2 = mulMV(Rabs, h2);
+    const S h1a[3] = {h1.x, h1.y, h1.z}, r2a[3] = {r2.x, r2.y, r2.z}, oa[3] = {trans.x, trans.y, trans.z},
+            ua[3] = {f.unit.x, f.unit.y, f.unit.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const bool pos = ua[i] > 0;
+      const S abs_disp = pos ? ua[i] * f.scalar : -ua[i] * f.scalar;
+      TocInterval<S> t;
+      if (tocOnAxis(h1a[i], abs_disp, pos, r2a[i], oa[i], t)) return true;
+      if (scaleAndIntersect(interval, t, abs_disp, zero_tol)) return true;
+    }
+  }
+  {  // box-2 axes
+    const V3<S> r1 = mulMtV(Rabs, h1), u2 = mulMtV(f.R, f.unit), off = mulMtV(f.R, trans);
+    const S r1a[3] = {r1.x, r1.y, r1.z}, h2a[3] = {h2.x, h2.y, h2.z}, oa[3] = {off.x, off.y, off.z}, ua[3] = {u2.x, u2.y, u2.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const bool pos = ua[i] > 0;
+      const S abs_disp = pos ? ua[i] * f.scalar : -ua[i] * f.scalar;
+      TocInterval<S> t;
+      if (tocOnAxis(r1a[i], abs_disp, pos, h2a[i], oa[i], t)) return true;
+      if (scaleAndIntersect(interval, t, abs_disp, zero_tol)) return true;
+    }
+  }
+  for (int k = 0; k < 3; k++) {
+    const V3<S> ek = mk<S>(k == 0 ? S(1) : S(0), k == 1 ? S(1) : S(0), k == 2 ? S(1) : S(0));
+    for (int i = 0; i < 3; i++) {
+      const V3<S> a1 = cross(ek, col(f.R, i));
+      const V3<S> a1abs = mk<S>(fabs_(a1.x), fabs_(a1.y), fabs_(a1.z));
+      const V3<S> a2 = mulMtV(f.R, a1);
+      const V3<S> a2abs = mk<S>(fabs_(a2.x), fabs_(a2.y), fabs_(a2.z));
+      const S r1 = dot(a1abs, h1), off = dot(a1, trans), r2 = dot(a2abs, h2);
+      const S proj = dot(a1, f.unit);
+      const bool pos = proj > 0;
+      const S abs_disp = pos ? proj * f.scalar : -proj * f.scalar;
+      TocInterval<S> t;
+      if (tocOnAxis(r1, abs_disp, pos, r2, off, t)) return true;
+      if (scaleAndIntersect(interval, t, abs_disp, zero_tol)) return true;
+    }
+  }
+  return false;
 }
 
 }  // namespace fclb

@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(kBlock) ccdMeshPairLeafKernel(CcdMeshPairArgs 
   }
 }
 
-__global__ void ccdGatherKeyKernel(const uint32_t* __restrict__ qkey, const uint32_t* __restrict__ order, uint32_t n, uint32_t* out) {
+static __global__ void ccdGatherKeyKernel(const uint32_t* __restrict__ qkey, const uint32_t* __restrict__ order, uint32_t n, uint32_t* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = qkey[order[i]];
 }

@@ -1,0 +1,559 @@
+// fclb_ccd_scene.cu -- translational continuous collision, shape vs heightmap / octree: kernels + C ABI.
+//
+// Reference: fcl::translational_ccd(shape, tf1, displacement, HeightMapCollisionGeometry | Octree2CollisionGeometry, tf2, ...)
+//   TranslationalDisplacementHeightMapSolver::runShapeHeightMap (detail/ccd/heightmap_ccd_solver-inl.h:8-112)
+//   TranslationalDisplacementOctreeSolver::runShapeOctree       (detail/ccd/octree2_ccd_solver-inl.h:58-198)
+// Both: the shape's OBB (computeBV<OBB, Shape>) becomes an AABB in its own box frame, the scene's node boxes are AABBs in
+// the scene frame, and FixedOrientationBoxPairTranslationalCCD (fixed relative rotation) culls a node or narrows the
+// time-of-collision interval its children inherit; a terminal box (bottom-layer pixel; fully occupied octree node; voxel
+// of a partial leaf -- those without a box test of their own) runs RunShapePair<Shape, Box> with the request's type.
+// The scene-first entries (RunHeightMapShape :138-166, RunOctreeShape) move the negated displacement into the shape's
+// frame and run the same walk.
+//
+// Here, as for meshes (fclb_ccd_mesh.cuh): (A) one warp per query walks the hierarchy and appends every terminal box
+// that survives, with its PATH -- the digits of the reference's visiting order, most significant first: heightmap roots
+// are pushed row by row and popped in reverse, the four / eight children are pushed in index order and popped in
+// reverse, the voxels of a partial octree leaf are visited in index order; (B) one thread per candidate runs the shape
+// pair; (C) two stable radix sorts (path, query) put the hits in the reference's order and the first max_contacts of
+// every query are written.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "fclb_ccd_mesh.cuh"
+#include "fclb_engine.h"
+#include "fclb_scene_pair_impl.cuh"
+
+namespace fclb {
+
+struct CcdSceneArgs {
+  HmView hm;
+  OctView oct;
+  const void* shapes;
+  const void* convex;
+  const void* local;    // LocalAabbD<S>[]
+  const uint32_t* shape_ids;
+  const void* poses_shape;
+  const void* poses_scene;
+  const void* disp;
+  size_t n;
+  int scene_moves;
+  int request_type;
+  double zero_tol, gjk_tol;
+  int max_iter;
+  uint32_t* cand_count;  // [0] appended, [1] stack overflows
+  uint32_t cand_cap;
+  uint32_t* cand_q;
+  long long* cand_code;
+  void* cand_box;       // 6 S per candidate
+  unsigned long long* cand_path;
+  unsigned long long* work_counter;
+  uint32_t* qkey;
+  void* cand_toc;
+};
+
+constexpr int kCsWarps = 4;
+constexpr int kCsStackCap = 320;
+
+template <typename S>
+struct CsElem {
+  BoxElem<S> box;
+  S lo, hi;
+  unsigned long long path;
+  int shift;  // free bits left below the path's digits
+};
+
+template <typename S>
+FCLB_DI V3<S> ccdDisplacementInShapeFrame(const S* disp, size_t q, const Pose<S>& tf_shape, const Pose<S>& tf_scene, int scene_moves) {
+  V3<S> unit = mk<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]);
+  if (scene_moves) unit = mulMtV(tf_shape.R, mulMV(tf_scene.R, -unit));
+  return unit;
+}
+
+template <typename S, int KIND>
+__global__ void __launch_bounds__(kCsWarps * 32) ccdSceneTraverseKernel(CcdSceneArgs a) {
+  extern __shared__ __align__(16) unsigned char s_cs[];
+  using Side = typename SideOf<S, KIND>::type;
+  const Side side = SideOf<S, KIND>::make(a.hm, a.oct);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  CsElem<S>* stack = reinterpret_cast<CsElem<S>*>(s_cs) + size_t(warp) * kCsStackCap;
+  S* fit_pts = reinterpret_cast<S*>(s_cs + size_t(kCsWarps) * kCsStackCap * sizeof(CsElem<S>)) + size_t(warp) * 3 * kFitMaxPoints;
+  const S* __restrict__ disp = static_cast<const S*>(a.disp);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const S zero_tol = S(a.zero_tol);
+  constexpr int kChildBits = KIND == FCLB_SCENE_HEIGHTMAP ? 2 : 3;
+  constexpr int kMaxChildren = KIND == FCLB_SCENE_HEIGHTMAP ? 4 : 8;
+  while (true) {
+    unsigned long long q64 = 0;
+    if (lane == 0) q64 = atomicAdd(a.work_counter, 1ull);
+    q64 = __shfl_sync(0xffffffffu, q64, 0);
+    if (q64 >= a.n) break;
+    const size_t q = size_t(q64);
+    const uint32_t sid = a.shape_ids[q];
+    const ShapeInst<S> sh = bindShape(static_cast<const ShapeD<S>*>(a.shapes), static_cast<const ConvexD<S>*>(a.convex), sid);
+    const Pose<S> tf_s = loadPose(static_cast<const S*>(a.poses_shape), q);
+    const Pose<S> tf_g = loadPose(static_cast<const S*>(a.poses_scene), q);
+    const V3<S> unit = ccdDisplacementInShapeFrame(disp, q, tf_s, tf_g, a.scene_moves);
+    // initializeShapeFixedOrientationBoxTranslationalCCD (ccd_solver_utility-inl.h:8-35)
+    Pose<S> tf_box;
+    V3<S> b_ext;
+    shapeObbForCcd(sh, tf_s, fit_pts, lane, tf_box.R, tf_box.t, b_ext);
+    FixedCcd<S> f;
+    {
+      const Pose<S> rel = compose(inverse(tf_box), tf_g);
+      f.R = rel.R;
+      f.t = rel.t;
+      f.unit = mulMtV(tf_box.R, mulMV(tf_s.R, unit));
+      f.scalar = disp[4 * q + 3];
+    }
+    const V3<S> mn1 = -b_ext, mx1 = b_ext;
+
+    // roots: pushed in index order, popped in reverse
+    const int n_roots = side.numRoots();
+    int root_bits = 0;
+    while ((1 << root_bits) < n_roots) root_bits++;
+    int sp = 0;
+    bool overflow = n_roots > kCsStackCap - 8 * 32;
+    if (!overflow) {
+      for (int base = 0; base < n_roots; base += 32) {
+        const int i = base + lane;
+        CsElem<S> e;
+        bool ok = false;
+        if (i < n_roots) {
+          ok = side.root(i, e.box);
+          e.lo = S(0.0);
+          e.hi = S(1.0);
+          e.shift = 64 - root_bits;
+          e.path = root_bits ? ((unsigned long long)(n_roots - 1 - i) << e.shift) : 0ull;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) stack[sp + __popc(m & lt_mask)] = e;
+        sp += __popc(m);
+      }
+    }
+    __syncwarp();
+    while (sp > 0 && !overflow) {
+      int take = sp < 32 ? sp : 32;
+      if (sp + take * kMaxChildren > kCsStackCap) take = (kCsStackCap - sp) / kMaxChildren > 0 ? 1 : 0;
+      if (take == 0) {
+        overflow = true;
+        break;
+      }
+      CsElem<S> e;
+      if (lane < take) e = stack[sp - 1 - lane];
+      sp -= take;
+      __syncwarp();
+      int n_push = 0, n_cand = 0;
+      unsigned child_mask = 0;
+      TocInterval<S> iv;
+      iv.lo = iv.hi = S(0);
+      bool voxels = false;
+      if (lane < take) {
+        iv.lo = e.lo;
+        iv.hi = e.hi;
+        const V3<S> mn2 = mk<S>(e.box.mn[0], e.box.mn[1], e.box.mn[2]), mx2 = mk<S>(e.box.mx[0], e.box.mx[1], e.box.mx[2]);
+        if (!fixedCcdDisjoint(f, mn1, mx1, mn2, mx2, iv, zero_tol)) {
+          if (e.box.meta & 1u) {
+            n_cand = 1;  // terminal: the box itself
+          } else {
+            child_mask = side.childMask(e.box);
+            voxels = KIND == FCLB_SCENE_OCTREE && (e.box.meta & 2u);  // partial leaf: its voxels, without a box test of their own
+            if (voxels)
+              n_cand = __popc(child_mask);
+            else if (e.shift < kChildBits)
+              overflow = true;
+            else
+              n_push = __popc(child_mask);
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, overflow)) {
+        overflow = true;
+        break;
+      }
+      // warp scans of the push / candidate counts
+      int push_off = n_push, cand_off = n_cand;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int p = __shfl_up_sync(0xffffffffu, push_off, o), c = __shfl_up_sync(0xffffffffu, cand_off, o);
+        if (lane >= o) {
+          push_off += p;
+          cand_off += c;
+        }
+      }
+      const int total_push = __shfl_sync(0xffffffffu, push_off, 31), total_cand = __shfl_sync(0xffffffffu, cand_off, 31);
+      push_off -= n_push;
+      cand_off -= n_cand;
+      if (n_push) {
+        int k = 0;
+        const int shift = e.shift - kChildBits;
+        for (int c = 0; c < kMaxChildren; c++) {
+          if (!(child_mask & (1u << c))) continue;
+          CsElem<S> ch;
+          ch.box = side.child(e.box, c);
+          ch.lo = iv.lo;
+          ch.hi = iv.hi;
+          ch.shift = shift;
+          ch.path = e.path | ((unsigned long long)(kMaxChildren - 1 - c) << shift);  // the last child pushed is visited first
+          stack[sp + push_off + k] = ch;
+          k++;
+        }
+      }
+      sp += total_push;
+      if (total_cand) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.cand_count, uint32_t(total_cand));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (n_cand) {
+          uint32_t slot = base + uint32_t(cand_off);
+          auto emit = [&](const BoxElem<S>& bx, unsigned long long path) {
+            if (slot < a.cand_cap) {
+              a.cand_q[slot] = uint32_t(q);
+              a.cand_code[slot] = Side::code(bx);
+              S* o = static_cast<S*>(a.cand_box) + 6 * size_t(slot);
+#pragma unroll
+              for (int j = 0; j < 3; j++) {
+                o[j] = bx.mn[j];
+                o[3 + j] = bx.mx[j];
+              }
+              a.cand_path[slot] = path;
+            }
+            slot++;
+          };
+          if (!voxels) {
+            emit(e.box, e.path);
+          } else {  // voxels of a partial leaf, in index order; they inherit the LEAF's place in the walk
+            const int shift = e.shift >= 3 ? e.shift - 3 : 0;
+            for (int c = 0; c < 8; c++)
+              if (child_mask & (1u << c)) emit(side.child(e.box, c), e.path | ((unsigned long long)c << shift));
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (overflow && lane == 0) atomicAdd(a.cand_count + 1, 1u);
+    __syncwarp();
+  }
+}
+
+// RunShapePair<Shape, Box> per candidate (heightmap_ccd_solver-inl.h:88-112, octree2_ccd_solver-inl.h shapeToBoxProcessLeafPair):
+// constructBox(aabb, tf_scene) makes the box; the contact carries no external interval, so the request's type stands
+template <typename S>
+__global__ void __launch_bounds__(kBlock) ccdSceneLeafKernel(CcdSceneArgs a, uint32_t n_cand) {
+  const S* __restrict__ disp = static_cast<const S*>(a.disp);
+  const LocalAabbD<S>* __restrict__ local = static_cast<const LocalAabbD<S>*>(a.local);
+  const S zero_tol = S(a.zero_tol), tol = S(a.gjk_tol);
+  for (size_t c = blockIdx.x * size_t(blockDim.x) + threadIdx.x; c < n_cand; c += size_t(gridDim.x) * blockDim.x) {
+    const size_t q = a.cand_q[c];
+    const uint32_t sid = a.shape_ids[q];
+    const Pose<S> tf_s = loadPose(static_cast<const S*>(a.poses_shape), q);
+    const Pose<S> tf_g = loadPose(static_cast<const S*>(a.poses_scene), q);
+    const V3<S> unit = ccdDisplacementInShapeFrame(disp, q, tf_s, tf_g, a.scene_moves);
+    const S* bx = static_cast<const S*>(a.cand_box) + 6 * c;
+    const V3<S> mn = mk<S>(bx[0], bx[1], bx[2]), mx = mk<S>(bx[3], bx[4], bx[5]);
+    // constructBox (geometry/shape/utility-inl.h:896-900): side = max - min, tf = tf_scene * Translation(center)
+    ShapeInst<S> box;
+    box.type = ST_BOX;
+    box.cvx = nullptr;
+    box.p0 = mx.x - mn.x;
+    box.p1 = mx.y - mn.y;
+    box.p2 = mx.z - mn.z;
+    const V3<S> center = (mn + mx) * S(0.5);
+    Pose<S> tf_b;
+    tf_b.R = tf_g.R;
+    tf_b.t = mulMV(tf_g.R, center) + tf_g.t;
+    LocalAabbD<S> lb;  // Box::computeLocalAABB(): +- side / 2 around the origin
+    lb.mx[0] = S(0.5) * box.p0; lb.mx[1] = S(0.5) * box.p1; lb.mx[2] = S(0.5) * box.p2;
+    lb.mn[0] = -lb.mx[0]; lb.mn[1] = -lb.mx[1]; lb.mn[2] = -lb.mx[2];
+    lb.center[0] = lb.center[1] = lb.center[2] = S(0);
+    lb.radius = S(0);
+    TocInterval<S> toc;
+    const bool hit = ccdShapePairEval<S>(bindShape(static_cast<const ShapeD<S>*>(a.shapes), static_cast<const ConvexD<S>*>(a.convex), sid),
+                                         local[sid], tf_s, box, lb, tf_b, unit, disp[4 * q + 3], a.request_type, zero_tol, tol,
+                                         a.max_iter, toc);
+    a.qkey[c] = hit ? uint32_t(q) : 0xffffffffu;
+    S* o = static_cast<S*>(a.cand_toc) + 2 * c;
+    const bool valid = toc.lo >= 0 && toc.hi >= 0;  // writeToContact(contact, toc): otherwise the (invalid) external interval
+    o[0] = valid ? toc.lo : S(-1.0);
+    o[1] = valid ? toc.hi : S(-1.0);
+  }
+}
+
+template <typename S>
+__global__ void ccdSceneSelectKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order, uint32_t n_cand,
+                                     const long long* __restrict__ cand_code, const S* __restrict__ cand_toc,
+                                     const S* __restrict__ cand_box, uint32_t max_contacts, uint32_t keep,
+                                     uint32_t* __restrict__ counts, long long* __restrict__ code, S* __restrict__ toc,
+                                     S* __restrict__ box) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n_cand) return;
+  const uint32_t q = keys[i];
+  if (q == 0xffffffffu) return;
+  auto lowerBound = [&](unsigned long long v) {
+    size_t lo = 0, hi = n_cand;
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if ((unsigned long long)keys[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  const size_t first = lowerBound(q);
+  const size_t k = i - first;
+  if (k == 0) {
+    const size_t cnt = lowerBound((unsigned long long)q + 1) - first;
+    counts[q] = uint32_t(cnt < max_contacts ? cnt : max_contacts);
+  }
+  if (k < max_contacts && k < keep) {
+    const uint32_t c = order[i];
+    const size_t o = size_t(q) * keep + k;
+    code[o] = cand_code[c];
+    if (toc) {
+      toc[2 * o] = cand_toc[2 * size_t(c)];
+      toc[2 * o + 1] = cand_toc[2 * size_t(c) + 1];
+    }
+    if (box)
+      for (int j = 0; j < 6; j++) box[6 * o + j] = cand_box[6 * size_t(c) + j];
+  }
+}
+
+__global__ void ccdSceneIotaKernel(uint32_t* p, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+__global__ void ccdSceneGatherKernel(const uint32_t* __restrict__ qkey, const uint32_t* __restrict__ order, uint32_t n, uint32_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = qkey[order[i]];
+}
+template <typename T>
+__global__ void ccdSceneFillKernel(T* p, size_t n, T v) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+struct CcdSceneScratch {
+  std::vector<void*> ptrs;
+  ~CcdSceneScratch() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <typename T>
+  cudaError_t get(T** p, size_t count) {
+    void* v = nullptr;
+    const cudaError_t e = cudaMalloc(&v, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(v);
+    *p = static_cast<T*>(v);
+    return e;
+  }
+};
+
+template <typename S>
+static int ccdSceneDev(Engine& e, int kind, fclb_handle scene, ShapeTable* t, const uint32_t* shape_ids, const void* poses_shape,
+                       const void* poses_scene, const void* disp, size_t n, const fclb_ccd_request* req, int scene_moves,
+                       uint32_t keep, uint32_t* counts, long long* code, void* toc, void* box) {
+  const int st = sizeof(S) == 4 ? 0 : 1;
+  CcdSceneArgs a{};
+  int rc = kind == FCLB_SCENE_HEIGHTMAP ? sceneHmView(scene, st, a.hm) : sceneOctView(scene, a.oct);
+  if (rc) return rc;
+  CcdSceneScratch sc;
+  uint32_t* d_count = nullptr;
+  unsigned long long* d_work = nullptr;
+  FCLB_CUDA(sc.get(&d_count, 2));
+  FCLB_CUDA(sc.get(&d_work, 1));
+  a.shapes = t->d_shapes[st];
+  a.convex = e.d_convex_tab[st];
+  a.local = t->d_local[st];
+  a.shape_ids = shape_ids;
+  a.poses_shape = poses_shape;
+  a.poses_scene = poses_scene;
+  a.disp = disp;
+  a.n = n;
+  a.scene_moves = scene_moves;
+  a.request_type = int(req->request_type);
+  a.zero_tol = req->zero_movement_tolerance > 0 ? req->zero_movement_tolerance : 1e-4;
+  a.gjk_tol = req->gjk_tolerance > 0 ? req->gjk_tolerance : 1e-6;
+  a.max_iter = req->max_gjk_iterations > 0 ? req->max_gjk_iterations : 128;
+  a.cand_count = d_count;
+  a.work_counter = d_work;
+  const size_t smem = size_t(kCsWarps) * (kCsStackCap * sizeof(CsElem<S>) + 3 * kFitMaxPoints * sizeof(S));
+  auto kern = kind == FCLB_SCENE_HEIGHTMAP ? ccdSceneTraverseKernel<S, FCLB_SCENE_HEIGHTMAP> : ccdSceneTraverseKernel<S, FCLB_SCENE_OCTREE>;
+  FCLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int grid = int(std::min<size_t>((n + kCsWarps - 1) / kCsWarps, size_t(e.sms) * 2));
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  size_t cap = std::min<size_t>(std::max<size_t>(n * 32, size_t(1) << 16), size_t(1) << 26);
+  uint32_t h_count[2] = {0, 0};
+  for (int attempt = 0; attempt < 3; attempt++) {
+    FCLB_CUDA(sc.get(&a.cand_q, cap));
+    FCLB_CUDA(sc.get(&a.cand_code, cap));
+    FCLB_CUDA(sc.get(&a.cand_path, cap));
+    S* bx = nullptr;
+    FCLB_CUDA(sc.get(&bx, 6 * cap));
+    a.cand_box = bx;
+    a.cand_cap = uint32_t(cap);
+    FCLB_CUDA(cudaMemsetAsync(d_count, 0, 2 * sizeof(uint32_t), e.compute));
+    FCLB_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), e.compute));
+    kern<<<grid, kCsWarps * 32, smem, e.compute>>>(a);
+    FCLB_CUDA(cudaGetLastError());
+    e.launches += 1;
+    FCLB_CUDA(cudaMemcpyAsync(h_count, d_count, sizeof(h_count), cudaMemcpyDeviceToHost, e.compute));
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+    if (h_count[1]) return fail(FCLB_ERR_CAPACITY, "scene CCD: hierarchy wider or deeper than the per-warp stack allows");
+    if (h_count[0] <= cap) break;
+    if (attempt == 2 || h_count[0] > (1u << 30)) return fail(FCLB_ERR_CAPACITY, "scene CCD: too many candidate boxes: split the batch");
+    cap = h_count[0];
+  }
+  const uint32_t n_cand = h_count[0];
+  FCLB_CUDA(cudaMemsetAsync(counts, 0, n * sizeof(uint32_t), e.compute));
+  if (n * keep) {
+    const int g = int((n * keep * 6 + 255) / 256);
+    ccdSceneFillKernel<long long><<<g, 256, 0, e.compute>>>(code, n * keep, -1ll);
+    if (toc) ccdSceneFillKernel<S><<<g, 256, 0, e.compute>>>(static_cast<S*>(toc), n * keep * 2, S(-1));
+    if (box) ccdSceneFillKernel<S><<<g, 256, 0, e.compute>>>(static_cast<S*>(box), n * keep * 6, S(0));
+  }
+  if (n_cand) {
+    unsigned long long* path_sorted = nullptr;
+    uint32_t *order = nullptr, *order1 = nullptr, *order2 = nullptr, *qkey = nullptr, *qkey1 = nullptr, *qkey2 = nullptr;
+    S* cand_toc = nullptr;
+    FCLB_CUDA(sc.get(&path_sorted, n_cand));
+    FCLB_CUDA(sc.get(&order, n_cand));
+    FCLB_CUDA(sc.get(&order1, n_cand));
+    FCLB_CUDA(sc.get(&order2, n_cand));
+    FCLB_CUDA(sc.get(&qkey, n_cand));
+    FCLB_CUDA(sc.get(&qkey1, n_cand));
+    FCLB_CUDA(sc.get(&qkey2, n_cand));
+    FCLB_CUDA(sc.get(&cand_toc, 2 * size_t(n_cand)));
+    a.qkey = qkey;
+    a.cand_toc = cand_toc;
+    const int lgrid = int(std::min<size_t>((n_cand + kBlock - 1) / kBlock, size_t(e.sms) * 8));
+    ccdSceneLeafKernel<S><<<lgrid, kBlock, 0, e.compute>>>(a, n_cand);
+    FCLB_CUDA(cudaGetLastError());
+    const int g256 = int((n_cand + 255) / 256);
+    ccdSceneIotaKernel<<<g256, 256, 0, e.compute>>>(order, n_cand);
+    size_t b1 = 0, b2 = 0;
+    FCLB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, a.cand_path, path_sorted, order, order1, int(n_cand), 0, 64, e.compute));
+    FCLB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b2, qkey1, qkey2, order1, order2, int(n_cand), 0, 32, e.compute));
+    unsigned char* tmp = nullptr;
+    FCLB_CUDA(sc.get(&tmp, std::max(b1, b2)));
+    FCLB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, b1, a.cand_path, path_sorted, order, order1, int(n_cand), 0, 64, e.compute));
+    ccdSceneGatherKernel<<<g256, 256, 0, e.compute>>>(qkey, order1, n_cand, qkey1);
+    FCLB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, b2, qkey1, qkey2, order1, order2, int(n_cand), 0, 32, e.compute));
+    ccdSceneSelectKernel<S><<<g256, 256, 0, e.compute>>>(qkey2, order2, n_cand, a.cand_code, cand_toc, static_cast<const S*>(a.cand_box),
+                                                         req->max_contacts ? req->max_contacts : 1u, keep, counts, code,
+                                                         static_cast<S*>(toc), static_cast<S*>(box));
+    FCLB_CUDA(cudaGetLastError());
+    e.launches += 6;
+  }
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.last_ms = e.last_call_ms = ms;
+  e.n_rec = 1;
+  e.rec_kind[0] = -9;
+  e.rec_count[0] = n;
+  e.rec_ms[0] = ms;
+  return FCLB_OK;
+}
+
+}  // namespace fclb
+
+using namespace fclb;
+
+extern "C" {
+
+int fclb_translational_ccd_scene_batch_dev(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                           const void* poses_shape, const void* poses_scene, const void* displacements, size_t n,
+                                           int scalar_type, const fclb_ccd_request* req, int scene_moves, uint32_t max_keep,
+                                           uint32_t* out_counts, int64_t* out_code, void* out_toc, void* out_box) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  if (scene_kind != FCLB_SCENE_HEIGHTMAP && scene_kind != FCLB_SCENE_OCTREE)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_scene_batch: scene_kind must be FCLB_SCENE_HEIGHTMAP or FCLB_SCENE_OCTREE");
+  ShapeTable* t = findTable(e, shapes);
+  if (!t) return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_scene_batch: unknown shape table handle");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (!req || req->request_type > 2) return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_scene_batch: bad request");
+  if (n == 0) return FCLB_OK;
+  if (n > 0xfffffffeull) return fail(FCLB_ERR_CAPACITY, "batch larger than 2^32-2 queries: split it");
+  if (!shape_ids || !poses_shape || !poses_scene || !displacements || !out_counts || (max_keep && !out_code))
+    return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_scene_batch: null array");
+  for (uint32_t i = 0; i < t->n; i++)
+    if (t->host[i].type == FCLB_CONVEX && t->host[i].geom < e.convex.size()) {
+      const int nv = e.convex[t->host[i].geom].n_verts;
+      if (nv == 1 || nv == 2 || nv == 3 || nv == 6)
+        return fail(FCLB_ERR_UNSUPPORTED, "scene CCD: Convex shapes with 1, 2, 3 or 6 vertices are not supported");
+    }
+  if (scalar_type == FCLB_F32)
+    return ccdSceneDev<float>(e, scene_kind, scene, t, shape_ids, poses_shape, poses_scene, displacements, n, req, scene_moves,
+                              max_keep, out_counts, reinterpret_cast<long long*>(out_code), out_toc, out_box);
+  return ccdSceneDev<double>(e, scene_kind, scene, t, shape_ids, poses_shape, poses_scene, displacements, n, req, scene_moves,
+                             max_keep, out_counts, reinterpret_cast<long long*>(out_code), out_toc, out_box);
+}
+
+static int translational_ccd_scene_batch_host_one(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                                  const void* poses_shape, const void* poses_scene, const void* displacements,
+                                                  size_t n, int scalar_type, const fclb_ccd_request* req, int scene_moves,
+                                                  uint32_t max_keep, uint32_t* out_counts, int64_t* out_code, void* out_toc,
+                                                  void* out_box) {
+  int rc = ensureInit();
+  if (rc) return rc;
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  if (n == 0) return FCLB_OK;
+  if (!shape_ids || !poses_shape || !poses_scene || !displacements || !out_counts)
+    return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_scene_batch: null array");
+  Engine& e = eng();
+  std::lock_guard<std::recursive_mutex> lk(e.mu);
+  {
+    ShapeTable* t = findTable(e, shapes);
+    if (!t) return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_scene_batch: unknown shape table handle");
+    for (size_t q = 0; q < n; q++)
+      if (shape_ids[q] >= t->n) return fail(FCLB_ERR_BAD_ARG, "shape id out of range");
+  }
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t o_ids = 0;
+  const size_t o_p1 = alignUp(o_ids + n * 4, 256);
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_d = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_cnt = alignUp(o_d + n * 4 * ss, 256);
+  const size_t o_code = alignUp(o_cnt + n * 4, 256);
+  const size_t o_toc = alignUp(o_code + n * max_keep * 8, 256);
+  const size_t o_box = alignUp(o_toc + n * max_keep * 2 * ss, 256);
+  const size_t total = alignUp(o_box + n * max_keep * 6 * ss, 256);
+  rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  FCLB_CUDA(cudaMemcpyAsync(base + o_ids, shape_ids, n * 4, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses_shape, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses_scene, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(base + o_d, displacements, n * 4 * ss, cudaMemcpyHostToDevice, e.compute));
+  rc = fclb_translational_ccd_scene_batch_dev(scene_kind, scene, shapes, reinterpret_cast<const uint32_t*>(base + o_ids), base + o_p1,
+                                              base + o_p2, base + o_d, n, scalar_type, req, scene_moves, max_keep,
+                                              reinterpret_cast<uint32_t*>(base + o_cnt), reinterpret_cast<int64_t*>(base + o_code),
+                                              out_toc ? base + o_toc : nullptr, out_box ? base + o_box : nullptr);
+  if (rc) return rc;
+  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
+  if (max_keep && out_code) FCLB_CUDA(cudaMemcpyAsync(out_code, base + o_code, n * max_keep * 8, cudaMemcpyDeviceToHost, e.compute));
+  if (max_keep && out_toc) FCLB_CUDA(cudaMemcpyAsync(out_toc, base + o_toc, n * max_keep * 2 * ss, cudaMemcpyDeviceToHost, e.compute));
+  if (max_keep && out_box) FCLB_CUDA(cudaMemcpyAsync(out_box, base + o_box, n * max_keep * 6 * ss, cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  return FCLB_OK;
+}
+
+int fclb_translational_ccd_scene_batch_host(int scene_kind, fclb_handle scene, fclb_handle shapes, const uint32_t* shape_ids,
+                                            const void* poses_shape, const void* poses_scene, const void* displacements, size_t n,
+                                            int scalar_type, const fclb_ccd_request* req, int scene_moves, uint32_t max_keep,
+                                            uint32_t* out_counts, int64_t* out_code, void* out_toc, void* out_box) {
+  if (engineCount() <= 1)
+    return translational_ccd_scene_batch_host_one(scene_kind, scene, shapes, shape_ids, poses_shape, poses_scene, displacements, n,
+                                                  scalar_type, req, scene_moves, max_keep, out_counts, out_code, out_toc, out_box);
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  return shardOverDevices(n, [&](size_t b, size_t m_) {
+    return translational_ccd_scene_batch_host_one(scene_kind, scene, shapes, offT(shape_ids, b), offPtr(poses_shape, b * 12 * ss),
+                                                  offPtr(poses_scene, b * 12 * ss), offPtr(displacements, b * 4 * ss), m_, scalar_type,
+                                                  req, scene_moves, max_keep, offT(out_counts, b), offT(out_code, b * max_keep),
+                                                  offPtr(out_toc, b * max_keep * 2 * ss), offPtr(out_box, b * max_keep * 6 * ss));
+  });
+}
+
+}  // extern "C"

@@ -196,6 +196,8 @@ struct OctView {          // octree2::Octree<S> flat arrays (see OctreeArgs)
   int num_layers;
   double root_box[6];
 };
+int sceneHmView(fclb_handle h, int st, HmView& v);  // fclb_scene_api.cu
+int sceneOctView(fclb_handle h, OctView& v);
 struct BvhView {
   const void* nodes;
   const void* tris;

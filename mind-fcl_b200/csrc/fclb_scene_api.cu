@@ -337,6 +337,19 @@ static void fillOctView(const OctreeDev* o, OctView& v) {
   for (int k = 0; k < 6; k++) v.root_box[k] = o->root_box[k];
 }
 
+// views of an uploaded heightmap / octree for the other translation units (fclb_ccd_scene.cu)
+int sceneHmView(fclb_handle h, int st, HmView& v) {
+  auto it = hmTable().find(h);
+  if (it == hmTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown heightmap handle");
+  return fillHmView(it->second, st, v);
+}
+int sceneOctView(fclb_handle h, OctView& v) {
+  auto it = octTable().find(h);
+  if (it == octTable().end()) return fail(FCLB_ERR_BAD_ARG, "unknown octree handle");
+  fillOctView(it->second, v);
+  return FCLB_OK;
+}
+
 template <typename S>
 static int scenePairDev(Engine& e, int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
                         const void* poses2, size_t n, const fclb_request* req, uint32_t max_keep, uint32_t* counts,

@@ -48,7 +48,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
-    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_octree_build_dev", "fclb_octree_build_points_host", "fclb_octree_info", "fclb_octree_export", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_translational_ccd_mesh_batch_host", "fclb_translational_ccd_mesh_batch_dev", "fclb_translational_ccd_mesh_pair_batch_host", "fclb_translational_ccd_mesh_pair_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
+    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_octree_build_dev", "fclb_octree_build_points_host", "fclb_octree_info", "fclb_octree_export", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_translational_ccd_mesh_batch_host", "fclb_translational_ccd_mesh_batch_dev", "fclb_translational_ccd_mesh_pair_batch_host", "fclb_translational_ccd_mesh_pair_batch_dev", "fclb_translational_ccd_scene_batch_host", "fclb_translational_ccd_scene_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
     "fclb_measure_fp_peak", "fclb_measure_l2_bandwidth", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -822,6 +822,25 @@ def translational_ccd_mesh_pair_batch_host(bvh1, bvh2, poses1, poses2, displacem
     check(fn(bvh1, bvh2, _ptr(poses1), _ptr(poses2), _ptr(displacements), n, scalar_type, C.cast(C.pointer(r), C.c_void_p), max_keep,
              _ptr(counts), _ptr(prim), _ptr(toc)))
     return counts, prim, toc
+
+
+def translational_ccd_scene_batch_host(scene_kind, scene, table, shape_ids, poses_shape, poses_scene, displacements, scalar_type,
+                                       request_type=0, max_contacts=1, scene_moves=False, max_keep=8):
+    """fcl::translational_ccd(shape, heightmap | octree): (counts, codes i64 [n, keep], toc [n, keep, 2], boxes [n, keep, 6])"""
+    n = len(shape_ids)
+    dt = np_dtype(scalar_type)
+    counts = np.zeros(n, np.uint32)
+    code = np.zeros((n, max_keep), np.int64)
+    toc = np.zeros((n, max_keep, 2), dt)
+    box = np.zeros((n, max_keep, 6), dt)
+    ids = np.ascontiguousarray(shape_ids, np.uint32)
+    r = CcdRequest(request_type, max_contacts, 0.0, 0.0, 0, 0)
+    fn = load().fclb_translational_ccd_scene_batch_host
+    fn.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                   C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    check(fn(scene_kind, scene, table, _ptr(ids), _ptr(poses_shape), _ptr(poses_scene), _ptr(displacements), n, scalar_type,
+             C.cast(C.pointer(r), C.c_void_p), 1 if scene_moves else 0, max_keep, _ptr(counts), _ptr(code), _ptr(toc), _ptr(box)))
+    return counts, code, toc, box
 
 
 def measure_l2_bandwidth() -> float:

@@ -228,6 +228,24 @@ class RefOracle(_Oracle):
           _p(prim), _p(toc), threads)
         return counts, prim, toc
 
+    def translational_ccd_scene_batch(self, kind, scene_id, shapes, shape_ids, poses_shape, poses_scene, disp, request_type=0,
+                                      max_contacts=1, scene_moves=False, keep=8, threads=1):
+        """fcl::translational_ccd(shape, heightmap | octree): (counts, codes i64 [n, keep], toc [n, keep, 2], boxes [n, keep, 6])"""
+        n = len(shape_ids)
+        dt = poses_shape.dtype
+        counts = np.zeros(n, np.uint32)
+        code = np.full((n, keep), -1, np.int64)
+        toc = np.full((n, keep, 2), -1, dt)
+        box = np.zeros((n, keep, 6), dt)
+        arr = _shape_array(shapes)
+        ids = np.ascontiguousarray(shape_ids, np.uint32)
+        f = self.fn("translational_ccd_scene_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                      C.c_int, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(dt), kind, scene_id, C.cast(arr, C.c_void_p), len(shapes), _p(ids), _p(poses_shape), _p(poses_scene), _p(disp), n,
+          request_type, max_contacts, 1 if scene_moves else 0, keep, _p(counts), _p(code), _p(toc), _p(box), threads)
+        return counts, code, toc, box
+
     # ---- meshes (reference BVHModel<OBBRSS<S>>) ----
     def bvh_create(self, verts, tris):
         verts = np.ascontiguousarray(verts, np.float64)

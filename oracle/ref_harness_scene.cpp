@@ -649,3 +649,73 @@ int fclref_mesh_shape_collide_batch(int scalar_type, int mesh_id, const void* sh
 }
 
 }  // extern "C"
+
+// ---- translational continuous collision, shape vs heightmap / octree ----------------------------
+// fcl::translational_ccd(shape, tf_shape, displacement, scene, tf_scene, ...) and the scene-first entry
+// (TranslationalDisplacementHeightMapSolver::RunShapeHeightMap / RunHeightMapShape, heightmap_ccd_solver-inl.h:8-166;
+// TranslationalDisplacementOctreeSolver::RunShapeOctree / RunOctreeShape, octree2_ccd_solver-inl.h).
+// kind: 1 heightmap, 2 octree.  Per contact: b2 (encodePixel / encodeOctree2Node), toc, o2_bv (6 S).
+namespace {
+template <typename S>
+void ccdSceneBatch(const fcl::CollisionGeometry<S>* scene, const ShapeRec* shapes, uint32_t n_shapes, const uint32_t* shape_ids,
+                   const S* poses_shape, const S* poses_scene, const S* disp, size_t n, int request_type, uint32_t max_contacts,
+                   int scene_moves, uint32_t keep, uint32_t* counts, int64_t* code, S* toc, S* box, int threads) {
+  std::vector<std::shared_ptr<fcl::ShapeBase<S>>> tab;
+  for (uint32_t i = 0; i < n_shapes; i++) {
+    tab.push_back(Sel<S>::shape(shapes + i));
+    tab.back()->computeLocalAABB();
+  }
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    fcl::ContinuousCollisionRequest<S> req;
+    req.request_type = static_cast<fcl::TimeOfCollisionRequestType>(request_type);
+    req.num_max_contacts = max_contacts;
+    for (size_t q = b; q < e; q++) {
+      const auto tf_s = loadPose<S>(poses_shape + 12 * q);
+      const auto tf_g = loadPose<S>(poses_scene + 12 * q);
+      fcl::TranslationalDisplacement<S> d;
+      d.unit_axis_in_shape1 = fcl::Vector3<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]);
+      d.scalar_displacement = disp[4 * q + 3];
+      fcl::ContinuousCollisionResult<S> res;
+      if (scene_moves)
+        fcl::translational_ccd<S>(scene, tf_g, d, tab[shape_ids[q]].get(), tf_s, req, res);
+      else
+        fcl::translational_ccd<S>(tab[shape_ids[q]].get(), tf_s, d, scene, tf_g, req, res);
+      counts[q] = uint32_t(res.num_contacts());
+      for (uint32_t k = 0; k < keep && k < res.num_contacts(); k++) {
+        const auto& c = res.raw_contacts()[k];
+        const size_t o = size_t(q) * keep + k;
+        // the scene geometry is o2 for the shape-first entry; record whichever side carries the id
+        const bool scene_is_o2 = c.o2 == scene;
+        code[o] = scene_is_o2 ? c.b2 : c.b1;
+        const auto& bv = scene_is_o2 ? c.o2_bv : c.o1_bv;
+        toc[2 * o] = c.toc.lower_bound;
+        toc[2 * o + 1] = c.toc.upper_bound;
+        for (int j = 0; j < 3; j++) {
+          box[6 * o + j] = bv.min_[j];
+          box[6 * o + 3 + j] = bv.max_[j];
+        }
+      }
+    }
+  });
+}
+}  // namespace
+extern "C" int fclref_translational_ccd_scene_batch(int scalar_type, int kind, int scene_id, const void* shapes, uint32_t n_shapes,
+                                                    const uint32_t* shape_ids, const void* poses_shape, const void* poses_scene,
+                                                    const void* disp, size_t n, int request_type, uint32_t max_contacts,
+                                                    int scene_moves, uint32_t keep, uint32_t* counts, int64_t* code, void* toc,
+                                                    void* box, int threads) {
+  if (scalar_type == 0) {
+    const fcl::CollisionGeometry<float>* g = kind == 1 ? (const fcl::CollisionGeometry<float>*)getHm<float>(scene_id)
+                                                        : (const fcl::CollisionGeometry<float>*)getOct<float>(scene_id);
+    ccdSceneBatch<float>(g, (const ShapeRec*)shapes, n_shapes, shape_ids, (const float*)poses_shape, (const float*)poses_scene,
+                         (const float*)disp, n, request_type, max_contacts, scene_moves, keep, counts, code, (float*)toc,
+                         (float*)box, threads);
+  } else {
+    const fcl::CollisionGeometry<double>* g = kind == 1 ? (const fcl::CollisionGeometry<double>*)getHm<double>(scene_id)
+                                                         : (const fcl::CollisionGeometry<double>*)getOct<double>(scene_id);
+    ccdSceneBatch<double>(g, (const ShapeRec*)shapes, n_shapes, shape_ids, (const double*)poses_shape, (const double*)poses_scene,
+                          (const double*)disp, n, request_type, max_contacts, scene_moves, keep, counts, code, (double*)toc,
+                          (double*)box, threads);
+  }
+  return 0;
+}

@@ -385,6 +385,28 @@ void runBatch() {
     EXPECT_TRUE(hit_r.num_contacts() >= 2 && hit_r.num_contacts() <= 4 && miss_r.num_contacts() == 0);
     for (const auto& ct : hit_r.raw_contacts()) EXPECT_TRUE(ct.o1 == &lid && ct.o2 == &floor && ct.b1 >= 0 && ct.b1 < 2 && ct.b2 >= 0 && ct.b2 < 2);
   }
+  // shape vs heightmap / octree: the bar dropping 1 m onto the four 0.5 m columns touches all four; the contact names the
+  // pixel and carries its box; an upward sweep touches nothing; the same with the octree's four voxels
+  {
+    TranslationalDisplacement<S> down, up;
+    down.unit_axis_in_shape1 = Vector3<S>(0, 0, -1);
+    up.unit_axis_in_shape1 = Vector3<S>(0, 0, 1);
+    down.scalar_displacement = up.scalar_displacement = 1;
+    ContinuousCollisionRequest<S> creq;
+    creq.num_max_contacts = 16;
+    creq.request_type = TimeOfCollisionRequestType::kBoxApproximate;
+    ContinuousCollisionResult<S> h_hit, h_miss, o_hit, hm_moves;
+    translational_ccd<S>(&bar, at(S(0.2), S(0.05), S(1.0)), down, &hm, I, creq, h_hit);
+    translational_ccd<S>(&bar, at(S(0.2), S(0.05), S(1.0)), up, &hm, I, creq, h_miss);
+    translational_ccd<S>(&bar, at(S(0.2), S(0.05), S(0.6)), down, &oct, I, creq, o_hit);
+    translational_ccd<S>(&hm, I, up, &bar, at(S(0.2), S(0.05), S(1.0)), creq, hm_moves);  // the map rises instead
+    EXPECT_TRUE(h_hit.num_contacts() == 4 && h_miss.num_contacts() == 0 && o_hit.num_contacts() == 4 && hm_moves.num_contacts() == 4);
+    for (const auto& ct : h_hit.raw_contacts()) {
+      EXPECT_TRUE(ct.o1 == &bar && ct.o2 == &hm && (ct.b2 & 0xffff) == 8);
+      EXPECT_TRUE(std::fabs(ct.o2_bv.max_[2] - S(0.5)) < S(1e-3) && ct.o2_bv.min_[2] == 0);
+      EXPECT_TRUE(std::fabs(ct.toc.lower_bound - S(0.47)) < S(1e-3));  // bar bottom at 0.97 reaches the column tops at 0.5
+    }
+  }
   // UserContactProcessFunctor on the host: keep only contacts on triangle 1, stop after two
   std::vector<CollisionQuery<S>> one_q{{&floor, I, &ball, at(0, 0, S(0.1))}};
   std::vector<CollisionResult<S>> fr;
