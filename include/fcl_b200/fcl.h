@@ -235,6 +235,37 @@ class BVHModel<OBBRSS<S>> : public CollisionGeometry<S> {
                   "fclb_bvh_build");
     return 0;
   }
+  // the replace / update protocol (BVH_model.h:127-160): same triangles, moved vertices; the hierarchy keeps its
+  // topology and is refitted on the device -- bottom-up by default, as the reference's default arguments ask
+  int beginReplaceModel() {
+    if (!handle_) return -1;  // BVH_ERR_BUILD_EMPTY_PREVIOUS_FRAME
+    new_verts_.clear();
+    return 0;
+  }
+  int replaceSubModel(const std::vector<Vector3<S>>& points) {
+    for (const auto& p : points)
+      for (int k = 0; k < 3; k++) new_verts_.push_back(double(p[k]));
+    return 0;
+  }
+  int endReplaceModel(bool refit = true, bool bottomup = true) {
+    if (new_verts_.size() != verts_.size()) {
+      std::cerr << "BVH Error! The replaced model should have the same number of vertices_ as the old model.\n";
+      return -4;  // BVH_ERR_INCORRECT_DATA
+    }
+    verts_ = new_verts_;
+    if (!refit) return endModel();  // reconstruct the tree from the current frame
+    std::vector<S> tri_verts(tris_.size() * 3);
+    for (std::size_t i = 0; i < tris_.size(); i++)
+      for (int k = 0; k < 3; k++) tri_verts[3 * i + k] = S(verts_[3 * std::size_t(tris_[i]) + k]);
+    const int n_tris = int(tris_.size() / 3);
+    detail::check(bottomup ? fclb_bvh_refit_bottomup_host(handle_, tri_verts.data(), n_tris)
+                           : fclb_bvh_refit_host(handle_, tri_verts.data(), n_tris),
+                  "fclb_bvh_refit");
+    return 0;
+  }
+  int beginUpdateModel() { return beginReplaceModel(); }
+  int updateSubModel(const std::vector<Vector3<S>>& points) { return replaceSubModel(points); }
+  int endUpdateModel(bool refit = true, bool bottomup = true) { return endReplaceModel(refit, bottomup); }
   int getNumBVs() const {
     int n = 0;
     if (handle_) fclb_bvh_info(handle_, &n, nullptr, nullptr);
@@ -250,7 +281,7 @@ class BVHModel<OBBRSS<S>> : public CollisionGeometry<S> {
 
  private:
   fclb_handle handle_ = 0;
-  std::vector<double> verts_;
+  std::vector<double> verts_, new_verts_;
   std::vector<int32_t> tris_;
 };
 

@@ -311,6 +311,12 @@ int fclb_bvh_build_host(const double* verts, int n_verts, const int32_t* tris, i
  * re-perceived scene mesh: no host rebuild, no re-upload of the tree. */
 int fclb_bvh_refit_host(fclb_handle bvh, const void* tri_verts, int n_tris);
 int fclb_bvh_refit_dev(fclb_handle bvh, const void* tri_verts, int n_tris);
+/* BVHModel::endReplaceModel(refit = true, bottomup = true) / endUpdateModel(true, true) -- the reference's DEFAULT arguments
+ * (BVH_model.h:137): refitTreeBottomUp (BVH_model-inl.h:580-617): leaf box = 3-point fit of its triangle, inner box =
+ * left + right (OBB<S>::operator+: merge_largedist / merge_smalldist, math/bv/OBB-inl.h:116-293).  Node-for-node identical
+ * to the reference's OBBs (tests/test_bvh_refit_gpu.py). */
+int fclb_bvh_refit_bottomup_host(fclb_handle bvh, const void* tri_verts, int n_tris);
+int fclb_bvh_refit_bottomup_dev(fclb_handle bvh, const void* tri_verts, int n_tris);
 int fclb_bvh_info(fclb_handle bvh, int* n_nodes, int* n_tris, int* scalar_type);
 /* copies the tree back in the fclb_bvh_upload layout (any pointer may be NULL) */
 int fclb_bvh_export(fclb_handle bvh, void* obb, int32_t* first_child, void* tri_verts);

@@ -518,6 +518,278 @@ __global__ void __launch_bounds__(256) bvhRefitKernel(S* __restrict__ nodes, con
   }
 }
 
+// ---- bottom-up refit (BVHModel::refitTreeBottomUp, BVH_model-inl.h:580-617) --------------------------------------
+// A leaf box is fit(3 points) -> OBB_fit_functions::fit3 (math/bv/utility-inl.h:85-109); an inner box is
+// left.bv + right.bv -> OBB<S>::operator+ (math/bv/OBB-inl.h:116-126): merge_largedist when the centres are further
+// apart than twice the summed largest half sides (first axis = the centre difference, the other two from the covariance
+// of the 16 corners projected off it, :197-244), else merge_smalldist (rotation = the normalised sum of the two
+// quaternions, box around the 16 corners, :248-293).  Only the OBB half of OBBRSS is kept (collide reads nothing else).
+template <typename S>
+struct ObbB {
+  S axis[9];  // row-major axis(i, j)
+  S To[3], ext[3];
+};
+template <typename S>
+FCLB_DI void obbCorners(const ObbB<S>& b, S v[8][3]) {  // computeVertices (OBB-inl.h:177-193)
+  S e0[3], e1[3], e2[3];
+  for (int k = 0; k < 3; k++) {
+    e0[k] = b.axis[3 * k + 0] * b.ext[0];
+    e1[k] = b.axis[3 * k + 1] * b.ext[1];
+    e2[k] = b.axis[3 * k + 2] * b.ext[2];
+  }
+  const int s0[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, s1[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, s2[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+  for (int i = 0; i < 8; i++)
+    for (int k = 0; k < 3; k++) {
+      S t = s0[i] > 0 ? b.To[k] + e0[k] : b.To[k] - e0[k];
+      t = s1[i] > 0 ? t + e1[k] : t - e1[k];
+      v[i][k] = s2[i] > 0 ? t + e2[k] : t - e2[k];
+    }
+}
+template <typename S>
+FCLB_DI void quatFromAxis(const S* m, S q[4]) {  // Quaternion(Matrix3): Shepperd's method; q = (x, y, z, w)
+  S t = m[0] + m[4] + m[8];
+  if (t > S(0)) {
+    t = fsqrt(t + S(1.0));
+    q[3] = S(0.5) * t;
+    t = S(0.5) / t;
+    q[0] = (m[7] - m[5]) * t;
+    q[1] = (m[2] - m[6]) * t;
+    q[2] = (m[3] - m[1]) * t;
+  } else {
+    int i = 0;
+    if (m[4] > m[0]) i = 1;
+    if (m[8] > m[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = fsqrt(m[4 * i] - m[4 * j] - m[4 * k] + S(1.0));
+    q[i] = S(0.5) * t;
+    t = S(0.5) / t;
+    q[3] = (m[3 * k + j] - m[3 * j + k]) * t;
+    q[j] = (m[3 * j + i] + m[3 * i + j]) * t;
+    q[k] = (m[3 * k + i] + m[3 * i + k]) * t;
+  }
+}
+template <typename S>
+FCLB_DI void obbMerge(const ObbB<S>& b1, const ObbB<S>& b2, ObbB<S>& b) {
+  const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
+  S cd[3];
+  for (int k = 0; k < 3; k++) cd[k] = b1.To[k] - b2.To[k];
+  const S m1 = fmax_(fmax_(b1.ext[0], b1.ext[1]), b1.ext[2]), m2 = fmax_(fmax_(b2.ext[0], b2.ext[1]), b2.ext[2]);
+  const S cd2 = (cd[0] * cd[0] + cd[1] * cd[1]) + cd[2] * cd[2];
+  S v[16][3];
+  obbCorners(b1, v);
+  obbCorners(b2, v + 8);
+  if (fsqrt(cd2) > 2 * (m1 + m2)) {  // merge_largedist
+    S a0[3] = {cd[0], cd[1], cd[2]};
+    if (cd2 > S(0)) {
+      const S n = fsqrt(cd2);
+      for (int k = 0; k < 3; k++) a0[k] = a0[k] / n;
+    }
+    S S1[3] = {0, 0, 0}, c00 = 0, c11 = 0, c22 = 0, c01 = 0, c02 = 0, c12 = 0;
+    for (int i = 0; i < 16; i++) {
+      const S d = (v[i][0] * a0[0] + v[i][1] * a0[1]) + v[i][2] * a0[2];
+      S p[3];
+      for (int k = 0; k < 3; k++) p[k] = v[i][k] - a0[k] * d;
+      for (int k = 0; k < 3; k++) S1[k] += p[k];
+      c00 += p[0] * p[0];
+      c11 += p[1] * p[1];
+      c22 += p[2] * p[2];
+      c01 += p[0] * p[1];
+      c02 += p[0] * p[2];
+      c12 += p[1] * p[2];
+    }
+    const int n_points = 16;
+    S M[3][3];
+    M[0][0] = c00 - S1[0] * S1[0] / n_points;
+    M[1][1] = c11 - S1[1] * S1[1] / n_points;
+    M[2][2] = c22 - S1[2] * S1[2] / n_points;
+    M[0][1] = c01 - S1[0] * S1[1] / n_points;
+    M[1][2] = c12 - S1[1] * S1[2] / n_points;
+    M[0][2] = c02 - S1[0] * S1[2] / n_points;
+    M[1][0] = M[0][1];
+    M[2][0] = M[0][2];
+    M[2][1] = M[1][2];
+    S d[3] = {0, 0, 0}, vec[3][3];
+    if (!hostbuild::jacobi3<S>(M, d, vec)) {
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) vec[i][j] = (i == j) ? S(1) : S(0);
+    }
+    int mn, md, mx;
+    if (d[0] > d[1]) {
+      mx = 0;
+      mn = 1;
+    } else {
+      mn = 0;
+      mx = 1;
+    }
+    if (d[2] < d[mn]) {
+      md = mn;
+      mn = 2;
+    } else if (d[2] > d[mx]) {
+      md = mx;
+      mx = 2;
+    } else {
+      md = 2;
+    }
+    (void)mn;
+    for (int r = 0; r < 3; r++) {
+      b.axis[3 * r + 0] = a0[r];
+      b.axis[3 * r + 1] = vec[r][mx];
+      b.axis[3 * r + 2] = vec[r][md];
+    }
+    S lo[3] = {big, big, big}, hi[3] = {-big, -big, -big};
+    for (int i = 0; i < 16; i++)
+      for (int j = 0; j < 3; j++) {
+        const S proj = (b.axis[j] * v[i][0] + b.axis[3 + j] * v[i][1]) + b.axis[6 + j] * v[i][2];
+        if (proj > hi[j]) hi[j] = proj;
+        if (proj < lo[j]) lo[j] = proj;
+      }
+    S o[3];
+    for (int k = 0; k < 3; k++) o[k] = (hi[k] + lo[k]) / 2;
+    for (int r = 0; r < 3; r++) b.To[r] = (b.axis[3 * r] * o[0] + b.axis[3 * r + 1] * o[1]) + b.axis[3 * r + 2] * o[2];
+    for (int k = 0; k < 3; k++) b.ext[k] = (hi[k] - lo[k]) * S(0.5);
+    return;
+  }
+  // merge_smalldist
+  for (int k = 0; k < 3; k++) b.To[k] = (b1.To[k] + b2.To[k]) * S(0.5);
+  S q0[4], q1[4], q[4];
+  quatFromAxis(b1.axis, q0);
+  quatFromAxis(b2.axis, q1);
+  const S dt = ((q0[0] * q1[0] + q0[1] * q1[1]) + q0[2] * q1[2]) + q0[3] * q1[3];
+  if (dt < 0)
+    for (int k = 0; k < 4; k++) q1[k] = -q1[k];
+  for (int k = 0; k < 4; k++) q[k] = q0[k] + q1[k];
+  {
+    const S z = ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3];
+    if (z > S(0)) {
+      const S n = fsqrt(z);
+      for (int k = 0; k < 4; k++) q[k] = q[k] / n;
+    }
+  }
+  {  // toRotationMatrix
+    const S tx = S(2) * q[0], ty = S(2) * q[1], tz = S(2) * q[2];
+    const S twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+    const S txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+    const S tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+    b.axis[0] = S(1) - (tyy + tzz);
+    b.axis[1] = txy - twz;
+    b.axis[2] = txz + twy;
+    b.axis[3] = txy + twz;
+    b.axis[4] = S(1) - (txx + tzz);
+    b.axis[5] = tyz - twx;
+    b.axis[6] = txz - twy;
+    b.axis[7] = tyz + twx;
+    b.axis[8] = S(1) - (txx + tyy);
+  }
+  S pmin[3] = {big, big, big}, pmax[3] = {-big, -big, -big};
+  for (int i = 0; i < 16; i++) {
+    S diff[3];
+    for (int k = 0; k < 3; k++) diff[k] = v[i][k] - b.To[k];
+    for (int j = 0; j < 3; j++) {
+      const S dot = (diff[0] * b.axis[j] + diff[1] * b.axis[3 + j]) + diff[2] * b.axis[6 + j];
+      if (dot > pmax[j])
+        pmax[j] = dot;
+      else if (dot < pmin[j])
+        pmin[j] = dot;
+    }
+  }
+  for (int j = 0; j < 3; j++) {
+    const S h = S(0.5) * (pmax[j] + pmin[j]);
+    for (int k = 0; k < 3; k++) b.To[k] += b.axis[3 * k + j] * h;
+    b.ext[j] = S(0.5) * (pmax[j] - pmin[j]);
+  }
+}
+template <typename S>
+FCLB_DI void loadObbB(const S* nodes, int i, ObbB<S>& b) {
+  const S* p = nodes + size_t(16) * i;
+  for (int k = 0; k < 9; k++) b.axis[k] = p[k];
+  for (int k = 0; k < 3; k++) {
+    b.To[k] = p[9 + k];
+    b.ext[k] = p[12 + k];
+  }
+}
+template <typename S>
+FCLB_DI void storeObbB(S* nodes, int i, const ObbB<S>& b) {
+  S* p = nodes + size_t(16) * i;
+  for (int k = 0; k < 9; k++) p[k] = b.axis[k];
+  for (int k = 0; k < 3; k++) {
+    p[9 + k] = b.To[k];
+    p[12 + k] = b.ext[k];
+  }
+}
+// one thread per leaf: fits its box, then climbs; the second thread to arrive at a node merges the two children
+template <typename S>
+__global__ void __launch_bounds__(128) bvhRefitBottomUpKernel(S* nodes, const S* __restrict__ tris, const int* __restrict__ leaf_node,
+                                                              const int* __restrict__ parent, int* __restrict__ arrived, int n_tris) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tris) return;
+  int node = leaf_node[t];
+  {
+    const S* p = tris + size_t(12) * t;
+    // OBB_fit_functions::fit3 + getExtentAndCenter_pointcloud
+    const S e0[3] = {p[0] - p[4], p[1] - p[5], p[2] - p[6]}, e1[3] = {p[4] - p[8], p[5] - p[9], p[6] - p[10]},
+            e2[3] = {p[8] - p[0], p[9] - p[1], p[10] - p[2]};
+    const S l0 = (e0[0] * e0[0] + e0[1] * e0[1]) + e0[2] * e0[2], l1 = (e1[0] * e1[0] + e1[1] * e1[1]) + e1[2] * e1[2],
+            l2 = (e2[0] * e2[0] + e2[1] * e2[1]) + e2[2] * e2[2];
+    int imax = 0;
+    if (l1 > l0) imax = 1;
+    if (l2 > (imax == 0 ? l0 : l1)) imax = 2;
+    S c2[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+    {
+      const S z = (c2[0] * c2[0] + c2[1] * c2[1]) + c2[2] * c2[2];
+      if (z > S(0)) {
+        const S n = fsqrt(z);
+        for (int k = 0; k < 3; k++) c2[k] = c2[k] / n;
+      }
+    }
+    S c0[3];
+    for (int k = 0; k < 3; k++) c0[k] = imax == 0 ? e0[k] : (imax == 1 ? e1[k] : e2[k]);
+    {
+      const S z = (c0[0] * c0[0] + c0[1] * c0[1]) + c0[2] * c0[2];
+      if (z > S(0)) {
+        const S n = fsqrt(z);
+        for (int k = 0; k < 3; k++) c0[k] = c0[k] / n;
+      }
+    }
+    const S c1[3] = {c2[1] * c0[2] - c2[2] * c0[1], c2[2] * c0[0] - c2[0] * c0[2], c2[0] * c0[1] - c2[1] * c0[0]};
+    ObbB<S> b;
+    for (int r = 0; r < 3; r++) {
+      b.axis[3 * r + 0] = c0[r];
+      b.axis[3 * r + 1] = c1[r];
+      b.axis[3 * r + 2] = c2[r];
+    }
+    const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
+    S lo[3] = {big, big, big}, hi[3] = {-big, -big, -big};
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        const S proj = (b.axis[j] * p[4 * i] + b.axis[3 + j] * p[4 * i + 1]) + b.axis[6 + j] * p[4 * i + 2];
+        if (proj > hi[j]) hi[j] = proj;
+        if (proj < lo[j]) lo[j] = proj;
+      }
+    S o[3];
+    for (int k = 0; k < 3; k++) o[k] = (hi[k] + lo[k]) / 2;
+    for (int r = 0; r < 3; r++) b.To[r] = (b.axis[3 * r] * o[0] + b.axis[3 * r + 1] * o[1]) + b.axis[3 * r + 2] * o[2];
+    for (int k = 0; k < 3; k++) b.ext[k] = (hi[k] - lo[k]) * S(0.5);
+    storeObbB(nodes, node, b);
+  }
+  while (node != 0) {
+    node = parent[node];
+    __threadfence();
+    if (atomicAdd(&arrived[node], 1) == 0) return;  // the sibling subtree is not done yet: its last thread continues
+    __threadfence();
+    S* np = nodes + size_t(16) * node;
+    int fc;
+    if (sizeof(S) == 4)
+      fc = __float_as_int(float(np[15]));
+    else
+      fc = int(__double_as_longlong(double(np[15])));
+    ObbB<S> a, c, m;
+    loadObbB(nodes, fc, a);
+    loadObbB(nodes, fc + 1, c);
+    obbMerge(a, c, m);
+    storeObbB(nodes, node, m);
+  }
+}
+
 // 9 S per triangle (upload layout) -> the 12 S device records
 template <typename S>
 __global__ void triRepackKernel(const S* __restrict__ in9, int n_tris, S* __restrict__ out12) {
@@ -559,15 +831,46 @@ static void deriveRanges(const int32_t* first_child, int n_nodes, int n_tris, st
   }
 }
 
+// parent links and the leaf of every triangle, for the bottom-up refit
+static int ensureParents(BvhDev* d) {
+  if (d->d_parent) return FCLB_OK;
+  if (int(d->h_child.size()) != d->n_nodes) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_refit: the BVH has no host copy of its child links");
+  std::vector<int> parent(size_t(d->n_nodes), 0), leaf(size_t(d->n_tris), 0);
+  for (int i = 0; i < d->n_nodes; i++) {
+    const int fc = d->h_child[size_t(i)];
+    if (fc < 0) {
+      leaf[size_t(-(fc + 1))] = i;
+    } else {
+      parent[size_t(fc)] = i;
+      parent[size_t(fc) + 1] = i;
+    }
+  }
+  FCLB_CUDA(cudaMalloc(&d->d_parent, parent.size() * sizeof(int)));
+  FCLB_CUDA(cudaMalloc(&d->d_leaf_node, leaf.size() * sizeof(int)));
+  FCLB_CUDA(cudaMalloc(&d->d_arrived, parent.size() * sizeof(int)));
+  FCLB_CUDA(cudaMemcpy(d->d_parent, parent.data(), parent.size() * sizeof(int), cudaMemcpyHostToDevice));
+  FCLB_CUDA(cudaMemcpy(d->d_leaf_node, leaf.data(), leaf.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return FCLB_OK;
+}
+
 template <typename S>
-static int refitDev(Engine& e, BvhDev* d, const void* d_tri9) {
+static int refitDev(Engine& e, BvhDev* d, const void* d_tri9, int bottomup) {
   const int g = int(std::min<size_t>((size_t(d->n_tris) * 3 + 255) / 256, size_t(e.sms) * 8));
   triRepackKernel<S><<<g, 256, 0, e.compute>>>(static_cast<const S*>(d_tri9), d->n_tris, static_cast<S*>(d->tris));
   const int warps_per_cta = 8;
   const int grid = int(std::min<size_t>((size_t(d->n_nodes) + warps_per_cta - 1) / warps_per_cta, size_t(e.sms) * 16));
+  if (bottomup) {
+    const int rc = ensureParents(d);
+    if (rc) return rc;
+    FCLB_CUDA(cudaMemsetAsync(d->d_arrived, 0, size_t(d->n_nodes) * sizeof(int), e.compute));
+  }
   FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
-  bvhRefitKernel<S><<<grid, warps_per_cta * 32, 0, e.compute>>>(static_cast<S*>(d->nodes), static_cast<const S*>(d->tris), d->d_range,
-                                                               d->d_prim, d->n_nodes);
+  if (bottomup)
+    bvhRefitBottomUpKernel<S><<<(d->n_tris + 127) / 128, 128, 0, e.compute>>>(static_cast<S*>(d->nodes), static_cast<const S*>(d->tris),
+                                                                            d->d_leaf_node, d->d_parent, d->d_arrived, d->n_tris);
+  else
+    bvhRefitKernel<S><<<grid, warps_per_cta * 32, 0, e.compute>>>(static_cast<S*>(d->nodes), static_cast<const S*>(d->tris), d->d_range,
+                                                                 d->d_prim, d->n_nodes);
   FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
   e.launches += 2;
   FCLB_CUDA(cudaGetLastError());
@@ -746,6 +1049,9 @@ static int bvh_release_one(fclb_handle h) {
   cudaFree(it->second->d_range);
   cudaFree(it->second->d_prim);
   cudaFree(it->second->d_dfs_rank);
+  cudaFree(it->second->d_parent);
+  cudaFree(it->second->d_leaf_node);
+  cudaFree(it->second->d_arrived);
   delete it->second;
   bvhTable().erase(it);
   return FCLB_OK;
@@ -758,7 +1064,7 @@ int fclb_bvh_release(fclb_handle h) {
 
 // BVHModel::beginReplaceModel / replaceSubModel / endReplaceModel(refit = true, bottomup = false): the vertices move, the
 // topology stays; every node OBB is fitted again on the device (bvhRefitKernel).
-static int bvh_refit_one(fclb_handle bvh, const void* tri_verts, int n_tris, int on_device) {
+static int bvh_refit_one(fclb_handle bvh, const void* tri_verts, int n_tris, int on_device, int bottomup = 0) {
   int rc = ensureInit();
   if (rc) return rc;
   Engine& e = eng();
@@ -775,7 +1081,7 @@ static int bvh_refit_one(fclb_handle bvh, const void* tri_verts, int n_tris, int
     FCLB_CUDA(cudaMemcpyAsync(e.d_stage, tri_verts, bytes, cudaMemcpyHostToDevice, e.compute));
     d_in = e.d_stage;
   }
-  return d->scalar_type == FCLB_F32 ? refitDev<float>(e, d, d_in) : refitDev<double>(e, d, d_in);
+  return d->scalar_type == FCLB_F32 ? refitDev<float>(e, d, d_in, bottomup) : refitDev<double>(e, d, d_in, bottomup);
 }
 int fclb_bvh_refit_host(fclb_handle bvh, const void* tri_verts, int n_tris) {
   const int rc_init_ = ensureInit();
@@ -783,6 +1089,12 @@ int fclb_bvh_refit_host(fclb_handle bvh, const void* tri_verts, int n_tris) {
   return forEachDevice([&] { return bvh_refit_one(bvh, tri_verts, n_tris, 0); });
 }
 int fclb_bvh_refit_dev(fclb_handle bvh, const void* tri_verts, int n_tris) { return bvh_refit_one(bvh, tri_verts, n_tris, 1); }
+int fclb_bvh_refit_bottomup_host(fclb_handle bvh, const void* tri_verts, int n_tris) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  return forEachDevice([&] { return bvh_refit_one(bvh, tri_verts, n_tris, 0, 1); });
+}
+int fclb_bvh_refit_bottomup_dev(fclb_handle bvh, const void* tri_verts, int n_tris) { return bvh_refit_one(bvh, tri_verts, n_tris, 1, 1); }
 
 int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* poses1, const void* poses2, size_t n,
                                int scalar_type, const fclb_request* req, uint32_t* out_counts,

@@ -24,6 +24,7 @@ struct BvhDev {
   // from the child links (the leaves of a subtree, left to right, are its slice of primitive_indices_)
   int2* d_range = nullptr;  // [n_nodes] (first, count)
   int* d_prim = nullptr;    // [n_tris]
+  int *d_parent = nullptr, *d_leaf_node = nullptr, *d_arrived = nullptr;  // bottom-up refit: parent links, leaf of every triangle, arrival counters
   int* d_dfs_rank = nullptr;  // [n_tris] position of the triangle's leaf in a right-child-first depth-first walk (CCD contact order)
 };
 

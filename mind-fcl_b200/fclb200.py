@@ -48,7 +48,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
-    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_octree_build_dev", "fclb_octree_build_points_host", "fclb_octree_info", "fclb_octree_export", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_translational_ccd_mesh_batch_host", "fclb_translational_ccd_mesh_batch_dev", "fclb_translational_ccd_mesh_pair_batch_host", "fclb_translational_ccd_mesh_pair_batch_dev", "fclb_translational_ccd_scene_batch_host", "fclb_translational_ccd_scene_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
+    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_bvh_refit_bottomup_host", "fclb_bvh_refit_bottomup_dev", "fclb_octree_build_dev", "fclb_octree_build_points_host", "fclb_octree_info", "fclb_octree_export", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_translational_ccd_mesh_batch_host", "fclb_translational_ccd_mesh_batch_dev", "fclb_translational_ccd_mesh_pair_batch_host", "fclb_translational_ccd_mesh_pair_batch_dev", "fclb_translational_ccd_scene_batch_host", "fclb_translational_ccd_scene_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
     "fclb_measure_fp_peak", "fclb_measure_l2_bandwidth", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -398,11 +398,13 @@ def bvh_build_host(verts: np.ndarray, tris: np.ndarray, scalar_type):
     return obb[:n.value], fc[:n.value], tv
 
 
-def bvh_refit_host(h: int, tri_verts: np.ndarray) -> None:
-    """refit on the device from the new triangle corners (n_tris x 9, the tree's scalar type)"""
+def bvh_refit_host(h: int, tri_verts: np.ndarray, bottomup: bool = False) -> None:
+    """refit on the device from the new triangle corners (n_tris x 9, the tree's scalar type); bottomup = the reference's
+    default endReplaceModel(): leaf boxes from their triangles, inner boxes merged from their children"""
     t = np.ascontiguousarray(tri_verts)
-    load().fclb_bvh_refit_host.argtypes = [C.c_uint64, C.c_void_p, C.c_int]
-    check(load().fclb_bvh_refit_host(h, _ptr(t), len(t)))
+    fn = load().fclb_bvh_refit_bottomup_host if bottomup else load().fclb_bvh_refit_host
+    fn.argtypes = [C.c_uint64, C.c_void_p, C.c_int]
+    check(fn(h, _ptr(t), len(t)))
 
 
 def bvh_export(h: int):

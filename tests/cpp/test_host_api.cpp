@@ -407,6 +407,25 @@ void runBatch() {
       EXPECT_TRUE(std::fabs(ct.toc.lower_bound - S(0.47)) < S(1e-3));  // bar bottom at 0.97 reaches the column tops at 0.5
     }
   }
+  // replace protocol: the floor drops by 0.5 m (default arguments: refit bottom-up); a ball that touched it no longer does
+  {
+    BVHModel<OBBRSS<S>> sheet;
+    sheet.beginModel();
+    sheet.addSubModel({Vector3<S>(-1, -1, 0), Vector3<S>(1, -1, 0), Vector3<S>(1, 1, 0), Vector3<S>(-1, 1, 0)}, {{0, 1, 2}, {0, 2, 3}});
+    sheet.endModel();
+    CollisionRequest<S> one(1);
+    CollisionResult<S> before, after, after_td;
+    EXPECT_TRUE(collide<S>(&sheet, I, &ball, at(S(0.5), S(-0.5), S(0.2)), one, before) == 1);
+    EXPECT_TRUE(sheet.beginReplaceModel() == 0);
+    sheet.replaceSubModel({Vector3<S>(-1, -1, S(-0.5)), Vector3<S>(1, -1, S(-0.5)), Vector3<S>(1, 1, S(-0.5)), Vector3<S>(-1, 1, S(-0.5))});
+    EXPECT_TRUE(sheet.endReplaceModel() == 0);
+    EXPECT_TRUE(collide<S>(&sheet, I, &ball, at(S(0.5), S(-0.5), S(0.2)), one, after) == 0);
+    EXPECT_TRUE(collide<S>(&sheet, I, &ball, at(S(0.5), S(-0.5), S(-0.3)), one, after) == 1);
+    sheet.beginUpdateModel();
+    sheet.updateSubModel({Vector3<S>(-1, -1, 0), Vector3<S>(1, -1, 0), Vector3<S>(1, 1, 0), Vector3<S>(-1, 1, 0)});
+    EXPECT_TRUE(sheet.endUpdateModel(true, false) == 0);  // top-down refit
+    EXPECT_TRUE(collide<S>(&sheet, I, &ball, at(S(0.5), S(-0.5), S(0.2)), one, after_td) == 1);
+  }
   // UserContactProcessFunctor on the host: keep only contacts on triangle 1, stop after two
   std::vector<CollisionQuery<S>> one_q{{&floor, I, &ball, at(0, 0, S(0.1))}};
   std::vector<CollisionResult<S>> fr;

@@ -62,3 +62,40 @@ def test_refit_large_mesh_timing(fclb):
     assert np.isfinite(obb).all() and np.array_equal(tri, tri_verts)
     print(f"[refit] {len(t)} triangles / {len(obb)} nodes refitted on the device in {ms:.2f} ms (kernel)")
     fclb.bvh_release(h)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_refit_bottomup_matches_reference(fclb, ref_oracle, dtype):
+    """endReplaceModel(refit = true, bottomup = true) -- the reference's default arguments (refitTreeBottomUp,
+    BVH_model-inl.h:580-617): leaf boxes from the 3-point fit, inner boxes merged from their children
+    (OBB::operator+, math/bv/OBB-inl.h:116-293).  Node-for-node identical OBBs, and the reference's answers on the tree."""
+    st = fclb.F32 if dtype == np.float32 else fclb.F64
+    for name, (v, t) in (("sphere", scenes.noisy_uv_sphere(n_lat=21, n_lon=40)), ("torus", scenes.noisy_torus())):
+        mid = ref_oracle.bvh_create(v, t)
+        h = fclb.bvh_build(v, t, st)
+        for step, amount in enumerate((0.05, 0.2)):
+            v2 = deform(v, 200 + step, amount)
+            ref_oracle.bvh_refit(mid, v2, bottomup=True)
+            e_obb, e_child, e_tri = ref_oracle.bvh_export(mid, dtype)
+            tri_verts = np.ascontiguousarray(v2.astype(dtype)[t].reshape(len(t), 9))
+            fclb.bvh_refit_host(h, tri_verts, bottomup=True)
+            obb, child, tri = fclb.bvh_export(h)
+            assert np.array_equal(child, e_child)
+            same = (obb == e_obb).all(axis=1)
+            leaves = child < 0
+            print(f"[bottom-up refit {name} {np.dtype(dtype).name} step {step}] nodes {len(obb)}, bit-identical OBBs "
+                  f"{int(same.sum())} (leaves {int(same[leaves].sum())} of {int(leaves.sum())}), max diff "
+                  f"{np.abs(obb - e_obb).max():.3g}")
+            assert same.all(), (np.nonzero(~same)[0][:10], np.abs(obb - e_obb).max())
+        n = 3000
+        rng = np.random.Generator(np.random.PCG64(19))
+        shapes = [(scenes.BOX, 0, (0.3, 0.2, 0.25)), (scenes.SPHERE, 0, (0.2,))]
+        table = fclb.shapes_upload(shapes)
+        pm, ps = scenes.random_poses(rng, n, 0.3, dtype), scenes.random_poses(rng, n, 1.0, dtype)
+        ids = (np.arange(n) % 2).astype(np.uint32)
+        req = fclb.make_request(max_contacts=2**31 - 1)
+        c, _ = fclb.bvh_shape_collide_batch_host(h, table, ids, pm, ps, st, req)
+        e, _ = ref_oracle.mesh_shape_collide_batch(mid, shapes, ids, pm, ps, threads=8, max_contacts=2**31 - 1)
+        assert np.array_equal(c, e) and e.any()
+        fclb.release(table)
+        fclb.bvh_release(h)
