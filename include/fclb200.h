@@ -299,6 +299,11 @@ int fclb_bvh_upload(const void* obb, const int32_t* first_child, int n_nodes, co
  * verts: n_verts x 3 doubles (rounded once to S); tris: n_tris x 3 vertex indices. */
 int fclb_bvh_build(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type,
                    fclb_handle* bvh);
+/* The same builder run ON THE DEVICE, level by level (fit sums in primitive order, the reference's in-place swap pass
+ * replayed per node, node ids from the depth-first order): obb / first_child / triangle order identical to fclb_bvh_build
+ * and to the reference's BVHModel (tests/test_bvh_build_gpu.py).  verts / tris are host arrays. */
+int fclb_bvh_build_device(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type,
+                          fclb_handle* bvh);
 /* same builder, host only (no GPU needed): obb / first_child / tri_verts must hold
  * 15*(2*n_tris-1) S / (2*n_tris-1) / 9*n_tris S entries; *n_nodes = nodes written. */
 int fclb_bvh_build_host(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type, void* obb,

@@ -831,6 +831,244 @@ static void deriveRanges(const int32_t* first_child, int n_nodes, int n_tris, st
   }
 }
 
+// ---- BVHModel<OBBRSS>::buildTree on the device (BVH_model-inl.h:402-570, detail/BV_fitter-inl.h:324-345,
+// detail/BV_splitter-inl.h:361-372), level by level ------------------------------------------------------------
+// The reference builds depth-first with an explicit stack: fit the node's box to its primitives, split them at the mean
+// of their centroids along the box's first axis by an in-place swap pass over primitive_indices_, allocate the two
+// children at the end of the node array and continue with the left one.  Everything observable is reproduced: the
+// fit sums run in primitive order (one lane per sum, as in the refit), the swap pass is replayed element by element on
+// the node's slice (the flags of 32 elements are evaluated in parallel, the swaps applied in order), and the node ids
+// follow from the depth-first order: the children of the k-th inner node in preorder are 2k+1 and 2k+2, and a node's
+// preorder rank among inner nodes is its parent's + 1 (left child) or + the left sibling's primitive count (right child).
+struct BuildNode {
+  int id, first, count, rank;
+};
+
+template <typename S>
+__global__ void __launch_bounds__(256) bvhBuildFitKernel(const BuildNode* __restrict__ level, int n_level, S* __restrict__ nodes,
+                                                         const S* __restrict__ tris, const int* __restrict__ prim,
+                                                         int2* __restrict__ range) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int w = warp; w < n_level; w += n_warps) {
+    const BuildNode nd = level[w];
+    const int2 r = make_int2(nd.first, nd.count);
+    const int a = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 0 : lane == 7 ? 0 : 1);
+    const int b = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : lane == 7 ? 2 : 2);
+    S acc = S(0);
+    if (lane < 9) {
+      for (int i = 0; i < r.y; i++) {
+        const S* t = tris + size_t(12) * size_t(prim[r.x + i]);
+        const S p1a = t[a], p2a = t[4 + a], p3a = t[8 + a];
+        if (lane < 3) {
+          acc += (p1a + p2a) + p3a;
+        } else {
+          const S p1b = t[b], p2b = t[4 + b], p3b = t[8 + b];
+          acc += (p1a * p1b + p2a * p2b + p3a * p3b);
+        }
+      }
+    }
+    S sums[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) sums[k] = __shfl_sync(0xffffffffu, acc, k);
+    const int n_points = 3 * r.y;
+    S M[3][3];
+    M[0][0] = sums[3] - sums[0] * sums[0] / n_points;
+    M[1][1] = sums[4] - sums[1] * sums[1] / n_points;
+    M[2][2] = sums[5] - sums[2] * sums[2] / n_points;
+    M[0][1] = sums[6] - sums[0] * sums[1] / n_points;
+    M[1][2] = sums[8] - sums[1] * sums[2] / n_points;
+    M[0][2] = sums[7] - sums[0] * sums[2] / n_points;
+    M[1][0] = M[0][1];
+    M[2][0] = M[0][2];
+    M[2][1] = M[1][2];
+    S d[3] = {0, 0, 0}, vec[3][3];
+    if (!hostbuild::jacobi3<S>(M, d, vec)) {
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) vec[i][j] = (i == j) ? S(1) : S(0);
+    }
+    S ax[9];
+    hostbuild::axesFromEigen<S>(vec, d, ax);
+    const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
+    S mn[3] = {big, big, big}, mx[3] = {-big, -big, -big};
+    for (int i = lane; i < 3 * r.y; i += 32) {
+      const S* p = tris + size_t(12) * size_t(prim[r.x + i / 3]) + 4 * (i % 3);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const S proj = (ax[0 + k] * p[0] + ax[3 + k] * p[1]) + ax[6 + k] * p[2];
+        if (proj > mx[k]) mx[k] = proj;
+        if (proj < mn[k]) mn[k] = proj;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const S omx = __shfl_xor_sync(0xffffffffu, mx[k], off), omn = __shfl_xor_sync(0xffffffffu, mn[k], off);
+        if (omx > mx[k]) mx[k] = omx;
+        if (omn < mn[k]) mn[k] = omn;
+      }
+    if (lane == 0) {
+      S* o = nodes + size_t(16) * nd.id;
+      for (int k = 0; k < 9; k++) o[k] = ax[k];
+      S c[3];
+      for (int k = 0; k < 3; k++) c[k] = (mx[k] + mn[k]) / 2;
+      for (int rr = 0; rr < 3; rr++) o[9 + rr] = (ax[3 * rr] * c[0] + ax[3 * rr + 1] * c[1]) + ax[3 * rr + 2] * c[2];
+      for (int k = 0; k < 3; k++) o[12 + k] = (mx[k] - mn[k]) / 2;
+      const int fc = nd.count == 1 ? -(prim[nd.first] + 1) : 1 + 2 * nd.rank;
+      if (sizeof(S) == 4)
+        o[15] = S(__int_as_float(fc));
+      else
+        o[15] = S(__longlong_as_double((long long)fc));
+      range[nd.id] = r;
+    }
+    __syncwarp();
+  }
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256) bvhBuildSplitKernel(const BuildNode* __restrict__ level, int n_level, const S* __restrict__ nodes,
+                                                           const S* __restrict__ tris, int* prim, BuildNode* __restrict__ next,
+                                                           int* __restrict__ next_count) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int w = warp; w < n_level; w += n_warps) {
+    const BuildNode nd = level[w];
+    if (nd.count <= 1) continue;  // (warp-uniform)
+    const S* o = nodes + size_t(16) * nd.id;
+    const S sv[3] = {o[0], o[3], o[6]};  // the box's first axis
+    // mean of the centroids, summed in primitive order (computeRule_mean)
+    S acc = S(0);
+    if (lane < 3)
+      for (int i = 0; i < nd.count; i++) {
+        const S* t = tris + size_t(12) * size_t(prim[nd.first + i]);
+        acc += ((t[lane] + t[4 + lane]) + t[8 + lane]) / 3;
+      }
+    const S c0 = __shfl_sync(0xffffffffu, acc, 0), c1v = __shfl_sync(0xffffffffu, acc, 1), c2 = __shfl_sync(0xffffffffu, acc, 2);
+    const S split_value = (c0 * sv[0] + c1v * sv[1] + c2 * sv[2]) / nd.count;
+    // the swap pass, replayed in order
+    int c1 = 0;
+    for (int base = 0; base < nd.count; base += 32) {
+      const int i = base + lane;
+      bool left = false;
+      if (i < nd.count) {
+        const S* t = tris + size_t(12) * size_t(prim[nd.first + i]);
+        S p[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[k] = ((t[k] + t[4 + k]) + t[8 + k]) / S(3.0);
+        left = !(((sv[0] * p[0] + sv[1] * p[1]) + sv[2] * p[2]) > split_value);
+      }
+      const unsigned lm = __ballot_sync(0xffffffffu, left);
+      if (lane == 0) {
+        unsigned m = lm;
+        while (m) {
+          const int bpos = __ffs(m) - 1;
+          m &= m - 1;
+          const int ii = nd.first + base + bpos, cc = nd.first + c1;
+          const int tmp = prim[ii];
+          prim[ii] = prim[cc];
+          prim[cc] = tmp;
+          c1++;
+        }
+      }
+      c1 = __shfl_sync(0xffffffffu, c1, 0);
+      __syncwarp();
+    }
+    if (c1 == 0 || c1 == nd.count) c1 = nd.count / 2;
+    if (lane == 0) {
+      const int slot = atomicAdd(next_count, 2);
+      next[slot] = BuildNode{1 + 2 * nd.rank, nd.first, c1, nd.rank + 1};
+      next[slot + 1] = BuildNode{2 + 2 * nd.rank, nd.first + c1, nd.count - c1, nd.rank + c1};
+    }
+    __syncwarp();
+  }
+}
+
+template <typename S>
+static int buildObbTreeOnDevice(Engine& e, const double* verts_d, int n_verts, const int32_t* tris, int n_tris,
+                                hostbuild::TreeOut<S>& out, float* build_ms) {
+  (void)n_verts;
+  const size_t n_nodes = size_t(2) * n_tris - 1;
+  out.tri.resize(size_t(9) * n_tris);
+  std::vector<S> tris12(size_t(12) * n_tris, S(0));
+  for (int t = 0; t < n_tris; t++)
+    for (int v = 0; v < 3; v++)
+      for (int k = 0; k < 3; k++) {
+        const S x = S(verts_d[size_t(3) * tris[size_t(3) * t + v] + k]);
+        out.tri[size_t(9) * t + 3 * v + k] = x;
+        tris12[size_t(12) * t + 4 * v + k] = x;
+      }
+  std::vector<int> ident(static_cast<size_t>(n_tris));
+  for (int i = 0; i < n_tris; i++) ident[static_cast<size_t>(i)] = i;
+  struct Scratch {
+    std::vector<void*> p;
+    ~Scratch() {
+      for (void* q : p) cudaFree(q);
+    }
+  } sc;
+  auto alloc = [&](void** ptr, size_t bytes) {
+    const cudaError_t err = cudaMalloc(ptr, bytes);
+    if (err == cudaSuccess) sc.p.push_back(*ptr);
+    return err;
+  };
+  S *d_tris = nullptr, *d_nodes = nullptr;
+  int *d_prim = nullptr, *d_next_count = nullptr;
+  int2* d_range = nullptr;
+  BuildNode *d_a = nullptr, *d_b = nullptr;
+  FCLB_CUDA(alloc(reinterpret_cast<void**>(&d_tris), tris12.size() * sizeof(S)));
+  FCLB_CUDA(alloc(reinterpret_cast<void**>(&d_nodes), n_nodes * 16 * sizeof(S)));
+  FCLB_CUDA(alloc(reinterpret_cast<void**>(&d_prim), size_t(n_tris) * sizeof(int)));
+  FCLB_CUDA(alloc(reinterpret_cast<void**>(&d_range), n_nodes * sizeof(int2)));
+  FCLB_CUDA(alloc(reinterpret_cast<void**>(&d_a), size_t(n_tris) * sizeof(BuildNode)));
+  FCLB_CUDA(alloc(reinterpret_cast<void**>(&d_b), size_t(n_tris) * sizeof(BuildNode)));
+  FCLB_CUDA(alloc(reinterpret_cast<void**>(&d_next_count), sizeof(int)));
+  FCLB_CUDA(cudaMemcpyAsync(d_tris, tris12.data(), tris12.size() * sizeof(S), cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaMemcpyAsync(d_prim, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice, e.compute));
+  const BuildNode root{0, 0, n_tris, 0};
+  FCLB_CUDA(cudaMemcpyAsync(d_a, &root, sizeof(root), cudaMemcpyHostToDevice, e.compute));
+  FCLB_CUDA(cudaEventRecord(e.ev0, e.compute));
+  int n_level = 1, levels = 0;
+  size_t done = 0;
+  while (n_level > 0) {
+    if (++levels > 8192) return fail(FCLB_ERR_CAPACITY, "fclb_bvh_build_device: tree deeper than 8192 levels");
+    const int grid = int(std::min<size_t>((size_t(n_level) + 7) / 8, size_t(e.sms) * 16));
+    bvhBuildFitKernel<S><<<grid, 256, 0, e.compute>>>(d_a, n_level, d_nodes, d_tris, d_prim, d_range);
+    FCLB_CUDA(cudaMemsetAsync(d_next_count, 0, sizeof(int), e.compute));
+    bvhBuildSplitKernel<S><<<grid, 256, 0, e.compute>>>(d_a, n_level, d_nodes, d_tris, d_prim, d_b, d_next_count);
+    FCLB_CUDA(cudaGetLastError());
+    e.launches += 2;
+    done += size_t(n_level);
+    int next = 0;
+    FCLB_CUDA(cudaMemcpyAsync(&next, d_next_count, sizeof(int), cudaMemcpyDeviceToHost, e.compute));
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+    n_level = next;
+    std::swap(d_a, d_b);
+  }
+  FCLB_CUDA(cudaEventRecord(e.ev1, e.compute));
+  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  if (done != n_nodes) return fail(FCLB_ERR_CUDA, "fclb_bvh_build_device: the build visited " + std::to_string(done) + " nodes, expected " + std::to_string(n_nodes));
+  if (build_ms) cudaEventElapsedTime(build_ms, e.ev0, e.ev1);
+  std::vector<S> nodes(n_nodes * 16);
+  FCLB_CUDA(cudaMemcpy(nodes.data(), d_nodes, nodes.size() * sizeof(S), cudaMemcpyDeviceToHost));
+  out.obb.resize(n_nodes * 15);
+  out.first_child.resize(n_nodes);
+  for (size_t i = 0; i < n_nodes; i++) {
+    for (int k = 0; k < 15; k++) out.obb[15 * i + k] = nodes[16 * i + k];
+    if (sizeof(S) == 4) {
+      int32_t v;
+      memcpy(&v, &nodes[16 * i + 15], 4);
+      out.first_child[i] = v;
+    } else {
+      long long v;
+      memcpy(&v, &nodes[16 * i + 15], 8);
+      out.first_child[i] = int32_t(v);
+    }
+  }
+  return FCLB_OK;
+}
+
 // parent links and the leaf of every triangle, for the bottom-up refit
 static int ensureParents(BvhDev* d) {
   if (d->d_parent) return FCLB_OK;
@@ -990,6 +1228,43 @@ int fclb_bvh_build(const double* verts, int n_verts, const int32_t* tris, int n_
   return forEachDevice([&] {
     return bvh_upload_one(t.obb.data(), t.first_child.data(), int(t.first_child.size()), t.tri.data(), n_tris, scalar_type, h);
   });
+}
+
+// the same tree, built on the device (level by level, see bvhBuildFitKernel / bvhBuildSplitKernel)
+int fclb_bvh_build_device(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type, fclb_handle* h) {
+  const int rc_init_ = ensureInit();
+  if (rc_init_) return rc_init_;
+  if (!verts || !tris || !h || n_verts <= 0 || n_tris <= 0) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build_device: null or empty input");
+  if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  for (size_t i = 0; i < size_t(3) * n_tris; i++)
+    if (tris[i] < 0 || tris[i] >= n_verts) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build_device: vertex index out of range");
+  float ms = 0.f;
+  int rc;
+  if (scalar_type == FCLB_F32) {
+    hostbuild::TreeOut<float> t;
+    {
+      Engine& e = eng();
+      std::lock_guard<std::recursive_mutex> lk(e.mu);
+      rc = buildObbTreeOnDevice<float>(e, verts, n_verts, tris, n_tris, t, &ms);
+    }
+    if (rc) return rc;
+    rc = forEachDevice([&] {
+      return bvh_upload_one(t.obb.data(), t.first_child.data(), int(t.first_child.size()), t.tri.data(), n_tris, scalar_type, h);
+    });
+  } else {
+    hostbuild::TreeOut<double> t;
+    {
+      Engine& e = eng();
+      std::lock_guard<std::recursive_mutex> lk(e.mu);
+      rc = buildObbTreeOnDevice<double>(e, verts, n_verts, tris, n_tris, t, &ms);
+    }
+    if (rc) return rc;
+    rc = forEachDevice([&] {
+      return bvh_upload_one(t.obb.data(), t.first_child.data(), int(t.first_child.size()), t.tri.data(), n_tris, scalar_type, h);
+    });
+  }
+  if (!rc) eng().last_ms = eng().last_call_ms = ms;  // the build launches alone (upload excluded)
+  return rc;
 }
 
 int fclb_bvh_build_host(const double* verts, int n_verts, const int32_t* tris, int n_tris, int scalar_type, void* obb,

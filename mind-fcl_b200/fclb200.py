@@ -48,7 +48,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
-    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_bvh_refit_bottomup_host", "fclb_bvh_refit_bottomup_dev", "fclb_octree_build_dev", "fclb_octree_build_points_host", "fclb_octree_info", "fclb_octree_export", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_translational_ccd_mesh_batch_host", "fclb_translational_ccd_mesh_batch_dev", "fclb_translational_ccd_mesh_pair_batch_host", "fclb_translational_ccd_mesh_pair_batch_dev", "fclb_translational_ccd_scene_batch_host", "fclb_translational_ccd_scene_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
+    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_bvh_refit_bottomup_host", "fclb_bvh_refit_bottomup_dev", "fclb_bvh_build_device", "fclb_octree_build_dev", "fclb_octree_build_points_host", "fclb_octree_info", "fclb_octree_export", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_translational_ccd_mesh_batch_host", "fclb_translational_ccd_mesh_batch_dev", "fclb_translational_ccd_mesh_pair_batch_host", "fclb_translational_ccd_mesh_pair_batch_dev", "fclb_translational_ccd_scene_batch_host", "fclb_translational_ccd_scene_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
     "fclb_measure_fp_peak", "fclb_measure_l2_bandwidth", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -380,6 +380,17 @@ def bvh_build(verts: np.ndarray, tris: np.ndarray, scalar_type) -> int:
     t = np.ascontiguousarray(tris, np.int32)
     h = C.c_uint64()
     check(load().fclb_bvh_build(_ptr(v), len(v), _ptr(t), len(t), scalar_type, C.byref(h)))
+    return h.value
+
+
+def bvh_build_device(verts: np.ndarray, tris: np.ndarray, scalar_type) -> int:
+    """the same tree built on the device, level by level (fclb_bvh_build_device); last_kernel_ms() = the build launches"""
+    v = np.ascontiguousarray(verts, np.float64)
+    t = np.ascontiguousarray(tris, np.int32)
+    h = C.c_uint64()
+    fn = load().fclb_bvh_build_device
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    check(fn(_ptr(v), len(v), _ptr(t), len(t), scalar_type, C.byref(h)))
     return h.value
 
 
