@@ -495,13 +495,19 @@ struct CollisionRequest {
   void disablePenetration() { penetration_mode_ = FCLB_PEN_DISABLED; }
   void useDefaultPenetration() { penetration_mode_ = FCLB_PEN_DEFAULT_GJK_EPA; }
   // collision_request.h:76-80 -> detail/collision_penetration_mode.h:16-76
+  // both normalise the direction in S, a zero vector becomes UnitZ (collision_request-inl.h:82-106)
   void useDirectedPenetration(const Vector3<S>& shape2_escape_direction) {
     penetration_mode_ = FCLB_PEN_DIRECTED;
-    direction_ = shape2_escape_direction;
+    direction_ = unitOrZ(shape2_escape_direction);
   }
   void useIncrementalMinimumDistancePenetration(const Vector3<S>& shape2_escape_direction_init) {
     penetration_mode_ = FCLB_PEN_INCREMENTAL_MIN;
-    direction_ = shape2_escape_direction_init;
+    direction_ = unitOrZ(shape2_escape_direction_init);
+  }
+  static Vector3<S> unitOrZ(const Vector3<S>& d) {
+    const S n = std::sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+    if (n <= S(0.0)) return Vector3<S>(S(0), S(0), S(1));
+    return Vector3<S>(d[0] / n, d[1] / n, d[2] / n);
   }
   bool isPenetrationEnabled() const { return penetration_mode_ != FCLB_PEN_DISABLED; }
   std::size_t maxNumContacts() const { return num_max_contacts_; }
@@ -811,10 +817,6 @@ void collideBatch(const std::vector<CollisionQuery<S>>& queries, const Collision
         queries[g.q[i]].tf1.toPose12(&pa[12 * i]);
         queries[g.q[i]].tf2.toPose12(&pb[12 * i]);
       }
-      if (mpr_pen) {
-        std::cerr << "Warning: MPR penetration modes between two meshes are not supported by the device path" << std::endl;
-        continue;
-      }
       std::vector<int32_t> ids;
       std::vector<S> rec;
       bool ok = true;
@@ -836,7 +838,7 @@ void collideBatch(const std::vector<CollisionQuery<S>>& queries, const Collision
           ct.o2 = g.g2;
           ct.b1 = ids[(i * keep + c) * 2];
           ct.b2 = ids[(i * keep + c) * 2 + 1];
-          if (pen) {
+          if (pen || mpr_pen) {
             const S* r = &rec[(i * keep + c) * 7];
             ct.normal = Vector3<S>(r[0], r[1], r[2]);
             ct.pos = Vector3<S>(r[3], r[4], r[5]);

@@ -78,7 +78,7 @@ typedef struct {
 typedef struct {
   uint32_t max_contacts;     /* num_max_contacts_; 0 => every query returns 0 (collision-inl.h:79-84) */
   uint32_t penetration_mode; /* FCLB_PEN_* */
-  double dir[3];             /* escape direction for the MPR penetration modes */
+  double dir[3];             /* escape direction for the MPR penetration modes: UNIT vector, as useDirectedPenetration stores it */
   double binary_tol;         /* GJK/MPR tolerance; <=0 => 1e-6 (collision_request.h:66) */
   double distance_tol;       /* EPA tolerance;     <=0 => 1e-6 (collision_request.h:67) */
   uint32_t gjk_max_iter;     /* 0 => 128 */

@@ -31,6 +31,7 @@
 
 #include "fclb_bvh_build.h"
 #include "fclb_bvh.cuh"
+#include "fclb_mpr_pen.cuh"
 
 namespace fclb {
 
@@ -515,6 +516,42 @@ __global__ void __launch_bounds__(256) bvhRefitKernel(S* __restrict__ nodes, con
 #pragma unroll
       for (int k = 0; k < 3; k++) o[12 + k] = (mx[k] - mn[k]) / 2;
     }
+  }
+}
+
+// collisionPenetrationMPR for mesh pairs (collision_penetration-inl.h:189-252): every contact of the boolean collide is a
+// triangle pair (b1, b2); computePenetrationMPR on (triangle b1 at tf1, triangle b2 at tf2) fills normal / pos / depth
+template <typename S>
+__global__ void __launch_bounds__(kBlock) bvhPairPenetrationKernel(const S* __restrict__ tris1, const S* __restrict__ tris2,
+                                                                   const S* __restrict__ poses1, const S* __restrict__ poses2, size_t n,
+                                                                   uint32_t max_keep, const uint32_t* __restrict__ counts,
+                                                                   const int32_t* __restrict__ ids, int incremental, double dx,
+                                                                   double dy, double dz, double tol, S* __restrict__ out) {
+  const size_t total = n * size_t(max_keep);
+  const V3<S> dir_world = mk<S>(S(dx), S(dy), S(dz));
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t q = i / max_keep;
+    const uint32_t k = uint32_t(i % max_keep);
+    S* o = out + i * 7;
+    if (k >= counts[q]) {
+#pragma unroll
+      for (int j = 0; j < 7; j++) o[j] = S(0);
+      continue;
+    }
+    const Pose<S> tf1 = loadPose(poses1, q), tf2 = loadPose(poses2, q);
+    MinkDiff<S, ST_TRIANGLE, ST_TRIANGLE> md;
+    md.s0.type = md.s1.type = ST_TRIANGLE;
+    md.s0.cvx = md.s1.cvx = nullptr;
+    md.s0.p0 = md.s0.p1 = md.s0.p2 = md.s1.p0 = md.s1.p1 = md.s1.p2 = S(0);
+    loadTri(tris1, ids[2 * i], md.s0.tri);
+    loadTri(tris2, ids[2 * i + 1], md.s1.tri);
+    md.setPoses(tf1, tf2);
+    V3<S> pos, normal;
+    S depth;
+    computePenetrationMpr<S>(md, tf1, dir_world, incremental != 0, 128, S(tol), pos, normal, depth);
+    o[0] = normal.x; o[1] = normal.y; o[2] = normal.z;
+    o[3] = pos.x; o[4] = pos.y; o[5] = pos.z;
+    o[6] = depth;
   }
 }
 
@@ -1475,11 +1512,35 @@ int fclb_bvh_collide_contacts_batch_dev(fclb_handle bvh1, fclb_handle bvh2, cons
   if (i1->second->scalar_type != scalar_type || i2->second->scalar_type != scalar_type)
     return fail(FCLB_ERR_BAD_ARG, "BVH was uploaded for a different scalar type");
   if (!req || !out_counts || !out_ids || !out_contacts || max_keep == 0) return fail(FCLB_ERR_BAD_ARG, "null output / max_keep == 0");
-  if (req->penetration_mode != FCLB_PEN_DEFAULT_GJK_EPA && req->penetration_mode != FCLB_PEN_DISABLED)
-    return fail(FCLB_ERR_UNSUPPORTED, "fclb_bvh_collide_contacts_batch serves boolean requests (ids only) and "
-                                      "request.useDefaultPenetration(); the MPR penetration modes are not built for mesh pairs");
+  if (req->penetration_mode > FCLB_PEN_INCREMENTAL_MIN) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_collide_contacts_batch: bad penetration_mode");
   if (n == 0) return FCLB_OK;
   if (!poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null pose array");
+  if (req->penetration_mode == FCLB_PEN_DIRECTED || req->penetration_mode == FCLB_PEN_INCREMENTAL_MIN) {
+    // boolean collide first (ids of the colliding triangle pairs), then one MPR penetration per kept pair
+    rc = scalar_type == FCLB_F32 ? bvhCollideDev<float>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts,
+                                                        nullptr, false, max_keep, out_ids, out_contacts)
+                                 : bvhCollideDev<double>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts,
+                                                         nullptr, false, max_keep, out_ids, out_contacts);
+    if (rc) return rc;
+    const size_t total = n * size_t(max_keep);
+    const int grid = int(std::min<size_t>((total + kBlock - 1) / kBlock, size_t(e.sms) * 16));
+    const int inc = req->penetration_mode == FCLB_PEN_INCREMENTAL_MIN ? 1 : 0;
+    const double tol = req->distance_tol > 0 ? req->distance_tol : 1e-6;  // MPR(128, request.distanceTolerance())
+    if (scalar_type == FCLB_F32)
+      bvhPairPenetrationKernel<float><<<grid, kBlock, 0, e.compute>>>(
+          static_cast<const float*>(i1->second->tris), static_cast<const float*>(i2->second->tris), static_cast<const float*>(poses1),
+          static_cast<const float*>(poses2), n, max_keep, out_counts, out_ids, inc, req->dir[0], req->dir[1], req->dir[2], tol,
+          static_cast<float*>(out_contacts));
+    else
+      bvhPairPenetrationKernel<double><<<grid, kBlock, 0, e.compute>>>(
+          static_cast<const double*>(i1->second->tris), static_cast<const double*>(i2->second->tris),
+          static_cast<const double*>(poses1), static_cast<const double*>(poses2), n, max_keep, out_counts, out_ids, inc, req->dir[0],
+          req->dir[1], req->dir[2], tol, static_cast<double*>(out_contacts));
+    FCLB_CUDA(cudaGetLastError());
+    e.launches += 1;
+    FCLB_CUDA(cudaStreamSynchronize(e.compute));
+    return FCLB_OK;
+  }
   const bool pen = req->penetration_mode == FCLB_PEN_DEFAULT_GJK_EPA;
   if (scalar_type == FCLB_F32)
     return bvhCollideDev<float>(e, i1->second, i2->second, poses1, poses2, n, req->max_contacts, out_counts, nullptr, pen,

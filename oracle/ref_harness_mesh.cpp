@@ -144,7 +144,14 @@ void collideContactsBatch(int id1, int id2, const S* poses1, const S* poses2, si
   const Model<S>* m2 = get<S>(id2);
   parallelFor(n, threads, [&](size_t b, size_t e) {
     fcl::CollisionRequest<S> req(rq->max_contacts);
-    req.useDefaultPenetration();
+    const fcl::Vector3<S> dir(S(rq->dir[0]), S(rq->dir[1]), S(rq->dir[2]));
+    if (rq->penetration_mode == 2)  // collisionPenetrationMPR (collision_penetration-inl.h:189-252)
+      req.useDirectedPenetration(dir);
+    else if (rq->penetration_mode == 3)
+      req.useIncrementalMinimumDistancePenetration(dir);
+    else
+      req.useDefaultPenetration();
+    if (rq->distance_tol > 0) req.setPenetrationDistanceTolerance(S(rq->distance_tol));
     for (size_t q = b; q < e; q++) {
       fcl::CollisionResult<S> res;
       const size_t c = fcl::collide<S>(m1, loadPose<S>(poses1 + 12 * q), m2, loadPose<S>(poses2 + 12 * q), req, res);

@@ -130,3 +130,37 @@ def test_mesh_mesh_contact_generation(fclb, ref_oracle, dtype):
     assert np.array_equal(c3, np.minimum(e_counts, 3))
     for h in handles:
         fclb.bvh_release(h)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", [2, 3])
+def test_mesh_mesh_mpr_penetration(fclb, ref_oracle, dtype, mode):
+    """request.useDirectedPenetration(dir) / useIncrementalMinimumDistancePenetration(dir) on mesh pairs:
+    collisionPenetrationMPR (collision_penetration-inl.h:189-252) = boolean collide, then computePenetrationMPR on the
+    (triangle b1, triangle b2) of every contact.  Counts identical; contacts compared per triangle pair, bit-exact."""
+    ids, handles, st = make_meshes(fclb, ref_oracle, dtype, small=True)
+    n = 1200
+    poses1, _ = scenes.config_c3_poses(n, dtype, extent=1.0, seed=18)
+    rng = np.random.Generator(np.random.PCG64(14))
+    poses2 = scenes.random_poses(rng, n, 0.2, dtype)
+    keep = 4096
+    d = (0.0, -0.6, 0.8)  # unit, as CollisionRequest::useDirectedPenetration stores it (it normalises in S)
+    req = fclb.make_request(max_contacts=2**31 - 1, penetration_mode=mode, direction=d)
+    counts, cid, contacts = fclb.bvh_collide_contacts_batch_host(handles[0], handles[1], poses1, poses2, st, req, keep)
+    e_counts, e_id, e_contacts = ref_oracle.bvh_collide_contacts_batch(ids[0], ids[1], poses1, poses2, keep, threads=8,
+                                                                       max_contacts=2**31 - 1, penetration_mode=mode, direction=d)
+    assert int(e_counts.max()) <= keep
+    assert np.array_equal(counts, e_counts)
+    n_cmp = n_same = 0
+    for q in np.nonzero(counts)[0]:
+        ref = {(int(e_id[q, j, 0]), int(e_id[q, j, 1])): e_contacts[q, j] for j in range(int(e_counts[q]))}
+        for j in range(int(counts[q])):
+            key = (int(cid[q, j, 0]), int(cid[q, j, 1]))
+            assert key in ref, (q, key)
+            n_cmp += 1
+            n_same += int(np.array_equal(contacts[q, j], ref[key]))
+    print(f"[mesh-mesh MPR penetration mode {mode} {np.dtype(dtype).name}] colliding={int((e_counts > 0).sum())} contacts compared "
+          f"{n_cmp}, bit-identical {n_same}")
+    assert n_cmp > 1000 and n_same == n_cmp
+    for h in handles:
+        fclb.bvh_release(h)
