@@ -798,7 +798,9 @@ struct EpaWarp {
     if (lane == 0) P.f_vis[start_face] = 1;  // the start face is visible by construction (:133)
     sync();
     // grow the visible patch: a face joins when it is "outside" and shares an
-    // edge with a patch face (computeVisiblePatch, :121-180)
+    // edge with a patch face (computeVisiblePatch, :121-180).  Lanes read f_vis while others relabel 3 -> 1 inside a round
+    // (compute-sanitizer racecheck reports it as a warning): labels only ever move 3 -> 1, a stale read postpones a face
+    // to the next round, and rounds repeat until nothing changes -- the fixed point, hence the result, is the same.
     bool broken = false;
     while (true) {
       bool changed = false;
