@@ -440,30 +440,78 @@ static int bvhCollideDev(Engine& e, const BvhDev* m1, const BvhDev* m2, const vo
 // (math/geometry-inl.h:713-780) and their rounding depends on that order, so lane k < 9 accumulates sum k over the
 // node's primitives in primitive_indices_ order; the 3x3 Jacobi solve runs on every lane; the extents are minima /
 // maxima (order-free) and are reduced across the lanes.  Results are bit-identical to the reference's refit.
+// The nine covariance sums of a node (S1[x, y, z], c00, c11, c22, c01, c02, c12: lane k < 9 owns sum k) accumulated in
+// primitive order.  The triangles of 32 primitives are fetched by the whole warp into a shared-memory stage (one gather per
+// lane instead of one dependent load pair per element of the sequential loop), then every owning lane adds its 32 terms in
+// order: same terms, same order, same rounding as the reference's sequential loop.
+template <typename S>
+FCLB_DI S orderedCovarianceSum(const S* __restrict__ tris, const int* __restrict__ prim, int first, int count, int lane, S* stage) {
+  const int a = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 0 : lane == 7 ? 0 : 1);
+  const int b = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : lane == 7 ? 2 : 2);
+  S acc = S(0);
+  for (int base = 0; base < count; base += 32) {
+    const int i = base + lane;
+    if (i < count) {
+      const S* t = tris + size_t(12) * size_t(prim[first + i]);
+#pragma unroll
+      for (int v = 0; v < 3; v++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) stage[lane * 9 + 3 * v + k] = t[4 * v + k];
+    }
+    __syncwarp();
+    const int m = count - base < 32 ? count - base : 32;
+    if (lane < 3) {
+      for (int j = 0; j < m; j++) {
+        const S* p = stage + 9 * j;
+        acc += (p[a] + p[3 + a]) + p[6 + a];
+      }
+    } else if (lane < 9) {
+      for (int j = 0; j < m; j++) {
+        const S* p = stage + 9 * j;
+        acc += (p[a] * p[b] + p[3 + a] * p[3 + b] + p[6 + a] * p[6 + b]);
+      }
+    }
+    __syncwarp();
+  }
+  return acc;
+}
+// lanes 0..2: sum over the primitives, in order, of the centroid component ((p1 + p2) + p3) / 3 (computeRule_mean)
+template <typename S>
+FCLB_DI S orderedCentroidSum(const S* __restrict__ tris, const int* __restrict__ prim, int first, int count, int lane, S* stage) {
+  S acc = S(0);
+  for (int base = 0; base < count; base += 32) {
+    const int i = base + lane;
+    if (i < count) {
+      const S* t = tris + size_t(12) * size_t(prim[first + i]);
+#pragma unroll
+      for (int v = 0; v < 3; v++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) stage[lane * 9 + 3 * v + k] = t[4 * v + k];
+    }
+    __syncwarp();
+    const int m = count - base < 32 ? count - base : 32;
+    if (lane < 3)
+      for (int j = 0; j < m; j++) {
+        const S* p = stage + 9 * j;
+        acc += ((p[lane] + p[3 + lane]) + p[6 + lane]) / 3;
+      }
+    __syncwarp();
+  }
+  return acc;
+}
+
 template <typename S>
 __global__ void __launch_bounds__(256) bvhRefitKernel(S* __restrict__ nodes, const S* __restrict__ tris, const int2* __restrict__ range,
                                                       const int* __restrict__ prim, int n_nodes) {
+  __shared__ S s_stage[8][32 * 9];
+  S* stage = s_stage[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int node = warp; node < n_nodes; node += n_warps) {
     const int2 r = range[node];
     // which scalars of a triangle this lane's sum needs: S1[k] (lanes 0-2), c00 c11 c22 c01 c02 c12 (lanes 3-8)
-    const int a = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 0 : lane == 7 ? 0 : 1);
-    const int b = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : lane == 7 ? 2 : 2);
-    S acc = S(0);
-    if (lane < 9) {
-      for (int i = 0; i < r.y; i++) {
-        const S* t = tris + size_t(12) * size_t(prim[r.x + i]);
-        const S p1a = t[a], p2a = t[4 + a], p3a = t[8 + a];
-        if (lane < 3) {
-          acc += (p1a + p2a) + p3a;
-        } else {
-          const S p1b = t[b], p2b = t[4 + b], p3b = t[8 + b];
-          acc += (p1a * p1b + p2a * p2b + p3a * p3b);
-        }
-      }
-    }
+    const S acc = orderedCovarianceSum<S>(tris, prim, r.x, r.y, lane, stage);
     S sums[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) sums[k] = __shfl_sync(0xffffffffu, acc, k);
@@ -885,27 +933,15 @@ template <typename S>
 __global__ void __launch_bounds__(256) bvhBuildFitKernel(const BuildNode* __restrict__ level, int n_level, S* __restrict__ nodes,
                                                          const S* __restrict__ tris, const int* __restrict__ prim,
                                                          int2* __restrict__ range) {
+  __shared__ S s_stage[8][32 * 9];
+  S* stage = s_stage[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int w = warp; w < n_level; w += n_warps) {
     const BuildNode nd = level[w];
     const int2 r = make_int2(nd.first, nd.count);
-    const int a = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 0 : lane == 7 ? 0 : 1);
-    const int b = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : lane == 7 ? 2 : 2);
-    S acc = S(0);
-    if (lane < 9) {
-      for (int i = 0; i < r.y; i++) {
-        const S* t = tris + size_t(12) * size_t(prim[r.x + i]);
-        const S p1a = t[a], p2a = t[4 + a], p3a = t[8 + a];
-        if (lane < 3) {
-          acc += (p1a + p2a) + p3a;
-        } else {
-          const S p1b = t[b], p2b = t[4 + b], p3b = t[8 + b];
-          acc += (p1a * p1b + p2a * p2b + p3a * p3b);
-        }
-      }
-    }
+    const S acc = orderedCovarianceSum<S>(tris, prim, r.x, r.y, lane, stage);
     S sums[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) sums[k] = __shfl_sync(0xffffffffu, acc, k);
@@ -968,6 +1004,8 @@ template <typename S>
 __global__ void __launch_bounds__(256) bvhBuildSplitKernel(const BuildNode* __restrict__ level, int n_level, const S* __restrict__ nodes,
                                                            const S* __restrict__ tris, int* prim, BuildNode* __restrict__ next,
                                                            int* __restrict__ next_count) {
+  __shared__ S s_stage[8][32 * 9];
+  S* stage = s_stage[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -977,12 +1015,7 @@ __global__ void __launch_bounds__(256) bvhBuildSplitKernel(const BuildNode* __re
     const S* o = nodes + size_t(16) * nd.id;
     const S sv[3] = {o[0], o[3], o[6]};  // the box's first axis
     // mean of the centroids, summed in primitive order (computeRule_mean)
-    S acc = S(0);
-    if (lane < 3)
-      for (int i = 0; i < nd.count; i++) {
-        const S* t = tris + size_t(12) * size_t(prim[nd.first + i]);
-        acc += ((t[lane] + t[4 + lane]) + t[8 + lane]) / 3;
-      }
+    const S acc = orderedCentroidSum<S>(tris, prim, nd.first, nd.count, lane, stage);
     const S c0 = __shfl_sync(0xffffffffu, acc, 0), c1v = __shfl_sync(0xffffffffu, acc, 1), c2 = __shfl_sync(0xffffffffu, acc, 2);
     const S split_value = (c0 * sv[0] + c1v * sv[1] + c2 * sv[2]) / nd.count;
     // the swap pass, replayed in order
