@@ -202,6 +202,7 @@ static int runCollideHost(fclb_handle shapes, const fclb_pair* pairs, const void
   FCLB_CUDA(cudaMemcpyAsync(base + o_pairs, pairs, n * sizeof(fclb_pair), cudaMemcpyHostToDevice, e.compute));
   FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
   FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
+  if (h_contacts) FCLB_CUDA(cudaMemsetAsync(base + o_cont, 0, cont_bytes, e.compute));  // slots beyond counts[q] come back as zeros
   CollideOut out{};
   out.contacts = h_contacts ? base + o_cont : nullptr;
   out.counts = reinterpret_cast<uint32_t*>(base + o_cnt);
