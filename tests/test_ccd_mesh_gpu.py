@@ -97,3 +97,48 @@ def test_mesh_pair_ccd(fclb, ref_oracle, dtype):
         assert int((ec > 0).sum()) > 100
     fclb.bvh_release(b1)
     fclb.bvh_release(b2)
+
+
+def test_ccd_edge_cases(fclb, ref_oracle):
+    """empty batches, a displacement of zero length, a sweep that starts in contact, refused inputs"""
+    st, dtype = fclb.F64, np.float64
+    v, t = scenes.noisy_uv_sphere(n_lat=9, n_lon=14, radius=0.5, noise=0.0)
+    bvh = fclb.bvh_build(v, t, st)
+    oid = ref_oracle.bvh_obb_create(v, t)
+    shapes = [(scenes.BOX, 0, (0.3, 0.2, 0.25)), (scenes.SPHERE, 0, (0.2,))]
+    table = fclb.shapes_upload(shapes)
+    ident = np.tile(np.concatenate([np.eye(3).reshape(9), np.zeros(3)]), (4, 1)).astype(dtype)
+    # empty batch
+    c, prim, toc = fclb.translational_ccd_mesh_batch_host(bvh, table, np.zeros(0, np.uint32), ident[:0], ident[:0],
+                                                          np.zeros((0, 4), dtype), st)
+    assert c.size == 0
+    # 0: far away, no motion; 1: inside the mesh's surface shell, no motion; 2: starts in contact, moves away; 3: grazing sweep
+    ps = ident.copy()
+    ps[0, 9:] = (3, 0, 0)
+    ps[1, 9:] = (0.5, 0, 0)
+    ps[2, 9:] = (0.5, 0, 0)
+    ps[3, 9:] = (-2, 0.69, 0)
+    disp = np.array([[1, 0, 0, 0.0], [1, 0, 0, 0.0], [1, 0, 0, 2.0], [1, 0, 0, 4.0]], dtype)
+    ids = np.array([0, 1, 0, 1], np.uint32)
+    for request_type in (0, 1, 2):
+        c, prim, toc = fclb.translational_ccd_mesh_batch_host(bvh, table, ids, ps, ident, disp, st, request_type=request_type,
+                                                              max_contacts=1000, max_keep=64)
+        ec, eprim, etoc = ref_oracle.translational_ccd_mesh_batch(oid, shapes, ids, ps, ident, disp, request_type=request_type,
+                                                                  max_contacts=1000, keep=64)
+        assert np.array_equal(c, ec) and np.array_equal(prim, eprim) and np.array_equal(toc, etoc)
+        assert c[0] == 0 and c[1] > 0 and c[2] > 0
+    # a Convex with six vertices takes the reference's fit6 box: refused, loudly
+    octa_v = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float64) * 0.2
+    octa_f = [(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5)]
+    faces = np.array([x for f in octa_f for x in (3,) + f], np.int32)  # the reference's encoding: count, then the indices
+    slot = fclb.convex_upload(octa_v, faces, len(octa_f))
+    t6 = fclb.shapes_upload([(scenes.CONVEX, slot, ())])
+    with pytest.raises(fclb.FclbError):
+        fclb.translational_ccd_mesh_batch_host(bvh, t6, np.zeros(1, np.uint32), ps[:1], ident[:1], disp[:1], st)
+    # a tree of the other scalar type is refused
+    with pytest.raises(fclb.FclbError):
+        fclb.translational_ccd_mesh_batch_host(bvh, table, ids, ps.astype(np.float32), ident.astype(np.float32),
+                                               disp.astype(np.float32), fclb.F32)
+    fclb.release(table)
+    fclb.release(t6)
+    fclb.bvh_release(bvh)
