@@ -281,6 +281,22 @@ int fclb_translational_ccd_scene_batch_dev(int scene_kind, fclb_handle scene, fc
                                            uint32_t max_keep, uint32_t* out_counts, int64_t* out_code, void* out_toc,
                                            void* out_box);
 
+/* heightmap / octree vs mesh: fcl::translational_ccd(scene, tf_scene, displacement, BVHModel<OBB<S>>, tf_mesh, ...) and the
+ * mesh-first entry (RunHeightMapObbBVH / RunObbBVH_HeightMap, heightmap_ccd_solver-inl.h:168-366; RunOctreeObbBVH /
+ * RunObbBVH_Octree, octree2_ccd_solver-inl.h:225-470): the walk over (box node, mesh node) pairs with the OBB swept-box
+ * test, RunShapeSimplex<Box>(pixel / voxel box swept, triangle) per surviving leaf pair.
+ *   mesh_moves  0: the scene geometry moves (displacement in its frame); 1: the mesh moves (displacement in the mesh frame)
+ *   out_ids[(q * max_keep + k) * 2 ..] = (pixel / node code, triangle id) of the k-th contact in the reference's order;
+ *   out_toc 2 S, out_box 6 S (the scene box, ContinuousCollisionContact::o1_bv) per contact; out_toc / out_box may be NULL */
+int fclb_translational_ccd_scene_mesh_batch_host(int scene_kind, fclb_handle scene, fclb_handle bvh, const void* poses_scene,
+                                                 const void* poses_mesh, const void* displacements, size_t n, int scalar_type,
+                                                 const fclb_ccd_request* req, int mesh_moves, uint32_t max_keep,
+                                                 uint32_t* out_counts, int64_t* out_ids, void* out_toc, void* out_box);
+int fclb_translational_ccd_scene_mesh_batch_dev(int scene_kind, fclb_handle scene, fclb_handle bvh, const void* poses_scene,
+                                                const void* poses_mesh, const void* displacements, size_t n, int scalar_type,
+                                                const fclb_ccd_request* req, int mesh_moves, uint32_t max_keep,
+                                                uint32_t* out_counts, int64_t* out_ids, void* out_toc, void* out_box);
+
 /* ---- meshes: BVHModel<OBBRSS<S>> flattened by the caller ------------------------
  * (reference geometry/bvh/BVH_model.h:63-196, BV_node_base.h:50-82).  Only the
  * OBB half of OBBRSS is ever read by collide (math/bv/OBBRSS-inl.h:130-135).

@@ -1156,8 +1156,8 @@ static int ensureParents(BvhDev* d) {
   FCLB_CUDA(cudaMalloc(&d->d_parent, parent.size() * sizeof(int)));
   FCLB_CUDA(cudaMalloc(&d->d_leaf_node, leaf.size() * sizeof(int)));
   FCLB_CUDA(cudaMalloc(&d->d_arrived, parent.size() * sizeof(int)));
-  FCLB_CUDA(cudaMemcpy(d->d_parent, parent.data(), parent.size() * sizeof(int), cudaMemcpyHostToDevice));
-  FCLB_CUDA(cudaMemcpy(d->d_leaf_node, leaf.data(), leaf.size() * sizeof(int), cudaMemcpyHostToDevice));
+  FCLB_CUDA(uploadSync(d->d_parent, parent.data(), parent.size() * sizeof(int)));
+  FCLB_CUDA(uploadSync(d->d_leaf_node, leaf.data(), leaf.size() * sizeof(int)));
   return FCLB_OK;
 }
 
@@ -1218,8 +1218,8 @@ static int uploadBvh(BvhDev* d, const void* obb, const int32_t* first_child, int
       for (int k = 0; k < 3; k++) tris[size_t(12) * t + 4 * v + k] = tv[size_t(9) * t + 3 * v + k];
   FCLB_CUDA(cudaMalloc(&d->nodes, nodes.size() * sizeof(S)));
   FCLB_CUDA(cudaMalloc(&d->tris, tris.size() * sizeof(S)));
-  FCLB_CUDA(cudaMemcpy(d->nodes, nodes.data(), nodes.size() * sizeof(S), cudaMemcpyHostToDevice));
-  FCLB_CUDA(cudaMemcpy(d->tris, tris.data(), tris.size() * sizeof(S), cudaMemcpyHostToDevice));
+  FCLB_CUDA(uploadSync(d->nodes, nodes.data(), nodes.size() * sizeof(S)));
+  FCLB_CUDA(uploadSync(d->tris, tris.data(), tris.size() * sizeof(S)));
   d->h_obb.assign(reinterpret_cast<const unsigned char*>(o), reinterpret_cast<const unsigned char*>(o + size_t(15) * n_nodes));
   d->h_tri.assign(reinterpret_cast<const unsigned char*>(tv), reinterpret_cast<const unsigned char*>(tv + size_t(9) * n_tris));
   d->h_child.assign(first_child, first_child + n_nodes);
@@ -1229,8 +1229,8 @@ static int uploadBvh(BvhDev* d, const void* obb, const int32_t* first_child, int
   if (int(prim.size()) != n_tris) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_upload: the leaves do not cover every triangle exactly once");
   FCLB_CUDA(cudaMalloc(&d->d_range, range.size() * sizeof(int2)));
   FCLB_CUDA(cudaMalloc(&d->d_prim, prim.size() * sizeof(int)));
-  FCLB_CUDA(cudaMemcpy(d->d_range, range.data(), range.size() * sizeof(int2), cudaMemcpyHostToDevice));
-  FCLB_CUDA(cudaMemcpy(d->d_prim, prim.data(), prim.size() * sizeof(int), cudaMemcpyHostToDevice));
+  FCLB_CUDA(uploadSync(d->d_range, range.data(), range.size() * sizeof(int2)));
+  FCLB_CUDA(uploadSync(d->d_prim, prim.data(), prim.size() * sizeof(int)));
   return FCLB_OK;
 }
 

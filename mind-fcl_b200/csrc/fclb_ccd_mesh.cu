@@ -47,7 +47,7 @@ static int ensureDfsRank(BvhDev* m) {
     }
   }
   FCLB_CUDA(cudaMalloc(&m->d_dfs_rank, rank.size() * sizeof(int)));
-  FCLB_CUDA(cudaMemcpy(m->d_dfs_rank, rank.data(), rank.size() * sizeof(int), cudaMemcpyHostToDevice));
+  FCLB_CUDA(uploadSync(m->d_dfs_rank, rank.data(), rank.size() * sizeof(int)));
   return FCLB_OK;
 }
 

@@ -209,8 +209,8 @@ static int uploadConvexTables(Engine& e) {
     }
     FCLB_CUDA(cudaMalloc(&e.d_convex_tab[0], tf.size() * sizeof(ConvexD<float>)));
     FCLB_CUDA(cudaMalloc(&e.d_convex_tab[1], td.size() * sizeof(ConvexD<double>)));
-    FCLB_CUDA(cudaMemcpy(e.d_convex_tab[0], tf.data(), tf.size() * sizeof(ConvexD<float>), cudaMemcpyHostToDevice));
-    FCLB_CUDA(cudaMemcpy(e.d_convex_tab[1], td.data(), td.size() * sizeof(ConvexD<double>), cudaMemcpyHostToDevice));
+    FCLB_CUDA(uploadSync(e.d_convex_tab[0], tf.data(), tf.size() * sizeof(ConvexD<float>)));
+    FCLB_CUDA(uploadSync(e.d_convex_tab[1], td.data(), td.size() * sizeof(ConvexD<double>)));
   }
   return FCLB_OK;
 }
@@ -257,12 +257,12 @@ static int buildShapeTable(Engine& e, ShapeTable* t, int st) {
     for (int k = 0; k < 3; k++) h[i].p[k] = S(s.p[k]);
   }
   FCLB_CUDA(cudaMalloc(&t->d_shapes[st], std::max<size_t>(1, h.size()) * sizeof(ShapeD<S>)));
-  FCLB_CUDA(cudaMemcpy(t->d_shapes[st], h.data(), h.size() * sizeof(ShapeD<S>), cudaMemcpyHostToDevice));
+  FCLB_CUDA(uploadSync(t->d_shapes[st], h.data(), h.size() * sizeof(ShapeD<S>)));
   // bounding polytopes of the primitives (getBoundVertices in the shape's own frame)
   std::vector<BoundD<S>> bd(t->n);
   for (uint32_t i = 0; i < t->n; i++) boundVertices<S>(t->host[i].type, h[i].p, bd[i]);
   FCLB_CUDA(cudaMalloc(&t->d_bound[st], std::max<size_t>(1, bd.size()) * sizeof(BoundD<S>)));
-  FCLB_CUDA(cudaMemcpy(t->d_bound[st], bd.data(), bd.size() * sizeof(BoundD<S>), cudaMemcpyHostToDevice));
+  FCLB_CUDA(uploadSync(t->d_bound[st], bd.data(), bd.size() * sizeof(BoundD<S>)));
   std::vector<LocalAabbD<S>> la(t->n);
   for (uint32_t i = 0; i < t->n; i++) {
     const bool cvx = t->host[i].type == FCLB_CONVEX;
@@ -270,7 +270,7 @@ static int buildShapeTable(Engine& e, ShapeTable* t, int st) {
     localAabb<S>(t->host[i].type, h[i].p, cvx ? c->h_verts.data() : nullptr, cvx ? c->n_verts : 0, la[i]);
   }
   FCLB_CUDA(cudaMalloc(&t->d_local[st], std::max<size_t>(1, la.size()) * sizeof(LocalAabbD<S>)));
-  FCLB_CUDA(cudaMemcpy(t->d_local[st], la.data(), la.size() * sizeof(LocalAabbD<S>), cudaMemcpyHostToDevice));
+  FCLB_CUDA(uploadSync(t->d_local[st], la.data(), la.size() * sizeof(LocalAabbD<S>)));
   return FCLB_OK;
 }
 
@@ -644,7 +644,7 @@ int fclb_dev_free(void* p) {
 int fclb_memcpy_h2d(void* dst, const void* src, size_t bytes) {
   int rc = ensureInit();
   if (rc) return rc;
-  FCLB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  FCLB_CUDA(uploadSync(dst, src, bytes));
   return FCLB_OK;
 }
 int fclb_memcpy_d2h(void* dst, const void* src, size_t bytes) {
@@ -783,10 +783,10 @@ static int convex_upload_one(const double* verts, int n_verts, const int* faces,
   FCLB_CUDA(cudaMalloc(&c.d_verts[1], vd4.size() * sizeof(double)));
   FCLB_CUDA(cudaMalloc(&c.d_nbr, csr.size() * sizeof(int)));
   FCLB_CUDA(cudaMalloc(&c.d_vinfo, vinfo.size() * sizeof(int)));
-  FCLB_CUDA(cudaMemcpy(c.d_verts[0], vf4.data(), vf4.size() * sizeof(float), cudaMemcpyHostToDevice));
-  FCLB_CUDA(cudaMemcpy(c.d_verts[1], vd4.data(), vd4.size() * sizeof(double), cudaMemcpyHostToDevice));
-  FCLB_CUDA(cudaMemcpy(c.d_nbr, csr.data(), csr.size() * sizeof(int), cudaMemcpyHostToDevice));
-  FCLB_CUDA(cudaMemcpy(c.d_vinfo, vinfo.data(), vinfo.size() * sizeof(int), cudaMemcpyHostToDevice));
+  FCLB_CUDA(uploadSync(c.d_verts[0], vf4.data(), vf4.size() * sizeof(float)));
+  FCLB_CUDA(uploadSync(c.d_verts[1], vd4.data(), vd4.size() * sizeof(double)));
+  FCLB_CUDA(uploadSync(c.d_nbr, csr.data(), csr.size() * sizeof(int)));
+  FCLB_CUDA(uploadSync(c.d_vinfo, vinfo.data(), vinfo.size() * sizeof(int)));
   e.convex.push_back(c);
   e.convex_epoch++;
   *slot = uint32_t(e.convex.size() - 1);

@@ -133,6 +133,15 @@ int ensureInit();
 ShapeTable* findTable(Engine& e, fclb_handle h);
 int ensureStage(Engine& e, size_t bytes);
 int ensureChunkEvents(Engine& e, int n);
+// cudaMemcpy from PAGEABLE host memory returns once the source is staged; the DMA into device memory may still be in
+// flight (CUDA runtime, "API synchronization behavior").  The engine's streams are non-blocking, so a kernel launched on
+// them right after an upload is not ordered behind that DMA: the first warps of the first query batch could read a
+// table that has not landed yet (seen under compute-sanitizer, whose launch timing differs).  Uploads drain the
+// legacy stream before they return.
+inline cudaError_t uploadSync(void* dst, const void* src, size_t bytes) {
+  const cudaError_t e_ = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  return e_ != cudaSuccess ? e_ : cudaStreamSynchronize(cudaStreamLegacy);
+}
 inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 SolverParams solverParams(int scalar_type, double gjk_tol, uint32_t gjk_max_iter, double epa_tol, uint32_t epa_max_faces,
                           uint32_t epa_max_iter, bool collide_defaults);

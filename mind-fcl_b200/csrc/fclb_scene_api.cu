@@ -1267,7 +1267,7 @@ static int heightmap_upload_one(const uint16_t* heights_mm, uint32_t full_x, uin
     return fail(FCLB_ERR_CUDA, "fclb_heightmap_upload: cudaMalloc failed");
   }
   for (size_t k = 0; k < layers.size(); k++)
-    cudaMemcpy(d->d_layers + d->off[k], layers[k].data(), layers[k].size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    uploadSync(d->d_layers + d->off[k], layers[k].data(), layers[k].size() * sizeof(uint16_t));
   const fclb_handle h = newHandle();
   hmTable()[h] = d;
   *hm = h;
@@ -1449,7 +1449,7 @@ static int octree_upload_one(const uint32_t* inner_children, const uint8_t* inne
   for (int k = 0; k < 6; k++) d->root_box[k] = root_aabb[k];
   auto up = [](auto** dst, const void* src, size_t bytes) -> bool {
     if (cudaMalloc(reinterpret_cast<void**>(dst), bytes ? bytes : 1) != cudaSuccess) return false;
-    return !bytes || cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    return !bytes || uploadSync(*dst, src, bytes) == cudaSuccess;
   };
   bool ok = up(&d->children, inner_children, size_t(32) * n_inner) && up(&d->inner_full, inner_full, n_inner) &&
             up(&d->leaf_bits, leaf_bits, n_leaf);

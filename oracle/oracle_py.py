@@ -246,6 +246,22 @@ class RefOracle(_Oracle):
           request_type, max_contacts, 1 if scene_moves else 0, keep, _p(counts), _p(code), _p(toc), _p(box), threads)
         return counts, code, toc, box
 
+    def translational_ccd_scene_mesh_batch(self, kind, scene_id, obb_mesh_id, poses_scene, poses_mesh, disp, request_type=0,
+                                           max_contacts=1, mesh_moves=False, keep=8, threads=1):
+        """fcl::translational_ccd(heightmap | octree, mesh): (counts, (code, triangle) i64 [n, keep, 2], toc, boxes)"""
+        n = len(poses_scene)
+        dt = poses_scene.dtype
+        counts = np.zeros(n, np.uint32)
+        ids = np.full((n, keep, 2), -1, np.int64)
+        toc = np.full((n, keep, 2), -1, dt)
+        box = np.zeros((n, keep, 6), dt)
+        f = self.fn("translational_ccd_scene_mesh_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_int,
+                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(dt), kind, scene_id, obb_mesh_id, _p(poses_scene), _p(poses_mesh), _p(disp), n, request_type, max_contacts,
+          1 if mesh_moves else 0, keep, _p(counts), _p(ids), _p(toc), _p(box), threads)
+        return counts, ids, toc, box
+
     # ---- meshes (reference BVHModel<OBBRSS<S>>) ----
     def bvh_create(self, verts, tris):
         verts = np.ascontiguousarray(verts, np.float64)

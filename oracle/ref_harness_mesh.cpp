@@ -474,6 +474,8 @@ extern "C" int fclref_translational_ccd_mesh_pair_batch(int scalar_type, int id1
 
 // mesh registry access for the other harness translation units (ref_harness_scene.cpp)
 namespace fclref {
+const fcl::BVHModel<fcl::OBB<float>>* obbMeshF(int id) { return ObbOf<float>::get(id); }
+const fcl::BVHModel<fcl::OBB<double>>* obbMeshD(int id) { return ObbOf<double>::get(id); }
 const fcl::BVHModel<fcl::OBBRSS<float>>* meshF(int id) { return get<float>(id); }
 const fcl::BVHModel<fcl::OBBRSS<double>>* meshD(int id) { return get<double>(id); }
 }  // namespace fclref

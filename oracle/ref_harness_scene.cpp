@@ -719,3 +719,70 @@ extern "C" int fclref_translational_ccd_scene_batch(int scalar_type, int kind, i
   }
   return 0;
 }
+
+// ---- translational continuous collision, heightmap / octree vs mesh (BVHModel<OBB>) ----------------
+// fcl::translational_ccd(scene, tf_scene, displacement, mesh, tf_mesh, ...) and the mesh-first entry
+// (TranslationalDisplacementHeightMapSolver::RunHeightMapObbBVH / RunObbBVH_HeightMap, heightmap_ccd_solver-inl.h:168-366;
+// TranslationalDisplacementOctreeSolver::RunOctreeObbBVH / RunObbBVH_Octree, octree2_ccd_solver-inl.h:225-470).
+// Per contact: (b1 = pixel / node code, b2 = triangle id), toc, o1_bv.
+namespace fclref {
+const fcl::BVHModel<fcl::OBB<float>>* obbMeshF(int id);
+const fcl::BVHModel<fcl::OBB<double>>* obbMeshD(int id);
+}  // namespace fclref
+namespace {
+template <typename S>
+void ccdSceneMeshBatch(const fcl::CollisionGeometry<S>* scene, const fcl::CollisionGeometry<S>* mesh, const S* poses_scene,
+                       const S* poses_mesh, const S* disp, size_t n, int request_type, uint32_t max_contacts, int mesh_moves,
+                       uint32_t keep, uint32_t* counts, int64_t* ids, S* toc, S* box, int threads) {
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    fcl::ContinuousCollisionRequest<S> req;
+    req.request_type = static_cast<fcl::TimeOfCollisionRequestType>(request_type);
+    req.num_max_contacts = max_contacts;
+    for (size_t q = b; q < e; q++) {
+      const auto tf_g = loadPose<S>(poses_scene + 12 * q);
+      const auto tf_m = loadPose<S>(poses_mesh + 12 * q);
+      fcl::TranslationalDisplacement<S> d;
+      d.unit_axis_in_shape1 = fcl::Vector3<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]);
+      d.scalar_displacement = disp[4 * q + 3];
+      fcl::ContinuousCollisionResult<S> res;
+      if (mesh_moves)
+        fcl::translational_ccd<S>(mesh, tf_m, d, scene, tf_g, req, res);
+      else
+        fcl::translational_ccd<S>(scene, tf_g, d, mesh, tf_m, req, res);
+      counts[q] = uint32_t(res.num_contacts());
+      for (uint32_t k = 0; k < keep && k < res.num_contacts(); k++) {
+        const auto& c = res.raw_contacts()[k];
+        const size_t o = size_t(q) * keep + k;
+        const bool scene_is_o1 = c.o1 == scene;
+        ids[2 * o] = scene_is_o1 ? c.b1 : c.b2;
+        ids[2 * o + 1] = scene_is_o1 ? c.b2 : c.b1;
+        const auto& bv = scene_is_o1 ? c.o1_bv : c.o2_bv;
+        toc[2 * o] = c.toc.lower_bound;
+        toc[2 * o + 1] = c.toc.upper_bound;
+        for (int j = 0; j < 3; j++) {
+          box[6 * o + j] = bv.min_[j];
+          box[6 * o + 3 + j] = bv.max_[j];
+        }
+      }
+    }
+  });
+}
+}  // namespace
+extern "C" int fclref_translational_ccd_scene_mesh_batch(int scalar_type, int kind, int scene_id, int obb_mesh_id,
+                                                         const void* poses_scene, const void* poses_mesh, const void* disp, size_t n,
+                                                         int request_type, uint32_t max_contacts, int mesh_moves, uint32_t keep,
+                                                         uint32_t* counts, int64_t* ids, void* toc, void* box, int threads) {
+  if (scalar_type == 0) {
+    const fcl::CollisionGeometry<float>* g = kind == 1 ? (const fcl::CollisionGeometry<float>*)getHm<float>(scene_id)
+                                                        : (const fcl::CollisionGeometry<float>*)getOct<float>(scene_id);
+    ccdSceneMeshBatch<float>(g, fclref::obbMeshF(obb_mesh_id), (const float*)poses_scene, (const float*)poses_mesh, (const float*)disp,
+                             n, request_type, max_contacts, mesh_moves, keep, counts, ids, (float*)toc, (float*)box, threads);
+  } else {
+    const fcl::CollisionGeometry<double>* g = kind == 1 ? (const fcl::CollisionGeometry<double>*)getHm<double>(scene_id)
+                                                         : (const fcl::CollisionGeometry<double>*)getOct<double>(scene_id);
+    ccdSceneMeshBatch<double>(g, fclref::obbMeshD(obb_mesh_id), (const double*)poses_scene, (const double*)poses_mesh,
+                              (const double*)disp, n, request_type, max_contacts, mesh_moves, keep, counts, ids, (double*)toc,
+                              (double*)box, threads);
+  }
+  return 0;
+}
