@@ -104,9 +104,10 @@ FCLB_DI bool boxShapeHit(const V3<S>& side, const Pose<S>& tf_box, const ShapeIn
     ContactPt<S> cp;
     return sphereBoxIntersect(sh.p0, tf_shape, side, tf_box, false, cp);
   } else if (type == ST_BOX) {
-    ContactPt<S> cp[4];
+    // the boolean answer is boxBox2's return code, final after the 15-axis test: the contact generation that follows it
+    // in the reference (box_box-inl.h:437-807) cannot change it and is left out of the traversal kernels
     int n = 0;
-    return boxBox2(side, tf_box, mk<S>(sh.p0, sh.p1, sh.p2), tf_shape, cp, &n) != 0;
+    return boxBox2<S, true>(side, tf_box, mk<S>(sh.p0, sh.p1, sh.p2), tf_shape, nullptr, &n) != 0;
   } else {
     MinkDiff<S, ST_BOX, T1> md;
     md.s0.type = ST_BOX;
