@@ -297,6 +297,25 @@ int fclb_translational_ccd_scene_mesh_batch_dev(int scene_kind, fclb_handle scen
                                                 const fclb_ccd_request* req, int mesh_moves, uint32_t max_keep,
                                                 uint32_t* out_counts, int64_t* out_ids, void* out_toc, void* out_box);
 
+/* heightmap / octree vs heightmap / octree: fcl::translational_ccd(scene1, tf1, displacement, scene2, tf2, ...)
+ * (RunHeightMapPair heightmap_ccd_solver-inl.h:636-779, RunHeightMapOctree / RunOctreeHeightMap :369-632, RunOctreePair
+ * octree2_ccd_solver-inl.h:467-922).  Geometry 1 moves, the displacement is given in its frame.  A contact is a pair of
+ * terminal boxes (bottom-layer pixel; fully occupied octree node; voxel of a partial leaf) whose swept-box test from
+ * [0, 1] is not disjoint; its toc is that test's interval (for every request type: these routines never consult it).
+ *   out_ids[(q * max_keep + k) * 2 ..] = (code on geometry 1, code on geometry 2) of the k-th contact in the reference's
+ *     order; pixel = x << 16 | y; octree node = encodeOctree2Node(index, is_leaf, voxel) in an octree pair, the plain
+ *     node_vector_index against a heightmap (as the reference writes b2 there).  For (octree, heightmap) the reference's
+ *     own contact names the heightmap as o1; the arrays here stay in the caller's argument order.
+ *   out_toc 2 S, out_box 12 S (box on geometry 1, box on geometry 2: o1_bv / o2_bv) per contact; either may be NULL */
+int fclb_translational_ccd_scene_pair_batch_host(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                                 const void* poses2, const void* displacements, size_t n, int scalar_type,
+                                                 const fclb_ccd_request* req, uint32_t max_keep, uint32_t* out_counts,
+                                                 int64_t* out_ids, void* out_toc, void* out_box);
+int fclb_translational_ccd_scene_pair_batch_dev(int kind1, fclb_handle scene1, int kind2, fclb_handle scene2, const void* poses1,
+                                                const void* poses2, const void* displacements, size_t n, int scalar_type,
+                                                const fclb_ccd_request* req, uint32_t max_keep, uint32_t* out_counts,
+                                                int64_t* out_ids, void* out_toc, void* out_box);
+
 /* ---- meshes: BVHModel<OBBRSS<S>> flattened by the caller ------------------------
  * (reference geometry/bvh/BVH_model.h:63-196, BV_node_base.h:50-82).  Only the
  * OBB half of OBBRSS is ever read by collide (math/bv/OBBRSS-inl.h:130-135).

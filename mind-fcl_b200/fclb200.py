@@ -48,7 +48,7 @@ EXPORTS = [
     "fclb_broadphase_query_pairs_host", "fclb_broadphase_update_host", "fclb_broadphase_last_visits",
     "fclb_compute_aabb_batch_host", "fclb_compute_aabb_batch_dev", "fclb_gather_pairs_dev",
     "fclb_scene_self_collide_host", "fclb_scene_self_collide_dev",
-    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_bvh_refit_bottomup_host", "fclb_bvh_refit_bottomup_dev", "fclb_bvh_build_device", "fclb_octree_build_dev", "fclb_octree_build_points_host", "fclb_octree_info", "fclb_octree_export", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_translational_ccd_mesh_batch_host", "fclb_translational_ccd_mesh_batch_dev", "fclb_translational_ccd_mesh_pair_batch_host", "fclb_translational_ccd_mesh_pair_batch_dev", "fclb_translational_ccd_scene_batch_host", "fclb_translational_ccd_scene_batch_dev", "fclb_translational_ccd_scene_mesh_batch_host", "fclb_translational_ccd_scene_mesh_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
+    "fclb_bvh_refit_host", "fclb_bvh_refit_dev", "fclb_bvh_refit_bottomup_host", "fclb_bvh_refit_bottomup_dev", "fclb_bvh_build_device", "fclb_octree_build_dev", "fclb_octree_build_points_host", "fclb_octree_info", "fclb_octree_export", "fclb_translational_ccd_batch_host", "fclb_translational_ccd_batch_dev", "fclb_translational_ccd_mesh_batch_host", "fclb_translational_ccd_mesh_batch_dev", "fclb_translational_ccd_mesh_pair_batch_host", "fclb_translational_ccd_mesh_pair_batch_dev", "fclb_translational_ccd_scene_batch_host", "fclb_translational_ccd_scene_batch_dev", "fclb_translational_ccd_scene_mesh_batch_host", "fclb_translational_ccd_scene_mesh_batch_dev", "fclb_translational_ccd_scene_pair_batch_host", "fclb_translational_ccd_scene_pair_batch_dev", "fclb_init_devices", "fclb_num_devices", "fclb_set_device", "fclb_distance_batch_qt_host", "fclb_expand_poses_dev",
     "fclb_measure_fp_peak", "fclb_measure_l2_bandwidth", "fclb_launch_count", "fclb_last_kernel_ms", "fclb_last_call_ms", "fclb_last_launches", "fclb_stream",
 ]
 
@@ -871,6 +871,25 @@ def translational_ccd_scene_mesh_batch_host(scene_kind, scene, bvh, poses_scene,
                    C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     check(fn(scene_kind, scene, bvh, _ptr(poses_scene), _ptr(poses_mesh), _ptr(displacements), n, scalar_type,
              C.cast(C.pointer(r), C.c_void_p), 1 if mesh_moves else 0, max_keep, _ptr(counts), _ptr(ids), _ptr(toc), _ptr(box)))
+    return counts, ids, toc, box
+
+
+def translational_ccd_scene_pair_batch_host(kind1, scene1, kind2, scene2, poses1, poses2, displacements, scalar_type, request_type=0,
+                                            max_contacts=1, max_keep=8):
+    """fcl::translational_ccd(heightmap | octree, heightmap | octree): (counts, (code1, code2) i64 [n, keep, 2], toc [n, keep, 2],
+    boxes [n, keep, 12])"""
+    n = len(poses1)
+    dt = np_dtype(scalar_type)
+    counts = np.zeros(n, np.uint32)
+    ids = np.zeros((n, max_keep, 2), np.int64)
+    toc = np.zeros((n, max_keep, 2), dt)
+    box = np.zeros((n, max_keep, 12), dt)
+    r = CcdRequest(request_type, max_contacts, 0.0, 0.0, 0, 0)
+    fn = load().fclb_translational_ccd_scene_pair_batch_host
+    fn.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                   C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    check(fn(kind1, scene1, kind2, scene2, _ptr(poses1), _ptr(poses2), _ptr(displacements), n, scalar_type,
+             C.cast(C.pointer(r), C.c_void_p), max_keep, _ptr(counts), _ptr(ids), _ptr(toc), _ptr(box)))
     return counts, ids, toc, box
 
 

@@ -262,6 +262,23 @@ class RefOracle(_Oracle):
           1 if mesh_moves else 0, keep, _p(counts), _p(ids), _p(toc), _p(box), threads)
         return counts, ids, toc, box
 
+    def translational_ccd_scene_pair_batch(self, kind1, id1, kind2, id2, poses1, poses2, disp, request_type=0, max_contacts=1,
+                                           keep=8, threads=1):
+        """fcl::translational_ccd(heightmap | octree, heightmap | octree): (counts, (code1, code2) i64 [n, keep, 2], toc, boxes
+        [n, keep, 12]) in the caller's argument order"""
+        n = len(poses1)
+        dt = poses1.dtype
+        counts = np.zeros(n, np.uint32)
+        ids = np.full((n, keep, 2), -1, np.int64)
+        toc = np.full((n, keep, 2), -1, dt)
+        box = np.zeros((n, keep, 12), dt)
+        f = self.fn("translational_ccd_scene_pair_batch")
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32,
+                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(_st(dt), kind1, id1, kind2, id2, _p(poses1), _p(poses2), _p(disp), n, request_type, max_contacts, keep, _p(counts), _p(ids),
+          _p(toc), _p(box), threads)
+        return counts, ids, toc, box
+
     # ---- meshes (reference BVHModel<OBBRSS<S>>) ----
     def bvh_create(self, verts, tris):
         verts = np.ascontiguousarray(verts, np.float64)

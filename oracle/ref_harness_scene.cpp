@@ -786,3 +786,62 @@ extern "C" int fclref_translational_ccd_scene_mesh_batch(int scalar_type, int ki
   }
   return 0;
 }
+
+// ---- translational continuous collision, heightmap / octree vs heightmap / octree ---------------------------------
+// fcl::translational_ccd(scene1, tf1, displacement, scene2, tf2, ...): RunHeightMapPair, RunHeightMapOctree /
+// RunOctreeHeightMap (heightmap_ccd_solver-inl.h:369-779), RunOctreePair (octree2_ccd_solver-inl.h:467-922).
+// Per contact, in the CALLER's argument order: (b on geometry 1, b on geometry 2), toc, (bv on geometry 1, bv on geometry 2).
+namespace {
+template <typename S>
+void ccdScenePairBatch(int kind1, int id1, int kind2, int id2, const S* poses1, const S* poses2, const S* disp, size_t n,
+                       int request_type, uint32_t max_contacts, uint32_t keep, uint32_t* counts, int64_t* ids, S* toc, S* box,
+                       int threads) {
+  const fcl::CollisionGeometry<S>* g1 = sceneGeom<S>(kind1, id1);
+  const fcl::CollisionGeometry<S>* g2 = sceneGeom<S>(kind2, id2);
+  // the reference names the heightmap o1 when it is handed (octree, heightmap)
+  const bool swapped = kind1 == 2 && kind2 == 1;
+  parallelFor(n, threads, [&](size_t b, size_t e) {
+    fcl::ContinuousCollisionRequest<S> req;
+    req.request_type = static_cast<fcl::TimeOfCollisionRequestType>(request_type);
+    req.num_max_contacts = max_contacts;
+    for (size_t q = b; q < e; q++) {
+      const auto tf1 = loadPose<S>(poses1 + 12 * q);
+      const auto tf2 = loadPose<S>(poses2 + 12 * q);
+      fcl::TranslationalDisplacement<S> d;
+      d.unit_axis_in_shape1 = fcl::Vector3<S>(disp[4 * q], disp[4 * q + 1], disp[4 * q + 2]);
+      d.scalar_displacement = disp[4 * q + 3];
+      fcl::ContinuousCollisionResult<S> res;
+      fcl::translational_ccd<S>(g1, tf1, d, g2, tf2, req, res);
+      counts[q] = uint32_t(res.num_contacts());
+      for (uint32_t k = 0; k < keep && k < res.num_contacts(); k++) {
+        const auto& c = res.raw_contacts()[k];
+        const size_t o = size_t(q) * keep + k;
+        ids[2 * o] = swapped ? c.b2 : c.b1;
+        ids[2 * o + 1] = swapped ? c.b1 : c.b2;
+        const auto& bv1 = swapped ? c.o2_bv : c.o1_bv;
+        const auto& bv2 = swapped ? c.o1_bv : c.o2_bv;
+        toc[2 * o] = c.toc.lower_bound;
+        toc[2 * o + 1] = c.toc.upper_bound;
+        for (int j = 0; j < 3; j++) {
+          box[12 * o + j] = bv1.min_[j];
+          box[12 * o + 3 + j] = bv1.max_[j];
+          box[12 * o + 6 + j] = bv2.min_[j];
+          box[12 * o + 9 + j] = bv2.max_[j];
+        }
+      }
+    }
+  });
+}
+}  // namespace
+extern "C" int fclref_translational_ccd_scene_pair_batch(int scalar_type, int kind1, int id1, int kind2, int id2, const void* poses1,
+                                                         const void* poses2, const void* disp, size_t n, int request_type,
+                                                         uint32_t max_contacts, uint32_t keep, uint32_t* counts, int64_t* ids,
+                                                         void* toc, void* box, int threads) {
+  if (scalar_type == 0)
+    ccdScenePairBatch<float>(kind1, id1, kind2, id2, (const float*)poses1, (const float*)poses2, (const float*)disp, n, request_type,
+                             max_contacts, keep, counts, ids, (float*)toc, (float*)box, threads);
+  else
+    ccdScenePairBatch<double>(kind1, id1, kind2, id2, (const double*)poses1, (const double*)poses2, (const double*)disp, n,
+                              request_type, max_contacts, keep, counts, ids, (double*)toc, (double*)box, threads);
+  return 0;
+}
