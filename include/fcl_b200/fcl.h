@@ -1046,8 +1046,8 @@ struct ContinuousCollisionQuery {
 // one C-ABI call for the shape pairs of the batch, one per mesh for its (shape, mesh) / (mesh, shape) queries and one per
 // pair of meshes, one per heightmap / octree for its shape queries
 // (the reference's CCD matrix serves OBB trees, translational_collision_func_matrix-inl.h:469-489; our BVHModel<OBBRSS>
-// has the same hierarchy, see fclb_translational_ccd_mesh_batch_host); heightmap / octree vs mesh / heightmap / octree
-// queries are not on the device path yet (warning, no contact)
+// has the same hierarchy, see fclb_translational_ccd_mesh_batch_host); one per (heightmap / octree, mesh) pair and
+// argument order and one per pair of heightmaps / octrees
 template <typename S>
 void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queries, const ContinuousCollisionRequest<S>& request,
                            std::vector<ContinuousCollisionResult<S>>& results) {
@@ -1078,6 +1078,12 @@ void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queri
     std::vector<std::size_t> idx;
   };
   std::map<std::pair<fclb_handle, fclb_handle>, PairGroup> mesh_pairs;
+  struct ScenePairGroup : PairGroup {
+    int kind1 = 0, kind2 = 0;
+    bool mesh_moves = false;  // (scene, mesh) groups only
+  };
+  std::map<std::pair<std::pair<fclb_handle, fclb_handle>, bool>, ScenePairGroup> scene_meshes;  // ((scene, mesh), mesh moves)
+  std::map<std::pair<fclb_handle, fclb_handle>, ScenePairGroup> scene_pairs;
   auto push12 = [](std::vector<S>& v, const Transform3<S>& tf) {
     v.resize(v.size() + 12);
     tf.toPose12(&v[v.size() - 12]);
@@ -1131,10 +1137,115 @@ void translationalCcdBatch(const std::vector<ContinuousCollisionQuery<S>>& queri
       for (int k = 0; k < 3; k++) g.disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
       g.disp.push_back(Q.o1_displacement.scalar_displacement);
       g.idx.push_back(q);
+    } else if ((g1 && m2) || (m1 && g2)) {  // heightmap / octree vs mesh, either order
+      const CollisionGeometry<S>* scene = g1 ? Q.o1 : Q.o2;
+      const CollisionGeometry<S>* mesh = g1 ? Q.o2 : Q.o1;
+      ScenePairGroup& g = scene_meshes[std::make_pair(std::make_pair(detail::sceneHandle(scene), detail::sceneHandle(mesh)), m1)];
+      g.kind1 = detail::sceneKind(scene);
+      g.mesh_moves = m1;
+      push12(g.pose1, g1 ? Q.tf1 : Q.tf2);  // scene
+      push12(g.pose2, g1 ? Q.tf2 : Q.tf1);  // mesh
+      for (int k = 0; k < 3; k++) g.disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
+      g.disp.push_back(Q.o1_displacement.scalar_displacement);
+      g.idx.push_back(q);
+    } else if (g1 && g2) {
+      ScenePairGroup& g = scene_pairs[std::make_pair(detail::sceneHandle(Q.o1), detail::sceneHandle(Q.o2))];
+      g.kind1 = detail::sceneKind(Q.o1);
+      g.kind2 = detail::sceneKind(Q.o2);
+      push12(g.pose1, Q.tf1);
+      push12(g.pose2, Q.tf2);
+      for (int k = 0; k < 3; k++) g.disp.push_back(Q.o1_displacement.unit_axis_in_shape1[k]);
+      g.disp.push_back(Q.o1_displacement.scalar_displacement);
+      g.idx.push_back(q);
     } else {
       std::cerr << "Warning: collision function between node type " << Q.o1->getNodeType() << " and node type " << Q.o2->getNodeType()
                 << " is not supported" << std::endl;
     }
+  }
+  for (auto& kv : scene_meshes) {  // contacts: o1 = the heightmap / octree, b1 = pixel / node code, o1_bv its box; o2 = the mesh, b2 = triangle
+    ScenePairGroup& g = kv.second;
+    const std::size_t m = g.idx.size();
+    uint32_t keep = uint32_t(std::min<std::size_t>(request.num_max_contacts, 64));
+    std::vector<uint32_t> counts(m);
+    std::vector<int64_t> ids;
+    std::vector<S> toc, box;
+    for (int pass = 0; pass < 2; pass++) {
+      ids.assign(m * keep * 2, -1);
+      toc.assign(m * keep * 2, S(-1));
+      box.assign(m * keep * 6, S(0));
+      if (!detail::batchOk(fclb_translational_ccd_scene_mesh_batch_host(g.kind1, kv.first.first.first, kv.first.first.second, g.pose1.data(),
+                                                                        g.pose2.data(), g.disp.data(), m, detail::scalarType<S>(), &rq,
+                                                                        g.mesh_moves ? 1 : 0, keep, counts.data(), ids.data(), toc.data(),
+                                                                        box.data()),
+                           "fclb_translational_ccd_scene_mesh_batch_host")) {
+        counts.assign(m, 0);
+        break;
+      }
+      const uint32_t most = *std::max_element(counts.begin(), counts.end());
+      if (most <= keep) break;
+      keep = most;
+    }
+    for (std::size_t i = 0; i < m; i++)
+      for (uint32_t k = 0; k < counts[i] && k < keep; k++) {
+        const auto& Q = queries[g.idx[i]];
+        ContinuousCollisionContact<S> c;
+        c.o1 = g.mesh_moves ? Q.o2 : Q.o1;
+        c.o2 = g.mesh_moves ? Q.o1 : Q.o2;
+        c.b1 = ids[(i * keep + k) * 2];
+        c.b2 = ids[(i * keep + k) * 2 + 1];
+        c.toc.lower_bound = toc[(i * keep + k) * 2];
+        c.toc.upper_bound = toc[(i * keep + k) * 2 + 1];
+        for (int j = 0; j < 3; j++) {
+          c.o1_bv.min_[j] = box[(i * keep + k) * 6 + j];
+          c.o1_bv.max_[j] = box[(i * keep + k) * 6 + 3 + j];
+        }
+        results[g.idx[i]].AddContact(c);
+      }
+  }
+  for (auto& kv : scene_pairs) {
+    ScenePairGroup& g = kv.second;
+    const std::size_t m = g.idx.size();
+    uint32_t keep = uint32_t(std::min<std::size_t>(request.num_max_contacts, 64));
+    std::vector<uint32_t> counts(m);
+    std::vector<int64_t> ids;
+    std::vector<S> toc, box;
+    for (int pass = 0; pass < 2; pass++) {
+      ids.assign(m * keep * 2, -1);
+      toc.assign(m * keep * 2, S(-1));
+      box.assign(m * keep * 12, S(0));
+      if (!detail::batchOk(fclb_translational_ccd_scene_pair_batch_host(g.kind1, kv.first.first, g.kind2, kv.first.second, g.pose1.data(),
+                                                                        g.pose2.data(), g.disp.data(), m, detail::scalarType<S>(), &rq,
+                                                                        keep, counts.data(), ids.data(), toc.data(), box.data()),
+                           "fclb_translational_ccd_scene_pair_batch_host")) {
+        counts.assign(m, 0);
+        break;
+      }
+      const uint32_t most = *std::max_element(counts.begin(), counts.end());
+      if (most <= keep) break;
+      keep = most;
+    }
+    // the reference names the heightmap o1 when it is handed (octree, heightmap) (RunOctreeHeightMap); every other pair keeps
+    // the caller's order
+    const bool swap = g.kind1 == FCLB_SCENE_OCTREE && g.kind2 == FCLB_SCENE_HEIGHTMAP;
+    for (std::size_t i = 0; i < m; i++)
+      for (uint32_t k = 0; k < counts[i] && k < keep; k++) {
+        const auto& Q = queries[g.idx[i]];
+        const std::size_t o = i * keep + k;
+        ContinuousCollisionContact<S> c;
+        c.o1 = swap ? Q.o2 : Q.o1;
+        c.o2 = swap ? Q.o1 : Q.o2;
+        c.b1 = ids[o * 2 + (swap ? 1 : 0)];
+        c.b2 = ids[o * 2 + (swap ? 0 : 1)];
+        c.toc.lower_bound = toc[o * 2];
+        c.toc.upper_bound = toc[o * 2 + 1];
+        for (int j = 0; j < 3; j++) {
+          c.o1_bv.min_[j] = box[o * 12 + (swap ? 6 : 0) + j];
+          c.o1_bv.max_[j] = box[o * 12 + (swap ? 6 : 0) + 3 + j];
+          c.o2_bv.min_[j] = box[o * 12 + (swap ? 0 : 6) + j];
+          c.o2_bv.max_[j] = box[o * 12 + (swap ? 0 : 6) + 3 + j];
+        }
+        results[g.idx[i]].AddContact(c);
+      }
   }
   for (auto& kv : mesh_pairs) {
     PairGroup& g = kv.second;

@@ -407,6 +407,42 @@ void runBatch() {
       EXPECT_TRUE(std::fabs(ct.toc.lower_bound - S(0.47)) < S(1e-3));  // bar bottom at 0.97 reaches the column tops at 0.5
     }
   }
+  // heightmap / octree vs mesh and vs each other: the four 0.5 m columns rise 1 m into the floor mesh held 1 m above them
+  // (o1 = the map, b1 = pixel, o1_bv its box, b2 = triangle -- in either argument order); into the octree's four voxels held
+  // 1 m above (for (octree, heightmap) the reference names the map o1 as well); two copies of the octree sweeping through
+  // each other
+  {
+    TranslationalDisplacement<S> down, up;
+    down.unit_axis_in_shape1 = Vector3<S>(0, 0, -1);
+    up.unit_axis_in_shape1 = Vector3<S>(0, 0, 1);
+    down.scalar_displacement = up.scalar_displacement = 1;
+    ContinuousCollisionRequest<S> creq;
+    creq.num_max_contacts = 64;
+    ContinuousCollisionResult<S> hm_mesh, hm_mesh_miss, mesh_hm, hm_oct, oct_hm, oct_oct, oct_oct_miss;
+    translational_ccd<S>(&hm, I, up, &floor, at(0, 0, 1), creq, hm_mesh);
+    translational_ccd<S>(&hm, I, down, &floor, at(0, 0, 1), creq, hm_mesh_miss);
+    translational_ccd<S>(&floor, at(0, 0, 1), down, &hm, I, creq, mesh_hm);
+    EXPECT_TRUE(hm_mesh.num_contacts() >= 4 && hm_mesh.num_contacts() <= 8 && hm_mesh_miss.num_contacts() == 0);
+    EXPECT_TRUE(mesh_hm.num_contacts() == hm_mesh.num_contacts());
+    for (const auto* r : {&hm_mesh, &mesh_hm})
+      for (const auto& ct : r->raw_contacts()) {
+        EXPECT_TRUE(ct.o1 == &hm && ct.o2 == &floor && (ct.b1 & 0xffff) == 8 && ct.b2 >= 0 && ct.b2 < 2);
+        EXPECT_TRUE(std::fabs(ct.o1_bv.max_[2] - S(0.5)) < S(1e-3) && ct.o1_bv.min_[2] == 0);
+      }
+    translational_ccd<S>(&hm, I, up, &oct, at(0, 0, 1), creq, hm_oct);
+    translational_ccd<S>(&oct, at(0, 0, 1), down, &hm, I, creq, oct_hm);
+    EXPECT_TRUE(hm_oct.num_contacts() >= 4 && hm_oct.num_contacts() <= 16 && oct_hm.num_contacts() == hm_oct.num_contacts());
+    for (const auto* r : {&hm_oct, &oct_hm})
+      for (const auto& ct : r->raw_contacts()) {
+        EXPECT_TRUE(ct.o1 == &hm && ct.o2 == &oct && (ct.b1 & 0xffff) == 8);
+        EXPECT_TRUE(std::fabs(ct.o1_bv.max_[2] - S(0.5)) < S(1e-3) && std::fabs(ct.o2_bv.max_[2] - ct.o2_bv.min_[2] - S(0.1)) < S(1e-3));
+        EXPECT_TRUE(std::fabs(ct.toc.lower_bound - S(0.5)) < S(1e-3));  // column tops at 0.5 reach the voxel bottoms at 1.0
+      }
+    translational_ccd<S>(&oct, I, up, &oct, at(0, 0, S(0.5)), creq, oct_oct);
+    translational_ccd<S>(&oct, I, down, &oct, at(0, 0, S(0.5)), creq, oct_oct_miss);
+    EXPECT_TRUE(oct_oct.num_contacts() >= 4 && oct_oct.num_contacts() <= 16 && oct_oct_miss.num_contacts() == 0);
+    for (const auto& ct : oct_oct.raw_contacts()) EXPECT_TRUE(ct.o1 == &oct && ct.o2 == &oct && ct.b1 >= 0 && ct.b2 >= 0);
+  }
   // replace protocol: the floor drops by 0.5 m (default arguments: refit bottom-up); a ball that touched it no longer does
   {
     BVHModel<OBBRSS<S>> sheet;
