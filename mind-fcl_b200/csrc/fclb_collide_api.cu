@@ -199,26 +199,70 @@ static int runCollideHost(fclb_handle shapes, const fclb_pair* pairs, const void
   rc = ensureStage(e, total);
   if (rc) return rc;
   char* base = static_cast<char*>(e.d_stage);
-  FCLB_CUDA(cudaMemcpyAsync(base + o_pairs, pairs, n * sizeof(fclb_pair), cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses1, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses2, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  if (h_contacts) FCLB_CUDA(cudaMemsetAsync(base + o_cont, 0, cont_bytes, e.compute));  // slots beyond counts[q] come back as zeros
-  CollideOut out{};
-  out.contacts = h_contacts ? base + o_cont : nullptr;
-  out.counts = reinterpret_cast<uint32_t*>(base + o_cnt);
-  out.max_keep = h_contacts ? max_keep : 0;
-  out.gjk_status = reinterpret_cast<int32_t*>(base + o_gjk);
-  out.epa_status = reinterpret_cast<int32_t*>(base + o_epa);
-  out.geom = base + o_geom;
-  rc = runCollide(shapes, reinterpret_cast<const fclb_pair*>(base + o_pairs), base + o_p1, base + o_p2, n, scalar_type,
-                  req, api_mode, out);
+  // Chunked three-stage pipeline, as in fclb_distance_batch_host: every H2D copy is queued up front on the copy-in stream
+  // (one event per chunk), the compute stream waits per chunk, and the copy-out stream drains a chunk's contacts while later
+  // chunks upload / compute.  A contact record batch is larger than its inputs (4 x 9 S against 2 x 12 S + 8 B per query),
+  // so the call is bounded by the copy-out direction instead of the sum of the two.
+  // Stages pay only where the copies dominate: boolean requests (one MPR / closed-form test per query) and contact requests
+  // on box / sphere tables (closed forms).  GJK + EPA batches are compute-bound and their tiered launches want the whole
+  // batch at once -- measured on B200, 1M queries: c1a 2.05e8 -> 2.41e8 q/s with four stages, c1b 9.6e7 -> 6.7e7
+  // (profiles/r02_collide_host_pipeline.txt) -- so those keep one stage.
+  bool copy_bound = req && req->penetration_mode == FCLB_PEN_DISABLED && api_mode == 0;
+  if (!copy_bound && api_mode == 0) {
+    if (const ShapeTable* t = findTable(e, shapes)) {
+      copy_bound = true;
+      for (uint32_t i = 0; i < t->n; i++)
+        if (t->host[i].type != FCLB_BOX && t->host[i].type != FCLB_SPHERE) copy_bound = false;
+    }
+  }
+  const size_t chunk = copy_bound ? std::max<size_t>(e.host_chunk / 8, 1024) : n;
+  const int n_chunks = int((n + chunk - 1) / chunk);
+  rc = ensureChunkEvents(e, n_chunks);
   if (rc) return rc;
-  if (h_contacts) FCLB_CUDA(cudaMemcpyAsync(h_contacts, base + o_cont, cont_bytes, cudaMemcpyDeviceToHost, e.compute));
-  if (h_counts) FCLB_CUDA(cudaMemcpyAsync(h_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
-  if (h_gjk) FCLB_CUDA(cudaMemcpyAsync(h_gjk, base + o_gjk, n * 4, cudaMemcpyDeviceToHost, e.compute));
-  if (h_epa) FCLB_CUDA(cudaMemcpyAsync(h_epa, base + o_epa, n * 4, cudaMemcpyDeviceToHost, e.compute));
-  if (h_geom) FCLB_CUDA(cudaMemcpyAsync(h_geom, base + o_geom, n * 7 * ss, cudaMemcpyDeviceToHost, e.compute));
-  FCLB_CUDA(cudaStreamSynchronize(e.compute));
+  const char* hp_pairs = reinterpret_cast<const char*>(pairs);
+  const char* hp_1 = static_cast<const char*>(poses1);
+  const char* hp_2 = static_cast<const char*>(poses2);
+  const size_t cb = size_t(max_keep) * 9 * ss;  // contact bytes per query
+  FCLB_CUDA(cudaStreamSynchronize(e.copy_out));  // the arena may still be read by a previous call's copy-out
+  for (int c = 0; c < n_chunks; c++) {
+    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    FCLB_CUDA(cudaMemcpyAsync(base + o_pairs + b0 * sizeof(fclb_pair), hp_pairs + b0 * sizeof(fclb_pair), m * sizeof(fclb_pair),
+                              cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaMemcpyAsync(base + o_p1 + b0 * 12 * ss, hp_1 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaMemcpyAsync(base + o_p2 + b0 * 12 * ss, hp_2 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaEventRecord(e.ev_in[c], e.copy_in));
+  }
+  for (int c = 0; c < n_chunks; c++) {
+    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    FCLB_CUDA(cudaStreamWaitEvent(e.compute, e.ev_in[c], 0));
+    if (h_contacts) FCLB_CUDA(cudaMemsetAsync(base + o_cont + b0 * cb, 0, m * cb, e.compute));  // slots beyond counts[q] come back as zeros
+    CollideOut out{};
+    out.contacts = h_contacts ? base + o_cont + b0 * cb : nullptr;
+    out.counts = reinterpret_cast<uint32_t*>(base + o_cnt) + b0;
+    out.max_keep = h_contacts ? max_keep : 0;
+    out.gjk_status = reinterpret_cast<int32_t*>(base + o_gjk) + b0;
+    out.epa_status = reinterpret_cast<int32_t*>(base + o_epa) + b0;
+    out.geom = base + o_geom + b0 * 7 * ss;
+    rc = runCollide(shapes, reinterpret_cast<const fclb_pair*>(base + o_pairs) + b0, base + o_p1 + b0 * 12 * ss,
+                    base + o_p2 + b0 * 12 * ss, m, scalar_type, req, api_mode, out);
+    if (rc) {  // drain the queued copies before the caller gets its buffers back
+      cudaStreamSynchronize(e.copy_in);
+      cudaStreamSynchronize(e.compute);
+      cudaStreamSynchronize(e.copy_out);
+      return rc;
+    }
+    FCLB_CUDA(cudaEventRecord(e.ev_done[c], e.compute));
+    FCLB_CUDA(cudaStreamWaitEvent(e.copy_out, e.ev_done[c], 0));
+    if (h_contacts)
+      FCLB_CUDA(cudaMemcpyAsync(static_cast<char*>(h_contacts) + b0 * cb, base + o_cont + b0 * cb, m * cb, cudaMemcpyDeviceToHost, e.copy_out));
+    if (h_counts) FCLB_CUDA(cudaMemcpyAsync(h_counts + b0, base + o_cnt + b0 * 4, m * 4, cudaMemcpyDeviceToHost, e.copy_out));
+    if (h_gjk) FCLB_CUDA(cudaMemcpyAsync(h_gjk + b0, base + o_gjk + b0 * 4, m * 4, cudaMemcpyDeviceToHost, e.copy_out));
+    if (h_epa) FCLB_CUDA(cudaMemcpyAsync(h_epa + b0, base + o_epa + b0 * 4, m * 4, cudaMemcpyDeviceToHost, e.copy_out));
+    if (h_geom)
+      FCLB_CUDA(cudaMemcpyAsync(static_cast<char*>(h_geom) + b0 * 7 * ss, base + o_geom + b0 * 7 * ss, m * 7 * ss, cudaMemcpyDeviceToHost,
+                                e.copy_out));
+  }
+  FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
   return FCLB_OK;
 }
 
