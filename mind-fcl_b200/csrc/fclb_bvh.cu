@@ -1454,7 +1454,7 @@ int fclb_bvh_collide_batch_dev(fclb_handle bvh1, fclb_handle bvh2, const void* p
     return fail(FCLB_ERR_BAD_ARG, "BVH was uploaded for a different scalar type");
   if (!req || !out_counts) return fail(FCLB_ERR_BAD_ARG, "null request / out_counts");
   if (req->penetration_mode != FCLB_PEN_DISABLED)
-    return fail(FCLB_ERR_UNSUPPORTED, "mesh-mesh contact generation (penetration modes) is not on the device yet");
+    return fail(FCLB_ERR_UNSUPPORTED, "this entry point answers boolean requests: contact records (every penetration mode) come from fclb_bvh_collide_contacts_batch_*");
   if (n == 0) return FCLB_OK;
   if (!poses1 || !poses2) return fail(FCLB_ERR_BAD_ARG, "null pose array");
   if (scalar_type == FCLB_F32)
