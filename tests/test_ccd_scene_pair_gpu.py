@@ -72,3 +72,49 @@ def test_scene_pair_ccd(fclb, ref_oracle, geometries, dtype, pair):
         assert same["toc"], (np.argwhere(toc != etoc)[:5], np.abs(toc - etoc).max())
         assert same["boxes"], np.argwhere(box != ebox)[:5]
         assert int((ec > 0).sum()) > 50
+
+
+def test_scene_ccd_edge_cases(fclb, ref_oracle, geometries):
+    """Empty batches, zero-length displacements, geometries that start in contact and refused inputs of the two entry points
+    for continuous collision between scene geometries (the same cases the reference is run on)."""
+    dtype, st = np.float64, fclb.F64
+    k1, h1, rk1, r1 = geometries[dtype]["hm1"]
+    k2, h2, rk2, r2 = geometries[dtype]["oc2"]
+    empty = np.zeros((0, 12), dtype)
+    c, ids, toc, box = fclb.translational_ccd_scene_pair_batch_host(k1, h1, k2, h2, empty, empty, np.zeros((0, 4), dtype), st)
+    assert c.shape == (0,) and ids.shape == (0, 8, 2)
+    ident = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype), (3, 1))
+    p1 = ident.copy()
+    p1[1, 9:] = (0.05, 0.0, 2.0)   # far above: nothing, whatever the sweep
+    p1[2, 9:] = (0.0, 0.0, 0.6)    # above the octree's points, swept down through them
+    disp = np.array([[0, 0, -1, 0.0], [0, 0, -1, 0.0], [0, 0, -1, 1.5]], dtype)
+    for request_type in (0, 2):
+        c, ids, toc, box = fclb.translational_ccd_scene_pair_batch_host(k1, h1, k2, h2, p1, ident, disp, st, request_type=request_type,
+                                                                        max_contacts=10**6, max_keep=32)
+        ec, eids, etoc, ebox = ref_oracle.translational_ccd_scene_pair_batch(rk1, r1, rk2, r2, p1, ident, disp,
+                                                                             request_type=request_type, max_contacts=10**6, keep=32)
+        assert np.array_equal(c, ec) and np.array_equal(ids, eids) and np.array_equal(toc, etoc) and np.array_equal(box, ebox)
+        # zero displacement: the maps overlap where they stand (the whole interval), the lifted one touches nothing
+        assert c[0] > 0 and c[1] == 0 and c[2] > 0
+        assert np.all(toc[0, : min(int(c[0]), 32), 0] == 0) and np.all(toc[0, : min(int(c[0]), 32), 1] == 1)
+    # max_keep = 0: counts only
+    c0, _, _, _ = fclb.translational_ccd_scene_pair_batch_host(k1, h1, k2, h2, p1, ident, disp, st, max_contacts=5, max_keep=0)
+    assert np.array_equal(c0, np.minimum(ec, 5))
+    # refused: a mesh handle where a heightmap / octree is expected, an unknown kind, an unknown request type
+    v, t = scenes.noisy_uv_sphere(n_lat=5, n_lon=8, radius=0.2, noise=0.0)
+    bvh = fclb.bvh_build(v, t, st)
+    with pytest.raises(fclb.FclbError):
+        fclb.translational_ccd_scene_pair_batch_host(k1, bvh, k2, h2, p1, ident, disp, st)
+    with pytest.raises(fclb.FclbError):
+        fclb.translational_ccd_scene_pair_batch_host(0, h1, k2, h2, p1, ident, disp, st)
+    with pytest.raises(fclb.FclbError):
+        fclb.translational_ccd_scene_pair_batch_host(k1, h1, k2, h2, p1, ident, disp, st, request_type=3)
+    # scene vs mesh: empty batch, a mesh of the other scalar type, a scene handle of the wrong kind
+    c, ids, toc, box = fclb.translational_ccd_scene_mesh_batch_host(k1, h1, bvh, empty, empty, np.zeros((0, 4), dtype), st)
+    assert c.shape == (0,)
+    with pytest.raises(fclb.FclbError):
+        fclb.translational_ccd_scene_mesh_batch_host(k1, h1, bvh, p1.astype(np.float32), ident.astype(np.float32),
+                                                     disp.astype(np.float32), fclb.F32)
+    with pytest.raises(fclb.FclbError):
+        fclb.translational_ccd_scene_mesh_batch_host(k2, h1, bvh, p1, ident, disp, st)
+    fclb.bvh_release(bvh)
