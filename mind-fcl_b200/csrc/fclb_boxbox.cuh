@@ -49,6 +49,7 @@ FCLB_DI int intersectRectQuad2(const S h[2], const S p[8], S ret[16]) {
       const S* pq = q;
       S* pr = r;
       nr = 0;
+      #pragma unroll 1
       for (int i = nq; i > 0; --i) {
         if (sg * pq[dir] < h[dir]) {
           pr[0] = pq[0];
@@ -80,6 +81,7 @@ FCLB_DI int intersectRectQuad2(const S h[2], const S p[8], S ret[16]) {
   }
 done:
   if (q != ret)
+    #pragma unroll 1
     for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
   return nr;
 }
@@ -98,6 +100,7 @@ FCLB_DI void cullPoints2(int n, const S p[], int m, int i0, int iret[]) {
     a = 0;
     cx = 0;
     cy = 0;
+    #pragma unroll 1
     for (int i = 0; i < n - 1; ++i) {
       q = p[i * 2] * p[i * 2 + 3] - p[i * 2 + 2] * p[i * 2 + 1];
       a += q;
@@ -113,18 +116,22 @@ FCLB_DI void cullPoints2(int n, const S p[], int m, int i0, int iret[]) {
     cy = a * (cy + q * (p[n * 2 - 1] + p[1]));
   }
   S A[8];
+  #pragma unroll 1
   for (int i = 0; i < n; ++i) A[i] = S(atan2(double(p[i * 2 + 1] - cy), double(p[i * 2] - cx)));
   int avail[8];
+  #pragma unroll 1
   for (int i = 0; i < n; ++i) avail[i] = 1;
   avail[i0] = 0;
   iret[0] = i0;
   int k = 1;
   const S pi = num_limits<S>::pi();
+  #pragma unroll 1
   for (int j = 1; j < m; ++j) {
     a = S(j) * (S(2) * pi / S(m)) + A[i0];
     if (a > pi) a -= S(2) * pi;
     S maxdiff = S(1e9), diff;
     iret[k] = i0;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       if (avail[i]) {
         diff = fabs_(A[i] - a);
@@ -383,6 +390,7 @@ FCLB_DI int boxBox2(const V3<S>& side1, const Pose<S>& tf1, const V3<S>& side2, 
   m21 *= det1;
   m22 *= det1;
   int cnum = 0;
+  #pragma unroll 1
   for (int j = 0; j < n_intersect; ++j) {
     const S k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
     const S k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
@@ -402,6 +410,7 @@ FCLB_DI int boxBox2(const V3<S>& side1, const Pose<S>& tf1, const V3<S>& side2, 
   if (cnum > maxc) {
     int i1 = 0;
     S maxdepth = dep[0];
+    #pragma unroll 1
     for (int i = 1; i < cnum; ++i) {
       if (dep[i] > maxdepth) {
         maxdepth = dep[i];
@@ -411,6 +420,7 @@ FCLB_DI int boxBox2(const V3<S>& side1, const Pose<S>& tf1, const V3<S>& side2, 
     cullPoints2(cnum, ret, maxc, i1, iret);
     cnum = maxc;
   }
+  #pragma unroll 1
   for (int j = 0; j < cnum; ++j) {
     const int i = iret[j];
     out[j].normal = normal;

@@ -88,6 +88,7 @@ __device__ __forceinline__ double atomicMaxD(double* addr, double v) {
 template <typename S>
 __global__ void bpBoundsKernel(const Box6<S>* __restrict__ box, int n, double* bounds) {
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  #pragma unroll 1
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -164,11 +165,13 @@ __global__ void bpHierarchyKernel(const unsigned long long* __restrict__ keys, i
   int lmax = 2;
   while (bpDelta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
   int l = 0;
+  #pragma unroll 1
   for (int t = lmax >> 1; t >= 1; t >>= 1)
     if (bpDelta(keys, n, i, i + (l + t) * d) > dmin) l += t;
   const int j = i + l * d;
   const int dnode = bpDelta(keys, n, i, j);
   int s = 0;
+  #pragma unroll 1
   for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
     if (bpDelta(keys, n, i, i + (s + t) * d) > dnode) s += t;
     if (t == 1) break;
@@ -499,6 +502,7 @@ static int buildTreeDev(Engine& e, const void* d_boxes, const uint64_t* d_ids, i
     FCLB_CUDA(cudaMemcpyAsync(ids.data(), t->leaf_id, size_t(n) * 8, cudaMemcpyDeviceToHost, e.compute));
     FCLB_CUDA(cudaStreamSynchronize(e.compute));
     t->pos_of.reserve(size_t(n) * 2);
+    #pragma unroll 1
     for (int i = 0; i < n; i++) t->pos_of[ids[i]] = i;
   }
   return FCLB_OK;  // stream-ordered: later work on e.compute sees the finished tree
@@ -544,6 +548,7 @@ __global__ void iotaKernel(uint64_t* ids, size_t n) {
 }
 __global__ void countNonZeroKernel(const uint32_t* __restrict__ v, size_t n, unsigned long long* out) {
   unsigned long long c = 0;
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) c += v[i] != 0;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
@@ -807,6 +812,7 @@ int fclb_broadphase_update_host(fclb_handle tree, const uint64_t* user_ids, cons
   std::vector<int> pos;
   std::vector<unsigned char> merged;
   std::unordered_map<int, size_t> slot_of;
+  #pragma unroll 1
   for (size_t i = 0; i < n; i++) {
     auto it = t->pos_of.find(user_ids[i]);
     if (it == t->pos_of.end()) return fail(FCLB_ERR_BAD_ARG, "fclb_broadphase_update: unknown user id");  // UpdateObjectAABB returns false

@@ -133,11 +133,13 @@ FCLB_DI unsigned triTriContacts(const V3<S> P[3], const V3<S> Q[3], const M3<S>&
   unsigned nc;
   if (pd1 > pd2) {
     nc = num2 < 2u ? num2 : 2u;
+    #pragma unroll 1
     for (unsigned i = 0; i < nc; i++) pts[i] = deep2[i];
     normal = n1;
     depth = pd2;
   } else {
     nc = num1 < 2u ? num1 : 2u;
+    #pragma unroll 1
     for (unsigned i = 0; i < nc; i++) pts[i] = deep1[i];
     normal = -n2;
     depth = pd1;
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(kBvhWarps * 32) bvhCollideKernel(BvhArgs a) {
             const int total = __shfl_sync(0xffffffffu, off, 31);
             off -= hit ? pen_nc : 0;
             if (hit && a.out_ids) {
+              #pragma unroll 1
               for (int k = 0; k < pen_nc; k++) {
                 const uint32_t slot = count + uint32_t(off + k);
                 if (slot < a.max_keep && slot < a.max_contacts) {
@@ -449,6 +452,7 @@ FCLB_DI S orderedCovarianceSum(const S* __restrict__ tris, const int* __restrict
   const int a = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 0 : lane == 7 ? 0 : 1);
   const int b = lane < 3 ? lane : (lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : lane == 7 ? 2 : 2);
   S acc = S(0);
+  #pragma unroll 1
   for (int base = 0; base < count; base += 32) {
     const int i = base + lane;
     if (i < count) {
@@ -461,11 +465,13 @@ FCLB_DI S orderedCovarianceSum(const S* __restrict__ tris, const int* __restrict
     __syncwarp();
     const int m = count - base < 32 ? count - base : 32;
     if (lane < 3) {
+      #pragma unroll 1
       for (int j = 0; j < m; j++) {
         const S* p = stage + 9 * j;
         acc += (p[a] + p[3 + a]) + p[6 + a];
       }
     } else if (lane < 9) {
+      #pragma unroll 1
       for (int j = 0; j < m; j++) {
         const S* p = stage + 9 * j;
         acc += (p[a] * p[b] + p[3 + a] * p[3 + b] + p[6 + a] * p[6 + b]);
@@ -479,6 +485,7 @@ FCLB_DI S orderedCovarianceSum(const S* __restrict__ tris, const int* __restrict
 template <typename S>
 FCLB_DI S orderedCentroidSum(const S* __restrict__ tris, const int* __restrict__ prim, int first, int count, int lane, S* stage) {
   S acc = S(0);
+  #pragma unroll 1
   for (int base = 0; base < count; base += 32) {
     const int i = base + lane;
     if (i < count) {
@@ -491,6 +498,7 @@ FCLB_DI S orderedCentroidSum(const S* __restrict__ tris, const int* __restrict__
     __syncwarp();
     const int m = count - base < 32 ? count - base : 32;
     if (lane < 3)
+      #pragma unroll 1
       for (int j = 0; j < m; j++) {
         const S* p = stage + 9 * j;
         acc += ((p[lane] + p[3 + lane]) + p[6 + lane]) / 3;
@@ -508,6 +516,7 @@ __global__ void __launch_bounds__(256) bvhRefitKernel(S* __restrict__ nodes, con
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  #pragma unroll 1
   for (int node = warp; node < n_nodes; node += n_warps) {
     const int2 r = range[node];
     // which scalars of a triangle this lane's sum needs: S1[k] (lanes 0-2), c00 c11 c22 c01 c02 c12 (lanes 3-8)
@@ -535,6 +544,7 @@ __global__ void __launch_bounds__(256) bvhRefitKernel(S* __restrict__ nodes, con
     hostbuild::axesFromEigen<S>(vec, d, ax);
     const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
     S mn[3] = {big, big, big}, mx[3] = {-big, -big, -big};
+    #pragma unroll 1
     for (int i = lane; i < 3 * r.y; i += 32) {  // one triangle corner per lane and round
       const S* p = tris + size_t(12) * size_t(prim[r.x + i / 3]) + 4 * (i % 3);
 #pragma unroll
@@ -577,6 +587,7 @@ __global__ void __launch_bounds__(kBlock) bvhPairPenetrationKernel(const S* __re
                                                                    double dy, double dz, double tol, S* __restrict__ out) {
   const size_t total = n * size_t(max_keep);
   const V3<S> dir_world = mk<S>(S(dx), S(dy), S(dz));
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const size_t q = i / max_keep;
     const uint32_t k = uint32_t(i % max_keep);
@@ -878,6 +889,7 @@ __global__ void __launch_bounds__(128) bvhRefitBottomUpKernel(S* nodes, const S*
 // 9 S per triangle (upload layout) -> the 12 S device records
 template <typename S>
 __global__ void triRepackKernel(const S* __restrict__ in9, int n_tris, S* __restrict__ out12) {
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < size_t(n_tris) * 3; i += size_t(gridDim.x) * blockDim.x) {
     const S* p = in9 + 3 * i;
     S* o = out12 + 4 * i;
@@ -938,6 +950,7 @@ __global__ void __launch_bounds__(256) bvhBuildFitKernel(const BuildNode* __rest
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  #pragma unroll 1
   for (int w = warp; w < n_level; w += n_warps) {
     const BuildNode nd = level[w];
     const int2 r = make_int2(nd.first, nd.count);
@@ -965,6 +978,7 @@ __global__ void __launch_bounds__(256) bvhBuildFitKernel(const BuildNode* __rest
     hostbuild::axesFromEigen<S>(vec, d, ax);
     const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
     S mn[3] = {big, big, big}, mx[3] = {-big, -big, -big};
+    #pragma unroll 1
     for (int i = lane; i < 3 * r.y; i += 32) {
       const S* p = tris + size_t(12) * size_t(prim[r.x + i / 3]) + 4 * (i % 3);
 #pragma unroll
@@ -1009,6 +1023,7 @@ __global__ void __launch_bounds__(256) bvhBuildSplitKernel(const BuildNode* __re
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  #pragma unroll 1
   for (int w = warp; w < n_level; w += n_warps) {
     const BuildNode nd = level[w];
     if (nd.count <= 1) continue;  // (warp-uniform)
@@ -1020,6 +1035,7 @@ __global__ void __launch_bounds__(256) bvhBuildSplitKernel(const BuildNode* __re
     const S split_value = (c0 * sv[0] + c1v * sv[1] + c2 * sv[2]) / nd.count;
     // the swap pass, replayed in order
     int c1 = 0;
+    #pragma unroll 1
     for (int base = 0; base < nd.count; base += 32) {
       const int i = base + lane;
       bool left = false;
@@ -1063,6 +1079,7 @@ static int buildObbTreeOnDevice(Engine& e, const double* verts_d, int n_verts, c
   const size_t n_nodes = size_t(2) * n_tris - 1;
   out.tri.resize(size_t(9) * n_tris);
   std::vector<S> tris12(size_t(12) * n_tris, S(0));
+  #pragma unroll 1
   for (int t = 0; t < n_tris; t++)
     for (int v = 0; v < 3; v++)
       for (int k = 0; k < 3; k++) {
@@ -1071,10 +1088,12 @@ static int buildObbTreeOnDevice(Engine& e, const double* verts_d, int n_verts, c
         tris12[size_t(12) * t + 4 * v + k] = x;
       }
   std::vector<int> ident(static_cast<size_t>(n_tris));
+  #pragma unroll 1
   for (int i = 0; i < n_tris; i++) ident[static_cast<size_t>(i)] = i;
   struct Scratch {
     std::vector<void*> p;
     ~Scratch() {
+      #pragma unroll 1
       for (void* q : p) cudaFree(q);
     }
   } sc;
@@ -1124,6 +1143,7 @@ static int buildObbTreeOnDevice(Engine& e, const double* verts_d, int n_verts, c
   FCLB_CUDA(cudaMemcpy(nodes.data(), d_nodes, nodes.size() * sizeof(S), cudaMemcpyDeviceToHost));
   out.obb.resize(n_nodes * 15);
   out.first_child.resize(n_nodes);
+  #pragma unroll 1
   for (size_t i = 0; i < n_nodes; i++) {
     for (int k = 0; k < 15; k++) out.obb[15 * i + k] = nodes[16 * i + k];
     if (sizeof(S) == 4) {
@@ -1144,6 +1164,7 @@ static int ensureParents(BvhDev* d) {
   if (d->d_parent) return FCLB_OK;
   if (int(d->h_child.size()) != d->n_nodes) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_refit: the BVH has no host copy of its child links");
   std::vector<int> parent(size_t(d->n_nodes), 0), leaf(size_t(d->n_tris), 0);
+  #pragma unroll 1
   for (int i = 0; i < d->n_nodes; i++) {
     const int fc = d->h_child[size_t(i)];
     if (fc < 0) {
@@ -1190,6 +1211,7 @@ static int refitDev(Engine& e, BvhDev* d, const void* d_tri9, int bottomup) {
   std::vector<S> nodes(size_t(16) * d->n_nodes);
   FCLB_CUDA(cudaMemcpy(nodes.data(), d->nodes, nodes.size() * sizeof(S), cudaMemcpyDeviceToHost));
   S* ho = reinterpret_cast<S*>(d->h_obb.data());
+  #pragma unroll 1
   for (int i = 0; i < d->n_nodes; i++)
     for (int k = 0; k < 15; k++) ho[size_t(15) * i + k] = nodes[size_t(16) * i + k];
   FCLB_CUDA(cudaMemcpy(d->h_tri.data(), d_tri9, d->h_tri.size(), cudaMemcpyDeviceToHost));
@@ -1201,6 +1223,7 @@ static int uploadBvh(BvhDev* d, const void* obb, const int32_t* first_child, int
   const S* o = static_cast<const S*>(obb);
   const S* tv = static_cast<const S*>(tri);
   std::vector<S> nodes(size_t(16) * n_nodes), tris(size_t(12) * n_tris, S(0));
+  #pragma unroll 1
   for (int i = 0; i < n_nodes; i++) {
     for (int k = 0; k < 15; k++) nodes[size_t(16) * i + k] = o[size_t(15) * i + k];
     S bits;
@@ -1213,6 +1236,7 @@ static int uploadBvh(BvhDev* d, const void* obb, const int32_t* first_child, int
     }
     nodes[size_t(16) * i + 15] = bits;
   }
+  #pragma unroll 1
   for (int t = 0; t < n_tris; t++)
     for (int v = 0; v < 3; v++)
       for (int k = 0; k < 3; k++) tris[size_t(12) * t + 4 * v + k] = tv[size_t(9) * t + 3 * v + k];
@@ -1247,6 +1271,7 @@ static int bvh_upload_one(const void* obb, const int32_t* first_child, int n_nod
   if (!obb || !first_child || !tri_verts || !h || n_nodes <= 0 || n_tris <= 0)
     return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_upload: null or empty input");
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  #pragma unroll 1
   for (int i = 0; i < n_nodes; i++) {
     const int fc = first_child[i];
     // children follow their parent in the array (BVHModel::recursiveBuildTree numbers them that way,
@@ -1284,6 +1309,7 @@ int fclb_bvh_build(const double* verts, int n_verts, const int32_t* tris, int n_
   if (rc_init_) return rc_init_;
   if (!verts || !tris || !h || n_verts <= 0 || n_tris <= 0) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build: null or empty input");
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  #pragma unroll 1
   for (size_t i = 0; i < size_t(3) * n_tris; i++)
     if (tris[i] < 0 || tris[i] >= n_verts) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build: vertex index out of range");
   if (scalar_type == FCLB_F32) {
@@ -1306,6 +1332,7 @@ int fclb_bvh_build_device(const double* verts, int n_verts, const int32_t* tris,
   if (rc_init_) return rc_init_;
   if (!verts || !tris || !h || n_verts <= 0 || n_tris <= 0) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build_device: null or empty input");
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  #pragma unroll 1
   for (size_t i = 0; i < size_t(3) * n_tris; i++)
     if (tris[i] < 0 || tris[i] >= n_verts) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build_device: vertex index out of range");
   float ms = 0.f;
@@ -1341,6 +1368,7 @@ int fclb_bvh_build_host(const double* verts, int n_verts, const int32_t* tris, i
                         int32_t* first_child, void* tri_verts, int* n_nodes) {
   if (!verts || !tris || n_verts <= 0 || n_tris <= 0) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build_host: null or empty input");
   if (scalar_type != FCLB_F32 && scalar_type != FCLB_F64) return fail(FCLB_ERR_BAD_ARG, "bad scalar_type");
+  #pragma unroll 1
   for (size_t i = 0; i < size_t(3) * n_tris; i++)
     if (tris[i] < 0 || tris[i] >= n_verts) return fail(FCLB_ERR_BAD_ARG, "fclb_bvh_build_host: vertex index out of range");
   auto emit = [&](auto& t) {
@@ -1493,6 +1521,7 @@ static int bvh_collide_batch_host_one(fclb_handle bvh1, fclb_handle bvh2, const 
   const char* h_p1 = static_cast<const char*>(poses1);
   const char* h_p2 = static_cast<const char*>(poses2);
   FCLB_CUDA(cudaStreamSynchronize(e.copy_out));  // the staging arena may still be read by an earlier call's copy-out
+  #pragma unroll 1
   for (int c = 0; c < n_chunks; c++) {
     const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
     FCLB_CUDA(cudaMemcpyAsync(base + o_p1 + b0 * 12 * ss, h_p1 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
@@ -1500,6 +1529,7 @@ static int bvh_collide_batch_host_one(fclb_handle bvh1, fclb_handle bvh2, const 
     FCLB_CUDA(cudaEventRecord(e.ev_in[c], e.copy_in));
   }
   unsigned long long visits[2] = {0, 0};
+  #pragma unroll 1
   for (int c = 0; c < n_chunks; c++) {
     const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
     FCLB_CUDA(cudaStreamWaitEvent(e.compute, e.ev_in[c], 0));

@@ -36,6 +36,7 @@ template <typename S, typename PointFn>
 FCLB_DI NodeD<S> fitObbPoints(int n, PointFn pt) {
   S S1[3] = {0, 0, 0};
   S c00 = 0, c11 = 0, c22 = 0, c01 = 0, c02 = 0, c12 = 0;
+  #pragma unroll 1
   for (int i = 0; i < n; i++) {  // getCovariance, point-cloud branch (math/geometry-inl.h:757-768)
     const V3<S> p = pt(i);
     S1[0] += p.x;
@@ -70,6 +71,7 @@ FCLB_DI NodeD<S> fitObbPoints(int n, PointFn pt) {
   const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
   V3<S> mn = mk<S>(big, big, big), mx = mk<S>(-big, -big, -big);
   const V3<S> a0 = col(bv.axis, 0), a1 = col(bv.axis, 1), a2 = col(bv.axis, 2);
+  #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const V3<S> p = pt(i);
     const V3<S> proj = mk<S>(dot(a0, p), dot(a1, p), dot(a2, p));
@@ -94,6 +96,7 @@ FCLB_DI NodeD<S> fitObbPoints(int n, PointFn pt) {
 constexpr int kFitMaxPoints = 256;
 template <typename S, typename PointFn>
 FCLB_DI NodeD<S> fitObbPointsWarp(int n, PointFn pt, S* pts, int lane) {
+  #pragma unroll 1
   for (int i = lane; i < n; i += 32) {
     const V3<S> p = pt(i);
     pts[3 * i] = p.x;
@@ -107,8 +110,10 @@ FCLB_DI NodeD<S> fitObbPointsWarp(int n, PointFn pt, S* pts, int lane) {
     const int a = lane < 3 ? lane : (lane == 3 ? 0 : (lane == 4 ? 1 : (lane == 5 ? 2 : (lane == 8 ? 1 : 0))));
     const int b = lane == 3 ? 0 : (lane == 4 ? 1 : (lane == 5 ? 2 : (lane == 6 ? 1 : 2)));
     if (lane < 3) {
+      #pragma unroll 1
       for (int i = 0; i < n; i++) acc += pts[3 * i + a];
     } else {
+      #pragma unroll 1
       for (int i = 0; i < n; i++) acc += (pts[3 * i + a] * pts[3 * i + b]);
     }
   }
@@ -136,6 +141,7 @@ FCLB_DI NodeD<S> fitObbPointsWarp(int n, PointFn pt, S* pts, int lane) {
   const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
   V3<S> mn = mk<S>(big, big, big), mx = mk<S>(-big, -big, -big);
   const V3<S> a0 = col(bv.axis, 0), a1 = col(bv.axis, 1), a2 = col(bv.axis, 2);
+  #pragma unroll 1
   for (int i = lane; i < n; i += 32) {
     const V3<S> p = mk<S>(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
     const V3<S> proj = mk<S>(dot(a0, p), dot(a1, p), dot(a2, p));

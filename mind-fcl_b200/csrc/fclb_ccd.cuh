@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(kBlock) translationalCcdKernel(CcdArgs a) {
   const LocalAabbD<S>* __restrict__ local = static_cast<const LocalAabbD<S>*>(a.local);
   const S* __restrict__ disp = static_cast<const S*>(a.disp);
   const S zero_tol = S(a.zero_tol), tol = S(a.gjk_tol);
+  #pragma unroll 1
   for (size_t q = blockIdx.x * size_t(blockDim.x) + threadIdx.x; q < a.n; q += size_t(gridDim.x) * blockDim.x) {
     const fclb_pair pr = a.pairs[q];
     const Pose<S> tf1 = loadPose(static_cast<const S*>(a.poses1), q);

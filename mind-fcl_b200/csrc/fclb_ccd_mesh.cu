@@ -54,6 +54,7 @@ static int ensureDfsRank(BvhDev* m) {
 struct CcdMeshScratch {
   std::vector<void*> ptrs;
   ~CcdMeshScratch() {
+    #pragma unroll 1
     for (void* p : ptrs) cudaFree(p);
   }
   template <typename T>
@@ -307,6 +308,7 @@ int fclb_translational_ccd_mesh_batch_dev(fclb_handle bvh, fclb_handle shapes, c
     return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_mesh_batch: null array");
   // computeBV<OBB, Convex> fits its box with fit1 / fit2 / fit3 / fit6 for hulls of exactly 1, 2, 3 or 6 vertices
   // (math/bv/utility-inl.h:468-490); only the general covariance fit is on the device
+  #pragma unroll 1
   for (uint32_t i = 0; i < t->n; i++)
     if (t->host[i].type == FCLB_CONVEX && t->host[i].geom < e.convex.size()) {
       const int nv = e.convex[t->host[i].geom].n_verts;
@@ -335,6 +337,7 @@ static int translational_ccd_mesh_batch_host_one(fclb_handle bvh, fclb_handle sh
   {
     ShapeTable* t = findTable(e, shapes);
     if (!t) return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_mesh_batch: unknown shape table handle");
+    #pragma unroll 1
     for (size_t q = 0; q < n; q++)
       if (shape_ids[q] >= t->n) return fail(FCLB_ERR_BAD_ARG, "shape id out of range");
   }

@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(kBlock) ccdMeshLeafKernel(CcdMeshArgs a, uint3
   const S* __restrict__ disp = static_cast<const S*>(a.disp);
   const S* __restrict__ tris = static_cast<const S*>(a.tris);
   const S tol = S(a.gjk_tol);
+  #pragma unroll 1
   for (size_t c = blockIdx.x * size_t(blockDim.x) + threadIdx.x; c < n_cand; c += size_t(gridDim.x) * blockDim.x) {
     const size_t q = a.cand_q[c];
     const int tri = a.cand_tri[c];
@@ -531,6 +532,7 @@ template <typename S>
 __global__ void __launch_bounds__(kBlock) ccdMeshPairLeafKernel(CcdMeshPairArgs a, uint32_t n_cand) {
   const S* __restrict__ disp = static_cast<const S*>(a.disp);
   const S tol = S(a.gjk_tol);
+  #pragma unroll 1
   for (size_t c = blockIdx.x * size_t(blockDim.x) + threadIdx.x; c < n_cand; c += size_t(gridDim.x) * blockDim.x) {
     const size_t q = a.cand_q[c];
     const int2 tri = a.cand_tri[c];

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kCsWarps * 32) ccdSceneTraverseKernel(CcdScene
     int sp = 0;
     bool overflow = n_roots > kCsStackCap - 8 * 32;
     if (!overflow) {
+      #pragma unroll 1
       for (int base = 0; base < n_roots; base += 32) {
         const int i = base + lane;
         CsElem<S> e;
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(kBlock) ccdSceneLeafKernel(CcdSceneArgs a, uin
   const S* __restrict__ disp = static_cast<const S*>(a.disp);
   const LocalAabbD<S>* __restrict__ local = static_cast<const LocalAabbD<S>*>(a.local);
   const S zero_tol = S(a.zero_tol), tol = S(a.gjk_tol);
+  #pragma unroll 1
   for (size_t c = blockIdx.x * size_t(blockDim.x) + threadIdx.x; c < n_cand; c += size_t(gridDim.x) * blockDim.x) {
     const size_t q = a.cand_q[c];
     const uint32_t sid = a.shape_ids[q];
@@ -334,6 +336,7 @@ __global__ void ccdSceneFillKernel(T* p, size_t n, T v) {
 struct CcdSceneScratch {
   std::vector<void*> ptrs;
   ~CcdSceneScratch() {
+    #pragma unroll 1
     for (void* p : ptrs) cudaFree(p);
   }
   template <typename T>
@@ -536,6 +539,7 @@ __global__ void __launch_bounds__(kCsWarps * 32) ccdSceneMeshTraverseKernel(CcdS
     int sp = 0;
     bool overflow = n_roots > kCmsStackCap - 8 * 32;
     if (!overflow) {
+      #pragma unroll 1
       for (int base = 0; base < n_roots; base += 32) {
         const int i = base + lane;
         CmsElem<S> e;
@@ -711,6 +715,7 @@ __global__ void __launch_bounds__(kBlock) ccdSceneMeshLeafKernel(CcdSceneMeshArg
   const S* __restrict__ disp = static_cast<const S*>(a.disp);
   const S zero_tol = S(a.zero_tol), tol = S(a.gjk_tol);
   const S big = sizeof(S) == 4 ? S(3.402823466e+38f) : S(1.7976931348623157e+308);
+  #pragma unroll 1
   for (size_t c = blockIdx.x * size_t(blockDim.x) + threadIdx.x; c < n_cand; c += size_t(gridDim.x) * blockDim.x) {
     const size_t q = a.cand_q[c];
     const Pose<S> tf_g = loadPose(static_cast<const S*>(a.poses_scene), q);
@@ -1019,6 +1024,7 @@ __global__ void __launch_bounds__(kCsWarps * 32) ccdScenePairKernel(CcdScenePair
     int root_bits = 0;
     while ((1 << root_bits) < n_roots) root_bits++;
     bool overflow = false;
+    #pragma unroll 1
     for (int base = 0; base < n_roots && !overflow; base += 32) {
       int sp = 0;
       {
@@ -1147,6 +1153,7 @@ __global__ void __launch_bounds__(kCsWarps * 32) ccdScenePairKernel(CcdScenePair
           int k = 0;
           const int bits = on_a ? kBitsA : kBitsB, n_child = on_a ? kChildA : kChildB;
           const int shift = e.shift - bits;
+          #pragma unroll 1
           for (int c = 0; c < n_child; c++) {
             if (!(child_mask & (1u << c))) continue;
             CspElem<S> ch;
@@ -1341,6 +1348,7 @@ int fclb_translational_ccd_scene_batch_dev(int scene_kind, fclb_handle scene, fc
   if (n > 0xfffffffeull) return fail(FCLB_ERR_CAPACITY, "batch larger than 2^32-2 queries: split it");
   if (!shape_ids || !poses_shape || !poses_scene || !displacements || !out_counts || (max_keep && !out_code))
     return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_scene_batch: null array");
+  #pragma unroll 1
   for (uint32_t i = 0; i < t->n; i++)
     if (t->host[i].type == FCLB_CONVEX && t->host[i].geom < e.convex.size()) {
       const int nv = e.convex[t->host[i].geom].n_verts;
@@ -1370,6 +1378,7 @@ static int translational_ccd_scene_batch_host_one(int scene_kind, fclb_handle sc
   {
     ShapeTable* t = findTable(e, shapes);
     if (!t) return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_scene_batch: unknown shape table handle");
+    #pragma unroll 1
     for (size_t q = 0; q < n; q++)
       if (shape_ids[q] >= t->n) return fail(FCLB_ERR_BAD_ARG, "shape id out of range");
   }
@@ -1509,6 +1518,7 @@ int fclb_translational_ccd_scene_pair_batch_dev(int kind1, fclb_handle scene1, i
   if (rc) return rc;
   Engine& e = eng();
   std::lock_guard<std::recursive_mutex> lk(e.mu);
+  #pragma unroll 1
   for (int k : {kind1, kind2})
     if (k != FCLB_SCENE_HEIGHTMAP && k != FCLB_SCENE_OCTREE)
       return fail(FCLB_ERR_BAD_ARG, "fclb_translational_ccd_scene_pair_batch: kinds must be FCLB_SCENE_HEIGHTMAP or FCLB_SCENE_OCTREE");

@@ -57,6 +57,7 @@ FCLB_DI void writeContact(const CollideOut& o, size_t q, uint32_t k, const Conta
 template <typename S>
 FCLB_DI void clearContacts(const CollideOut& o, size_t q, uint32_t from) {
   if (!o.contacts) return;
+  #pragma unroll 1
   for (uint32_t k = from; k < o.max_keep; k++) {
     S* p = static_cast<S*>(o.contacts) + (q * o.max_keep + k) * 9;
 #pragma unroll
@@ -109,6 +110,7 @@ struct SmallPartialSort {
         parent--;
       }
     }
+    #pragma unroll 1
     for (int i = k; i < n; i++) {
       if (comp(idx[i], idx[0])) {  // __pop_heap(first, middle, i)
         const int value = idx[i];
@@ -150,6 +152,7 @@ FCLB_DI void emitContacts(const CollideOut& o, size_t q, bool hit, const Contact
   if (free_space < uint32_t(n)) {
     S depth[8];
     SmallPartialSort<S> ps;
+    #pragma unroll 1
     for (int i = 0; i < n; i++) {
       depth[i] = cps[i].depth;
       ps.idx[i] = i;
@@ -157,8 +160,10 @@ FCLB_DI void emitContacts(const CollideOut& o, size_t q, bool hit, const Contact
     ps.depth = depth;
     ps.run(n, int(free_space));
     adding = free_space;
+    #pragma unroll 1
     for (uint32_t k = 0; k < adding; k++) writeContact(o, q, k, cps[ps.idx[k]]);
   } else {
+    #pragma unroll 1
     for (uint32_t k = 0; k < adding; k++) writeContact(o, q, k, cps[k]);
   }
   if (o.counts) o.counts[q] = adding;
@@ -196,6 +201,7 @@ __global__ void __launch_bounds__(kBlock) collideClosedKernel(BatchView b, Colli
   const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
   const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
   const bool want = out.penetration != 0;
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < b.count; i += size_t(gridDim.x) * blockDim.x) {
     const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
     const fclb_pair pr = b.pairs[q];
@@ -268,6 +274,7 @@ __global__ void __launch_bounds__(kBlock) boxBoxCollideKernel(BatchView b, Colli
   };
   const size_t chunk = size_t(gridDim.x) * blockDim.x;
   const size_t rounds = (b.count + chunk - 1) / chunk;
+  #pragma unroll 1
   for (size_t r = 0; r < rounds; r++) {
     const size_t i = r * chunk + blockIdx.x * size_t(blockDim.x) + threadIdx.x;
     bool hit = false;
@@ -321,6 +328,7 @@ __global__ void __launch_bounds__(kBlock) convexBoolKernel(BatchView b, S tol, i
   const ConvexD<S>* __restrict__ cvx = static_cast<const ConvexD<S>*>(b.convex);
   const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
   const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < b.count; i += size_t(gridDim.x) * blockDim.x) {
     const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
     const fclb_pair pr = b.pairs[q];
@@ -590,6 +598,7 @@ __global__ void __launch_bounds__(kBlock) mprPenetrationKernel(BatchView b, S to
   const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
   const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
   const V3<S> dir_world = mk<S>(dx, dy, dz);
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < b.count; i += size_t(gridDim.x) * blockDim.x) {
     const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
     if (out.counts[q] == 0) continue;

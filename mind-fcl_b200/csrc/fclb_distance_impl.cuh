@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kBlock) distanceClosedKernel(BatchView b, S ep
   const ShapeD<S>* __restrict__ shapes = static_cast<const ShapeD<S>*>(b.shapes);
   const S* __restrict__ poses1 = static_cast<const S*>(b.poses1);
   const S* __restrict__ poses2 = static_cast<const S*>(b.poses2);
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < b.count; i += size_t(gridDim.x) * blockDim.x) {
     const size_t q = b.perm ? size_t(b.perm[b.begin + i]) : (b.begin + i);
     const fclb_pair pr = b.pairs[q];
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(kBlock, FCLB_GJK_MIN_BLOCKS) distanceGjkKernel
           to_dist = true;
         } else {
           bool dup = false;
+          #pragma unroll 1
           for (int j = 0; j < simplex.rank; j++)
             if (sqnorm(st.vtx(slotOf(simplex, j)) - v) < tol_sq) dup = true;
           if (dup || sqnorm(v) <= tol_sq) {
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(kBlock, FCLB_GJK_MIN_BLOCKS) distanceGjkKernel
         const S delta = dot(d, v - cur);
         bool stop = delta < tol;
         if (!stop) {
+          #pragma unroll 1
           for (int j = 0; j < simplex.rank; j++)
             if (sqnorm(st.vtx(slotOf(simplex, j)) - v) < tol_sq) stop = true;
         }
@@ -398,9 +401,11 @@ __global__ void __launch_bounds__(kCtaWarps ? kCtaWarps * 32 : kBlock)
   bool trip_open = false;  // (CTA pool) inside a trip: the unit list below is valid
   int u_nfull = 0, u_rem = 0, u_incl = 0, u_total_full = 0, u_rank = 0, u_count = 0;
   if (kCta) {
+    #pragma unroll 1
     for (int k = threadIdx.x; k < NS; k += kWarps * 32) fU[U_PHASE * NS + k] = 0;
     if (threadIdx.x == 0) s_more = 1;
   } else {
+    #pragma unroll 1
     for (int k = lane; k < NS; k += 32) fU[U_PHASE * NS + k] = 0;
     __syncwarp();
   }
@@ -730,6 +735,7 @@ __global__ void __launch_bounds__(kCtaWarps ? kCtaWarps * 32 : kBlock)
             to_dist = true;
           } else {
             bool dup = false;
+            #pragma unroll 1
             for (int j = 0; j < simplex.rank; j++)
               if (sqnorm(st.vtx(slotOf(simplex, j)) - v) < tol_sq) dup = true;
             if (dup || sqnorm(v) <= tol_sq) {
@@ -747,6 +753,7 @@ __global__ void __launch_bounds__(kCtaWarps ? kCtaWarps * 32 : kBlock)
           const S delta = dot(d, v - cur);
           bool stop = delta < tol;
           if (!stop) {
+            #pragma unroll 1
             for (int j = 0; j < simplex.rank; j++)
               if (sqnorm(st.vtx(slotOf(simplex, j)) - v) < tol_sq) stop = true;
           }

@@ -296,8 +296,11 @@ struct EpaWarp {
 
   // Polytope::Reset (epa_polytope.hpp:78-103)
   FCLB_DI void reset() {
+    #pragma unroll 1
     for (int i = lane; i < P.vcap; i += T) P.v_alive[i] = 0;
+    #pragma unroll 1
     for (int i = lane; i < P.ecap; i += T) P.e_alive[i] = 0;
+    #pragma unroll 1
     for (int i = lane; i < P.fcap; i += T) P.f_alive[i] = 0;
     v_hw = e_hw = f_hw = 0;
     v_n = e_n = f_n = 0;
@@ -308,6 +311,7 @@ struct EpaWarp {
   // a dead slot of a pool (uniform result), recycled ones first (see gatherFree); -1 if the pool is full
   FCLB_DI int allocSlot(const uint8_t* alive, int cap, int& hw, int n_alive) const {
     if (n_alive < hw) {
+      #pragma unroll 1
       for (int base = 0; base < hw; base += T) {
         const int i = base + lane;
         const unsigned m = ballot(i < hw && !alive[i]);
@@ -326,6 +330,7 @@ struct EpaWarp {
     int got = 0;
     const unsigned lt = (1u << lane) - 1u;
     if (n_alive < hw) {
+      #pragma unroll 1
       for (int base = 0; base < hw && got < need; base += T) {
         const int i = base + lane;
         const bool pred = i < hw && !alive[i];
@@ -337,6 +342,7 @@ struct EpaWarp {
       if (got > need) got = need;
     }
     const int fresh = need - got;
+    #pragma unroll 1
     for (int j = lane; j < fresh; j += T) out[got + j] = uint16_t(hw + j);
     hw += fresh;
     (void)cap;
@@ -401,6 +407,7 @@ struct EpaWarp {
       P.f_alive[s] = 1;
       P.f_vis[s] = 0;
       const int es[3] = {e1, e2, e3};
+      #pragma unroll 1
       for (int i = 0; i < 3 && ok; i++) {
         if (P.e_f0[es[i]] == kNil) {
           P.e_f0[es[i]] = uint16_t(s);
@@ -437,6 +444,7 @@ struct EpaWarp {
     // a pool too small for the sequence fails one of the reference's allocations => "Failed"
     if (P.vcap < NV || P.ecap < ne || P.fcap < nf) return false;
     auto nib = [](unsigned long long t, int k) { return int((t >> (4 * k)) & 0xfull); };
+    #pragma unroll 1
     for (int k = lane; k < NV; k += T) {
       V3<S> vv = v[0], dd = d[0];
 #pragma unroll
@@ -451,10 +459,12 @@ struct EpaWarp {
       P.v_seq[k] = uint16_t(k);
       P.v_alive[k] = 1;
     }
+    #pragma unroll 1
     for (int k = lane; k < ne; k += T) {
       P.e_v0[k] = uint16_t(nib(ev0, k));
       P.e_v1[k] = uint16_t(nib(ev1, k));
       int f0 = kNil, f1 = kNil;
+      #pragma unroll 1
       for (int f = nf - 1; f >= 0; f--)
         if (nib(fe0, f) == k || nib(fe1, f) == k || nib(fe2, f) == k) {
           f1 = f0;
@@ -466,6 +476,7 @@ struct EpaWarp {
       P.e_alive[k] = 1;
       P.e_vis[k] = 0;
     }
+    #pragma unroll 1
     for (int k = lane; k < nf; k += T) {
       const int e1 = nib(fe0, k), e2 = nib(fe1, k), e3 = nib(fe2, k);
       const int a = nib(ev0, e1), b = nib(ev1, e1);
@@ -484,6 +495,7 @@ struct EpaWarp {
     e_hw = e_n = e_sq = ne;
     f_hw = f_n = f_sq = nf;
     sync();
+    #pragma unroll 1
     for (int k = lane; k < ne + nf; k += T) {
       if (k < ne)
         fillEdge(k);
@@ -617,10 +629,12 @@ struct EpaWarp {
       v[i] = zero3<S>();
       d[i] = zero3<S>();
     }
+    #pragma unroll 1
     for (int i = 0; i < sx.rank; i++) {
       v[i] = st.vtx(slotOf(sx, i));
       d[i] = st.dir(slotOf(sx, i));
     }
+    #pragma unroll 1
     for (int i = 0; i < sx.rank; i++) {
       if (sqnorm(v[i]) <= thr_sq) {
         touchingPoint(d[i], p0, p1);
@@ -670,6 +684,7 @@ struct EpaWarp {
     S bd = S(INFINITY);
     int bcls = 3, bseq = -1, bidx = -1;
     if (!exclude_vertex) {
+      #pragma unroll 1
       for (int i = lane; i < v_hw; i += T) {
         if (!P.v_alive[i]) continue;
         const S d = P.vd[i];
@@ -678,6 +693,7 @@ struct EpaWarp {
         }
       }
     }
+    #pragma unroll 1
     for (int i = lane; i < e_hw; i += T) {
       if (!P.e_alive[i]) continue;
       if (!exclude_vertex && !P.e_in[i]) continue;
@@ -686,6 +702,7 @@ struct EpaWarp {
         bd = d; bcls = 1; bseq = P.e_seq[i]; bidx = i;
       }
     }
+    #pragma unroll 1
     for (int i = lane; i < f_hw; i += T) {
       if (!P.f_alive[i] || !P.f_in[i]) continue;
       const S d = P.f_d[i];
@@ -726,6 +743,7 @@ struct EpaWarp {
     }
     S max_pos = S(0), min_neg = S(0);
     if (par) {
+      #pragma unroll 1
       for (int i = lane; i < v_hw; i += T) {
         if (!P.v_alive[i]) continue;
         const S dv = dot(P.vloc(i), dir);
@@ -740,6 +758,7 @@ struct EpaWarp {
         if (on < min_neg) min_neg = on;
       }
     } else {
+      #pragma unroll 1
       for (int i = 0; i < v_hw; i++) {
         if (!P.v_alive[i]) continue;
         const S dv = dot(P.vloc(i), dir);
@@ -789,7 +808,9 @@ struct EpaWarp {
   FCLB_DI int expand(const V3<S>& nv, const V3<S>& nd, int start_face) {
     // initVisibilityCacheVariables + visibility predicate of EVERY face
     // (cached_vertex2new_v_edge and the edges' cached_visibility are written before they are read below)
+    #pragma unroll 1
     for (int i = lane; i < v_hw; i += T) P.v_rm[i] = 1;
+    #pragma unroll 1
     for (int i = lane; i < f_hw; i += T) {
       if (!P.f_alive[i]) continue;
       P.f_vis[i] = pointOutsideFace(i, nv, false) ? 3 : 2;  // 3 = outside (not reached yet), 2 = hidden
@@ -804,6 +825,7 @@ struct EpaWarp {
     bool broken = false;
     while (true) {
       bool changed = false;
+      #pragma unroll 1
       for (int i = lane; i < f_hw; i += T) {
         if (!P.f_alive[i] || P.f_vis[i] != 1) continue;
         const int es[3] = {P.f_e0[i], P.f_e1[i], P.f_e2[i]};
@@ -825,6 +847,7 @@ struct EpaWarp {
     }
     if (any(broken)) return 1;
     // edge classification + vertex keep flags (updateVertexRemoveFlag, :183-205)
+    #pragma unroll 1
     for (int i = lane; i < e_hw; i += T) {
       if (!P.e_alive[i]) continue;
       const int f0 = P.e_f0[i], f1 = P.e_f1[i];
@@ -840,6 +863,7 @@ struct EpaWarp {
     sync();
     // removeAccordingToVisibility (:244-281)
     int rm_f = 0, rm_e = 0, rm_v = 0;
+    #pragma unroll 1
     for (int i = lane; i < e_hw; i += T) {
       if (!P.e_alive[i]) continue;
       if (P.e_vis[i] == 2) {
@@ -854,12 +878,14 @@ struct EpaWarp {
       }
     }
     sync();
+    #pragma unroll 1
     for (int i = lane; i < f_hw; i += T) {
       if (P.f_alive[i] && P.f_vis[i] == 1) {
         P.f_alive[i] = 0;
         rm_f++;
       }
     }
+    #pragma unroll 1
     for (int i = lane; i < v_hw; i += T) {
       if (P.v_alive[i] && P.v_rm[i]) {
         P.v_alive[i] = 0;
@@ -893,6 +919,7 @@ struct EpaWarp {
     // MallocFailed (epa.hpp:221-226) whatever the order, so they are detected up front.
     const unsigned lt = (1u << lane) - 1u;
     int m = 0;
+    #pragma unroll 1
     for (int base = 0; base < e_hw; base += T) {
       const int i = base + lane;
       const bool pred = i < e_hw && P.e_alive[i] && P.e_vis[i] == 1;
@@ -901,10 +928,12 @@ struct EpaWarp {
       m += __popc(mask);
     }
     sync();
+    #pragma unroll 1
     for (int j = lane; j < m; j += T) {
       const int ej = P.e_tmp0[j];
       const int sj = P.e_seq[ej];
       int r = 0;
+      #pragma unroll 1
       for (int k = 0; k < m; k++) r += (int(P.e_seq[P.e_tmp0[k]]) > sj) ? 1 : 0;
       P.e_tmp1[r] = uint16_t(ej);
     }
@@ -912,6 +941,7 @@ struct EpaWarp {
     // first uses, in key order: e_tmp0[ordinal of the side edge] = vertex (the unsorted list is dead by now)
     int n_new = 0;
     bool wrong = false;
+    #pragma unroll 1
     for (int base = 0; base < 2 * m; base += T) {
       const int t = base + lane;
       bool first = false;
@@ -921,6 +951,7 @@ struct EpaWarp {
         vtx = (t & 1) ? P.e_v1[e] : P.e_v0[e];
         first = true;
         int occ = 0;
+        #pragma unroll 1
         for (int u = 0; u < 2 * m; u++) {
           const int eu = P.e_tmp1[u >> 1];
           const int vu = (u & 1) ? P.e_v1[eu] : P.e_v0[eu];
@@ -940,6 +971,7 @@ struct EpaWarp {
     sync();
     gatherFree(P.e_alive, P.ecap, e_hw, e_n, n_new, P.e_tmp2);
     sync();
+    #pragma unroll 1
     for (int o = lane; o < n_new; o += T) {
       const int sl = P.e_tmp2[o], vi = P.e_tmp0[o];
       P.e_v0[sl] = uint16_t(new_v);
@@ -957,6 +989,7 @@ struct EpaWarp {
     sync();
     gatherFree(P.f_alive, P.fcap, f_hw, f_n, m, P.e_tmp2);
     sync();
+    #pragma unroll 1
     for (int r = lane; r < m; r += T) {
       const int sl = P.e_tmp2[r], edge = P.e_tmp1[r];
       const int va = P.e_v0[edge], vb = P.e_v1[edge];
@@ -972,9 +1005,11 @@ struct EpaWarp {
       P.e_f1[edge] = uint16_t(sl);  // removeAccordingToVisibility left the hidden face in slot 0
       fillFace(sl);
     }
+    #pragma unroll 1
     for (int o = lane; o < n_new; o += T) {  // faces of the side edges, by rank
       const int vi = P.e_tmp0[o], sl = P.v_newedge[vi];
       int f0 = kNil, f1 = kNil;
+      #pragma unroll 1
       for (int r = m - 1; r >= 0; r--) {
         const int edge = P.e_tmp1[r];
         if (P.e_v0[edge] == vi || P.e_v1[edge] == vi) {

@@ -465,6 +465,7 @@ FCLB_DI bool gjkMinDistance(const MD& shape, SlotStore<S>& st, Simp& s, S tol, i
     if (n_support) *n_support += 2;
     const S delta = dot(next_dir, nv - cur);
     if (delta < tol) return extractSeparationPoint(shape, st, s, p0, p1);
+    #pragma unroll 1
     for (int j = 0; j < s.rank; j++) {
       if (sqnorm(st.vtx(slotOf(s, j)) - nv) < tol_sq) return extractSeparationPoint(shape, st, s, p0, p1);
     }
@@ -530,6 +531,7 @@ FCLB_DI int gjkEvaluate(const MD& shape, SlotStore<S>& st, Simp& s, V3<S> guess,
         break;
       }
       bool dup = false;
+      #pragma unroll 1
       for (int j = 0; j < s.rank; j++) {
         if (sqnorm(st.vtx(slotOf(s, j)) - v) < tol_sq) dup = true;
       }

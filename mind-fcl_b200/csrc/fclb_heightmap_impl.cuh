@@ -58,6 +58,7 @@ FCLB_DI void shapeAabb(const ShapeInst<S>& sh, const Pose<S>& tf, V3<S>& mn, V3<
     mn = mk<S>(big, big, big);
     mx = mk<S>(-big, -big, -big);
     const ConvexD<S>& c = *sh.cvx;
+    #pragma unroll 1
     for (int i = 0; i < c.n_verts; i++) {
       const V3<S> p = mulMV(R, loadVert(c.verts, i)) + T;
       mn = mk<S>(fmin_(mn.x, p.x), fmin_(mn.y, p.y), fmin_(mn.z, p.z));
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(kHmWarps * 32, FCLB_HM_MIN_BLOCKS) heightmapSh
       const int ty0 = y0 >> a.coarse_shift, ty1 = y1 >> a.coarse_shift;
       const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
       const int n_tiles = ntx * nty;
+      #pragma unroll 1
       for (int tb = 0; tb < n_tiles && !done; tb += 32) {
         // ---- tile stage: one coarse pixel per lane
         const int ti = tb + lane;
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(kHmWarps * 32, FCLB_HM_MIN_BLOCKS) heightmapSh
           const int bx0 = max(cx << a.coarse_shift, x0), bx1 = min((cx << a.coarse_shift) + tile - 1, x1);
           const int by0 = max(cy << a.coarse_shift, y0), by1 = min((cy << a.coarse_shift) + tile - 1, y1);
           const int w = bx1 - bx0 + 1, npx = w * (by1 - by0 + 1);
+          #pragma unroll 1
           for (int pb = 0; pb < npx && !done; pb += 32) {
             const int pi = pb + lane;
             bool cand = false;

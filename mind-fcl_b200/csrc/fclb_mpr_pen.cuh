@@ -299,6 +299,7 @@ FCLB_DI int mprIncrementalPenetration(const MD& shape, const V3<S>& init_directi
   p.v1 = p.v2 = p.v3 = p.d1 = p.d2 = p.d3 = zero3<S>();
   V3<S> prev_direction = init_direction;
   S prev_lb = S(-1), prev_ub = S(-1);
+  #pragma unroll 1
   for (int outer = 0; outer < max_iteration; outer++) {
     V3<S> new_d = zero3<S>();
     S lb = S(0), ub = S(0);

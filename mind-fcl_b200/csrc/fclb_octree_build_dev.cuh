@@ -22,6 +22,7 @@ namespace fclb {
 template <typename S>
 __global__ void octKeyKernel(const S* __restrict__ pts, size_t n, S inv, int half, int num_layers, unsigned long long* __restrict__ key,
                              uint32_t* __restrict__ idx) {
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     const S px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
     unsigned long long k = ~0ull;
@@ -33,6 +34,7 @@ __global__ void octKeyKernel(const S* __restrict__ pts, size_t n, S inv, int hal
         const int x = int(fx), y = int(fy), z = int(fz);
         if (x >= 0 && y >= 0 && z >= 0) {
           k = 0;
+          #pragma unroll 1
           for (int layer = 0; layer <= num_layers - 2; layer++) {  // computeChildIndex(voxel, parent layer)
             const int diff = num_layers - layer - 2;
             const unsigned c = ((x >> diff) & 1) | (((y >> diff) & 1) << 1) | (((z >> diff) & 1) << 2);
@@ -57,6 +59,7 @@ struct OctLevel {
 
 // head[j] = 1 when item j starts a new prefix (key >> shift differs from its predecessor's)
 __global__ void octHeadKernel(const unsigned long long* __restrict__ key, uint32_t n, int shift, uint32_t* __restrict__ head) {
+  #pragma unroll 1
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
     head[j] = (j == 0 || (key[j] >> shift) != (key[j - 1] >> shift)) ? 1u : 0u;
 }
@@ -64,6 +67,7 @@ __global__ void octHeadKernel(const unsigned long long* __restrict__ key, uint32
 __global__ void octFoldKernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ first, const uint32_t* __restrict__ scanned,
                               uint32_t n, int shift, unsigned long long* __restrict__ pkey, uint32_t* __restrict__ pfirst,
                               uint32_t* __restrict__ parent) {
+  #pragma unroll 1
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const uint32_t p = scanned[j] - 1;
     parent[j] = p;
@@ -72,11 +76,13 @@ __global__ void octFoldKernel(const unsigned long long* __restrict__ key, const 
   }
 }
 __global__ void octFillKernel(uint32_t* p, uint32_t n, uint32_t v) {
+  #pragma unroll 1
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) p[j] = v;
 }
 // creation-time key of the inner nodes of one level: (first point << 5) | depth, value = (level, position) packed
 __global__ void octRankKeyKernel(const uint32_t* __restrict__ first, uint32_t n, int depth, uint32_t offset, unsigned long long* __restrict__ key,
                                  uint32_t* __restrict__ val) {
+  #pragma unroll 1
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     key[offset + j] = (static_cast<unsigned long long>(first[j]) << 5) | unsigned(depth);
     val[offset + j] = offset + j;
@@ -84,11 +90,13 @@ __global__ void octRankKeyKernel(const uint32_t* __restrict__ first, uint32_t n,
 }
 // sorted_val[r] = flat position of the node with rank r  =>  index[flat position] = r + base
 __global__ void octAssignIndexKernel(const uint32_t* __restrict__ sorted_val, uint32_t n, uint32_t base, uint32_t* __restrict__ flat_index) {
+  #pragma unroll 1
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) flat_index[sorted_val[r]] = r + base;
 }
 // children[8 * index(parent) + c] = index(item), c = the item's last 3 key bits
 __global__ void octLinkKernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ parent, const uint32_t* __restrict__ index,
                               uint32_t n, const uint32_t* __restrict__ parent_index, uint32_t* __restrict__ children) {
+  #pragma unroll 1
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const uint32_t pi = parent_index ? parent_index[parent[j]] : 0u;
     children[size_t(8) * pi + unsigned(key[j] & 7ull)] = index[j];
@@ -97,16 +105,19 @@ __global__ void octLinkKernel(const unsigned long long* __restrict__ key, const 
 // voxels (full keys) -> the occupancy mask of their leaf node
 __global__ void octLeafBitsKernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ parent, uint32_t n,
                                   const uint32_t* __restrict__ leaf_index, uint32_t* __restrict__ bits32) {
+  #pragma unroll 1
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
     atomicOr(&bits32[leaf_index[parent[j]]], 1u << unsigned(key[j] & 7ull));
 }
 __global__ void octNarrowKernel(const uint32_t* __restrict__ in, uint32_t n, uint8_t* __restrict__ out) {
+  #pragma unroll 1
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[j] = uint8_t(in[j]);
 }
 // fully-occupied flag of the inner nodes of one depth (octree_construction-inl.h:111-172): all eight children present
 // and full (a leaf-layer child: mask 0xff)
 __global__ void octFullKernel(const uint32_t* __restrict__ index, uint32_t n, const uint32_t* __restrict__ children, int children_are_leaves,
                               const uint8_t* __restrict__ leaf_bits, uint8_t* __restrict__ full) {
+  #pragma unroll 1
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const uint32_t node = index ? index[j] : 0u;
     bool all = true;
@@ -119,6 +130,7 @@ __global__ void octFullKernel(const uint32_t* __restrict__ index, uint32_t n, co
 }
 __global__ void octUniqueKernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ scanned,
                                 uint32_t n, unsigned long long* __restrict__ ukey, uint32_t* __restrict__ ufirst) {
+  #pragma unroll 1
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
     if (j == 0 || key[j] != key[j - 1]) {  // stable sort: the first entry of a key carries its first point
       ukey[scanned[j] - 1] = key[j];

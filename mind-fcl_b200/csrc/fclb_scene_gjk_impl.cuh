@@ -74,6 +74,7 @@ FCLB_DI void copyPose(const S* src, S* dst) {
 
 template <typename S>
 __global__ void __launch_bounds__(256) leafBatchBuildKernel(LeafBuildArgs<S> a) {
+  #pragma unroll 1
   for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < a.m; j += size_t(gridDim.x) * blockDim.x) {
     const uint32_t c = a.order[j];
     const uint32_t ql = a.cq[c];
@@ -167,10 +168,12 @@ struct LeafScatterArgs {
 // (shape_pair_intersect-inl.h:88-115): all of them while they fit, else the `free_space` deepest.
 template <typename S>
 __global__ void __launch_bounds__(128) leafBatchScatterKernel(LeafScatterArgs<S> a) {
+  #pragma unroll 1
   for (size_t ql = blockIdx.x * size_t(blockDim.x) + threadIdx.x; ql < a.n_chunk; ql += size_t(gridDim.x) * blockDim.x) {
     const size_t q = a.q_base + ql;
     uint32_t total = 0;
     const uint32_t first = a.q_off[ql], cnt = a.q_count[ql];
+    #pragma unroll 1
     for (uint32_t i = 0; i < cnt && total < a.max_contacts; i++) {
       const uint32_t j = first + i;
       const uint32_t c = a.leaf_counts[j];
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(128) leafBatchScatterKernel(LeafScatterArgs<S>
       if (free_space < c) {
         S depth[8];
         SmallPartialSort<S> ps;
+        #pragma unroll 1
         for (uint32_t k = 0; k < c; k++) {
           depth[k] = a.leaf_contacts[(size_t(j) * 4 + k) * 9 + 8];
           ps.idx[k] = int(k);
@@ -188,9 +192,11 @@ __global__ void __launch_bounds__(128) leafBatchScatterKernel(LeafScatterArgs<S>
         ps.depth = depth;
         ps.run(int(c), int(free_space));
         adding = free_space;
+        #pragma unroll 1
         for (uint32_t k = 0; k < adding; k++) pick[k] = ps.idx[k];
       }
       const S sgn = (a.item_flags[j] & 1) ? S(-1) : S(1);
+      #pragma unroll 1
       for (uint32_t k = 0; k < adding; k++) {
         const uint32_t slot = total + k;
         if (slot >= a.max_keep) break;
@@ -206,6 +212,7 @@ __global__ void __launch_bounds__(128) leafBatchScatterKernel(LeafScatterArgs<S>
       total += adding;
     }
     a.counts[q] = total;
+    #pragma unroll 1
     for (uint32_t slot = total; slot < a.max_keep; slot++) {
       const size_t o = q * a.max_keep + slot;
       a.out_b1[o] = -1;
@@ -221,15 +228,18 @@ __global__ void __launch_bounds__(128) leafBatchScatterKernel(LeafScatterArgs<S>
 __global__ void gatherI64Kernel(const long long* __restrict__ src, const uint32_t* __restrict__ idx, size_t m,
                                 unsigned long long* __restrict__ dst) {
   // ids are >= -1: bias by one so that the unsigned radix order equals the signed order
+  #pragma unroll 1
   for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < m; j += size_t(gridDim.x) * blockDim.x)
     dst[j] = static_cast<unsigned long long>(src[idx[j]] + 1);
 }
 __global__ void gatherU32Kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, size_t m,
                                 unsigned long long* __restrict__ dst) {
+  #pragma unroll 1
   for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < m; j += size_t(gridDim.x) * blockDim.x)
     dst[j] = src[idx[j]];
 }
 __global__ void iotaKernel(uint32_t* dst, size_t m) {
+  #pragma unroll 1
   for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < m; j += size_t(gridDim.x) * blockDim.x) dst[j] = uint32_t(j);
 }
 

@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
       const int na = sideA.numRoots();
       const int nb = MESH ? (a.bvh2.n_nodes > 0 ? 1 : 0) : sideB.numRoots();
       if (lane == 0) {
+        #pragma unroll 1
         for (int i = 0; i < na; i++) {
           Elem el;
           if (!sideA.root(i, el.a)) continue;
@@ -328,6 +329,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) scenePairKernel(ScenePairArgs
               stack[sp++] = el;
             }
           } else {
+            #pragma unroll 1
             for (int j = 0; j < nb; j++)
               if (sideB.root(j, el.b)) stack[sp++] = el;
           }

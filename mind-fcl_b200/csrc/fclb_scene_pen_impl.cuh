@@ -16,6 +16,7 @@ template <typename S>
 __global__ void __launch_bounds__(kBlock) scenePenetrationKernel(ScenePenArgs a) {
   const size_t total = a.n * size_t(a.max_keep);
   const V3<S> dir_world = mk<S>(S(a.dir[0]), S(a.dir[1]), S(a.dir[2]));
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const size_t q = i / a.max_keep;
     const uint32_t k = uint32_t(i % a.max_keep);
@@ -74,6 +75,7 @@ template <typename S>
 __global__ void __launch_bounds__(kBlock) scenePairPenetrationKernel(ScenePairPenArgs a) {
   const size_t total = a.n * size_t(a.max_keep);
   const V3<S> dir_world = mk<S>(S(a.dir[0]), S(a.dir[1]), S(a.dir[2]));
+  #pragma unroll 1
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const size_t q = i / a.max_keep;
     const uint32_t k = uint32_t(i % a.max_keep);

@@ -109,6 +109,7 @@ FCLB_DI int convexExtremeNaive(const ConvexD<S>& c, const V3<S>& d) {
 #if FCLB_CVX_UNROLL
 #pragma unroll 4
 #endif
+  #pragma unroll 1
   for (int i = 1; i < c.n_verts; i++) {
     const S v = dot(d, loadVert(c.verts, i));
     if (v > best_v) {
@@ -154,6 +155,7 @@ FCLB_DI int convexExtremeWalk(const ConvexD<S>& c, const V3<S>& d) {
 #if FCLB_CVX_UNROLL
 #pragma unroll 4
 #endif
+    #pragma unroll 1
     for (int k = 0; k < span.y; k++) {
 #if FCLB_CVX_OLDWALK
       const int nb = c.nbr[span.x + k];
