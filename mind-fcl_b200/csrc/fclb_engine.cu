@@ -135,14 +135,26 @@ __global__ void classifyKernel(const ShapeD<S>* __restrict__ shapes, uint32_t n_
 }
 
 // hist[0..K) counts -> hist[K..2K) exclusive offsets (also used as cursors)
-__global__ void scanKernel(uint32_t* hist) {
+// The histogram also goes to `host_copy` (pinned, mapped host memory) with plain stores: a cudaMemcpyAsync of these 500
+// bytes would queue on the device-to-host copy engine BEHIND the previous pipeline stage's result copy (60 MB, 1.3 ms),
+// and the host cannot launch this stage's kernels before it has the counts (profiles/r02_e2e_taper.txt).
+__global__ void scanKernel(uint32_t* hist, volatile uint32_t* host_copy) {
+  __shared__ uint32_t offs[kNumKinds];
   if (threadIdx.x == 0) {
     uint32_t acc = 0;
     for (int i = 0; i < kNumKinds; i++) {
       hist[kNumKinds + i] = acc;
+      offs[i] = acc;
       acc += hist[i];
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNumKinds; i += blockDim.x) {
+    host_copy[i] = hist[i];
+    host_copy[kNumKinds + i] = offs[i];
+  }
+  if (threadIdx.x == 0) host_copy[2 * kNumKinds] = hist[2 * kNumKinds];
+  __threadfence_system();
 }
 
 // Stable within a block-chunk: each block owns a contiguous chunk of queries,
@@ -301,9 +313,9 @@ int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs, size_t
   const int grid = int(std::min<size_t>((n + block - 1) / block, size_t(e.sms) * 8));
   classifyKernel<S><<<grid, block, 0, e.compute>>>(static_cast<const ShapeD<S>*>(t->d_shapes[st]), t->n, d_pairs, n, e.d_kind,
                                                    e.d_hist);
-  scanKernel<<<1, 32, 0, e.compute>>>(e.d_hist);
+  scanKernel<<<1, 64, 0, e.compute>>>(e.d_hist, e.h_hist_dev);
   e.launches += 2;
-  FCLB_CUDA(cudaMemcpyAsync(e.h_hist, e.d_hist, (2 * kNumKinds + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, e.compute));
+  FCLB_CUDA(cudaGetLastError());
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   if (e.h_hist[2 * kNumKinds]) return fail(FCLB_ERR_BAD_ARG, "a pair names a shape index outside the shape table");
   *uniform_kind = -1;
@@ -564,10 +576,15 @@ static int initEngine(Engine& e, int device) {
     }
   }
   FCLB_CUDA(cudaMalloc(&e.d_hist, (2 * kNumKinds + 1) * sizeof(uint32_t)));
-  FCLB_CUDA(cudaHostAlloc(&e.h_hist, (2 * kNumKinds + 1) * sizeof(uint32_t), cudaHostAllocPortable));
+  FCLB_CUDA(cudaHostAlloc(&e.h_hist, (2 * kNumKinds + 1) * sizeof(uint32_t), cudaHostAllocPortable | cudaHostAllocMapped));
+  FCLB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&e.h_hist_dev), e.h_hist, 0));
   if (const char* hc = getenv("FCLB_HOST_CHUNK")) {  // queries per pipeline stage of the *_host entry points (tuning)
     const long long v = atoll(hc);
     if (v >= 1024) e.host_chunk = size_t(v);
+  }
+  if (const char* ht = getenv("FCLB_HOST_TAPER")) {  // shortest tapered stage of fclb_distance_batch_*host (0: equal stages)
+    const long long v = atoll(ht);
+    e.host_taper = v <= 0 ? 0 : std::max<size_t>(size_t(v), 4096);
   }
   e.ready = true;
   return FCLB_OK;
@@ -1003,25 +1020,47 @@ static int distance_batch_host_fmt(int pose_format, fclb_handle shapes, const fc
   // bucketed kernels, and the copy-out stream drains each chunk's results while later
   // chunks are still uploading / computing.  PCIe is full duplex, so with pinned
   // host buffers the call is bounded by the larger of the two copy directions.
-  const size_t chunk = e.host_chunk;
-  const int n_chunks = int((n + chunk - 1) / chunk);
+  // Stage sizes: e.host_chunk queries while plenty is left, then halving down to e.host_taper -- the call ends one
+  // stage's compute + copy-out after the last upload, so the last stages are kept short (profiles/r02_e2e_taper.txt).
+  std::vector<size_t> c_begin, c_size;
+  for (size_t b = 0; b < n;) {
+    const size_t rem = n - b;
+    size_t m = e.host_chunk;
+    if (e.host_taper && rem < 2 * e.host_chunk) {
+      m = std::max(e.host_taper, (rem / 2 + 4095) / 4096 * 4096);
+      if (rem < m + e.host_taper) m = rem;
+    }
+    m = std::min(m, rem);
+    c_begin.push_back(b);
+    c_size.push_back(m);
+    b += m;
+  }
+  const int n_chunks = int(c_size.size());
   rc = ensureChunkEvents(e, n_chunks);
   if (rc) return rc;
+  const bool trace = getenv("FCLB_TRACE_HOST") != nullptr;  // per-stage timeline on stderr (tuning aid)
+  std::vector<cudaEvent_t> tr;                              // start, then (in, done, out) per stage
+  if (trace) {
+    tr.resize(1 + 3 * size_t(n_chunks));
+    for (auto& ev : tr) FCLB_CUDA(cudaEventCreate(&ev));
+  }
   const char* h_pairs = reinterpret_cast<const char*>(pairs);
   const char* h_p1 = static_cast<const char*>(poses1);
   const char* h_p2 = static_cast<const char*>(poses2);
   // the staging arena may still be read by copy-out work of a previous call
   FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
+  if (trace) FCLB_CUDA(cudaEventRecord(tr[0], e.copy_in));
   for (int c = 0; c < n_chunks; c++) {
-    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    const size_t b0 = c_begin[c], m = c_size[c];
     FCLB_CUDA(cudaMemcpyAsync(base + o_pairs + b0 * sizeof(fclb_pair), h_pairs + b0 * sizeof(fclb_pair),
                               m * sizeof(fclb_pair), cudaMemcpyHostToDevice, e.copy_in));
     FCLB_CUDA(cudaMemcpyAsync(base + in1 + b0 * hp, h_p1 + b0 * hp, m * hp, cudaMemcpyHostToDevice, e.copy_in));
     FCLB_CUDA(cudaMemcpyAsync(base + in2 + b0 * hp, h_p2 + b0 * hp, m * hp, cudaMemcpyHostToDevice, e.copy_in));
     FCLB_CUDA(cudaEventRecord(e.ev_in[c], e.copy_in));
+    if (trace) FCLB_CUDA(cudaEventRecord(tr[1 + 3 * c], e.copy_in));
   }
   for (int c = 0; c < n_chunks; c++) {
-    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    const size_t b0 = c_begin[c], m = c_size[c];
     FCLB_CUDA(cudaStreamWaitEvent(e.compute, e.ev_in[c], 0));
     if (qt) {
       rc = launchExpandQt7(e, scalar_type, base + o_q1 + b0 * hp, m, base + o_p1 + b0 * 12 * ss);
@@ -1039,6 +1078,7 @@ static int distance_batch_host_fmt(int pose_format, fclb_handle shapes, const fc
       return rc;
     }
     FCLB_CUDA(cudaEventRecord(e.ev_done[c], e.compute));
+    if (trace) FCLB_CUDA(cudaEventRecord(tr[2 + 3 * c], e.compute));
     FCLB_CUDA(cudaStreamWaitEvent(e.copy_out, e.ev_done[c], 0));
     if (out_dist)
       FCLB_CUDA(cudaMemcpyAsync(static_cast<char*>(out_dist) + b0 * ss, base + o_dist + b0 * ss, m * ss,
@@ -1050,8 +1090,20 @@ static int distance_batch_host_fmt(int pose_format, fclb_handle shapes, const fc
       FCLB_CUDA(cudaMemcpyAsync(static_cast<char*>(out_p2) + b0 * 3 * ss, base + o_w2 + b0 * 3 * ss, m * 3 * ss,
                                 cudaMemcpyDeviceToHost, e.copy_out));
     if (out_ok) FCLB_CUDA(cudaMemcpyAsync(out_ok + b0, base + o_ok + b0, m, cudaMemcpyDeviceToHost, e.copy_out));
+    if (trace) FCLB_CUDA(cudaEventRecord(tr[3 + 3 * c], e.copy_out));
   }
   FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
+  if (trace) {
+    for (int c = 0; c < n_chunks; c++) {
+      float t_in = 0.f, t_done = 0.f, t_out = 0.f;
+      cudaEventElapsedTime(&t_in, tr[0], tr[1 + 3 * c]);
+      cudaEventElapsedTime(&t_done, tr[0], tr[2 + 3 * c]);
+      cudaEventElapsedTime(&t_out, tr[0], tr[3 + 3 * c]);
+      fprintf(stderr, "fclb trace: stage %d  %zu queries  uploaded %.3f ms  computed %.3f ms  copied out %.3f ms\n", c,
+              c_size[c], t_in, t_done, t_out);
+    }
+    for (auto& ev : tr) cudaEventDestroy(ev);
+  }
   return FCLB_OK;
 }
 static int distance_batch_host_any(int pose_format, fclb_handle shapes, const fclb_pair* pairs, const void* poses1, const void* poses2,

@@ -65,11 +65,13 @@ struct Engine {
   uint8_t* d_kind = nullptr;
   size_t scratch_cap = 0;
   uint32_t* d_hist = nullptr;  // kNumKinds counters + kNumKinds cursors
-  uint32_t* h_hist = nullptr;  // pinned
+  uint32_t* h_hist = nullptr;  // pinned, mapped: scanKernel stores the histogram here itself
+  uint32_t* h_hist_dev = nullptr;  // the device's pointer to h_hist
   // staging for host entry points
   void* d_stage = nullptr;
   size_t stage_cap = 0;
   size_t host_chunk = size_t(1) << 21;  // queries per pipeline stage of the *_host entry points
+  size_t host_taper = size_t(1) << 19;  // shortest stage of the tapered tail of fclb_distance_batch_*host (0: equal stages)
   std::vector<cudaEvent_t> ev_in, ev_done;
   std::atomic<uint64_t> launches{0};
   double last_ms = 0.0;       // kernels of the last call (bucketing excluded)
