@@ -521,7 +521,9 @@ __global__ void __launch_bounds__(kCtaWarps ? kCtaWarps * 32 : kBlock)
       } else {
         trip_open = false;
       }
-      if (u >= u_count) {
+      // FCLB_GJK_SHARE_UNITS=2: as 1, but only FULL units are drawn beyond the first kWarps of the list
+      const int u_limit = (FCLB_GJK_SHARE_UNITS == 2 && u_count > kWarps) ? (u_total_full > kWarps ? u_total_full : kWarps) : u_count;
+      if (u >= u_limit) {
         trip_open = false;
         continue;
       }
