@@ -165,3 +165,59 @@ def test_qt7_pose_encoding(fclb, ref_oracle, dtype):
     R = p1[:1000, :9].reshape(-1, 3, 3).astype(np.float64)
     assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < (1e-5 if dtype == np.float32 else 1e-13)
     fclb.release(table)
+
+
+_STAGED = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import fclb200, scenes
+fclb200.init(0)
+n = int(sys.argv[4])
+shapes, pairs, qt1, qt2 = scenes.config_c2_qt(n, np.float32)
+table = fclb200.shapes_upload(shapes)
+a = fclb200.distance_batch_qt_host(table, pairs, qt1, qt2, fclb200.F32)
+b = fclb200.distance_batch_host(table, pairs, scenes.expand_qt7(qt1), scenes.expand_qt7(qt2), fclb200.F32)
+np.savez(sys.argv[3], qd=a.dist, qp1=a.p1, qp2=a.p2, qok=a.ok, d=b.dist, p1=b.p1, p2=b.p2, ok=b.ok)
+"""
+
+
+def _stage_sizes(n, chunk, taper):
+    """The schedule of distance_batch_host_fmt (fclb_engine.cu)."""
+    out, b = [], 0
+    while b < n:
+        rem, m = n - b, chunk
+        if taper and rem < 2 * chunk:
+            m = max(taper, (rem // 2 + 4095) // 4096 * 4096)
+            if rem < m + taper:
+                m = rem
+        m = min(m, rem)
+        out.append(m)
+        b += m
+    return out
+
+
+@pytest.mark.parametrize("chunk,taper,n", [(32768, 4096, 200_001), (16384, 0, 50_001), (4096, 65536, 50_001)])
+def test_host_stage_schedule(fclb, tmp_path, chunk, taper, n):
+    """The pipeline stages of fclb_distance_batch_*host (FCLB_HOST_CHUNK queries, tail tapering to FCLB_HOST_TAPER; read at
+    engine start, hence the child process) cut the batch at different places -- ragged last stages included -- and
+    every query's result equals the single-stage call's bit for bit."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "staged.npz")
+    env = dict(os.environ, FCLB_HOST_CHUNK=str(chunk), FCLB_HOST_TAPER=str(taper), FCLB_TRACE_HOST="1")
+    p = subprocess.run([sys.executable, "-c", _STAGED, os.path.join(root, "mind-fcl_b200"), os.path.join(root, "oracle"), out,
+                        str(n)], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    stages = [int(l.split()[4]) for l in p.stderr.splitlines() if l.startswith("fclb trace: stage")]
+    want = _stage_sizes(n, chunk, max(taper, 4096) if taper else 0)
+    assert len(want) > 3 and stages == want + want, (stages, want)
+    shapes, pairs, qt1, qt2 = scenes.config_c2_qt(n, np.float32)
+    table = fclb.shapes_upload(shapes)
+    one = fclb.distance_batch_host(table, pairs, scenes.expand_qt7(qt1), scenes.expand_qt7(qt2), fclb.F32)  # 2M stages: one
+    z = np.load(out)
+    for k, ref in (("d", one.dist), ("p1", one.p1), ("p2", one.p2), ("ok", one.ok)):
+        assert np.array_equal(z[k], ref) and np.array_equal(z["q" + k], ref)
+    fclb.release(table)
