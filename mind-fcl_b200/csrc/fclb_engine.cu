@@ -316,6 +316,9 @@ int bucketBatch(Engine& e, const ShapeTable* t, const fclb_pair* d_pairs, size_t
   scanKernel<<<1, 64, 0, e.compute>>>(e.d_hist, e.h_hist_dev);
   e.launches += 2;
   FCLB_CUDA(cudaGetLastError());
+  static const bool hist_copy = getenv("FCLB_HIST_COPY") != nullptr;  // A/B: fetch it with a copy as well (the old path)
+  if (hist_copy)
+    FCLB_CUDA(cudaMemcpyAsync(e.h_hist, e.d_hist, (2 * kNumKinds + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, e.compute));
   FCLB_CUDA(cudaStreamSynchronize(e.compute));
   if (e.h_hist[2 * kNumKinds]) return fail(FCLB_ERR_BAD_ARG, "a pair names a shape index outside the shape table");
   *uniform_kind = -1;
