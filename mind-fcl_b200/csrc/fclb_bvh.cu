@@ -1514,8 +1514,11 @@ static int bvh_collide_batch_host_one(fclb_handle bvh1, fclb_handle bvh2, const 
   // Chunked three-stage pipeline, as fclb_distance_batch_host: every chunk's poses are queued on the copy-in stream up
   // front, the compute stream waits per chunk, the copy-out stream drains a chunk's results while later chunks upload
   // and traverse (queries are independent; per-query cost varies 100x, which the kernel's work counter absorbs).
+  // (the traversal is compute-bound: the first stage is short so that the kernels start early, then the stages double)
   const size_t chunk = e.host_chunk / 4 ? e.host_chunk / 4 : 1;
-  const int n_chunks = int((n + chunk - 1) / chunk);
+  std::vector<size_t> c_begin, c_size;
+  stageSizes(n, chunk, e.host_head, 0, c_begin, c_size);
+  const int n_chunks = int(c_size.size());
   rc = ensureChunkEvents(e, n_chunks);
   if (rc) return rc;
   const char* h_p1 = static_cast<const char*>(poses1);
@@ -1523,7 +1526,7 @@ static int bvh_collide_batch_host_one(fclb_handle bvh1, fclb_handle bvh2, const 
   FCLB_CUDA(cudaStreamSynchronize(e.copy_out));  // the staging arena may still be read by an earlier call's copy-out
   #pragma unroll 1
   for (int c = 0; c < n_chunks; c++) {
-    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    const size_t b0 = c_begin[c], m = c_size[c];
     FCLB_CUDA(cudaMemcpyAsync(base + o_p1 + b0 * 12 * ss, h_p1 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
     FCLB_CUDA(cudaMemcpyAsync(base + o_p2 + b0 * 12 * ss, h_p2 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
     FCLB_CUDA(cudaEventRecord(e.ev_in[c], e.copy_in));
@@ -1531,7 +1534,7 @@ static int bvh_collide_batch_host_one(fclb_handle bvh1, fclb_handle bvh2, const 
   unsigned long long visits[2] = {0, 0};
   #pragma unroll 1
   for (int c = 0; c < n_chunks; c++) {
-    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    const size_t b0 = c_begin[c], m = c_size[c];
     FCLB_CUDA(cudaStreamWaitEvent(e.compute, e.ev_in[c], 0));
     rc = fclb_bvh_collide_batch_dev(bvh1, bvh2, base + o_p1 + b0 * 12 * ss, base + o_p2 + b0 * 12 * ss, m, scalar_type, req,
                                     reinterpret_cast<uint32_t*>(base + o_cnt) + b0,

@@ -215,8 +215,11 @@ static int runCollideHost(fclb_handle shapes, const fclb_pair* pairs, const void
         if (t->host[i].type != FCLB_BOX && t->host[i].type != FCLB_SPHERE) copy_bound = false;
     }
   }
+  // (copy-OUT bound: the result copies can only start after the first stage's upload + kernels, so that stage is short)
   const size_t chunk = copy_bound ? std::max<size_t>(e.host_chunk / 8, 1024) : n;
-  const int n_chunks = int((n + chunk - 1) / chunk);
+  std::vector<size_t> c_begin, c_size;
+  stageSizes(n, chunk, copy_bound ? e.host_head : 0, 0, c_begin, c_size);
+  const int n_chunks = int(c_size.size());
   rc = ensureChunkEvents(e, n_chunks);
   if (rc) return rc;
   const char* hp_pairs = reinterpret_cast<const char*>(pairs);
@@ -225,7 +228,7 @@ static int runCollideHost(fclb_handle shapes, const fclb_pair* pairs, const void
   const size_t cb = size_t(max_keep) * 9 * ss;  // contact bytes per query
   FCLB_CUDA(cudaStreamSynchronize(e.copy_out));  // the arena may still be read by a previous call's copy-out
   for (int c = 0; c < n_chunks; c++) {
-    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    const size_t b0 = c_begin[c], m = c_size[c];
     FCLB_CUDA(cudaMemcpyAsync(base + o_pairs + b0 * sizeof(fclb_pair), hp_pairs + b0 * sizeof(fclb_pair), m * sizeof(fclb_pair),
                               cudaMemcpyHostToDevice, e.copy_in));
     FCLB_CUDA(cudaMemcpyAsync(base + o_p1 + b0 * 12 * ss, hp_1 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
@@ -233,7 +236,7 @@ static int runCollideHost(fclb_handle shapes, const fclb_pair* pairs, const void
     FCLB_CUDA(cudaEventRecord(e.ev_in[c], e.copy_in));
   }
   for (int c = 0; c < n_chunks; c++) {
-    const size_t b0 = size_t(c) * chunk, m = std::min(chunk, n - b0);
+    const size_t b0 = c_begin[c], m = c_size[c];
     FCLB_CUDA(cudaStreamWaitEvent(e.compute, e.ev_in[c], 0));
     if (h_contacts) FCLB_CUDA(cudaMemsetAsync(base + o_cont + b0 * cb, 0, m * cb, e.compute));  // slots beyond counts[q] come back as zeros
     CollideOut out{};

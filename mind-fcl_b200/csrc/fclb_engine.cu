@@ -410,6 +410,32 @@ ShapeTable* findTable(Engine& e, fclb_handle h) {
   return it == e.tables.end() ? nullptr : it->second;
 }
 
+// Stage sizes of a chunked host pipeline.  taper > 0 (copy-bound calls: the call ends one stage's compute + copy-out after
+// the last upload): `chunk` queries while two or more stages are left, then halving down to `taper`.  head > 0
+// (compute-bound calls: nothing runs before the first upload is in): the first stage has `head` queries and the stages
+// double up to `chunk`.
+void stageSizes(size_t n, size_t chunk, size_t head, size_t taper, std::vector<size_t>& begin, std::vector<size_t>& size) {
+  begin.clear();
+  size.clear();
+  if (chunk == 0) chunk = 1;
+  size_t ramp = head ? std::min(head, chunk) : chunk;
+  for (size_t b = 0; b < n;) {
+    const size_t rem = n - b;
+    size_t m = ramp;
+    if (ramp < chunk) {
+      ramp = std::min(chunk, 2 * ramp);
+      if (rem < m + m / 2) m = rem;  // no sliver at the end
+    } else if (taper && rem < 2 * chunk) {
+      m = std::max(taper, (rem / 2 + 4095) / 4096 * 4096);
+      if (rem < m + taper) m = rem;
+    }
+    m = std::min(m, rem);
+    begin.push_back(b);
+    size.push_back(m);
+    b += m;
+  }
+}
+
 int ensureChunkEvents(Engine& e, int n) {
   while (int(e.ev_in.size()) < n) {
     cudaEvent_t a = nullptr, b = nullptr;
@@ -584,6 +610,10 @@ static int initEngine(Engine& e, int device) {
   if (const char* hc = getenv("FCLB_HOST_CHUNK")) {  // queries per pipeline stage of the *_host entry points (tuning)
     const long long v = atoll(hc);
     if (v >= 1024) e.host_chunk = size_t(v);
+  }
+  if (const char* hh = getenv("FCLB_HOST_HEAD")) {  // first (short) stage of the compute-bound *_host pipelines (0: equal stages)
+    const long long v = atoll(hh);
+    e.host_head = v <= 0 ? 0 : std::max<size_t>(size_t(v), 1024);
   }
   if (const char* ht = getenv("FCLB_HOST_TAPER")) {  // shortest tapered stage of fclb_distance_batch_*host (0: equal stages)
     const long long v = atoll(ht);
@@ -1026,18 +1056,7 @@ static int distance_batch_host_fmt(int pose_format, fclb_handle shapes, const fc
   // Stage sizes: e.host_chunk queries while plenty is left, then halving down to e.host_taper -- the call ends one
   // stage's compute + copy-out after the last upload, so the last stages are kept short (profiles/r02_e2e_taper.txt).
   std::vector<size_t> c_begin, c_size;
-  for (size_t b = 0; b < n;) {
-    const size_t rem = n - b;
-    size_t m = e.host_chunk;
-    if (e.host_taper && rem < 2 * e.host_chunk) {
-      m = std::max(e.host_taper, (rem / 2 + 4095) / 4096 * 4096);
-      if (rem < m + e.host_taper) m = rem;
-    }
-    m = std::min(m, rem);
-    c_begin.push_back(b);
-    c_size.push_back(m);
-    b += m;
-  }
+  stageSizes(n, e.host_chunk, 0, e.host_taper, c_begin, c_size);
   const int n_chunks = int(c_size.size());
   rc = ensureChunkEvents(e, n_chunks);
   if (rc) return rc;

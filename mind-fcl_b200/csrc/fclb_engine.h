@@ -71,6 +71,7 @@ struct Engine {
   void* d_stage = nullptr;
   size_t stage_cap = 0;
   size_t host_chunk = size_t(1) << 21;  // queries per pipeline stage of the *_host entry points
+  size_t host_head = size_t(1) << 16;   // first stage of the compute-bound *_host pipelines; the stages double up to their chunk (0: equal stages)
   size_t host_taper = size_t(1) << 19;  // shortest stage of the tapered tail of fclb_distance_batch_*host (0: equal stages)
   std::vector<cudaEvent_t> ev_in, ev_done;
   std::atomic<uint64_t> launches{0};
@@ -135,6 +136,7 @@ int ensureInit();
 ShapeTable* findTable(Engine& e, fclb_handle h);
 int ensureStage(Engine& e, size_t bytes);
 int ensureChunkEvents(Engine& e, int n);
+void stageSizes(size_t n, size_t chunk, size_t head, size_t taper, std::vector<size_t>& begin, std::vector<size_t>& size);
 // cudaMemcpy from PAGEABLE host memory returns once the source is staged; the DMA into device memory may still be in
 // flight (CUDA runtime, "API synchronization behavior").  The engine's streams are non-blocking, so a kernel launched on
 // them right after an upload is not ordered behind that DMA: the first warps of the first query batch could read a

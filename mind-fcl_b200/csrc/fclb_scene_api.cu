@@ -1128,6 +1128,69 @@ static int heightmapBuildDev(Engine& e, const void* d_points, size_t n_points, d
 
 using namespace fclb;
 
+// The host pipeline shared by the three scene-vs-shape boolean entry points (mesh, heightmap, octree): every stage's
+// shape ids + poses are queued on the copy-in stream up front, the compute stream waits per stage and runs `dev` on it,
+// the copy-out stream drains a stage's counts / first ids while later stages upload and traverse.
+// ONE stage by default: measured on C4 (700k + 700k queries, profiles/r02_host_head_ab.txt) the traversal kernels lose more
+// on part-batches (a query costs 1 - 100x the median, and every launch ends with a tail of the expensive ones) than the
+// overlapped upload saves -- 41.6 ms in one stage, 42.4 ms in equal 512k stages, 42.9 ms with a short first stage.
+// FCLB_SCENE_HOST_STAGED=1 turns the stages on (first stage e.host_head, doubling up to a quarter of e.host_chunk).
+// first_bytes: size of one "first contact id" record (4, or 8 for octree node codes).
+template <typename DevCall>
+static int sceneShapeHostStaged(Engine& e, const uint32_t* shape_ids, const void* poses_scene, const void* poses_shape, size_t n,
+                                int scalar_type, uint32_t* out_counts, void* out_first, size_t first_bytes, DevCall dev) {
+  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
+  const size_t o_ids = 0;
+  const size_t o_p1 = alignUp(o_ids + n * 4, 256);
+  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
+  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
+  const size_t o_first = alignUp(o_cnt + n * 4, 256);
+  const size_t total = alignUp(o_first + n * first_bytes, 256);
+  int rc = ensureStage(e, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(e.d_stage);
+  std::vector<size_t> c_begin, c_size;
+  static const bool staged = getenv("FCLB_SCENE_HOST_STAGED") != nullptr;
+  stageSizes(n, staged ? (e.host_chunk / 4 ? e.host_chunk / 4 : 1) : n, staged ? e.host_head : 0, 0, c_begin, c_size);
+  const int n_chunks = int(c_size.size());
+  rc = ensureChunkEvents(e, n_chunks);
+  if (rc) return rc;
+  const char* h_p1 = static_cast<const char*>(poses_scene);
+  const char* h_p2 = static_cast<const char*>(poses_shape);
+  FCLB_CUDA(cudaStreamSynchronize(e.copy_out));  // the staging arena may still be read by an earlier call's copy-out
+  for (int c = 0; c < n_chunks; c++) {
+    const size_t b0 = c_begin[c], m = c_size[c];
+    FCLB_CUDA(cudaMemcpyAsync(base + o_ids + b0 * 4, shape_ids + b0, m * 4, cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaMemcpyAsync(base + o_p1 + b0 * 12 * ss, h_p1 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaMemcpyAsync(base + o_p2 + b0 * 12 * ss, h_p2 + b0 * 12 * ss, m * 12 * ss, cudaMemcpyHostToDevice, e.copy_in));
+    FCLB_CUDA(cudaEventRecord(e.ev_in[c], e.copy_in));
+  }
+  unsigned long long visits[2] = {0, 0};
+  for (int c = 0; c < n_chunks; c++) {
+    const size_t b0 = c_begin[c], m = c_size[c];
+    FCLB_CUDA(cudaStreamWaitEvent(e.compute, e.ev_in[c], 0));
+    rc = dev(reinterpret_cast<const uint32_t*>(base + o_ids) + b0, base + o_p1 + b0 * 12 * ss, base + o_p2 + b0 * 12 * ss, m,
+             reinterpret_cast<uint32_t*>(base + o_cnt) + b0, out_first ? base + o_first + b0 * first_bytes : nullptr);
+    if (rc) {  // drain the queued copies before the caller gets its buffers back
+      cudaStreamSynchronize(e.copy_in);
+      cudaStreamSynchronize(e.copy_out);
+      return rc;
+    }
+    visits[0] += g_stats[0];
+    visits[1] += g_stats[1];
+    FCLB_CUDA(cudaEventRecord(e.ev_done[c], e.compute));
+    FCLB_CUDA(cudaStreamWaitEvent(e.copy_out, e.ev_done[c], 0));
+    FCLB_CUDA(cudaMemcpyAsync(out_counts + b0, base + o_cnt + b0 * 4, m * 4, cudaMemcpyDeviceToHost, e.copy_out));
+    if (out_first)
+      FCLB_CUDA(cudaMemcpyAsync(static_cast<char*>(out_first) + b0 * first_bytes, base + o_first + b0 * first_bytes, m * first_bytes,
+                                cudaMemcpyDeviceToHost, e.copy_out));
+  }
+  g_stats[0] = visits[0];  // fclb_scene_last_visit_counts: the whole call
+  g_stats[1] = visits[1];
+  FCLB_CUDA(cudaStreamSynchronize(e.copy_out));
+  return FCLB_OK;
+}
+
 extern "C" {
 
 int fclb_bvh_shape_collide_batch_dev(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids, const void* poses_mesh,
@@ -1170,27 +1233,11 @@ static int bvh_shape_collide_batch_host_one(fclb_handle bvh, fclb_handle shapes,
     for (size_t q = 0; q < n; q++)
       if (shape_ids[q] >= t->n) return fail(FCLB_ERR_BAD_ARG, "shape id out of range");
   }
-  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
-  const size_t o_ids = 0;
-  const size_t o_p1 = alignUp(o_ids + n * 4, 256);
-  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
-  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
-  const size_t o_ft = alignUp(o_cnt + n * 4, 256);
-  const size_t total = alignUp(o_ft + n * 4, 256);
-  rc = ensureStage(e, total);
-  if (rc) return rc;
-  char* base = static_cast<char*>(e.d_stage);
-  FCLB_CUDA(cudaMemcpyAsync(base + o_ids, shape_ids, n * 4, cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses_mesh, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses_shape, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  rc = fclb_bvh_shape_collide_batch_dev(bvh, shapes, reinterpret_cast<const uint32_t*>(base + o_ids), base + o_p1,
-                                        base + o_p2, n, scalar_type, req, reinterpret_cast<uint32_t*>(base + o_cnt),
-                                        out_first_tri ? reinterpret_cast<int32_t*>(base + o_ft) : nullptr);
-  if (rc) return rc;
-  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
-  if (out_first_tri) FCLB_CUDA(cudaMemcpyAsync(out_first_tri, base + o_ft, n * 4, cudaMemcpyDeviceToHost, e.compute));
-  FCLB_CUDA(cudaStreamSynchronize(e.compute));
-  return FCLB_OK;
+  return sceneShapeHostStaged(e, shape_ids, poses_mesh, poses_shape, n, scalar_type, out_counts, out_first_tri, 4,
+                              [&](const uint32_t* d_ids, const void* d_p1, const void* d_p2, size_t m, uint32_t* d_cnt, void* d_first) {
+                                return fclb_bvh_shape_collide_batch_dev(bvh, shapes, d_ids, d_p1, d_p2, m, scalar_type, req, d_cnt,
+                                          static_cast<int32_t*>(d_first));
+                              });
 }
 int fclb_bvh_shape_collide_batch_host(fclb_handle bvh, fclb_handle shapes, const uint32_t* shape_ids, const void* poses_mesh,
                                       const void* poses_shape, size_t n, int scalar_type, const fclb_request* req,
@@ -1399,28 +1446,11 @@ static int heightmap_shape_collide_batch_host_one(fclb_handle hm, fclb_handle sh
     for (size_t q = 0; q < n; q++)
       if (shape_ids[q] >= t->n) return fail(FCLB_ERR_BAD_ARG, "shape id out of range");
   }
-  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
-  const size_t o_ids = 0;
-  const size_t o_p1 = alignUp(o_ids + n * 4, 256);
-  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
-  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
-  const size_t o_fp = alignUp(o_cnt + n * 4, 256);
-  const size_t total = alignUp(o_fp + n * 4, 256);
-  rc = ensureStage(e, total);
-  if (rc) return rc;
-  char* base = static_cast<char*>(e.d_stage);
-  FCLB_CUDA(cudaMemcpyAsync(base + o_ids, shape_ids, n * 4, cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses_hm, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses_shape, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  rc = fclb_heightmap_shape_collide_batch_dev(hm, shapes, reinterpret_cast<const uint32_t*>(base + o_ids), base + o_p1,
-                                              base + o_p2, n, scalar_type, req, reinterpret_cast<uint32_t*>(base + o_cnt),
-                                              out_first_pixel ? reinterpret_cast<int32_t*>(base + o_fp) : nullptr);
-  if (rc) return rc;
-  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
-  if (out_first_pixel)
-    FCLB_CUDA(cudaMemcpyAsync(out_first_pixel, base + o_fp, n * 4, cudaMemcpyDeviceToHost, e.compute));
-  FCLB_CUDA(cudaStreamSynchronize(e.compute));
-  return FCLB_OK;
+  return sceneShapeHostStaged(e, shape_ids, poses_hm, poses_shape, n, scalar_type, out_counts, out_first_pixel, 4,
+                              [&](const uint32_t* d_ids, const void* d_p1, const void* d_p2, size_t m, uint32_t* d_cnt, void* d_first) {
+                                return fclb_heightmap_shape_collide_batch_dev(hm, shapes, d_ids, d_p1, d_p2, m, scalar_type, req, d_cnt,
+                                          static_cast<int32_t*>(d_first));
+                              });
 }
 int fclb_heightmap_shape_collide_batch_host(fclb_handle hm, fclb_handle shapes, const uint32_t* shape_ids,
                                             const void* poses_hm, const void* poses_shape, size_t n, int scalar_type,
@@ -1722,27 +1752,11 @@ static int octree_shape_collide_batch_host_one(fclb_handle octree, fclb_handle s
     for (size_t q = 0; q < n; q++)
       if (shape_ids[q] >= t->n) return fail(FCLB_ERR_BAD_ARG, "shape id out of range");
   }
-  const size_t ss = scalar_type == FCLB_F32 ? 4 : 8;
-  const size_t o_ids = 0;
-  const size_t o_p1 = alignUp(o_ids + n * 4, 256);
-  const size_t o_p2 = alignUp(o_p1 + n * 12 * ss, 256);
-  const size_t o_cnt = alignUp(o_p2 + n * 12 * ss, 256);
-  const size_t o_fn = alignUp(o_cnt + n * 4, 256);
-  const size_t total = alignUp(o_fn + n * 8, 256);
-  rc = ensureStage(e, total);
-  if (rc) return rc;
-  char* base = static_cast<char*>(e.d_stage);
-  FCLB_CUDA(cudaMemcpyAsync(base + o_ids, shape_ids, n * 4, cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p1, poses_octree, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  FCLB_CUDA(cudaMemcpyAsync(base + o_p2, poses_shape, n * 12 * ss, cudaMemcpyHostToDevice, e.compute));
-  rc = fclb_octree_shape_collide_batch_dev(octree, shapes, reinterpret_cast<const uint32_t*>(base + o_ids), base + o_p1,
-                                           base + o_p2, n, scalar_type, req, reinterpret_cast<uint32_t*>(base + o_cnt),
-                                           out_first_node ? reinterpret_cast<int64_t*>(base + o_fn) : nullptr);
-  if (rc) return rc;
-  FCLB_CUDA(cudaMemcpyAsync(out_counts, base + o_cnt, n * 4, cudaMemcpyDeviceToHost, e.compute));
-  if (out_first_node) FCLB_CUDA(cudaMemcpyAsync(out_first_node, base + o_fn, n * 8, cudaMemcpyDeviceToHost, e.compute));
-  FCLB_CUDA(cudaStreamSynchronize(e.compute));
-  return FCLB_OK;
+  return sceneShapeHostStaged(e, shape_ids, poses_octree, poses_shape, n, scalar_type, out_counts, out_first_node, 8,
+                              [&](const uint32_t* d_ids, const void* d_p1, const void* d_p2, size_t m, uint32_t* d_cnt, void* d_first) {
+                                return fclb_octree_shape_collide_batch_dev(octree, shapes, d_ids, d_p1, d_p2, m, scalar_type, req, d_cnt,
+                                          static_cast<int64_t*>(d_first));
+                              });
 }
 int fclb_octree_shape_collide_batch_host(fclb_handle octree, fclb_handle shapes, const uint32_t* shape_ids,
                                          const void* poses_octree, const void* poses_shape, size_t n, int scalar_type,
