@@ -55,9 +55,12 @@ cudaError_t launchEpaTier(const BatchView& b, const CollideLaunchArgs& a, int po
 }
 
 // lanes per query of the first tier; FCLB_EPA_TILE overrides it for tuning (4, 8 or 16; 0 = by pair kind).
-// Measured on B200 (profiles/r01_epa_sweep.txt): 8 lanes are best for Convex pairs (70 ms against 72 / 80 ms with
-// 4 / 16 on c1b_convex), 16 lanes for box pairs (7.0 ms against 7.5 / 9.2 ms with 8 / 4 on c1b, whose run time is
-// set by the few queries that run to the iteration limit, i.e. by the latency of one iteration).
+// Measured on B200: 8 lanes are best for Convex pairs (round 1, profiles/r01_epa_sweep.txt: 70 ms against 72 / 80 ms
+// with 4 / 16 on c1b_convex; after the unroll-1 change 48.1 against 49.8 / 51.7 ms, f64 90 against 100 / 116 ms).
+// Box pairs: round 1 picked 16 lanes (7.0 ms against 7.5 / 9.2 ms with 8 / 4 on c1b, when the few queries that run to
+// the iteration limit set the run time); since tier 1 hands those to tier 2 after 32 iterations and the kernel is a
+// quarter smaller, FOUR lanes win -- 6.34 ms against 6.50 / 7.03 ms with 8 / 16, f64 6.94 against 6.96 / 8.79 ms
+// (profiles/r02_epa_knobs_after_unroll.txt): a box polytope rarely has more than a dozen faces.
 inline int tier1TileOverride() {
   static int v = [] {
     const char* e = getenv("FCLB_EPA_TILE");
@@ -69,7 +72,7 @@ inline int tier1TileOverride() {
 template <typename S, int T0, int T1>
 cudaError_t launchEpaTier1(const BatchView& b, const CollideLaunchArgs& a, int pool_faces, const EpaDefer& defer,
                            cudaStream_t st) {
-  const int tile = tier1TileOverride() ? tier1TileOverride() : ((T0 == ST_BOX && T1 == ST_BOX) ? 16 : 8);
+  const int tile = tier1TileOverride() ? tier1TileOverride() : ((T0 == ST_BOX && T1 == ST_BOX) ? 4 : 8);
   switch (tile) {
     case 4: return launchEpaTier<S, T0, T1, 4>(b, a, pool_faces, defer, st);
     case 16: return launchEpaTier<S, T0, T1, 16>(b, a, pool_faces, defer, st);
