@@ -84,7 +84,11 @@ cudaError_t launchEpaTier1(const BatchView& b, const CollideLaunchArgs& a, int p
 inline int epaEarlyTier2Ctas() {
   static int v = [] {
     const char* e = getenv("FCLB_EPA_EARLY_TIER2");
-    return e ? atoi(e) : 0;  // CTAs of 4 warps beside tier 1 (measured on C1b: 7.79 -> 7.70 ms with 37 CTAs, within noise on Convex pairs: off by default)
+    // CTAs of 4 warps beside tier 1.  Mid-round, with 16-lane box tiles, they were within noise (c1b 7.79 -> 7.70 ms) and off.
+    // Since box pairs run 4-lane tiles, tier 1 is 3.1 ms of c1b's step and tier 2 -- the latency chain of the four queries
+    // that run all 255 iterations -- 2.9 ms: started inside tier 1's run time, c1b 6.31 -> 5.99 ms (f64 6.94 -> 6.73 ms),
+    // Convex pairs unchanged (profiles/r02_epa_knobs_after_unroll.txt).  On by default with 74 CTAs.
+    return e ? atoi(e) : 74;
   }();
   return v;
 }
