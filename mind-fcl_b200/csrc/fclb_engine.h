@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include "fclb_stages.h"
+
 #include "fclb_internal.h"
 
 namespace fclb {
@@ -136,7 +138,6 @@ int ensureInit();
 ShapeTable* findTable(Engine& e, fclb_handle h);
 int ensureStage(Engine& e, size_t bytes);
 int ensureChunkEvents(Engine& e, int n);
-void stageSizes(size_t n, size_t chunk, size_t head, size_t taper, std::vector<size_t>& begin, std::vector<size_t>& size);
 // cudaMemcpy from PAGEABLE host memory returns once the source is staged; the DMA into device memory may still be in
 // flight (CUDA runtime, "API synchronization behavior").  The engine's streams are non-blocking, so a kernel launched on
 // them right after an upload is not ordered behind that DMA: the first warps of the first query batch could read a
